@@ -1,0 +1,124 @@
+"""ctypes binding of libmlb200.so (the C-ABI in include/mlb200.h).
+
+This is the host-side stub a maintainer of the reference would add where the reference
+today relies on XLA to compile its jnp expressions (INTEGRATION.md shows the jax.ffi
+equivalent).  PyTorch is used only for device memory and streams: every call passes raw
+device pointers (``Tensor.data_ptr()``) and ``torch.cuda.current_stream().cuda_stream``.
+
+There is NO CPU fallback: if the shared library is missing or a call fails, an exception is
+raised (``MLBError``).
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(_HERE, 'csrc')
+LIB_PATH = os.path.join(_HERE, 'lib', 'libmlb200.so')
+ABI_VERSION = 1
+
+c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
+                                            ctypes.c_float, ctypes.c_size_t)
+
+
+class MLBError(RuntimeError):
+    pass
+
+
+class Metric(ctypes.Structure):
+    """mlb_metric (ml/metrics.py:12-18)."""
+    _fields_ = [('mean', c_float), ('m2', c_float), ('min', c_float), ('max', c_float),
+                ('count', ctypes.c_int32)]
+
+
+P = c_void_p
+# name -> (restype, argtypes); mirrors include/mlb200.h one to one
+SIGNATURES = {
+    'mlb_abi_version': (c_int, []),
+    'mlb_gae_workspace': (c_size_t, [c_int, c_ll]),
+    'mlb_gae_f32': (c_int, [P, P, P, P, P, P, P, c_int, c_ll, c_float, c_float, P, P, P, c_size_t]),
+    'mlb_returns_f32': (c_int, [P, P, P, P, P, c_int, c_ll, c_float]),
+    'mlb_moments_workspace': (c_size_t, [c_ll]),
+    'mlb_moments_f32': (c_int, [P, P, c_ll, c_float, P, P, c_size_t]),
+    'mlb_zscore_apply_f32': (c_int, [P, P, P, c_ll, P]),
+    'mlb_zscore_f32': (c_int, [P, P, P, c_ll, P, P, c_size_t]),
+    'mlb_metric_f32': (c_int, [P, P, c_ll, P, P, c_size_t]),
+    'mlb_traj_moments_f32': (c_int, [P, P, c_int, c_ll, c_int, P]),
+    'mlb_mb_moments_f32': (c_int, [P, P, P, c_int, c_ll, c_ll, c_int, c_float, P]),
+    'mlb_ema_update_f32': (c_int, [P, P, c_int, P, P, c_float, c_float]),
+    'mlb_ema_scan_f32': (c_int, [P, P, P, c_int, c_float, c_float, P]),
+    'mlb_ema_normalize_f32': (c_int, [P, P, c_int, P, P, c_ll]),
+    'mlb_ema_invert_f32': (c_int, [P, P, c_int, P, P, c_ll]),
+    'mlb_threefry_split': (c_int, [P, P, P, c_int, c_int]),
+    'mlb_threefry_bits': (c_int, [P, P, P, c_ll, c_int]),
+    'mlb_ppo_permutations_workspace': (c_size_t, [c_int, c_ll]),
+    'mlb_ppo_permutations': (c_int, [P, P, P, c_int, c_ll, c_int, P, c_size_t]),
+    'mlb_mb_gather': (c_int, [P, P, P, P, c_int, c_int, c_ll, c_ll, c_ll]),
+    'mlb_mb_gather_rnn': (c_int, [P, P, P, P, c_int, c_ll, c_ll, c_ll]),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libmlb200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    cmd = ['make', '-C', CSRC_DIR, '-j', str(os.cpu_count() or 4)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise MLBError('libmlb200 build failed')
+    return LIB_PATH
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MLBError(f'{LIB_PATH} not found: run `python -c "import __graft_entry__ as g; '
+                       f'g.build()"` (there is no CPU fallback)')
+    h = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(h, name)
+        except AttributeError as e:
+            raise MLBError(f'libmlb200.so does not export {name}; rebuild') from e
+        fn.restype = res
+        fn.argtypes = args
+    v = h.mlb_abi_version()
+    if v != ABI_VERSION:
+        raise MLBError(f'libmlb200 ABI {v} != binding {ABI_VERSION}; rebuild')
+    _lib = h
+    return h
+
+
+def check(rc, name):
+    if rc != 0:
+        kind = 'cudaError' if rc > 0 else 'MLB_E'
+        raise MLBError(f'{name} failed: {kind} {rc}')
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise MLBError('libmlb200 takes device pointers only (tensor is on CPU)')
+    if not t.is_contiguous():
+        raise MLBError('libmlb200 requires contiguous buffers')
+    return c_void_p(t.data_ptr())
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point on the current torch stream and check its code."""
+    fn = getattr(lib(), name)
+    rc = fn(stream_ptr(), *args)
+    check(rc, name)

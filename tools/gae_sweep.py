@@ -1,0 +1,87 @@
+"""BASELINE config 5: standalone GAE(+returns) / z-score sweep on one B200.
+
+T in {16..256} x N in {4K..1M}; CUDA-event timing on the launching stream, L2 flushed
+(write of a 256 MiB buffer) between timed launches, median of `reps`.  Algorithmic bytes
+17*T*N+4*N (GAE+returns) and 8*T*N (z-score apply).  Peak = MEASURED_PEAKS.json hbm_gbs.
+Writes gpurun_out/gae_sweep.json and prints a table.
+"""
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import madrona_learn_b200 as mlb  # noqa: E402
+
+K = mlb.kernels
+
+
+def peak():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'], 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+def time_op(fn, flush, reps=7, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.add_(1)                      # evict L2 (256 MiB > 126 MB)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return statistics.median(ts)
+
+
+def main():
+    dev = 'cuda:0'
+    pk, src = peak()
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
+    rows = []
+    Ts = [16, 32, 64, 128, 256]
+    Ns = [4096, 16384, 65536, 262144, 1048576]
+    if len(sys.argv) > 1 and sys.argv[1] == 'quick':
+        Ts, Ns = [32, 256], [8192, 65536, 1048576]
+    for T in Ts:
+        for N in Ns:
+            r = torch.randn(T, N, device=dev)
+            v = torch.randn(T, N, device=dev)
+            d = (torch.rand(T, N, device=dev) < 0.02)
+            b = torch.randn(N, device=dev)
+            adv = torch.empty_like(r)
+            ret = torch.empty_like(r)
+            t = time_op(lambda: K.gae(r, v, d, b, 0.99, 0.95, advantages=adv, returns=ret), flush)
+            by = 17 * T * N + 4 * N
+            mbuf = torch.zeros(80, dtype=torch.uint8, device=dev)
+            ws = torch.empty(mlb._lib.lib().mlb_gae_workspace(T, N) + 16, dtype=torch.uint8, device=dev)
+            tm = time_op(lambda: K.gae(r, v, d, b, 0.99, 0.95, advantages=adv, returns=ret,
+                                       metrics=mbuf, ws=ws), flush)
+            m4 = K.moments(adv)
+            tz = time_op(lambda: K.zscore_apply(adv, m4, out=ret), flush)
+            tr = time_op(lambda: K.discounted_returns(r, d, b, 0.99, returns=ret), flush)
+            row = dict(T=T, N=N, bytes=by, gae_us=t * 1e6, gae_gbs=by / t / 1e9, gae_frac=by / t / 1e9 / pk,
+                       gae_metrics_us=tm * 1e6, gae_metrics_gbs=by / tm / 1e9,
+                       zscore_us=tz * 1e6, zscore_gbs=8 * T * N / tz / 1e9,
+                       returns_us=tr * 1e6, returns_gbs=(9 * T * N + 4 * N) / tr / 1e9,
+                       l2_resident=by < 126e6)
+            rows.append(row)
+            print(f"T={T:4d} N={N:8d} {by/1e6:9.1f} MB  gae {t*1e6:9.1f} us {row['gae_gbs']:7.0f} GB/s "
+                  f"({row['gae_frac']:.2f})  +metrics {row['gae_metrics_gbs']:7.0f}  zscore {row['zscore_gbs']:7.0f}  "
+                  f"returns {row['returns_gbs']:7.0f}", flush=True)
+            del r, v, d, b, adv, ret
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(dict(peak_gbs=pk, peak_src=src, rows=rows),
+              open(os.path.join(ROOT, 'gpurun_out', 'gae_sweep.json'), 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()
