@@ -52,9 +52,10 @@ typedef struct mlb_metric {
 /*   rewards, values : f32 [T, N]     dones : u8 [T, N] (0/1)     bootstrap : f32 [N]     */
 /*   advantages, returns : f32 [T, N] out (returns may be NULL)                           */
 /*   gamma_lambda = (float)(gamma * gae_lambda) formed in double (ml/algo_common.py:120)   */
-/*   vn_mu_sigma : NULL, or device f32[2] = {mu, sigma}: values/bootstrap are stored      */
-/*                 normalised and are inverted (v*sigma+mu) on load; the un-normalised     */
-/*                 values are what `returns` and the Values metric see.                    */
+/*   vn_mu_sigma : NULL, or the device EMA-normaliser state of dim 1 (layout below: mu at  */
+/*                 [0], sigma at [2]): values/bootstrap are stored normalised and are      */
+/*                 inverted (v*sigma+mu) on load; the un-normalised values are what        */
+/*                 `returns` and the Values metric see.                                    */
 /*   metrics : NULL, or device mlb_metric[4] out (rewards, values, returns, advantages);   */
 /*             needs ws of mlb_gae_workspace(T, N) bytes.                                  */
 /* Algorithmic bytes: 17*T*N + 4*N.                                                       */
@@ -116,6 +117,12 @@ int mlb_ema_normalize_f32(void* stream, const float* state, int dim, const float
 int mlb_ema_invert_f32(void* stream, const float* state, int dim, const float* x,
                        float* out, long long rows);
 
+/* Per-step episodic-return bookkeeping of the rollout loop (ml/rollouts.py:938-939,971-973): */
+/* er = r + gamma*er; trace[n] = er (may be NULL; feeds the 'Env Returns' metric);           */
+/* er = done ? 0 : er.                                                                       */
+int mlb_env_returns_f32(void* stream, const float* rewards, const uint8_t* dones,
+                        float* env_returns, float* trace, long long N, float gamma);
+
 /* ------------------------------------------------------------------------------------ */
 /* PRNG: JAX threefry2x32 (bit-exact).  keys are uint32[2].  partitionable selects the     */
 /* jax>=0.5 counter layout.                                                                */
@@ -141,6 +148,101 @@ int mlb_mb_gather(void* stream, const void* store, const int32_t* idx, void* out
 /* rnn_start_states [C, B, row] -> [M, row] (ml/rollouts.py:800-804 + :321-323) */
 int mlb_mb_gather_rnn(void* stream, const void* store, const int32_t* idx, void* out,
                       int C, long long B, long long M, long long row_bytes);
+
+/* ------------------------------------------------------------------------------------ */
+/* K6/K9 (fp32 path): Dense layers and their transposes.                                  */
+/* C[M,N] (+)= op(A)[M,K] * op(B)[K,N] (+ bias[N]); op(X) = X or X^T (row-major storage).   */
+/* Replaces nn.Dense's dot_general (ml/models.py:110-115,129-135,148-154) and its autodiff  */
+/* (ml/ppo.py:276-281).  splitk > 1 reduces K-slices with fp32 atomics into a pre-          */
+/* initialised C (requires accumulate != 0).                                               */
+/* ------------------------------------------------------------------------------------ */
+int mlb_gemm_f32(void* stream, const float* A, const float* B, float* C, const float* bias,
+                 int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+                 int accumulate, int splitk);
+
+/* LayerNorm(eps 1e-6, fast variance) + ReLU (ml/models.py:46-56,116-117).                  */
+/* fwd: y = relu(((z-mean)*rstd)*scale+bias); stats (may be NULL) f32 [rows][2]={mean,rstd}  */
+/* bwd: dz from dy; dscale/dbias are ACCUMULATED (fp32 atomics) into pre-zeroed buffers.     */
+int mlb_ln_relu_fwd_f32(void* stream, const float* z, const float* scale, const float* bias,
+                        float* y, float* stats, long long rows, int H);
+int mlb_ln_relu_bwd_f32(void* stream, const float* dy, const float* z, const float* stats,
+                        const float* scale, const float* bias, float* dz, float* dscale,
+                        float* dbias, long long rows, int H);
+
+/* ------------------------------------------------------------------------------------ */
+/* K7: rollout action sampling.  `head` f32 [rows, ld]: columns [0,sumA) logits of the      */
+/* concatenated discrete components, column sumA the critic value.                          */
+/* mlb_rollout_keys: (prng_key, step_key) = split(prng_key); policy_key =                   */
+/*   split(step_key, 1)[0]  (ml/rollouts.py:878-880, one policy chunk).                     */
+/* mlb_sample_discrete_f32: DiscreteActionDistributions.sample (ml/dists.py:26-44):         */
+/*   keys = split(policy_key, A); a_i = argmax(logits_i + gumbel(keys_i));                  */
+/*   log_prob = logit[a] - logsumexp.  deterministic != 0 -> best() (:46-52).               */
+/*   buckets_host: HOST int32[A].  values (may be NULL) <- head[:, sumA].                   */
+/* ------------------------------------------------------------------------------------ */
+#define MLB_MAX_ACTION_COMPONENTS 16
+int mlb_rollout_keys(void* stream, uint32_t* prng_key, uint32_t* policy_key, int partitionable);
+int mlb_sample_discrete_f32(void* stream, const float* head, int ld, const uint32_t* policy_key,
+                            const int32_t* buckets_host, int num_components, long long rows,
+                            int partitionable, int deterministic, int32_t* actions,
+                            float* log_probs, float* values);
+
+/* ------------------------------------------------------------------------------------ */
+/* K8: fused PPO loss + gradient w.r.t. the head outputs (ml/ppo.py:129-262 + autodiff).    */
+/* rows = T'*M in [T', M] order.  adv_mean_rstd: NULL or device f32[2] (per-minibatch       */
+/* z-score, ml/ppo.py:134-143).  vn_params: NULL or device f32[4] = {mu_old, sigma_old,     */
+/* mu_new, inv_sigma_new} (value normaliser before / after this minibatch's EMA update,     */
+/* ml/ppo.py:190-211).  obj_scale_host[i] = 1/(rows*A_g), ent_scale_host[i] =                */
+/* entropy_coef[g]/(rows*A_g) for component i of action group g (HOST arrays).              */
+/* d_head f32 [rows, ld] out.  stats out; ws of mlb_ppo_loss_workspace(rows) bytes.          */
+/* ------------------------------------------------------------------------------------ */
+#define MLB_PPO_CLIP_VALUE_LOSS  1
+#define MLB_PPO_HUBER_VALUE_LOSS 2
+typedef struct mlb_ppo_stats {
+    float loss, action_obj, value_loss, entropy;
+    mlb_metric metrics[5];   /* Loss, Action Obj, Value Loss, Value Errors (abs), Entropy
+                                (the order of PPO.add_metrics, ml/ppo.py:98-104) */
+} mlb_ppo_stats;
+size_t mlb_ppo_loss_workspace(long long rows);
+int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int32_t* actions,
+                     const float* old_log_probs, const float* advantages, const float* returns,
+                     const float* old_values, const float* mb_weights,
+                     const float* adv_mean_rstd, const float* vn_params,
+                     const int32_t* buckets_host, const float* obj_scale_host,
+                     const float* ent_scale_host, int num_components, long long rows,
+                     long long M, float clip_coef, float value_loss_coef, int flags,
+                     float* d_head, mlb_ppo_stats* stats, void* ws, size_t ws_bytes);
+
+/* ------------------------------------------------------------------------------------ */
+/* K10: optimiser over a flat fp32 arena (ml/ppo.py:84-90,283-338).                         */
+/* ------------------------------------------------------------------------------------ */
+typedef struct mlb_segment {
+    long long offset, length;   /* in floats, within the parameter arena */
+    int32_t kind;               /* 0 none, 1 kernel re-projection, 2 LayerNorm (scale|bias) */
+    float target;               /* kind 1: initial L2 norm; kind 2: num_features */
+} mlb_segment;
+int mlb_fill_zero(void* stream, void* p, size_t bytes);
+int mlb_copy_bytes(void* stream, const void* src, void* dst, size_t bytes);
+size_t mlb_sumsq_workspace(long long n);
+int mlb_sumsq_f32(void* stream, const float* x, long long n, double* out, void* ws, size_t ws_bytes);
+/* step: device int32 (number of Adam steps taken so far; incremented by mlb_renorm_segments) */
+/* grad_sumsq: device double (sum of squares of `grads`) or NULL; grads are used as         */
+/* grad_scale*grads (1/world_size after a sum-allreduce).                                   */
+int mlb_adam_step_f32(void* stream, float* params, const float* grads, float* m, float* v,
+                      long long n, const int32_t* step, const double* grad_sumsq, float lr,
+                      float b1, float b2, float eps, float max_grad_norm, float grad_scale);
+int mlb_renorm_segments(void* stream, float* params, const mlb_segment* segments_dev,
+                        int num_segments, int32_t* step);
+/* out[c] += sum_r x[r, c] for c < ncols (bias gradients of the heads) */
+int mlb_colsum_f32(void* stream, const float* x, long long rows, int ld, int ncols, float* out);
+
+/* ------------------------------------------------------------------------------------ */
+/* Synthetic vector environment (stand-in for sim_fns['step'], ml/rollouts.py:905-936).     */
+/* ------------------------------------------------------------------------------------ */
+int mlb_synth_env_init(void* stream, float* obs, long long N, int D, uint32_t seed,
+                       int32_t* tcount);
+int mlb_synth_env_step(void* stream, const float* obs_in, float* obs_out, const int32_t* actions,
+                       int A, float* rewards, uint8_t* dones, int32_t* tcount, long long N,
+                       int D, uint32_t seed, float p_done);
 
 #ifdef __cplusplus
 }

@@ -50,13 +50,45 @@ SIGNATURES = {
     'mlb_ema_scan_f32': (c_int, [P, P, P, c_int, c_float, c_float, P]),
     'mlb_ema_normalize_f32': (c_int, [P, P, c_int, P, P, c_ll]),
     'mlb_ema_invert_f32': (c_int, [P, P, c_int, P, P, c_ll]),
+    'mlb_env_returns_f32': (c_int, [P, P, P, P, P, c_ll, c_float]),
     'mlb_threefry_split': (c_int, [P, P, P, c_int, c_int]),
     'mlb_threefry_bits': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_ppo_permutations_workspace': (c_size_t, [c_int, c_ll]),
     'mlb_ppo_permutations': (c_int, [P, P, P, c_int, c_ll, c_int, P, c_size_t]),
     'mlb_mb_gather': (c_int, [P, P, P, P, c_int, c_int, c_ll, c_ll, c_ll]),
     'mlb_mb_gather_rnn': (c_int, [P, P, P, P, c_int, c_ll, c_ll, c_ll]),
+    'mlb_gemm_f32': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_int, c_int]),
+    'mlb_ln_relu_fwd_f32': (c_int, [P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_ln_relu_bwd_f32': (c_int, [P, P, P, P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
+    'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P]),
+    'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),
+    'mlb_ppo_loss_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, c_ll, c_ll,
+                                 c_float, c_float, c_int, P, P, P, c_size_t]),
+    'mlb_fill_zero': (c_int, [P, P, c_size_t]),
+    'mlb_copy_bytes': (c_int, [P, P, P, c_size_t]),
+    'mlb_sumsq_workspace': (c_size_t, [c_ll]),
+    'mlb_sumsq_f32': (c_int, [P, P, c_ll, P, P, c_size_t]),
+    'mlb_adam_step_f32': (c_int, [P, P, P, P, P, c_ll, P, P, c_float, c_float, c_float, c_float,
+                                  c_float, c_float]),
+    'mlb_renorm_segments': (c_int, [P, P, P, c_int, P]),
+    'mlb_colsum_f32': (c_int, [P, P, c_ll, c_int, c_int, P]),
+    'mlb_synth_env_init': (c_int, [P, P, c_ll, c_int, ctypes.c_uint32, P]),
+    'mlb_synth_env_step': (c_int, [P, P, P, P, c_int, P, P, P, c_ll, c_int, ctypes.c_uint32,
+                                   c_float]),
 }
+
+
+class Segment(ctypes.Structure):
+    """mlb_segment."""
+    _fields_ = [('offset', c_ll), ('length', c_ll), ('kind', ctypes.c_int32), ('target', c_float)]
+
+
+class PPOStats(ctypes.Structure):
+    """mlb_ppo_stats."""
+    _fields_ = [('loss', c_float), ('action_obj', c_float), ('value_loss', c_float),
+                ('entropy', c_float), ('metrics', Metric * 5)]
 
 _lib = None
 

@@ -71,7 +71,7 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
     const long long col = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     const bool active = col < N;
     const float mu = vn ? vn[0] : 0.f;
-    const float sigma = vn ? vn[1] : 1.f;
+    const float sigma = vn ? vn[2] : 1.f;   // EMA state layout (dim 1): mu, inv_sigma, sigma, ...
 
     ThreadStats st;
     if (STATS) st.init();

@@ -1,0 +1,191 @@
+// LayerNorm + ReLU forward / backward for the fp32 path.
+//
+// Replaces flax nn.LayerNorm (eps 1e-6, fast variance var = max(0, E[x^2] - E[x]^2), scale and
+// bias; ml/models.py:46-56) followed by nn.relu (ml/models.py:117), and their autodiff.
+// One warp per row (H <= 1024, H % 4 == 0): 128-bit loads, warp-shuffle row reductions, the
+// per-feature dscale/dbias sums stay in registers across the rows a warp visits and are
+// reduced through shared memory + one fp32 atomic per feature per block.
+#include "common.cuh"
+
+namespace {
+
+constexpr float LN_EPS = 1e-6f;
+constexpr int MAXV = 8;           // float4 vectors per lane: H <= 32*4*8 = 1024
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_relu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ scale,
+                   const float* __restrict__ bias, float* __restrict__ y,
+                   float* __restrict__ stats, long long rows, int H) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nvec = H / 4;
+    float4 s[NV], b[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nvec) { s[i] = __ldg(reinterpret_cast<const float4*>(scale) + c);
+                        b[i] = __ldg(reinterpret_cast<const float4*>(bias) + c); }
+    }
+    const float invH = 1.f / (float)H;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const float4* zr = reinterpret_cast<const float4*>(z + r * H);
+        float4 v[NV];
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                v[i] = __ldg(zr + c);
+                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+            }
+        }
+        sum = warp_sum(sum);
+        sq = warp_sum(sq);
+        const float mean = sum * invH;
+        const float var = fmaxf(0.f, sq * invH - mean * mean);
+        const float rstd = rsqrtf(var + LN_EPS);
+        float4* yr = reinterpret_cast<float4*>(y + r * H);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                float4 o;
+                o.x = fmaxf(0.f, (v[i].x - mean) * rstd * s[i].x + b[i].x);
+                o.y = fmaxf(0.f, (v[i].y - mean) * rstd * s[i].y + b[i].y);
+                o.z = fmaxf(0.f, (v[i].z - mean) * rstd * s[i].z + b[i].z);
+                o.w = fmaxf(0.f, (v[i].w - mean) * rstd * s[i].w + b[i].w);
+                yr[c] = o;
+            }
+        }
+        if (stats && lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                   const float* __restrict__ stats, const float* __restrict__ scale,
+                   const float* __restrict__ bias, float* __restrict__ dz,
+                   float* __restrict__ dscale, float* __restrict__ dbias, long long rows, int H) {
+    extern __shared__ float sm[];           // [2][H] per-block feature sums
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nvec = H / 4;
+    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    float4 s[NV], b[NV], gs[NV], gb[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        gs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nvec) { s[i] = __ldg(reinterpret_cast<const float4*>(scale) + c);
+                        b[i] = __ldg(reinterpret_cast<const float4*>(bias) + c); }
+    }
+    const float invH = 1.f / (float)H;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+        const float4* zr = reinterpret_cast<const float4*>(z + r * H);
+        const float4* dr = reinterpret_cast<const float4*>(dy + r * H);
+        float4 xh[NV], dx[NV];
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                const float4 zv = __ldg(zr + c), dv = __ldg(dr + c);
+                float4 x, g;
+                x.x = (zv.x - mean) * rstd; x.y = (zv.y - mean) * rstd;
+                x.z = (zv.z - mean) * rstd; x.w = (zv.w - mean) * rstd;
+                g.x = (x.x * s[i].x + b[i].x > 0.f) ? dv.x : 0.f;
+                g.y = (x.y * s[i].y + b[i].y > 0.f) ? dv.y : 0.f;
+                g.z = (x.z * s[i].z + b[i].z > 0.f) ? dv.z : 0.f;
+                g.w = (x.w * s[i].w + b[i].w > 0.f) ? dv.w : 0.f;
+                gs[i].x += g.x * x.x; gs[i].y += g.y * x.y; gs[i].z += g.z * x.z; gs[i].w += g.w * x.w;
+                gb[i].x += g.x; gb[i].y += g.y; gb[i].z += g.z; gb[i].w += g.w;
+                g.x *= s[i].x; g.y *= s[i].y; g.z *= s[i].z; g.w *= s[i].w;
+                m1 += (g.x + g.y) + (g.z + g.w);
+                m2 += (g.x * x.x + g.y * x.y) + (g.z * x.z + g.w * x.w);
+                xh[i] = x; dx[i] = g;
+            }
+        }
+        m1 = warp_sum(m1) * invH;
+        m2 = warp_sum(m2) * invH;
+        float4* or_ = reinterpret_cast<float4*>(dz + r * H);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nvec) {
+                float4 o;
+                o.x = rstd * (dx[i].x - m1 - xh[i].x * m2);
+                o.y = rstd * (dx[i].y - m1 - xh[i].y * m2);
+                o.z = rstd * (dx[i].z - m1 - xh[i].z * m2);
+                o.w = rstd * (dx[i].w - m1 - xh[i].w * m2);
+                or_[c] = o;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nvec) {
+            atomicAdd(&sm[4 * c + 0], gs[i].x); atomicAdd(&sm[4 * c + 1], gs[i].y);
+            atomicAdd(&sm[4 * c + 2], gs[i].z); atomicAdd(&sm[4 * c + 3], gs[i].w);
+            atomicAdd(&sm[H + 4 * c + 0], gb[i].x); atomicAdd(&sm[H + 4 * c + 1], gb[i].y);
+            atomicAdd(&sm[H + 4 * c + 2], gb[i].z); atomicAdd(&sm[H + 4 * c + 3], gb[i].w);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        atomicAdd(dscale + i, sm[i]);
+        atomicAdd(dbias + i, sm[H + i]);
+    }
+}
+
+unsigned row_grid(long long rows) {
+    long long b = (rows + 7) / 8;           // 8 warps per block
+    const long long cap = (long long)MLB_NUM_SMS * 8;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+MLB_API int mlb_ln_relu_fwd_f32(void* stream, const float* z, const float* scale,
+                                const float* bias, float* y, float* stats, long long rows, int H) {
+    MLB_REQUIRE(z && scale && bias && y && rows >= 0 && H > 0 && H % 4 == 0 && H <= 128 * MAXV);
+    if (rows == 0) return MLB_OK;
+    if (!(mlb_aligned16(z) && mlb_aligned16(y) && mlb_aligned16(scale) && mlb_aligned16(bias))) return MLB_EALIGN;
+    cudaStream_t s = mlb_stream(stream);
+    const unsigned g = row_grid(rows);
+    const int nv = (H / 4 + 31) / 32;
+    if (nv <= 1) ln_relu_fwd_kernel<1><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
+    else if (nv <= 2) ln_relu_fwd_kernel<2><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
+    else if (nv <= 4) ln_relu_fwd_kernel<4><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
+    else ln_relu_fwd_kernel<8><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+MLB_API int mlb_ln_relu_bwd_f32(void* stream, const float* dy, const float* z, const float* stats,
+                                const float* scale, const float* bias, float* dz, float* dscale,
+                                float* dbias, long long rows, int H) {
+    MLB_REQUIRE(dy && z && stats && scale && bias && dz && dscale && dbias);
+    MLB_REQUIRE(rows >= 0 && H > 0 && H % 4 == 0 && H <= 128 * MAXV);
+    if (rows == 0) return MLB_OK;
+    if (!(mlb_aligned16(z) && mlb_aligned16(dy) && mlb_aligned16(dz) && mlb_aligned16(scale) && mlb_aligned16(bias))) return MLB_EALIGN;
+    cudaStream_t s = mlb_stream(stream);
+    const unsigned g = row_grid(rows);
+    const size_t smem = 2 * (size_t)H * sizeof(float);
+    const int nv = (H / 4 + 31) / 32;
+    if (nv <= 1) ln_relu_bwd_kernel<1><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
+    else if (nv <= 2) ln_relu_bwd_kernel<2><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
+    else if (nv <= 4) ln_relu_bwd_kernel<4><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
+    else ln_relu_bwd_kernel<8><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}

@@ -1,0 +1,171 @@
+// Fused multi-tensor optimiser over a flat fp32 parameter arena.
+//
+// Replaces optax.chain(clip_by_global_norm, adam) + apply_updates (ml/ppo.py:84-90,283-286),
+// the kernel re-projection  w <- ||w0|| * w / ||w||  (ml/ppo.py:303-310, norms from
+// ml/train_state.py:413-423) and the LayerNorm renormalisation
+// (b, s) <- sqrt(F / (b.b + s.s)) * (b, s)  (ml/ppo.py:312-338).
+// Three launches per step regardless of the number of parameter tensors:
+//   mlb_sumsq_f32      global gradient norm (double accumulation, deterministic tree)
+//   mlb_adam_step_f32  clip scale + Adam moments + parameter update (28 B/param)
+//   mlb_renorm_segments one block per re-projected tensor / LayerNorm pair
+#include "common.cuh"
+
+namespace {
+
+struct SumPartial { double s; };
+
+constexpr int OPT_BLOCK = 256;
+
+unsigned opt_grid(long long n) {
+    long long b = (n + OPT_BLOCK * 8 - 1) / (OPT_BLOCK * 8);
+    const long long cap = (long long)MLB_NUM_SMS * 4;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+__global__ void __launch_bounds__(OPT_BLOCK)
+sumsq_partial_kernel(const float* __restrict__ x, long long n, double* __restrict__ part) {
+    double s = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = x[i];
+        s += (double)v * (double)v;
+    }
+    __shared__ double smd[32];
+    s = block_sum_d(s, smd);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(OPT_BLOCK)
+sumsq_final_kernel(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nparts; b += blockDim.x) s += part[b];
+    __shared__ double smd[32];
+    s = block_sum_d(s, smd);
+    if (threadIdx.x == 0) *out = s;
+}
+
+// optax.adam: m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; t += 1
+//             u = -lr * (m / (1-b1^t)) / (sqrt(v / (1-b2^t)) + eps) ; p += u
+__global__ void __launch_bounds__(OPT_BLOCK)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, long long n, const int* __restrict__ step,
+            const double* __restrict__ grad_sumsq, float lr, float b1, float b2, float eps,
+            float max_grad_norm, float grad_scale) {
+    const int t = *step + 1;
+    float scale = grad_scale;
+    if (grad_sumsq && max_grad_norm > 0.f) {
+        // the reduced gradient is grad_scale * g; its norm is grad_scale * sqrt(sumsq)
+        const float gn = (float)(sqrt(*grad_sumsq) * (double)fabsf(grad_scale));
+        if (!(gn < max_grad_norm)) scale *= max_grad_norm / gn;   // optax: (x / g_norm) * c
+    }
+    const float bc1 = 1.f - powf(b1, (float)t);
+    const float bc2 = 1.f - powf(b2, (float)t);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i] * scale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float u = -lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+        p[i] += u;
+    }
+}
+
+// One block per segment: kind 1 -> w *= target / ||w|| ; kind 2 -> (s,b) *= sqrt(target / (s.s+b.b))
+__global__ void __launch_bounds__(1024)
+renorm_kernel(float* __restrict__ p, const mlb_segment* __restrict__ segs, int* __restrict__ step) {
+    const mlb_segment sg = segs[blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && step) *step += 1;
+    if (sg.kind == 0) return;
+    float* w = p + sg.offset;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < sg.length; i += blockDim.x) { const float v = w[i]; s += (double)v * v; }
+    __shared__ double smd[32];
+    __shared__ float fac;
+    s = block_sum_d(s, smd);
+    if (threadIdx.x == 0)
+        fac = sg.kind == 1 ? (float)((double)sg.target / sqrt(s)) : (float)sqrt((double)sg.target / s);
+    __syncthreads();
+    const float f = fac;
+    for (long long i = threadIdx.x; i < sg.length; i += blockDim.x) w[i] *= f;
+}
+
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long long rows, int ld, int ncols, float* __restrict__ out) {
+    // blockDim = (32 cols, 8 row-lanes); each block strides over rows
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    float s = 0.f;
+    if (c < ncols)
+        for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y)
+            s += x[r * ld + c];
+    __shared__ float sm[8][33];
+    sm[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < ncols) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+        atomicAdd(out + c, t);
+    }
+}
+
+}  // namespace
+
+MLB_API int mlb_fill_zero(void* stream, void* p, size_t bytes) {
+    MLB_REQUIRE(p || bytes == 0);
+    if (bytes == 0) return MLB_OK;
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, mlb_stream(stream));
+    return e == cudaSuccess ? MLB_OK : (int)e;
+}
+
+MLB_API int mlb_copy_bytes(void* stream, const void* src, void* dst, size_t bytes) {
+    MLB_REQUIRE((src && dst) || bytes == 0);
+    if (bytes == 0) return MLB_OK;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, mlb_stream(stream));
+    return e == cudaSuccess ? MLB_OK : (int)e;
+}
+
+MLB_API size_t mlb_sumsq_workspace(long long n) { return (size_t)opt_grid(n) * sizeof(double); }
+
+MLB_API int mlb_sumsq_f32(void* stream, const float* x, long long n, double* out, void* ws,
+                          size_t ws_bytes) {
+    MLB_REQUIRE(x && out && n > 0);
+    const unsigned g = opt_grid(n);
+    if (!ws || ws_bytes < g * sizeof(double)) return MLB_EWS;
+    cudaStream_t s = mlb_stream(stream);
+    sumsq_partial_kernel<<<g, OPT_BLOCK, 0, s>>>(x, n, reinterpret_cast<double*>(ws));
+    MLB_CHECK_LAUNCH();
+    sumsq_final_kernel<<<1, OPT_BLOCK, 0, s>>>(reinterpret_cast<double*>(ws), (int)g, out);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+MLB_API int mlb_adam_step_f32(void* stream, float* params, const float* grads, float* m, float* v,
+                              long long n, const int32_t* step, const double* grad_sumsq,
+                              float lr, float b1, float b2, float eps, float max_grad_norm,
+                              float grad_scale) {
+    MLB_REQUIRE(params && grads && m && v && step && n > 0);
+    adam_kernel<<<opt_grid(n), OPT_BLOCK, 0, mlb_stream(stream)>>>(params, grads, m, v, n, step,
+        grad_sumsq, lr, b1, b2, eps, max_grad_norm, grad_scale);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+MLB_API int mlb_renorm_segments(void* stream, float* params, const mlb_segment* segments_dev,
+                                int num_segments, int32_t* step) {
+    MLB_REQUIRE(params && segments_dev && num_segments > 0);
+    renorm_kernel<<<num_segments, 1024, 0, mlb_stream(stream)>>>(params, segments_dev, step);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+MLB_API int mlb_colsum_f32(void* stream, const float* x, long long rows, int ld, int ncols,
+                           float* out) {
+    MLB_REQUIRE(x && out && rows >= 0 && ncols > 0 && ld >= ncols);
+    if (rows == 0) return MLB_OK;
+    long long g = (rows + 63) / 64;
+    if (g > MLB_NUM_SMS * 4) g = MLB_NUM_SMS * 4;
+    colsum_kernel<<<dim3((unsigned)g, (unsigned)((ncols + 31) / 32)), dim3(32, 8), 0, mlb_stream(stream)>>>(x, rows, ld, ncols, out);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}

@@ -121,7 +121,7 @@ __global__ void perm_apply_kernel(const unsigned long long* __restrict__ comp,
     const int e = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= J) return;
-    const uint32_t pos = (uint32_t)comp[(long long)e * Jpad + i];
+    const uint32_t pos = comp ? (uint32_t)comp[(long long)e * Jpad + i] : (uint32_t)i;
     out[(long long)e * J + i] = in ? in[(long long)e * J + pos] : (int32_t)pos;
 }
 

@@ -1,0 +1,360 @@
+"""PolicyProgram: lowers an ActorCritic descriptor onto libmlb200 kernels.
+
+This is the B200-side replacement for "flax module + XLA": parameters live in ONE flat fp32
+arena (with gradient / Adam-moment arenas of the same layout) so the optimiser, the gradient
+all-reduce and the norm re-projection are single launches; activations live in preallocated
+workspaces so the whole update can be captured in a CUDA graph.
+
+Supported family: BackboneShared(prefix=None|identity,
+encoder=BackboneEncoder(net=MLP)) + DenseLayerDiscreteActor + DenseLayerCritic, fp32.
+Everything else raises NotImplementedError loudly (no fallback).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import c_float, c_int, c_ll, c_size_t, call, ptr
+from .actor_critic import ActorCritic, BackboneEncoder, BackboneShared, RecurrentBackboneEncoder
+from .cfg import DiscreteActionsConfig
+from .models import MLP, DenseLayerCritic, DenseLayerDiscreteActor
+
+F32 = torch.float32
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def gemm(A, B, C, bias, M, N, K, lda, ldb, ldc, ta=0, tb=0, accumulate=0, splitk=1):
+    call('mlb_gemm_f32', ptr(A), ptr(B), ptr(C), ptr(bias), c_int(M), c_int(N), c_int(K),
+         c_int(lda), c_int(ldb), c_int(ldc), c_int(ta), c_int(tb), c_int(accumulate),
+         c_int(splitk))
+
+
+def _splitk_for(M, N, K):
+    bm, bn = (128, 32) if N <= 32 else ((64, 64) if (N <= 64 or M <= 64) else (128, 128))
+    tiles = math.ceil(M / bm) * math.ceil(N / bn)
+    want = max(1, math.ceil(2 * 148 / tiles))
+    return int(max(1, min(want, K // 512 if K >= 1024 else 1)))
+
+
+class PolicyProgram:
+    def __init__(self, actor_critic, obs_dim, actions_cfg, device, compute_dtype=F32):
+        if not isinstance(actor_critic, ActorCritic):
+            raise TypeError('policy.actor_critic must be an ActorCritic descriptor')
+        if compute_dtype != F32:
+            raise NotImplementedError('compute_dtype other than float32: tcgen05 bf16 path not built yet')
+        bb = actor_critic.backbone
+        if not isinstance(bb, BackboneShared):
+            raise NotImplementedError('only BackboneShared is lowered (BackboneSeparate: next)')
+        if bb.prefix is not None and not getattr(bb.prefix, 'is_identity', False):
+            raise NotImplementedError('BackboneShared.prefix must be None (obs are one [N, D] tensor)')
+        enc = bb.encoder
+        if isinstance(enc, RecurrentBackboneEncoder):
+            raise NotImplementedError('RecurrentBackboneEncoder/LSTM kernels: next (cfg 4)')
+        if not isinstance(enc, BackboneEncoder) or not isinstance(enc.net, MLP):
+            raise NotImplementedError('encoder must be BackboneEncoder(net=MLP)')
+        if not isinstance(actor_critic.actor, DenseLayerDiscreteActor):
+            raise NotImplementedError('actor must be DenseLayerDiscreteActor')
+        if not isinstance(actor_critic.critic, DenseLayerCritic):
+            raise NotImplementedError('critic must be DenseLayerCritic (distributional critics: next)')
+        self.ac = actor_critic
+        self.device = torch.device(device)
+        self.mlp = enc.net
+        self.obs_dim = int(obs_dim)
+        self.H = int(self.mlp.num_channels)
+        self.L = int(self.mlp.num_layers)
+        if self.H % 4 or self.H > 1024:
+            raise NotImplementedError('MLP width must be a multiple of 4 and <= 1024')
+        # action layout: groups in cfg.actions order, components concatenated
+        self.groups = []
+        buckets = []
+        for name, ac in actions_cfg.items():
+            if not isinstance(ac, DiscreteActionsConfig):
+                raise NotImplementedError('continuous actions: next (SURVEY 8f rank 3)')
+            self.groups.append((name, len(buckets), len(ac.actions_num_buckets)))
+            buckets += list(ac.actions_num_buckets)
+        if len(self.groups) != 1:
+            raise NotImplementedError('DenseLayerDiscreteActor drives exactly one action group')
+        self.buckets = buckets
+        self.A = len(buckets)
+        self.sumA = int(sum(buckets))
+        self.V = 1
+        self.NH = _round_up(self.sumA + self.V, 4)
+        self._buckets_c = (ctypes.c_int32 * self.A)(*buckets)
+        # ---- arena layout -------------------------------------------------------------
+        off = 0
+        self.layer_off = []
+        d = self.obs_dim
+        for _ in range(self.L):
+            k_off = off
+            off += d * self.H
+            ln_off = off                      # scale[H] | bias[H] contiguous (one LN segment)
+            off += 2 * self.H
+            self.layer_off.append((k_off, ln_off, d))
+            d = self.H
+        self.feat = self.H
+        self.head_w_off = off
+        off += self.feat * self.NH
+        self.head_b_off = off
+        off += self.NH
+        self.num_params = off
+        dev = self.device
+        self.params = torch.zeros(off, dtype=F32, device=dev)
+        self.grads = torch.zeros(off, dtype=F32, device=dev)
+        self.adam_m = torch.zeros(off, dtype=F32, device=dev)
+        self.adam_v = torch.zeros(off, dtype=F32, device=dev)
+        self.adam_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.grad_sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._sumsq_ws = torch.empty(_lib.lib().mlb_sumsq_workspace(off) + 16, dtype=torch.uint8, device=dev)
+        self.segments = None
+        self._train_ws = None
+        self._infer_ws = None
+
+    # ---------------------------------------------------------------------------------
+    # parameters
+    # ---------------------------------------------------------------------------------
+    def _view(self, arena, off, *shape):
+        n = int(np.prod(shape))
+        return arena[off:off + n].view(*shape)
+
+    def layer_views(self, arena, i):
+        k_off, ln_off, d = self.layer_off[i]
+        return (self._view(arena, k_off, d, self.H), self._view(arena, ln_off, self.H),
+                self._view(arena, ln_off + self.H, self.H))
+
+    def head_views(self, arena):
+        return (self._view(arena, self.head_w_off, self.feat, self.NH),
+                self._view(arena, self.head_b_off, self.NH))
+
+    def param_tree(self, arena=None):
+        """flax-style nested dict of VIEWS into the arena (ml/train_state.py:34-40 `params`)."""
+        a = self.params if arena is None else arena
+        net = {}
+        for i in range(self.L):
+            k, s, b = self.layer_views(a, i)
+            net[f'Dense_{i}'] = {'kernel': k}
+            net[f'LayerNorm_{i}'] = {'impl': {'scale': s, 'bias': b}}
+        W, B = self.head_views(a)
+        return {
+            'backbone': {'encoder': {'net': net}},
+            'actor': {'impl': {'kernel': W[:, :self.sumA], 'bias': B[:self.sumA]}},
+            'critic': {'Dense_0': {'kernel': W[:, self.sumA:self.sumA + 1],
+                                   'bias': B[self.sumA:self.sumA + 1]}},
+        }
+
+    def init_params(self, seed):
+        """orthogonal(sqrt2) Dense kernels, LayerNorm (1, 0), orthogonal(0.01) actor,
+        orthogonal(1.0) critic, zero biases (ml/models.py:103,125,144).  Done once on the
+        host; init parity with jax's QR is not required (tests load identical weights)."""
+        g = torch.Generator().manual_seed(int(seed) & 0x7FFFFFFF)
+
+        def orth(rows, cols, scale):
+            a = torch.randn(max(rows, cols), min(rows, cols), generator=g, dtype=torch.float64)
+            q, r = torch.linalg.qr(a)
+            q = q * torch.sign(torch.diagonal(r))
+            if rows < cols:
+                q = q.t()
+            return (scale * q[:rows, :cols]).to(F32)
+        host = torch.zeros(self.num_params, dtype=F32)
+        for i in range(self.L):
+            k_off, ln_off, d = self.layer_off[i]
+            host[k_off:k_off + d * self.H] = orth(d, self.H, self.mlp.weight_init_scale).reshape(-1)
+            host[ln_off:ln_off + self.H] = 1.0
+        W = torch.zeros(self.feat, self.NH, dtype=F32)
+        W[:, :self.sumA] = orth(self.feat, self.sumA, self.ac.actor.weight_init_scale)
+        W[:, self.sumA:self.sumA + 1] = orth(self.feat, 1, self.ac.critic.weight_init_scale)
+        host[self.head_w_off:self.head_w_off + W.numel()] = W.reshape(-1)
+        self.params.copy_(host)
+        self.finalize_params()
+
+    def load_oracle_params(self, p):
+        """Load a parameter tree in oracle/nn.py format (tests)."""
+        host = torch.zeros(self.num_params, dtype=F32)
+        for i in range(self.L):
+            k_off, ln_off, d = self.layer_off[i]
+            host[k_off:k_off + d * self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['kernel'], np.float32)).reshape(-1)
+            host[ln_off:ln_off + self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['scale'], np.float32))
+            host[ln_off + self.H:ln_off + 2 * self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['bias'], np.float32))
+        W = torch.zeros(self.feat, self.NH, dtype=F32)
+        W[:, :self.sumA] = torch.from_numpy(np.asarray(p['actor']['kernel'], np.float32))
+        W[:, self.sumA:self.sumA + 1] = torch.from_numpy(np.asarray(p['critic']['kernel'], np.float32))
+        B = torch.zeros(self.NH, dtype=F32)
+        B[:self.sumA] = torch.from_numpy(np.asarray(p['actor']['bias'], np.float32))
+        B[self.sumA:self.sumA + 1] = torch.from_numpy(np.asarray(p['critic']['bias'], np.float32))
+        host[self.head_w_off:self.head_w_off + W.numel()] = W.reshape(-1)
+        host[self.head_b_off:self.head_b_off + self.NH] = B
+        self.params.copy_(host)
+        self.finalize_params()
+
+    def to_oracle_params(self, arena=None):
+        t = self.param_tree(arena)
+        net = t['backbone']['encoder']['net']
+        c = lambda x: x.detach().cpu().numpy().copy()
+        return {'mlp': [{'kernel': c(net[f'Dense_{i}']['kernel']),
+                         'scale': c(net[f'LayerNorm_{i}']['impl']['scale']),
+                         'bias': c(net[f'LayerNorm_{i}']['impl']['bias'])} for i in range(self.L)],
+                'actor': {'kernel': c(t['actor']['impl']['kernel']), 'bias': c(t['actor']['impl']['bias'])},
+                'critic': {'kernel': c(t['critic']['Dense_0']['kernel']), 'bias': c(t['critic']['Dense_0']['bias'])}}
+
+    def finalize_params(self):
+        """Record initial kernel norms (ml/train_state.py:413-423) -> device segment table."""
+        self.initial_weight_norms = {}
+        host = self.params.detach().cpu()
+        for i in range(self.L):
+            k_off, ln_off, d = self.layer_off[i]
+            n0 = float(torch.linalg.vector_norm(host[k_off:k_off + d * self.H].double()))
+            self.initial_weight_norms[f'Dense_{i}'] = n0
+        self.rebuild_segments()
+
+    def rebuild_segments(self):
+        segs = []
+        for i in range(self.L):
+            k_off, ln_off, d = self.layer_off[i]
+            segs.append(_lib.Segment(k_off, d * self.H, 1, float(self.initial_weight_norms[f'Dense_{i}'])))
+            segs.append(_lib.Segment(ln_off, 2 * self.H, 2, float(self.H)))
+        arr = (_lib.Segment * len(segs))(*segs)
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.segments = torch.from_numpy(raw).to(self.device)
+        self.num_segments = len(segs)
+
+    # ---------------------------------------------------------------------------------
+    # workspaces
+    # ---------------------------------------------------------------------------------
+    def infer_ws(self, rows):
+        w = self._infer_ws
+        if w is None or w['rows'] < rows:
+            dev = self.device
+            w = dict(rows=rows, z=torch.empty(rows, self.H, dtype=F32, device=dev),
+                     y=[torch.empty(rows, self.H, dtype=F32, device=dev) for _ in range(2)],
+                     head=torch.empty(rows, self.NH, dtype=F32, device=dev))
+            self._infer_ws = w
+        return w
+
+    def train_ws(self, rows):
+        w = self._train_ws
+        if w is None or w['rows'] < rows:
+            dev = self.device
+            e = lambda *s: torch.empty(*s, dtype=F32, device=dev)
+            w = dict(rows=rows, z=[e(rows, self.H) for _ in range(self.L)],
+                     y=[e(rows, self.H) for _ in range(self.L)],
+                     stats=[e(rows, 2) for _ in range(self.L)],
+                     head=e(rows, self.NH), dhead=e(rows, self.NH),
+                     dy=e(rows, self.H), dz=e(rows, self.H),
+                     loss_ws=torch.empty(_lib.lib().mlb_ppo_loss_workspace(rows) + 16, dtype=torch.uint8, device=dev),
+                     stats_out=torch.zeros(ctypes.sizeof(_lib.PPOStats), dtype=torch.uint8, device=dev))
+            self._train_ws = w
+        return w
+
+    # ---------------------------------------------------------------------------------
+    # forward (rollout / critic_only): ActorCritic.rollout ml/actor_critic.py:74-96
+    # ---------------------------------------------------------------------------------
+    def forward_infer(self, obs, rows):
+        """obs f32 [rows, D] -> head f32 [rows, NH] (logits | value)."""
+        w = self.infer_ws(rows)
+        x, d = obs, self.obs_dim
+        for i in range(self.L):
+            k, s, b = self.layer_views(self.params, i)
+            gemm(x, k, w['z'], None, rows, self.H, d, d, self.H, self.H)
+            y = w['y'][i & 1]
+            call('mlb_ln_relu_fwd_f32', ptr(w['z']), ptr(s), ptr(b), ptr(y), ptr(None), c_ll(rows), c_int(self.H))
+            x, d = y, self.H
+        W, B = self.head_views(self.params)
+        gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
+        return w['head']
+
+    def sample(self, head, rows, policy_key, actions, log_probs, values, partitionable=False,
+               deterministic=False):
+        call('mlb_sample_discrete_f32', ptr(head), c_int(self.NH), ptr(policy_key), self._buckets_c,
+             c_int(self.A), c_ll(rows), c_int(int(partitionable)), c_int(int(deterministic)),
+             ptr(actions), ptr(log_probs), ptr(values))
+
+    # ---------------------------------------------------------------------------------
+    # training forward + backward (ActorCritic.update ml/actor_critic.py:98-128 + autodiff)
+    # ---------------------------------------------------------------------------------
+    def forward_train(self, obs, rows):
+        w = self.train_ws(rows)
+        x, d = obs, self.obs_dim
+        for i in range(self.L):
+            k, s, b = self.layer_views(self.params, i)
+            gemm(x, k, w['z'][i], None, rows, self.H, d, d, self.H, self.H)
+            call('mlb_ln_relu_fwd_f32', ptr(w['z'][i]), ptr(s), ptr(b), ptr(w['y'][i]), ptr(w['stats'][i]),
+                 c_ll(rows), c_int(self.H))
+            x, d = w['y'][i], self.H
+        W, B = self.head_views(self.params)
+        gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
+        return w['head']
+
+    def backward(self, obs, rows):
+        """Consumes train_ws['dhead']; accumulates into self.grads (pre-zeroed)."""
+        w = self.train_ws(rows)
+        W, B = self.head_views(self.params)
+        gW, gB = self.head_views(self.grads)
+        feat = w['y'][self.L - 1]
+        # dW_h = feat^T dhead ; db_h = colsum(dhead) ; dfeat = dhead W_h^T
+        gemm(feat, w['dhead'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH,
+             ta=1, tb=0, accumulate=1, splitk=_splitk_for(self.feat, self.NH, rows))
+        call('mlb_colsum_f32', ptr(w['dhead']), c_ll(rows), c_int(self.NH), c_int(self.NH), ptr(gB))
+        gemm(w['dhead'], W, w['dy'], None, rows, self.feat, self.NH, self.NH, self.NH, self.feat,
+             ta=0, tb=1)
+        for i in range(self.L - 1, -1, -1):
+            k, s, b = self.layer_views(self.params, i)
+            gk, gs, gb = self.layer_views(self.grads, i)
+            d = self.layer_off[i][2]
+            call('mlb_ln_relu_bwd_f32', ptr(w['dy']), ptr(w['z'][i]), ptr(w['stats'][i]), ptr(s), ptr(b),
+                 ptr(w['dz']), ptr(gs), ptr(gb), c_ll(rows), c_int(self.H))
+            x = obs if i == 0 else w['y'][i - 1]
+            gemm(x, w['dz'], gk, None, d, self.H, rows, d, self.H, self.H, ta=1, tb=0,
+                 accumulate=1, splitk=_splitk_for(d, self.H, rows))
+            if i > 0:
+                gemm(w['dz'], k, w['dy'], None, rows, d, self.H, self.H, self.H, d, ta=0, tb=1)
+
+    def zero_grads(self):
+        call('mlb_fill_zero', ptr(self.grads), c_size_t(self.num_params * 4))
+
+    def optimizer_step(self, lr, max_grad_norm, grad_scale=1.0, b1=0.9, b2=0.999, eps=1e-8):
+        """clip_by_global_norm -> adam -> re-projection / LN renorm (ml/ppo.py:283-338)."""
+        call('mlb_sumsq_f32', ptr(self.grads), c_ll(self.num_params), ptr(self.grad_sumsq),
+             ptr(self._sumsq_ws), c_size_t(self._sumsq_ws.numel()))
+        call('mlb_adam_step_f32', ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v),
+             c_ll(self.num_params), ptr(self.adam_step), ptr(self.grad_sumsq), c_float(lr),
+             c_float(b1), c_float(b2), c_float(eps), c_float(max_grad_norm), c_float(grad_scale))
+        call('mlb_renorm_segments', ptr(self.params), ptr(self.segments), c_int(self.num_segments),
+             ptr(self.adam_step))
+
+    # ---------------------------------------------------------------------------------
+    # flax-style apply(method=...) entry points (ml/actor_critic.py:65-128); these allocate
+    # their outputs and are meant for API parity / tests -- the training loop calls the
+    # buffer-explicit methods above.
+    # ---------------------------------------------------------------------------------
+    def _obs2d(self, obs):
+        (ob,) = obs.values() if isinstance(obs, dict) else (obs,)
+        return ob.reshape(-1, self.obs_dim)
+
+    def apply_rollout(self, prng_key, rnn_states, obs, train=False, sample_actions=True,
+                      return_debug=False, partitionable=False):
+        x = self._obs2d(obs)
+        rows = x.shape[0]
+        head = self.forward_infer(x, rows)
+        actions = torch.empty(rows, self.A, dtype=torch.int32, device=self.device)
+        log_probs = torch.empty(rows, self.A, dtype=F32, device=self.device)
+        values = torch.empty(rows, 1, dtype=F32, device=self.device)
+        self.sample(head, rows, prng_key, actions, log_probs if sample_actions else None, values,
+                    partitionable, deterministic=not sample_actions)
+        name = self.groups[0][0]
+        out = {'actions': {name: actions}, 'critic': values}
+        if sample_actions:
+            out['log_probs'] = {name: log_probs}
+        return out, rnn_states
+
+    def apply_critic_only(self, rnn_states, obs, train=False):
+        x = self._obs2d(obs)
+        head = self.forward_infer(x, x.shape[0])
+        return {'critic': head[:, self.sumA:self.sumA + 1].clone()}, rnn_states
+
+    def apply_actor_only(self, rnn_states, obs, train=False):
+        out, rnn = self.apply_rollout(None, rnn_states, obs, sample_actions=False)
+        return {'actions': out['actions']}, rnn

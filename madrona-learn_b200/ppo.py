@@ -1,0 +1,198 @@
+"""PPO algorithm plugin (ml/ppo.py:24-488): PPOConfig / PPOHyperParams / PPO(AlgoBase).
+
+`_ppo` is the reference's epoch x minibatch loop (default branch, :437-488) restructured for
+the B200: all `num_epochs` permutations are generated up-front by the
+device threefry + sort kernels (the key stream only depends on update_prng_key); the
+per-minibatch z-score statistics of the advantages and the value-normaliser recurrence are
+computed for every minibatch in three launches right after GAE; the minibatch loop itself
+is gather -> fwd -> fused loss/grad -> bwd -> [grad all-reduce] -> fused optimiser.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, Union
+
+import torch
+
+from . import _lib
+from . import kernels as K
+from ._lib import c_float, c_int, c_ll, c_size_t, call, ptr
+from .algo_common import AlgoBase, HyperParams
+from .cfg import AlgoConfig, ParamExplore, TrainConfig
+from .profile import profile
+
+__all__ = ['PPOConfig']
+
+
+@dataclass(frozen=True)
+class PPOConfig(AlgoConfig):                    # ml/ppo.py:24-39
+    num_epochs: int
+    minibatch_size: int                         # in TRAJECTORIES (ml/ppo.py:437-439)
+    clip_coef: float
+    value_loss_coef: float
+    entropy_coef: Union[float, Dict[str, float], ParamExplore]
+    max_grad_norm: float
+    clip_value_loss: bool = False
+    huber_value_loss: bool = False
+
+    def name(self):
+        return 'ppo'
+
+    def setup(self):
+        return PPO()
+
+
+@dataclass
+class PPOHyperParams(HyperParams):              # ml/ppo.py:42-46
+    clip_coef: float = 0.0
+    value_loss_coef: float = 0.0
+    entropy_coef: Any = 0.0
+    max_grad_norm: float = 0.0
+
+
+METRIC_NAMES = ['Loss', 'Action Obj', 'Value Loss', 'Value Errors', 'Entropy']
+
+
+class PPO(AlgoBase):
+    def init_hyperparams(self, cfg: TrainConfig):            # ml/ppo.py:50-81
+        if cfg.dreamer_v3_critic or cfg.hlgauss_critic:
+            assert not cfg.algo.clip_value_loss
+            assert not cfg.algo.huber_value_loss
+            assert not cfg.normalize_values
+        lr = cfg.lr.base if isinstance(cfg.lr, ParamExplore) else cfg.lr
+        ent = cfg.algo.entropy_coef.base if isinstance(cfg.algo.entropy_coef, ParamExplore) \
+            else cfg.algo.entropy_coef
+        return PPOHyperParams(
+            lr=lr, gamma=cfg.gamma, gae_lambda=cfg.gae_lambda, normalize_values=cfg.normalize_values,
+            value_normalizer_decay=cfg.value_normalizer_decay,
+            max_advantage_est_decay=cfg.max_advantage_est_decay, clip_coef=cfg.algo.clip_coef,
+            value_loss_coef=cfg.algo.value_loss_coef, entropy_coef=ent,
+            max_grad_norm=cfg.algo.max_grad_norm)
+
+    def make_optimizer(self, hyper_params):                  # ml/ppo.py:83-90
+        """optax.chain(clip_by_global_norm, adam): lr is baked here, exactly like the
+        reference (the PBT-mutable hyper_params.lr array is NOT what the optimiser reads)."""
+        return dict(kind='clip_by_global_norm+adam', max_grad_norm=float(hyper_params.max_grad_norm),
+                    lr=float(hyper_params.lr), b1=0.9, b2=0.999, eps=1e-8)
+
+    def update(self, *args, **kwargs):
+        return _ppo(*args, **kwargs)
+
+    def add_metrics(self, cfg, metrics):                     # ml/ppo.py:95-106
+        return metrics + METRIC_NAMES
+
+
+def _entropy_coef(cfg, group):
+    ec = cfg.algo.entropy_coef
+    if isinstance(ec, dict):                                 # ml/ppo.py:233 indexes by group name
+        return float(ec[group])
+    if isinstance(ec, ParamExplore):
+        return float(ec.base)
+    return float(ec)
+
+
+class _PPOWorkspace:
+    """Per-run device buffers of the learner (allocated once)."""
+
+    def __init__(self, cfg, prog, C, Tp, B, dist_ctx):
+        dev = prog.device
+        E, M = cfg.algo.num_epochs, cfg.algo.minibatch_size
+        J = C * B
+        assert J % M == 0, 'num trajectories must be divisible by minibatch_size (ml/ppo.py:439)'
+        self.E, self.M, self.J, self.nmb, self.rows = E, M, J, J // M, Tp * M
+        e = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
+        self.perm = e(E, J, dtype=torch.int32)
+        self.perm_ws = torch.empty(K.lib().mlb_ppo_permutations_workspace(E, J) + 16,
+                                   dtype=torch.uint8, device=dev)
+        self.tm_adv = e(J, 2, dtype=torch.float64)
+        self.tm_ret = e(J, 2, dtype=torch.float64)
+        self.mb_adv = e(E * self.nmb, 4)
+        self.mb_ret = e(E * self.nmb, 4)
+        self.vn_params = e(E * self.nmb, 4)
+        self.mb = {
+            'obs': e(Tp, M, prog.obs_dim), 'actions': e(Tp, M, prog.A, dtype=torch.int32),
+            'log_probs': e(Tp, M, prog.A), 'advantages': e(Tp, M, 1), 'returns': e(Tp, M, 1),
+            'values': e(Tp, M, 1),
+        }
+        A = prog.A
+        g_name, _, g_size = prog.groups[0]
+        coef = _entropy_coef(cfg, g_name)
+        rows_global = self.rows * (dist_ctx.world_size if dist_ctx else 1)
+        self.rows_global = rows_global
+        self.obj_scale = (ctypes.c_float * A)(*[1.0 / (rows_global * g_size)] * A)
+        self.ent_scale = (ctypes.c_float * A)(*[coef / (rows_global * g_size)] * A)
+        prog.train_ws(self.rows)
+
+
+def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics, dist_ctx=None,
+         ws=None, partitionable=False):
+    """ml/ppo.py:366-488, default branch (valid_inds = arange(J), weights = 1)."""
+    if cfg.filter_advantages or cfg.importance_sample_trajectories:
+        raise NotImplementedError('filter_advantages / importance_sample_trajectories are "next" '
+                                  'rows (SURVEY 8f rank 2)')
+    prog = policy_state.program
+    st = rollout_data.store
+    C, Tp, B = rollout_data.C, rollout_data.Tp, rollout_data.B
+    if ws is None:
+        ws = _PPOWorkspace(cfg, prog, C, Tp, B, dist_ctx)
+    E, M, J, nmb, rows = ws.E, ws.M, ws.J, ws.nmb, ws.rows
+    T, N = C * Tp, B
+    tx = train_state.tx
+    hp = train_state.hyper_params
+
+    with profile('Compute Minibatch Indices'):
+        K.ppo_permutations(train_state.update_prng_key, E, J, partitionable, ws.perm, ws.perm_ws)
+
+    # per-minibatch statistics for ALL minibatches of the update (App. C.1)
+    score_key = 'advantages' if cfg.compute_advantages else 'returns'
+    normalize_scores = cfg.normalize_advantages if cfg.compute_advantages else cfg.normalize_returns
+    if normalize_scores:
+        K.traj_moments(st[score_key].view(T, N), C, ws.tm_adv)
+        K.mb_moments(ws.tm_adv, ws.perm, M, Tp, 1e-5, ws.mb_adv)
+        if dist_ctx is not None:
+            dist_ctx.allreduce_moments(ws.mb_adv, 1e-5)
+    vn = train_state.value_normalizer
+    if vn is not None:
+        K.traj_moments(st['returns'].view(T, N), C, ws.tm_ret)
+        K.mb_moments(ws.tm_ret, ws.perm, M, Tp, 0.0, ws.mb_ret)
+        if dist_ctx is not None:
+            dist_ctx.allreduce_moments(ws.mb_ret, 0.0)
+        K.ema_scan(train_state.value_normalizer_state, ws.mb_ret, vn.decay, vn.eps, ws.vn_params)
+
+    flags = (1 if cfg.algo.clip_value_loss else 0) | (2 if cfg.algo.huber_value_loss else 0)
+    keys = ['obs', 'actions', 'log_probs', score_key, 'returns']
+    if cfg.algo.clip_value_loss:
+        keys.append('values')
+    tw = prog.train_ws(rows)
+    mb = ws.mb
+    for e in range(E):
+        for k in range(nmb):
+            mbi = e * nmb + k
+            with profile('Gather Minibatch'):
+                idx = ws.perm[e, k * M:(k + 1) * M]
+                for name in set(keys):
+                    K.mb_gather(st[name][:, :, 0], idx, C, Tp, B, mb[name])
+            with profile('AC Forward'):
+                head = prog.forward_train(mb['obs'].view(rows, prog.obs_dim), rows)
+            with profile('Optimize'):
+                call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(mb['actions']),
+                     ptr(mb['log_probs']), ptr(mb[score_key]), ptr(mb['returns']),
+                     ptr(mb['values']) if cfg.algo.clip_value_loss else ptr(None), ptr(None),
+                     ptr(ws.mb_adv[mbi]) if normalize_scores else ptr(None),
+                     ptr(ws.vn_params[mbi]) if vn is not None else ptr(None),
+                     prog._buckets_c, ws.obj_scale, ws.ent_scale, c_int(prog.A), c_ll(rows), c_ll(M),
+                     c_float(hp.clip_coef), c_float(hp.value_loss_coef), c_int(flags),
+                     ptr(tw['dhead']), ptr(tw['stats_out']), ptr(tw['loss_ws']),
+                     c_size_t(tw['loss_ws'].numel()))
+                prog.zero_grads()
+                prog.backward(mb['obs'].view(rows, prog.obs_dim), rows)
+                grad_scale = 1.0
+                if dist_ctx is not None:
+                    dist_ctx.allreduce_grads(prog.grads)      # sum over ranks; scales already global
+                prog.optimizer_step(tx['lr'], tx['max_grad_norm'], grad_scale, tx['b1'], tx['b2'], tx['eps'])
+            with profile('Metrics Callback'):
+                metrics = user_metrics_cb(metrics, e, mb, policy_state, train_state)
+    with profile('Record Metrics'):
+        # per-minibatch records overwrite the same slot: the last minibatch wins (App. C.4)
+        dst = metrics.slot('Loss', 5)
+        call('mlb_copy_bytes', ptr(tw['stats_out'][16:]), ptr(dst), c_size_t(dst.numel()))
+    return policy_state, train_state, metrics

@@ -1,0 +1,291 @@
+"""Rollout buffers + inference loop (ml/rollouts.py:28-978), non-PBT branch (P = 1).
+
+Differences from the reference that are deliberate B200 design, not omissions:
+  * buffers are allocated once and reused (XLA donation made explicit);
+  * the per-step store (`store.at[(c, s)].set`, :356-367) is the kernels writing straight
+    into the [c, s] slab of the [C, T', P, B, ...] store;
+  * `_finalize_rollouts` never materialises the [P, C*B, T', ...] relayout (:788-804):
+    GAE runs on the [T, N] view and minibatches are gathered from the store by the K5 kernel
+    (`RolloutData.minibatch`), bit-identical to take+swapaxes on the relayout.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+
+from . import kernels as K
+from ._lib import c_float, c_int, c_ll, c_size_t, call, ptr
+from .algo_common import compute_advantages, compute_returns
+from .cfg import DiscreteActionsConfig
+from .profile import profile
+
+
+@dataclass(frozen=True)
+class PBTMatchmakeConfig:               # the arithmetic RolloutConfig.setup needs (ml/pbt.py:21-118)
+    num_current_policies: int
+    num_past_policies: int
+    total_num_policies: int
+    num_teams: int
+    team_size: int
+    self_play_batch_size: int
+    cross_play_batch_size: int
+    past_play_batch_size: int
+    static_play_batch_size: int
+    complex_matchmaking: bool
+    custom_policy_ids: List[int]
+
+
+@dataclass(frozen=True)
+class RolloutConfig:                    # ml/rollouts.py:28-134
+    sim_batch_size: int
+    num_worlds: int
+    actions_cfg: Dict[str, Any]
+    policy_chunk_size: int
+    num_policy_chunks: int
+    total_policy_batch_size: int
+    reward_gamma: float
+    policy_dtype: Any
+    reward_dtype: Any
+    prob_dtype: Any
+    pbt: PBTMatchmakeConfig
+
+    @staticmethod
+    def setup(num_current_policies, num_past_policies, num_teams, team_size, sim_batch_size,
+              actions_cfg, self_play_portion, cross_play_portion, past_play_portion,
+              static_play_portion, reward_gamma, custom_policy_ids, policy_dtype,
+              reward_dtype=torch.float32, prob_dtype=torch.float32,
+              policy_chunk_size_override=0):
+        assert (self_play_portion + cross_play_portion + past_play_portion +
+                static_play_portion == 1.0)
+        if self_play_portion != 1.0 or num_past_policies != 0 or num_current_policies != 1:
+            raise NotImplementedError('PBT matchmaking / multi-policy batching is out of scope '
+                                      '(SURVEY 8f rank 1); only pbt=None configs are lowered')
+        pbt = PBTMatchmakeConfig(
+            num_current_policies=1, num_past_policies=0, total_num_policies=1,
+            num_teams=num_teams, team_size=team_size, self_play_batch_size=sim_batch_size,
+            cross_play_batch_size=0, past_play_batch_size=0, static_play_batch_size=0,
+            complex_matchmaking=False, custom_policy_ids=list(custom_policy_ids))
+        chunk = sim_batch_size // num_current_policies
+        if policy_chunk_size_override != 0:
+            chunk = policy_chunk_size_override
+        nchunks = -(sim_batch_size // -chunk)
+        return RolloutConfig(
+            sim_batch_size=sim_batch_size, num_worlds=sim_batch_size // (team_size * num_teams),
+            actions_cfg=actions_cfg, policy_chunk_size=chunk, num_policy_chunks=nchunks,
+            total_policy_batch_size=nchunks * chunk, reward_gamma=reward_gamma,
+            policy_dtype=policy_dtype, reward_dtype=reward_dtype, prob_dtype=prob_dtype, pbt=pbt)
+
+
+@dataclass
+class RolloutState:                     # ml/rollouts.py:171-183
+    cfg: RolloutConfig
+    step_fn: Callable
+    load_ckpts_fn: Optional[Callable]
+    get_ckpts_fn: Optional[Callable]
+    sim_state: Any
+    cur_obs: Dict[str, torch.Tensor]
+    prng_key: torch.Tensor              # int32[2] on device
+    rnn_states: Any
+    reorder_state: Any
+    policy_assignments: torch.Tensor
+    sim_ctrl: Any
+    env_returns: torch.Tensor
+
+    @staticmethod
+    def create(rollout_cfg, sim_fns, prng_key, rnn_states, init_sim_ctrl,
+               static_play_assignments, device, partitionable=False):
+        # prng_key, assign_rnd = split(prng_key)   (ml/rollouts.py:200)
+        ks = K.threefry_split(prng_key, 2, partitionable)
+        prng_key = ks[0].clone()
+        init_out = sim_fns['init']()
+        return RolloutState(
+            cfg=rollout_cfg, step_fn=sim_fns['step'], load_ckpts_fn=sim_fns.get('load_ckpts'),
+            get_ckpts_fn=sim_fns.get('get_ckpts'), sim_state=init_out['state'],
+            cur_obs=dict(init_out['obs']), prng_key=prng_key, rnn_states=rnn_states,
+            reorder_state=None,
+            policy_assignments=torch.zeros(rollout_cfg.sim_batch_size, dtype=torch.int32, device=device),
+            sim_ctrl=init_sim_ctrl,
+            env_returns=torch.zeros(rollout_cfg.sim_batch_size, 1, dtype=torch.float32, device=device))
+
+    def update(self, **kw):
+        for k, v in kw.items():
+            if v is not None:
+                setattr(self, k, v)
+        return self
+
+
+class RolloutData:                      # ml/rollouts.py:311-334
+    """`store` holds every per-step leaf as [C, T', P=1, B, *leaf] (+ rnn_start_states
+    [C, P, B, *]).  `all()` materialises the reference's training layout [J, T', ...] on
+    demand (hooks / debugging); the learner never does."""
+
+    def __init__(self, store, C, Tp, B):
+        self.store = store
+        self.C, self.Tp, self.B = C, Tp, B
+        self.num_train_seqs_per_policy = C * B
+        self.num_train_policies = 1
+        self._out = {}
+
+    def all(self):
+        def relayout(x):
+            t = x.permute(2, 0, 3, 1, *range(4, x.dim()))
+            return t.reshape(t.shape[0], -1, *t.shape[3:])[0]
+        return {k: relayout(v) for k, v in self.store.items() if k != 'rnn_start_states'}
+
+    def minibatch(self, indices, keys=None, out=None):
+        """-> dict name -> [T', M, *leaf]  (take(axis 0) + swapaxes(0, 1), :319-329)."""
+        res = {}
+        for k, v in self.store.items():
+            if k == 'rnn_start_states' or (keys is not None and k not in keys):
+                continue
+            res[k] = K.mb_gather(v[:, :, 0], indices, self.C, self.Tp, self.B,
+                                 None if out is None else out[k])
+        return res
+
+
+class RolloutManager:                   # ml/rollouts.py:373-826
+    def __init__(self, train_cfg, init_rollout_state, example_policy_states):
+        self._cfg = init_rollout_state.cfg
+        if train_cfg.dreamer_v3_critic or train_cfg.hlgauss_critic:
+            raise NotImplementedError('distributional critics are a "next" row (SURVEY 8f rank 3): '
+                                      'set dreamer_v3_critic=False, hlgauss_critic=False')
+        self._num_bptt_chunks = train_cfg.num_bptt_chunks
+        assert train_cfg.steps_per_update % train_cfg.num_bptt_chunks == 0
+        self._num_bptt_steps = train_cfg.steps_per_update // train_cfg.num_bptt_chunks
+        self._num_train_policies = 1
+        self._num_train_agents_per_policy = self._cfg.sim_batch_size
+        self._num_train_seqs_per_policy = self._num_train_agents_per_policy * self._num_bptt_chunks
+        self._use_advantages = train_cfg.compute_advantages
+        self._train_cfg = train_cfg
+        prog = example_policy_states.program
+        self._prog = prog
+        dev = prog.device
+        C, Tp, B = self._num_bptt_chunks, self._num_bptt_steps, self._cfg.sim_batch_size
+        (ob_name, ob), = init_rollout_state.cur_obs.items()
+        self._ob_name = ob_name
+        self._act_name = prog.groups[0][0]
+        e = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
+        # store schema: ml/rollouts.py:409-480
+        self.store = {
+            'obs': e(C, Tp, 1, B, prog.obs_dim),
+            'actions': e(C, Tp, 1, B, prog.A, dtype=torch.int32),
+            'log_probs': e(C, Tp, 1, B, prog.A),
+            'rewards': e(C, Tp, 1, B, 1),
+            'dones': e(C, Tp, 1, B, 1, dtype=torch.bool),
+            'values': e(C, Tp, 1, B, 1),
+            'advantages': e(C, Tp, 1, B, 1),
+            'returns': e(C, Tp, 1, B, 1),
+        }
+        self.bootstrap = e(1, B, 1)
+        self._scratch_actions = e(B, prog.A, dtype=torch.int32)
+        self.env_returns_trace = e(C * Tp, B)
+        self.policy_key = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.resets = torch.zeros(self._cfg.num_worlds, 1, dtype=torch.int32, device=dev)
+        T = C * Tp
+        self._gae_ws = torch.empty(K.lib().mlb_gae_workspace(T, B) + 16, dtype=torch.uint8, device=dev)
+        self._met_ws = torch.empty(K.lib().mlb_moments_workspace(T * B) + 16, dtype=torch.uint8, device=dev)
+        self.partitionable = False
+
+    def add_metrics(self, train_cfg, metrics):          # :482-499
+        names = ['Rewards', 'Est Returns', 'Env Returns', 'Values']
+        if train_cfg.compute_advantages:
+            names.append('Advantages')
+        names.append('Bootstrap Values')
+        return metrics + names
+
+    # ---------------------------------------------------------------------------------
+    def collect(self, train_state_mgr, rollout_state, metrics, user_start_rollouts_hook,
+                user_finish_rollouts_hook, user_metrics_hook):
+        """ml/rollouts.py:501-577."""
+        rollout_state, user_state = user_start_rollouts_hook(rollout_state, train_state_mgr.user_state)
+        policy_states = train_state_mgr.policy_states
+        train_states = train_state_mgr.train_states
+        for c in range(self._num_bptt_chunks):
+            # (rnn_start_states[c] would be cached here for recurrent policies, :533-537)
+            rollout_state = self.rollout_loop(rollout_state, policy_states, c)
+        with profile('Bootstrap Values'):
+            self._bootstrap_values(policy_states, rollout_state)
+        with profile('Finalize Rollouts'):
+            rollout_data, metrics, user_state = self._finalize_rollouts(
+                train_states, metrics, user_state, user_finish_rollouts_hook, user_metrics_hook)
+        train_state_mgr.user_state = user_state
+        return train_state_mgr, rollout_state, rollout_data, None, metrics
+
+    def rollout_loop(self, rs, policy_states, c):
+        """rollout_iter x T' (ml/rollouts.py:829-978) for BPTT chunk c."""
+        prog, N, st = self._prog, self._cfg.sim_batch_size, self.store
+        gamma = self._cfg.reward_gamma
+        Tp = self._num_bptt_steps
+        for s in range(Tp):
+            with profile('Policy Inference'):
+                call('mlb_rollout_keys', ptr(rs.prng_key), ptr(self.policy_key),
+                     c_int(int(self.partitionable)))
+                pre = policy_states.obs_preprocess.preprocess(
+                    policy_states.obs_preprocess_state, rs.cur_obs, True)
+                ob = pre[self._ob_name]
+                slab = st['obs'][c, s, 0]
+                call('mlb_copy_bytes', ptr(ob), ptr(slab), c_size_t(slab.numel() * 4))
+                head = prog.forward_infer(slab, N)
+                actions = st['actions'][c, s, 0]
+                prog.sample(head, N, self.policy_key, actions, st['log_probs'][c, s, 0],
+                            st['values'][c, s, 0], self.partitionable)
+            with profile('Rollout Step'):
+                step_input = {
+                    'state': rs.sim_state, 'actions': {self._act_name: actions},
+                    'resets': self.resets, 'sim_ctrl': rs.sim_ctrl,
+                    'pbt': {'policy_assignments': rs.policy_assignments},
+                }
+                out = rs.step_fn(step_input)
+                rs.sim_state = out['state']
+                rs.cur_obs = dict(out['obs'])
+                dones, rewards = out['dones'], out['rewards']
+                if dones.dtype not in (torch.bool, torch.uint8):
+                    dones = dones != 0
+                if rewards.dtype != torch.float32:
+                    rewards = rewards.float()
+            with profile('Post Step Rollout Store'):
+                d_slab, r_slab = st['dones'][c, s, 0], st['rewards'][c, s, 0]
+                call('mlb_copy_bytes', ptr(dones), ptr(d_slab), c_size_t(N))
+                call('mlb_copy_bytes', ptr(rewards), ptr(r_slab), c_size_t(N * 4))
+                call('mlb_env_returns_f32', ptr(r_slab), ptr(d_slab), ptr(rs.env_returns),
+                     ptr(self.env_returns_trace[c * Tp + s]), c_ll(N), c_float(gamma))
+        return rs
+
+    def _bootstrap_values(self, policy_states, rs):     # :607-635
+        prog, N = self._prog, self._cfg.sim_batch_size
+        pre = policy_states.obs_preprocess.preprocess(policy_states.obs_preprocess_state, rs.cur_obs, False)
+        ob = pre[self._ob_name].reshape(N, prog.obs_dim)
+        head = prog.forward_infer(ob, N)
+        # critic column of the head -> bootstrap [1, B, 1] (the greedy actions are discarded)
+        prog.sample(head, N, None, self._scratch_actions, None, self.bootstrap, deterministic=True)
+
+    def _finalize_rollouts(self, train_states, metrics, user_state, finish_hook, metrics_hook):
+        """ml/rollouts.py:716-826."""
+        st, cfg = self.store, self._train_cfg
+        vn_state = train_states.value_normalizer_state if train_states.value_normalizer is not None else None
+        hooked, user_state = finish_hook(st, self.bootstrap, st['values'], self.bootstrap, user_state)
+        if hooked is not st:
+            raise NotImplementedError('finish_rollouts must modify the rollout store in place')
+        if self._use_advantages:
+            compute_advantages(cfg, st['rewards'], st['values'], st['dones'], self.bootstrap,
+                               advantages=st['advantages'], returns=st['returns'],
+                               vn_mu_sigma=vn_state, metrics=metrics.slot('Rewards', 4)
+                               if self._metrics_contiguous(metrics) else None, ws=self._gae_ws)
+        else:
+            if vn_state is not None:
+                raise NotImplementedError('normalize_values with compute_advantages=False')
+            compute_returns(cfg, st['rewards'], st['dones'], self.bootstrap, returns=st['returns'])
+        K.metric(self.bootstrap, metrics.slot('Bootstrap Values'), self._met_ws)
+        K.metric(self.env_returns_trace, metrics.slot('Env Returns'), self._met_ws)
+        data = RolloutData(st, self._num_bptt_chunks, self._num_bptt_steps, self._cfg.sim_batch_size)
+        metrics = metrics_hook(metrics, data, user_state)
+        return data, metrics, user_state
+
+    @staticmethod
+    def _metrics_contiguous(metrics):
+        """The GAE kernel writes 4 consecutive records: Rewards, Values, Est Returns,
+        Advantages -- the training metrics table is laid out that way by init_training."""
+        i = metrics.index
+        return (i.get('Values') == i['Rewards'] + 1 and i.get('Est Returns') == i['Rewards'] + 2 and
+                i.get('Advantages') == i['Rewards'] + 3)

@@ -1,0 +1,163 @@
+"""Train / policy state containers (ml/train_state.py:34-488).  Field names follow the
+reference; leaves are device tensors.  P (number of train policies) is 1: PBT is out of scope.
+"""
+import os
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, Optional
+
+import torch
+
+from . import kernels as K
+from .algo_common import HyperParams
+from .engine import PolicyProgram
+from .moving_avg import EMAEstimate, EMANormalizer
+from .observations import ObservationsPreprocessNoop
+
+
+@dataclass
+class PolicyState:                                     # ml/train_state.py:34-82
+    apply_fn: Callable
+    rnn_reset_fn: Callable
+    params: Dict[str, Any]
+    batch_stats: Dict[str, Any]
+    obs_preprocess: Any
+    obs_preprocess_state: Any
+    reward_hyper_params: Any
+    get_episode_scores_fn: Callable
+    episode_score: Any
+    mmr: Any
+    program: PolicyProgram = None
+
+    def update(self, **kw):
+        for k, v in kw.items():
+            if v is not None:
+                setattr(self, k, v)
+        return self
+
+
+@dataclass
+class PolicyTrainState:                                # ml/train_state.py:85-136
+    value_normalizer: Optional[EMANormalizer]
+    max_advantage_est: EMAEstimate
+    initial_weight_norms: Dict[str, Any]
+    tx: Any
+    value_normalizer_state: Any
+    max_advantage_est_state: Any
+    hyper_params: HyperParams
+    opt_state: Dict[str, Any]
+    scheduler: Any
+    scaler: Any
+    update_prng_key: torch.Tensor          # int32[2] device tensor holding the uint32 key words
+
+    def update(self, **kw):
+        for k, v in kw.items():
+            if v is not None:
+                setattr(self, k, v)
+        return self
+
+    def gen_update_rnd(self, partitionable=False):     # :134-136
+        ks = K.threefry_split(self.update_prng_key, 2, partitionable)
+        self.update_prng_key.copy_(ks[1])
+        return ks[0], self
+
+
+@dataclass
+class TrainStateManager:                               # ml/train_state.py:139-304
+    policy_states: PolicyState
+    train_states: PolicyTrainState
+    pbt_rng: torch.Tensor
+    user_state: Any
+
+    def replace(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+        return self
+
+    # checkpoint: same dict keys as ml/train_state.py:145-164; torch.save stands in for orbax
+    def save(self, next_update, path):
+        ps, ts = self.policy_states, self.train_states
+        prog = ps.program
+        ckpt = {
+            'next_update': int(next_update),
+            'policy_states': {'params': prog.params.cpu(),
+                              'obs_preprocess_state': ps.obs_preprocess_state},
+            'train_states': {'opt_state': {'m': prog.adam_m.cpu(), 'v': prog.adam_v.cpu(),
+                                           'count': prog.adam_step.cpu()},
+                             'value_normalizer_state': None if ts.value_normalizer_state is None
+                             else ts.value_normalizer_state.cpu(),
+                             'update_prng_key': ts.update_prng_key.cpu(),
+                             'initial_weight_norms': ts.initial_weight_norms},
+            'pbt_rng': self.pbt_rng.cpu(),
+            'user_state': self.user_state,
+        }
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        torch.save(ckpt, path)
+
+    def load(self, path):
+        ckpt = torch.load(path, map_location='cpu', weights_only=False)
+        ps, ts = self.policy_states, self.train_states
+        prog = ps.program
+        prog.params.copy_(ckpt['policy_states']['params'])
+        prog.adam_m.copy_(ckpt['train_states']['opt_state']['m'])
+        prog.adam_v.copy_(ckpt['train_states']['opt_state']['v'])
+        prog.adam_step.copy_(ckpt['train_states']['opt_state']['count'])
+        if ts.value_normalizer_state is not None:
+            ts.value_normalizer_state.copy_(ckpt['train_states']['value_normalizer_state'])
+        ts.update_prng_key.copy_(ckpt['train_states']['update_prng_key'])
+        ts.initial_weight_norms = ckpt['train_states']['initial_weight_norms']
+        # re-derive the device segment table from the restored initial norms
+        prog.initial_weight_norms = ts.initial_weight_norms
+        prog.rebuild_segments()
+        self.pbt_rng.copy_(ckpt['pbt_rng'])
+        self.user_state = ckpt['user_state']
+        return self, ckpt['next_update']
+
+    @staticmethod
+    def create(policy, cfg, algo, init_user_state_cb, base_rng, example_obs, example_rnn_states,
+               use_competitive_mmr, device, partitionable=False):
+        """ml/train_state.py:278-304 + _make_policies :439-488 (P = 1)."""
+        ks = K.threefry_split(base_rng, 2, partitionable)          # base_init_rng, pbt_rng
+        base_init, pbt_rng = ks[0].clone(), ks[1].clone()
+        ks = K.threefry_split(base_init, 2, partitionable)         # policy_init_base, train_init_base
+        policy_init_base, train_init_base = ks[0].clone(), ks[1].clone()
+        policy_init = K.threefry_split(policy_init_base, 1, partitionable)[0]
+        train_init = K.threefry_split(train_init_base, 1, partitionable)[0].clone()
+
+        obs_preprocess = policy.obs_preprocess or ObservationsPreprocessNoop.create()
+        obs_state = obs_preprocess.init_state(example_obs, False)
+        pre = obs_preprocess.preprocess(obs_state, example_obs, False)
+        if len(pre) != 1:
+            raise NotImplementedError('exactly one observation tensor is supported '
+                                      '(multi-tensor prefix concat: next)')
+        (ob,) = pre.values()
+        obs_dim = ob[0].numel()
+        prog = PolicyProgram(policy.actor_critic, obs_dim, cfg.actions, device, cfg.compute_dtype)
+        seed_words = policy_init.cpu().numpy().view('uint32')
+        prog.init_params(int(seed_words[0]) ^ (int(seed_words[1]) << 1))
+
+        hyper = algo.init_hyperparams(cfg)
+        tx = algo.make_optimizer(hyper)
+        if cfg.normalize_values:
+            vn = EMANormalizer(decay=hyper.value_normalizer_decay, norm_dtype=torch.float32,
+                               inv_dtype=torch.float32)
+            vn_state = K.ema_state_init(1, device)
+        else:
+            vn, vn_state = None, None
+
+        def apply_fn(variables, *args, train=False, method='rollout', **kw):
+            return getattr(prog, 'apply_' + method)(*args, train=train, **kw)
+
+        ps = PolicyState(
+            apply_fn=apply_fn, rnn_reset_fn=lambda states, dones: states,
+            params=prog.param_tree(), batch_stats={}, obs_preprocess=obs_preprocess,
+            obs_preprocess_state=obs_state, reward_hyper_params=None,
+            get_episode_scores_fn=policy.get_episode_scores or (lambda x: 0.0),
+            episode_score=None, mmr=None, program=prog)
+        ts = PolicyTrainState(
+            value_normalizer=vn, max_advantage_est=EMAEstimate(hyper.max_advantage_est_decay),
+            initial_weight_norms=dict(prog.initial_weight_norms), tx=tx,
+            value_normalizer_state=vn_state, max_advantage_est_state=None, hyper_params=hyper,
+            opt_state={'m': prog.adam_m, 'v': prog.adam_v, 'count': prog.adam_step},
+            scheduler=None, scaler=None, update_prng_key=train_init)
+        return TrainStateManager(policy_states=ps, train_states=ts, pbt_rng=pbt_rng,
+                                 user_state=init_user_state_cb())

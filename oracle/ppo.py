@@ -1,0 +1,210 @@
+"""Oracle (test infrastructure): PPO minibatch loss / gradients / optimiser / update loop.
+
+Restates /root/reference/src/madrona_learn/ppo.py:109-488 (default branch: no
+filter_advantages, no importance sampling, plain critic = DenseLayerCritic, P = 1) on top
+of oracle/nn.py.  optax pieces (PARITY UNPINNED, optax 0.1.9 is not under /root/reference):
+clip_by_global_norm, adam(b1 .9, b2 .999, eps 1e-8), l2_loss = 0.5 d^2, huber_loss(delta 1).
+"""
+import numpy as np
+
+from . import algo_common, layouts, nn, prng
+from .moving_avg import EMANormalizer
+
+
+class PPOCfg:
+    """The hyper-parameters the loss/update read (ml/ppo.py:24-46, ml/cfg.py:68-96)."""
+
+    def __init__(self, buckets, num_epochs=4, minibatch_size=2048, clip_coef=0.2,
+                 value_loss_coef=0.5, entropy_coef=0.01, max_grad_norm=0.5, lr=3e-4,
+                 clip_value_loss=False, huber_value_loss=False, normalize_advantages=True,
+                 normalize_values=False, value_normalizer_decay=0.99999, gamma=0.99,
+                 gae_lambda=0.95, partitionable=False):
+        self.__dict__.update(locals())
+        del self.__dict__['self']
+
+
+def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True):
+    """_ppo_update's loss_fn (ml/ppo.py:129-262) and its gradient w.r.t. params.
+
+    mb: dict with obs [T', M, D], actions [T', M, A] i32, log_probs [T', M, A],
+    advantages/returns/values [T', M, 1], mb_weights [M, 1] (ones on the default branch).
+    Returns dict(loss, action_obj, value_loss, entropy, grads, new_vn_state, aux...).
+    """
+    f = dtype
+    Tp, M = mb['obs'].shape[:2]
+    rows = Tp * M
+    A = len(cfg.buckets)
+    p = nn.cast_tree(params, f)
+    obs = mb['obs'].reshape(rows, -1).astype(f)
+    acts = mb['actions'].reshape(rows, A)
+    old_lp = mb['log_probs'].reshape(rows, A).astype(f)
+    w = np.broadcast_to(mb['mb_weights'].reshape(1, M, 1), (Tp, M, 1)).reshape(rows, 1).astype(f)
+
+    logits, critic, cache = nn.actor_critic_fwd(p, obs)
+    new_lp, ent = nn.action_stats(logits, acts, cfg.buckets)
+
+    # advantages: per-MINIBATCH z-score (ml/ppo.py:134-137 -> ml/algo_common.py:133-140)
+    adv = mb['advantages'].reshape(rows, 1).astype(np.float32)
+    if cfg.normalize_advantages:
+        adv = algo_common.zscore_data(adv)
+    adv = adv.astype(f)
+
+    ratio = np.exp(new_lp - old_lp)                                       # :146-147
+    surr1 = adv * ratio                                                   # :155
+    clipped = np.clip(ratio, 1.0 - cfg.clip_coef, 1.0 + cfg.clip_coef)    # :157-159
+    surr2 = adv * clipped
+    obj = np.minimum(surr1, surr2)                                        # :162
+
+    # value loss, plain critic branch (:186-218)
+    v_new = critic.reshape(rows, 1)
+    returns = mb['returns'].reshape(rows, 1).astype(np.float32)
+    norm = EMANormalizer(cfg.value_normalizer_decay) if cfg.normalize_values else None
+    if norm is None:
+        value_errs = v_new - returns.astype(f)
+        norm_returns = returns.astype(f)
+        new_vn = None
+    else:
+        value_errs = (v_new * f(vn_state['sigma'][0]) + f(vn_state['mu'][0])) - returns.astype(f)
+        new_vn, nr = norm.normalize_and_update_estimates(vn_state, returns)
+        norm_returns = nr.astype(f)
+    v_used = v_new
+    vclip_mask = np.ones_like(v_new)
+    if cfg.clip_value_loss:
+        old_v = mb['values'].reshape(rows, 1).astype(f)
+        lo, hi = old_v - cfg.clip_coef, old_v + cfg.clip_coef
+        v_used = np.clip(v_new, lo, hi)
+        vclip_mask = ((v_new >= lo) & (v_new <= hi)).astype(f)
+    d = v_used - norm_returns
+    if cfg.huber_value_loss:
+        q = np.minimum(np.abs(d), 1.0)
+        vloss = 0.5 * q * q + (np.abs(d) - q)
+        dvloss = np.clip(d, -1.0, 1.0)
+    else:
+        vloss = 0.5 * d * d
+        dvloss = d
+
+    action_obj_avg = np.mean(w * obj)                                     # :220-224 (one group)
+    value_loss = cfg.value_loss_coef * np.mean(w * vloss)                 # :227-228, :247
+    entropy_avg = cfg.entropy_coef * np.mean(w * ent)                     # :231-239
+    loss = -action_obj_avg + value_loss - entropy_avg                     # :245-252
+
+    out = dict(loss=f(loss), action_obj=obj, value_losses=vloss, entropies=ent,
+               value_errs=value_errs, new_vn_state=new_vn, logits=logits, critic=critic,
+               new_log_probs=new_lp)
+    if not want_grads:
+        return out
+
+    # d loss / d new_lp: min() picks surr1 unless the clipped branch is strictly smaller
+    pick1 = (surr1 <= surr2)
+    inside = (ratio >= 1.0 - cfg.clip_coef) & (ratio <= 1.0 + cfg.clip_coef)
+    dobj_dratio = np.where(pick1 | inside, adv, 0.0)
+    dlogp = -(w * dobj_dratio * ratio) / (rows * A)
+    dent = -(cfg.entropy_coef * w) / (rows * A) * np.ones_like(ent)
+    dlogits = nn.action_stats_bwd(logits, acts, cfg.buckets, dlogp, dent)
+    dcritic = cfg.value_loss_coef * w * dvloss * vclip_mask / rows
+    out['grads'] = nn.actor_critic_bwd(p, cache, dlogits, dcritic)
+    out['dlogits'] = dlogits
+    out['dcritic'] = dcritic
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# optimiser (ml/ppo.py:84-90, 283-338)
+# ---------------------------------------------------------------------------------------
+def adam_init(params):
+    z = lambda x: np.zeros_like(x)
+    return dict(m=nn.tree_map(z, params), v=nn.tree_map(z, params), t=0)
+
+
+def global_norm(grads):
+    return np.sqrt(sum(float(np.sum(np.square(g.astype(np.float64)))) for g in nn.tree_leaves(grads)))
+
+
+def optimizer_step(params, grads, opt, cfg, init_norms, dtype=np.float32):
+    """clip_by_global_norm -> adam -> apply_updates -> kernel re-projection -> LN renorm."""
+    f = dtype
+    gn = global_norm(grads)
+    scale = 1.0 if gn < cfg.max_grad_norm else cfg.max_grad_norm / gn
+    t = opt['t'] + 1
+    b1, b2, eps = 0.9, 0.999, 1e-8
+    bc1, bc2 = 1.0 - b1 ** t, 1.0 - b2 ** t
+
+    def upd(p, g, m, v):
+        g = g.astype(f) * f(scale)
+        m2 = f(b1) * m + f(1 - b1) * g
+        v2 = f(b2) * v + f(1 - b2) * g * g
+        u = -f(cfg.lr) * (m2 / f(bc1)) / (np.sqrt(v2 / f(bc2)) + f(eps))
+        return (p + u).astype(f), m2.astype(f), v2.astype(f)
+
+    trip = nn.tree_map(upd, params, grads, opt['m'], opt['v'])
+
+    def pick(i):
+        def rec(t3):
+            if isinstance(t3, dict):
+                return {k: rec(v) for k, v in t3.items()}
+            if isinstance(t3, list):
+                return [rec(v) for v in t3]
+            return t3[i]
+        return rec(trip)
+    new_p, new_m, new_v = pick(0), pick(1), pick(2)
+
+    # kernel re-projection to the initial L2 norm for every backbone 'kernel' (:303-310);
+    # top-level actor / critic are excluded (ml/train_state.py:422-423)
+    for i, lyr in enumerate(new_p['mlp']):
+        k = lyr['kernel']
+        lyr['kernel'] = (f(init_norms['mlp'][i]) * k / np.sqrt(np.sum(np.square(k), dtype=np.float64))).astype(f)
+        # LayerNorm renorm (:312-338): factor = sqrt(F / (b.b + s.s))
+        s, b = lyr['scale'], lyr['bias']
+        fac = np.sqrt(s.shape[-1] / (np.dot(b.astype(np.float64), b) + np.dot(s.astype(np.float64), s)))
+        lyr['scale'] = (fac * s).astype(f)
+        lyr['bias'] = (fac * b).astype(f)
+    for i, lyr in enumerate(new_p.get('lstm', [])):
+        for kk in ('wi', 'wh'):
+            k = lyr[kk]
+            lyr[kk] = (f(init_norms['lstm'][i][kk]) * k / np.sqrt(np.sum(np.square(k), dtype=np.float64))).astype(f)
+    return new_p, dict(m=new_m, v=new_v, t=t), gn
+
+
+def initial_weight_norms(params):
+    """ml/train_state.py:413-423."""
+    n = {'mlp': [float(np.sqrt(np.sum(np.square(l['kernel'].astype(np.float64))))) for l in params['mlp']]}
+    if 'lstm' in params:
+        n['lstm'] = [{k: float(np.sqrt(np.sum(np.square(l[k].astype(np.float64))))) for k in ('wi', 'wh')}
+                     for l in params['lstm']]
+    return n
+
+
+# ---------------------------------------------------------------------------------------
+# the update loop (ml/ppo.py:366-488, default branch)
+# ---------------------------------------------------------------------------------------
+def ppo_update(params, opt, init_norms, rollout, cfg, update_key, vn_state=None,
+               dtype=np.float32, perms=None):
+    """rollout: dict name -> [J, T', ...] training layout (ml/rollouts.py:788-804), P=1.
+    Returns (params, opt, new_key, vn_state, last_minibatch_outputs, perms)."""
+    J = rollout['dones'].shape[0]
+    M = cfg.minibatch_size
+    assert J % M == 0                                                     # :439
+    traj_w = np.ones((J, 1), np.float32)                                  # :443
+    key = np.asarray(update_key, np.uint32)
+    used = []
+    last = None
+    for e in range(cfg.num_epochs):
+        if perms is None:
+            ks = prng.split(key, 2, cfg.partitionable)                    # gen_update_rnd
+            rnd, key = ks[0], ks[1]
+            inds = prng.permutation(rnd, J, cfg.partitionable)            # :451
+        else:
+            inds = perms[e]
+        used.append(inds)
+        for i in range(J // M):
+            mb_inds = inds[i * M:(i + 1) * M]                             # :464-466
+            mb = layouts.minibatch(rollout, mb_inds)
+            mb['mb_weights'] = traj_w[mb_inds]
+            out = ppo_loss(params, mb, cfg, vn_state, dtype=dtype)
+            if out['new_vn_state'] is not None:
+                vn_state = out['new_vn_state']
+            grads = nn.cast_tree(out['grads'], dtype)
+            params, opt, gn = optimizer_step(params, grads, opt, cfg, init_norms, dtype)
+            out['grad_norm'] = gn
+            last = out
+    return params, opt, key, vn_state, last, np.stack(used)

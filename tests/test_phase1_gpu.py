@@ -65,7 +65,7 @@ def test_gae_value_denorm_and_metrics(mlb):
     T, N = 32, 4096
     r, v, d, b = _mk(T, N, seed=3)
     mu, sigma = np.float32(0.7), np.float32(2.5)
-    vn = _dev(np.array([mu, sigma], np.float32))
+    vn = _dev(np.array([mu, 1 / sigma, sigma, 0, 0, 0], np.float32))
     mbuf = torch.zeros(80, dtype=torch.uint8, device=DEV)
     adv, ret = K.gae(_dev(r), _dev(v), _dev(d), _dev(b), 0.99, 0.95, vn_mu_sigma=vn, metrics=mbuf)
     v_un = (v * sigma + mu).astype(np.float32)

@@ -34,7 +34,8 @@ def time_op(fn, flush, reps=7, warm=3):
         flush.add_(1)                      # evict L2 (256 MiB > 126 MB)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        e0.record()
+        torch.cuda._sleep(400000)          # keep the GPU busy while the host enqueues, so
+        e0.record()                        # e0->e1 brackets device time only (no launch gap)
         fn()
         e1.record()
         torch.cuda.synchronize()
