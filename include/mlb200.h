@@ -96,8 +96,13 @@ int mlb_traj_moments_f32(void* stream, const float* x, int T, long long N, int C
 /* Per-minibatch moments for ALL (epoch, minibatch) pairs of an update at once (SURVEY    */
 /* App. C.1): perm i32 [E, J] trajectory ids; minibatch k of epoch e = perm[e, k*M:(k+1)*M]*/
 /* out f32 [E*J/M][4] = {mean, rstd(var floor), var, n} with n = M*T'.                    */
+/* raw_out (may be NULL): f64 [E*J/M][2] = {sum, sumsq} -- what a data-parallel run        */
+/* all-reduces (SUM) across ranks before mlb_moments_finalize_f32 (count = global n).       */
 int mlb_mb_moments_f32(void* stream, const double* traj_moments, const int32_t* perm,
-                       int E, long long J, long long M, int Tp, float var_floor, float* out);
+                       int E, long long J, long long M, int Tp, float var_floor, float* out,
+                       double* raw_out);
+int mlb_moments_finalize_f32(void* stream, const double* raw, int K, double count,
+                             float var_floor, float* out);
 
 /* ------------------------------------------------------------------------------------ */
 /* K3: EMA normaliser (ml/moving_avg.py:48-198).  State: f32 [5][dim] rows = mu,           */

@@ -45,7 +45,8 @@ SIGNATURES = {
     'mlb_zscore_f32': (c_int, [P, P, P, c_ll, P, P, c_size_t]),
     'mlb_metric_f32': (c_int, [P, P, c_ll, P, P, c_size_t]),
     'mlb_traj_moments_f32': (c_int, [P, P, c_int, c_ll, c_int, P]),
-    'mlb_mb_moments_f32': (c_int, [P, P, P, c_int, c_ll, c_ll, c_int, c_float, P]),
+    'mlb_mb_moments_f32': (c_int, [P, P, P, c_int, c_ll, c_ll, c_int, c_float, P, P]),
+    'mlb_moments_finalize_f32': (c_int, [P, P, c_int, ctypes.c_double, c_float, P]),
     'mlb_ema_update_f32': (c_int, [P, P, c_int, P, P, c_float, c_float]),
     'mlb_ema_scan_f32': (c_int, [P, P, P, c_int, c_float, c_float, P]),
     'mlb_ema_normalize_f32': (c_int, [P, P, c_int, P, P, c_ll]),
@@ -149,8 +150,13 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
+CALLS = 0     # number of C-ABI enqueue calls made by this process (bench.py's gpu_launches)
+
+
 def call(name, *args):
     """Invoke an int-returning entry point on the current torch stream and check its code."""
+    global CALLS
+    CALLS += 1
     fn = getattr(lib(), name)
     rc = fn(stream_ptr(), *args)
     check(rc, name)

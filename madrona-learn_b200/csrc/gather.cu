@@ -57,16 +57,16 @@ int gather_dispatch(cudaStream_t st, const void* store, const int32_t* idx, void
 
 MLB_API int mlb_mb_gather(void* stream, const void* store, const int32_t* idx, void* out, int C,
                           int Tp, long long B, long long M, long long row_bytes) {
-    MLB_REQUIRE(store && idx && out && C > 0 && Tp > 0 && B > 0 && M >= 0 && row_bytes > 0);
-    MLB_REQUIRE(Tp <= 65535);
     if (M == 0) return MLB_OK;
+    MLB_REQUIRE(store && idx && out && C > 0 && Tp > 0 && B > 0 && M > 0 && row_bytes > 0);
+    MLB_REQUIRE(Tp <= 65535);
     return gather_dispatch(mlb_stream(stream), store, idx, out, Tp, B, M, row_bytes);
 }
 
 MLB_API int mlb_mb_gather_rnn(void* stream, const void* store, const int32_t* idx, void* out,
                               int C, long long B, long long M, long long row_bytes) {
-    MLB_REQUIRE(store && idx && out && C > 0 && B > 0 && M >= 0 && row_bytes > 0);
     if (M == 0) return MLB_OK;
+    MLB_REQUIRE(store && idx && out && C > 0 && B > 0 && M > 0 && row_bytes > 0);
     // [C, B, row] is the Tp == 1 case of the step store: out[m] = store[j/B, j%B] = flat[j]
     return gather_dispatch(mlb_stream(stream), store, idx, out, 1, B, M, row_bytes);
 }

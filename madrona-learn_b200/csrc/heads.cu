@@ -154,7 +154,7 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
                 const float p = expf(l[off + j] - mxl) * inv_se;        // jax.nn.softmax
                 H -= p * lp;
             }
-            const int act = actions[row * L.A + i];
+            const int act = min(max(actions[row * L.A + i], 0), nb - 1);   // never index outside the bucket
             const float lp_new = l[off + act] - lse;
             const float ratio = expf(lp_new - old_lp[row * L.A + i]);   // ml/ppo.py:146-147
             const float surr1 = a * ratio;

@@ -130,7 +130,8 @@ traj_moments_kernel(const float* __restrict__ x, int T, long long N, int C,
 // grid = E * (J/M) blocks; block k reduces the M trajectories of minibatch k.
 __global__ void __launch_bounds__(256)
 mb_moments_kernel(const double* __restrict__ tm, const int32_t* __restrict__ perm,
-                  long long J, long long M, int Tp, float var_floor, float* __restrict__ out) {
+                  long long J, long long M, int Tp, float var_floor, float* __restrict__ out,
+                  double* __restrict__ raw) {
     const long long nmb = J / M;
     const long long e = blockIdx.x / nmb, k = blockIdx.x % nmb;
     const int32_t* idx = perm + e * J + k * M;
@@ -143,14 +144,31 @@ mb_moments_kernel(const double* __restrict__ tm, const int32_t* __restrict__ per
     s = block_sum_d(s, smd);
     ss = block_sum_d(ss, smd);
     if (threadIdx.x == 0) {
-        const double count = (double)M * (double)Tp;
-        const double mean = s / count;
-        double m2 = ss - s * mean;
-        if (m2 < 0.0) m2 = 0.0;
-        const float var = (float)(m2 / count);
-        float* o = out + 4ll * blockIdx.x;
-        o[0] = (float)mean; o[1] = rsqrtf(fmaxf(var, var_floor)); o[2] = var; o[3] = (float)count;
+        if (raw) { raw[2ll * blockIdx.x] = s; raw[2ll * blockIdx.x + 1] = ss; }
+        if (out) {
+            const double count = (double)M * (double)Tp;
+            const double mean = s / count;
+            double m2 = ss - s * mean;
+            if (m2 < 0.0) m2 = 0.0;
+            const float var = (float)(m2 / count);
+            float* o = out + 4ll * blockIdx.x;
+            o[0] = (float)mean; o[1] = rsqrtf(fmaxf(var, var_floor)); o[2] = var; o[3] = (float)count;
+        }
     }
+}
+
+// raw [K][2] = {sum, sumsq} (already summed over ranks) -> out [K][4]
+__global__ void moments_finalize_kernel(const double* __restrict__ raw, int K, double count,
+                                        float var_floor, float* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const double s = raw[2 * k], ss = raw[2 * k + 1];
+    const double mean = s / count;
+    double m2 = ss - s * mean;
+    if (m2 < 0.0) m2 = 0.0;
+    const float var = (float)(m2 / count);
+    float* o = out + 4ll * k;
+    o[0] = (float)mean; o[1] = rsqrtf(fmaxf(var, var_floor)); o[2] = var; o[3] = (float)count;
 }
 
 // EMANormalizer.update_estimates (ml/moving_avg.py:131-181), one thread per feature.
@@ -299,10 +317,18 @@ MLB_API int mlb_traj_moments_f32(void* stream, const float* x, int T, long long 
 
 MLB_API int mlb_mb_moments_f32(void* stream, const double* traj_moments, const int32_t* perm,
                                int E, long long J, long long M, int Tp, float var_floor,
-                               float* out) {
-    MLB_REQUIRE(traj_moments && perm && out && E > 0 && J > 0 && M > 0 && J % M == 0 && Tp > 0);
+                               float* out, double* raw_out) {
+    MLB_REQUIRE(traj_moments && perm && (out || raw_out) && E > 0 && J > 0 && M > 0 && J % M == 0 && Tp > 0);
     const unsigned g = (unsigned)(E * (J / M));
-    mb_moments_kernel<<<g, 256, 0, mlb_stream(stream)>>>(traj_moments, perm, J, M, Tp, var_floor, out);
+    mb_moments_kernel<<<g, 256, 0, mlb_stream(stream)>>>(traj_moments, perm, J, M, Tp, var_floor, out, raw_out);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+MLB_API int mlb_moments_finalize_f32(void* stream, const double* raw, int K, double count,
+                                     float var_floor, float* out) {
+    MLB_REQUIRE(raw && out && K > 0 && count > 0);
+    moments_finalize_kernel<<<mlb_cdiv(K, 128), 128, 0, mlb_stream(stream)>>>(raw, K, count, var_floor, out);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }

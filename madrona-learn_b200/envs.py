@@ -36,3 +36,43 @@ class SyntheticVectorEnv:
 
     def sim_fns(self):
         return {'init': self.init, 'step': self.step}
+
+
+class HostTraceEnv:
+    """sim_fns whose observations / rewards / dones live in PINNED HOST memory and are
+    streamed to the device step by step (cudaMemcpyAsync on the compute stream, capturable
+    in the update graph).  This is the end-to-end arm of bench.py: the simulator is on the
+    host side of the boundary, so every update moves T*N*(4D+5) bytes host->device."""
+
+    def __init__(self, num_worlds, steps, obs_dim=64, seed=0, p_done=1.0 / 64, device='cuda:0',
+                 action_key='act', obs_key='obs'):
+        self.N, self.T, self.D = int(num_worlds), int(steps), int(obs_dim)
+        self.device = torch.device(device)
+        self.action_key, self.obs_key = action_key, obs_key
+        g = torch.Generator().manual_seed(int(seed))
+        pin = lambda t: t.pin_memory()
+        self.h_obs = pin(torch.randn(self.T + 1, self.N, self.D, generator=g))
+        self.h_rew = pin(torch.randn(self.T, self.N, 1, generator=g) * 0.1)
+        self.h_done = pin((torch.rand(self.T, self.N, 1, generator=g) < p_done).to(torch.uint8))
+        self.obs = torch.empty(self.N, self.D, dtype=torch.float32, device=self.device)
+        self.rewards = torch.empty(self.N, 1, dtype=torch.float32, device=self.device)
+        self.dones = torch.empty(self.N, 1, dtype=torch.uint8, device=self.device)
+        self.t = 0
+        self.h2d_bytes_per_update = self.T * self.N * (4 * self.D + 4 + 1)
+
+    def init(self):
+        self.obs.copy_(self.h_obs[0], non_blocking=True)
+        self.t = 0
+        return {'state': None, 'obs': {self.obs_key: self.obs}}
+
+    def step(self, step_input):
+        t = self.t % self.T
+        self.rewards.copy_(self.h_rew[t], non_blocking=True)
+        self.dones.copy_(self.h_done[t], non_blocking=True)
+        self.obs.copy_(self.h_obs[t + 1], non_blocking=True)
+        self.t += 1
+        return {'state': None, 'obs': {self.obs_key: self.obs}, 'rewards': self.rewards,
+                'dones': self.dones}
+
+    def sim_fns(self):
+        return {'init': self.init, 'step': self.step}

@@ -118,11 +118,17 @@ def traj_moments(x, C, out=None):
     return out
 
 
-def mb_moments(tm, perm, M, Tp, var_floor=1e-5, out=None):
+def mb_moments(tm, perm, M, Tp, var_floor=1e-5, out=None, raw_out=None):
     E, J = perm.shape
-    if out is None:
+    if out is None and raw_out is None:
         out = torch.empty((E * (J // M), 4), dtype=torch.float32, device=perm.device)
     call('mlb_mb_moments_f32', ptr(tm), ptr(perm), c_int(E), c_ll(J), c_ll(M), c_int(Tp),
+         c_float(var_floor), ptr(out), ptr(raw_out))
+    return out
+
+
+def moments_finalize(raw, count, var_floor, out):
+    call('mlb_moments_finalize_f32', ptr(raw), c_int(raw.shape[0]), ctypes.c_double(count),
          c_float(var_floor), ptr(out))
     return out
 

@@ -108,6 +108,7 @@ class _PPOWorkspace:
         self.mb_adv = e(E * self.nmb, 4)
         self.mb_ret = e(E * self.nmb, 4)
         self.vn_params = e(E * self.nmb, 4)
+        self.raw = torch.zeros(2 * E * self.nmb, 2, dtype=torch.float64, device=dev)
         self.mb = {
             'obs': e(Tp, M, prog.obs_dim), 'actions': e(Tp, M, prog.A, dtype=torch.int32),
             'log_probs': e(Tp, M, prog.A), 'advantages': e(Tp, M, 1), 'returns': e(Tp, M, 1),
@@ -145,17 +146,30 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
     # per-minibatch statistics for ALL minibatches of the update (App. C.1)
     score_key = 'advantages' if cfg.compute_advantages else 'returns'
     normalize_scores = cfg.normalize_advantages if cfg.compute_advantages else cfg.normalize_returns
-    if normalize_scores:
-        K.traj_moments(st[score_key].view(T, N), C, ws.tm_adv)
-        K.mb_moments(ws.tm_adv, ws.perm, M, Tp, 1e-5, ws.mb_adv)
-        if dist_ctx is not None:
-            dist_ctx.allreduce_moments(ws.mb_adv, 1e-5)
     vn = train_state.value_normalizer
+    if dist_ctx is None:
+        if normalize_scores:
+            K.traj_moments(st[score_key].view(T, N), C, ws.tm_adv)
+            K.mb_moments(ws.tm_adv, ws.perm, M, Tp, 1e-5, ws.mb_adv)
+        if vn is not None:
+            K.traj_moments(st['returns'].view(T, N), C, ws.tm_ret)
+            K.mb_moments(ws.tm_ret, ws.perm, M, Tp, 0.0, ws.mb_ret)
+    else:
+        # raw (sum, sumsq) of every minibatch -> ONE all-reduce for the whole update
+        Kmb = E * nmb
+        if normalize_scores:
+            K.traj_moments(st[score_key].view(T, N), C, ws.tm_adv)
+            K.mb_moments(ws.tm_adv, ws.perm, M, Tp, 1e-5, None, ws.raw[:Kmb])
+        if vn is not None:
+            K.traj_moments(st['returns'].view(T, N), C, ws.tm_ret)
+            K.mb_moments(ws.tm_ret, ws.perm, M, Tp, 0.0, None, ws.raw[Kmb:])
+        dist_ctx.allreduce_raw_moments(ws.raw)
+        cnt = float(ws.rows_global)
+        if normalize_scores:
+            K.moments_finalize(ws.raw[:Kmb], cnt, 1e-5, ws.mb_adv)
+        if vn is not None:
+            K.moments_finalize(ws.raw[Kmb:], cnt, 0.0, ws.mb_ret)
     if vn is not None:
-        K.traj_moments(st['returns'].view(T, N), C, ws.tm_ret)
-        K.mb_moments(ws.tm_ret, ws.perm, M, Tp, 0.0, ws.mb_ret)
-        if dist_ctx is not None:
-            dist_ctx.allreduce_moments(ws.mb_ret, 0.0)
         K.ema_scan(train_state.value_normalizer_state, ws.mb_ret, vn.decay, vn.eps, ws.vn_params)
 
     flags = (1 if cfg.algo.clip_value_loss else 0) | (2 if cfg.algo.huber_value_loss else 0)

@@ -187,8 +187,9 @@ def test_ppo_loss_and_full_backward(mlb, clipv, huber, vn):
     obj_scale = (ctypes.c_float * A)(*[1.0 / (rows * A)] * A)
     ent_scale = (ctypes.c_float * A)(*[cfg.entropy_coef / (rows * A)] * A)
     flags = (1 if clipv else 0) | (2 if huber else 0)
-    call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(_dev(mb['actions'])), ptr(_dev(mb['log_probs'])),
-         ptr(_dev(mb['advantages'])), ptr(_dev(mb['returns'])), ptr(_dev(mb['values'])), ptr(None),
+    dv = {k: _dev(mb[k]) for k in ('actions', 'log_probs', 'advantages', 'returns', 'values')}  # keep alive
+    call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(dv['actions']), ptr(dv['log_probs']),
+         ptr(dv['advantages']), ptr(dv['returns']), ptr(dv['values']), ptr(None),
          ptr(adv_mr), ptr(vnp), prog._buckets_c, obj_scale, ent_scale, c_int(A), c_ll(rows), c_ll(M),
          c_float(cfg.clip_coef), c_float(cfg.value_loss_coef), c_int(flags), ptr(tw['dhead']),
          ptr(tw['stats_out']), ptr(tw['loss_ws']), c_size_t(tw['loss_ws'].numel()))
