@@ -50,6 +50,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_flag, self.proc = gpu, [], False, None
+        self.t0, self.t1 = None, None          # the timed window (host clock)
 
     def run(self):
         try:
@@ -57,7 +58,7 @@ class ClockSampler(threading.Thread):
                 ['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                  '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(',')])
+                self.rows.append([time.time()] + [x.strip() for x in line.split(',')])
                 if self.stop_flag:
                     break
         except Exception:
@@ -68,7 +69,10 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        rows = [r[1:] for r in self.rows if self.t0 is None or self.t0 <= r[0] <= (self.t1 or 1e30)]
+        if not rows:                            # window shorter than one sample: take all
+            rows = [r[1:] for r in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -104,7 +108,9 @@ def make_policy(m):
 def timed_updates(torch, mgr, steps, warmup, dist_ctx, dev, after_step=None, sampler=None):
     """W untimed + exactly K timed update_iters, barrier + synchronize on both sides, CUDA
     events on the launching stream, max over ranks.  Returns seconds."""
-    for _ in range(warmup):
+    if sampler:
+        sampler.start()                        # nvidia-smi needs ~1 s to come up: start early,
+    for _ in range(warmup):                    # keep only samples inside the timed window
         mgr.update_iter()
         if after_step:
             after_step()
@@ -113,7 +119,7 @@ def timed_updates(torch, mgr, steps, warmup, dist_ctx, dev, after_step=None, sam
         dist_ctx.barrier()
     torch.cuda.synchronize()
     if sampler:
-        sampler.start()
+        sampler.t0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -125,6 +131,8 @@ def timed_updates(torch, mgr, steps, warmup, dist_ctx, dev, after_step=None, sam
     if dist_ctx:
         dist_ctx.barrier()
     torch.cuda.synchronize()
+    if sampler:
+        sampler.t1 = time.time()
     sec = e0.elapsed_time(e1) * 1e-3
     if dist_ctx:
         sec = dist_ctx.max_over_ranks(sec, dev)
@@ -171,8 +179,8 @@ def cpu_reference_arm(steps, warmup, worlds):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=60)
+    ap.add_argument('--warmup', type=int, default=30)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -9,7 +9,7 @@ from .actor_critic import (ActorCritic, Backbone, BackboneEncoder, BackboneSepar
                            BackboneShared, RecurrentBackboneEncoder)
 from .cfg import (ContinuousActionsConfig, DiscreteActionsConfig, EvalConfig, ParamExplore,  # noqa: F401
                   PBTConfig, TrainConfig)
-from .envs import SyntheticVectorEnv  # noqa: F401
+from .envs import HostTraceEnv, SyntheticVectorEnv  # noqa: F401
 from .moving_avg import EMANormalizer  # noqa: F401
 from .observations import ObservationsCaster, ObservationsEMANormalizer  # noqa: F401
 from .policy import Policy  # noqa: F401
