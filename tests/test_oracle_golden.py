@@ -1,0 +1,134 @@
+"""CPU: the oracle restatement vs golden outputs produced by the REFERENCE'S OWN SOURCE run
+under oracle/jax_shim (tests/golden/make_golden.py), plus the known-answer vectors we hold
+for the third-party PRNG.  This is what pins the oracle (DESIGN.md "Oracle")."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import algo_common as oac
+from oracle import cgae, dists as odists, layouts, metrics as omet, nn as onn, prng
+from oracle.moving_avg import EMANormalizer
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+CASES = ['small', 'chunks', 'ragged', 'nodone', 'alldone', 'one']
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_gae_returns_zscore_match_reference(name):
+    z = np.load(os.path.join(G, 'algo_common.npz'))
+    g = lambda k: z[f'{name}/{k}']
+    gamma, lam = g('cfg')
+    adv = oac.compute_advantages(gamma, lam, g('r'), g('v'), g('d'), g('b'))
+    np.testing.assert_array_equal(adv, g('adv'))                       # bit-exact
+    np.testing.assert_array_equal(oac.compute_returns(gamma, g('r'), g('d'), g('b')), g('ret'))
+    np.testing.assert_allclose(oac.zscore_data(g('adv')), g('z'), rtol=1e-5, atol=1e-6)
+    # the C restatement agrees bit-for-bit too
+    T = g('r').shape[0] * g('r').shape[1]
+    a2, _ = cgae.gae(g('r').reshape(T, -1), g('v').reshape(T, -1), g('d').reshape(T, -1),
+                     g('b').reshape(-1), gamma, lam)
+    np.testing.assert_array_equal(a2.reshape(g('adv').shape), g('adv'))
+
+
+def test_ema_normalizer_matches_reference():
+    z = np.load(os.path.join(G, 'ema.npz'))
+    vals, hist = z['vals'], z['hist']
+    iters, batch, dims = vals.shape
+    sub = 8
+    norm = EMANormalizer(0.999)
+    est = norm.init_estimates(dims)
+    for i in range(iters):
+        stats = norm.init_input_stats(est)
+        for j in range(sub):
+            stats = norm.update_input_stats(stats, j, vals[i].reshape(sub, batch // sub, dims)[j])
+        est = norm.update_estimates(est, stats)
+        got = np.concatenate([est[k] for k in ('mu', 'inv_sigma', 'sigma', 'mu_biased', 'sigma_sq_biased')] +
+                             [stats[0], stats[1]])
+        np.testing.assert_allclose(got, hist[i], rtol=2e-5, atol=1e-6)
+    assert est['N'] == z['N']
+    np.testing.assert_allclose(norm.invert(est, vals[5]), z['inverted'], rtol=1e-5)
+    est2, normed = norm.normalize_and_update_estimates(est, vals[3])
+    np.testing.assert_allclose(normed, z['normalized'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(est2['mu'], z['est2_mu'], rtol=2e-5)
+    np.testing.assert_allclose(est2['inv_sigma'], z['est2_inv_sigma'], rtol=2e-5)
+
+
+def test_value_normalizer_recurrence_matches_reference():
+    z = np.load(os.path.join(G, 'ema_value_norm.npz'))
+    norm = EMANormalizer(0.99999)
+    e = norm.init_estimates(1)
+    for i in range(z['rets'].shape[0]):
+        e, nr = norm.normalize_and_update_estimates(e, z['rets'][i])
+        got = [e['mu'][0], e['inv_sigma'][0], e['sigma'][0], e['mu_biased'][0], e['sigma_sq_biased'][0]]
+        np.testing.assert_allclose(got, z['hist'][i], rtol=3e-5, atol=1e-7)
+    np.testing.assert_allclose(nr, z['last_normalized'], rtol=1e-4, atol=1e-5)
+
+
+def test_metric_matches_reference():
+    z = np.load(os.path.join(G, 'metric.npz'))
+    pack = lambda m: np.array([m['mean'], m['m2'], m['min'], m['max'], m['count']], np.float64)
+    m1, m2 = omet.metric_from_data(z['x1']), omet.metric_from_data(z['x2'])
+    np.testing.assert_allclose(pack(m1), z['m1'], rtol=1e-5)
+    np.testing.assert_allclose(pack(m2), z['m2'], rtol=1e-5)
+    np.testing.assert_allclose(pack(omet.metric_merge(m1, m2)), z['merged'], rtol=1e-5)
+
+
+def test_action_stats_match_reference():
+    z = np.load(os.path.join(G, 'dists.npz'))
+    buckets = list(z['buckets'])
+    lp, ent = onn.action_stats(z['logits'].astype(np.float64), z['actions'], buckets)
+    np.testing.assert_allclose(lp, z['log_probs'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ent, z['entropies'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(onn.best_actions(z['logits'], buckets), z['best'])
+
+
+def test_twohot_matches_reference():
+    z = np.load(os.path.join(G, 'twohot.npz'))
+    np.testing.assert_allclose(odists.twohot_mean(z['logits']), z['mean'], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(odists.twohot_loss(z['logits'], z['targets']), z['loss'], rtol=1e-5)
+
+
+def test_minibatch_relayout_matches_reference():
+    z = np.load(os.path.join(G, 'minibatch.npz'))
+    idx = z['idx']
+    for k in ('obs', 'rewards'):
+        store = z[f'store_{k}']
+        ref = z[f'mb_{k}']
+        np.testing.assert_array_equal(layouts.minibatch({'x': layouts.reorder_seq_data(store)[0]}, idx)['x'], ref)
+        np.testing.assert_array_equal(layouts.minibatch_from_store(store, idx), ref)     # fused path
+    np.testing.assert_array_equal(layouts.reorder_rnn_data(z['rnn'])[0][idx], z['mb_rnn_start_states'])
+
+
+def test_reorder_chunks_match_reference_and_roundtrip():
+    z = np.load(os.path.join(G, 'reorder_chunks.npz'))
+    for i in range(4):
+        a = z[f'v{i}_in']
+        P, C = 6, 4
+        B = a.size // C + P - 1
+        tp, ts = layouts.compute_reorder_chunks(a, P, C, B)
+        np.testing.assert_array_equal(tp, z[f'v{i}_to_policy'])
+        np.testing.assert_array_equal(ts, z[f'v{i}_to_sim'])
+        # the property the reference's own test asserts (tests/test_rollouts.py:36-56)
+        pb = np.where(tp < a.size, a[np.clip(tp, 0, a.size - 1)], -1)
+        np.testing.assert_array_equal(pb.reshape(-1)[ts], a)
+
+
+def test_threefry_known_answers():
+    kat = json.load(open(os.path.join(G, 'threefry_kat.json')))
+    for v in kat['threefry2x32']:
+        y0, y1 = prng.threefry2x32(v['key'][0], v['key'][1], v['ctr'][0], v['ctr'][1])
+        assert [int(y0), int(y1)] == v['out']
+    np.testing.assert_array_equal(prng.split(prng.key(0)), kat['split_prngkey0'])
+
+
+def test_permutation_properties():
+    for part in (False, True):
+        for n in (1, 2, 17, 1625, 1626, 5000):
+            p = prng.permutation(prng.key(n), n, part)
+            assert sorted(p.tolist()) == list(range(n))
+        a = prng.permutation(prng.key(3), 100, part)
+        b = prng.permutation(prng.key(4), 100, part)
+        assert not np.array_equal(a, b)
+    assert prng.shuffle_rounds(1625) == 1 and prng.shuffle_rounds(1626) == 2
+    assert prng.shuffle_rounds(8192) == 2 and prng.shuffle_rounds(1 << 20) == 2
