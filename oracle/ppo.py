@@ -23,7 +23,8 @@ class PPOCfg:
         del self.__dict__['self']
 
 
-def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True):
+def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, adv_stats=None,
+             new_vn_state=None):
     """_ppo_update's loss_fn (ml/ppo.py:129-262) and its gradient w.r.t. params.
 
     mb: dict with obs [T', M, D], actions [T', M, A] i32, log_probs [T', M, A],
@@ -46,7 +47,10 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True):
     # advantages: per-MINIBATCH z-score (ml/ppo.py:134-137 -> ml/algo_common.py:133-140)
     adv = mb['advantages'].reshape(rows, 1).astype(np.float32)
     if cfg.normalize_advantages:
-        adv = algo_common.zscore_data(adv)
+        if adv_stats is None:
+            adv = algo_common.zscore_data(adv)
+        else:       # data-parallel: (mean, rstd) of the GLOBAL minibatch, computed elsewhere
+            adv = ((adv - np.float32(adv_stats[0])) * np.float32(adv_stats[1])).astype(np.float32)
     adv = adv.astype(f)
 
     ratio = np.exp(new_lp - old_lp)                                       # :146-147
@@ -65,7 +69,10 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True):
         new_vn = None
     else:
         value_errs = (v_new * f(vn_state['sigma'][0]) + f(vn_state['mu'][0])) - returns.astype(f)
-        new_vn, nr = norm.normalize_and_update_estimates(vn_state, returns)
+        if new_vn_state is None:
+            new_vn, nr = norm.normalize_and_update_estimates(vn_state, returns)
+        else:       # data-parallel: the EMA was advanced with the GLOBAL minibatch statistics
+            new_vn, nr = new_vn_state, norm.normalize(new_vn_state, returns)
         norm_returns = nr.astype(f)
     v_used = v_new
     vclip_mask = np.ones_like(v_new)
