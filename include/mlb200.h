@@ -174,6 +174,29 @@ int mlb_ln_relu_bwd_f32(void* stream, const float* dy, const float* z, const flo
                         const float* scale, const float* bias, float* dz, float* dscale,
                         float* dbias, long long rows, int H);
 
+int mlb_ln_relu_fwd_bf16(void* stream, const float* z, const float* scale, const float* bias,
+                         void* y_bf16, float* stats, long long rows, int H);
+int mlb_ln_relu_bwd_bf16(void* stream, const void* dy_bf16, const float* z, const float* stats,
+                         const float* scale, const float* bias, void* dz_bf16, float* dscale,
+                         float* dbias, long long rows, int H);
+
+/* ------------------------------------------------------------------------------------ */
+/* K6/K9 (tensor-core path, compute_dtype=bfloat16): tcgen05 / TMEM / TMA GEMM.           */
+/* C[M,N] (+)= A * B^T, bf16 operands, fp32 accumulation.                                 */
+/*   a_mn == 0: A row-major [M, K] (lda);  a_mn == 1: A stored [K, M] (MN-major operand)   */
+/*   b_mn == 0: B row-major [N, K] (ldb);  b_mn == 1: B stored [K, N]                      */
+/*   epi 0: fp32 store (+ bias[N]);  1: bf16 store;  2: fp32 atomic add into a             */
+/*   pre-initialised C (split-K over `splitk` CTAs; the dW = X^T dZ product).              */
+/* lda/ldb multiples of 8, N multiple of 8, 16-byte aligned pointers.                      */
+/* ------------------------------------------------------------------------------------ */
+int mlb_gemm_bf16_tc(void* stream, const void* A, const void* B, void* C, const float* bias,
+                     int M, int N, int K, int lda, int ldb, int ldc, int a_mn, int b_mn, int epi,
+                     int splitk);
+int mlb_cast_f32_bf16(void* stream, const float* src, void* dst, long long n);
+/* bf16 copies of an fp32 weight matrix W [rows, cols]: dst_t = W^T (ld_t), dst = W (ld_d, may be NULL) */
+int mlb_cast_weight_bf16(void* stream, const float* src, void* dst_t, void* dst, int rows,
+                         int cols, int ld_src, int ld_t, int ld_d);
+
 /* ------------------------------------------------------------------------------------ */
 /* K7: rollout action sampling.  `head` f32 [rows, ld]: columns [0,sumA) logits of the      */
 /* concatenated discrete components, column sumA the critic value.                          */

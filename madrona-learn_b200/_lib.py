@@ -62,6 +62,12 @@ SIGNATURES = {
                              c_int, c_int]),
     'mlb_ln_relu_fwd_f32': (c_int, [P, P, P, P, P, P, c_ll, c_int]),
     'mlb_ln_relu_bwd_f32': (c_int, [P, P, P, P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_ln_relu_fwd_bf16': (c_int, [P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_ln_relu_bwd_bf16': (c_int, [P, P, P, P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_gemm_bf16_tc': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_int]),
+    'mlb_cast_f32_bf16': (c_int, [P, P, P, c_ll]),
+    'mlb_cast_weight_bf16': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int]),
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P]),
     'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),

@@ -5,6 +5,8 @@
 // One warp per row (H <= 1024, H % 4 == 0): 128-bit loads, warp-shuffle row reductions, the
 // per-feature dscale/dbias sums stay in registers across the rows a warp visits and are
 // reduced through shared memory + one fp32 atomic per feature per block.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -12,10 +14,27 @@ namespace {
 constexpr float LN_EPS = 1e-6f;
 constexpr int MAXV = 8;           // float4 vectors per lane: H <= 32*4*8 = 1024
 
-template <int NV>
+// 4-element vector load / store in fp32 or bf16 storage (bf16 path: activations of the
+// tensor-core MLP are bf16 in HBM, statistics and arithmetic stay fp32)
+__device__ __forceinline__ float4 ld4(const float* p, int c) { return __ldg(reinterpret_cast<const float4*>(p) + c); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p, int c) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p) + c);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, int c, float4 v) { reinterpret_cast<float4*>(p)[c] = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, int c, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(p)[c] = u;
+}
+
+template <int NV, typename TY>
 __global__ void __launch_bounds__(256)
 ln_relu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ scale,
-                   const float* __restrict__ bias, float* __restrict__ y,
+                   const float* __restrict__ bias, TY* __restrict__ y,
                    float* __restrict__ stats, long long rows, int H) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -47,7 +66,7 @@ ln_relu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ scale,
         const float mean = sum * invH;
         const float var = fmaxf(0.f, sq * invH - mean * mean);
         const float rstd = rsqrtf(var + LN_EPS);
-        float4* yr = reinterpret_cast<float4*>(y + r * H);
+        TY* yr = y + r * H;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
@@ -57,18 +76,18 @@ ln_relu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ scale,
                 o.y = fmaxf(0.f, (v[i].y - mean) * rstd * s[i].y + b[i].y);
                 o.z = fmaxf(0.f, (v[i].z - mean) * rstd * s[i].z + b[i].z);
                 o.w = fmaxf(0.f, (v[i].w - mean) * rstd * s[i].w + b[i].w);
-                yr[c] = o;
+                st4(yr, c, o);
             }
         }
         if (stats && lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
     }
 }
 
-template <int NV>
+template <int NV, typename TD>
 __global__ void __launch_bounds__(256)
-ln_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+ln_relu_bwd_kernel(const TD* __restrict__ dy, const float* __restrict__ z,
                    const float* __restrict__ stats, const float* __restrict__ scale,
-                   const float* __restrict__ bias, float* __restrict__ dz,
+                   const float* __restrict__ bias, TD* __restrict__ dz,
                    float* __restrict__ dscale, float* __restrict__ dbias, long long rows, int H) {
     extern __shared__ float sm[];           // [2][H] per-block feature sums
     const int lane = threadIdx.x & 31;
@@ -90,14 +109,14 @@ ln_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
     for (long long r = warp; r < rows; r += nwarps) {
         const float mean = stats[2 * r], rstd = stats[2 * r + 1];
         const float4* zr = reinterpret_cast<const float4*>(z + r * H);
-        const float4* dr = reinterpret_cast<const float4*>(dy + r * H);
+        const TD* dr = dy + r * H;
         float4 xh[NV], dx[NV];
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
             if (c < nvec) {
-                const float4 zv = __ldg(zr + c), dv = __ldg(dr + c);
+                const float4 zv = __ldg(zr + c), dv = ld4(dr, c);
                 float4 x, g;
                 x.x = (zv.x - mean) * rstd; x.y = (zv.y - mean) * rstd;
                 x.z = (zv.z - mean) * rstd; x.w = (zv.w - mean) * rstd;
@@ -115,7 +134,7 @@ ln_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
         }
         m1 = warp_sum(m1) * invH;
         m2 = warp_sum(m2) * invH;
-        float4* or_ = reinterpret_cast<float4*>(dz + r * H);
+        TD* or_ = dz + r * H;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
@@ -125,7 +144,7 @@ ln_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                 o.y = rstd * (dx[i].y - m1 - xh[i].y * m2);
                 o.z = rstd * (dx[i].z - m1 - xh[i].z * m2);
                 o.w = rstd * (dx[i].w - m1 - xh[i].w * m2);
-                or_[c] = o;
+                st4(or_, c, o);
             }
         }
     }
@@ -155,25 +174,38 @@ unsigned row_grid(long long rows) {
 
 }  // namespace
 
-MLB_API int mlb_ln_relu_fwd_f32(void* stream, const float* z, const float* scale,
-                                const float* bias, float* y, float* stats, long long rows, int H) {
+template <typename TY>
+static int ln_fwd_impl(void* stream, const float* z, const float* scale, const float* bias, TY* y,
+                       float* stats, long long rows, int H) {
     MLB_REQUIRE(z && scale && bias && y && rows >= 0 && H > 0 && H % 4 == 0 && H <= 128 * MAXV);
     if (rows == 0) return MLB_OK;
     if (!(mlb_aligned16(z) && mlb_aligned16(y) && mlb_aligned16(scale) && mlb_aligned16(bias))) return MLB_EALIGN;
     cudaStream_t s = mlb_stream(stream);
     const unsigned g = row_grid(rows);
     const int nv = (H / 4 + 31) / 32;
-    if (nv <= 1) ln_relu_fwd_kernel<1><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
-    else if (nv <= 2) ln_relu_fwd_kernel<2><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
-    else if (nv <= 4) ln_relu_fwd_kernel<4><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
-    else ln_relu_fwd_kernel<8><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
+    if (nv <= 1) ln_relu_fwd_kernel<1, TY><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
+    else if (nv <= 2) ln_relu_fwd_kernel<2, TY><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
+    else if (nv <= 4) ln_relu_fwd_kernel<4, TY><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
+    else ln_relu_fwd_kernel<8, TY><<<g, 256, 0, s>>>(z, scale, bias, y, stats, rows, H);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }
 
-MLB_API int mlb_ln_relu_bwd_f32(void* stream, const float* dy, const float* z, const float* stats,
-                                const float* scale, const float* bias, float* dz, float* dscale,
-                                float* dbias, long long rows, int H) {
+MLB_API int mlb_ln_relu_fwd_f32(void* stream, const float* z, const float* scale,
+                                const float* bias, float* y, float* stats, long long rows, int H) {
+    return ln_fwd_impl<float>(stream, z, scale, bias, y, stats, rows, H);
+}
+
+MLB_API int mlb_ln_relu_fwd_bf16(void* stream, const float* z, const float* scale,
+                                 const float* bias, void* y_bf16, float* stats, long long rows, int H) {
+    return ln_fwd_impl<__nv_bfloat16>(stream, z, scale, bias, reinterpret_cast<__nv_bfloat16*>(y_bf16),
+                                      stats, rows, H);
+}
+
+template <typename TD>
+static int ln_bwd_impl(void* stream, const TD* dy, const float* z, const float* stats,
+                       const float* scale, const float* bias, TD* dz, float* dscale,
+                       float* dbias, long long rows, int H) {
     MLB_REQUIRE(dy && z && stats && scale && bias && dz && dscale && dbias);
     MLB_REQUIRE(rows >= 0 && H > 0 && H % 4 == 0 && H <= 128 * MAXV);
     if (rows == 0) return MLB_OK;
@@ -182,10 +214,24 @@ MLB_API int mlb_ln_relu_bwd_f32(void* stream, const float* dy, const float* z, c
     const unsigned g = row_grid(rows);
     const size_t smem = 2 * (size_t)H * sizeof(float);
     const int nv = (H / 4 + 31) / 32;
-    if (nv <= 1) ln_relu_bwd_kernel<1><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
-    else if (nv <= 2) ln_relu_bwd_kernel<2><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
-    else if (nv <= 4) ln_relu_bwd_kernel<4><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
-    else ln_relu_bwd_kernel<8><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
+    if (nv <= 1) ln_relu_bwd_kernel<1, TD><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
+    else if (nv <= 2) ln_relu_bwd_kernel<2, TD><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
+    else if (nv <= 4) ln_relu_bwd_kernel<4, TD><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
+    else ln_relu_bwd_kernel<8, TD><<<g, 256, smem, s>>>(dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
+}
+
+MLB_API int mlb_ln_relu_bwd_f32(void* stream, const float* dy, const float* z, const float* stats,
+                                const float* scale, const float* bias, float* dz, float* dscale,
+                                float* dbias, long long rows, int H) {
+    return ln_bwd_impl<float>(stream, dy, z, stats, scale, bias, dz, dscale, dbias, rows, H);
+}
+
+MLB_API int mlb_ln_relu_bwd_bf16(void* stream, const void* dy_bf16, const float* z, const float* stats,
+                                 const float* scale, const float* bias, void* dz_bf16, float* dscale,
+                                 float* dbias, long long rows, int H) {
+    return ln_bwd_impl<__nv_bfloat16>(stream, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), z, stats,
+                                      scale, bias, reinterpret_cast<__nv_bfloat16*>(dz_bf16), dscale, dbias,
+                                      rows, H);
 }
