@@ -34,6 +34,19 @@ def gemm(A, B, C, bias, M, N, K, lda, ldb, ldc, ta=0, tb=0, accumulate=0, splitk
          c_int(splitk))
 
 
+def gemm_tc(A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn=0, b_mn=0, epi=0, splitk=1):
+    """mlb_gemm_bf16_tc: C[M,N] (+)= A * B^T on tcgen05 (bf16 operands, fp32 accumulate)."""
+    call('mlb_gemm_bf16_tc', ptr(A), ptr(B), ptr(C), ptr(bias), c_int(M), c_int(N), c_int(K), c_int(lda),
+         c_int(ldb), c_int(ldc), c_int(a_mn), c_int(b_mn), c_int(epi), c_int(splitk))
+
+
+def _splitk_tc(M, N, K):
+    bn = 64 if N <= 64 else (128 if N <= 128 else 256)
+    tiles = math.ceil(M / 128) * math.ceil(N / bn)
+    want = max(1, 148 // tiles)
+    return int(max(1, min(want, K // 256)))
+
+
 def _splitk_for(M, N, K):
     bm, bn = (128, 32) if N <= 32 else ((64, 64) if (N <= 64 or M <= 64) else (128, 128))
     tiles = math.ceil(M / bm) * math.ceil(N / bn)
@@ -45,8 +58,9 @@ class PolicyProgram:
     def __init__(self, actor_critic, obs_dim, actions_cfg, device, compute_dtype=F32):
         if not isinstance(actor_critic, ActorCritic):
             raise TypeError('policy.actor_critic must be an ActorCritic descriptor')
-        if compute_dtype != F32:
-            raise NotImplementedError('compute_dtype other than float32: tcgen05 bf16 path not built yet')
+        if compute_dtype not in (F32, torch.bfloat16):
+            raise NotImplementedError('compute_dtype must be float32 (SIMT) or bfloat16 (tcgen05)')
+        self.tc = compute_dtype == torch.bfloat16
         bb = actor_critic.backbone
         if not isinstance(bb, BackboneShared):
             raise NotImplementedError('only BackboneShared is lowered (BackboneSeparate: next)')
@@ -69,6 +83,8 @@ class PolicyProgram:
         self.L = int(self.mlp.num_layers)
         if self.H % 4 or self.H > 1024:
             raise NotImplementedError('MLP width must be a multiple of 4 and <= 1024')
+        if self.tc and (self.H % 8 or self.obs_dim % 8):
+            raise NotImplementedError('tensor-core path needs obs_dim and width multiples of 8 (TMA 16 B rows)')
         # action layout: groups in cfg.actions order, components concatenated
         self.groups = []
         buckets = []
@@ -83,7 +99,9 @@ class PolicyProgram:
         self.A = len(buckets)
         self.sumA = int(sum(buckets))
         self.V = 1
-        self.NH = _round_up(self.sumA + self.V, 4)
+        # head width: padded to 4 (fp32 path) or to 64 (tensor-core path: one 64-wide UMMA N tile
+        # and one SWIZZLE_128B atom of the MN-major dhead operand)
+        self.NH = _round_up(self.sumA + self.V, 64 if self.tc else 4)
         self._buckets_c = (ctypes.c_int32 * self.A)(*buckets)
         # ---- arena layout -------------------------------------------------------------
         off = 0
@@ -113,6 +131,14 @@ class PolicyProgram:
         self.segments = None
         self._train_ws = None
         self._infer_ws = None
+        if self.tc:
+            BF = torch.bfloat16
+            # bf16 operand copies of the weights: W^T [H, in] (forward, K-major B) and W [in, H]
+            # (dX, K-major B); refreshed by refresh_bf16() after every optimiser step
+            self.w_t = [torch.zeros(self.H, d_, dtype=BF, device=dev) for (_, _, d_) in self.layer_off]
+            self.w_c = [torch.zeros(d_, self.H, dtype=BF, device=dev) for (_, _, d_) in self.layer_off]
+            self.wh_t = torch.zeros(self.NH, self.feat, dtype=BF, device=dev)
+            self.wh_c = torch.zeros(self.feat, self.NH, dtype=BF, device=dev)
 
     # ---------------------------------------------------------------------------------
     # parameters
@@ -210,7 +236,21 @@ class PolicyProgram:
             self.initial_weight_norms[f'Dense_{i}'] = n0
         self.rebuild_segments()
 
+    def refresh_bf16(self):
+        """Re-derive the bf16 operand copies from the fp32 master weights (tensor-core path)."""
+        if not self.tc:
+            return
+        for i in range(self.L):
+            k, _, _ = self.layer_views(self.params, i)
+            d = self.layer_off[i][2]
+            call('mlb_cast_weight_bf16', ptr(k), ptr(self.w_t[i]), ptr(self.w_c[i]), c_int(d), c_int(self.H),
+                 c_int(self.H), c_int(d), c_int(self.H))
+        W, _ = self.head_views(self.params)
+        call('mlb_cast_weight_bf16', ptr(W), ptr(self.wh_t), ptr(self.wh_c), c_int(self.feat), c_int(self.NH),
+             c_int(self.NH), c_int(self.feat), c_int(self.NH))
+
     def rebuild_segments(self):
+        self.refresh_bf16()
         segs = []
         for i in range(self.L):
             k_off, ln_off, d = self.layer_off[i]
@@ -228,9 +268,12 @@ class PolicyProgram:
         w = self._infer_ws
         if w is None or w['rows'] < rows:
             dev = self.device
+            AT = torch.bfloat16 if self.tc else F32
             w = dict(rows=rows, z=torch.empty(rows, self.H, dtype=F32, device=dev),
-                     y=[torch.empty(rows, self.H, dtype=F32, device=dev) for _ in range(2)],
+                     y=[torch.empty(rows, self.H, dtype=AT, device=dev) for _ in range(2)],
                      head=torch.empty(rows, self.NH, dtype=F32, device=dev))
+            if self.tc:
+                w['x'] = torch.empty(rows, self.obs_dim, dtype=AT, device=dev)
             self._infer_ws = w
         return w
 
@@ -238,14 +281,18 @@ class PolicyProgram:
         w = self._train_ws
         if w is None or w['rows'] < rows:
             dev = self.device
-            e = lambda *s: torch.empty(*s, dtype=F32, device=dev)
+            AT = torch.bfloat16 if self.tc else F32
+            e = lambda *s, dtype=F32: torch.empty(*s, dtype=dtype, device=dev)
             w = dict(rows=rows, z=[e(rows, self.H) for _ in range(self.L)],
-                     y=[e(rows, self.H) for _ in range(self.L)],
+                     y=[e(rows, self.H, dtype=AT) for _ in range(self.L)],
                      stats=[e(rows, 2) for _ in range(self.L)],
                      head=e(rows, self.NH), dhead=e(rows, self.NH),
-                     dy=e(rows, self.H), dz=e(rows, self.H),
+                     dy=e(rows, self.H, dtype=AT), dz=e(rows, self.H, dtype=AT),
                      loss_ws=torch.empty(_lib.lib().mlb_ppo_loss_workspace(rows) + 16, dtype=torch.uint8, device=dev),
                      stats_out=torch.zeros(ctypes.sizeof(_lib.PPOStats), dtype=torch.uint8, device=dev))
+            if self.tc:
+                w['x'] = e(rows, self.obs_dim, dtype=AT)
+                w['dhead16'] = e(rows, self.NH, dtype=AT)
             self._train_ws = w
         return w
 
@@ -255,6 +302,9 @@ class PolicyProgram:
     def forward_infer(self, obs, rows):
         """obs f32 [rows, D] -> head f32 [rows, NH] (logits | value)."""
         w = self.infer_ws(rows)
+        if self.tc:
+            return self._forward_tc(obs, rows, w, [w['z']] * self.L, [w['y'][i & 1] for i in range(self.L)],
+                                    [None] * self.L)
         x, d = obs, self.obs_dim
         for i in range(self.L):
             k, s, b = self.layer_views(self.params, i)
@@ -264,6 +314,21 @@ class PolicyProgram:
             x, d = y, self.H
         W, B = self.head_views(self.params)
         gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
+        return w['head']
+
+    def _forward_tc(self, obs, rows, w, zs, ys, stats):
+        """bf16 tensor-core forward: cast obs -> [tcgen05 GEMM -> LayerNorm+ReLU (bf16 out)] x L
+        -> head GEMM (fp32 out + bias)."""
+        call('mlb_cast_f32_bf16', ptr(obs), ptr(w['x']), c_ll(rows * self.obs_dim))
+        x, d = w['x'], self.obs_dim
+        for i in range(self.L):
+            _, s, b = self.layer_views(self.params, i)
+            gemm_tc(x, self.w_t[i], zs[i], None, rows, self.H, d, d, d, self.H, 0, 0, 0)
+            call('mlb_ln_relu_fwd_bf16', ptr(zs[i]), ptr(s), ptr(b), ptr(ys[i]), ptr(stats[i]), c_ll(rows),
+                 c_int(self.H))
+            x, d = ys[i], self.H
+        _, B = self.head_views(self.params)
+        gemm_tc(x, self.wh_t, w['head'], B, rows, self.NH, self.feat, self.feat, self.feat, self.NH, 0, 0, 0)
         return w['head']
 
     def sample(self, head, rows, policy_key, actions, log_probs, values, partitionable=False,
@@ -277,6 +342,8 @@ class PolicyProgram:
     # ---------------------------------------------------------------------------------
     def forward_train(self, obs, rows):
         w = self.train_ws(rows)
+        if self.tc:
+            return self._forward_tc(obs, rows, w, w['z'], w['y'], w['stats'])
         x, d = obs, self.obs_dim
         for i in range(self.L):
             k, s, b = self.layer_views(self.params, i)
@@ -291,6 +358,8 @@ class PolicyProgram:
     def backward(self, obs, rows):
         """Consumes train_ws['dhead']; accumulates into self.grads (pre-zeroed)."""
         w = self.train_ws(rows)
+        if self.tc:
+            return self._backward_tc(rows, w)
         W, B = self.head_views(self.params)
         gW, gB = self.head_views(self.grads)
         feat = w['y'][self.L - 1]
@@ -312,6 +381,28 @@ class PolicyProgram:
             if i > 0:
                 gemm(w['dz'], k, w['dy'], None, rows, d, self.H, self.H, self.H, d, ta=0, tb=1)
 
+    def _backward_tc(self, rows, w):
+        """bf16 tensor-core backward.  dW products are MN-major x MN-major split-K GEMMs with
+        fp32 atomic accumulation straight into the gradient arena."""
+        gW, gB = self.head_views(self.grads)
+        feat = w['y'][self.L - 1]
+        call('mlb_cast_f32_bf16', ptr(w['dhead']), ptr(w['dhead16']), c_ll(rows * self.NH))
+        gemm_tc(feat, w['dhead16'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH, 1, 1, 2,
+                _splitk_tc(self.feat, self.NH, rows))
+        call('mlb_colsum_f32', ptr(w['dhead']), c_ll(rows), c_int(self.NH), c_int(self.NH), ptr(gB))
+        gemm_tc(w['dhead16'], self.wh_c, w['dy'], None, rows, self.feat, self.NH, self.NH, self.NH, self.feat,
+                0, 0, 1)
+        for i in range(self.L - 1, -1, -1):
+            _, s, b = self.layer_views(self.params, i)
+            gk, gs, gb = self.layer_views(self.grads, i)
+            d = self.layer_off[i][2]
+            call('mlb_ln_relu_bwd_bf16', ptr(w['dy']), ptr(w['z'][i]), ptr(w['stats'][i]), ptr(s), ptr(b),
+                 ptr(w['dz']), ptr(gs), ptr(gb), c_ll(rows), c_int(self.H))
+            x = w['x'] if i == 0 else w['y'][i - 1]
+            gemm_tc(x, w['dz'], gk, None, d, self.H, rows, d, self.H, self.H, 1, 1, 2, _splitk_tc(d, self.H, rows))
+            if i > 0:
+                gemm_tc(w['dz'], self.w_c[i], w['dy'], None, rows, d, self.H, self.H, self.H, d, 0, 0, 1)
+
     def zero_grads(self):
         call('mlb_fill_zero', ptr(self.grads), c_size_t(self.num_params * 4))
 
@@ -324,6 +415,7 @@ class PolicyProgram:
              c_float(b1), c_float(b2), c_float(eps), c_float(max_grad_norm), c_float(grad_scale))
         call('mlb_renorm_segments', ptr(self.params), ptr(self.segments), c_int(self.num_segments),
              ptr(self.adam_step))
+        self.refresh_bf16()
 
     # ---------------------------------------------------------------------------------
     # flax-style apply(method=...) entry points (ml/actor_critic.py:65-128); these allocate

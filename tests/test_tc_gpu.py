@@ -84,3 +84,118 @@ def test_cast_kernels(mlb):
     call('mlb_cast_weight_bf16', ptr(W), ptr(Wt), ptr(Wc), c_int(70), c_int(45), c_int(45), c_int(72), c_int(48))
     assert torch.equal(Wt[:, :70], W.t().to(torch.bfloat16))
     assert torch.equal(Wc[:, :45], W.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------
+# the bf16 tensor-core policy path (compute_dtype=bfloat16) vs the fp64 oracle
+# stated tolerance: logits-derived quantities rel 2e-2; gradients cosine >= 0.999
+# and rel-L2 <= 3e-2
+# ------------------------------------------------------------------------------------------
+def _program(mlb, D, H, L, buckets, dtype):
+    m = mlb
+    from madrona_learn_b200.engine import PolicyProgram
+    ac = m.ActorCritic(
+        backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(net=m.models.MLP(H, L))),
+        actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(buckets)),
+        critic=m.models.DenseLayerCritic())
+    return PolicyProgram(ac, D, {'act': m.DiscreteActionsConfig(buckets)}, DEV, dtype)
+
+
+@pytest.mark.parametrize('D,H,L,rows', [(64, 256, 3, 4096), (32, 128, 2, 1000), (64, 512, 3, 2048)])
+def test_tc_policy_forward_backward_vs_oracle(mlb, D, H, L, rows):
+    import ctypes
+    from madrona_learn_b200._lib import c_float, c_int, c_ll, c_size_t, call, ptr
+    from oracle import nn as onn, ppo as oppo, algo_common as oac
+    buckets = [4, 8, 5, 5, 2, 2]
+    A = len(buckets)
+    rng = np.random.default_rng(H + rows)
+    p = onn.init_params(rng, D, H, L, buckets)
+    p['actor']['kernel'] = (rng.standard_normal(p['actor']['kernel'].shape) * 0.2).astype(np.float32)
+    for l in p['mlp']:
+        l['scale'] = (1 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+        l['bias'] = (0.1 * rng.standard_normal(H)).astype(np.float32)
+    prog = _program(mlb, D, H, L, buckets, torch.bfloat16)
+    assert prog.tc and prog.NH == 64
+    prog.load_oracle_params(p)
+    Tp, M = 4, rows // 4
+    cfg = oppo.PPOCfg(buckets, entropy_coef=0.02)
+    mb = dict(obs=rng.standard_normal((Tp, M, D)).astype(np.float32),
+              actions=np.stack([rng.integers(0, b, (Tp, M)) for b in buckets], -1).astype(np.int32),
+              advantages=rng.standard_normal((Tp, M, 1)).astype(np.float32),
+              returns=rng.standard_normal((Tp, M, 1)).astype(np.float32),
+              values=rng.standard_normal((Tp, M, 1)).astype(np.float32), mb_weights=np.ones((M, 1), np.float32))
+    lg, cr, _ = onn.actor_critic_fwd(onn.cast_tree(p, np.float64), mb['obs'].reshape(rows, D).astype(np.float64))
+    lp0, _ = onn.action_stats(lg, mb['actions'].reshape(rows, A), buckets)
+    mb['log_probs'] = (lp0 + 0.2 * rng.standard_normal(lp0.shape)).reshape(Tp, M, A).astype(np.float32)
+    ref = oppo.ppo_loss(p, mb, cfg, None, dtype=np.float64)
+
+    dv = {k: torch.from_numpy(v).to(DEV) for k, v in mb.items()}
+    obs_d = dv['obs'].view(rows, D)
+    head = prog.forward_train(obs_d, rows)
+    h = head.cpu().numpy()
+    assert np.linalg.norm(h[:, :26] - lg) / np.linalg.norm(lg) < 2e-2
+    assert np.linalg.norm(h[:, 26:27] - cr) / np.linalg.norm(cr) < 2e-2
+    assert np.all(h[:, 27:] == 0)
+    # inference path gives the same head
+    h2 = prog.forward_infer(obs_d, rows).cpu().numpy()
+    np.testing.assert_allclose(h2, h, rtol=1e-5, atol=1e-5)
+    tw = prog.train_ws(rows)
+    mean, rstd = oac.zscore_stats(mb['advantages'])
+    adv_mr = torch.tensor([mean, rstd, 0, 0], dtype=torch.float32, device=DEV)
+    obj_scale = (ctypes.c_float * A)(*[1.0 / (rows * A)] * A)
+    ent_scale = (ctypes.c_float * A)(*[cfg.entropy_coef / (rows * A)] * A)
+    call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(dv['actions']), ptr(dv['log_probs']),
+         ptr(dv['advantages']), ptr(dv['returns']), ptr(None), ptr(None), ptr(adv_mr), ptr(None),
+         prog._buckets_c, obj_scale, ent_scale, c_int(A), c_ll(rows), c_ll(M), c_float(cfg.clip_coef),
+         c_float(cfg.value_loss_coef), c_int(0), ptr(tw['dhead']), ptr(tw['stats_out']), ptr(tw['loss_ws']),
+         c_size_t(tw['loss_ws'].numel()))
+    prog.zero_grads()
+    prog.backward(obs_d, rows)
+    g = prog.to_oracle_params(prog.grads)
+    flat = lambda t: np.concatenate([x.reshape(-1).astype(np.float64) for x in
+                                     (onn.tree_leaves(t['mlp']) + onn.tree_leaves(t['actor']) + onn.tree_leaves(t['critic']))])
+    a, b = flat(g), flat(ref['grads'])
+    cos = a @ b / (np.linalg.norm(a) * np.linalg.norm(b))
+    rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert cos > 0.999 and rel < 3e-2, (cos, rel)
+    # per-tensor check so a broken small tensor cannot hide behind the big ones
+    onn.tree_map(lambda x, y: np.testing.assert_array_less(
+        np.linalg.norm(x - y) / max(np.linalg.norm(y), 1e-12), 6e-2), g, ref['grads'])
+    # optimiser step refreshes the bf16 operand copies
+    prog.optimizer_step(3e-4, 0.5)
+    k0, _, _ = prog.layer_views(prog.params, 0)
+    assert torch.equal(prog.w_c[0], k0.to(torch.bfloat16))
+    assert torch.equal(prog.w_t[0], k0.t().contiguous().to(torch.bfloat16))
+
+
+def test_tc_update_iter_runs_and_tracks_fp32(mlb, monkeypatch):
+    """Same seeds, fp32 vs bf16 path: the rollout statistics and the loss stay close."""
+    import madrona_learn_b200 as m
+    out = {}
+    for dt in (torch.float32, torch.bfloat16):
+        monkeypatch.setenv('MLB_CUDA_GRAPH', '1')
+        buckets = [4, 8, 5, 5, 2, 2]
+        env = m.SyntheticVectorEnv(256, 64, 6, seed=3, p_done=1 / 16, device=DEV)
+        policy = m.Policy(actor_critic=m.ActorCritic(
+            backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(net=m.models.MLP(128, 2))),
+            actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(buckets)),
+            critic=m.models.DenseLayerCritic()))
+        cfg = m.TrainConfig(num_worlds=256, num_agents_per_world=1, num_updates=4,
+                            actions={'act': m.DiscreteActionsConfig(buckets)}, steps_per_update=16, lr=3e-4,
+                            algo=m.PPOConfig(num_epochs=2, minibatch_size=64, clip_coef=0.2, value_loss_coef=0.5,
+                                             entropy_coef={'act': 0.01}, max_grad_norm=0.5),
+                            num_bptt_chunks=1, gamma=0.99, seed=4, metrics_buffer_size=2, gae_lambda=0.95,
+                            dreamer_v3_critic=False, compute_dtype=dt)
+        mgr = m.init_training(DEV, cfg, env.sim_fns(), policy, None, verbose=False)
+        for _ in range(3):
+            mgr.update_iter()
+        torch.cuda.synchronize()
+        lat = mgr.metrics.latest()
+        out[dt] = (lat['Loss'].mean, lat['Entropy'].mean, lat['Values'].mean,
+                   mgr.state.policy_states.program.params.cpu().numpy().copy())
+    f, b = out[torch.float32], out[torch.bfloat16]
+    assert np.isfinite(b[0])
+    np.testing.assert_allclose(b[1], f[1], rtol=2e-2)        # entropy
+    # identical init (same seed): after 3 updates the weights moved by ~lr each step; the two
+    # paths must stay within a few lr of each other
+    assert np.abs(f[3] - b[3]).max() < 3e-3
