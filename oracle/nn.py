@@ -45,24 +45,44 @@ def layernorm_relu_bwd(dy, cache, scale):
     return dz, dscale, dbias
 
 
-def mlp_fwd(x, layers):
+def bf16_round(x):
+    """Round-to-nearest-even to bfloat16 precision (value returned in x's dtype).  Used to
+    emulate the quantisation points of the tensor-core path (compute_dtype=bfloat16): weights,
+    layer inputs/outputs and the back-propagated dY / dZ are bf16 in HBM; every accumulation,
+    LayerNorm statistic and the loss stay fp32."""
+    x32 = np.ascontiguousarray(x, np.float32)
+    u = x32.view(np.uint32)
+    r = ((u >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    out = ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+    return out.astype(np.asarray(x).dtype)
+
+
+def _id(x):
+    return x
+
+
+def mlp_fwd(x, layers, q=None):
+    q = q or _id
     caches = []
+    x = q(x)
     for lyr in layers:
-        z = x @ lyr['kernel']
+        z = x @ q(lyr['kernel'])
         y, c = layernorm_relu_fwd(z, lyr['scale'], lyr['bias'])
         caches.append((x, c))
-        x = y
+        x = q(y)
     return x, caches
 
 
-def mlp_bwd(dy, caches, layers, need_dx=False):
+def mlp_bwd(dy, caches, layers, need_dx=False, q=None):
+    q = q or _id
     grads = [None] * len(layers)
     for i in range(len(layers) - 1, -1, -1):
         x, c = caches[i]
         dz, ds, db = layernorm_relu_bwd(dy, c, layers[i]['scale'])
+        dz = q(dz)
         grads[i] = {'kernel': x.T @ dz, 'scale': ds, 'bias': db}
         if i > 0 or need_dx:
-            dy = dz @ layers[i]['kernel'].T
+            dy = q(dz @ q(layers[i]['kernel']).T)
     return (dy if need_dx else None), grads
 
 
@@ -212,25 +232,29 @@ def lstm_sequence_bwd(douts, caches, lstm, H):
 # ---------------------------------------------------------------------------------------
 # full actor-critic
 # ---------------------------------------------------------------------------------------
-def heads_fwd(feat, params):
-    logits = feat @ params['actor']['kernel'] + params['actor']['bias']
-    critic = feat @ params['critic']['kernel'] + params['critic']['bias']
+def heads_fwd(feat, params, q=None):
+    q = q or _id
+    logits = feat @ q(params['actor']['kernel']) + params['actor']['bias']
+    critic = feat @ q(params['critic']['kernel']) + params['critic']['bias']
     return logits, critic
 
 
-def actor_critic_fwd(params, obs):
-    """Non-recurrent BackboneShared(BackboneEncoder(MLP)) forward (ml/actor_critic.py)."""
-    feat, caches = mlp_fwd(obs, params['mlp'])
-    logits, critic = heads_fwd(feat, params)
+def actor_critic_fwd(params, obs, q=None):
+    """Non-recurrent BackboneShared(BackboneEncoder(MLP)) forward (ml/actor_critic.py).
+    q: optional quantiser (bf16_round) applied at the tensor-core path's storage points."""
+    feat, caches = mlp_fwd(obs, params['mlp'], q)
+    logits, critic = heads_fwd(feat, params, q)
     return logits, critic, (feat, caches)
 
 
-def actor_critic_bwd(params, cache, dlogits, dcritic):
+def actor_critic_bwd(params, cache, dlogits, dcritic, q=None):
     feat, caches = cache
-    g = {'actor': {'kernel': feat.T @ dlogits, 'bias': dlogits.sum(axis=0)},
-         'critic': {'kernel': feat.T @ dcritic, 'bias': dcritic.sum(axis=0)}}
-    dfeat = dlogits @ params['actor']['kernel'].T + dcritic @ params['critic']['kernel'].T
-    _, g['mlp'] = mlp_bwd(dfeat, caches, params['mlp'])
+    qq = q or _id
+    dl, dc = qq(dlogits), qq(dcritic)
+    g = {'actor': {'kernel': feat.T @ dl, 'bias': dlogits.sum(axis=0)},
+         'critic': {'kernel': feat.T @ dc, 'bias': dcritic.sum(axis=0)}}
+    dfeat = qq(dl @ qq(params['actor']['kernel']).T + dc @ qq(params['critic']['kernel']).T)
+    _, g['mlp'] = mlp_bwd(dfeat, caches, params['mlp'], q=q)
     return g
 
 

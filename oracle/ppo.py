@@ -24,7 +24,7 @@ class PPOCfg:
 
 
 def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, adv_stats=None,
-             new_vn_state=None):
+             new_vn_state=None, quant=None):
     """_ppo_update's loss_fn (ml/ppo.py:129-262) and its gradient w.r.t. params.
 
     mb: dict with obs [T', M, D], actions [T', M, A] i32, log_probs [T', M, A],
@@ -41,7 +41,7 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, 
     old_lp = mb['log_probs'].reshape(rows, A).astype(f)
     w = np.broadcast_to(mb['mb_weights'].reshape(1, M, 1), (Tp, M, 1)).reshape(rows, 1).astype(f)
 
-    logits, critic, cache = nn.actor_critic_fwd(p, obs)
+    logits, critic, cache = nn.actor_critic_fwd(p, obs, quant)
     new_lp, ent = nn.action_stats(logits, acts, cfg.buckets)
 
     # advantages: per-MINIBATCH z-score (ml/ppo.py:134-137 -> ml/algo_common.py:133-140)
@@ -109,7 +109,7 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, 
     dent = -(cfg.entropy_coef * w) / (rows * A) * np.ones_like(ent)
     dlogits = nn.action_stats_bwd(logits, acts, cfg.buckets, dlogp, dent)
     dcritic = cfg.value_loss_coef * w * dvloss * vclip_mask / rows
-    out['grads'] = nn.actor_critic_bwd(p, cache, dlogits, dcritic)
+    out['grads'] = nn.actor_critic_bwd(p, cache, dlogits, dcritic, quant)
     out['dlogits'] = dlogits
     out['dcritic'] = dcritic
     return out
