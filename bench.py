@@ -86,7 +86,8 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def make_cfg(m, worlds, lr=3e-4):
+def make_cfg(m, worlds, lr=3e-4, dtype=None):
+    import torch
     return m.TrainConfig(
         num_worlds=worlds, num_agents_per_world=1, num_updates=1 << 30,
         actions={'act': m.DiscreteActionsConfig(BUCKETS)}, steps_per_update=WORKLOAD['steps'], lr=lr,
@@ -94,7 +95,8 @@ def make_cfg(m, worlds, lr=3e-4):
                          minibatch_size=worlds // WORKLOAD['minibatches'], clip_coef=0.2,
                          value_loss_coef=0.5, entropy_coef={'act': 0.01}, max_grad_norm=0.5),
         num_bptt_chunks=1, gamma=0.99, seed=0, metrics_buffer_size=4, gae_lambda=0.95,
-        dreamer_v3_critic=False, normalize_values=False)
+        dreamer_v3_critic=False, normalize_values=False,
+        compute_dtype=torch.bfloat16 if dtype == 'bf16' else torch.float32)
 
 
 def make_policy(m):
@@ -183,6 +185,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=30)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'],
+                    help='bf16: tcgen05 tensor-core MLP (fp32 accumulate/statistics); f32: SIMT fp32 MLP')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get('RANK', '0'))
@@ -211,7 +215,7 @@ def main():
     import torch
     import madrona_learn_b200 as m
     from madrona_learn_b200 import _lib
-    from madrona_learn_b200.engine import gemm
+    from madrona_learn_b200.engine import gemm, gemm_tc
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     dist_ctx = None
@@ -225,7 +229,7 @@ def main():
 
     # ---- device-resident arm ---------------------------------------------------------
     env = m.SyntheticVectorEnv(N, WORKLOAD['obs_dim'], len(BUCKETS), seed=rank, device=dev)
-    mgr = m.init_training(dev, make_cfg(m, N), env.sim_fns(), make_policy(m), None, dist_ctx=dist_ctx,
+    mgr = m.init_training(dev, make_cfg(m, N, dtype=args.dtype), env.sim_fns(), make_policy(m), None, dist_ctx=dist_ctx,
                           verbose=False)
     calls0 = _lib.CALLS
     mgr.update_iter()                                      # eager: counts the enqueue calls
@@ -240,7 +244,7 @@ def main():
 
     # ---- end-to-end arm: simulator outputs in pinned host memory ----------------------
     henv = m.HostTraceEnv(N, T, WORKLOAD['obs_dim'], seed=rank, device=dev)
-    hmgr = m.init_training(dev, make_cfg(m, N), henv.sim_fns(), make_policy(m), None, dist_ctx=dist_ctx,
+    hmgr = m.init_training(dev, make_cfg(m, N, dtype=args.dtype), henv.sim_fns(), make_policy(m), None, dist_ctx=dist_ctx,
                            verbose=False)
     d2h = [0]
 
@@ -258,16 +262,30 @@ def main():
     if rank == 0:
         # ---- dominant kernel (Dense GEMM of one minibatch) roofline --------------------
         rows, H = (N // WORKLOAD['minibatches']) * T, WORKLOAD['hidden']
-        A = torch.randn(rows, H, device=dev)
-        B = torch.randn(H, H, device=dev)
-        C = torch.empty(rows, H, device=dev)
-        t_gemm = time_kernel(torch, lambda: gemm(A, B, C, None, rows, H, H, H, H, H), 10)
         flops = 2.0 * rows * H * H
+        if args.dtype == 'bf16':
+            A = torch.randn(rows, H, device=dev).to(torch.bfloat16)
+            B = torch.randn(H, H, device=dev).to(torch.bfloat16)
+            C = torch.empty(rows, H, device=dev)
+            t_gemm = time_kernel(torch, lambda: gemm_tc(A, B, C, None, rows, H, H, H, H, H, 0, 0, 0), 10)
+            kname = 'tc_gemm_kernel<256,3,K-major,K-major,f32-out> (tcgen05 Dense forward, 65536 x 256 x 256)'
+            note = ('tcgen05.mma kind::f16, M=128 N=256 per CTA, fp32 store epilogue; at K=256 the tile is '
+                    'output-write bound (64 MB fp32 out per launch), not MMA bound')
+            # algorithmic HBM bytes of this launch: A bf16 in + C fp32 out (+ B once)
+            hbm = rows * H * 2 + rows * H * 4 + H * H * 2
+        else:
+            A = torch.randn(rows, H, device=dev)
+            B = torch.randn(H, H, device=dev)
+            C = torch.empty(rows, H, device=dev)
+            t_gemm = time_kernel(torch, lambda: gemm(A, B, C, None, rows, H, H, H, H, H), 10)
+            kname = 'sgemm_kernel<128,128,8,8> (fp32 SIMT Dense forward, 65536 x 256 x 256)'
+            note = 'fp32 FFMA path (compute_dtype=float32)'
+            hbm = rows * H * 4 * 2 + H * H * 4
         tf = flops / t_gemm / 1e12
-        roof = dict(bound='tensor', kernel='sgemm_kernel<128,128,8,8> (fp32 SIMT Dense, rows x 256 x 256)',
-                    achieved=tf, peak=pk['bf16_tflops_sustained'], unit='TFLOP/s',
-                    frac=tf / pk['bf16_tflops_sustained'], traffic=None, peak_source=pk_src,
-                    note='fp32 FFMA path (compute_dtype=float32); tcgen05 bf16 path is the next milestone')
+        roof = dict(bound='tensor', kernel=kname, achieved=tf, peak=pk['bf16_tflops_sustained'],
+                    unit='TFLOP/s', frac=tf / pk['bf16_tflops_sustained'], traffic=None,
+                    peak_source=pk_src, us_per_launch=t_gemm * 1e6,
+                    hbm_gbs=hbm / t_gemm / 1e9, hbm_frac=hbm / t_gemm / 1e9 / pk['hbm_gbs'], note=note)
         del A, B, C
         # ---- GAE kernel HBM roofline (configs[4] sweep point, > L2) --------------------
         K = m.kernels
@@ -281,7 +299,9 @@ def main():
         by = 17.0 * Tg * Ng + 4.0 * Ng
         gae = dict(bound='hbm', kernel='gae_kernel<4,4,false>', workload=f'T={Tg}, N={Ng} (inputs 4.6 GB > L2)',
                    achieved=by / t_gae / 1e9, peak=pk['hbm_gbs'], unit='GB/s',
-                   frac=by / t_gae / 1e9 / pk['hbm_gbs'], traffic=None, peak_source=pk_src)
+                   frac=by / t_gae / 1e9 / pk['hbm_gbs'], algorithmic_bytes=by,
+                   traffic=4.5228e9, traffic_source='profiles/r1_ncu_full_gae_raw.csv (dram read+write per launch)',
+                   peak_source=pk_src, us_per_launch=t_gae * 1e6)
         del r, v, d, b, adv, ret
         torch.cuda.empty_cache()
         cpu = None
@@ -294,7 +314,7 @@ def main():
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': sec / args.steps * 1e3, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': WORKLOAD['name'], 'worlds_per_gpu': N, 'steps_per_update': T,
                        'obs_dim': WORKLOAD['obs_dim'], 'actions': BUCKETS, 'parallelism': f'dp{world}',
                        'cuda_graph': graph_on,

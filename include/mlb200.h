@@ -192,6 +192,18 @@ int mlb_ln_relu_bwd_bf16(void* stream, const void* dy_bf16, const float* z, cons
 int mlb_gemm_bf16_tc(void* stream, const void* A, const void* B, void* C, const float* bias,
                      int M, int N, int K, int lda, int ldb, int ldc, int a_mn, int b_mn, int epi,
                      int splitk);
+/* Fused layer kernels (whole 128 x H accumulator tile in TMEM, H <= 256 multiple of 32, or 512): */
+/* forward  Y = relu(LN(X Wt^T)*scale+bias): X bf16 [M,K] (ldx), Wt bf16 [HN,K] (ldw) = W^T;      */
+/*   Y bf16 [M,HN]; XH (NULL at inference) bf16 [M,HN] = normalised pre-activation; rstd f32 [M]. */
+/* backward dZ_out = LN'/ReLU'(DZ_in W^T) for the PREVIOUS layer, whose scale/bias/XH/rstd are    */
+/*   given; W bf16 [HN, K] (ldw) is this layer's kernel [in=HN, out=K]; dscale/dbias f32 [HN]     */
+/*   accumulated (pre-zeroed).  Z and dY never touch HBM.                                         */
+int mlb_dense_ln_relu_fwd_tc(void* stream, const void* X, const void* Wt, const float* scale,
+                             const float* bias, void* Y, void* XH, float* rstd, int M, int K,
+                             int HN, int ldx, int ldw);
+int mlb_dense_dx_lnbwd_tc(void* stream, const void* DZ_in, const void* W, const float* scale,
+                          const float* bias, const void* XH, const float* rstd, void* DZ_out,
+                          float* dscale, float* dbias, int M, int K, int HN, int lda, int ldw);
 int mlb_cast_f32_bf16(void* stream, const float* src, void* dst, long long n);
 /* bf16 copies of an fp32 weight matrix W [rows, cols]: dst_t = W^T (ld_t), dst = W (ld_d, may be NULL) */
 int mlb_cast_weight_bf16(void* stream, const float* src, void* dst_t, void* dst, int rows,

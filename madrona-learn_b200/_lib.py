@@ -66,6 +66,8 @@ SIGNATURES = {
     'mlb_ln_relu_bwd_bf16': (c_int, [P, P, P, P, P, P, P, P, P, c_ll, c_int]),
     'mlb_gemm_bf16_tc': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int]),
+    'mlb_dense_ln_relu_fwd_tc': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int]),
+    'mlb_dense_dx_lnbwd_tc': (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int]),
     'mlb_cast_f32_bf16': (c_int, [P, P, P, c_ll]),
     'mlb_cast_weight_bf16': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int]),
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),

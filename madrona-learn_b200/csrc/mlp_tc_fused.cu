@@ -1,0 +1,365 @@
+// Fused tensor-core MLP layer kernels (tcgen05 / TMEM / TMA), compute_dtype=bfloat16.
+//
+//   mlb_dense_ln_relu_fwd_tc   Y = relu(LayerNorm(X W) * scale + bias)
+//       replaces nn.Dense -> nn.LayerNorm(eps 1e-6, fast variance) -> relu (ml/models.py:107-117)
+//   mlb_dense_dx_lnbwd_tc      dZ_prev = LayerNormReLU'( dZ W^T )   (+ dscale_prev, dbias_prev)
+//       replaces the autodiff of the same three ops for the previous layer (ml/ppo.py:276-281)
+//
+// Both keep a whole 128-row x H accumulator tile in TMEM (H <= 512 = all 512 columns), so the
+// LayerNorm row statistics, the ReLU mask and the LayerNorm backward -- which need a full row --
+// run in the epilogue straight out of TMEM: the pre-activation Z and the back-propagated dY are
+// never written to HBM.  Epilogue thread t of warp w owns accumulator row 32*(w%4)+t
+// (tcgen05.ld 32x32b), so row reductions are thread-local; the per-feature sums of the
+// backward (dscale, dbias) use a 31-shuffle warp reduce-scatter per 32-column chunk.
+//
+// Forward (training) stores, per element, y (bf16) and xhat (bf16), plus rstd per row: that is
+// what the backward needs (xhat for the LN Jacobian, sign(xhat*scale+bias) for the ReLU mask).
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int FUSED_THREADS = 192;
+constexpr float LN_EPS = 1e-6f;
+
+template <int STAGES>
+struct FusedSmem {
+    // stage = A tile (16 KB) + B tile (HN * 128 B)
+    static __host__ __device__ constexpr int stage_bytes(int hn) { return BM * BK * 2 + hn * BK * 2; }
+    static __host__ __device__ constexpr int bar_off(int hn) { return STAGES * stage_bytes(hn); }
+    // + barriers (2*STAGES+1) + tmem slot + scale/bias (2*hn floats) + colsum (2*hn floats) + slack
+    static __host__ __device__ constexpr int total(int hn) {
+        return bar_off(hn) + (2 * STAGES + 1) * 8 + 16 + 4 * hn * 4 + 1024;
+    }
+};
+
+// 32-value warp reduce-scatter: on return lane i holds sum over the 32 lanes of v[i].
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int b = 16; b >= 1; b >>= 1) {
+        const bool up = (lane & b) != 0;
+#pragma unroll
+        for (int j = 0; j < b; ++j) {
+            const float send = up ? v[j] : v[j + b];
+            const float keep = up ? v[j + b] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, b);
+        }
+    }
+    return v[0];
+}
+
+// Shared mainloop: TMA producer (warp 0) + MMA issuer (warp 1); accumulator [128 x HN] in TMEM.
+// A K-major [M rows, K]; B K-major [HN rows, K] loaded as HN/256 (or 1) boxes.
+template <int STAGES>
+__device__ __forceinline__ void mainloop(const CUtensorMap* tmA, const CUtensorMap* tmB, uint8_t* smem,
+                                         uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_bar,
+                                         uint32_t tmem_base, int warp, int lane, int m0, int K, int HN) {
+    const int num_kb = (K + BK - 1) / BK;
+    const int stage_bytes = FusedSmem<STAGES>::stage_bytes(HN);
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+                uint8_t* sa = smem + s * stage_bytes;
+                uint8_t* sb = sa + BM * BK * 2;
+                mbar_expect_tx(&full_bar[s], stage_bytes);
+                tma_load_2d(tmA, &full_bar[s], sa, kb * BK, m0);
+                for (int n = 0; n < HN; n += 256)            // box rows <= 256
+                    tma_load_2d(tmB, &full_bar[s], sb + n * BK * 2, kb * BK, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const int n_inst = HN > 256 ? 256 : HN;          // N of one tcgen05.mma
+            const uint32_t idesc = umma_idesc(false, false, n_inst);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + s * stage_bytes);
+                const uint32_t sb = sa + BM * BK * 2;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t ad = umma_desc(sa + k * 32, 16, 1024);
+                    for (int n = 0; n < HN; n += 256) {
+                        const uint64_t bd = umma_desc(sb + n * BK * 2 + k * 32, 16, 1024);
+                        tcgen05_mma_f16(tmem_base + n, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    }
+                }
+                tcgen05_commit(&empty_bar[s]);
+            }
+            tcgen05_commit(acc_bar);
+        }
+    }
+}
+
+struct Prologue {
+    uint8_t* smem;
+    uint64_t *full_bar, *empty_bar, *acc_bar;
+    float* fsm;            // 4*HN floats: scale | bias | colsum0 | colsum1
+    uint32_t tmem_base;
+};
+
+template <int STAGES>
+__device__ __forceinline__ Prologue prologue(uint8_t* smem_raw, const CUtensorMap* tmA,
+                                             const CUtensorMap* tmB, int HN, uint32_t tmem_cols,
+                                             const float* scale, const float* bias) {
+    Prologue p;
+    p.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    p.full_bar = reinterpret_cast<uint64_t*>(p.smem + FusedSmem<STAGES>::bar_off(HN));
+    p.empty_bar = p.full_bar + STAGES;
+    p.acc_bar = p.empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p.acc_bar + 1);
+    p.fsm = reinterpret_cast<float*>(tmem_slot + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmB)) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&p.full_bar[s], 1); mbar_init(&p.empty_bar[s], 1); }
+        mbar_init(p.acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < HN; i += blockDim.x) {
+        p.fsm[i] = scale[i];
+        p.fsm[HN + i] = bias[i];
+        p.fsm[2 * HN + i] = 0.f;
+        p.fsm[3 * HN + i] = 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    p.tmem_base = *tmem_slot;
+    return p;
+}
+
+__device__ __forceinline__ void epilogue_done(uint32_t tmem_base, uint32_t tmem_cols, int warp) {
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+                     : "memory");
+    }
+}
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        uint4 o;
+        o.x = pack_bf16(v[j], v[j + 1]); o.y = pack_bf16(v[j + 2], v[j + 3]);
+        o.z = pack_bf16(v[j + 4], v[j + 5]); o.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(dst + j) = o;
+    }
+}
+
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + j));
+        v[j] = bf16lo(u.x); v[j + 1] = bf16hi(u.x); v[j + 2] = bf16lo(u.y); v[j + 3] = bf16hi(u.y);
+        v[j + 4] = bf16lo(u.z); v[j + 5] = bf16hi(u.z); v[j + 6] = bf16lo(u.w); v[j + 7] = bf16hi(u.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward: Y = relu(LN(X W))
+// ------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(FUSED_THREADS)
+dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const float* __restrict__ scale, const float* __restrict__ bias,
+                         __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ XH,
+                         float* __restrict__ rstd_out, int M, int K, int HN, uint32_t tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM;
+    Prologue p = prologue<STAGES>(smem_raw, &tmA, &tmB, HN, tmem_cols, scale, bias);
+    if (warp < 2) {
+        mainloop<STAGES>(&tmA, &tmB, p.smem, p.full_bar, p.empty_bar, p.acc_bar, p.tmem_base, warp, lane, m0, K, HN);
+    } else {
+        const int quad = warp & 3;
+        const int row = m0 + quad * 32 + lane;
+        const uint32_t taddr = p.tmem_base + ((uint32_t)(quad * 32) << 16);
+        mbar_wait(p.acc_bar, 0);
+        tcgen05_fence_after();
+        // pass 1: row statistics (fp32), fast variance like flax: var = max(0, E[z^2] - E[z]^2)
+        float sum = 0.f, sq = 0.f;
+        for (int c = 0; c < HN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float z = __uint_as_float(r[j]); sum += z; sq = fmaf(z, z, sq); }
+        }
+        const float invH = 1.f / (float)HN;
+        const float mean = sum * invH;
+        const float var = fmaxf(0.f, sq * invH - mean * mean);
+        const float rstd = rsqrtf(var + LN_EPS);
+        if (row < M && rstd_out) rstd_out[row] = rstd;
+        // pass 2: normalise, scale/bias, ReLU, store bf16
+        const float* s = p.fsm;
+        const float* b = p.fsm + HN;
+        for (int c = 0; c < HN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c, r);
+            float xh[32], y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                xh[j] = (__uint_as_float(r[j]) - mean) * rstd;
+                y[j] = fmaxf(0.f, fmaf(xh[j], s[c + j], b[c + j]));
+            }
+            if (row < M) {
+                store_bf16x32(Y + (long long)row * HN + c, y);
+                if (XH) store_bf16x32(XH + (long long)row * HN + c, xh);
+            }
+        }
+    }
+    epilogue_done(p.tmem_base, tmem_cols, warp);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: dZ_prev = LN'/ReLU'(dY),  dY = dZ W^T  (accumulator), per-feature dscale / dbias
+// ------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(FUSED_THREADS)
+dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const float* __restrict__ scale, const float* __restrict__ bias,
+                      const __nv_bfloat16* __restrict__ XH, const float* __restrict__ rstd_in,
+                      __nv_bfloat16* __restrict__ DZ, float* __restrict__ dscale,
+                      float* __restrict__ dbias, int M, int K, int HN, uint32_t tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM;
+    Prologue p = prologue<STAGES>(smem_raw, &tmA, &tmB, HN, tmem_cols, scale, bias);
+    if (warp < 2) {
+        mainloop<STAGES>(&tmA, &tmB, p.smem, p.full_bar, p.empty_bar, p.acc_bar, p.tmem_base, warp, lane, m0, K, HN);
+    } else {
+        const int quad = warp & 3;
+        const int row = m0 + quad * 32 + lane;
+        const bool valid = row < M;
+        const uint32_t taddr = p.tmem_base + ((uint32_t)(quad * 32) << 16);
+        const float* s = p.fsm;
+        const float* b = p.fsm + HN;
+        float* cs = p.fsm + 2 * HN;          // per-CTA dscale partial
+        float* cb = p.fsm + 3 * HN;          // per-CTA dbias partial
+        const __nv_bfloat16* xrow = XH + (long long)(valid ? row : 0) * HN;
+        const float rstd = valid ? rstd_in[row] : 0.f;
+        mbar_wait(p.acc_bar, 0);
+        tcgen05_fence_after();
+        // pass 1: m1 = mean(dxhat), m2 = mean(dxhat * xhat); per-feature sums of du*xhat and du
+        float m1 = 0.f, m2 = 0.f;
+        for (int c = 0; c < HN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c, r);
+            float xh[32], gx[32], g[32];
+            load_bf16x32(xrow + c, xh);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float dy = valid ? __uint_as_float(r[j]) : 0.f;
+                const float du = (fmaf(xh[j], s[c + j], b[c + j]) > 0.f) ? dy : 0.f;   // ReLU mask
+                const float dxh = du * s[c + j];
+                m1 += dxh;
+                m2 = fmaf(dxh, xh[j], m2);
+                gx[j] = du * xh[j];
+                g[j] = du;
+            }
+            const float csum = warp_reduce_scatter32(gx, lane);
+            const float bsum = warp_reduce_scatter32(g, lane);
+            atomicAdd(&cs[c + lane], csum);
+            atomicAdd(&cb[c + lane], bsum);
+        }
+        const float invH = 1.f / (float)HN;
+        m1 *= invH;
+        m2 *= invH;
+        // pass 2: dz = rstd * (dxhat - m1 - xhat * m2)
+        for (int c = 0; c < HN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c, r);
+            float xh[32], dz[32];
+            load_bf16x32(xrow + c, xh);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float dy = __uint_as_float(r[j]);
+                const float du = (fmaf(xh[j], s[c + j], b[c + j]) > 0.f) ? dy : 0.f;
+                const float dxh = du * s[c + j];
+                dz[j] = rstd * (dxh - m1 - xh[j] * m2);
+            }
+            if (valid) store_bf16x32(DZ + (long long)row * HN + c, dz);
+        }
+        // the four epilogue warps publish the CTA's per-feature partials
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x - 64; i < HN; i += 128) {
+            atomicAdd(dscale + i, cs[i]);
+            atomicAdd(dbias + i, cb[i]);
+        }
+    }
+    epilogue_done(p.tmem_base, tmem_cols, warp);
+}
+
+uint32_t tmem_cols_for(int hn) {
+    uint32_t c = 32;
+    while ((int)c < hn) c <<= 1;
+    return c;
+}
+
+bool width_ok(int hn) { return hn >= 32 && hn % 32 == 0 && (hn <= 256 || hn == 512); }
+
+}  // namespace
+
+// X bf16 [M, K] (ldx) ; Wt bf16 [HN, K] (= W^T, ldw) ; scale/bias f32 [HN]
+// Y bf16 [M, HN] ; XH (may be NULL) bf16 [M, HN] ; rstd (may be NULL) f32 [M]
+MLB_API int mlb_dense_ln_relu_fwd_tc(void* stream, const void* X, const void* Wt, const float* scale,
+                                     const float* bias, void* Y, void* XH, float* rstd, int M, int K,
+                                     int HN, int ldx, int ldw) {
+    MLB_REQUIRE(X && Wt && scale && bias && Y && M > 0 && K > 0 && width_ok(HN));
+    MLB_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && mlb_aligned16(X) && mlb_aligned16(Wt) && mlb_aligned16(Y) &&
+                (XH == nullptr || mlb_aligned16(XH)));
+    CUtensorMap tA, tB;
+    int rc = make_map(&tA, X, K, M, ldx, 64, 128);
+    if (rc) return rc;
+    rc = make_map(&tB, Wt, K, HN, ldw, 64, HN > 256 ? 256 : HN);
+    if (rc) return rc;
+    constexpr int ST = 2;
+    const int smem = FusedSmem<ST>::total(HN);
+    auto kern = dense_ln_relu_fwd_kernel<ST>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<mlb_cdiv(M, BM), FUSED_THREADS, smem, mlb_stream(stream)>>>(
+        tA, tB, scale, bias, reinterpret_cast<__nv_bfloat16*>(Y), reinterpret_cast<__nv_bfloat16*>(XH), rstd,
+        M, K, HN, tmem_cols_for(HN));
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+// DZ_in bf16 [M, K] (lda) : gradient w.r.t. this layer's pre-activation (K = this layer's width,
+//   or the head width for the last layer) ; W bf16 [HN, K] (ldw): this layer's kernel [in=HN, out=K]
+// scale/bias/XH/rstd: the PREVIOUS layer's LayerNorm parameters and stashed forward state
+// DZ_out bf16 [M, HN] ; dscale/dbias f32 [HN] accumulated with atomics (pre-zeroed)
+MLB_API int mlb_dense_dx_lnbwd_tc(void* stream, const void* DZ_in, const void* W, const float* scale,
+                                  const float* bias, const void* XH, const float* rstd, void* DZ_out,
+                                  float* dscale, float* dbias, int M, int K, int HN, int lda, int ldw) {
+    MLB_REQUIRE(DZ_in && W && scale && bias && XH && rstd && DZ_out && dscale && dbias);
+    MLB_REQUIRE(M > 0 && K > 0 && width_ok(HN) && lda % 8 == 0 && ldw % 8 == 0);
+    MLB_REQUIRE(mlb_aligned16(DZ_in) && mlb_aligned16(W) && mlb_aligned16(XH) && mlb_aligned16(DZ_out));
+    CUtensorMap tA, tB;
+    int rc = make_map(&tA, DZ_in, K, M, lda, 64, 128);
+    if (rc) return rc;
+    rc = make_map(&tB, W, K, HN, ldw, 64, HN > 256 ? 256 : HN);
+    if (rc) return rc;
+    constexpr int ST = 2;
+    const int smem = FusedSmem<ST>::total(HN);
+    auto kern = dense_dx_lnbwd_kernel<ST>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<mlb_cdiv(M, BM), FUSED_THREADS, smem, mlb_stream(stream)>>>(
+        tA, tB, scale, bias, reinterpret_cast<const __nv_bfloat16*>(XH), rstd,
+        reinterpret_cast<__nv_bfloat16*>(DZ_out), dscale, dbias, M, K, HN, tmem_cols_for(HN));
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}

@@ -269,7 +269,7 @@ class PolicyProgram:
         if w is None or w['rows'] < rows:
             dev = self.device
             AT = torch.bfloat16 if self.tc else F32
-            w = dict(rows=rows, z=torch.empty(rows, self.H, dtype=F32, device=dev),
+            w = dict(rows=rows, z=None if self.tc else torch.empty(rows, self.H, dtype=F32, device=dev),
                      y=[torch.empty(rows, self.H, dtype=AT, device=dev) for _ in range(2)],
                      head=torch.empty(rows, self.NH, dtype=F32, device=dev))
             if self.tc:
@@ -283,9 +283,9 @@ class PolicyProgram:
             dev = self.device
             AT = torch.bfloat16 if self.tc else F32
             e = lambda *s, dtype=F32: torch.empty(*s, dtype=dtype, device=dev)
-            w = dict(rows=rows, z=[e(rows, self.H) for _ in range(self.L)],
+            w = dict(rows=rows, z=None if self.tc else [e(rows, self.H) for _ in range(self.L)],
                      y=[e(rows, self.H, dtype=AT) for _ in range(self.L)],
-                     stats=[e(rows, 2) for _ in range(self.L)],
+                     stats=None if self.tc else [e(rows, 2) for _ in range(self.L)],
                      head=e(rows, self.NH), dhead=e(rows, self.NH),
                      dy=e(rows, self.H, dtype=AT), dz=e(rows, self.H, dtype=AT),
                      loss_ws=torch.empty(_lib.lib().mlb_ppo_loss_workspace(rows) + 16, dtype=torch.uint8, device=dev),
@@ -293,6 +293,10 @@ class PolicyProgram:
             if self.tc:
                 w['x'] = e(rows, self.obs_dim, dtype=AT)
                 w['dhead16'] = e(rows, self.NH, dtype=AT)
+                w['xh'] = [e(rows, self.H, dtype=AT) for _ in range(self.L)]     # normalised pre-activations
+                w['rstd'] = [e(rows) for _ in range(self.L)]
+                w['dz2'] = e(rows, self.H, dtype=AT)
+                w['z'] = None                                                    # never materialised
             self._train_ws = w
         return w
 
@@ -303,8 +307,7 @@ class PolicyProgram:
         """obs f32 [rows, D] -> head f32 [rows, NH] (logits | value)."""
         w = self.infer_ws(rows)
         if self.tc:
-            return self._forward_tc(obs, rows, w, [w['z']] * self.L, [w['y'][i & 1] for i in range(self.L)],
-                                    [None] * self.L)
+            return self._forward_tc(obs, rows, w, [w['y'][i & 1] for i in range(self.L)], None, None)
         x, d = obs, self.obs_dim
         for i in range(self.L):
             k, s, b = self.layer_views(self.params, i)
@@ -316,16 +319,16 @@ class PolicyProgram:
         gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
         return w['head']
 
-    def _forward_tc(self, obs, rows, w, zs, ys, stats):
-        """bf16 tensor-core forward: cast obs -> [tcgen05 GEMM -> LayerNorm+ReLU (bf16 out)] x L
-        -> head GEMM (fp32 out + bias)."""
+    def _forward_tc(self, obs, rows, w, ys, xhs, rstds):
+        """bf16 tensor-core forward: cast obs -> L x fused [tcgen05 GEMM + LayerNorm + ReLU epilogue
+        out of TMEM] -> head GEMM (fp32 out + bias).  Training also stashes xhat (bf16) and rstd."""
         call('mlb_cast_f32_bf16', ptr(obs), ptr(w['x']), c_ll(rows * self.obs_dim))
         x, d = w['x'], self.obs_dim
         for i in range(self.L):
             _, s, b = self.layer_views(self.params, i)
-            gemm_tc(x, self.w_t[i], zs[i], None, rows, self.H, d, d, d, self.H, 0, 0, 0)
-            call('mlb_ln_relu_fwd_bf16', ptr(zs[i]), ptr(s), ptr(b), ptr(ys[i]), ptr(stats[i]), c_ll(rows),
-                 c_int(self.H))
+            call('mlb_dense_ln_relu_fwd_tc', ptr(x), ptr(self.w_t[i]), ptr(s), ptr(b), ptr(ys[i]),
+                 ptr(None if xhs is None else xhs[i]), ptr(None if rstds is None else rstds[i]),
+                 c_int(rows), c_int(d), c_int(self.H), c_int(d), c_int(d))
             x, d = ys[i], self.H
         _, B = self.head_views(self.params)
         gemm_tc(x, self.wh_t, w['head'], B, rows, self.NH, self.feat, self.feat, self.feat, self.NH, 0, 0, 0)
@@ -343,7 +346,7 @@ class PolicyProgram:
     def forward_train(self, obs, rows):
         w = self.train_ws(rows)
         if self.tc:
-            return self._forward_tc(obs, rows, w, w['z'], w['y'], w['stats'])
+            return self._forward_tc(obs, rows, w, w['y'], w['xh'], w['rstd'])
         x, d = obs, self.obs_dim
         for i in range(self.L):
             k, s, b = self.layer_views(self.params, i)
@@ -390,18 +393,26 @@ class PolicyProgram:
         gemm_tc(feat, w['dhead16'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH, 1, 1, 2,
                 _splitk_tc(self.feat, self.NH, rows))
         call('mlb_colsum_f32', ptr(w['dhead']), c_ll(rows), c_int(self.NH), c_int(self.NH), ptr(gB))
-        gemm_tc(w['dhead16'], self.wh_c, w['dy'], None, rows, self.feat, self.NH, self.NH, self.NH, self.feat,
-                0, 0, 1)
+        # dfeat = dhead Wh^T fused with the LayerNorm/ReLU backward of the last layer -> dZ_{L-1}
+        dz_cur, dz_nxt = w['dz'], w['dz2']
+        i = self.L - 1
+        _, s, b = self.layer_views(self.params, i)
+        _, gs, gb = self.layer_views(self.grads, i)
+        call('mlb_dense_dx_lnbwd_tc', ptr(w['dhead16']), ptr(self.wh_c), ptr(s), ptr(b), ptr(w['xh'][i]),
+             ptr(w['rstd'][i]), ptr(dz_cur), ptr(gs), ptr(gb), c_int(rows), c_int(self.NH), c_int(self.H),
+             c_int(self.NH), c_int(self.NH))
         for i in range(self.L - 1, -1, -1):
-            _, s, b = self.layer_views(self.params, i)
-            gk, gs, gb = self.layer_views(self.grads, i)
+            gk, _, _ = self.layer_views(self.grads, i)
             d = self.layer_off[i][2]
-            call('mlb_ln_relu_bwd_bf16', ptr(w['dy']), ptr(w['z'][i]), ptr(w['stats'][i]), ptr(s), ptr(b),
-                 ptr(w['dz']), ptr(gs), ptr(gb), c_ll(rows), c_int(self.H))
             x = w['x'] if i == 0 else w['y'][i - 1]
-            gemm_tc(x, w['dz'], gk, None, d, self.H, rows, d, self.H, self.H, 1, 1, 2, _splitk_tc(d, self.H, rows))
+            gemm_tc(x, dz_cur, gk, None, d, self.H, rows, d, self.H, self.H, 1, 1, 2, _splitk_tc(d, self.H, rows))
             if i > 0:
-                gemm_tc(w['dz'], self.w_c[i], w['dy'], None, rows, d, self.H, self.H, self.H, d, 0, 0, 1)
+                _, s, b = self.layer_views(self.params, i - 1)
+                _, gs, gb = self.layer_views(self.grads, i - 1)
+                call('mlb_dense_dx_lnbwd_tc', ptr(dz_cur), ptr(self.w_c[i]), ptr(s), ptr(b), ptr(w['xh'][i - 1]),
+                     ptr(w['rstd'][i - 1]), ptr(dz_nxt), ptr(gs), ptr(gb), c_int(rows), c_int(self.H), c_int(d),
+                     c_int(self.H), c_int(self.H))
+                dz_cur, dz_nxt = dz_nxt, dz_cur
 
     def zero_grads(self):
         call('mlb_fill_zero', ptr(self.grads), c_size_t(self.num_params * 4))

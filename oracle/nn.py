@@ -62,12 +62,17 @@ def _id(x):
 
 
 def mlp_fwd(x, layers, q=None):
+    quant = q is not None
     q = q or _id
     caches = []
     x = q(x)
     for lyr in layers:
         z = x @ q(lyr['kernel'])
         y, c = layernorm_relu_fwd(z, lyr['scale'], lyr['bias'])
+        if quant:
+            # the tensor-core path stashes xhat in bf16 and re-derives the ReLU mask from it
+            xh = q(c[0])
+            c = (xh, c[1], (xh * lyr['scale'] + lyr['bias']) > 0)
         caches.append((x, c))
         x = q(y)
     return x, caches
