@@ -30,7 +30,7 @@ struct FusedSmem {
     static __host__ __device__ constexpr int bar_off(int hn) { return STAGES * stage_bytes(hn); }
     // + barriers (2*STAGES+1) + tmem slot + scale/bias (2*hn floats) + colsum (2*hn floats) + slack
     static __host__ __device__ constexpr int total(int hn) {
-        return bar_off(hn) + (2 * STAGES + 1) * 8 + 16 + 4 * hn * 4 + 1024;
+        return bar_off(hn) + (2 * STAGES + 2) * 8 + 16 + 4 * hn * 4 + 1024;
     }
 };
 
@@ -97,7 +97,7 @@ __device__ __forceinline__ void mainloop(const CUtensorMap* tmA, const CUtensorM
 
 struct Prologue {
     uint8_t* smem;
-    uint64_t *full_bar, *empty_bar, *acc_bar;
+    uint64_t *full_bar, *empty_bar, *acc_bar, *aux_bar;
     float* fsm;            // 4*HN floats: scale | bias | colsum0 | colsum1
     uint32_t tmem_base;
 };
@@ -111,7 +111,8 @@ __device__ __forceinline__ Prologue prologue(uint8_t* smem_raw, const CUtensorMa
     p.full_bar = reinterpret_cast<uint64_t*>(p.smem + FusedSmem<STAGES>::bar_off(HN));
     p.empty_bar = p.full_bar + STAGES;
     p.acc_bar = p.empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p.acc_bar + 1);
+    p.aux_bar = p.acc_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p.aux_bar + 1);
     p.fsm = reinterpret_cast<float*>(tmem_slot + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -119,6 +120,7 @@ __device__ __forceinline__ Prologue prologue(uint8_t* smem_raw, const CUtensorMa
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmB)) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&p.full_bar[s], 1); mbar_init(&p.empty_bar[s], 1); }
         mbar_init(p.acc_bar, 1);
+        mbar_init(p.aux_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -174,9 +176,10 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&v
 template <int STAGES>
 __global__ void __launch_bounds__(FUSED_THREADS)
 dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmXH,
                          const float* __restrict__ scale, const float* __restrict__ bias,
-                         __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ XH,
-                         float* __restrict__ rstd_out, int M, int K, int HN, uint32_t tmem_cols) {
+                         int has_xh, float* __restrict__ rstd_out, int M, int K, int HN,
+                         uint32_t tmem_cols) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM;
@@ -185,9 +188,11 @@ dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mainloop<STAGES>(&tmA, &tmB, p.smem, p.full_bar, p.empty_bar, p.acc_bar, p.tmem_base, warp, lane, m0, K, HN);
     } else {
         const int quad = warp & 3;
-        const int row = m0 + quad * 32 + lane;
+        const int rt = quad * 32 + lane;                 // row inside the tile = TMEM lane
+        const int row = m0 + rt;
+        const int et = threadIdx.x - 64;                 // epilogue thread id 0..127
         const uint32_t taddr = p.tmem_base + ((uint32_t)(quad * 32) << 16);
-        mbar_wait(p.acc_bar, 0);
+        mbar_wait(p.acc_bar, 0);                         // all MMAs retired: operand stages are free
         tcgen05_fence_after();
         // pass 1: row statistics (fp32), fast variance like flax: var = max(0, E[z^2] - E[z]^2)
         float sum = 0.f, sq = 0.f;
@@ -202,23 +207,50 @@ dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const float var = fmaxf(0.f, sq * invH - mean * mean);
         const float rstd = rsqrtf(var + LN_EPS);
         if (row < M && rstd_out) rstd_out[row] = rstd;
-        // pass 2: normalise, scale/bias, ReLU, store bf16
+        // pass 2: normalise, scale/bias, ReLU -> bf16 into SWIZZLE_128B panels in the (now free)
+        // operand stages -> TMA store.  Two 32 KB panel buffers (Y | XH), 64 columns per panel.
         const float* s = p.fsm;
         const float* b = p.fsm + HN;
-        for (int c = 0; c < HN; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c, r);
-            float xh[32], y[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                xh[j] = (__uint_as_float(r[j]) - mean) * rstd;
-                y[j] = fmaxf(0.f, fmaf(xh[j], s[c + j], b[c + j]));
+        const int num_panels = HN / 64;
+        for (int pnl = 0; pnl < num_panels; ++pnl) {
+            uint8_t* buf = p.smem + (pnl & 1) * 32768;
+            if (pnl >= 2) {                               // buffer reuse: its previous store must have read it
+                if (et == 0) tma_store_wait_read<1>();
+                named_bar_sync(1, 128);
             }
-            if (row < M) {
-                store_bf16x32(Y + (long long)row * HN + c, y);
-                if (XH) store_bf16x32(XH + (long long)row * HN + c, xh);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int c = pnl * 64 + half * 32;
+                uint32_t r[32];
+                tmem_ld32(taddr + c, r);
+                float xh[32], y[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    xh[j] = (__uint_as_float(r[j]) - mean) * rstd;
+                    y[j] = fmaxf(0.f, fmaf(xh[j], s[c + j], b[c + j]));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 o;
+                    o.x = pack_bf16(y[8 * q], y[8 * q + 1]); o.y = pack_bf16(y[8 * q + 2], y[8 * q + 3]);
+                    o.z = pack_bf16(y[8 * q + 4], y[8 * q + 5]); o.w = pack_bf16(y[8 * q + 6], y[8 * q + 7]);
+                    *reinterpret_cast<uint4*>(buf + sw128(rt, half * 4 + q)) = o;
+                    if (has_xh) {
+                        o.x = pack_bf16(xh[8 * q], xh[8 * q + 1]); o.y = pack_bf16(xh[8 * q + 2], xh[8 * q + 3]);
+                        o.z = pack_bf16(xh[8 * q + 4], xh[8 * q + 5]); o.w = pack_bf16(xh[8 * q + 6], xh[8 * q + 7]);
+                        *reinterpret_cast<uint4*>(buf + 16384 + sw128(rt, half * 4 + q)) = o;
+                    }
+                }
+            }
+            fence_async_smem();
+            named_bar_sync(1, 128);
+            if (et == 0) {
+                tma_store_2d(&tmY, buf, pnl * 64, m0);    // rows >= M are clipped by the tensor map
+                if (has_xh) tma_store_2d(&tmXH, buf + 16384, pnl * 64, m0);
+                tma_store_commit();
             }
         }
+        if (et == 0) tma_store_wait<0>();
     }
     epilogue_done(p.tmem_base, tmem_cols, warp);
 }
@@ -229,9 +261,9 @@ dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 template <int STAGES>
 __global__ void __launch_bounds__(FUSED_THREADS)
 dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmXH, const __grid_constant__ CUtensorMap tmDZ,
                       const float* __restrict__ scale, const float* __restrict__ bias,
-                      const __nv_bfloat16* __restrict__ XH, const float* __restrict__ rstd_in,
-                      __nv_bfloat16* __restrict__ DZ, float* __restrict__ dscale,
+                      const float* __restrict__ rstd_in, float* __restrict__ dscale,
                       float* __restrict__ dbias, int M, int K, int HN, uint32_t tmem_cols) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,33 +273,54 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mainloop<STAGES>(&tmA, &tmB, p.smem, p.full_bar, p.empty_bar, p.acc_bar, p.tmem_base, warp, lane, m0, K, HN);
     } else {
         const int quad = warp & 3;
-        const int row = m0 + quad * 32 + lane;
+        const int rt = quad * 32 + lane;
+        const int row = m0 + rt;
+        const int et = threadIdx.x - 64;
         const bool valid = row < M;
         const uint32_t taddr = p.tmem_base + ((uint32_t)(quad * 32) << 16);
         const float* s = p.fsm;
         const float* b = p.fsm + HN;
         float* cs = p.fsm + 2 * HN;          // per-CTA dscale partial
         float* cb = p.fsm + 3 * HN;          // per-CTA dbias partial
-        const __nv_bfloat16* xrow = XH + (long long)(valid ? row : 0) * HN;
         const float rstd = valid ? rstd_in[row] : 0.f;
-        mbar_wait(p.acc_bar, 0);
+        const int num_panels = HN / 64;
+        mbar_wait(p.acc_bar, 0);             // MMAs retired: operand stages are free
         tcgen05_fence_after();
+        // xhat tile [128 x HN] bf16 -> SWIZZLE_128B panels in the freed operand stages (TMA load,
+        // rows >= M zero-filled); dz is later written in place and TMA-stored from the same panels
+        if (et == 0) {
+            mbar_expect_tx(p.aux_bar, (uint32_t)num_panels * 16384u);
+            for (int pnl = 0; pnl < num_panels; ++pnl)
+                tma_load_2d(&tmXH, p.aux_bar, p.smem + pnl * 16384, pnl * 64, m0);
+        }
+        mbar_wait(p.aux_bar, 0);
         // pass 1: m1 = mean(dxhat), m2 = mean(dxhat * xhat); per-feature sums of du*xhat and du
         float m1 = 0.f, m2 = 0.f;
         for (int c = 0; c < HN; c += 32) {
             uint32_t r[32];
             tmem_ld32(taddr + c, r);
-            float xh[32], gx[32], g[32];
-            load_bf16x32(xrow + c, xh);
+            const uint8_t* pan = p.smem + (c >> 6) * 16384;
+            const int half = (c >> 5) & 1;
+            float gx[32], g[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float dy = valid ? __uint_as_float(r[j]) : 0.f;
-                const float du = (fmaf(xh[j], s[c + j], b[c + j]) > 0.f) ? dy : 0.f;   // ReLU mask
-                const float dxh = du * s[c + j];
-                m1 += dxh;
-                m2 = fmaf(dxh, xh[j], m2);
-                gx[j] = du * xh[j];
-                g[j] = du;
+            for (int q = 0; q < 4; ++q) {
+                const uint4 u = *reinterpret_cast<const uint4*>(pan + sw128(rt, half * 4 + q));
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const int j = 8 * q + 2 * e + hlf;
+                        const float xh = hlf ? bf16hi(w4[e]) : bf16lo(w4[e]);
+                        const float dy = __uint_as_float(r[j]);
+                        const float du = (fmaf(xh, s[c + j], b[c + j]) > 0.f) ? dy : 0.f;   // ReLU mask
+                        const float dxh = du * s[c + j];
+                        m1 += dxh;
+                        m2 = fmaf(dxh, xh, m2);
+                        gx[j] = du * xh;
+                        g[j] = du;
+                    }
+                }
             }
             const float csum = warp_reduce_scatter32(gx, lane);
             const float bsum = warp_reduce_scatter32(g, lane);
@@ -277,27 +330,48 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const float invH = 1.f / (float)HN;
         m1 *= invH;
         m2 *= invH;
-        // pass 2: dz = rstd * (dxhat - m1 - xhat * m2)
+        // pass 2: dz = rstd * (dxhat - m1 - xhat * m2), written over xhat in the panels
         for (int c = 0; c < HN; c += 32) {
             uint32_t r[32];
             tmem_ld32(taddr + c, r);
-            float xh[32], dz[32];
-            load_bf16x32(xrow + c, xh);
+            uint8_t* pan = p.smem + (c >> 6) * 16384;
+            const int half = (c >> 5) & 1;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float dy = __uint_as_float(r[j]);
-                const float du = (fmaf(xh[j], s[c + j], b[c + j]) > 0.f) ? dy : 0.f;
-                const float dxh = du * s[c + j];
-                dz[j] = rstd * (dxh - m1 - xh[j] * m2);
+            for (int q = 0; q < 4; ++q) {
+                uint4* slot = reinterpret_cast<uint4*>(pan + sw128(rt, half * 4 + q));
+                const uint4 u = *slot;
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                uint32_t o4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float dz2[2];
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const int j = 8 * q + 2 * e + hlf;
+                        const float xh = hlf ? bf16hi(w4[e]) : bf16lo(w4[e]);
+                        const float dy = __uint_as_float(r[j]);
+                        const float du = (fmaf(xh, s[c + j], b[c + j]) > 0.f) ? dy : 0.f;
+                        const float dxh = du * s[c + j];
+                        dz2[hlf] = rstd * (dxh - m1 - xh * m2);
+                    }
+                    o4[e] = pack_bf16(dz2[0], dz2[1]);
+                }
+                *slot = make_uint4(o4[0], o4[1], o4[2], o4[3]);
             }
-            if (valid) store_bf16x32(DZ + (long long)row * HN + c, dz);
         }
-        // the four epilogue warps publish the CTA's per-feature partials
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = threadIdx.x - 64; i < HN; i += 128) {
+        fence_async_smem();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+            for (int pnl = 0; pnl < num_panels; ++pnl)
+                tma_store_2d(&tmDZ, p.smem + pnl * 16384, pnl * 64, m0);
+            tma_store_commit();
+        }
+        // the four epilogue warps publish the CTA's per-feature partials (bar above ordered the atomics)
+        for (int i = et; i < HN; i += 128) {
             atomicAdd(dscale + i, cs[i]);
             atomicAdd(dbias + i, cb[i]);
         }
+        if (et == 0) tma_store_wait<0>();
     }
     epilogue_done(p.tmem_base, tmem_cols, warp);
 }
@@ -308,7 +382,7 @@ uint32_t tmem_cols_for(int hn) {
     return c;
 }
 
-bool width_ok(int hn) { return hn >= 32 && hn % 32 == 0 && (hn <= 256 || hn == 512); }
+bool width_ok(int hn) { return hn >= 64 && hn % 64 == 0 && (hn <= 256 || hn == 512); }
 
 }  // namespace
 
@@ -325,14 +399,18 @@ MLB_API int mlb_dense_ln_relu_fwd_tc(void* stream, const void* X, const void* Wt
     if (rc) return rc;
     rc = make_map(&tB, Wt, K, HN, ldw, 64, HN > 256 ? 256 : HN);
     if (rc) return rc;
+    CUtensorMap tY, tXH;
+    rc = make_map(&tY, Y, HN, M, HN, 64, 128);
+    if (rc) return rc;
+    rc = make_map(&tXH, XH ? XH : Y, HN, M, HN, 64, 128);
+    if (rc) return rc;
     constexpr int ST = 2;
     const int smem = FusedSmem<ST>::total(HN);
     auto kern = dense_ln_relu_fwd_kernel<ST>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<mlb_cdiv(M, BM), FUSED_THREADS, smem, mlb_stream(stream)>>>(
-        tA, tB, scale, bias, reinterpret_cast<__nv_bfloat16*>(Y), reinterpret_cast<__nv_bfloat16*>(XH), rstd,
-        M, K, HN, tmem_cols_for(HN));
+        tA, tB, tY, tXH, scale, bias, XH ? 1 : 0, rstd, M, K, HN, tmem_cols_for(HN));
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }
@@ -352,14 +430,18 @@ MLB_API int mlb_dense_dx_lnbwd_tc(void* stream, const void* DZ_in, const void* W
     if (rc) return rc;
     rc = make_map(&tB, W, K, HN, ldw, 64, HN > 256 ? 256 : HN);
     if (rc) return rc;
+    CUtensorMap tXH, tDZ;
+    rc = make_map(&tXH, XH, HN, M, HN, 64, 128);
+    if (rc) return rc;
+    rc = make_map(&tDZ, DZ_out, HN, M, HN, 64, 128);
+    if (rc) return rc;
     constexpr int ST = 2;
     const int smem = FusedSmem<ST>::total(HN);
     auto kern = dense_dx_lnbwd_kernel<ST>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<mlb_cdiv(M, BM), FUSED_THREADS, smem, mlb_stream(stream)>>>(
-        tA, tB, scale, bias, reinterpret_cast<const __nv_bfloat16*>(XH), rstd,
-        reinterpret_cast<__nv_bfloat16*>(DZ_out), dscale, dbias, M, K, HN, tmem_cols_for(HN));
+        tA, tB, tXH, tDZ, scale, bias, rstd, dscale, dbias, M, K, HN, tmem_cols_for(HN));
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }
