@@ -20,7 +20,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int FUSED_THREADS = 192;
+constexpr int FUSED_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 column halves x 4 lane quadrants)
 constexpr float LN_EPS = 1e-6f;
 
 template <int STAGES>
@@ -30,9 +30,14 @@ struct FusedSmem {
     static __host__ __device__ constexpr int bar_off(int hn) { return STAGES * stage_bytes(hn); }
     // + barriers (2*STAGES+1) + tmem slot + scale/bias (2*hn floats) + colsum (2*hn floats) + slack
     static __host__ __device__ constexpr int total(int hn) {
-        return bar_off(hn) + (2 * STAGES + 2) * 8 + 16 + 4 * hn * 4 + 1024;
+        return bar_off(hn) + (2 * STAGES + 2) * 8 + 16 + (4 * hn + 512) * 4 + 1024;
     }
 };
+
+// barrier of one 128-thread epilogue half-group (compile-time ids keep the barrier count low)
+__device__ __forceinline__ void group_bar(int half) {
+    if (half == 0) named_bar_sync(1, 128); else named_bar_sync(2, 128);
+}
 
 // 32-value warp reduce-scatter: on return lane i holds sum over the 32 lanes of v[i].
 __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
@@ -98,7 +103,7 @@ __device__ __forceinline__ void mainloop(const CUtensorMap* tmA, const CUtensorM
 struct Prologue {
     uint8_t* smem;
     uint64_t *full_bar, *empty_bar, *acc_bar, *aux_bar;
-    float* fsm;            // 4*HN floats: scale | bias | colsum0 | colsum1
+    float* fsm;            // 4*HN + 512 floats: scale | bias | colsum0 | colsum1 | row partials [2][128][2]
     uint32_t tmem_base;
 };
 
@@ -174,7 +179,7 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&v
 // forward: Y = relu(LN(X W))
 // ------------------------------------------------------------------------------------------
 template <int STAGES>
-__global__ void __launch_bounds__(FUSED_THREADS)
+__global__ void __launch_bounds__(FUSED_THREADS, 2)
 dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmXH,
                          const float* __restrict__ scale, const float* __restrict__ bias,
@@ -187,40 +192,50 @@ dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp < 2) {
         mainloop<STAGES>(&tmA, &tmB, p.smem, p.full_bar, p.empty_bar, p.acc_bar, p.tmem_base, warp, lane, m0, K, HN);
     } else {
-        const int quad = warp & 3;
+        const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;                // column half handled by this warp
         const int rt = quad * 32 + lane;                 // row inside the tile = TMEM lane
         const int row = m0 + rt;
-        const int et = threadIdx.x - 64;                 // epilogue thread id 0..127
+        const int et = (((warp - 2) & 3) << 5) | lane;   // thread id inside the half-group, 0..127
         const uint32_t taddr = p.tmem_base + ((uint32_t)(quad * 32) << 16);
+        float* part = p.fsm + 4 * HN;                    // [2][128][2] row partials
+        const int nchunks = HN / 32, num_panels = HN / 64;
         mbar_wait(p.acc_bar, 0);                         // all MMAs retired: operand stages are free
         tcgen05_fence_after();
-        // pass 1: row statistics (fp32), fast variance like flax: var = max(0, E[z^2] - E[z]^2)
+        // pass 1: row statistics (fp32) over this half's columns, combined through shared memory;
+        // fast variance like flax: var = max(0, E[z^2] - E[z]^2)
         float sum = 0.f, sq = 0.f;
-        for (int c = 0; c < HN; c += 32) {
+        for (int ch = half * nchunks / 2; ch < (half + 1) * nchunks / 2; ++ch) {
             uint32_t r[32];
-            tmem_ld32(taddr + c, r);
+            tmem_ld32(taddr + ch * 32, r);
 #pragma unroll
             for (int j = 0; j < 32; ++j) { const float z = __uint_as_float(r[j]); sum += z; sq = fmaf(z, z, sq); }
         }
+        part[(half * 128 + rt) * 2] = sum;
+        part[(half * 128 + rt) * 2 + 1] = sq;
+        named_bar_sync(3, 256);
+        sum += part[((half ^ 1) * 128 + rt) * 2];
+        sq += part[((half ^ 1) * 128 + rt) * 2 + 1];
         const float invH = 1.f / (float)HN;
         const float mean = sum * invH;
         const float var = fmaxf(0.f, sq * invH - mean * mean);
         const float rstd = rsqrtf(var + LN_EPS);
-        if (row < M && rstd_out) rstd_out[row] = rstd;
+        if (half == 0 && row < M && rstd_out) rstd_out[row] = rstd;
         // pass 2: normalise, scale/bias, ReLU -> bf16 into SWIZZLE_128B panels in the (now free)
-        // operand stages -> TMA store.  Two 32 KB panel buffers (Y | XH), 64 columns per panel.
+        // operand stages -> TMA store.  One 32 KB panel buffer (Y | XH) per half-group.
         const float* s = p.fsm;
         const float* b = p.fsm + HN;
-        const int num_panels = HN / 64;
-        for (int pnl = 0; pnl < num_panels; ++pnl) {
-            uint8_t* buf = p.smem + (pnl & 1) * 32768;
-            if (pnl >= 2) {                               // buffer reuse: its previous store must have read it
-                if (et == 0) tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
+        uint8_t* buf = p.smem + half * 32768;
+        const int p_lo = num_panels >= 2 ? half * num_panels / 2 : 0;
+        const int p_hi = num_panels >= 2 ? (half + 1) * num_panels / 2 : (half == 0 ? 1 : 0);
+        for (int pnl = p_lo; pnl < p_hi; ++pnl) {
+            if (pnl > p_lo) {                             // buffer reuse: its previous store must have read it
+                if (et == 0) tma_store_wait_read<0>();
+                group_bar(half);
             }
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int c = pnl * 64 + half * 32;
+            for (int hf = 0; hf < 2; ++hf) {
+                const int c = pnl * 64 + hf * 32;
                 uint32_t r[32];
                 tmem_ld32(taddr + c, r);
                 float xh[32], y[32];
@@ -234,16 +249,16 @@ dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     uint4 o;
                     o.x = pack_bf16(y[8 * q], y[8 * q + 1]); o.y = pack_bf16(y[8 * q + 2], y[8 * q + 3]);
                     o.z = pack_bf16(y[8 * q + 4], y[8 * q + 5]); o.w = pack_bf16(y[8 * q + 6], y[8 * q + 7]);
-                    *reinterpret_cast<uint4*>(buf + sw128(rt, half * 4 + q)) = o;
+                    *reinterpret_cast<uint4*>(buf + sw128(rt, hf * 4 + q)) = o;
                     if (has_xh) {
                         o.x = pack_bf16(xh[8 * q], xh[8 * q + 1]); o.y = pack_bf16(xh[8 * q + 2], xh[8 * q + 3]);
                         o.z = pack_bf16(xh[8 * q + 4], xh[8 * q + 5]); o.w = pack_bf16(xh[8 * q + 6], xh[8 * q + 7]);
-                        *reinterpret_cast<uint4*>(buf + 16384 + sw128(rt, half * 4 + q)) = o;
+                        *reinterpret_cast<uint4*>(buf + 16384 + sw128(rt, hf * 4 + q)) = o;
                     }
                 }
             }
             fence_async_smem();
-            named_bar_sync(1, 128);
+            group_bar(half);
             if (et == 0) {
                 tma_store_2d(&tmY, buf, pnl * 64, m0);    // rows >= M are clipped by the tensor map
                 if (has_xh) tma_store_2d(&tmXH, buf + 16384, pnl * 64, m0);
@@ -259,7 +274,7 @@ dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // backward: dZ_prev = LN'/ReLU'(dY),  dY = dZ W^T  (accumulator), per-feature dscale / dbias
 // ------------------------------------------------------------------------------------------
 template <int STAGES>
-__global__ void __launch_bounds__(FUSED_THREADS)
+__global__ void __launch_bounds__(FUSED_THREADS, 2)
 dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmXH, const __grid_constant__ CUtensorMap tmDZ,
                       const float* __restrict__ scale, const float* __restrict__ bias,
@@ -273,22 +288,25 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mainloop<STAGES>(&tmA, &tmB, p.smem, p.full_bar, p.empty_bar, p.acc_bar, p.tmem_base, warp, lane, m0, K, HN);
     } else {
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int rt = quad * 32 + lane;
         const int row = m0 + rt;
-        const int et = threadIdx.x - 64;
+        const int et256 = threadIdx.x - 64;              // 0..255 over both half-groups
         const bool valid = row < M;
         const uint32_t taddr = p.tmem_base + ((uint32_t)(quad * 32) << 16);
         const float* s = p.fsm;
         const float* b = p.fsm + HN;
         float* cs = p.fsm + 2 * HN;          // per-CTA dscale partial
         float* cb = p.fsm + 3 * HN;          // per-CTA dbias partial
+        float* part = p.fsm + 4 * HN;        // [2][128][2] row partials
         const float rstd = valid ? rstd_in[row] : 0.f;
-        const int num_panels = HN / 64;
+        const int nchunks = HN / 32, num_panels = HN / 64;
+        const int ch_lo = half * nchunks / 2, ch_hi = (half + 1) * nchunks / 2;
         mbar_wait(p.acc_bar, 0);             // MMAs retired: operand stages are free
         tcgen05_fence_after();
         // xhat tile [128 x HN] bf16 -> SWIZZLE_128B panels in the freed operand stages (TMA load,
         // rows >= M zero-filled); dz is later written in place and TMA-stored from the same panels
-        if (et == 0) {
+        if (et256 == 0) {
             mbar_expect_tx(p.aux_bar, (uint32_t)num_panels * 16384u);
             for (int pnl = 0; pnl < num_panels; ++pnl)
                 tma_load_2d(&tmXH, p.aux_bar, p.smem + pnl * 16384, pnl * 64, m0);
@@ -296,22 +314,23 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_wait(p.aux_bar, 0);
         // pass 1: m1 = mean(dxhat), m2 = mean(dxhat * xhat); per-feature sums of du*xhat and du
         float m1 = 0.f, m2 = 0.f;
-        for (int c = 0; c < HN; c += 32) {
+        for (int ch = ch_lo; ch < ch_hi; ++ch) {
+            const int c = ch * 32;
             uint32_t r[32];
             tmem_ld32(taddr + c, r);
             const uint8_t* pan = p.smem + (c >> 6) * 16384;
-            const int half = (c >> 5) & 1;
+            const int hf = ch & 1;
             float gx[32], g[32];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint4 u = *reinterpret_cast<const uint4*>(pan + sw128(rt, half * 4 + q));
+                const uint4 u = *reinterpret_cast<const uint4*>(pan + sw128(rt, hf * 4 + q));
                 const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
 #pragma unroll
-                    for (int hlf = 0; hlf < 2; ++hlf) {
-                        const int j = 8 * q + 2 * e + hlf;
-                        const float xh = hlf ? bf16hi(w4[e]) : bf16lo(w4[e]);
+                    for (int hl = 0; hl < 2; ++hl) {
+                        const int j = 8 * q + 2 * e + hl;
+                        const float xh = hl ? bf16hi(w4[e]) : bf16lo(w4[e]);
                         const float dy = __uint_as_float(r[j]);
                         const float du = (fmaf(xh, s[c + j], b[c + j]) > 0.f) ? dy : 0.f;   // ReLU mask
                         const float dxh = du * s[c + j];
@@ -327,18 +346,24 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             atomicAdd(&cs[c + lane], csum);
             atomicAdd(&cb[c + lane], bsum);
         }
+        part[(half * 128 + rt) * 2] = m1;
+        part[(half * 128 + rt) * 2 + 1] = m2;
+        named_bar_sync(3, 256);
+        m1 += part[((half ^ 1) * 128 + rt) * 2];
+        m2 += part[((half ^ 1) * 128 + rt) * 2 + 1];
         const float invH = 1.f / (float)HN;
         m1 *= invH;
         m2 *= invH;
         // pass 2: dz = rstd * (dxhat - m1 - xhat * m2), written over xhat in the panels
-        for (int c = 0; c < HN; c += 32) {
+        for (int ch = ch_lo; ch < ch_hi; ++ch) {
+            const int c = ch * 32;
             uint32_t r[32];
             tmem_ld32(taddr + c, r);
             uint8_t* pan = p.smem + (c >> 6) * 16384;
-            const int half = (c >> 5) & 1;
+            const int hf = ch & 1;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                uint4* slot = reinterpret_cast<uint4*>(pan + sw128(rt, half * 4 + q));
+                uint4* slot = reinterpret_cast<uint4*>(pan + sw128(rt, hf * 4 + q));
                 const uint4 u = *slot;
                 const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
                 uint32_t o4[4];
@@ -346,13 +371,13 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 for (int e = 0; e < 4; ++e) {
                     float dz2[2];
 #pragma unroll
-                    for (int hlf = 0; hlf < 2; ++hlf) {
-                        const int j = 8 * q + 2 * e + hlf;
-                        const float xh = hlf ? bf16hi(w4[e]) : bf16lo(w4[e]);
+                    for (int hl = 0; hl < 2; ++hl) {
+                        const int j = 8 * q + 2 * e + hl;
+                        const float xh = hl ? bf16hi(w4[e]) : bf16lo(w4[e]);
                         const float dy = __uint_as_float(r[j]);
                         const float du = (fmaf(xh, s[c + j], b[c + j]) > 0.f) ? dy : 0.f;
                         const float dxh = du * s[c + j];
-                        dz2[hlf] = rstd * (dxh - m1 - xh * m2);
+                        dz2[hl] = rstd * (dxh - m1 - xh * m2);
                     }
                     o4[e] = pack_bf16(dz2[0], dz2[1]);
                 }
@@ -360,18 +385,18 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
         }
         fence_async_smem();
-        named_bar_sync(1, 128);
-        if (et == 0) {
+        named_bar_sync(3, 256);
+        if (et256 == 0) {
             for (int pnl = 0; pnl < num_panels; ++pnl)
                 tma_store_2d(&tmDZ, p.smem + pnl * 16384, pnl * 64, m0);
             tma_store_commit();
         }
-        // the four epilogue warps publish the CTA's per-feature partials (bar above ordered the atomics)
-        for (int i = et; i < HN; i += 128) {
+        // the eight epilogue warps publish the CTA's per-feature partials (bar above ordered the atomics)
+        for (int i = et256; i < HN; i += 256) {
             atomicAdd(dscale + i, cs[i]);
             atomicAdd(dbias + i, cb[i]);
         }
-        if (et == 0) tma_store_wait<0>();
+        if (et256 == 0) tma_store_wait<0>();
     }
     epilogue_done(p.tmem_base, tmem_cols, warp);
 }

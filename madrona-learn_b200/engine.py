@@ -41,7 +41,7 @@ def gemm_tc(A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn=0, b_mn=0, epi=0, splitk
 
 
 def _splitk_tc(M, N, K):
-    bn = 64 if N <= 64 else (128 if N <= 128 else 256)
+    bn = 64 if N <= 64 else 128          # the split-K (atomic) epilogue uses N tiles <= 128
     tiles = math.ceil(M / 128) * math.ceil(N / bn)
     want = max(1, 148 // tiles)
     return int(max(1, min(want, K // 256)))
