@@ -233,10 +233,14 @@ int mlb_sample_discrete_f32(void* stream, const float* head, int ld, const uint3
 /* mu_new, inv_sigma_new} (value normaliser before / after this minibatch's EMA update,     */
 /* ml/ppo.py:190-211).  obj_scale_host[i] = 1/(rows*A_g), ent_scale_host[i] =                */
 /* entropy_coef[g]/(rows*A_g) for component i of action group g (HOST arrays).              */
-/* d_head f32 [rows, ld] out.  stats out; ws of mlb_ppo_loss_workspace(rows) bytes.          */
+/* d_head [rows, ld] out: f32, or bf16 when flags has MLB_PPO_DHEAD_BF16 (tensor-core path); */
+/* padding columns are written as zeros.  d_bias (may be NULL): f32 [sumA+1], the heads' bias  */
+/* gradients (column sums of d_head) are ACCUMULATED here.  stats out; ws of                    */
+/* mlb_ppo_loss_workspace(rows) bytes.                                                         */
 /* ------------------------------------------------------------------------------------ */
 #define MLB_PPO_CLIP_VALUE_LOSS  1
 #define MLB_PPO_HUBER_VALUE_LOSS 2
+#define MLB_PPO_DHEAD_BF16       4
 typedef struct mlb_ppo_stats {
     float loss, action_obj, value_loss, entropy;
     mlb_metric metrics[5];   /* Loss, Action Obj, Value Loss, Value Errors (abs), Entropy
@@ -250,7 +254,7 @@ int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int32_t* act
                      const int32_t* buckets_host, const float* obj_scale_host,
                      const float* ent_scale_host, int num_components, long long rows,
                      long long M, float clip_coef, float value_loss_coef, int flags,
-                     float* d_head, mlb_ppo_stats* stats, void* ws, size_t ws_bytes);
+                     void* d_head, float* d_bias, mlb_ppo_stats* stats, void* ws, size_t ws_bytes);
 
 /* ------------------------------------------------------------------------------------ */
 /* K10: optimiser over a flat fp32 arena (ml/ppo.py:84-90,283-338).                         */
@@ -270,8 +274,17 @@ int mlb_sumsq_f32(void* stream, const float* x, long long n, double* out, void* 
 int mlb_adam_step_f32(void* stream, float* params, const float* grads, float* m, float* v,
                       long long n, const int32_t* step, const double* grad_sumsq, float lr,
                       float b1, float b2, float eps, float max_grad_norm, float grad_scale);
+/* Optional per-segment bf16 operand copies refreshed in the same pass (tensor-core path):  */
+/* the segment is an fp32 matrix [rows, cols]; dst_t = bf16 W^T [cols, rows] (ld_t), dst =   */
+/* bf16 W [rows, cols] (ld_d, may be NULL).  dst_t == NULL: no copy for this segment.         */
+typedef struct mlb_bf16_copy {
+    void* dst_t;
+    void* dst;
+    int32_t rows, cols, ld_t, ld_d;
+} mlb_bf16_copy;
+/* One 8-CTA thread-block cluster per segment (DSMEM reduction).  copies_dev may be NULL.    */
 int mlb_renorm_segments(void* stream, float* params, const mlb_segment* segments_dev,
-                        int num_segments, int32_t* step);
+                        int num_segments, int32_t* step, const mlb_bf16_copy* copies_dev);
 /* out[c] += sum_r x[r, c] for c < ncols (bias gradients of the heads) */
 int mlb_colsum_f32(void* stream, const float* x, long long rows, int ld, int ncols, float* out);
 

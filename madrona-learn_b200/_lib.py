@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmlb200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                             ctypes.c_float, ctypes.c_size_t)
@@ -74,14 +74,14 @@ SIGNATURES = {
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P]),
     'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),
     'mlb_ppo_loss_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, c_ll, c_ll,
-                                 c_float, c_float, c_int, P, P, P, c_size_t]),
+                                 c_float, c_float, c_int, P, P, P, P, c_size_t]),
     'mlb_fill_zero': (c_int, [P, P, c_size_t]),
     'mlb_copy_bytes': (c_int, [P, P, P, c_size_t]),
     'mlb_sumsq_workspace': (c_size_t, [c_ll]),
     'mlb_sumsq_f32': (c_int, [P, P, c_ll, P, P, c_size_t]),
     'mlb_adam_step_f32': (c_int, [P, P, P, P, P, c_ll, P, P, c_float, c_float, c_float, c_float,
                                   c_float, c_float]),
-    'mlb_renorm_segments': (c_int, [P, P, P, c_int, P]),
+    'mlb_renorm_segments': (c_int, [P, P, P, c_int, P, P]),
     'mlb_colsum_f32': (c_int, [P, P, c_ll, c_int, c_int, P]),
     'mlb_synth_env_init': (c_int, [P, P, c_ll, c_int, ctypes.c_uint32, P]),
     'mlb_synth_env_step': (c_int, [P, P, P, P, c_int, P, P, P, c_ll, c_int, ctypes.c_uint32,
@@ -92,6 +92,12 @@ SIGNATURES = {
 class Segment(ctypes.Structure):
     """mlb_segment."""
     _fields_ = [('offset', c_ll), ('length', c_ll), ('kind', ctypes.c_int32), ('target', c_float)]
+
+
+class Bf16Copy(ctypes.Structure):
+    """mlb_bf16_copy."""
+    _fields_ = [('dst_t', c_void_p), ('dst', c_void_p), ('rows', ctypes.c_int32), ('cols', ctypes.c_int32),
+                ('ld_t', ctypes.c_int32), ('ld_d', ctypes.c_int32)]
 
 
 class PPOStats(ctypes.Structure):

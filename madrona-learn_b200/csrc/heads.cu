@@ -11,6 +11,8 @@
 // A block stages a [128 x ld] tile of head rows in shared memory with coalesced 128-bit
 // loads, each thread then owns one row (conflict-free, stride ld+1), and gradients go back
 // through the same tile so global stores are coalesced too.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -38,25 +40,27 @@ __global__ void rollout_keys_kernel(uint32_t* __restrict__ prng_key, uint32_t* _
     policy_key[0] = p0; policy_key[1] = p1;
 }
 
-__device__ __forceinline__ void stage_in(float* tile, const float* __restrict__ g, long long row0,
-                                         long long rows, int ld) {
+// Division-free staging of the first `ncols` columns of a [128 x ld] tile of head rows: one warp
+// per row, lanes over columns (shared tile stride `ts` is odd -> conflict-free row access).
+__device__ __forceinline__ void stage_in(float* tile, int ts, const float* __restrict__ g, long long row0,
+                                         long long rows, int ld, int ncols) {
     const int nrow = (int)min((long long)ROWS_PER_BLOCK, rows - row0);
-    const int total = nrow * ld;
-    const float* src = g + row0 * ld;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int r = e / ld, c = e - r * ld;
-        tile[r * (ld + 1) + c] = __ldg(src + e);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < nrow; r += nw) {
+        const float* src = g + (row0 + r) * ld;
+        for (int c = lane; c < ncols; c += 32) tile[r * ts + c] = __ldg(src + c);
     }
 }
 
-__device__ __forceinline__ void stage_out(const float* tile, float* __restrict__ g, long long row0,
-                                          long long rows, int ld) {
+// Gradients back to global: fp32 or bf16 rows of width ld; columns >= ncols are written as zeros.
+template <typename T>
+__device__ __forceinline__ void stage_out(const float* tile, int ts, T* __restrict__ g, long long row0,
+                                          long long rows, int ld, int ncols) {
     const int nrow = (int)min((long long)ROWS_PER_BLOCK, rows - row0);
-    const int total = nrow * ld;
-    float* dst = g + row0 * ld;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int r = e / ld, c = e - r * ld;
-        dst[e] = tile[r * (ld + 1) + c];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < nrow; r += nw) {
+        T* dst = g + (row0 + r) * ld;
+        for (int c = lane; c < ld; c += 32) dst[c] = (T)(c < ncols ? tile[r * ts + c] : 0.f);
     }
 }
 
@@ -118,11 +122,13 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
                 const float* __restrict__ ret, const float* __restrict__ old_v,
                 const float* __restrict__ mb_w, const float* __restrict__ adv_mr,
                 const float* __restrict__ vn, Layout L, long long rows, long long M,
-                float clip, float vcoef, int flags, int vcol, float* __restrict__ dhead,
-                LossPartial* __restrict__ part) {
+                float clip, float vcoef, int flags, int vcol, void* __restrict__ dhead,
+                float* __restrict__ dbias, LossPartial* __restrict__ part) {
     extern __shared__ float tile[];
     const long long row0 = (long long)blockIdx.x * ROWS_PER_BLOCK;
-    stage_in(tile, head, row0, rows, ld);
+    const int ncols = vcol + 1;
+    const int ts = ncols | 1;                 // odd tile stride
+    stage_in(tile, ts, head, row0, rows, ld, ncols);
     __syncthreads();
     const long long row = row0 + threadIdx.x;
     double p_obj = 0.0, p_vl = 0.0, p_ent = 0.0;
@@ -132,7 +138,7 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
     auto acc = [&](int k, float x) { s[k] += (double)x; ss[k] += (double)x * (double)x;
                                      mn[k] = fminf(mn[k], x); mx[k] = fmaxf(mx[k], x); };
     if (row < rows) {
-        float* l = tile + threadIdx.x * (ld + 1);
+        float* l = tile + threadIdx.x * ts;
         const float w = mb_w ? mb_w[row % M] : 1.f;
         float a = adv[row];
         if (adv_mr) a = (a - adv_mr[0]) * adv_mr[1];                    // zscore_data, per minibatch
@@ -197,10 +203,18 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
         acc(1, vl);
         acc(2, fabsf(verr));
         l[vcol] = vcoef * w * dvl * vmask * inv_rows;
-        for (int c = vcol + 1; c < ld; ++c) l[c] = 0.f;                 // padding columns
     }
     __syncthreads();
-    stage_out(tile, dhead, row0, rows, ld);
+    if (flags & MLB_PPO_DHEAD_BF16) stage_out(tile, ts, reinterpret_cast<__nv_bfloat16*>(dhead), row0, rows, ld, ncols);
+    else stage_out(tile, ts, reinterpret_cast<float*>(dhead), row0, rows, ld, ncols);
+    if (dbias) {                              // bias gradients of the heads: column sums of this tile
+        const int nrow = (int)min((long long)ROWS_PER_BLOCK, rows - row0);
+        for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+            float acc = 0.f;
+            for (int r = 0; r < nrow; ++r) acc += tile[r * ts + c];
+            atomicAdd(dbias + c, acc);
+        }
+    }
 
     __shared__ double smd[32];
     __shared__ float smf[32];
@@ -310,7 +324,7 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
                              const float* vn_params, const int32_t* buckets_host,
                              const float* obj_scale_host, const float* ent_scale_host,
                              int num_components, long long rows, long long M, float clip_coef,
-                             float value_loss_coef, int flags, float* d_head,
+                             float value_loss_coef, int flags, void* d_head, float* d_bias,
                              mlb_ppo_stats* stats, void* ws, size_t ws_bytes) {
     MLB_REQUIRE(head && actions && old_log_probs && advantages && returns && d_head && stats);
     MLB_REQUIRE(rows > 0 && M > 0 && ld > 0 && obj_scale_host && ent_scale_host);
@@ -327,7 +341,7 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     LossPartial* part = reinterpret_cast<LossPartial*>(ws);
     ppo_loss_kernel<<<g, ROWS_PER_BLOCK, smem, s>>>(head, ld, actions, old_log_probs, advantages,
         returns, old_values, mb_weights, adv_mean_rstd, vn_params, L, rows, M, clip_coef,
-        value_loss_coef, flags, vcol, d_head, part);
+        value_loss_coef, flags, vcol, d_head, d_bias, part);
     MLB_CHECK_LAUNCH();
     ppo_loss_final_kernel<<<1, 256, 0, s>>>(part, (int)g, (double)rows, num_components,
                                             value_loss_coef, stats);

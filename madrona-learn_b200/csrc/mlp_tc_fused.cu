@@ -14,6 +14,8 @@
 //
 // Forward (training) stores, per element, y (bf16) and xhat (bf16), plus rstd per row: that is
 // what the backward needs (xhat for the LN Jacobian, sign(xhat*scale+bias) for the ReLU mask).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -273,8 +275,8 @@ dense_ln_relu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // ------------------------------------------------------------------------------------------
 // backward: dZ_prev = LN'/ReLU'(dY),  dY = dZ W^T  (accumulator), per-feature dscale / dbias
 // ------------------------------------------------------------------------------------------
-template <int STAGES>
-__global__ void __launch_bounds__(FUSED_THREADS, 2)
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(FUSED_THREADS, MINB)
 dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmXH, const __grid_constant__ CUtensorMap tmDZ,
                       const float* __restrict__ scale, const float* __restrict__ bias,
@@ -312,7 +314,9 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tma_load_2d(&tmXH, p.aux_bar, p.smem + pnl * 16384, pnl * 64, m0);
         }
         mbar_wait(p.aux_bar, 0);
-        // pass 1: m1 = mean(dxhat), m2 = mean(dxhat * xhat); per-feature sums of du*xhat and du
+        // pass 1: dxhat = relu'(.) * dy * scale is written back over dy in TMEM (tcgen05.st) so that
+        // pass 2 is two FMAs per element; m1 = mean(dxhat), m2 = mean(dxhat * xhat); per-feature
+        // sums of du*xhat and du by warp reduce-scatter
         float m1 = 0.f, m2 = 0.f;
         for (int ch = ch_lo; ch < ch_hi; ++ch) {
             const int c = ch * 32;
@@ -325,22 +329,27 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int q = 0; q < 4; ++q) {
                 const uint4 u = *reinterpret_cast<const uint4*>(pan + sw128(rt, hf * 4 + q));
                 const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                const float4 sa = *reinterpret_cast<const float4*>(s + c + 8 * q);
+                const float4 sb = *reinterpret_cast<const float4*>(s + c + 8 * q + 4);
+                const float4 ba = *reinterpret_cast<const float4*>(b + c + 8 * q);
+                const float4 bb = *reinterpret_cast<const float4*>(b + c + 8 * q + 4);
+                const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-#pragma unroll
-                    for (int hl = 0; hl < 2; ++hl) {
-                        const int j = 8 * q + 2 * e + hl;
-                        const float xh = hl ? bf16hi(w4[e]) : bf16lo(w4[e]);
-                        const float dy = __uint_as_float(r[j]);
-                        const float du = (fmaf(xh, s[c + j], b[c + j]) > 0.f) ? dy : 0.f;   // ReLU mask
-                        const float dxh = du * s[c + j];
-                        m1 += dxh;
-                        m2 = fmaf(dxh, xh, m2);
-                        gx[j] = du * xh;
-                        g[j] = du;
-                    }
+                for (int e = 0; e < 8; ++e) {
+                    const int j = 8 * q + e;
+                    const float xh = (e & 1) ? bf16hi(w4[e >> 1]) : bf16lo(w4[e >> 1]);
+                    const float dy = __uint_as_float(r[j]);
+                    const float du = (fmaf(xh, sv[e], bv[e]) > 0.f) ? dy : 0.f;       // ReLU mask
+                    const float dxh = du * sv[e];
+                    m1 += dxh;
+                    m2 = fmaf(dxh, xh, m2);
+                    gx[j] = du * xh;
+                    g[j] = du;
+                    r[j] = __float_as_uint(dxh);
                 }
             }
+            tmem_st32(taddr + c, r);
             const float csum = warp_reduce_scatter32(gx, lane);
             const float bsum = warp_reduce_scatter32(g, lane);
             atomicAdd(&cs[c + lane], csum);
@@ -352,9 +361,9 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         m1 += part[((half ^ 1) * 128 + rt) * 2];
         m2 += part[((half ^ 1) * 128 + rt) * 2 + 1];
         const float invH = 1.f / (float)HN;
-        m1 *= invH;
-        m2 *= invH;
-        // pass 2: dz = rstd * (dxhat - m1 - xhat * m2), written over xhat in the panels
+        const float c1 = rstd * m1 * invH;               // dz = rstd*dxhat - rstd*m1 - xhat*(rstd*m2)
+        const float c2 = rstd * m2 * invH;
+        // pass 2: written over xhat in the panels
         for (int ch = ch_lo; ch < ch_hi; ++ch) {
             const int c = ch * 32;
             uint32_t r[32];
@@ -369,17 +378,9 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 uint32_t o4[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float dz2[2];
-#pragma unroll
-                    for (int hl = 0; hl < 2; ++hl) {
-                        const int j = 8 * q + 2 * e + hl;
-                        const float xh = hl ? bf16hi(w4[e]) : bf16lo(w4[e]);
-                        const float dy = __uint_as_float(r[j]);
-                        const float du = (fmaf(xh, s[c + j], b[c + j]) > 0.f) ? dy : 0.f;
-                        const float dxh = du * s[c + j];
-                        dz2[hl] = rstd * (dxh - m1 - xh * m2);
-                    }
-                    o4[e] = pack_bf16(dz2[0], dz2[1]);
+                    const float d0 = fmaf(-c2, bf16lo(w4[e]), fmaf(rstd, __uint_as_float(r[8 * q + 2 * e]), -c1));
+                    const float d1 = fmaf(-c2, bf16hi(w4[e]), fmaf(rstd, __uint_as_float(r[8 * q + 2 * e + 1]), -c1));
+                    o4[e] = pack_bf16(d0, d1);
                 }
                 *slot = make_uint4(o4[0], o4[1], o4[2], o4[3]);
             }
@@ -462,7 +463,8 @@ MLB_API int mlb_dense_dx_lnbwd_tc(void* stream, const void* DZ_in, const void* W
     if (rc) return rc;
     constexpr int ST = 2;
     const int smem = FusedSmem<ST>::total(HN);
-    auto kern = dense_dx_lnbwd_kernel<ST>;
+    static const int minb = [] { const char* v = getenv("MLB_DX_MINBLOCKS"); return v ? atoi(v) : 2; }();
+    auto kern = minb == 1 ? dense_dx_lnbwd_kernel<ST, 1> : dense_dx_lnbwd_kernel<ST, 2>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<mlb_cdiv(M, BM), FUSED_THREADS, smem, mlb_stream(stream)>>>(

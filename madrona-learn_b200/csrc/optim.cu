@@ -8,7 +8,12 @@
 //   mlb_sumsq_f32      global gradient norm (double accumulation, deterministic tree)
 //   mlb_adam_step_f32  clip scale + Adam moments + parameter update (28 B/param)
 //   mlb_renorm_segments one block per re-projected tensor / LayerNorm pair
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -72,23 +77,56 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
-// One block per segment: kind 1 -> w *= target / ||w|| ; kind 2 -> (s,b) *= sqrt(target / (s.s+b.b))
-__global__ void __launch_bounds__(1024)
-renorm_kernel(float* __restrict__ p, const mlb_segment* __restrict__ segs, int* __restrict__ step) {
-    const mlb_segment sg = segs[blockIdx.x];
+// One thread-block CLUSTER (8 CTAs, distributed shared memory) per segment:
+//   kind 1 -> w *= target / ||w|| ; kind 2 -> (s,b) *= sqrt(target / (s.s+b.b)) ; kind 0 -> copy only
+// Each CTA reduces its slice, the 8 partial sums are exchanged through DSMEM
+// (cluster.map_shared_rank) after one cluster barrier, then every CTA rescales its slice and --
+// when a bf16 copy table is given -- refreshes the tensor-core operand copies W (row-major) and
+// W^T of the weight it just re-projected, so the optimiser step needs no separate cast pass.
+constexpr int RENORM_CLUSTER = 8;
+
+__global__ void __cluster_dims__(RENORM_CLUSTER, 1, 1) __launch_bounds__(512)
+renorm_kernel(float* __restrict__ p, const mlb_segment* __restrict__ segs,
+              const mlb_bf16_copy* __restrict__ copies, int* __restrict__ step) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int seg = blockIdx.x / RENORM_CLUSTER;
+    const int rank = (int)cluster.block_rank();
+    const mlb_segment sg = segs[seg];
     if (blockIdx.x == 0 && threadIdx.x == 0 && step) *step += 1;
-    if (sg.kind == 0) return;
     float* w = p + sg.offset;
-    double s = 0.0;
-    for (long long i = threadIdx.x; i < sg.length; i += blockDim.x) { const float v = w[i]; s += (double)v * v; }
+    const long long per = (sg.length + RENORM_CLUSTER - 1) / RENORM_CLUSTER;
+    const long long lo = rank * per, hi = min(sg.length, lo + per);
     __shared__ double smd[32];
+    __shared__ double partial;
     __shared__ float fac;
+    double s = 0.0;
+    if (sg.kind != 0)
+        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) { const float v = w[i]; s += (double)v * v; }
     s = block_sum_d(s, smd);
-    if (threadIdx.x == 0)
-        fac = sg.kind == 1 ? (float)((double)sg.target / sqrt(s)) : (float)sqrt((double)sg.target / s);
+    if (threadIdx.x == 0) partial = s;
+    cluster.sync();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int r = 0; r < RENORM_CLUSTER; ++r) tot += *cluster.map_shared_rank(&partial, r);
+        fac = sg.kind == 1 ? (float)((double)sg.target / sqrt(tot))
+                           : (sg.kind == 2 ? (float)sqrt((double)sg.target / tot) : 1.f);
+    }
     __syncthreads();
     const float f = fac;
-    for (long long i = threadIdx.x; i < sg.length; i += blockDim.x) w[i] *= f;
+    mlb_bf16_copy cp;
+    cp.dst = nullptr; cp.dst_t = nullptr; cp.rows = cp.cols = cp.ld_t = cp.ld_d = 0;
+    if (copies) cp = copies[seg];
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        float v = w[i];
+        if (sg.kind != 0) { v *= f; w[i] = v; }
+        if (cp.dst_t) {
+            const int r = (int)(i / cp.cols), c = (int)(i - (long long)r * cp.cols);
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            reinterpret_cast<__nv_bfloat16*>(cp.dst_t)[(long long)c * cp.ld_t + r] = h;
+            if (cp.dst) reinterpret_cast<__nv_bfloat16*>(cp.dst)[(long long)r * cp.ld_d + c] = h;
+        }
+    }
+    cluster.sync();      // keep every CTA's shared memory alive until all remote reads are done
 }
 
 __global__ void __launch_bounds__(256)
@@ -152,9 +190,10 @@ MLB_API int mlb_adam_step_f32(void* stream, float* params, const float* grads, f
 }
 
 MLB_API int mlb_renorm_segments(void* stream, float* params, const mlb_segment* segments_dev,
-                                int num_segments, int32_t* step) {
+                                int num_segments, int32_t* step, const mlb_bf16_copy* copies_dev) {
     MLB_REQUIRE(params && segments_dev && num_segments > 0);
-    renorm_kernel<<<num_segments, 1024, 0, mlb_stream(stream)>>>(params, segments_dev, step);
+    renorm_kernel<<<num_segments * RENORM_CLUSTER, 512, 0, mlb_stream(stream)>>>(params, segments_dev,
+                                                                                copies_dev, step);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }

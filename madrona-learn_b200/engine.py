@@ -251,11 +251,22 @@ class PolicyProgram:
 
     def rebuild_segments(self):
         self.refresh_bf16()
-        segs = []
+        segs, copies = [], []
+        none = _lib.Bf16Copy(None, None, 0, 0, 0, 0)
         for i in range(self.L):
             k_off, ln_off, d = self.layer_off[i]
             segs.append(_lib.Segment(k_off, d * self.H, 1, float(self.initial_weight_norms[f'Dense_{i}'])))
+            copies.append(_lib.Bf16Copy(self.w_t[i].data_ptr(), self.w_c[i].data_ptr(), d, self.H, d, self.H)
+                          if self.tc else none)
             segs.append(_lib.Segment(ln_off, 2 * self.H, 2, float(self.H)))
+            copies.append(none)
+        # the fused actor+critic head matrix is not re-projected (kind 0) but its bf16 copies are refreshed
+        segs.append(_lib.Segment(self.head_w_off, self.feat * self.NH, 0, 0.0))
+        copies.append(_lib.Bf16Copy(self.wh_t.data_ptr(), self.wh_c.data_ptr(), self.feat, self.NH, self.feat,
+                                    self.NH) if self.tc else none)
+        carr = (_lib.Bf16Copy * len(copies))(*copies)
+        self.copies = torch.from_numpy(np.frombuffer(bytes(carr), dtype=np.uint8).copy()).to(self.device) \
+            if self.tc else None
         arr = (_lib.Segment * len(segs))(*segs)
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
         self.segments = torch.from_numpy(raw).to(self.device)
@@ -286,13 +297,12 @@ class PolicyProgram:
             w = dict(rows=rows, z=None if self.tc else [e(rows, self.H) for _ in range(self.L)],
                      y=[e(rows, self.H, dtype=AT) for _ in range(self.L)],
                      stats=None if self.tc else [e(rows, 2) for _ in range(self.L)],
-                     head=e(rows, self.NH), dhead=e(rows, self.NH),
+                     head=e(rows, self.NH), dhead=e(rows, self.NH, dtype=AT),
                      dy=e(rows, self.H, dtype=AT), dz=e(rows, self.H, dtype=AT),
                      loss_ws=torch.empty(_lib.lib().mlb_ppo_loss_workspace(rows) + 16, dtype=torch.uint8, device=dev),
                      stats_out=torch.zeros(ctypes.sizeof(_lib.PPOStats), dtype=torch.uint8, device=dev))
             if self.tc:
                 w['x'] = e(rows, self.obs_dim, dtype=AT)
-                w['dhead16'] = e(rows, self.NH, dtype=AT)
                 w['xh'] = [e(rows, self.H, dtype=AT) for _ in range(self.L)]     # normalised pre-activations
                 w['rstd'] = [e(rows) for _ in range(self.L)]
                 w['dz2'] = e(rows, self.H, dtype=AT)
@@ -369,7 +379,6 @@ class PolicyProgram:
         # dW_h = feat^T dhead ; db_h = colsum(dhead) ; dfeat = dhead W_h^T
         gemm(feat, w['dhead'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH,
              ta=1, tb=0, accumulate=1, splitk=_splitk_for(self.feat, self.NH, rows))
-        call('mlb_colsum_f32', ptr(w['dhead']), c_ll(rows), c_int(self.NH), c_int(self.NH), ptr(gB))
         gemm(w['dhead'], W, w['dy'], None, rows, self.feat, self.NH, self.NH, self.NH, self.feat,
              ta=0, tb=1)
         for i in range(self.L - 1, -1, -1):
@@ -387,18 +396,16 @@ class PolicyProgram:
     def _backward_tc(self, rows, w):
         """bf16 tensor-core backward.  dW products are MN-major x MN-major split-K GEMMs with
         fp32 atomic accumulation straight into the gradient arena."""
-        gW, gB = self.head_views(self.grads)
+        gW, _ = self.head_views(self.grads)       # (head bias grads were accumulated by the loss kernel)
         feat = w['y'][self.L - 1]
-        call('mlb_cast_f32_bf16', ptr(w['dhead']), ptr(w['dhead16']), c_ll(rows * self.NH))
-        gemm_tc(feat, w['dhead16'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH, 1, 1, 2,
+        gemm_tc(feat, w['dhead'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH, 1, 1, 2,
                 _splitk_tc(self.feat, self.NH, rows))
-        call('mlb_colsum_f32', ptr(w['dhead']), c_ll(rows), c_int(self.NH), c_int(self.NH), ptr(gB))
         # dfeat = dhead Wh^T fused with the LayerNorm/ReLU backward of the last layer -> dZ_{L-1}
         dz_cur, dz_nxt = w['dz'], w['dz2']
         i = self.L - 1
         _, s, b = self.layer_views(self.params, i)
         _, gs, gb = self.layer_views(self.grads, i)
-        call('mlb_dense_dx_lnbwd_tc', ptr(w['dhead16']), ptr(self.wh_c), ptr(s), ptr(b), ptr(w['xh'][i]),
+        call('mlb_dense_dx_lnbwd_tc', ptr(w['dhead']), ptr(self.wh_c), ptr(s), ptr(b), ptr(w['xh'][i]),
              ptr(w['rstd'][i]), ptr(dz_cur), ptr(gs), ptr(gb), c_int(rows), c_int(self.NH), c_int(self.H),
              c_int(self.NH), c_int(self.NH))
         for i in range(self.L - 1, -1, -1):
@@ -414,6 +421,14 @@ class PolicyProgram:
                      c_int(self.H), c_int(self.H))
                 dz_cur, dz_nxt = dz_nxt, dz_cur
 
+    @property
+    def loss_flags(self):
+        """Extra mlb_ppo_loss_f32 flags for this program (bf16 d_head on the tensor-core path)."""
+        return 4 if self.tc else 0
+
+    def head_bias_grad(self):
+        return self.head_views(self.grads)[1]
+
     def zero_grads(self):
         call('mlb_fill_zero', ptr(self.grads), c_size_t(self.num_params * 4))
 
@@ -425,8 +440,7 @@ class PolicyProgram:
              c_ll(self.num_params), ptr(self.adam_step), ptr(self.grad_sumsq), c_float(lr),
              c_float(b1), c_float(b2), c_float(eps), c_float(max_grad_norm), c_float(grad_scale))
         call('mlb_renorm_segments', ptr(self.params), ptr(self.segments), c_int(self.num_segments),
-             ptr(self.adam_step))
-        self.refresh_bf16()
+             ptr(self.adam_step), ptr(self.copies))
 
     # ---------------------------------------------------------------------------------
     # flax-style apply(method=...) entry points (ml/actor_critic.py:65-128); these allocate

@@ -188,16 +188,16 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
             with profile('AC Forward'):
                 head = prog.forward_train(mb['obs'].view(rows, prog.obs_dim), rows)
             with profile('Optimize'):
+                prog.zero_grads()
                 call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(mb['actions']),
                      ptr(mb['log_probs']), ptr(mb[score_key]), ptr(mb['returns']),
                      ptr(mb['values']) if cfg.algo.clip_value_loss else ptr(None), ptr(None),
                      ptr(ws.mb_adv[mbi]) if normalize_scores else ptr(None),
                      ptr(ws.vn_params[mbi]) if vn is not None else ptr(None),
                      prog._buckets_c, ws.obj_scale, ws.ent_scale, c_int(prog.A), c_ll(rows), c_ll(M),
-                     c_float(hp.clip_coef), c_float(hp.value_loss_coef), c_int(flags),
-                     ptr(tw['dhead']), ptr(tw['stats_out']), ptr(tw['loss_ws']),
+                     c_float(hp.clip_coef), c_float(hp.value_loss_coef), c_int(flags | prog.loss_flags),
+                     ptr(tw['dhead']), ptr(prog.head_bias_grad()), ptr(tw['stats_out']), ptr(tw['loss_ws']),
                      c_size_t(tw['loss_ws'].numel()))
-                prog.zero_grads()
                 prog.backward(mb['obs'].view(rows, prog.obs_dim), rows)
                 grad_scale = 1.0
                 if dist_ctx is not None:

@@ -188,11 +188,12 @@ def test_ppo_loss_and_full_backward(mlb, clipv, huber, vn):
     ent_scale = (ctypes.c_float * A)(*[cfg.entropy_coef / (rows * A)] * A)
     flags = (1 if clipv else 0) | (2 if huber else 0)
     dv = {k: _dev(mb[k]) for k in ('actions', 'log_probs', 'advantages', 'returns', 'values')}  # keep alive
+    prog.zero_grads()          # the loss kernel accumulates the head bias gradients
     call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(dv['actions']), ptr(dv['log_probs']),
          ptr(dv['advantages']), ptr(dv['returns']), ptr(dv['values']), ptr(None),
          ptr(adv_mr), ptr(vnp), prog._buckets_c, obj_scale, ent_scale, c_int(A), c_ll(rows), c_ll(M),
-         c_float(cfg.clip_coef), c_float(cfg.value_loss_coef), c_int(flags), ptr(tw['dhead']),
-         ptr(tw['stats_out']), ptr(tw['loss_ws']), c_size_t(tw['loss_ws'].numel()))
+         c_float(cfg.clip_coef), c_float(cfg.value_loss_coef), c_int(flags | prog.loss_flags), ptr(tw['dhead']),
+         ptr(prog.head_bias_grad()), ptr(tw['stats_out']), ptr(tw['loss_ws']), c_size_t(tw['loss_ws'].numel()))
     st = _lib.PPOStats.from_buffer_copy(tw['stats_out'].cpu().numpy().tobytes())
     np.testing.assert_allclose(st.loss, ref['loss'], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(st.action_obj, np.mean(ref['action_obj']), rtol=1e-4, atol=1e-6)
@@ -210,7 +211,6 @@ def test_ppo_loss_and_full_backward(mlb, clipv, huber, vn):
     assert _rel_l2(dhead[:, :26], ref['dlogits']) < 1e-4
     assert _rel_l2(dhead[:, 26:27], ref['dcritic']) < 1e-4
     assert np.all(dhead[:, 27:] == 0)
-    prog.zero_grads()
     prog.backward(obs_d, rows)
     g = prog.to_oracle_params(prog.grads)
     onn.tree_map(lambda a, b: np.testing.assert_array_less(_rel_l2(a, b), 1e-4), g, ref['grads'])
