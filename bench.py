@@ -215,7 +215,7 @@ def main():
     import torch
     import madrona_learn_b200 as m
     from madrona_learn_b200 import _lib
-    from madrona_learn_b200.engine import gemm, gemm_tc
+    from madrona_learn_b200.engine import gemm
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     dist_ctx = None
@@ -264,29 +264,41 @@ def main():
         rows, H = (N // WORKLOAD['minibatches']) * T, WORKLOAD['hidden']
         flops = 2.0 * rows * H * H
         if args.dtype == 'bf16':
-            A = torch.randn(rows, H, device=dev).to(torch.bfloat16)
-            B = torch.randn(H, H, device=dev).to(torch.bfloat16)
-            C = torch.empty(rows, H, device=dev)
-            t_gemm = time_kernel(torch, lambda: gemm_tc(A, B, C, None, rows, H, H, H, H, H, 0, 0, 0), 10)
-            kname = 'tc_gemm_kernel<256,3,K-major,K-major,f32-out> (tcgen05 Dense forward, 65536 x 256 x 256)'
-            note = ('tcgen05.mma kind::f16, M=128 N=256 per CTA, fp32 store epilogue; at K=256 the tile is '
-                    'output-write bound (64 MB fp32 out per launch), not MMA bound')
-            # algorithmic HBM bytes of this launch: A bf16 in + C fp32 out (+ B once)
-            hbm = rows * H * 2 + rows * H * 4 + H * H * 2
+            from madrona_learn_b200._lib import c_int, call, ptr
+            BF = torch.bfloat16
+            X = torch.randn(rows, H, device=dev).to(BF)
+            Wt = (torch.randn(H, H, device=dev) * 0.06).to(BF)
+            sc, bi = torch.ones(H, device=dev), torch.zeros(H, device=dev)
+            Y, XH = torch.empty(rows, H, device=dev, dtype=BF), torch.empty(rows, H, device=dev, dtype=BF)
+            rs = torch.empty(rows, device=dev)
+            flush = torch.zeros(64 << 20, device=dev)
+            t_k = time_kernel(torch, lambda: call(
+                'mlb_dense_ln_relu_fwd_tc', ptr(X), ptr(Wt), ptr(sc), ptr(bi), ptr(Y), ptr(XH), ptr(rs),
+                c_int(rows), c_int(H), c_int(H), c_int(H), c_int(H)), 10, flush)
+            # algorithmic HBM bytes of one launch: X in (bf16) + Y and xhat out (bf16) + rstd + W once
+            hbm = rows * H * 2 * 3 + rows * 4 + H * H * 2
+            roof = dict(bound='hbm',
+                        kernel='dense_ln_relu_fwd_kernel (tcgen05 Dense + LayerNorm + ReLU, training variant, '
+                               f'{rows} x {H} x {H}, bf16 in/out, fp32 TMEM accumulate)',
+                        achieved=hbm / t_k / 1e9, peak=pk['hbm_gbs'], unit='GB/s',
+                        frac=hbm / t_k / 1e9 / pk['hbm_gbs'], traffic=None, peak_source=pk_src,
+                        us_per_launch=t_k * 1e6, algorithmic_bytes=hbm,
+                        tensor_tflops=flops / t_k / 1e12,
+                        tensor_frac=flops / t_k / 1e12 / pk['bf16_tflops_sustained'],
+                        note='arithmetic intensity 85 flop/B < ridge (1395 TF / 6.5 TB/s = 213): the fused layer '
+                             'is HBM-bound; L2 flushed between timed launches')
+            del X, Wt, Y, XH, rs, flush
         else:
             A = torch.randn(rows, H, device=dev)
             B = torch.randn(H, H, device=dev)
             C = torch.empty(rows, H, device=dev)
-            t_gemm = time_kernel(torch, lambda: gemm(A, B, C, None, rows, H, H, H, H, H), 10)
-            kname = 'sgemm_kernel<128,128,8,8> (fp32 SIMT Dense forward, 65536 x 256 x 256)'
-            note = 'fp32 FFMA path (compute_dtype=float32)'
-            hbm = rows * H * 4 * 2 + H * H * 4
-        tf = flops / t_gemm / 1e12
-        roof = dict(bound='tensor', kernel=kname, achieved=tf, peak=pk['bf16_tflops_sustained'],
-                    unit='TFLOP/s', frac=tf / pk['bf16_tflops_sustained'], traffic=None,
-                    peak_source=pk_src, us_per_launch=t_gemm * 1e6,
-                    hbm_gbs=hbm / t_gemm / 1e9, hbm_frac=hbm / t_gemm / 1e9 / pk['hbm_gbs'], note=note)
-        del A, B, C
+            t_k = time_kernel(torch, lambda: gemm(A, B, C, None, rows, H, H, H, H, H), 10)
+            tf = flops / t_k / 1e12
+            roof = dict(bound='tensor', kernel='sgemm_kernel<128,128,8,8> (fp32 SIMT Dense forward, 65536 x 256 x 256)',
+                        achieved=tf, peak=pk['bf16_tflops_sustained'], unit='TFLOP/s',
+                        frac=tf / pk['bf16_tflops_sustained'], traffic=None, peak_source=pk_src,
+                        us_per_launch=t_k * 1e6, note='fp32 FFMA path (compute_dtype=float32)')
+            del A, B, C
         # ---- GAE kernel HBM roofline (configs[4] sweep point, > L2) --------------------
         K = m.kernels
         Tg, Ng = 256, 1 << 20

@@ -314,9 +314,9 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tma_load_2d(&tmXH, p.aux_bar, p.smem + pnl * 16384, pnl * 64, m0);
         }
         mbar_wait(p.aux_bar, 0);
-        // pass 1: dxhat = relu'(.) * dy * scale is written back over dy in TMEM (tcgen05.st) so that
-        // pass 2 is two FMAs per element; m1 = mean(dxhat), m2 = mean(dxhat * xhat); per-feature
-        // sums of du*xhat and du by warp reduce-scatter
+        // pass 1: m1 = mean(dxhat), m2 = mean(dxhat * xhat); per-feature sums of du*xhat and du by
+        // warp reduce-scatter.  (Writing dxhat back to TMEM with tcgen05.st to shorten pass 2 was
+        // measured slower: the extra live registers spill at 2 CTAs/SM.)
         float m1 = 0.f, m2 = 0.f;
         for (int ch = ch_lo; ch < ch_hi; ++ch) {
             const int c = ch * 32;
@@ -346,10 +346,8 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     m2 = fmaf(dxh, xh, m2);
                     gx[j] = du * xh;
                     g[j] = du;
-                    r[j] = __float_as_uint(dxh);
                 }
             }
-            tmem_st32(taddr + c, r);
             const float csum = warp_reduce_scatter32(gx, lane);
             const float bsum = warp_reduce_scatter32(g, lane);
             atomicAdd(&cs[c + lane], csum);
@@ -363,7 +361,7 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const float invH = 1.f / (float)HN;
         const float c1 = rstd * m1 * invH;               // dz = rstd*dxhat - rstd*m1 - xhat*(rstd*m2)
         const float c2 = rstd * m2 * invH;
-        // pass 2: written over xhat in the panels
+        // pass 2: dz = rstd*dxhat - rstd*m1 - xhat*(rstd*m2), written over xhat in the panels
         for (int ch = ch_lo; ch < ch_hi; ++ch) {
             const int c = ch * 32;
             uint32_t r[32];
@@ -375,14 +373,22 @@ dense_dx_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 uint4* slot = reinterpret_cast<uint4*>(pan + sw128(rt, hf * 4 + q));
                 const uint4 u = *slot;
                 const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-                uint32_t o4[4];
+                const float4 sa = *reinterpret_cast<const float4*>(s + c + 8 * q);
+                const float4 sb = *reinterpret_cast<const float4*>(s + c + 8 * q + 4);
+                const float4 ba = *reinterpret_cast<const float4*>(b + c + 8 * q);
+                const float4 bb = *reinterpret_cast<const float4*>(b + c + 8 * q + 4);
+                const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                float dz8[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float d0 = fmaf(-c2, bf16lo(w4[e]), fmaf(rstd, __uint_as_float(r[8 * q + 2 * e]), -c1));
-                    const float d1 = fmaf(-c2, bf16hi(w4[e]), fmaf(rstd, __uint_as_float(r[8 * q + 2 * e + 1]), -c1));
-                    o4[e] = pack_bf16(d0, d1);
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (e & 1) ? bf16hi(w4[e >> 1]) : bf16lo(w4[e >> 1]);
+                    const float dy = __uint_as_float(r[8 * q + e]);
+                    const float rs = (fmaf(xh, sv[e], bv[e]) > 0.f) ? rstd * sv[e] : 0.f;   // rstd * mask * scale
+                    dz8[e] = fmaf(-c2, xh, fmaf(rs, dy, -c1));
                 }
-                *slot = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                *slot = make_uint4(pack_bf16(dz8[0], dz8[1]), pack_bf16(dz8[2], dz8[3]),
+                                   pack_bf16(dz8[4], dz8[5]), pack_bf16(dz8[6], dz8[7]));
             }
         }
         fence_async_smem();
