@@ -210,6 +210,25 @@ int mlb_cast_weight_bf16(void* stream, const float* src, void* dst_t, void* dst,
                          int cols, int ld_src, int ld_t, int ld_d);
 
 /* ------------------------------------------------------------------------------------ */
+/* K11: LSTM cell (flax OptimizedLSTMCell semantics, ml/rnn.py:10-111), fp32.               */
+/* z f32 [M, 4H] = x W_i + h W_h (gate blocks i|f|g|o, without bias), bias f32 [4H].        */
+/* fwd: h_seq = unmasked output of the step; (c_carry, h_carry) = next-step state, zeroed   */
+/*      where ends[m] (LSTM.sequence resets AFTER the step, ml/rnn.py:91-96); ends may be   */
+/*      NULL (rollout: the reset is mlb_rnn_reset_f32 after the env step); stash (may be    */
+/*      NULL) f32 [M, 5H] = i, f, g, o, tanh(c') for the backward.                           */
+/* bwd: dh_seq [M, ld_dh] gradient w.r.t. the unmasked output, dh_carry/dc_carry gradients   */
+/*      w.r.t. the masked carry (both NULL at the last step) -> dz [M, 4H], dc_prev [M, H]. */
+/* ------------------------------------------------------------------------------------ */
+int mlb_lstm_cell_fwd_f32(void* stream, const float* z, const float* bias, const float* c_prev,
+                          const uint8_t* ends, float* h_seq, float* c_carry, float* h_carry,
+                          float* stash, long long M, int H);
+int mlb_lstm_cell_bwd_f32(void* stream, const float* dh_seq, int ld_dh, const float* dh_carry,
+                          const float* dc_carry, const uint8_t* ends, const float* stash,
+                          const float* c_prev, float* dz, float* dc_prev, long long M, int H);
+/* clear_recurrent_state (ml/rnn.py:66-81): state[m, :] = 0 where dones[m] */
+int mlb_rnn_reset_f32(void* stream, float* state, const uint8_t* dones, long long M, int H);
+
+/* ------------------------------------------------------------------------------------ */
 /* K7: rollout action sampling.  `head` f32 [rows, ld]: columns [0,sumA) logits of the      */
 /* concatenated discrete components, column sumA the critic value.                          */
 /* mlb_rollout_keys: (prng_key, step_key) = split(prng_key); policy_key =                   */

@@ -70,6 +70,9 @@ SIGNATURES = {
     'mlb_dense_dx_lnbwd_tc': (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int]),
     'mlb_cast_f32_bf16': (c_int, [P, P, P, c_ll]),
     'mlb_cast_weight_bf16': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int]),
+    'mlb_lstm_cell_fwd_f32': (c_int, [P, P, P, P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_lstm_cell_bwd_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_rnn_reset_f32': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P]),
     'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),

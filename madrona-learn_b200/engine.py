@@ -67,10 +67,11 @@ class PolicyProgram:
         if bb.prefix is not None and not getattr(bb.prefix, 'is_identity', False):
             raise NotImplementedError('BackboneShared.prefix must be None (obs are one [N, D] tensor)')
         enc = bb.encoder
-        if isinstance(enc, RecurrentBackboneEncoder):
-            raise NotImplementedError('RecurrentBackboneEncoder/LSTM kernels: next (cfg 4)')
-        if not isinstance(enc, BackboneEncoder) or not isinstance(enc.net, MLP):
-            raise NotImplementedError('encoder must be BackboneEncoder(net=MLP)')
+        if not isinstance(enc, (BackboneEncoder, RecurrentBackboneEncoder)) or not isinstance(enc.net, MLP):
+            raise NotImplementedError('encoder must be [Recurrent]BackboneEncoder(net=MLP[, rnn=LSTM])')
+        self._rnn_desc = enc.rnn if isinstance(enc, RecurrentBackboneEncoder) else None
+        if self._rnn_desc is not None and self.tc:
+            raise NotImplementedError('LSTM on the bf16 tensor-core path: next (use compute_dtype=float32)')
         if not isinstance(actor_critic.actor, DenseLayerDiscreteActor):
             raise NotImplementedError('actor must be DenseLayerDiscreteActor')
         if not isinstance(actor_critic.critic, DenseLayerCritic):
@@ -114,7 +115,13 @@ class PolicyProgram:
             off += 2 * self.H
             self.layer_off.append((k_off, ln_off, d))
             d = self.H
+        self.lstm = None
         self.feat = self.H
+        if self._rnn_desc is not None:
+            from .recurrent import LSTMLowering
+            self.lstm = LSTMLowering(self, self._rnn_desc, self.H, off)
+            off = self.lstm.end_off
+            self.feat = self.lstm.RH * self.lstm.RL
         self.head_w_off = off
         off += self.feat * self.NH
         self.head_b_off = off
@@ -165,8 +172,11 @@ class PolicyProgram:
             net[f'Dense_{i}'] = {'kernel': k}
             net[f'LayerNorm_{i}'] = {'impl': {'scale': s, 'bias': b}}
         W, B = self.head_views(a)
+        enc = {'net': net}
+        if self.lstm is not None:
+            enc['rnn'] = self.lstm.param_tree(a)
         return {
-            'backbone': {'encoder': {'net': net}},
+            'backbone': {'encoder': enc},
             'actor': {'impl': {'kernel': W[:, :self.sumA], 'bias': B[:self.sumA]}},
             'critic': {'Dense_0': {'kernel': W[:, self.sumA:self.sumA + 1],
                                    'bias': B[self.sumA:self.sumA + 1]}},
@@ -190,6 +200,8 @@ class PolicyProgram:
             k_off, ln_off, d = self.layer_off[i]
             host[k_off:k_off + d * self.H] = orth(d, self.H, self.mlp.weight_init_scale).reshape(-1)
             host[ln_off:ln_off + self.H] = 1.0
+        if self.lstm is not None:
+            self.lstm.init_host(host, orth)
         W = torch.zeros(self.feat, self.NH, dtype=F32)
         W[:, :self.sumA] = orth(self.feat, self.sumA, self.ac.actor.weight_init_scale)
         W[:, self.sumA:self.sumA + 1] = orth(self.feat, 1, self.ac.critic.weight_init_scale)
@@ -205,6 +217,8 @@ class PolicyProgram:
             host[k_off:k_off + d * self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['kernel'], np.float32)).reshape(-1)
             host[ln_off:ln_off + self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['scale'], np.float32))
             host[ln_off + self.H:ln_off + 2 * self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['bias'], np.float32))
+        if self.lstm is not None:
+            self.lstm.load_oracle(host, p['lstm'][0])
         W = torch.zeros(self.feat, self.NH, dtype=F32)
         W[:, :self.sumA] = torch.from_numpy(np.asarray(p['actor']['kernel'], np.float32))
         W[:, self.sumA:self.sumA + 1] = torch.from_numpy(np.asarray(p['critic']['kernel'], np.float32))
@@ -220,7 +234,8 @@ class PolicyProgram:
         t = self.param_tree(arena)
         net = t['backbone']['encoder']['net']
         c = lambda x: x.detach().cpu().numpy().copy()
-        return {'mlp': [{'kernel': c(net[f'Dense_{i}']['kernel']),
+        extra = {'lstm': self.lstm.to_oracle(self.params if arena is None else arena)} if self.lstm is not None else {}
+        return {**extra, 'mlp': [{'kernel': c(net[f'Dense_{i}']['kernel']),
                          'scale': c(net[f'LayerNorm_{i}']['impl']['scale']),
                          'bias': c(net[f'LayerNorm_{i}']['impl']['bias'])} for i in range(self.L)],
                 'actor': {'kernel': c(t['actor']['impl']['kernel']), 'bias': c(t['actor']['impl']['bias'])},
@@ -260,6 +275,10 @@ class PolicyProgram:
                           if self.tc else none)
             segs.append(_lib.Segment(ln_off, 2 * self.H, 2, float(self.H)))
             copies.append(none)
+        if self.lstm is not None:
+            lsegs = self.lstm.segments(self.params.detach().cpu(), self.initial_weight_norms)
+            segs += lsegs
+            copies += [none] * len(lsegs)
         # the fused actor+critic head matrix is not re-projected (kind 0) but its bf16 copies are refreshed
         segs.append(_lib.Segment(self.head_w_off, self.feat * self.NH, 0, 0.0))
         copies.append(_lib.Bf16Copy(self.wh_t.data_ptr(), self.wh_c.data_ptr(), self.feat, self.NH, self.feat,
@@ -313,8 +332,9 @@ class PolicyProgram:
     # ---------------------------------------------------------------------------------
     # forward (rollout / critic_only): ActorCritic.rollout ml/actor_critic.py:74-96
     # ---------------------------------------------------------------------------------
-    def forward_infer(self, obs, rows):
-        """obs f32 [rows, D] -> head f32 [rows, NH] (logits | value)."""
+    def forward_infer(self, obs, rows, rnn_states=None):
+        """obs f32 [rows, D] -> head f32 [rows, NH] (logits | value).  Recurrent encoders update
+        `rnn_states` ([c], [h]) in place."""
         w = self.infer_ws(rows)
         if self.tc:
             return self._forward_tc(obs, rows, w, [w['y'][i & 1] for i in range(self.L)], None, None)
@@ -325,6 +345,11 @@ class PolicyProgram:
             y = w['y'][i & 1]
             call('mlb_ln_relu_fwd_f32', ptr(w['z']), ptr(s), ptr(b), ptr(y), ptr(None), c_ll(rows), c_int(self.H))
             x, d = y, self.H
+        if self.lstm is not None:
+            if 'rz' not in w:
+                w['rz'] = torch.empty(rows, 4 * self.lstm.RH, dtype=F32, device=self.device)
+                w['rout'] = torch.empty(rows, self.lstm.RH, dtype=F32, device=self.device)
+            x = self.lstm.step_infer(x, rows, rnn_states, w['rz'], w['rout'])
         W, B = self.head_views(self.params)
         gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
         return w['head']
@@ -353,7 +378,8 @@ class PolicyProgram:
     # ---------------------------------------------------------------------------------
     # training forward + backward (ActorCritic.update ml/actor_critic.py:98-128 + autodiff)
     # ---------------------------------------------------------------------------------
-    def forward_train(self, obs, rows):
+    def forward_train(self, obs, rows, seq=None):
+        """seq (recurrent encoders): dict(Tp, M, ends u8 [T', M], c0, h0 [M, RH])."""
         w = self.train_ws(rows)
         if self.tc:
             return self._forward_tc(obs, rows, w, w['y'], w['xh'], w['rstd'])
@@ -364,23 +390,31 @@ class PolicyProgram:
             call('mlb_ln_relu_fwd_f32', ptr(w['z'][i]), ptr(s), ptr(b), ptr(w['y'][i]), ptr(w['stats'][i]),
                  c_ll(rows), c_int(self.H))
             x, d = w['y'][i], self.H
+        if self.lstm is not None:
+            x = self.lstm.sequence_fwd(x, seq)
         W, B = self.head_views(self.params)
         gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
         return w['head']
 
-    def backward(self, obs, rows):
+    def backward(self, obs, rows, seq=None):
         """Consumes train_ws['dhead']; accumulates into self.grads (pre-zeroed)."""
         w = self.train_ws(rows)
         if self.tc:
             return self._backward_tc(rows, w)
         W, B = self.head_views(self.params)
         gW, gB = self.head_views(self.grads)
-        feat = w['y'][self.L - 1]
+        if self.lstm is not None:
+            lw = self.lstm.train_ws(seq['Tp'], seq['M'])
+            feat, dfeat = lw['h_seq'].view(rows, self.feat), lw['d_hseq'].view(rows, self.feat)
+        else:
+            feat, dfeat = w['y'][self.L - 1], w['dy']
         # dW_h = feat^T dhead ; db_h = colsum(dhead) ; dfeat = dhead W_h^T
         gemm(feat, w['dhead'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH,
              ta=1, tb=0, accumulate=1, splitk=_splitk_for(self.feat, self.NH, rows))
-        gemm(w['dhead'], W, w['dy'], None, rows, self.feat, self.NH, self.NH, self.NH, self.feat,
+        gemm(w['dhead'], W, dfeat, None, rows, self.feat, self.NH, self.NH, self.NH, self.feat,
              ta=0, tb=1)
+        if self.lstm is not None:
+            self.lstm.sequence_bwd(w['y'][self.L - 1], seq, w['dy'])
         for i in range(self.L - 1, -1, -1):
             k, s, b = self.layer_views(self.params, i)
             gk, gs, gb = self.layer_views(self.grads, i)
@@ -455,7 +489,7 @@ class PolicyProgram:
                       return_debug=False, partitionable=False):
         x = self._obs2d(obs)
         rows = x.shape[0]
-        head = self.forward_infer(x, rows)
+        head = self.forward_infer(x, rows, rnn_states)
         actions = torch.empty(rows, self.A, dtype=torch.int32, device=self.device)
         log_probs = torch.empty(rows, self.A, dtype=F32, device=self.device)
         values = torch.empty(rows, 1, dtype=F32, device=self.device)
@@ -469,7 +503,7 @@ class PolicyProgram:
 
     def apply_critic_only(self, rnn_states, obs, train=False):
         x = self._obs2d(obs)
-        head = self.forward_infer(x, x.shape[0])
+        head = self.forward_infer(x, x.shape[0], rnn_states)
         return {'critic': head[:, self.sumA:self.sumA + 1].clone()}, rnn_states
 
     def apply_actor_only(self, rnn_states, obs, train=False):

@@ -112,8 +112,12 @@ class _PPOWorkspace:
         self.mb = {
             'obs': e(Tp, M, prog.obs_dim), 'actions': e(Tp, M, prog.A, dtype=torch.int32),
             'log_probs': e(Tp, M, prog.A), 'advantages': e(Tp, M, 1), 'returns': e(Tp, M, 1),
-            'values': e(Tp, M, 1),
+            'values': e(Tp, M, 1), 'dones': e(Tp, M, 1, dtype=torch.uint8),
         }
+        if prog.lstm is not None:
+            self.mb['rnn_start_c'] = e(M, prog.lstm.RH)
+            self.mb['rnn_start_h'] = e(M, prog.lstm.RH)
+        self.Tp = Tp
         A = prog.A
         g_name, _, g_size = prog.groups[0]
         coef = _entropy_coef(cfg, g_name)
@@ -178,15 +182,23 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
         keys.append('values')
     tw = prog.train_ws(rows)
     mb = ws.mb
+    seq = None
+    if prog.lstm is not None:
+        keys.append('dones')
+        seq = dict(Tp=Tp, M=M, ends=mb['dones'].view(Tp, M), c0=mb['rnn_start_c'], h0=mb['rnn_start_h'])
     for e in range(E):
         for k in range(nmb):
             mbi = e * nmb + k
             with profile('Gather Minibatch'):
                 idx = ws.perm[e, k * M:(k + 1) * M]
                 for name in set(keys):
-                    K.mb_gather(st[name][:, :, 0], idx, C, Tp, B, mb[name])
+                    src = st[name][:, :, 0]
+                    K.mb_gather(src.view(torch.uint8) if src.dtype == torch.bool else src, idx, C, Tp, B, mb[name])
+                if seq is not None:
+                    K.mb_gather_rnn(st['rnn_start_c'][:, 0], idx, C, B, mb['rnn_start_c'])
+                    K.mb_gather_rnn(st['rnn_start_h'][:, 0], idx, C, B, mb['rnn_start_h'])
             with profile('AC Forward'):
-                head = prog.forward_train(mb['obs'].view(rows, prog.obs_dim), rows)
+                head = prog.forward_train(mb['obs'].view(rows, prog.obs_dim), rows, seq)
             with profile('Optimize'):
                 prog.zero_grads()
                 call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(mb['actions']),
@@ -198,7 +210,7 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
                      c_float(hp.clip_coef), c_float(hp.value_loss_coef), c_int(flags | prog.loss_flags),
                      ptr(tw['dhead']), ptr(prog.head_bias_grad()), ptr(tw['stats_out']), ptr(tw['loss_ws']),
                      c_size_t(tw['loss_ws'].numel()))
-                prog.backward(mb['obs'].view(rows, prog.obs_dim), rows)
+                prog.backward(mb['obs'].view(rows, prog.obs_dim), rows, seq)
                 grad_scale = 1.0
                 if dist_ctx is not None:
                     dist_ctx.allreduce_grads(prog.grads)      # sum over ranks; scales already global

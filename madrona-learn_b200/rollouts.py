@@ -131,13 +131,13 @@ class RolloutData:                      # ml/rollouts.py:311-334
         def relayout(x):
             t = x.permute(2, 0, 3, 1, *range(4, x.dim()))
             return t.reshape(t.shape[0], -1, *t.shape[3:])[0]
-        return {k: relayout(v) for k, v in self.store.items() if k != 'rnn_start_states'}
+        return {k: relayout(v) for k, v in self.store.items() if not k.startswith('rnn_start')}
 
     def minibatch(self, indices, keys=None, out=None):
         """-> dict name -> [T', M, *leaf]  (take(axis 0) + swapaxes(0, 1), :319-329)."""
         res = {}
         for k, v in self.store.items():
-            if k == 'rnn_start_states' or (keys is not None and k not in keys):
+            if k.startswith('rnn_start') or (keys is not None and k not in keys):
                 continue
             res[k] = K.mb_gather(v[:, :, 0], indices, self.C, self.Tp, self.B,
                                  None if out is None else out[k])
@@ -178,6 +178,13 @@ class RolloutManager:                   # ml/rollouts.py:373-826
             'returns': e(C, Tp, 1, B, 1),
         }
         self.bootstrap = e(1, B, 1)
+        self._lstm = prog.lstm
+        if self._lstm is not None:
+            # rnn_start_states [C, P, B, *] (ml/rollouts.py:471-478): the carry entering each BPTT chunk
+            RH = self._lstm.RH
+            self.store['rnn_start_c'] = e(C, 1, B, RH)
+            self.store['rnn_start_h'] = e(C, 1, B, RH)
+            self._boot_states = self._lstm.init_states(B, dev)
         self._scratch_actions = e(B, prog.A, dtype=torch.int32)
         self.env_returns_trace = e(C * Tp, B)
         self.policy_key = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -202,7 +209,13 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         policy_states = train_state_mgr.policy_states
         train_states = train_state_mgr.train_states
         for c in range(self._num_bptt_chunks):
-            # (rnn_start_states[c] would be cached here for recurrent policies, :533-537)
+            if self._lstm is not None:
+                with profile('Cache RNN state'):          # :533-537
+                    nbytes = self._cfg.sim_batch_size * self._lstm.RH * 4
+                    call('mlb_copy_bytes', ptr(rollout_state.rnn_states[0][0]),
+                         ptr(self.store['rnn_start_c'][c, 0]), c_size_t(nbytes))
+                    call('mlb_copy_bytes', ptr(rollout_state.rnn_states[1][0]),
+                         ptr(self.store['rnn_start_h'][c, 0]), c_size_t(nbytes))
             rollout_state = self.rollout_loop(rollout_state, policy_states, c)
         with profile('Bootstrap Values'):
             self._bootstrap_values(policy_states, rollout_state)
@@ -226,7 +239,7 @@ class RolloutManager:                   # ml/rollouts.py:373-826
                 ob = pre[self._ob_name]
                 slab = st['obs'][c, s, 0]
                 call('mlb_copy_bytes', ptr(ob), ptr(slab), c_size_t(slab.numel() * 4))
-                head = prog.forward_infer(slab, N)
+                head = prog.forward_infer(slab, N, rs.rnn_states)
                 actions = st['actions'][c, s, 0]
                 prog.sample(head, N, self.policy_key, actions, st['log_probs'][c, s, 0],
                             st['values'][c, s, 0], self.partitionable)
@@ -250,13 +263,21 @@ class RolloutManager:                   # ml/rollouts.py:373-826
                 call('mlb_copy_bytes', ptr(rewards), ptr(r_slab), c_size_t(N * 4))
                 call('mlb_env_returns_f32', ptr(r_slab), ptr(d_slab), ptr(rs.env_returns),
                      ptr(self.env_returns_trace[c * Tp + s]), c_ll(N), c_float(gamma))
+                if self._lstm is not None:                # rnn_reset_fn(rnn_states, dones)  (:942)
+                    self._lstm.reset(rs.rnn_states, d_slab.view(torch.uint8), N)
         return rs
 
     def _bootstrap_values(self, policy_states, rs):     # :607-635
         prog, N = self._prog, self._cfg.sim_batch_size
         pre = policy_states.obs_preprocess.preprocess(policy_states.obs_preprocess_state, rs.cur_obs, False)
         ob = pre[self._ob_name].reshape(N, prog.obs_dim)
-        head = prog.forward_infer(ob, N)
+        states = None
+        if self._lstm is not None:                        # critic_only must not advance the rollout's carry
+            states = self._boot_states
+            nbytes = N * self._lstm.RH * 4
+            call('mlb_copy_bytes', ptr(rs.rnn_states[0][0]), ptr(states[0][0]), c_size_t(nbytes))
+            call('mlb_copy_bytes', ptr(rs.rnn_states[1][0]), ptr(states[1][0]), c_size_t(nbytes))
+        head = prog.forward_infer(ob, N, states)
         # critic column of the head -> bootstrap [1, B, 1] (the greedy actions are discarded)
         prog.sample(head, N, None, self._scratch_actions, None, self.bootstrap, deterministic=True)
 

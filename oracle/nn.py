@@ -244,15 +244,35 @@ def heads_fwd(feat, params, q=None):
     return logits, critic
 
 
-def actor_critic_fwd(params, obs, q=None):
-    """Non-recurrent BackboneShared(BackboneEncoder(MLP)) forward (ml/actor_critic.py).
-    q: optional quantiser (bf16_round) applied at the tensor-core path's storage points."""
+def actor_critic_fwd(params, obs, q=None, seq=None):
+    """BackboneShared([Recurrent]BackboneEncoder(MLP[, LSTM])) forward (ml/actor_critic.py).
+    q: optional quantiser (bf16_round) applied at the tensor-core path's storage points.
+    seq (recurrent, ActorCritic.update -> RecurrentBackboneEncoder.sequence :179-199):
+    dict(Tp, M, ends [T', M], c0 [list of M x RH], h0) -- obs rows are in [T', M] order."""
     feat, caches = mlp_fwd(obs, params['mlp'], q)
+    if 'lstm' in params:
+        Tp, M = seq['Tp'], seq['M']
+        xs = feat.reshape(Tp, M, -1)
+        outs, lcaches = lstm_sequence_fwd([np.asarray(c, feat.dtype) for c in seq['c0']],
+                                          [np.asarray(h, feat.dtype) for h in seq['h0']],
+                                          xs, seq['ends'], params['lstm'])
+        rfeat = outs.reshape(Tp * M, -1)
+        logits, critic = heads_fwd(rfeat, params, q)
+        return logits, critic, (rfeat, caches, lcaches, (Tp, M))
     logits, critic = heads_fwd(feat, params, q)
     return logits, critic, (feat, caches)
 
 
 def actor_critic_bwd(params, cache, dlogits, dcritic, q=None):
+    if len(cache) == 4:                       # recurrent
+        rfeat, caches, lcaches, (Tp, M) = cache
+        g = {'actor': {'kernel': rfeat.T @ dlogits, 'bias': dlogits.sum(axis=0)},
+             'critic': {'kernel': rfeat.T @ dcritic, 'bias': dcritic.sum(axis=0)}}
+        dr = dlogits @ params['actor']['kernel'].T + dcritic @ params['critic']['kernel'].T
+        H = params['lstm'][0]['wh'].shape[0]
+        dxs, g['lstm'] = lstm_sequence_bwd(dr.reshape(Tp, M, -1), lcaches, params['lstm'], H)
+        _, g['mlp'] = mlp_bwd(dxs.reshape(Tp * M, -1), caches, params['mlp'])
+        return g
     feat, caches = cache
     qq = q or _id
     dl, dc = qq(dlogits), qq(dcritic)

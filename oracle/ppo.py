@@ -41,7 +41,11 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, 
     old_lp = mb['log_probs'].reshape(rows, A).astype(f)
     w = np.broadcast_to(mb['mb_weights'].reshape(1, M, 1), (Tp, M, 1)).reshape(rows, 1).astype(f)
 
-    logits, critic, cache = nn.actor_critic_fwd(p, obs, quant)
+    seq = None
+    if 'lstm' in p:
+        rs = mb['rnn_start_states']
+        seq = dict(Tp=Tp, M=M, ends=np.asarray(mb['dones']).reshape(Tp, M).astype(bool), c0=rs[0], h0=rs[1])
+    logits, critic, cache = nn.actor_critic_fwd(p, obs, quant, seq)
     new_lp, ent = nn.action_stats(logits, acts, cfg.buckets)
 
     # advantages: per-MINIBATCH z-score (ml/ppo.py:134-137 -> ml/algo_common.py:133-140)
@@ -165,10 +169,17 @@ def optimizer_step(params, grads, opt, cfg, init_norms, dtype=np.float32):
         fac = np.sqrt(s.shape[-1] / (np.dot(b.astype(np.float64), b) + np.dot(s.astype(np.float64), s)))
         lyr['scale'] = (fac * s).astype(f)
         lyr['bias'] = (fac * b).astype(f)
+    # flax keeps one kernel leaf PER GATE (ii, if, ig, io, hi, hf, hg, ho): each column block of the
+    # stacked [in, 4H] matrices is re-projected to its own initial norm
     for i, lyr in enumerate(new_p.get('lstm', [])):
         for kk in ('wi', 'wh'):
-            k = lyr[kk]
-            lyr[kk] = (f(init_norms['lstm'][i][kk]) * k / np.sqrt(np.sum(np.square(k), dtype=np.float64))).astype(f)
+            k = lyr[kk].copy()
+            Hh = k.shape[1] // 4
+            for g in range(4):
+                blk = k[:, g * Hh:(g + 1) * Hh]
+                k[:, g * Hh:(g + 1) * Hh] = f(init_norms['lstm'][i][kk][g]) * blk / np.sqrt(
+                    np.sum(np.square(blk), dtype=np.float64))
+            lyr[kk] = k.astype(f)
     return new_p, dict(m=new_m, v=new_v, t=t), gn
 
 
@@ -176,8 +187,10 @@ def initial_weight_norms(params):
     """ml/train_state.py:413-423."""
     n = {'mlp': [float(np.sqrt(np.sum(np.square(l['kernel'].astype(np.float64))))) for l in params['mlp']]}
     if 'lstm' in params:
-        n['lstm'] = [{k: float(np.sqrt(np.sum(np.square(l[k].astype(np.float64))))) for k in ('wi', 'wh')}
-                     for l in params['lstm']]
+        def gate_norms(k):
+            Hh = k.shape[1] // 4
+            return [float(np.sqrt(np.sum(np.square(k[:, g * Hh:(g + 1) * Hh].astype(np.float64))))) for g in range(4)]
+        n['lstm'] = [{k: gate_norms(l[k]) for k in ('wi', 'wh')} for l in params['lstm']]
     return n
 
 
