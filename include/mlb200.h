@@ -239,11 +239,16 @@ int mlb_rnn_reset_f32(void* stream, float* state, const uint8_t* dones, long lon
 /*   buckets_host: HOST int32[A].  values (may be NULL) <- head[:, sumA].                   */
 /* ------------------------------------------------------------------------------------ */
 #define MLB_MAX_ACTION_COMPONENTS 16
+#define MLB_MAX_CRITIC_BINS 127
 int mlb_rollout_keys(void* stream, uint32_t* prng_key, uint32_t* policy_key, int partitionable);
 int mlb_sample_discrete_f32(void* stream, const float* head, int ld, const uint32_t* policy_key,
                             const int32_t* buckets_host, int num_components, long long rows,
                             int partitionable, int deterministic, int32_t* actions,
-                            float* log_probs, float* values);
+                            float* log_probs, float* values, const float* critic_bins_host,
+                            int num_critic_bins);
+/* critic_bins_host / num_critic_bins: NULL / <=1 for the plain critic (one value column); else  */
+/* the HOST array of the DreamerV3 critic's bin centres (odd count, ml/dists.py:127-141): the    */
+/* head then carries num_critic_bins critic logits and `values` receives the two-hot mean.       */
 
 /* ------------------------------------------------------------------------------------ */
 /* K8: fused PPO loss + gradient w.r.t. the head outputs (ml/ppo.py:129-262 + autodiff).    */
@@ -273,7 +278,8 @@ int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int32_t* act
                      const int32_t* buckets_host, const float* obj_scale_host,
                      const float* ent_scale_host, int num_components, long long rows,
                      long long M, float clip_coef, float value_loss_coef, int flags,
-                     void* d_head, float* d_bias, mlb_ppo_stats* stats, void* ws, size_t ws_bytes);
+                     void* d_head, float* d_bias, mlb_ppo_stats* stats, void* ws, size_t ws_bytes,
+                     const float* critic_bins_host, int num_critic_bins);
 
 /* ------------------------------------------------------------------------------------ */
 /* K10: optimiser over a flat fp32 arena (ml/ppo.py:84-90,283-338).                         */

@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmlb200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                             ctypes.c_float, ctypes.c_size_t)
@@ -74,10 +74,10 @@ SIGNATURES = {
     'mlb_lstm_cell_bwd_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, c_ll, c_int]),
     'mlb_rnn_reset_f32': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
-    'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P]),
+    'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
     'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),
     'mlb_ppo_loss_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, c_ll, c_ll,
-                                 c_float, c_float, c_int, P, P, P, P, c_size_t]),
+                                 c_float, c_float, c_int, P, P, P, P, c_size_t, P, c_int]),
     'mlb_fill_zero': (c_int, [P, P, c_size_t]),
     'mlb_copy_bytes': (c_int, [P, P, P, c_size_t]),
     'mlb_sumsq_workspace': (c_size_t, [c_ll]),

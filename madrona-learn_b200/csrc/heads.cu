@@ -28,6 +28,28 @@ struct Layout {
     float ent_scale[MAXC];
 };
 
+// Distributional critic (DreamerV3Critic, ml/models.py:157-174 -> SymExpTwoHotDistribution,
+// ml/dists.py:119-208): V logits over fixed symexp-spaced bins.  V == 1 is the plain critic.
+struct CriticBins {
+    int V;
+    float bins[MLB_MAX_CRITIC_BINS];
+};
+
+// SymExpTwoHotDistribution.mean (ml/dists.py:143-170): softmax-weighted bins, summed symmetrically
+// around the midpoint so the estimate is exactly 0 at the zero-initialised critic.
+__device__ __forceinline__ float twohot_mean(const float* l, const CriticBins& cb) {
+    const int V = cb.V, mid = (V - 1) / 2;
+    float mx = -INFINITY;
+    for (int k = 0; k < V; ++k) mx = fmaxf(mx, l[k]);
+    float se = 0.f;
+    for (int k = 0; k < V; ++k) se += expf(l[k] - mx);
+    const float inv = 1.f / se;
+    float acc = 0.f;
+    for (int k = 0; k < mid; ++k)
+        acc += expf(l[mid - 1 - k] - mx) * inv * cb.bins[mid - 1 - k] + expf(l[mid + 1 + k] - mx) * inv * cb.bins[mid + 1 + k];
+    return expf(l[mid] - mx) * inv * cb.bins[mid] + acc;
+}
+
 __global__ void rollout_keys_kernel(uint32_t* __restrict__ prng_key, uint32_t* __restrict__ policy_key,
                                     int part) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -78,7 +100,7 @@ __global__ void __launch_bounds__(128)
 sample_kernel(const float* __restrict__ head, int ld, const uint32_t* __restrict__ policy_key,
               Layout L, long long rows, int part, int deterministic,
               int32_t* __restrict__ actions, float* __restrict__ log_probs,
-              float* __restrict__ values, int vcol) {
+              float* __restrict__ values, int vcol, CriticBins cb) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * L.A) return;
     const long long row = t / L.A;
@@ -107,7 +129,7 @@ sample_kernel(const float* __restrict__ head, int ld, const uint32_t* __restrict
     }
     actions[row * L.A + i] = best;
     if (log_probs) log_probs[row * L.A + i] = __ldg(l + off + best) - lse;
-    if (values && i == 0) values[row] = __ldg(l + vcol);
+    if (values && i == 0) values[row] = cb.V == 1 ? __ldg(l + vcol) : twohot_mean(l + vcol, cb);
 }
 
 struct LossPartial {
@@ -123,10 +145,10 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
                 const float* __restrict__ mb_w, const float* __restrict__ adv_mr,
                 const float* __restrict__ vn, Layout L, long long rows, long long M,
                 float clip, float vcoef, int flags, int vcol, void* __restrict__ dhead,
-                float* __restrict__ dbias, LossPartial* __restrict__ part) {
+                float* __restrict__ dbias, LossPartial* __restrict__ part, CriticBins cb) {
     extern __shared__ float tile[];
     const long long row0 = (long long)blockIdx.x * ROWS_PER_BLOCK;
-    const int ncols = vcol + 1;
+    const int ncols = vcol + cb.V;
     const int ts = ncols | 1;                 // odd tile stride
     stage_in(tile, ts, head, row0, rows, ld, ncols);
     __syncthreads();
@@ -180,6 +202,36 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
                 l[off + j] = g;                                         // overwrite logits with grads
             }
         }
+        if (cb.V > 1) {
+            // distributional critic: two-hot cross-entropy (ml/ppo.py:169-177, ml/dists.py:172-208)
+            const int V = cb.V;
+            float* lc = l + vcol;
+            const float r = ret[row];
+            const float vmean = twohot_mean(lc, cb);
+            int nle = 0, ngt = 0;
+            for (int k = 0; k < V; ++k) { nle += (cb.bins[k] <= r); ngt += (cb.bins[k] > r); }
+            const int lo = min(max(nle - 1, 0), V - 1), hi = min(max(V - ngt, 0), V - 1);
+            const bool same = lo == hi;
+            const float dl = same ? 1.f : fabsf(cb.bins[lo] - r);
+            const float du = same ? 1.f : fabsf(cb.bins[hi] - r);
+            const float wl = dl / (dl + du), wu = du / (dl + du);     // (sic) the reference's weights
+            float mxc = -INFINITY;
+            for (int k = 0; k < V; ++k) mxc = fmaxf(mxc, lc[k]);
+            float sec = 0.f;
+            for (int k = 0; k < V; ++k) sec += expf(lc[k] - mxc);
+            const float lsec = logf(sec) + mxc;
+            const float vl = -(wl * (lc[lo] - lsec) + wu * (lc[hi] - lsec));
+            p_vl += (double)(w * vl) * (double)inv_rows;
+            acc(1, vl);
+            acc(2, fabsf(vmean - r));
+            const float gsc = vcoef * w * inv_rows;
+            for (int k = 0; k < V; ++k) {
+                float tk = 0.f;
+                if (k == lo) tk += wl;
+                if (k == hi) tk += wu;
+                lc[k] = gsc * (expf(lc[k] - lsec) - tk);                // d CE / d logit = softmax - target
+            }
+        } else {
         // critic (plain, V = 1): ml/ppo.py:186-218
         const float v = l[vcol];
         const float r = ret[row];
@@ -203,6 +255,7 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
         acc(1, vl);
         acc(2, fabsf(verr));
         l[vcol] = vcoef * w * dvl * vmask * inv_rows;
+        }
     }
     __syncthreads();
     if (flags & MLB_PPO_DHEAD_BF16) stage_out(tile, ts, reinterpret_cast<__nv_bfloat16*>(dhead), row0, rows, ld, ncols);
@@ -271,6 +324,14 @@ ppo_loss_final_kernel(const LossPartial* __restrict__ part, int nparts, double r
     }
 }
 
+int make_bins(CriticBins& cb, const float* bins_host, int num_bins) {
+    if (num_bins <= 1 || !bins_host) { cb.V = 1; return MLB_OK; }
+    if (num_bins > MLB_MAX_CRITIC_BINS || num_bins % 2 == 0) return MLB_EINVAL;
+    cb.V = num_bins;
+    for (int k = 0; k < num_bins; ++k) cb.bins[k] = bins_host[k];
+    return MLB_OK;
+}
+
 int make_layout(Layout& L, const int32_t* buckets, int A, const float* obj_scale,
                 const float* ent_scale, int ld, int extra_cols) {
     if (A <= 0 || A > MAXC || !buckets) return MLB_EINVAL;
@@ -301,14 +362,17 @@ MLB_API int mlb_sample_discrete_f32(void* stream, const float* head, int ld,
                                     const uint32_t* policy_key, const int32_t* buckets_host,
                                     int num_components, long long rows, int partitionable,
                                     int deterministic, int32_t* actions, float* log_probs,
-                                    float* values) {
+                                    float* values, const float* critic_bins_host,
+                                    int num_critic_bins) {
     MLB_REQUIRE(head && actions && rows >= 0 && ld > 0 && (deterministic || policy_key));
     if (rows == 0) return MLB_OK;
     Layout L;
-    const int vcol = make_layout(L, buckets_host, num_components, nullptr, nullptr, ld, values ? 1 : 0);
+    CriticBins cb;
+    if (make_bins(cb, critic_bins_host, num_critic_bins)) return MLB_EINVAL;
+    const int vcol = make_layout(L, buckets_host, num_components, nullptr, nullptr, ld, values ? cb.V : 0);
     if (vcol < 0) return vcol;
     sample_kernel<<<mlb_cdiv(rows * num_components, 128), 128, 0, mlb_stream(stream)>>>(
-        head, ld, policy_key, L, rows, partitionable, deterministic, actions, log_probs, values, vcol);
+        head, ld, policy_key, L, rows, partitionable, deterministic, actions, log_probs, values, vcol, cb);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }
@@ -325,12 +389,16 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
                              const float* obj_scale_host, const float* ent_scale_host,
                              int num_components, long long rows, long long M, float clip_coef,
                              float value_loss_coef, int flags, void* d_head, float* d_bias,
-                             mlb_ppo_stats* stats, void* ws, size_t ws_bytes) {
+                             mlb_ppo_stats* stats, void* ws, size_t ws_bytes,
+                             const float* critic_bins_host, int num_critic_bins) {
     MLB_REQUIRE(head && actions && old_log_probs && advantages && returns && d_head && stats);
     MLB_REQUIRE(rows > 0 && M > 0 && ld > 0 && obj_scale_host && ent_scale_host);
     MLB_REQUIRE(!(flags & MLB_PPO_CLIP_VALUE_LOSS) || old_values);
     Layout L;
-    const int vcol = make_layout(L, buckets_host, num_components, obj_scale_host, ent_scale_host, ld, 1);
+    CriticBins cb;
+    if (make_bins(cb, critic_bins_host, num_critic_bins)) return MLB_EINVAL;
+    MLB_REQUIRE(cb.V == 1 || !(vn_params || (flags & (MLB_PPO_CLIP_VALUE_LOSS | MLB_PPO_HUBER_VALUE_LOSS))));
+    const int vcol = make_layout(L, buckets_host, num_components, obj_scale_host, ent_scale_host, ld, cb.V);
     if (vcol < 0) return vcol;
     const unsigned g = mlb_cdiv(rows, ROWS_PER_BLOCK);
     if (!ws || ws_bytes < (size_t)g * sizeof(LossPartial)) return MLB_EWS;
@@ -341,7 +409,7 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     LossPartial* part = reinterpret_cast<LossPartial*>(ws);
     ppo_loss_kernel<<<g, ROWS_PER_BLOCK, smem, s>>>(head, ld, actions, old_log_probs, advantages,
         returns, old_values, mb_weights, adv_mean_rstd, vn_params, L, rows, M, clip_coef,
-        value_loss_coef, flags, vcol, d_head, d_bias, part);
+        value_loss_coef, flags, vcol, d_head, d_bias, part, cb);
     MLB_CHECK_LAUNCH();
     ppo_loss_final_kernel<<<1, 256, 0, s>>>(part, (int)g, (double)rows, num_components,
                                             value_loss_coef, stats);

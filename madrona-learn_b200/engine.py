@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import c_float, c_int, c_ll, c_size_t, call, ptr
 from .actor_critic import ActorCritic, BackboneEncoder, BackboneShared, RecurrentBackboneEncoder
 from .cfg import DiscreteActionsConfig
-from .models import MLP, DenseLayerCritic, DenseLayerDiscreteActor
+from .models import MLP, DenseLayerCritic, DenseLayerDiscreteActor, DreamerV3Critic
 
 F32 = torch.float32
 
@@ -74,8 +74,8 @@ class PolicyProgram:
             raise NotImplementedError('LSTM on the bf16 tensor-core path: next (use compute_dtype=float32)')
         if not isinstance(actor_critic.actor, DenseLayerDiscreteActor):
             raise NotImplementedError('actor must be DenseLayerDiscreteActor')
-        if not isinstance(actor_critic.critic, DenseLayerCritic):
-            raise NotImplementedError('critic must be DenseLayerCritic (distributional critics: next)')
+        if not isinstance(actor_critic.critic, (DenseLayerCritic, DreamerV3Critic)):
+            raise NotImplementedError('critic must be DenseLayerCritic or DreamerV3Critic (HL-Gauss: next)')
         self.ac = actor_critic
         self.device = torch.device(device)
         self.mlp = enc.net
@@ -99,7 +99,17 @@ class PolicyProgram:
         self.buckets = buckets
         self.A = len(buckets)
         self.sumA = int(sum(buckets))
-        self.V = 1
+        # critic columns: 1 (plain) or num_bins two-hot logits (DreamerV3Critic, ml/models.py:157-174)
+        self.twohot = isinstance(actor_critic.critic, DreamerV3Critic)
+        self.V = int(actor_critic.critic.num_bins) if self.twohot else 1
+        if self.twohot:
+            # SymExpTwoHotDistribution._compute_bins (ml/dists.py:127-141), float32 like the reference
+            half = np.linspace(-14, 0, self.V // 2 + 1, dtype=np.float32)
+            half = (np.sign(half) * np.expm1(np.abs(half))).astype(np.float32)
+            bins = np.concatenate([half, -half[:-1][::-1]]).astype(np.float32)
+            self._bins_c = (ctypes.c_float * self.V)(*bins.tolist())
+        else:
+            self._bins_c = None
         # head width: padded to 4 (fp32 path) or to 64 (tensor-core path: one 64-wide UMMA N tile
         # and one SWIZZLE_128B atom of the MN-major dhead operand)
         self.NH = _round_up(self.sumA + self.V, 64 if self.tc else 4)
@@ -178,8 +188,8 @@ class PolicyProgram:
         return {
             'backbone': {'encoder': enc},
             'actor': {'impl': {'kernel': W[:, :self.sumA], 'bias': B[:self.sumA]}},
-            'critic': {'Dense_0': {'kernel': W[:, self.sumA:self.sumA + 1],
-                                   'bias': B[self.sumA:self.sumA + 1]}},
+            'critic': {'Dense_0': {'kernel': W[:, self.sumA:self.sumA + self.V],
+                                   'bias': B[self.sumA:self.sumA + self.V]}},
         }
 
     def init_params(self, seed):
@@ -204,7 +214,8 @@ class PolicyProgram:
             self.lstm.init_host(host, orth)
         W = torch.zeros(self.feat, self.NH, dtype=F32)
         W[:, :self.sumA] = orth(self.feat, self.sumA, self.ac.actor.weight_init_scale)
-        W[:, self.sumA:self.sumA + 1] = orth(self.feat, 1, self.ac.critic.weight_init_scale)
+        if not self.twohot:      # DreamerV3Critic is zero-initialised (ml/models.py:159)
+            W[:, self.sumA:self.sumA + 1] = orth(self.feat, 1, self.ac.critic.weight_init_scale)
         host[self.head_w_off:self.head_w_off + W.numel()] = W.reshape(-1)
         self.params.copy_(host)
         self.finalize_params()
@@ -221,10 +232,10 @@ class PolicyProgram:
             self.lstm.load_oracle(host, p['lstm'][0])
         W = torch.zeros(self.feat, self.NH, dtype=F32)
         W[:, :self.sumA] = torch.from_numpy(np.asarray(p['actor']['kernel'], np.float32))
-        W[:, self.sumA:self.sumA + 1] = torch.from_numpy(np.asarray(p['critic']['kernel'], np.float32))
+        W[:, self.sumA:self.sumA + self.V] = torch.from_numpy(np.asarray(p['critic']['kernel'], np.float32))
         B = torch.zeros(self.NH, dtype=F32)
         B[:self.sumA] = torch.from_numpy(np.asarray(p['actor']['bias'], np.float32))
-        B[self.sumA:self.sumA + 1] = torch.from_numpy(np.asarray(p['critic']['bias'], np.float32))
+        B[self.sumA:self.sumA + self.V] = torch.from_numpy(np.asarray(p['critic']['bias'], np.float32))
         host[self.head_w_off:self.head_w_off + W.numel()] = W.reshape(-1)
         host[self.head_b_off:self.head_b_off + self.NH] = B
         self.params.copy_(host)
@@ -373,7 +384,7 @@ class PolicyProgram:
                deterministic=False):
         call('mlb_sample_discrete_f32', ptr(head), c_int(self.NH), ptr(policy_key), self._buckets_c,
              c_int(self.A), c_ll(rows), c_int(int(partitionable)), c_int(int(deterministic)),
-             ptr(actions), ptr(log_probs), ptr(values))
+             ptr(actions), ptr(log_probs), ptr(values), self._bins_c, c_int(self.V))
 
     # ---------------------------------------------------------------------------------
     # training forward + backward (ActorCritic.update ml/actor_critic.py:98-128 + autodiff)
@@ -504,7 +515,7 @@ class PolicyProgram:
     def apply_critic_only(self, rnn_states, obs, train=False):
         x = self._obs2d(obs)
         head = self.forward_infer(x, x.shape[0], rnn_states)
-        return {'critic': head[:, self.sumA:self.sumA + 1].clone()}, rnn_states
+        return {'critic': head[:, self.sumA:self.sumA + self.V].clone()}, rnn_states
 
     def apply_actor_only(self, rnn_states, obs, train=False):
         out, rnn = self.apply_rollout(None, rnn_states, obs, sample_actions=False)

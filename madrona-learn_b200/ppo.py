@@ -135,6 +135,9 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
         raise NotImplementedError('filter_advantages / importance_sample_trajectories are "next" '
                                   'rows (SURVEY 8f rank 2)')
     prog = policy_state.program
+    if bool(cfg.dreamer_v3_critic) != bool(prog.twohot) or cfg.hlgauss_critic:
+        raise ValueError('cfg.dreamer_v3_critic must match the critic module (DreamerV3Critic <-> True, '
+                         'DenseLayerCritic <-> False); hlgauss_critic is a "next" row')
     st = rollout_data.store
     C, Tp, B = rollout_data.C, rollout_data.Tp, rollout_data.B
     if ws is None:
@@ -209,7 +212,7 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
                      prog._buckets_c, ws.obj_scale, ws.ent_scale, c_int(prog.A), c_ll(rows), c_ll(M),
                      c_float(hp.clip_coef), c_float(hp.value_loss_coef), c_int(flags | prog.loss_flags),
                      ptr(tw['dhead']), ptr(prog.head_bias_grad()), ptr(tw['stats_out']), ptr(tw['loss_ws']),
-                     c_size_t(tw['loss_ws'].numel()))
+                     c_size_t(tw['loss_ws'].numel()), prog._bins_c, c_int(prog.V))
                 prog.backward(mb['obs'].view(rows, prog.obs_dim), rows, seq)
                 grad_scale = 1.0
                 if dist_ctx is not None:

@@ -18,7 +18,7 @@ class PPOCfg:
                  value_loss_coef=0.5, entropy_coef=0.01, max_grad_norm=0.5, lr=3e-4,
                  clip_value_loss=False, huber_value_loss=False, normalize_advantages=True,
                  normalize_values=False, value_normalizer_decay=0.99999, gamma=0.99,
-                 gae_lambda=0.95, partitionable=False):
+                 gae_lambda=0.95, partitionable=False, dreamer_v3_critic=False):
         self.__dict__.update(locals())
         del self.__dict__['self']
 
@@ -63,9 +63,46 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, 
     surr2 = adv * clipped
     obj = np.minimum(surr1, surr2)                                        # :162
 
+    returns = mb['returns'].reshape(rows, 1).astype(np.float32)
+    if cfg.dreamer_v3_critic:
+        # two-hot cross-entropy on the critic's bin logits (:169-177, ml/dists.py:172-208)
+        from . import dists
+        clog = critic.reshape(rows, -1)
+        V = clog.shape[1]
+        b = dists.bins(V)
+        lo = np.clip((b <= returns).astype(np.int32).sum(-1) - 1, 0, V - 1)
+        hi = np.clip(V - (b > returns).astype(np.int32).sum(-1), 0, V - 1)
+        same = lo == hi
+        dl = np.where(same, 1, np.abs(b[lo] - returns[:, 0]))
+        du = np.where(same, 1, np.abs(b[hi] - returns[:, 0]))
+        wl, wu = dl / (dl + du), du / (dl + du)
+        two_hot = np.zeros((rows, V), f)
+        np.add.at(two_hot, (np.arange(rows), lo), wl)
+        np.add.at(two_hot, (np.arange(rows), hi), wu)
+        m_ = clog.max(-1, keepdims=True)
+        logp = clog - (np.log(np.exp(clog - m_).sum(-1, keepdims=True)) + m_)
+        vloss = -(two_hot * logp).sum(-1, keepdims=True)
+        value_errs = dists.twohot_mean(clog.astype(np.float32)).astype(f) - returns.astype(f)
+        action_obj_avg = np.mean(w * obj)
+        value_loss = cfg.value_loss_coef * np.mean(w * vloss)
+        entropy_avg = cfg.entropy_coef * np.mean(w * ent)
+        loss = -action_obj_avg + value_loss - entropy_avg
+        out = dict(loss=f(loss), action_obj=obj, value_losses=vloss, entropies=ent, value_errs=value_errs,
+                   new_vn_state=None, logits=logits, critic=critic, new_log_probs=new_lp)
+        if not want_grads:
+            return out
+        pick1 = (surr1 <= surr2)
+        inside = (ratio >= 1.0 - cfg.clip_coef) & (ratio <= 1.0 + cfg.clip_coef)
+        dobj_dratio = np.where(pick1 | inside, adv, 0.0)
+        dlogp = -(w * dobj_dratio * ratio) / (rows * A)
+        dent = -(cfg.entropy_coef * w) / (rows * A) * np.ones_like(ent)
+        dlogits = nn.action_stats_bwd(logits, acts, cfg.buckets, dlogp, dent)
+        dcritic = cfg.value_loss_coef * w * (np.exp(logp) - two_hot) / rows
+        out['grads'] = nn.actor_critic_bwd(p, cache, dlogits, dcritic, quant)
+        out['dlogits'], out['dcritic'] = dlogits, dcritic
+        return out
     # value loss, plain critic branch (:186-218)
     v_new = critic.reshape(rows, 1)
-    returns = mb['returns'].reshape(rows, 1).astype(np.float32)
     norm = EMANormalizer(cfg.value_normalizer_decay) if cfg.normalize_values else None
     if norm is None:
         value_errs = v_new - returns.astype(f)

@@ -193,7 +193,7 @@ def test_ppo_loss_and_full_backward(mlb, clipv, huber, vn):
          ptr(dv['advantages']), ptr(dv['returns']), ptr(dv['values']), ptr(None),
          ptr(adv_mr), ptr(vnp), prog._buckets_c, obj_scale, ent_scale, c_int(A), c_ll(rows), c_ll(M),
          c_float(cfg.clip_coef), c_float(cfg.value_loss_coef), c_int(flags | prog.loss_flags), ptr(tw['dhead']),
-         ptr(prog.head_bias_grad()), ptr(tw['stats_out']), ptr(tw['loss_ws']), c_size_t(tw['loss_ws'].numel()))
+         ptr(prog.head_bias_grad()), ptr(tw['stats_out']), ptr(tw['loss_ws']), c_size_t(tw['loss_ws'].numel()), None, c_int(0))
     st = _lib.PPOStats.from_buffer_copy(tw['stats_out'].cpu().numpy().tobytes())
     np.testing.assert_allclose(st.loss, ref['loss'], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(st.action_obj, np.mean(ref['action_obj']), rtol=1e-4, atol=1e-6)

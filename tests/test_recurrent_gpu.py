@@ -74,7 +74,7 @@ def test_lstm_forward_backward_vs_oracle(mlb):
          ptr(dv['advantages']), ptr(dv['returns']), ptr(None), ptr(None), ptr(adv_mr), ptr(None),
          prog._buckets_c, obj_scale, ent_scale, c_int(A), c_ll(rows), c_ll(M), c_float(cfg.clip_coef),
          c_float(cfg.value_loss_coef), c_int(prog.loss_flags), ptr(tw['dhead']), ptr(prog.head_bias_grad()),
-         ptr(tw['stats_out']), ptr(tw['loss_ws']), c_size_t(tw['loss_ws'].numel()))
+         ptr(tw['stats_out']), ptr(tw['loss_ws']), c_size_t(tw['loss_ws'].numel()), None, c_int(0))
     prog.backward(obs_d, rows, seq)
     g = prog.to_oracle_params(prog.grads)
     onn.tree_map(lambda a, b: np.testing.assert_array_less(_rel(a, b), 2e-4), g, ref['grads'])

@@ -154,7 +154,7 @@ def test_tc_policy_forward_backward_vs_oracle(mlb, D, H, L, rows):
          ptr(dv['advantages']), ptr(dv['returns']), ptr(None), ptr(None), ptr(adv_mr), ptr(None),
          prog._buckets_c, obj_scale, ent_scale, c_int(A), c_ll(rows), c_ll(M), c_float(cfg.clip_coef),
          c_float(cfg.value_loss_coef), c_int(prog.loss_flags), ptr(tw['dhead']), ptr(prog.head_bias_grad()), ptr(tw['stats_out']), ptr(tw['loss_ws']),
-         c_size_t(tw['loss_ws'].numel()))
+         c_size_t(tw['loss_ws'].numel()), None, c_int(0))
     prog.backward(obs_d, rows)
     g = prog.to_oracle_params(prog.grads)
     flat = lambda t: np.concatenate([x.reshape(-1).astype(np.float64) for x in

@@ -36,7 +36,7 @@ for clip in (0.2, 10.0):
     adv_mr=torch.tensor([mean,rstd,0,0],dtype=torch.float32,device=DEV)
     obj_scale=(ctypes.c_float*A)(*[1.0/(rows*A)]*A); ent_scale=(ctypes.c_float*A)(*[cfg.entropy_coef/(rows*A)]*A)
     prog.zero_grads()
-    call('mlb_ppo_loss_f32',ptr(head),c_int(prog.NH),ptr(dv['actions']),ptr(dv['log_probs']),ptr(dv['advantages']),ptr(dv['returns']),ptr(None),ptr(None),ptr(adv_mr),ptr(None),prog._buckets_c,obj_scale,ent_scale,c_int(A),c_ll(rows),c_ll(M),c_float(cfg.clip_coef),c_float(cfg.value_loss_coef),c_int(prog.loss_flags),ptr(tw['dhead']),ptr(prog.head_bias_grad()),ptr(tw['stats_out']),ptr(tw['loss_ws']),c_size_t(tw['loss_ws'].numel()))
+    call('mlb_ppo_loss_f32',ptr(head),c_int(prog.NH),ptr(dv['actions']),ptr(dv['log_probs']),ptr(dv['advantages']),ptr(dv['returns']),ptr(None),ptr(None),ptr(adv_mr),ptr(None),prog._buckets_c,obj_scale,ent_scale,c_int(A),c_ll(rows),c_ll(M),c_float(cfg.clip_coef),c_float(cfg.value_loss_coef),c_int(prog.loss_flags),ptr(tw['dhead']),ptr(prog.head_bias_grad()),ptr(tw['stats_out']),ptr(tw['loss_ws']),c_size_t(tw['loss_ws'].numel()), None, c_int(0))
     prog.backward(obs_d,rows)
     g=prog.to_oracle_params(prog.grads)
     dh=tw['dhead'].cpu().numpy()
