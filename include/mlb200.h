@@ -251,6 +251,33 @@ int mlb_sample_discrete_f32(void* stream, const float* head, int ld, const uint3
 /* head then carries num_critic_bins critic logits and `values` receives the two-hot mean.       */
 
 /* ------------------------------------------------------------------------------------ */
+/* mlb_policy_rollout_tc: one launch for a whole rollout policy step (compute_dtype bf16):  */
+/* the PRNG key chain of ml/rollouts.py:878-880 (key_in -> key_out, policy key internal),   */
+/* the observation copy into the rollout store (:637-668; obs_store may be NULL),           */
+/* ActorCritic.rollout (ml/actor_critic.py:74-96) = num_layers x [Dense, LayerNorm, ReLU]   */
+/* + heads, and DiscreteActionDistributions.sample (ml/dists.py:26-44).  A CTA owns 128     */
+/* agents; activations stay in shared memory / TMEM between layers.                         */
+/* Weights are the bf16 transposed copies W_l^T [hidden, d_l] (d_0 = obs_dim) and           */
+/* Wh^T [head_width, hidden] with fp32 LayerNorm scale/bias and head bias; key_in != key_out. */
+/* head_out (may be NULL) [rows, head_width] fp32 receives the raw head outputs.            */
+/* ------------------------------------------------------------------------------------ */
+#define MLB_MLP_TC_MAX_LAYERS 4
+typedef struct mlb_mlp_tc_desc {
+    int num_layers, obs_dim, hidden, head_width;
+    const void* w_t[MLB_MLP_TC_MAX_LAYERS];
+    const float* scale[MLB_MLP_TC_MAX_LAYERS];
+    const float* bias[MLB_MLP_TC_MAX_LAYERS];
+    const void* wh_t;
+    const float* head_bias;
+} mlb_mlp_tc_desc;
+int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* desc_host, const float* obs,
+                          float* obs_store, long long rows, const uint32_t* key_in,
+                          uint32_t* key_out, const int32_t* buckets_host, int num_components,
+                          int partitionable, int deterministic, int32_t* actions,
+                          float* log_probs, float* values, const float* critic_bins_host,
+                          int num_critic_bins, float* head_out);
+
+/* ------------------------------------------------------------------------------------ */
 /* K8: fused PPO loss + gradient w.r.t. the head outputs (ml/ppo.py:129-262 + autodiff).    */
 /* rows = T'*M in [T', M] order.  adv_mean_rstd: NULL or device f32[2] (per-minibatch       */
 /* z-score, ml/ppo.py:134-143).  vn_params: NULL or device f32[4] = {mu_old, sigma_old,     */

@@ -75,6 +75,7 @@ SIGNATURES = {
     'mlb_rnn_reset_f32': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
+    'mlb_policy_rollout_tc': (c_int, [P, P, P, P, c_ll, P, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P]),
     'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),
     'mlb_ppo_loss_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, c_ll, c_ll,
                                  c_float, c_float, c_int, P, P, P, P, c_size_t, P, c_int]),
@@ -101,6 +102,13 @@ class Bf16Copy(ctypes.Structure):
     """mlb_bf16_copy."""
     _fields_ = [('dst_t', c_void_p), ('dst', c_void_p), ('rows', ctypes.c_int32), ('cols', ctypes.c_int32),
                 ('ld_t', ctypes.c_int32), ('ld_d', ctypes.c_int32)]
+
+
+class MlpTcDesc(ctypes.Structure):
+    """mlb_mlp_tc_desc."""
+    _fields_ = [('num_layers', ctypes.c_int32), ('obs_dim', ctypes.c_int32), ('hidden', ctypes.c_int32),
+                ('head_width', ctypes.c_int32), ('w_t', c_void_p * 4), ('scale', c_void_p * 4),
+                ('bias', c_void_p * 4), ('wh_t', c_void_p), ('head_bias', c_void_p)]
 
 
 class PPOStats(ctypes.Structure):

@@ -11,6 +11,7 @@ Everything else raises NotImplementedError loudly (no fallback).
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -379,6 +380,35 @@ class PolicyProgram:
         _, B = self.head_views(self.params)
         gemm_tc(x, self.wh_t, w['head'], B, rows, self.NH, self.feat, self.feat, self.feat, self.NH, 0, 0, 0)
         return w['head']
+
+    @property
+    def fused_rollout(self):
+        """True when mlb_policy_rollout_tc covers this network (bf16, feed-forward MLP encoder that
+        fits one CTA's shared memory); MLB_FUSED_ROLLOUT=0 keeps the layer-by-layer path."""
+        if not self.tc or self.lstm is not None or os.environ.get('MLB_FUSED_ROLLOUT', '1') == '0':
+            return False
+        if self.H > 256 or self.H % 64 or self.L > 4 or self.NH > 256 or self.obs_dim > 256:
+            return False
+        panels = (max(self.H, self.obs_dim + 63)) // 64
+        smem = panels * 16384 + 2 * self.H * 128 + 128 * (self.NH + 1) * 4 + (4 * self.H + 512) * 4 + 1216
+        return smem <= 227 * 1024
+
+    def rollout_step_fused(self, obs, obs_store, rows, key_in, key_out, actions, log_probs, values,
+                           partitionable=False, deterministic=False, head_out=None):
+        """One launch: key chain + obs store copy + MLP + heads + sampling (mlb_policy_rollout_tc)."""
+        if getattr(self, '_tc_desc', None) is None or self._tc_desc_base != self.params.data_ptr():
+            d = _lib.MlpTcDesc()
+            d.num_layers, d.obs_dim, d.hidden, d.head_width = self.L, self.obs_dim, self.H, self.NH
+            for i in range(self.L):
+                _, s, b = self.layer_views(self.params, i)
+                d.w_t[i], d.scale[i], d.bias[i] = self.w_t[i].data_ptr(), s.data_ptr(), b.data_ptr()
+            _, B = self.head_views(self.params)
+            d.wh_t, d.head_bias = self.wh_t.data_ptr(), B.data_ptr()
+            self._tc_desc, self._tc_desc_base = d, self.params.data_ptr()
+        call('mlb_policy_rollout_tc', ctypes.byref(self._tc_desc), ptr(obs), ptr(obs_store), c_ll(rows),
+             ptr(key_in), ptr(key_out), self._buckets_c, c_int(self.A), c_int(int(partitionable)),
+             c_int(int(deterministic)), ptr(actions), ptr(log_probs), ptr(values), self._bins_c,
+             c_int(self.V), ptr(head_out))
 
     def sample(self, head, rows, policy_key, actions, log_probs, values, partitionable=False,
                deterministic=False):

@@ -190,6 +190,7 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         self._scratch_actions = e(B, prog.A, dtype=torch.int32)
         self.env_returns_trace = e(C * Tp, B)
         self.policy_key = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._key_alt = torch.zeros(2, dtype=torch.int32, device=dev)
         self.resets = torch.zeros(self._cfg.num_worlds, 1, dtype=torch.int32, device=dev)
         T = C * Tp
         self._gae_ws = torch.empty(K.lib().mlb_gae_workspace(T, B) + 16, dtype=torch.uint8, device=dev)
@@ -232,19 +233,28 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         prog, N, st = self._prog, self._cfg.sim_batch_size, self.store
         gamma = self._cfg.reward_gamma
         Tp = self._num_bptt_steps
+        key_home = rs.prng_key
         for s in range(Tp):
             with profile('Policy Inference'):
-                call('mlb_rollout_keys', ptr(rs.prng_key), ptr(self.policy_key),
-                     c_int(int(self.partitionable)))
                 pre = policy_states.obs_preprocess.preprocess(
                     policy_states.obs_preprocess_state, rs.cur_obs, True)
                 ob = pre[self._ob_name]
                 slab = st['obs'][c, s, 0]
-                call('mlb_copy_bytes', ptr(ob), ptr(slab), c_size_t(slab.numel() * 4))
-                head = prog.forward_infer(slab, N, rs.rnn_states)
                 actions = st['actions'][c, s, 0]
-                prog.sample(head, N, self.policy_key, actions, st['log_probs'][c, s, 0],
-                            st['values'][c, s, 0], self.partitionable)
+                if prog.fused_rollout:
+                    # key chain + obs store + MLP + heads + sampling in one launch; the advanced
+                    # PRNG key lands in the alternate buffer, so the two buffers trade places
+                    prog.rollout_step_fused(ob, slab, N, rs.prng_key, self._key_alt, actions,
+                                            st['log_probs'][c, s, 0], st['values'][c, s, 0],
+                                            self.partitionable)
+                    rs.prng_key, self._key_alt = self._key_alt, rs.prng_key
+                else:
+                    call('mlb_rollout_keys', ptr(rs.prng_key), ptr(self.policy_key),
+                         c_int(int(self.partitionable)))
+                    call('mlb_copy_bytes', ptr(ob), ptr(slab), c_size_t(slab.numel() * 4))
+                    head = prog.forward_infer(slab, N, rs.rnn_states)
+                    prog.sample(head, N, self.policy_key, actions, st['log_probs'][c, s, 0],
+                                st['values'][c, s, 0], self.partitionable)
             with profile('Rollout Step'):
                 step_input = {
                     'state': rs.sim_state, 'actions': {self._act_name: actions},
@@ -267,6 +277,9 @@ class RolloutManager:                   # ml/rollouts.py:373-826
                      ptr(self.env_returns_trace[c * Tp + s]), c_ll(N), c_float(gamma))
                 if self._lstm is not None:                # rnn_reset_fn(rnn_states, dones)  (:942)
                     self._lstm.reset(rs.rnn_states, d_slab.view(torch.uint8), N)
+        if rs.prng_key is not key_home:                   # odd number of fused steps: move the key home
+            call('mlb_copy_bytes', ptr(rs.prng_key), ptr(key_home), c_size_t(8))
+            rs.prng_key, self._key_alt = key_home, rs.prng_key
         return rs
 
     def _bootstrap_values(self, policy_states, rs):     # :607-635
@@ -279,8 +292,12 @@ class RolloutManager:                   # ml/rollouts.py:373-826
             nbytes = N * self._lstm.RH * 4
             call('mlb_copy_bytes', ptr(rs.rnn_states[0][0]), ptr(states[0][0]), c_size_t(nbytes))
             call('mlb_copy_bytes', ptr(rs.rnn_states[1][0]), ptr(states[1][0]), c_size_t(nbytes))
-        head = prog.forward_infer(ob, N, states)
         # critic column of the head -> bootstrap [1, B, 1] (the greedy actions are discarded)
+        if prog.fused_rollout:
+            prog.rollout_step_fused(ob, None, N, None, None, self._scratch_actions, None, self.bootstrap,
+                                    deterministic=True)
+            return
+        head = prog.forward_infer(ob, N, states)
         prog.sample(head, N, None, self._scratch_actions, None, self.bootstrap, deterministic=True)
 
     def _finalize_rollouts(self, train_states, metrics, user_state, finish_hook, metrics_hook):

@@ -215,3 +215,79 @@ def test_tc_update_iter_runs_and_tracks_fp32(mlb, monkeypatch):
     # paths must stay within a few lr of each other
     n = min(f[3].size, b[3].size)      # head padding differs (NH 28 vs 64): compare the MLP part
     assert np.abs(f[3][:n // 2] - b[3][:n // 2]).max() < 3e-3
+
+
+# ------------------------------------------------------------------------------------------
+# one-launch rollout step (mlb_policy_rollout_tc) == key chain + obs copy + layer-by-layer
+# forward + sampling kernel.  Key bits / obs copy: bit-exact.  Heads: both paths quantise to bf16
+# at the same points and differ only in fp32 summation order inside LayerNorm, so rel-L2 <= 5e-3;
+# sampled actions may flip only where two Gumbel-perturbed logits are within that noise (>= 99.5 %
+# equal); log-probs of equal actions agree to 2e-2 abs.
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('D,H,L,rows,twohot', [(64, 256, 3, 8192, False), (32, 128, 2, 1000, False),
+                                               (40, 64, 1, 130, False), (64, 256, 3, 4096, True),
+                                               (256, 256, 4, 512, False)])
+def test_fused_rollout_step_matches_layerwise(mlb, D, H, L, rows, twohot):
+    from madrona_learn_b200._lib import c_int, call, ptr
+    from madrona_learn_b200.engine import PolicyProgram
+    m = mlb
+    buckets = [4, 8, 5, 5, 2, 2]
+    A = len(buckets)
+    ac = m.ActorCritic(
+        backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(net=m.models.MLP(H, L))),
+        actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(buckets)),
+        critic=m.models.DreamerV3Critic() if twohot else m.models.DenseLayerCritic())
+    prog = PolicyProgram(ac, D, {'act': m.DiscreteActionsConfig(buckets)}, DEV, torch.bfloat16)
+    prog.init_params(7)
+    with torch.no_grad():          # non-trivial LayerNorm affine + head weights
+        g = torch.Generator(device=DEV).manual_seed(3)
+        for i in range(L):
+            _, s, b = prog.layer_views(prog.params, i)
+            s.add_(0.1 * torch.randn(s.shape, device=DEV, generator=g))
+            b.add_(0.1 * torch.randn(b.shape, device=DEV, generator=g))
+        W, B = prog.head_views(prog.params)
+        W.add_(0.2 * torch.randn(W.shape, device=DEV, generator=g))
+        B.add_(0.1 * torch.randn(B.shape, device=DEV, generator=g))
+    prog.refresh_bf16()
+    assert prog.fused_rollout
+    obs = torch.randn(rows, D, device=DEV, generator=g)
+    key = torch.tensor([123456789, -42], dtype=torch.int32, device=DEV)
+
+    # layer-by-layer path
+    k_ref, pk = key.clone(), torch.zeros(2, dtype=torch.int32, device=DEV)
+    call('mlb_rollout_keys', ptr(k_ref), ptr(pk), c_int(0))
+    head_ref = prog.forward_infer(obs, rows).clone()
+    a_ref = torch.zeros(rows, A, dtype=torch.int32, device=DEV)
+    lp_ref = torch.zeros(rows, A, device=DEV)
+    v_ref = torch.zeros(rows, device=DEV)
+    prog.sample(head_ref, rows, pk, a_ref, lp_ref, v_ref)
+
+    # fused path
+    k_out = torch.zeros(2, dtype=torch.int32, device=DEV)
+    store = torch.zeros(rows, D, device=DEV)
+    head = torch.zeros(rows, prog.NH, device=DEV)
+    a = torch.full((rows, A), -1, dtype=torch.int32, device=DEV)
+    lp = torch.zeros(rows, A, device=DEV)
+    v = torch.zeros(rows, device=DEV)
+    prog.rollout_step_fused(obs, store, rows, key, k_out, a, lp, v, head_out=head)
+    torch.cuda.synchronize()
+    assert torch.equal(k_out, k_ref)
+    assert torch.equal(store, obs)
+    used = prog.sumA + prog.V
+    rel = (head[:, :used] - head_ref[:, :used]).norm() / head_ref[:, :used].norm()
+    assert rel < 5e-3, rel
+    same = (a == a_ref).all(dim=1)
+    assert same.float().mean() > 0.995, same.float().mean()
+    assert (a >= 0).all() and (a < torch.tensor(buckets, device=DEV)).all()
+    assert (lp - lp_ref)[same].abs().max() < 2e-2
+    assert (v - v_ref).abs().max() < 2e-2 * max(1.0, v_ref.abs().max().item())
+
+    # deterministic (bootstrap) mode: greedy actions + values, no keys, no store
+    a2 = torch.zeros(rows, A, dtype=torch.int32, device=DEV)
+    v2 = torch.zeros(rows, device=DEV)
+    prog.rollout_step_fused(obs, None, rows, None, None, a2, None, v2, deterministic=True)
+    a3 = torch.zeros(rows, A, dtype=torch.int32, device=DEV)
+    prog.sample(head_ref, rows, None, a3, None, None, deterministic=True)
+    torch.cuda.synchronize()
+    assert ((a2 == a3).all(dim=1)).float().mean() > 0.995
+    assert torch.allclose(v2, v, atol=1e-6)
