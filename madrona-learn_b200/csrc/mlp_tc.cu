@@ -47,7 +47,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int K, int k_per_split) {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_bar = empty_bar + STAGES;

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "tc_common.cuh"
+#include "mlp_tc_persist.cuh"
 
 namespace {
 
@@ -114,7 +115,7 @@ __device__ __forceinline__ Prologue prologue(uint8_t* smem_raw, const CUtensorMa
                                              const CUtensorMap* tmB, int HN, uint32_t tmem_cols,
                                              const float* scale, const float* bias) {
     Prologue p;
-    p.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    p.smem = align_smem_1024(smem_raw);
     p.full_bar = reinterpret_cast<uint64_t*>(p.smem + FusedSmem<STAGES>::bar_off(HN));
     p.empty_bar = p.full_bar + STAGES;
     p.acc_bar = p.empty_bar + STAGES;
@@ -426,6 +427,8 @@ MLB_API int mlb_dense_ln_relu_fwd_tc(void* stream, const void* X, const void* Wt
     MLB_REQUIRE(X && Wt && scale && bias && Y && M > 0 && K > 0 && width_ok(HN));
     MLB_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && mlb_aligned16(X) && mlb_aligned16(Wt) && mlb_aligned16(Y) &&
                 (XH == nullptr || mlb_aligned16(XH)));
+    if (tcp::persist_ok(M, K, HN))
+        return tcp::launch_fwd_persist(mlb_stream(stream), X, Wt, scale, bias, Y, XH, rstd, M, K, HN, ldx, ldw);
     CUtensorMap tA, tB;
     int rc = make_map(&tA, X, K, M, ldx, 64, 128);
     if (rc) return rc;
@@ -457,6 +460,9 @@ MLB_API int mlb_dense_dx_lnbwd_tc(void* stream, const void* DZ_in, const void* W
     MLB_REQUIRE(DZ_in && W && scale && bias && XH && rstd && DZ_out && dscale && dbias);
     MLB_REQUIRE(M > 0 && K > 0 && width_ok(HN) && lda % 8 == 0 && ldw % 8 == 0);
     MLB_REQUIRE(mlb_aligned16(DZ_in) && mlb_aligned16(W) && mlb_aligned16(XH) && mlb_aligned16(DZ_out));
+    if (tcp::persist_ok(M, K, HN))
+        return tcp::launch_dx_persist(mlb_stream(stream), DZ_in, W, scale, bias, XH, rstd, DZ_out, dscale, dbias,
+                                      M, K, HN, lda, ldw);
     CUtensorMap tA, tB;
     int rc = make_map(&tA, DZ_in, K, M, lda, 64, 128);
     if (rc) return rc;

@@ -1,0 +1,556 @@
+// Persistent variants of the fused tensor-core MLP layer kernels (see mlp_tc_fused.cu for the math
+// and the reference lines they replace).  Used for the PPO minibatch shapes (many more 128-row
+// tiles than SMs, layer width <= 256):
+//
+//   * one CTA per SM loops over row tiles (static round-robin schedule);
+//   * the layer's weight matrix (<= 128 KB bf16) is loaded into shared memory ONCE per CTA and
+//     stays resident, so the mainloop only streams the 16 KB activation k-blocks through a TMA
+//     ring (the non-persistent kernels re-read W from L2 for every tile: 2x the A traffic);
+//   * the fp32 accumulator is double-buffered in TMEM (2 x 256 of the 512 columns): the MMA warp
+//     fills tile i+1 while the eight epilogue warps run LayerNorm(+backward) on tile i;
+//   * sixteen epilogue warps (4 TMEM lane quadrants x 4 column groups) work independently: the
+//     only CTA-level synchronisation per tile is the 128-thread exchange of LayerNorm row
+//     partials inside a quadrant.  Each warp transposes its [32 rows x 32 cols] bf16 block
+//     through shared memory (conflict-free XOR layouts) so that global stores are 64-byte row
+//     segments -- no TMA-store staging panels, proxy fences or CTA barriers on the critical path.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+#include "mlp_tc_persist.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int P_THREADS = 576;           // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
+constexpr int FWD_A_STAGES = 3;         // forward: 3 x 16 KB activation ring + 16 x 2 KB per-warp transpose tiles
+constexpr int BWD_A_STAGES = 2;         // backward: 2 x 16 KB dZ ring + 3 x 16 KB xhat/dz panel ring
+constexpr int BWD_XH_BUFS = 3;
+constexpr int MAX_A_STAGES = 8;
+constexpr float LN_EPS = 1e-6f;
+
+struct PLayout {
+    int w_bytes, a_off, stage_off, misc_off, total;
+};
+// staging_bytes: fwd 32 KB (Y | XH panel); bwd: xhat/dz panel ring
+__host__ __device__ inline PLayout p_layout(int K, int HN, int a_stages, int staging_bytes) {
+    PLayout l;
+    const int num_kb = (K + BK - 1) / BK;
+    l.w_bytes = num_kb * HN * 128;
+    l.a_off = l.w_bytes;
+    l.stage_off = l.a_off + a_stages * 16384;
+    l.misc_off = l.stage_off + staging_bytes;
+    // misc: scale|bias (2*HN f32) + colsums (2*HN f32) + row partials [2][4][128][2] f32 + barriers (256 B)
+    l.total = l.misc_off + (4 * HN + 2048) * 4 + 256 + 1024;
+    return l;
+}
+
+struct PBars {
+    uint64_t *full, *empty, *w_bar, *acc_full, *acc_empty, *xh_full, *xh_empty;
+    uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ PBars p_bars(uint8_t* misc_end) {
+    PBars b;
+    b.full = reinterpret_cast<uint64_t*>(misc_end);
+    b.empty = b.full + MAX_A_STAGES;
+    b.w_bar = b.empty + MAX_A_STAGES;
+    b.acc_full = b.w_bar + 1;        // [2]
+    b.acc_empty = b.acc_full + 2;    // [2]
+    b.xh_full = b.acc_empty + 2;     // [4]
+    b.xh_empty = b.xh_full + 4;      // [4]
+    b.tmem_slot = reinterpret_cast<uint32_t*>(b.xh_empty + 4);
+    return b;
+}
+
+// producer + MMA issuer shared by both kernels.  XH_BUFS > 0: the producer also streams the xhat
+// panels of every tile twice (LayerNorm-backward pass 1 and pass 2) through an XH_BUFS-deep ring.
+template <int XH_BUFS>
+__device__ __forceinline__ void p_mainloop(const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                           const CUtensorMap* tmXH, uint8_t* smem, const PLayout& L,
+                                           const PBars& bars, uint32_t tmem_base, int warp, int lane,
+                                           int num_tiles, int K, int HN, int A_STAGES) {
+    const int num_kb = (K + BK - 1) / BK;
+    if (warp == 0) {
+        if (lane == 0) {
+            // W and the first A_STAGES activation k-blocks were issued by p_prologue (p_prime)
+            const int num_panels = HN / 64;
+            const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            const int a_total = my_tiles * num_kb;
+            int it = a_total < A_STAGES ? a_total : A_STAGES, xit = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                // the NEXT tile's operand first: its MMA overlaps this tile's epilogue, while the xhat
+                // panels below are paced by that epilogue
+                const int a_target = (ti + 2) * num_kb < a_total ? (ti + 2) * num_kb : a_total;
+                for (; it < a_target; ++it) {
+                    const int s = it % A_STAGES;
+                    const int tile = blockIdx.x + (it / num_kb) * gridDim.x;
+                    mbar_wait_spin(&bars.empty[s], ((it / A_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&bars.full[s], 16384u);
+                    tma_load_2d(tmA, &bars.full[s], smem + L.a_off + s * 16384, (it % num_kb) * BK, tile * BM);
+                }
+                if (XH_BUFS > 0) {
+                    const int tile = blockIdx.x + ti * gridDim.x;
+                    for (int rep = 0; rep < 2; ++rep)
+                        for (int pnl = 0; pnl < num_panels; ++pnl, ++xit) {
+                            const int s = xit % (XH_BUFS > 0 ? XH_BUFS : 1);
+                            mbar_wait_spin(&bars.xh_empty[s], ((xit / (XH_BUFS > 0 ? XH_BUFS : 1)) & 1) ^ 1);
+                            mbar_expect_tx(&bars.xh_full[s], 16384u);
+                            tma_load_2d(tmXH, &bars.xh_full[s], smem + L.stage_off + s * 16384, pnl * 64, tile * BM);
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(false, false, HN);
+            mbar_wait_spin(bars.w_bar, 0);
+            int it = 0, i = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mbar_wait_spin(&bars.acc_empty[buf], ((i >> 1) & 1) ^ 1);     // epilogue drained this buffer
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % A_STAGES;
+                    mbar_wait_spin(&bars.full[s], (it / A_STAGES) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + L.a_off + s * 16384);
+                    const uint32_t sb = smem_u32(smem + kb * HN * 128);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        tcgen05_mma_f16(d_tmem, umma_desc(sa + k * 32, 16, 1024), umma_desc(sb + k * 32, 16, 1024),
+                                        idesc, (kb | k) ? 1u : 0u);
+                    tcgen05_commit(&bars.empty[s]);
+                }
+                tcgen05_commit(&bars.acc_full[buf]);
+            }
+        }
+    }
+}
+
+struct PState {
+    uint8_t* smem;
+    PLayout L;
+    PBars bars;
+    float* fsm;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ PState p_prologue(uint8_t* smem_raw, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                             int M, int K, int HN, int a_stages, int staging_bytes,
+                                             const float* scale, const float* bias) {
+    PState p;
+    p.smem = align_smem_1024(smem_raw);
+    p.L = p_layout(K, HN, a_stages, staging_bytes);
+    p.fsm = reinterpret_cast<float*>(p.smem + p.L.misc_off);
+    p.bars = p_bars(reinterpret_cast<uint8_t*>(p.fsm + 4 * HN + 2048));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmB)) : "memory");
+        for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(&p.bars.full[s], 1); mbar_init(&p.bars.empty[s], 1); }
+        mbar_init(p.bars.w_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&p.bars.acc_full[s], 1); mbar_init(&p.bars.acc_empty[s], 16); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&p.bars.xh_full[s], 1); mbar_init(&p.bars.xh_empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // prime the pipeline before anything else in the prologue: resident W + the first ring fill
+        const int num_kb = (K + BK - 1) / BK;
+        const int num_tiles = (M + BM - 1) / BM;
+        mbar_expect_tx(p.bars.w_bar, (uint32_t)p.L.w_bytes);
+        for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_2d(tmB, p.bars.w_bar, p.smem + kb * HN * 128, kb * BK, 0);
+        const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int prime = my_tiles * num_kb < a_stages ? my_tiles * num_kb : a_stages;
+        for (int it = 0; it < prime; ++it) {
+            mbar_expect_tx(&p.bars.full[it], 16384u);
+            tma_load_2d(tmA, &p.bars.full[it], p.smem + p.L.a_off + it * 16384, (it % num_kb) * BK,
+                        (blockIdx.x + (it / num_kb) * gridDim.x) * BM);
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(p.bars.tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < HN; i += blockDim.x) {
+        p.fsm[i] = scale[i];
+        p.fsm[HN + i] = bias[i];
+        p.fsm[2 * HN + i] = 0.f;
+        p.fsm[3 * HN + i] = 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    p.tmem_base = *p.bars.tmem_slot;
+    return p;
+}
+
+__device__ __forceinline__ void p_teardown(uint32_t tmem_base, int warp) {
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+__device__ __forceinline__ float warp_reduce_scatter32p(float (&v)[32], int lane) {
+#pragma unroll
+    for (int b = 16; b >= 1; b >>= 1) {
+        const bool up = (lane & b) != 0;
+#pragma unroll
+        for (int j = 0; j < b; ++j) {
+            const float send = up ? v[j] : v[j + b];
+            const float keep = up ? v[j + b] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, b);
+        }
+    }
+    return v[0];
+}
+
+// the four warps of one TMEM lane quadrant (one per column group) meet here
+__device__ __forceinline__ void quad_bar(int quad) { named_bar_sync(1 + quad, 128); }
+
+// Row-partial exchange between the 4 column groups of a quadrant (double-buffered by tile parity)
+__device__ __forceinline__ void exchange2(float* part, int buf, int grp, int rt, int quad, float& a, float& b) {
+    float2* pp = reinterpret_cast<float2*>(part) + buf * 512;
+    pp[grp * 128 + rt] = make_float2(a, b);
+    quad_bar(quad);
+    const float2 p0 = pp[rt], p1 = pp[128 + rt], p2 = pp[256 + rt], p3 = pp[384 + rt];
+    a = (p0.x + p1.x) + (p2.x + p3.x);
+    b = (p0.y + p1.y) + (p2.y + p3.y);
+}
+
+// ---- per-warp transpose tile: [32 rows x 64 B], 16-byte slot q of row r at r*64 + ((q ^ ((r>>1)&3)) << 4)
+__device__ __forceinline__ void wtile_put(uint8_t* wt, int lane, const uint32_t (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(wt + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+            make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+// coalesced write-out: instruction k covers rows 8k..8k+7, four lanes per row (64 contiguous bytes)
+__device__ __forceinline__ void wtile_store(const uint8_t* wt, int lane, __nv_bfloat16* gbase, int ld,
+                                            int rows_valid) {
+    const int c = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = k * 8 + (lane >> 2);
+        const uint4 v = *reinterpret_cast<const uint4*>(wt + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+        if (r < rows_valid) *reinterpret_cast<uint4*>(gbase + (size_t)r * ld + c * 8) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(P_THREADS, 1)
+fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const float* __restrict__ scale, const float* __restrict__ bias,
+                   __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ XH,
+                   float* __restrict__ rstd_out, int M, int K, int HN, int a_stages, int dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (M + BM - 1) / BM;
+    PState p = p_prologue(smem_raw, &tmA, &tmB, M, K, HN, a_stages, 32768, scale, bias);
+    if (warp < 2) {
+        p_mainloop<0>(&tmA, &tmB, nullptr, p.smem, p.L, p.bars, p.tmem_base, warp, lane, num_tiles, K, HN, a_stages);
+    } else {
+        const int quad = warp & 3, grp = (warp - 2) >> 2;
+        const int rt = quad * 32 + lane;
+        float* part = p.fsm + 4 * HN;
+        const float* s = p.fsm;
+        const float* b = p.fsm + HN;
+        uint8_t* wt = p.smem + p.L.stage_off + (warp - 2) * 2048;
+        const int nchunks = HN / 32;
+        const float invH = 1.f / (float)HN;
+        int i = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int m0 = tile * BM;
+            const int rows_valid = M - (m0 + quad * 32);         // rows of this warp's block inside M
+            const uint32_t taddr = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
+            mbar_wait(&p.bars.acc_full[buf], (i >> 1) & 1);
+            tcgen05_fence_after();
+            // pass 1: row statistics over this column group's chunks
+            float sum = 0.f, sq = 0.f;
+            if (!(dbg & 4))
+            for (int ch = grp; ch < nchunks; ch += 4) {
+                uint32_t r[32];
+                tmem_ld32(taddr + ch * 32, r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float z = __uint_as_float(r[j]); sum += z; sq = fmaf(z, z, sq); }
+            }
+            exchange2(part, buf, grp, rt, quad, sum, sq);
+            const float mean = sum * invH;
+            const float rstd = rsqrtf(fmaxf(0.f, sq * invH - mean * mean) + LN_EPS);
+            if (grp == 0 && m0 + rt < M && rstd_out) rstd_out[m0 + rt] = rstd;
+            // pass 2: normalise, scale/bias, ReLU -> bf16, transposed through the warp tile
+            bool released = false;
+            if (!(dbg & 2))
+            for (int ch = grp; ch < nchunks; ch += 4) {
+                const int c = ch * 32;
+                uint32_t r[32];
+                tmem_ld32(taddr + c, r);
+                if (ch + 4 >= nchunks) {                     // last TMEM read of this warp for this tile
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+                    released = true;
+                }
+                uint32_t yp[16], xp[16];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 sv = *reinterpret_cast<const float4*>(s + c + 4 * q);
+                    const float4 bv = *reinterpret_cast<const float4*>(b + c + 4 * q);
+                    const float x0 = (__uint_as_float(r[4 * q]) - mean) * rstd;
+                    const float x1 = (__uint_as_float(r[4 * q + 1]) - mean) * rstd;
+                    const float x2 = (__uint_as_float(r[4 * q + 2]) - mean) * rstd;
+                    const float x3 = (__uint_as_float(r[4 * q + 3]) - mean) * rstd;
+                    yp[2 * q] = pack_bf16(fmaxf(0.f, fmaf(x0, sv.x, bv.x)), fmaxf(0.f, fmaf(x1, sv.y, bv.y)));
+                    yp[2 * q + 1] = pack_bf16(fmaxf(0.f, fmaf(x2, sv.z, bv.z)), fmaxf(0.f, fmaf(x3, sv.w, bv.w)));
+                    xp[2 * q] = pack_bf16(x0, x1);
+                    xp[2 * q + 1] = pack_bf16(x2, x3);
+                }
+                __syncwarp();                                // earlier read-back of the tile is complete
+                wtile_put(wt, lane, yp);
+                __syncwarp();
+                wtile_store(wt, lane, Y + (size_t)(m0 + quad * 32) * HN + c, HN, (dbg & 1) ? 0 : rows_valid);
+                if (XH) {
+                    __syncwarp();
+                    wtile_put(wt, lane, xp);
+                    __syncwarp();
+                    wtile_store(wt, lane, XH + (size_t)(m0 + quad * 32) * HN + c, HN, (dbg & 1) ? 0 : rows_valid);
+                }
+            }
+            if (!released) {                                 // column group without chunks (HN < 128)
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+            }
+        }
+    }
+    p_teardown(p.tmem_base, warp);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: dZ_prev = LN'/ReLU'(dZ W^T), per-feature dscale / dbias
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(P_THREADS, 1)
+dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmXH, const float* __restrict__ scale,
+                  const float* __restrict__ bias, const float* __restrict__ rstd_in,
+                  __nv_bfloat16* __restrict__ DZ, float* __restrict__ dscale, float* __restrict__ dbias,
+                  int M, int K, int HN, int a_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (M + BM - 1) / BM;
+    PState p = p_prologue(smem_raw, &tmA, &tmB, M, K, HN, a_stages, BWD_XH_BUFS * 16384, scale, bias);
+    if (warp < 2) {
+        p_mainloop<BWD_XH_BUFS>(&tmA, &tmB, &tmXH, p.smem, p.L, p.bars, p.tmem_base, warp, lane, num_tiles, K, HN,
+                                a_stages);
+    } else {
+        const int quad = warp & 3, grp = (warp - 2) >> 2;
+        const int rt = quad * 32 + lane;
+        const float* s = p.fsm;
+        const float* b = p.fsm + HN;
+        float* cs = p.fsm + 2 * HN;
+        float* cb = p.fsm + 3 * HN;
+        float* part = p.fsm + 4 * HN;
+        uint8_t* ring = p.smem + p.L.stage_off;
+        const int nchunks = HN / 32, num_panels = HN / 64;
+        const float invH = 1.f / (float)HN;
+        int i = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int m0 = tile * BM;
+            const int row = m0 + rt;
+            const float rstd = row < M ? rstd_in[row] : 0.f;
+            const uint32_t taddr = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
+            const int xbase = i * 2 * num_panels;            // producer's panel sequence number of this tile
+            mbar_wait(&p.bars.acc_full[buf], (i >> 1) & 1);
+            tcgen05_fence_after();
+            // pass 1: m1 = mean(dxhat), m2 = mean(dxhat * xhat); dscale / dbias partial sums
+            float m1 = 0.f, m2 = 0.f;
+            for (int ch = grp; ch < nchunks; ch += 4) {
+                const int xit = xbase + (ch >> 1);
+                const int xs = xit % BWD_XH_BUFS;
+                mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
+                const int c = ch * 32, hf = ch & 1;
+                uint32_t r[32];
+                tmem_ld32(taddr + c, r);
+                const uint8_t* pan = ring + xs * 16384;
+                float gx[32], g[32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(pan + sw128(rt, hf * 4 + q));
+                    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                    const float4 sa = *reinterpret_cast<const float4*>(s + c + 8 * q);
+                    const float4 sb = *reinterpret_cast<const float4*>(s + c + 8 * q + 4);
+                    const float4 ba = *reinterpret_cast<const float4*>(b + c + 8 * q);
+                    const float4 bb = *reinterpret_cast<const float4*>(b + c + 8 * q + 4);
+                    const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int j = 8 * q + e;
+                        const float xh = (e & 1) ? bf16hi(w4[e >> 1]) : bf16lo(w4[e >> 1]);
+                        const float dy = __uint_as_float(r[j]);
+                        const float du = (fmaf(xh, sv[e], bv[e]) > 0.f) ? dy : 0.f;       // ReLU mask
+                        const float dxh = du * sv[e];
+                        m1 += dxh;
+                        m2 = fmaf(dxh, xh, m2);
+                        gx[j] = du * xh;
+                        g[j] = du;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p.bars.xh_empty[xs]);       // this warp is done with the panel
+                const float csum = warp_reduce_scatter32p(gx, lane);
+                const float bsum = warp_reduce_scatter32p(g, lane);
+                atomicAdd(&cs[c + lane], csum);
+                atomicAdd(&cb[c + lane], bsum);
+            }
+            exchange2(part, buf, grp, rt, quad, m1, m2);
+            const float c1 = rstd * m1 * invH;               // dz = rstd*dxhat - rstd*m1 - xhat*(rstd*m2)
+            const float c2 = rstd * m2 * invH;
+            // pass 2: dz written over xhat in the (re-loaded) panel, then written out by the same warp
+            bool released = false;
+            for (int ch = grp; ch < nchunks; ch += 4) {
+                const int xit = xbase + num_panels + (ch >> 1);
+                const int xs = xit % BWD_XH_BUFS;
+                mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
+                const int c = ch * 32, hf = ch & 1;
+                uint32_t r[32];
+                tmem_ld32(taddr + c, r);
+                if (ch + 4 >= nchunks) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+                    released = true;
+                }
+                uint8_t* pan = ring + xs * 16384;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4* slot = reinterpret_cast<uint4*>(pan + sw128(rt, hf * 4 + q));
+                    const uint4 u = *slot;
+                    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                    const float4 sa = *reinterpret_cast<const float4*>(s + c + 8 * q);
+                    const float4 sb = *reinterpret_cast<const float4*>(s + c + 8 * q + 4);
+                    const float4 ba = *reinterpret_cast<const float4*>(b + c + 8 * q);
+                    const float4 bb = *reinterpret_cast<const float4*>(b + c + 8 * q + 4);
+                    const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                    float dz8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float xh = (e & 1) ? bf16hi(w4[e >> 1]) : bf16lo(w4[e >> 1]);
+                        const float dy = __uint_as_float(r[8 * q + e]);
+                        const float rs = (fmaf(xh, sv[e], bv[e]) > 0.f) ? rstd * sv[e] : 0.f;
+                        dz8[e] = fmaf(-c2, xh, fmaf(rs, dy, -c1));
+                    }
+                    *slot = make_uint4(pack_bf16(dz8[0], dz8[1]), pack_bf16(dz8[2], dz8[3]),
+                                       pack_bf16(dz8[4], dz8[5]), pack_bf16(dz8[6], dz8[7]));
+                }
+                __syncwarp();
+                // coalesced write-out of this warp's [32 x 32] block: a quarter-warp reads rows R and
+                // R+4 (different swizzle halves -> conflict-free), four lanes per 64-byte row segment
+                {
+                    const int cc = lane & 3, sub = (lane >> 2) & 1, pair = lane >> 3;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rl = k * 8 + pair + 4 * sub;
+                        const int rr = quad * 32 + rl;
+                        const uint4 v = *reinterpret_cast<const uint4*>(pan + sw128(rr, hf * 4 + cc));
+                        if (m0 + rr < M) *reinterpret_cast<uint4*>(DZ + (size_t)(m0 + rr) * HN + c + cc * 8) = v;
+                    }
+                }
+                fence_async_smem();                          // generic accesses before the panel's next TMA fill
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p.bars.xh_empty[xs]);
+            }
+            if (!released) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+            }
+        }
+        named_bar_sync(5, 512);                              // all shared-memory column sums are final
+        for (int k = threadIdx.x - 64; k < HN; k += 512) {
+            atomicAdd(dscale + k, cs[k]);
+            atomicAdd(dbias + k, cb[k]);
+        }
+    }
+    p_teardown(p.tmem_base, warp);
+}
+
+}  // namespace
+
+namespace tcp {
+
+int sm_count() {
+    static int n = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return n;
+}
+
+// deepest activation ring that fits next to the resident weights (at least `floor_stages`)
+static int pick_stages(int K, int HN, int staging_bytes, int floor_stages) {
+    static const int cap = [] { const char* v = getenv("MLB_TC_STAGES"); return v ? atoi(v) : MAX_A_STAGES; }();
+    int st = floor_stages;
+    while (st < cap && st < MAX_A_STAGES && p_layout(K, HN, st + 1, staging_bytes).total <= 227 * 1024) ++st;
+    return st;
+}
+
+bool persist_ok(int M, int K, int HN) {
+    static const int mode = [] {
+        const char* v = getenv("MLB_TC_PERSIST");
+        return !v ? 1 : (v[0] == '0' ? 0 : (v[0] == 'f' ? 2 : 1));
+    }();
+    if (mode == 0 || HN < 64 || HN > 256 || HN % 64 || K > 256) return false;
+    return mode == 2 || (M + tc::BM - 1) / tc::BM > sm_count();
+}
+
+int launch_fwd_persist(cudaStream_t st, const void* X, const void* Wt, const float* scale, const float* bias,
+                       void* Y, void* XH, float* rstd, int M, int K, int HN, int ldx, int ldw) {
+    CUtensorMap tA, tB;
+    int rc;
+    if ((rc = make_map(&tA, X, K, M, ldx, 64, 128))) return rc;
+    if ((rc = make_map(&tB, Wt, K, HN, ldw, 64, HN))) return rc;
+    const int a_stages = pick_stages(K, HN, 32768, FWD_A_STAGES);
+    const int smem = p_layout(K, HN, a_stages, 32768).total;
+    cudaError_t e = cudaFuncSetAttribute(fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles = (M + BM - 1) / BM;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    static const int dbg = [] { const char* v = getenv("MLB_TC_DEBUG"); return v ? atoi(v) : 0; }();
+    fwd_persist_kernel<<<grid, P_THREADS, smem, st>>>(tA, tB, scale, bias, static_cast<__nv_bfloat16*>(Y),
+                                                     static_cast<__nv_bfloat16*>(XH), rstd, M, K, HN, a_stages, dbg);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+int launch_dx_persist(cudaStream_t st, const void* DZ_in, const void* W, const float* scale, const float* bias,
+                      const void* XH, const float* rstd, void* DZ_out, float* dscale, float* dbias, int M,
+                      int K, int HN, int lda, int ldw) {
+    CUtensorMap tA, tB, tXH;
+    int rc;
+    if ((rc = make_map(&tA, DZ_in, K, M, lda, 64, 128))) return rc;
+    if ((rc = make_map(&tB, W, K, HN, ldw, 64, HN))) return rc;
+    if ((rc = make_map(&tXH, XH, HN, M, HN, 64, 128))) return rc;
+    const int a_stages = pick_stages(K, HN, BWD_XH_BUFS * 16384, BWD_A_STAGES);
+    const int smem = p_layout(K, HN, a_stages, BWD_XH_BUFS * 16384).total;
+    cudaError_t e = cudaFuncSetAttribute(dx_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles = (M + BM - 1) / BM;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    dx_persist_kernel<<<grid, P_THREADS, smem, st>>>(tA, tB, tXH, scale, bias, rstd, static_cast<__nv_bfloat16*>(DZ_out),
+                                                    dscale, dbias, M, K, HN, a_stages);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+}  // namespace tcp

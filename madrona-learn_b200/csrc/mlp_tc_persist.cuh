@@ -1,0 +1,17 @@
+// Internal launchers of the persistent fused-layer kernels (mlp_tc_persist.cu), dispatched from the
+// C-ABI entry points in mlp_tc_fused.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tcp {
+
+int sm_count();
+// MLB_TC_PERSIST=0 disables, =force uses the persistent kernels for every supported shape
+bool persist_ok(int M, int K, int HN);
+int launch_fwd_persist(cudaStream_t st, const void* X, const void* Wt, const float* scale, const float* bias,
+                       void* Y, void* XH, float* rstd, int M, int K, int HN, int ldx, int ldw);
+int launch_dx_persist(cudaStream_t st, const void* DZ_in, const void* W, const float* scale, const float* bias,
+                      const void* XH, const float* rstd, void* DZ_out, float* dscale, float* dbias, int M,
+                      int K, int HN, int lda, int ldw);
+
+}  // namespace tcp

@@ -53,7 +53,7 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
                       int deterministic, int32_t* __restrict__ actions, float* __restrict__ log_probs,
                       float* __restrict__ values, float* __restrict__ head_out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     const int H = a.H, NH = a.NH, L = a.L, D = a.D;
     const int act_panels = (H > D ? H : D + 63) / 64;                 // panels of [128 x 64] bf16
     uint8_t* act = smem;                                              // act_panels * 16 KB

@@ -18,6 +18,12 @@ constexpr int UMMA_K = 16;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// 1024-byte alignment (SWIZZLE_128B atoms) of the dynamic shared-memory base.  Done as an offset on
+// the __shared__ array itself: round-tripping the pointer through uintptr_t loses the address
+// space and every later access degrades to generic LD/ST instead of LDS/STS.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+    return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -43,6 +49,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 22)) __trap();      // never hang the GPU on a protocol bug
+    }
+}
+// latency-critical single-thread roles (TMA producer, MMA issuer): poll without the suspend hint
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 26)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst,
