@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int ROWS_PER_BLOCK = 128;
+constexpr int LOSS_RB_MIN = 32;          // smallest rows-per-block of the loss kernel (workspace sizing)
 constexpr int MAXC = MLB_MAX_ACTION_COMPONENTS;
 
 struct Layout {
@@ -62,27 +62,51 @@ __global__ void rollout_keys_kernel(uint32_t* __restrict__ prng_key, uint32_t* _
     policy_key[0] = p0; policy_key[1] = p1;
 }
 
-// Division-free staging of the first `ncols` columns of a [128 x ld] tile of head rows: one warp
-// per row, lanes over columns (shared tile stride `ts` is odd -> conflict-free row access).
+// Staging of a [rb x ld] tile of head rows (ld % 4 == 0, 16-byte aligned rows): flat float4 /
+// packed accesses over the whole row width; the shared tile keeps an odd row stride `ts` so the
+// row-owning threads read it without bank conflicts.  Only the first `ncols` columns are kept.
 __device__ __forceinline__ void stage_in(float* tile, int ts, const float* __restrict__ g, long long row0,
-                                         long long rows, int ld, int ncols) {
-    const int nrow = (int)min((long long)ROWS_PER_BLOCK, rows - row0);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int r = warp; r < nrow; r += nw) {
-        const float* src = g + (row0 + r) * ld;
-        for (int c = lane; c < ncols; c += 32) tile[r * ts + c] = __ldg(src + c);
+                                         long long rows, int ld, int ncols, int rb) {
+    const int nrow = (int)min((long long)rb, rows - row0);
+    const int vpr = ld >> 2;                                   // float4 per row
+    const float4* src = reinterpret_cast<const float4*>(g + row0 * ld);
+    for (int e = threadIdx.x; e < nrow * vpr; e += blockDim.x) {
+        const int r = e / vpr, c = (e - r * vpr) << 2;
+        if (c < ncols) {
+            const float4 v = __ldg(src + e);
+            float* t = tile + r * ts + c;
+            t[0] = v.x;
+            if (c + 1 < ncols) t[1] = v.y;
+            if (c + 2 < ncols) t[2] = v.z;
+            if (c + 3 < ncols) t[3] = v.w;
+        }
     }
 }
 
 // Gradients back to global: fp32 or bf16 rows of width ld; columns >= ncols are written as zeros.
-template <typename T>
-__device__ __forceinline__ void stage_out(const float* tile, int ts, T* __restrict__ g, long long row0,
-                                          long long rows, int ld, int ncols) {
-    const int nrow = (int)min((long long)ROWS_PER_BLOCK, rows - row0);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int r = warp; r < nrow; r += nw) {
-        T* dst = g + (row0 + r) * ld;
-        for (int c = lane; c < ld; c += 32) dst[c] = (T)(c < ncols ? tile[r * ts + c] : 0.f);
+__device__ __forceinline__ void stage_out(const float* tile, int ts, float* __restrict__ g, long long row0,
+                                          long long rows, int ld, int ncols, int rb) {
+    const int nrow = (int)min((long long)rb, rows - row0);
+    const int vpr = ld >> 2;
+    float4* dst = reinterpret_cast<float4*>(g + row0 * ld);
+    for (int e = threadIdx.x; e < nrow * vpr; e += blockDim.x) {
+        const int r = e / vpr, c = (e - r * vpr) << 2;
+        const float* t = tile + r * ts + c;
+        dst[e] = make_float4(c < ncols ? t[0] : 0.f, c + 1 < ncols ? t[1] : 0.f, c + 2 < ncols ? t[2] : 0.f,
+                             c + 3 < ncols ? t[3] : 0.f);
+    }
+}
+__device__ __forceinline__ void stage_out(const float* tile, int ts, __nv_bfloat16* __restrict__ g, long long row0,
+                                          long long rows, int ld, int ncols, int rb) {
+    const int nrow = (int)min((long long)rb, rows - row0);
+    const int vpr = ld >> 2;
+    uint2* dst = reinterpret_cast<uint2*>(g + row0 * ld);
+    for (int e = threadIdx.x; e < nrow * vpr; e += blockDim.x) {
+        const int r = e / vpr, c = (e - r * vpr) << 2;
+        const float* t = tile + r * ts + c;
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(c < ncols ? t[0] : 0.f, c + 1 < ncols ? t[1] : 0.f);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(c + 2 < ncols ? t[2] : 0.f, c + 3 < ncols ? t[3] : 0.f);
+        dst[e] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
     }
 }
 
@@ -138,82 +162,152 @@ struct LossPartial {
     float mn[4], mx[4];
 };
 
-__global__ void __launch_bounds__(ROWS_PER_BLOCK)
+// Fused PPO loss + head gradients.  Thread layout: a block owns RB rows; thread t plays role
+// t / RB for row t % RB -- roles 0..A-1 are the action components, role A is the critic.  RB is a
+// multiple of 32, so a warp holds 32 consecutive rows of ONE role: no divergence between lanes,
+// conflict-free tile rows (odd stride), and (A+1)x the parallelism of a thread-per-row layout.
+struct WarpPartial {
+    float p0, p1;                  // loss contributions (obj | vl, entropy | -)
+    float s0, ss0, mn0, mx0;       // metric stream 0 of the role (action obj | value loss)
+    float s1, ss1, mn1, mx1;       // metric stream 1 of the role (entropy | |value err|)
+};
+
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// One action component of one row, bucket count known at compile time (warp-uniform dispatch):
+// fully unrolled, logits / exponentials in registers, no predication.
+struct CompOut { float obj, H; };
+template <int NB>
+__device__ __forceinline__ CompOut loss_component(float* __restrict__ l, int act, float olp, float a, float w,
+                                                  float clip, float obj_scale, float ent_scale) {
+    float lg[NB], e[NB];
+    float mxl = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) { lg[j] = l[j]; mxl = fmaxf(mxl, lg[j]); }
+    float se = 0.f;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) { e[j] = expf(lg[j] - mxl); se += e[j]; }
+    const float lse = logf(se) + mxl;
+    const float inv_se = __frcp_rn(se);
+    float H = 0.f, lp_new = 0.f;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        lg[j] -= lse;                                   // log_softmax
+        e[j] *= inv_se;                                 // softmax
+        H = fmaf(-e[j], lg[j], H);
+        lp_new = (j == act) ? lg[j] : lp_new;
+    }
+    const float ratio = expf(lp_new - olp);                         // ml/ppo.py:146-147
+    const float surr1 = a * ratio;
+    const float surr2 = a * fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
+    const float obj = fminf(surr1, surr2);                          // :155-162
+    const bool inside = (ratio >= 1.f - clip) && (ratio <= 1.f + clip);
+    const float dobj = (surr1 <= surr2 || inside) ? a : 0.f;
+    const float dlp = -(w * dobj * ratio) * obj_scale;              // d loss / d lp_new
+    const float dH = -(w * ent_scale);                              // d loss / d H
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        float g = -e[j] * dlp + dH * (-e[j] * (lg[j] + H));
+        if (j == act) g += dlp;
+        l[j] = g;                                                   // overwrite logits with grads
+    }
+    return CompOut{obj, H};
+}
+
+__global__ void __launch_bounds__(1024)
 ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restrict__ actions,
                 const float* __restrict__ old_lp, const float* __restrict__ adv,
                 const float* __restrict__ ret, const float* __restrict__ old_v,
                 const float* __restrict__ mb_w, const float* __restrict__ adv_mr,
                 const float* __restrict__ vn, Layout L, long long rows, long long M,
                 float clip, float vcoef, int flags, int vcol, void* __restrict__ dhead,
-                float* __restrict__ dbias, LossPartial* __restrict__ part, CriticBins cb) {
+                float* __restrict__ dbias, LossPartial* __restrict__ part, CriticBins cb, int RB, float inv_rows) {
     extern __shared__ float tile[];
-    const long long row0 = (long long)blockIdx.x * ROWS_PER_BLOCK;
+    __shared__ WarpPartial wpart[32];
+    const long long row0 = (long long)blockIdx.x * RB;
     const int ncols = vcol + cb.V;
     const int ts = ncols | 1;                 // odd tile stride
-    stage_in(tile, ts, head, row0, rows, ld, ncols);
+    float* colsum = tile + RB * ts;           // [ncols]
+    stage_in(tile, ts, head, row0, rows, ld, ncols, RB);
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) colsum[c] = 0.f;
     __syncthreads();
-    const long long row = row0 + threadIdx.x;
-    double p_obj = 0.0, p_vl = 0.0, p_ent = 0.0;
-    double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-    float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    auto acc = [&](int k, float x) { s[k] += (double)x; ss[k] += (double)x * (double)x;
-                                     mn[k] = fminf(mn[k], x); mx[k] = fmaxf(mx[k], x); };
-    if (row < rows) {
-        float* l = tile + threadIdx.x * ts;
+    const int role = threadIdx.x / RB, r = threadIdx.x - role * RB;
+    const long long row = row0 + r;
+    const bool valid = row < rows;
+    float p0 = 0.f, p1 = 0.f, x0 = 0.f, x1 = 0.f;
+    if (valid) {
+        float* l = tile + r * ts;
         const float w = mb_w ? mb_w[row % M] : 1.f;
-        float a = adv[row];
-        if (adv_mr) a = (a - adv_mr[0]) * adv_mr[1];                    // zscore_data, per minibatch
-        const float inv_rows = 1.f / (float)rows;
-        for (int i = 0; i < L.A; ++i) {
+        if (role < L.A) {
+            const int i = role;
+            float a = adv[row];
+            if (adv_mr) a = (a - adv_mr[0]) * adv_mr[1];                // zscore_data, per minibatch
             const int off = L.off[i], nb = L.nb[i];
-            float mxl = -INFINITY;
-            for (int j = 0; j < nb; ++j) mxl = fmaxf(mxl, l[off + j]);
-            float se = 0.f;
-            for (int j = 0; j < nb; ++j) se += expf(l[off + j] - mxl);
-            const float lse = logf(se) + mxl;
-            const float inv_se = 1.f / se;
-            float H = 0.f;
-            for (int j = 0; j < nb; ++j) {
-                const float lp = l[off + j] - lse;
-                const float p = expf(l[off + j] - mxl) * inv_se;        // jax.nn.softmax
-                H -= p * lp;
-            }
             const int act = min(max(actions[row * L.A + i], 0), nb - 1);   // never index outside the bucket
-            const float lp_new = l[off + act] - lse;
-            const float ratio = expf(lp_new - old_lp[row * L.A + i]);   // ml/ppo.py:146-147
-            const float surr1 = a * ratio;
-            const float cr = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
-            const float surr2 = a * cr;
-            const float obj = fminf(surr1, surr2);                      // :155-162
-            const bool inside = (ratio >= 1.f - clip) && (ratio <= 1.f + clip);
-            const float dobj = (surr1 <= surr2 || inside) ? a : 0.f;
-            const float dlp = -(w * dobj * ratio) * L.obj_scale[i];     // d loss / d lp_new
-            const float dH = -(w * L.ent_scale[i]);                     // d loss / d H
-            p_obj += (double)(w * obj) * (double)L.obj_scale[i];
-            p_ent += (double)(w * H) * (double)L.ent_scale[i];
-            acc(0, obj);
-            acc(3, H);
-            for (int j = 0; j < nb; ++j) {
-                const float lp = l[off + j] - lse;
-                const float p = expf(l[off + j] - mxl) * inv_se;
-                float g = -p * dlp + dH * (-p * (lp + H));
-                if (j == act) g += dlp;
-                l[off + j] = g;                                         // overwrite logits with grads
+            const float olp = old_lp[row * L.A + i];
+            const float os = L.obj_scale[i], es = L.ent_scale[i];
+            float* lo = l + off;
+            CompOut o;
+            switch (nb) {                                               // warp-uniform
+                case 1: o = loss_component<1>(lo, act, olp, a, w, clip, os, es); break;
+                case 2: o = loss_component<2>(lo, act, olp, a, w, clip, os, es); break;
+                case 3: o = loss_component<3>(lo, act, olp, a, w, clip, os, es); break;
+                case 4: o = loss_component<4>(lo, act, olp, a, w, clip, os, es); break;
+                case 5: o = loss_component<5>(lo, act, olp, a, w, clip, os, es); break;
+                case 6: o = loss_component<6>(lo, act, olp, a, w, clip, os, es); break;
+                case 7: o = loss_component<7>(lo, act, olp, a, w, clip, os, es); break;
+                case 8: o = loss_component<8>(lo, act, olp, a, w, clip, os, es); break;
+                default: {
+                    float mxl = -INFINITY;
+                    for (int j = 0; j < nb; ++j) mxl = fmaxf(mxl, lo[j]);
+                    float se = 0.f;
+                    for (int j = 0; j < nb; ++j) se += expf(lo[j] - mxl);
+                    const float lse = logf(se) + mxl;
+                    const float inv_se = __frcp_rn(se);
+                    float H = 0.f;
+                    for (int j = 0; j < nb; ++j) H -= (expf(lo[j] - mxl) * inv_se) * (lo[j] - lse);
+                    const float ratio = expf((lo[act] - lse) - olp);
+                    const float surr1 = a * ratio;
+                    const float surr2 = a * fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
+                    const bool inside = (ratio >= 1.f - clip) && (ratio <= 1.f + clip);
+                    const float dobj = (surr1 <= surr2 || inside) ? a : 0.f;
+                    const float dlp = -(w * dobj * ratio) * os;
+                    const float dH = -(w * es);
+                    for (int j = 0; j < nb; ++j) {
+                        const float lpj = lo[j] - lse;
+                        const float pj = expf(lo[j] - mxl) * inv_se;
+                        float g = -pj * dlp + dH * (-pj * (lpj + H));
+                        if (j == act) g += dlp;
+                        lo[j] = g;
+                    }
+                    o = CompOut{fminf(surr1, surr2), H};
+                }
             }
-        }
-        if (cb.V > 1) {
+            p0 = (w * o.obj) * os;
+            p1 = (w * o.H) * es;
+            x0 = o.obj;
+            x1 = o.H;
+        } else if (cb.V > 1) {
             // distributional critic: two-hot cross-entropy (ml/ppo.py:169-177, ml/dists.py:172-208)
             const int V = cb.V;
             float* lc = l + vcol;
-            const float r = ret[row];
+            const float rr = ret[row];
             const float vmean = twohot_mean(lc, cb);
             int nle = 0, ngt = 0;
-            for (int k = 0; k < V; ++k) { nle += (cb.bins[k] <= r); ngt += (cb.bins[k] > r); }
+            for (int k = 0; k < V; ++k) { nle += (cb.bins[k] <= rr); ngt += (cb.bins[k] > rr); }
             const int lo = min(max(nle - 1, 0), V - 1), hi = min(max(V - ngt, 0), V - 1);
             const bool same = lo == hi;
-            const float dl = same ? 1.f : fabsf(cb.bins[lo] - r);
-            const float du = same ? 1.f : fabsf(cb.bins[hi] - r);
+            const float dl = same ? 1.f : fabsf(cb.bins[lo] - rr);
+            const float du = same ? 1.f : fabsf(cb.bins[hi] - rr);
             const float wl = dl / (dl + du), wu = du / (dl + du);     // (sic) the reference's weights
             float mxc = -INFINITY;
             for (int k = 0; k < V; ++k) mxc = fmaxf(mxc, lc[k]);
@@ -221,9 +315,9 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
             for (int k = 0; k < V; ++k) sec += expf(lc[k] - mxc);
             const float lsec = logf(sec) + mxc;
             const float vl = -(wl * (lc[lo] - lsec) + wu * (lc[hi] - lsec));
-            p_vl += (double)(w * vl) * (double)inv_rows;
-            acc(1, vl);
-            acc(2, fabsf(vmean - r));
+            p0 = (w * vl) * inv_rows;
+            x0 = vl;
+            x1 = fabsf(vmean - rr);
             const float gsc = vcoef * w * inv_rows;
             for (int k = 0; k < V; ++k) {
                 float tk = 0.f;
@@ -232,95 +326,125 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
                 lc[k] = gsc * (expf(lc[k] - lsec) - tk);                // d CE / d logit = softmax - target
             }
         } else {
-        // critic (plain, V = 1): ml/ppo.py:186-218
-        const float v = l[vcol];
-        const float r = ret[row];
-        float verr, rn;
-        if (vn) { verr = (v * vn[1] + vn[0]) - r; rn = (r - vn[2]) * vn[3]; }
-        else { verr = v - r; rn = r; }
-        float vu = v, vmask = 1.f;
-        if (flags & MLB_PPO_CLIP_VALUE_LOSS) {
-            const float lo = old_v[row] - clip, hi = old_v[row] + clip;
-            vu = fminf(fmaxf(v, lo), hi);
-            vmask = (v >= lo && v <= hi) ? 1.f : 0.f;
+            // critic (plain, V = 1): ml/ppo.py:186-218
+            const float v = l[vcol];
+            const float rr = ret[row];
+            float verr, rn;
+            if (vn) { verr = (v * vn[1] + vn[0]) - rr; rn = (rr - vn[2]) * vn[3]; }
+            else { verr = v - rr; rn = rr; }
+            float vu = v, vmask = 1.f;
+            if (flags & MLB_PPO_CLIP_VALUE_LOSS) {
+                const float lo = old_v[row] - clip, hi = old_v[row] + clip;
+                vu = fminf(fmaxf(v, lo), hi);
+                vmask = (v >= lo && v <= hi) ? 1.f : 0.f;
+            }
+            const float d = vu - rn;
+            float vl, dvl;
+            if (flags & MLB_PPO_HUBER_VALUE_LOSS) {
+                const float q = fminf(fabsf(d), 1.f);
+                vl = 0.5f * q * q + (fabsf(d) - q);
+                dvl = fminf(fmaxf(d, -1.f), 1.f);
+            } else { vl = 0.5f * d * d; dvl = d; }
+            p0 = (w * vl) * inv_rows;
+            x0 = vl;
+            x1 = fabsf(verr);
+            l[vcol] = vcoef * w * dvl * vmask * inv_rows;
         }
-        const float d = vu - rn;
-        float vl, dvl;
-        if (flags & MLB_PPO_HUBER_VALUE_LOSS) {
-            const float q = fminf(fabsf(d), 1.f);
-            vl = 0.5f * q * q + (fabsf(d) - q);
-            dvl = fminf(fmaxf(d, -1.f), 1.f);
-        } else { vl = 0.5f * d * d; dvl = d; }
-        p_vl += (double)(w * vl) * (double)inv_rows;
-        acc(1, vl);
-        acc(2, fabsf(verr));
-        l[vcol] = vcoef * w * dvl * vmask * inv_rows;
-        }
+    }
+    // warp-level partials (fp32 over 32 rows), combined across warps / blocks in fp64 below
+    {
+        WarpPartial P;
+        P.p0 = warp_sum(p0); P.p1 = warp_sum(p1);
+        P.s0 = warp_sum(x0); P.ss0 = warp_sum(x0 * x0);
+        P.s1 = warp_sum(x1); P.ss1 = warp_sum(x1 * x1);
+        P.mn0 = warp_min_f(valid ? x0 : INFINITY); P.mx0 = warp_max_f(valid ? x0 : -INFINITY);
+        P.mn1 = warp_min_f(valid ? x1 : INFINITY); P.mx1 = warp_max_f(valid ? x1 : -INFINITY);
+        if ((threadIdx.x & 31) == 0) wpart[threadIdx.x >> 5] = P;
     }
     __syncthreads();
-    if (flags & MLB_PPO_DHEAD_BF16) stage_out(tile, ts, reinterpret_cast<__nv_bfloat16*>(dhead), row0, rows, ld, ncols);
-    else stage_out(tile, ts, reinterpret_cast<float*>(dhead), row0, rows, ld, ncols);
+    if (flags & MLB_PPO_DHEAD_BF16) stage_out(tile, ts, reinterpret_cast<__nv_bfloat16*>(dhead), row0, rows, ld, ncols, RB);
+    else stage_out(tile, ts, reinterpret_cast<float*>(dhead), row0, rows, ld, ncols, RB);
     if (dbias) {                              // bias gradients of the heads: column sums of this tile
-        const int nrow = (int)min((long long)ROWS_PER_BLOCK, rows - row0);
-        for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+        const int nrow = (int)min((long long)RB, rows - row0);
+        const int c = threadIdx.x & 63, seg = threadIdx.x >> 6, nseg = blockDim.x >> 6;
+        for (int cc = c; cc < ncols; cc += 64) {
             float acc = 0.f;
-            for (int r = 0; r < nrow; ++r) acc += tile[r * ts + c];
-            atomicAdd(dbias + c, acc);
+            for (int rr = seg; rr < nrow; rr += nseg) acc += tile[rr * ts + cc];
+            atomicAdd(&colsum[cc], acc);
         }
     }
-
-    __shared__ double smd[32];
-    __shared__ float smf[32];
-    LossPartial P;
-    P.obj = block_sum_d(p_obj, smd);
-    P.vl = block_sum_d(p_vl, smd);
-    P.ent = block_sum_d(p_ent, smd);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        P.s[k] = block_sum_d(s[k], smd);
-        P.ss[k] = block_sum_d(ss[k], smd);
-        P.mn[k] = block_min_f(mn[k], smf);
-        P.mx[k] = block_max_f(mx[k], smf);
+    if (threadIdx.x < 32) {
+        // one warp folds the per-warp partials of the block: lane = warp index
+        const int nw = blockDim.x >> 5, wpr = RB >> 5;       // warps per role
+        const int wi = threadIdx.x;
+        const bool on = wi < nw;
+        const bool comp = on && (wi / wpr) < L.A, crit = on && !comp;
+        const WarpPartial P = wpart[on ? wi : 0];
+        LossPartial out;
+        out.obj = warp_sum(comp ? (double)P.p0 : 0.0);
+        out.ent = warp_sum(comp ? (double)P.p1 : 0.0);
+        out.vl = warp_sum(crit ? (double)P.p0 : 0.0);
+        out.s[0] = warp_sum(comp ? (double)P.s0 : 0.0);  out.ss[0] = warp_sum(comp ? (double)P.ss0 : 0.0);
+        out.s[3] = warp_sum(comp ? (double)P.s1 : 0.0);  out.ss[3] = warp_sum(comp ? (double)P.ss1 : 0.0);
+        out.s[1] = warp_sum(crit ? (double)P.s0 : 0.0);  out.ss[1] = warp_sum(crit ? (double)P.ss0 : 0.0);
+        out.s[2] = warp_sum(crit ? (double)P.s1 : 0.0);  out.ss[2] = warp_sum(crit ? (double)P.ss1 : 0.0);
+        out.mn[0] = warp_min_f(comp ? P.mn0 : INFINITY); out.mx[0] = warp_max_f(comp ? P.mx0 : -INFINITY);
+        out.mn[3] = warp_min_f(comp ? P.mn1 : INFINITY); out.mx[3] = warp_max_f(comp ? P.mx1 : -INFINITY);
+        out.mn[1] = warp_min_f(crit ? P.mn0 : INFINITY); out.mx[1] = warp_max_f(crit ? P.mx0 : -INFINITY);
+        out.mn[2] = warp_min_f(crit ? P.mn1 : INFINITY); out.mx[2] = warp_max_f(crit ? P.mx1 : -INFINITY);
+        if (threadIdx.x == 0) part[blockIdx.x] = out;
     }
-    if (threadIdx.x == 0) part[blockIdx.x] = P;
+    if (dbias) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < ncols; c += blockDim.x) atomicAdd(dbias + c, colsum[c]);
+    }
 }
 
-__global__ void __launch_bounds__(256)
+// One warp per reduced quantity: warps 0-10 the fp64 sums (obj, vl, ent, s[4], ss[4]), 11-14 the
+// minima, 15-18 the maxima; thread 0 assembles mlb_ppo_stats.
+__global__ void __launch_bounds__(640)
 ppo_loss_final_kernel(const LossPartial* __restrict__ part, int nparts, double rows, int A,
                       float vcoef, mlb_ppo_stats* __restrict__ out) {
-    __shared__ double smd[32];
-    __shared__ float smf[32];
-    double obj = 0, vl = 0, ent = 0;
-    for (int b = threadIdx.x; b < nparts; b += blockDim.x) { obj += part[b].obj; vl += part[b].vl; ent += part[b].ent; }
-    obj = block_sum_d(obj, smd);
-    vl = block_sum_d(vl, smd);
-    ent = block_sum_d(ent, smd);
+    __shared__ double sd[11];
+    __shared__ float sf[8];
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q < 11) {
+        double a = 0.0;
+        for (int b = lane; b < nparts; b += 32) {
+            const LossPartial& P = part[b];
+            a += q == 0 ? P.obj : q == 1 ? P.vl : q == 2 ? P.ent : q < 7 ? P.s[q - 3] : P.ss[q - 7];
+        }
+        a = warp_sum(a);
+        if (lane == 0) sd[q] = a;
+    } else if (q < 15) {
+        float m = INFINITY;
+        for (int b = lane; b < nparts; b += 32) m = fminf(m, part[b].mn[q - 11]);
+        m = warp_min_f(m);
+        if (lane == 0) sf[q - 11] = m;
+    } else if (q < 19) {
+        float m = -INFINITY;
+        for (int b = lane; b < nparts; b += 32) m = fmaxf(m, part[b].mx[q - 15]);
+        m = warp_max_f(m);
+        if (lane == 0) sf[4 + q - 15] = m;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        const double obj = sd[0], vl = sd[1], ent = sd[2];
         const float loss = (float)(-obj + (double)vcoef * vl - ent);
         out->loss = loss; out->action_obj = (float)obj; out->value_loss = (float)((double)vcoef * vl);
         out->entropy = (float)ent;
         mlb_metric* m = &out->metrics[0];          // 'Loss': a scalar record (ml/ppo.py:352)
         m->mean = loss; m->m2 = 0.f; m->min = loss; m->max = loss; m->count = 1;
     }
-    for (int k = 0; k < 4; ++k) {
-        double s = 0, ss = 0;
-        float mn = INFINITY, mx = -INFINITY;
-        for (int b = threadIdx.x; b < nparts; b += blockDim.x) {
-            s += part[b].s[k]; ss += part[b].ss[k];
-            mn = fminf(mn, part[b].mn[k]); mx = fmaxf(mx, part[b].mx[k]);
-        }
-        s = block_sum_d(s, smd);
-        ss = block_sum_d(ss, smd);
-        mn = block_min_f(mn, smf);
-        mx = block_max_f(mx, smf);
-        if (threadIdx.x == 0) {
-            const double cnt = (k == 0 || k == 3) ? rows * A : rows;
-            const double mean = s / cnt;
-            double m2 = ss - s * mean;
-            if (m2 < 0) m2 = 0;
-            mlb_metric* m = &out->metrics[k + 1];
-            m->mean = (float)mean; m->m2 = (float)m2; m->min = mn; m->max = mx; m->count = (int32_t)cnt;
-        }
+    if (threadIdx.x < 4) {
+        const int k = threadIdx.x;
+        const double s = sd[3 + k], ss = sd[7 + k];
+        const double cnt = (k == 0 || k == 3) ? rows * A : rows;
+        const double mean = s / cnt;
+        double m2 = ss - s * mean;
+        if (m2 < 0) m2 = 0;
+        mlb_metric* m = &out->metrics[k + 1];
+        m->mean = (float)mean; m->m2 = (float)m2; m->min = sf[k]; m->max = sf[4 + k]; m->count = (int32_t)cnt;
     }
 }
 
@@ -378,7 +502,7 @@ MLB_API int mlb_sample_discrete_f32(void* stream, const float* head, int ld,
 }
 
 MLB_API size_t mlb_ppo_loss_workspace(long long rows) {
-    return (size_t)mlb_cdiv(rows, ROWS_PER_BLOCK) * sizeof(LossPartial);
+    return (size_t)mlb_cdiv(rows, LOSS_RB_MIN) * sizeof(LossPartial);
 }
 
 MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int32_t* actions,
@@ -392,7 +516,8 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
                              mlb_ppo_stats* stats, void* ws, size_t ws_bytes,
                              const float* critic_bins_host, int num_critic_bins) {
     MLB_REQUIRE(head && actions && old_log_probs && advantages && returns && d_head && stats);
-    MLB_REQUIRE(rows > 0 && M > 0 && ld > 0 && obj_scale_host && ent_scale_host);
+    MLB_REQUIRE(rows > 0 && M > 0 && ld > 0 && ld % 4 == 0 && obj_scale_host && ent_scale_host);
+    MLB_REQUIRE(mlb_aligned16(head) && (reinterpret_cast<uintptr_t>(d_head) & 15) == 0);
     MLB_REQUIRE(!(flags & MLB_PPO_CLIP_VALUE_LOSS) || old_values);
     Layout L;
     CriticBins cb;
@@ -400,18 +525,20 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     MLB_REQUIRE(cb.V == 1 || !(vn_params || (flags & (MLB_PPO_CLIP_VALUE_LOSS | MLB_PPO_HUBER_VALUE_LOSS))));
     const int vcol = make_layout(L, buckets_host, num_components, obj_scale_host, ent_scale_host, ld, cb.V);
     if (vcol < 0) return vcol;
-    const unsigned g = mlb_cdiv(rows, ROWS_PER_BLOCK);
+    const int RB = (num_components + 1) * 64 <= 1024 ? 64 : LOSS_RB_MIN;
+    const unsigned g = mlb_cdiv(rows, RB);
     if (!ws || ws_bytes < (size_t)g * sizeof(LossPartial)) return MLB_EWS;
-    const size_t smem = (size_t)ROWS_PER_BLOCK * (ld + 1) * sizeof(float);
+    const int ncols = vcol + cb.V;
+    const size_t smem = ((size_t)RB * (ncols | 1) + ncols) * sizeof(float);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(ppo_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t s = mlb_stream(stream);
     LossPartial* part = reinterpret_cast<LossPartial*>(ws);
-    ppo_loss_kernel<<<g, ROWS_PER_BLOCK, smem, s>>>(head, ld, actions, old_log_probs, advantages,
+    ppo_loss_kernel<<<g, (num_components + 1) * RB, smem, s>>>(head, ld, actions, old_log_probs, advantages,
         returns, old_values, mb_weights, adv_mean_rstd, vn_params, L, rows, M, clip_coef,
-        value_loss_coef, flags, vcol, d_head, d_bias, part, cb);
+        value_loss_coef, flags, vcol, d_head, d_bias, part, cb, RB, 1.f / (float)rows);
     MLB_CHECK_LAUNCH();
-    ppo_loss_final_kernel<<<1, 256, 0, s>>>(part, (int)g, (double)rows, num_components,
+    ppo_loss_final_kernel<<<1, 640, 0, s>>>(part, (int)g, (double)rows, num_components,
                                             value_loss_coef, stats);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
