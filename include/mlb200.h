@@ -127,6 +127,12 @@ int mlb_ema_invert_f32(void* stream, const float* state, int dim, const float* x
 /* er = done ? 0 : er.                                                                       */
 int mlb_env_returns_f32(void* stream, const float* rewards, const uint8_t* dones,
                         float* env_returns, float* trace, long long N, float gamma);
+/* "Post Step Rollout Store" (ml/rollouts.py:946-978) in one launch: copies the simulator's   */
+/* rewards (f32 [N]) and dones (1 byte [N]) into the store slabs and advances the discounted   */
+/* env-return trace exactly like mlb_env_returns_f32.                                          */
+int mlb_post_step_store_f32(void* stream, const float* rewards, const uint8_t* dones,
+                            float* reward_slab, uint8_t* done_slab, float* env_returns,
+                            float* trace, long long N, float gamma);
 
 /* ------------------------------------------------------------------------------------ */
 /* PRNG: JAX threefry2x32 (bit-exact).  keys are uint32[2].  partitionable selects the     */
@@ -153,6 +159,17 @@ int mlb_mb_gather(void* stream, const void* store, const int32_t* idx, void* out
 /* rnn_start_states [C, B, row] -> [M, row] (ml/rollouts.py:800-804 + :321-323) */
 int mlb_mb_gather_rnn(void* stream, const void* store, const int32_t* idx, void* out,
                       int C, long long B, long long M, long long row_bytes);
+/* All leaves of one minibatch in a single launch.  Per leaf: store [C, T', B, row], out            */
+/* [T', M, row] (may be NULL when out_bf16 is set), out_bf16 (may be NULL): the same rows converted */
+/* f32 -> bf16 (row_bytes % 16 == 0) -- the tensor-core forward's A operand.  Up to 8 leaves.       */
+typedef struct mlb_gather_leaf {
+    const void* store;
+    void* out;
+    void* out_bf16;
+    long long row_bytes;
+} mlb_gather_leaf;
+int mlb_mb_gather_multi(void* stream, const mlb_gather_leaf* leaves_host, int num_leaves,
+                        const int32_t* idx, int C, int Tp, long long B, long long M);
 
 /* ------------------------------------------------------------------------------------ */
 /* K6/K9 (fp32 path): Dense layers and their transposes.                                  */
@@ -342,6 +359,8 @@ int mlb_colsum_f32(void* stream, const float* x, long long rows, int ld, int nco
 
 /* ------------------------------------------------------------------------------------ */
 /* Synthetic vector environment (stand-in for sim_fns['step'], ml/rollouts.py:905-936).     */
+/* tcount: device int32[2] = {step counter, block-arrival scratch}; the step kernel advances  */
+/* the counter itself (last block to finish), so a step is ONE launch.                        */
 /* ------------------------------------------------------------------------------------ */
 int mlb_synth_env_init(void* stream, float* obs, long long N, int D, uint32_t seed,
                        int32_t* tcount);

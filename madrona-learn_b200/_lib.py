@@ -52,6 +52,7 @@ SIGNATURES = {
     'mlb_ema_normalize_f32': (c_int, [P, P, c_int, P, P, c_ll]),
     'mlb_ema_invert_f32': (c_int, [P, P, c_int, P, P, c_ll]),
     'mlb_env_returns_f32': (c_int, [P, P, P, P, P, c_ll, c_float]),
+    'mlb_post_step_store_f32': (c_int, [P, P, P, P, P, P, P, c_ll, c_float]),
     'mlb_threefry_split': (c_int, [P, P, P, c_int, c_int]),
     'mlb_threefry_bits': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_ppo_permutations_workspace': (c_size_t, [c_int, c_ll]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     'mlb_rnn_reset_f32': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
+    'mlb_mb_gather_multi': (c_int, [P, P, c_int, P, c_int, c_int, c_ll, c_ll]),
     'mlb_policy_rollout_tc': (c_int, [P, P, P, P, c_ll, P, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P]),
     'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),
     'mlb_ppo_loss_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, c_ll, c_ll,
@@ -102,6 +104,11 @@ class Bf16Copy(ctypes.Structure):
     """mlb_bf16_copy."""
     _fields_ = [('dst_t', c_void_p), ('dst', c_void_p), ('rows', ctypes.c_int32), ('cols', ctypes.c_int32),
                 ('ld_t', ctypes.c_int32), ('ld_d', ctypes.c_int32)]
+
+
+class GatherLeaf(ctypes.Structure):
+    """mlb_gather_leaf."""
+    _fields_ = [('store', c_void_p), ('out', c_void_p), ('out_bf16', c_void_p), ('row_bytes', ctypes.c_longlong)]
 
 
 class MlpTcDesc(ctypes.Structure):

@@ -22,36 +22,49 @@ __host__ __device__ __forceinline__ float env_noise(uint32_t bits) {
 #endif
 }
 
+// Step-counter tick folded into the step kernel: every block has read tcount[0] before it
+// arrives here, so the LAST block to arrive (tcount[1] = arrival counter) advances the clock.
+__device__ __forceinline__ void env_tick_last_block(int32_t* tcount, int t) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&tcount[1], 1) == (int)gridDim.x - 1) {
+            tcount[1] = 0;
+            tcount[0] = t + 1;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 synth_env_step_kernel(const float* obs_in, float* obs_out,   // may alias (in-place step)
                       const int32_t* __restrict__ actions, int A, float* __restrict__ rewards,
-                      uint8_t* __restrict__ dones, int32_t* __restrict__ tcount, long long N,
+                      uint8_t* __restrict__ dones, int32_t* tcount, long long N,
                       int D, uint32_t seed, float p_done) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = *tcount;
-    if (e >= N * D) return;
-    const long long n = e / D;
-    const int d = (int)(e - n * D);
-    bool done;
-    if (p_done < 0.f) done = ((t + n) % 61) == 0;
-    else {
-        uint32_t x0 = (uint32_t)n, x1 = 0x80000000u | (uint32_t)t;
-        threefry2x32(seed, 0x9E3779B9u, x0, x1);
-        done = (float)(x0 >> 8) * 5.9604644775390625e-08f < p_done;
+    const int t = *tcount;     // L1 is invalidated at launch boundaries; only the last block writes it
+    if (e < N * D) {
+        const long long n = e / D;
+        const int d = (int)(e - n * D);
+        bool done;
+        if (p_done < 0.f) done = ((t + n) % 61) == 0;
+        else {
+            uint32_t x0 = (uint32_t)n, x1 = 0x80000000u | (uint32_t)t;
+            threefry2x32(seed, 0x9E3779B9u, x0, x1);
+            done = (float)(x0 >> 8) * 5.9604644775390625e-08f < p_done;
+        }
+        uint32_t x0 = (uint32_t)e, x1 = (uint32_t)t;
+        threefry2x32(seed, (uint32_t)(e >> 32), x0, x1);
+        const float xi = env_noise(x0);
+        const float o = obs_in[e];
+        if (d == 0) {
+            const float a0 = (float)actions[n * A];
+            rewards[n] = __fmul_rn(__fmul_rn(o, __fadd_rn(a0, -1.5f)), 0.1f);
+            dones[n] = done ? 1 : 0;
+        }
+        obs_out[e] = done ? xi : __fadd_rn(__fmul_rn(0.9f, o), __fmul_rn(0.1f, xi));
     }
-    uint32_t x0 = (uint32_t)e, x1 = (uint32_t)t;
-    threefry2x32(seed, (uint32_t)(e >> 32), x0, x1);
-    const float xi = env_noise(x0);
-    const float o = obs_in[e];
-    if (d == 0) {
-        const float a0 = (float)actions[n * A];
-        rewards[n] = __fmul_rn(__fmul_rn(o, __fadd_rn(a0, -1.5f)), 0.1f);
-        dones[n] = done ? 1 : 0;
-    }
-    obs_out[e] = done ? xi : __fadd_rn(__fmul_rn(0.9f, o), __fmul_rn(0.1f, xi));
+    env_tick_last_block(tcount, t);
 }
-
-__global__ void synth_env_tick_kernel(int32_t* tcount) { if (threadIdx.x == 0 && blockIdx.x == 0) *tcount += 1; }
 
 __global__ void __launch_bounds__(256)
 synth_env_init_kernel(float* __restrict__ obs, long long total, uint32_t seed) {
@@ -68,7 +81,7 @@ MLB_API int mlb_synth_env_init(void* stream, float* obs, long long N, int D, uin
                                int32_t* tcount) {
     MLB_REQUIRE(obs && tcount && N > 0 && D > 0);
     cudaStream_t s = mlb_stream(stream);
-    cudaError_t e = cudaMemsetAsync(tcount, 0, sizeof(int32_t), s);
+    cudaError_t e = cudaMemsetAsync(tcount, 0, 2 * sizeof(int32_t), s);
     if (e != cudaSuccess) return (int)e;
     synth_env_init_kernel<<<mlb_cdiv(N * D, 256), 256, 0, s>>>(obs, N * D, seed);
     MLB_CHECK_LAUNCH();
@@ -82,8 +95,6 @@ MLB_API int mlb_synth_env_step(void* stream, const float* obs_in, float* obs_out
     cudaStream_t s = mlb_stream(stream);
     synth_env_step_kernel<<<mlb_cdiv(N * D, 256), 256, 0, s>>>(obs_in, obs_out, actions, A, rewards,
                                                                dones, tcount, N, D, seed, p_done);
-    MLB_CHECK_LAUNCH();
-    synth_env_tick_kernel<<<1, 32, 0, s>>>(tcount);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }

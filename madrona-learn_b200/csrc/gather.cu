@@ -7,6 +7,8 @@
 // so the relayout copy never exists.  Rows are copied as 16-byte vectors when the row size
 // and pointers allow it; a warp covers consecutive bytes of consecutive rows of one time
 // step, so global stores are fully coalesced and loads are coalesced within each row.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -53,7 +55,85 @@ int gather_dispatch(cudaStream_t st, const void* store, const int32_t* idx, void
     return launch_gather<uint8_t>(st, store, idx, out, Tp, B, M, row_bytes);
 }
 
+// All leaves of a minibatch in ONE launch.  Per leaf the vector width (16/8/4/1 bytes) is chosen on
+// the host; the observation leaf can additionally be emitted as bf16 (the tensor-core forward's
+// A operand), which replaces a separate cast pass over the minibatch.
+constexpr int MAX_LEAVES = 8;
+struct LeafDev {
+    const uint8_t* store;
+    uint8_t* out;
+    __nv_bfloat16* out_bf16;
+    int row_vecs, vec_bytes;
+};
+struct LeafPack { LeafDev l[MAX_LEAVES]; int n; };
+
+__global__ void __launch_bounds__(256)
+gather_multi_kernel(const __grid_constant__ LeafPack P, const int32_t* __restrict__ idx, int Tp, int B, int M) {
+    const int s = blockIdx.y;
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int li = 0; li < P.n; ++li) {
+        const LeafDev& L = P.l[li];
+        const int rv = L.row_vecs, total = M * rv;
+        for (int e = t0; e < total; e += stride) {
+            const int m = e / rv, k = e - m * rv;
+            const int j = idx[m];
+            const int c = j / B, b = j - c * B;
+            const long long src = (((long long)c * Tp + s) * B + b) * rv + k;
+            const long long dst = ((long long)s * M + m) * rv + k;
+            switch (L.vec_bytes) {
+                case 16: {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(L.store) + src);
+                    if (L.out) reinterpret_cast<uint4*>(L.out)[dst] = v;
+                    if (L.out_bf16) {
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(v.x), __uint_as_float(v.y));
+                        const __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(v.z), __uint_as_float(v.w));
+                        reinterpret_cast<uint2*>(L.out_bf16)[dst] =
+                            make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                    }
+                    break;
+                }
+                case 8: reinterpret_cast<uint2*>(L.out)[dst] = __ldg(reinterpret_cast<const uint2*>(L.store) + src); break;
+                case 4: reinterpret_cast<uint32_t*>(L.out)[dst] = __ldg(reinterpret_cast<const uint32_t*>(L.store) + src); break;
+                default: L.out[dst] = __ldg(L.store + src); break;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+MLB_API int mlb_mb_gather_multi(void* stream, const mlb_gather_leaf* leaves_host, int num_leaves,
+                                const int32_t* idx, int C, int Tp, long long B, long long M) {
+    if (M == 0 || num_leaves == 0) return MLB_OK;
+    MLB_REQUIRE(leaves_host && idx && num_leaves > 0 && num_leaves <= MAX_LEAVES && C > 0 && Tp > 0 &&
+                Tp <= 65535 && B > 0 && M > 0 && B < (1ll << 31) && (long long)C * B < (1ll << 31));
+    LeafPack P;
+    P.n = num_leaves;
+    long long max_total = 0;
+    for (int i = 0; i < num_leaves; ++i) {
+        const mlb_gather_leaf& h = leaves_host[i];
+        MLB_REQUIRE(h.store && (h.out || h.out_bf16) && h.row_bytes > 0);
+        const uintptr_t a = reinterpret_cast<uintptr_t>(h.store) | reinterpret_cast<uintptr_t>(h.out);
+        int vb = 1;
+        if (h.row_bytes % 16 == 0 && (a & 15) == 0) vb = 16;
+        else if (h.row_bytes % 8 == 0 && (a & 7) == 0) vb = 8;
+        else if (h.row_bytes % 4 == 0 && (a & 3) == 0) vb = 4;
+        MLB_REQUIRE(!h.out_bf16 || (vb == 16 && (reinterpret_cast<uintptr_t>(h.out_bf16) & 7) == 0));
+        MLB_REQUIRE(h.out || vb == 16);
+        const long long rv = h.row_bytes / vb;
+        MLB_REQUIRE(M * rv < (1ll << 31));
+        P.l[i] = LeafDev{static_cast<const uint8_t*>(h.store), static_cast<uint8_t*>(h.out),
+                         static_cast<__nv_bfloat16*>(h.out_bf16), (int)rv, vb};
+        if (M * rv > max_total) max_total = M * rv;
+    }
+    long long gx = (max_total + 255) / 256;
+    const long long cap = (long long)MLB_NUM_SMS * 8 / (Tp < 8 ? Tp : 8) + 1;
+    if (gx > cap) gx = cap;
+    gather_multi_kernel<<<dim3((unsigned)gx, (unsigned)Tp), 256, 0, mlb_stream(stream)>>>(P, idx, Tp, (int)B, (int)M);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
 
 MLB_API int mlb_mb_gather(void* stream, const void* store, const int32_t* idx, void* out, int C,
                           int Tp, long long B, long long M, long long row_bytes) {

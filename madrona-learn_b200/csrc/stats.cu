@@ -253,6 +253,21 @@ env_returns_kernel(const float* __restrict__ r, const uint8_t* __restrict__ d,
     er[i] = d[i] ? 0.f : v;
 }
 
+__global__ void __launch_bounds__(256)
+post_step_kernel(const float* __restrict__ r, const uint8_t* __restrict__ d, float* __restrict__ rs,
+                 uint8_t* __restrict__ ds, float* __restrict__ er, float* __restrict__ trace,
+                 long long N, float gamma) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float ri = r[i];
+    const uint8_t di = d[i];
+    rs[i] = ri;
+    ds[i] = di;
+    const float v = __fadd_rn(ri, __fmul_rn(gamma, er[i]));
+    if (trace) trace[i] = v;
+    er[i] = di ? 0.f : v;
+}
+
 unsigned ew_grid(long long n, int per_thread) {
     long long b = (n + 256ll * per_thread - 1) / (256ll * per_thread);
     if (b < 1) b = 1;
@@ -364,6 +379,17 @@ MLB_API int mlb_ema_invert_f32(void* stream, const float* state, int dim, const 
     MLB_REQUIRE(state && x && out && dim > 0 && rows >= 0);
     if (rows == 0) return MLB_OK;
     ema_apply_kernel<true><<<ew_grid(rows * dim, 4), 256, 0, mlb_stream(stream)>>>(state, dim, x, out, rows * dim);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+MLB_API int mlb_post_step_store_f32(void* stream, const float* rewards, const uint8_t* dones,
+                                    float* reward_slab, uint8_t* done_slab, float* env_returns,
+                                    float* trace, long long N, float gamma) {
+    MLB_REQUIRE(rewards && dones && reward_slab && done_slab && env_returns && N >= 0);
+    if (N == 0) return MLB_OK;
+    post_step_kernel<<<mlb_cdiv(N, 256), 256, 0, mlb_stream(stream)>>>(rewards, dones, reward_slab, done_slab,
+                                                                       env_returns, trace, N, gamma);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }

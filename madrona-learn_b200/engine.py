@@ -366,10 +366,11 @@ class PolicyProgram:
         gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
         return w['head']
 
-    def _forward_tc(self, obs, rows, w, ys, xhs, rstds):
+    def _forward_tc(self, obs, rows, w, ys, xhs, rstds, x_ready=False):
         """bf16 tensor-core forward: cast obs -> L x fused [tcgen05 GEMM + LayerNorm + ReLU epilogue
         out of TMEM] -> head GEMM (fp32 out + bias).  Training also stashes xhat (bf16) and rstd."""
-        call('mlb_cast_f32_bf16', ptr(obs), ptr(w['x']), c_ll(rows * self.obs_dim))
+        if not x_ready:                    # x_ready: the minibatch gather already wrote the bf16 copy into w['x']
+            call('mlb_cast_f32_bf16', ptr(obs), ptr(w['x']), c_ll(rows * self.obs_dim))
         x, d = w['x'], self.obs_dim
         for i in range(self.L):
             _, s, b = self.layer_views(self.params, i)
@@ -419,11 +420,11 @@ class PolicyProgram:
     # ---------------------------------------------------------------------------------
     # training forward + backward (ActorCritic.update ml/actor_critic.py:98-128 + autodiff)
     # ---------------------------------------------------------------------------------
-    def forward_train(self, obs, rows, seq=None):
+    def forward_train(self, obs, rows, seq=None, x_ready=False):
         """seq (recurrent encoders): dict(Tp, M, ends u8 [T', M], c0, h0 [M, RH])."""
         w = self.train_ws(rows)
         if self.tc:
-            return self._forward_tc(obs, rows, w, w['y'], w['xh'], w['rstd'])
+            return self._forward_tc(obs, rows, w, w['y'], w['xh'], w['rstd'], x_ready)
         x, d = obs, self.obs_dim
         for i in range(self.L):
             k, s, b = self.layer_views(self.params, i)

@@ -19,7 +19,7 @@ class SyntheticVectorEnv:
         self.obs = torch.empty(self.N, self.D, dtype=torch.float32, device=self.device)
         self.rewards = torch.empty(self.N, 1, dtype=torch.float32, device=self.device)
         self.dones = torch.empty(self.N, 1, dtype=torch.uint8, device=self.device)
-        self.tcount = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.tcount = torch.zeros(2, dtype=torch.int32, device=self.device)   # [step counter, block arrivals]
 
     def init(self):
         call('mlb_synth_env_init', ptr(self.obs), c_ll(self.N), c_int(self.D),

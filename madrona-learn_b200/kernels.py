@@ -7,6 +7,7 @@ import ctypes
 
 import torch
 
+from . import _lib
 from ._lib import (Metric, c_float, c_int, c_ll, c_size_t, call, lib, ptr)
 
 _METRIC_BYTES = ctypes.sizeof(Metric)   # 20
@@ -216,6 +217,21 @@ def mb_gather(store, idx, C, Tp, B, out=None):
     call('mlb_mb_gather', ptr(store), ptr(idx), ptr(out), c_int(C), c_int(Tp), c_ll(B), c_ll(M),
          c_ll(row_bytes))
     return out
+
+
+def mb_gather_multi(leaves, idx, C, Tp, B):
+    """leaves: list of (store [C, T', B, *leaf], out [T', M, *leaf] or None, out_bf16 or None)."""
+    arr = (_lib.GatherLeaf * len(leaves))()
+    for i, (store, out, out_bf16) in enumerate(leaves):
+        row_elems = 1
+        for d in store.shape[3:]:
+            row_elems *= d
+        arr[i].store = store.data_ptr()
+        arr[i].out = out.data_ptr() if out is not None else None
+        arr[i].out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+        arr[i].row_bytes = row_elems * store.element_size()
+    call('mlb_mb_gather_multi', arr, c_int(len(leaves)), ptr(idx), c_int(C), c_int(Tp), c_ll(B),
+         c_ll(idx.numel()))
 
 
 def mb_gather_rnn(store, idx, C, B, out=None):

@@ -194,14 +194,17 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
             mbi = e * nmb + k
             with profile('Gather Minibatch'):
                 idx = ws.perm[e, k * M:(k + 1) * M]
-                for name in set(keys):
+                leaves = []
+                for name in dict.fromkeys(keys):
                     src = st[name][:, :, 0]
-                    K.mb_gather(src.view(torch.uint8) if src.dtype == torch.bool else src, idx, C, Tp, B, mb[name])
+                    leaves.append((src.view(torch.uint8) if src.dtype == torch.bool else src, mb[name],
+                                   tw['x'] if (name == 'obs' and prog.tc) else None))
+                K.mb_gather_multi(leaves, idx, C, Tp, B)
                 if seq is not None:
                     K.mb_gather_rnn(st['rnn_start_c'][:, 0], idx, C, B, mb['rnn_start_c'])
                     K.mb_gather_rnn(st['rnn_start_h'][:, 0], idx, C, B, mb['rnn_start_h'])
             with profile('AC Forward'):
-                head = prog.forward_train(mb['obs'].view(rows, prog.obs_dim), rows, seq)
+                head = prog.forward_train(mb['obs'].view(rows, prog.obs_dim), rows, seq, x_ready=prog.tc)
             with profile('Optimize'):
                 prog.zero_grads()
                 call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(mb['actions']),

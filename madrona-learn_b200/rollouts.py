@@ -271,10 +271,8 @@ class RolloutManager:                   # ml/rollouts.py:373-826
                     rewards = rewards.float()
             with profile('Post Step Rollout Store'):
                 d_slab, r_slab = st['dones'][c, s, 0], st['rewards'][c, s, 0]
-                call('mlb_copy_bytes', ptr(dones), ptr(d_slab), c_size_t(N))
-                call('mlb_copy_bytes', ptr(rewards), ptr(r_slab), c_size_t(N * 4))
-                call('mlb_env_returns_f32', ptr(r_slab), ptr(d_slab), ptr(rs.env_returns),
-                     ptr(self.env_returns_trace[c * Tp + s]), c_ll(N), c_float(gamma))
+                call('mlb_post_step_store_f32', ptr(rewards), ptr(dones), ptr(r_slab), ptr(d_slab),
+                     ptr(rs.env_returns), ptr(self.env_returns_trace[c * Tp + s]), c_ll(N), c_float(gamma))
                 if self._lstm is not None:                # rnn_reset_fn(rnn_states, dones)  (:942)
                     self._lstm.reset(rs.rnn_states, d_slab.view(torch.uint8), N)
         if rs.prng_key is not key_home:                   # odd number of fused steps: move the key home
