@@ -10,17 +10,18 @@
 //     bf16, into shared memory in the canonical K-major SWIZZLE_128B operand layout;
 //   * warp 0 streams every layer's W^T through a 2-stage TMA ring (weights are L2-resident);
 //   * warp 1 issues tcgen05.mma with the A operand taken from the activation panels;
-//   * the epilogue warps (8 = 4 TMEM lane quadrants x 2 column halves) run LayerNorm + ReLU out
+//   * the epilogue warps (16 = 4 TMEM lane quadrants x 4 column groups) run LayerNorm + ReLU out
 //     of TMEM and write the next layer's A operand straight back into the same panels;
 //   * the head GEMM lands in TMEM columns [256, 256+NH), is staged as fp32 in shared memory and
-//     sampled by all 256 epilogue threads ((row, component) work items, threefry Gumbel-max).
+//     sampled by all 512 epilogue threads ((row, component) work items, threefry Gumbel-max).
 #include "tc_common.cuh"
 
 namespace {
 
 using namespace tc;
 
-constexpr int PR_THREADS = 320;
+constexpr int PR_THREADS = 576;          // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue (4 lane quadrants x 4 column groups)
+constexpr int PR_EPI = 512;
 constexpr int PR_STAGES = 2;
 constexpr int MAXL = MLB_MLP_TC_MAX_LAYERS;
 constexpr int MAXC = MLB_MAX_ACTION_COMPONENTS;
@@ -60,8 +61,8 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
     uint8_t* ring = act + act_panels * 16384;                         // PR_STAGES * (H * 128 B)
     const int stage_bytes = H * 128;
     float* head_sm = reinterpret_cast<float*>(ring + PR_STAGES * stage_bytes);   // [128][NH + 1]
-    float* fsm = head_sm + 128 * (NH + 1);                            // [2][2H] scale|bias, [512] partials
-    uint64_t* bars = reinterpret_cast<uint64_t*>(fsm + 4 * H + 512);
+    float* fsm = head_sm + 128 * (NH + 1);                            // [2][2H] scale|bias, [4][128][2] partials
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fsm + 4 * H + 1024);
     uint64_t* full_bar = bars;                   // [PR_STAGES]
     uint64_t* empty_bar = bars + PR_STAGES;      // [PR_STAGES]
     uint64_t* acc_bar = bars + 2 * PR_STAGES;    // accumulator of the current layer complete
@@ -78,7 +79,7 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.wh)) : "memory");
         for (int s = 0; s < PR_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(acc_bar, 1);
-        mbar_init(a_bar, 256);
+        mbar_init(a_bar, PR_EPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // PRNG key chain (ml/rollouts.py:878-880): (prng_key, step_key) = split(prng_key);
         // policy_key = split(step_key, 1)[0].  Every CTA derives it; CTA 0 publishes the new key.
@@ -146,15 +147,15 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
         }
     } else {
         // ================= epilogue warps =================
-        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int quad = warp & 3, grp = (warp - 2) >> 2;
         const int rt = quad * 32 + lane;
-        const int et = threadIdx.x - 64;                 // 0..255
+        const int et = threadIdx.x - 64;                 // 0..511
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         float* partials = fsm + 4 * H;
         // ---- observations: fp32 rows -> store slab (fp32) + bf16 A panels (SWIZZLE_128B, K-major) ----
         {
             const int chunks = kb_of_layer0 * 8;         // 16-byte bf16 chunks per row (zero padded)
-            for (int item = et; item < 128 * chunks; item += 256) {
+            for (int item = et; item < 128 * chunks; item += PR_EPI) {
                 const int r = item / chunks, j = item - r * chunks;
                 const long long row = m0 + r;
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
@@ -178,25 +179,28 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
         for (int l = 0; l < L; ++l) {
             float* s = fsm + (l & 1) * 2 * H;
             float* b = s + H;
-            for (int i = et; i < H; i += 256) { s[i] = a.scale[l][i]; b[i] = a.bias[l][i]; }
+            for (int i = et; i < H; i += PR_EPI) { s[i] = a.scale[l][i]; b[i] = a.bias[l][i]; }
             mbar_wait(acc_bar, (uint32_t)(l & 1));
             tcgen05_fence_after();
             float sum = 0.f, sq = 0.f;
-            for (int ch = half * nchunks / 2; ch < (half + 1) * nchunks / 2; ++ch) {
+            for (int ch = grp; ch < nchunks; ch += 4) {
                 uint32_t r[32];
                 tmem_ld32(taddr + ch * 32, r);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { const float z = __uint_as_float(r[j]); sum += z; sq = fmaf(z, z, sq); }
             }
-            partials[(half * 128 + rt) * 2] = sum;
-            partials[(half * 128 + rt) * 2 + 1] = sq;
-            named_bar_sync(3, 256);
-            sum += partials[((half ^ 1) * 128 + rt) * 2];
-            sq += partials[((half ^ 1) * 128 + rt) * 2 + 1];
+            {
+                float2* pp = reinterpret_cast<float2*>(partials);
+                pp[grp * 128 + rt] = make_float2(sum, sq);
+                named_bar_sync(3, PR_EPI);             // also orders the s/b loads above
+                const float2 p0 = pp[rt], p1 = pp[128 + rt], p2 = pp[256 + rt], p3 = pp[384 + rt];
+                sum = (p0.x + p1.x) + (p2.x + p3.x);
+                sq = (p0.y + p1.y) + (p2.y + p3.y);
+            }
             const float invH = 1.f / (float)H;
             const float mean = sum * invH;
             const float rstd = rsqrtf(fmaxf(0.f, sq * invH - mean * mean) + LN_EPS);
-            for (int ch = half * nchunks / 2; ch < (half + 1) * nchunks / 2; ++ch) {
+            for (int ch = grp; ch < nchunks; ch += 4) {
                 const int c = ch * 32;
                 uint32_t r[32];
                 tmem_ld32(taddr + c, r);
@@ -223,7 +227,7 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
         tcgen05_fence_after();
         {
             const int hch = NH / 32;                      // NH is a multiple of 64
-            for (int ch = half * hch / 2; ch < (half + 1) * hch / 2; ++ch) {
+            for (int ch = grp; ch < hch; ch += 4) {
                 uint32_t r[32];
                 tmem_ld32(taddr + 256 + ch * 32, r);
 #pragma unroll
@@ -231,16 +235,16 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
                     head_sm[rt * (NH + 1) + ch * 32 + j] = __uint_as_float(r[j]) + a.head_bias[ch * 32 + j];
             }
         }
-        named_bar_sync(3, 256);
+        named_bar_sync(3, PR_EPI);
         if (head_out) {
-            for (int e = et; e < 128 * NH; e += 256) {
+            for (int e = et; e < 128 * NH; e += PR_EPI) {
                 const int r = e / NH, c = e - r * NH;
                 if (m0 + r < rows) head_out[(m0 + r) * NH + c] = head_sm[r * (NH + 1) + c];
             }
         }
-        // ---- sampling: (row, component) work items over the 256 epilogue threads ----
+        // ---- sampling: (row, component) work items over the 512 epilogue threads ----
         const uint32_t pk0 = keys_sm[0], pk1 = keys_sm[1];
-        for (int item = et; item < 128 * a.A; item += 256) {
+        for (int item = et; item < 128 * a.A; item += PR_EPI) {
             const int r = item / a.A, i = item - r * a.A;
             const long long row = m0 + r;
             if (row >= rows) continue;
@@ -327,7 +331,7 @@ MLB_API int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* d, const 
     a.head_bias = d->head_bias;
     const int act_panels = (a.H > a.D ? a.H : a.D + 63) / 64;
     const size_t smem = (size_t)act_panels * 16384 + (size_t)PR_STAGES * a.H * 128 +
-                        (size_t)128 * (a.NH + 1) * 4 + (size_t)(4 * a.H + 512) * 4 + 16 * 8 + 64 + 1024;
+                        (size_t)128 * (a.NH + 1) * 4 + (size_t)(4 * a.H + 1024) * 4 + 16 * 8 + 64 + 1024;
     if (smem > 227 * 1024) return MLB_EINVAL;
     cudaError_t e = cudaFuncSetAttribute(policy_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
