@@ -70,8 +70,10 @@ __device__ __forceinline__ void stage_in(float* tile, int ts, const float* __res
     const int nrow = (int)min((long long)rb, rows - row0);
     const int vpr = ld >> 2;                                   // float4 per row
     const float4* src = reinterpret_cast<const float4*>(g + row0 * ld);
+    const bool p2 = (vpr & (vpr - 1)) == 0;
+    const int sh = 31 - __clz(vpr);
     for (int e = threadIdx.x; e < nrow * vpr; e += blockDim.x) {
-        const int r = e / vpr, c = (e - r * vpr) << 2;
+        const int r = p2 ? (e >> sh) : e / vpr, c = (e - r * vpr) << 2;
         if (c < ncols) {
             const float4 v = __ldg(src + e);
             float* t = tile + r * ts + c;
@@ -89,8 +91,10 @@ __device__ __forceinline__ void stage_out(const float* tile, int ts, float* __re
     const int nrow = (int)min((long long)rb, rows - row0);
     const int vpr = ld >> 2;
     float4* dst = reinterpret_cast<float4*>(g + row0 * ld);
+    const bool p2 = (vpr & (vpr - 1)) == 0;
+    const int sh = 31 - __clz(vpr);
     for (int e = threadIdx.x; e < nrow * vpr; e += blockDim.x) {
-        const int r = e / vpr, c = (e - r * vpr) << 2;
+        const int r = p2 ? (e >> sh) : e / vpr, c = (e - r * vpr) << 2;
         const float* t = tile + r * ts + c;
         dst[e] = make_float4(c < ncols ? t[0] : 0.f, c + 1 < ncols ? t[1] : 0.f, c + 2 < ncols ? t[2] : 0.f,
                              c + 3 < ncols ? t[3] : 0.f);
@@ -101,8 +105,10 @@ __device__ __forceinline__ void stage_out(const float* tile, int ts, __nv_bfloat
     const int nrow = (int)min((long long)rb, rows - row0);
     const int vpr = ld >> 2;
     uint2* dst = reinterpret_cast<uint2*>(g + row0 * ld);
+    const bool p2 = (vpr & (vpr - 1)) == 0;
+    const int sh = 31 - __clz(vpr);
     for (int e = threadIdx.x; e < nrow * vpr; e += blockDim.x) {
-        const int r = e / vpr, c = (e - r * vpr) << 2;
+        const int r = p2 ? (e >> sh) : e / vpr, c = (e - r * vpr) << 2;
         const float* t = tile + r * ts + c;
         const __nv_bfloat162 lo = __floats2bfloat162_rn(c < ncols ? t[0] : 0.f, c + 1 < ncols ? t[1] : 0.f);
         const __nv_bfloat162 hi = __floats2bfloat162_rn(c + 2 < ncols ? t[2] : 0.f, c + 3 < ncols ? t[3] : 0.f);
@@ -223,6 +229,7 @@ __device__ __forceinline__ CompOut loss_component(float* __restrict__ l, int act
     return CompOut{obj, H};
 }
 
+template <int RB>
 __global__ void __launch_bounds__(1024)
 ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restrict__ actions,
                 const float* __restrict__ old_lp, const float* __restrict__ adv,
@@ -230,7 +237,7 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
                 const float* __restrict__ mb_w, const float* __restrict__ adv_mr,
                 const float* __restrict__ vn, Layout L, long long rows, long long M,
                 float clip, float vcoef, int flags, int vcol, void* __restrict__ dhead,
-                float* __restrict__ dbias, LossPartial* __restrict__ part, CriticBins cb, int RB, float inv_rows) {
+                float* __restrict__ dbias, LossPartial* __restrict__ part, CriticBins cb, float inv_rows) {
     extern __shared__ float tile[];
     __shared__ WarpPartial wpart[32];
     const long long row0 = (long long)blockIdx.x * RB;
@@ -408,24 +415,40 @@ ppo_loss_final_kernel(const LossPartial* __restrict__ part, int nparts, double r
     __shared__ double sd[11];
     __shared__ float sf[8];
     const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // independent loads first (the partials sit in L2: one round trip per 8 blocks, not per block)
     if (q < 11) {
         double a = 0.0;
-        for (int b = lane; b < nparts; b += 32) {
-            const LossPartial& P = part[b];
-            a += q == 0 ? P.obj : q == 1 ? P.vl : q == 2 ? P.ent : q < 7 ? P.s[q - 3] : P.ss[q - 7];
+        for (int b0 = lane; b0 < nparts; b0 += 32 * 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int b = b0 + 32 * u;
+                if (b < nparts) {
+                    const LossPartial& P = part[b];
+                    v[u] = q == 0 ? P.obj : q == 1 ? P.vl : q == 2 ? P.ent : q < 7 ? P.s[q - 3] : P.ss[q - 7];
+                } else v[u] = 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a += v[u];
         }
         a = warp_sum(a);
         if (lane == 0) sd[q] = a;
-    } else if (q < 15) {
-        float m = INFINITY;
-        for (int b = lane; b < nparts; b += 32) m = fminf(m, part[b].mn[q - 11]);
-        m = warp_min_f(m);
-        if (lane == 0) sf[q - 11] = m;
     } else if (q < 19) {
-        float m = -INFINITY;
-        for (int b = lane; b < nparts; b += 32) m = fmaxf(m, part[b].mx[q - 15]);
-        m = warp_max_f(m);
-        if (lane == 0) sf[4 + q - 15] = m;
+        const bool is_min = q < 15;
+        const int k = is_min ? q - 11 : q - 15;
+        float m = is_min ? INFINITY : -INFINITY;
+        for (int b0 = lane; b0 < nparts; b0 += 32 * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int b = b0 + 32 * u;
+                v[u] = b < nparts ? (is_min ? part[b].mn[k] : part[b].mx[k]) : (is_min ? INFINITY : -INFINITY);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) m = is_min ? fminf(m, v[u]) : fmaxf(m, v[u]);
+        }
+        m = is_min ? warp_min_f(m) : warp_max_f(m);
+        if (lane == 0) sf[is_min ? k : 4 + k] = m;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -530,13 +553,14 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     if (!ws || ws_bytes < (size_t)g * sizeof(LossPartial)) return MLB_EWS;
     const int ncols = vcol + cb.V;
     const size_t smem = ((size_t)RB * (ncols | 1) + ncols) * sizeof(float);
+    auto kern = RB == 64 ? ppo_loss_kernel<64> : ppo_loss_kernel<LOSS_RB_MIN>;
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(ppo_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t s = mlb_stream(stream);
     LossPartial* part = reinterpret_cast<LossPartial*>(ws);
-    ppo_loss_kernel<<<g, (num_components + 1) * RB, smem, s>>>(head, ld, actions, old_log_probs, advantages,
+    kern<<<g, (num_components + 1) * RB, smem, s>>>(head, ld, actions, old_log_probs, advantages,
         returns, old_values, mb_weights, adv_mean_rstd, vn_params, L, rows, M, clip_coef,
-        value_loss_coef, flags, vcol, d_head, d_bias, part, cb, RB, 1.f / (float)rows);
+        value_loss_coef, flags, vcol, d_head, d_bias, part, cb, 1.f / (float)rows);
     MLB_CHECK_LAUNCH();
     ppo_loss_final_kernel<<<1, 640, 0, s>>>(part, (int)g, (double)rows, num_components,
                                             value_loss_coef, stats);
