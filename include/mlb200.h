@@ -358,6 +358,27 @@ int mlb_renorm_segments(void* stream, float* params, const mlb_segment* segments
 int mlb_colsum_f32(void* stream, const float* x, long long rows, int ld, int ncols, float* out);
 
 /* ------------------------------------------------------------------------------------ */
+/* Data-parallel gradient exchange: SUM all-reduce of the flat gradient arena     */
+/* over NVLink peer memory fused with the clip_by_global_norm reduction (ml/ppo.py:84-90).     */
+/* Every rank's arena and a signal region (uint32[2*MLB_MAX_PEERS], zero-initialised) live in  */
+/* peer-mapped (symmetric) memory; peers_host lists all ranks' pointers as mapped in THIS      */
+/* process.  out <- sum over ranks (rank order: bit-identical on every rank); sumsq_out (may   */
+/* be NULL) <- sum(out^2) in fp64; state = device uint32[2] (zero-initialised, private to this */
+/* rank); ws of mlb_allreduce_workspace() bytes.  Every rank must enqueue the call the same    */
+/* number of times; the arena may be rewritten as soon as the call's kernel completes.          */
+/* ------------------------------------------------------------------------------------ */
+#define MLB_MAX_PEERS 16
+typedef struct mlb_peer_table {
+    int rank, world;
+    const float* grads[MLB_MAX_PEERS];
+    uint32_t* signals[MLB_MAX_PEERS];
+} mlb_peer_table;
+size_t mlb_allreduce_workspace(void);
+int mlb_allreduce_sumsq_f32(void* stream, const mlb_peer_table* peers_host, float* out,
+                            long long n, double* sumsq_out, uint32_t* state, void* ws,
+                            size_t ws_bytes);
+
+/* ------------------------------------------------------------------------------------ */
 /* Synthetic vector environment (stand-in for sim_fns['step'], ml/rollouts.py:905-936).     */
 /* tcount: device int32[2] = {step counter, block-arrival scratch}; the step kernel advances  */
 /* the counter itself (last block to finish), so a step is ONE launch.                        */

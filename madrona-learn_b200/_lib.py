@@ -77,6 +77,8 @@ SIGNATURES = {
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
     'mlb_mb_gather_multi': (c_int, [P, P, c_int, P, c_int, c_int, c_ll, c_ll]),
+    'mlb_allreduce_workspace': (c_size_t, []),
+    'mlb_allreduce_sumsq_f32': (c_int, [P, P, P, c_ll, P, P, P, c_size_t]),
     'mlb_policy_rollout_tc': (c_int, [P, P, P, P, c_ll, P, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P]),
     'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),
     'mlb_ppo_loss_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, c_ll, c_ll,
@@ -109,6 +111,12 @@ class Bf16Copy(ctypes.Structure):
 class GatherLeaf(ctypes.Structure):
     """mlb_gather_leaf."""
     _fields_ = [('store', c_void_p), ('out', c_void_p), ('out_bf16', c_void_p), ('row_bytes', ctypes.c_longlong)]
+
+
+class PeerTable(ctypes.Structure):
+    """mlb_peer_table."""
+    _fields_ = [('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('grads', c_void_p * 16),
+                ('signals', c_void_p * 16)]
 
 
 class MlpTcDesc(ctypes.Structure):

@@ -508,11 +508,22 @@ class PolicyProgram:
     def zero_grads(self):
         call('mlb_fill_zero', ptr(self.grads), c_size_t(self.num_params * 4))
 
-    def optimizer_step(self, lr, max_grad_norm, grad_scale=1.0, b1=0.9, b2=0.999, eps=1e-8):
-        """clip_by_global_norm -> adam -> re-projection / LN renorm (ml/ppo.py:283-338)."""
-        call('mlb_sumsq_f32', ptr(self.grads), c_ll(self.num_params), ptr(self.grad_sumsq),
-             ptr(self._sumsq_ws), c_size_t(self._sumsq_ws.numel()))
-        call('mlb_adam_step_f32', ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v),
+    def adopt_grad_arena(self, arena):
+        """Move the gradient arena into caller-provided memory (e.g. NVLink symmetric memory for
+        the fused data-parallel all-reduce); every gradient view is derived from self.grads."""
+        assert arena.numel() >= self.num_params and arena.dtype == F32 and arena.is_contiguous()
+        arena.zero_()
+        self.grads = arena
+
+    def optimizer_step(self, lr, max_grad_norm, grad_scale=1.0, b1=0.9, b2=0.999, eps=1e-8, reduced=None):
+        """clip_by_global_norm -> adam -> re-projection / LN renorm (ml/ppo.py:283-338).
+        reduced: the already all-reduced gradient whose sum of squares is in self.grad_sumsq
+        (mlb_allreduce_sumsq_f32); otherwise the local arena is used and its norm computed here."""
+        grads = self.grads if reduced is None else reduced
+        if reduced is None:
+            call('mlb_sumsq_f32', ptr(grads), c_ll(self.num_params), ptr(self.grad_sumsq),
+                 ptr(self._sumsq_ws), c_size_t(self._sumsq_ws.numel()))
+        call('mlb_adam_step_f32', ptr(self.params), ptr(grads), ptr(self.adam_m), ptr(self.adam_v),
              c_ll(self.num_params), ptr(self.adam_step), ptr(self.grad_sumsq), c_float(lr),
              c_float(b1), c_float(b2), c_float(eps), c_float(max_grad_norm), c_float(grad_scale))
         call('mlb_renorm_segments', ptr(self.params), ptr(self.segments), c_int(self.num_segments),

@@ -238,9 +238,14 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
                     ws.side.wait_stream(main)
                     with torch.cuda.stream(ws.side):
                         gather(*nxt)
-                if dist_ctx is not None:
-                    dist_ctx.allreduce_grads(prog.grads)      # sum over ranks; scales already global
-                prog.optimizer_step(tx['lr'], tx['max_grad_norm'], grad_scale, tx['b1'], tx['b2'], tx['eps'])
+                reduced = None
+                if dist_ctx is not None:                      # sum over ranks; scales already global
+                    if dist_ctx.fused:
+                        reduced = dist_ctx.allreduce_grads_fused(prog)     # NVLink peer reads + norm, one kernel
+                    else:
+                        dist_ctx.allreduce_grads(prog.grads)
+                prog.optimizer_step(tx['lr'], tx['max_grad_norm'], grad_scale, tx['b1'], tx['b2'], tx['eps'],
+                                    reduced=reduced)
                 if nxt is not None:
                     main.wait_stream(ws.side)
             with profile('Metrics Callback'):

@@ -165,6 +165,8 @@ def _init_training(dev, cfg, sim_fns, policy, sim_ctrl, user_hooks, restore_ckpt
     names = user_hooks.add_metrics(names)
     metrics = TrainingMetrics.create(cfg, names, start_update_idx, dev)
     prog = train_state_mgr.policy_states.program
+    if dist_ctx is not None and hasattr(dist_ctx, 'enable_fused_allreduce'):
+        dist_ctx.enable_fused_allreduce(prog)          # NVLink peer-memory all-reduce when available
     ppo_ws = _PPOWorkspace(cfg, prog, cfg.num_bptt_chunks,
                            cfg.steps_per_update // cfg.num_bptt_chunks,
                            rollout_cfg.sim_batch_size, dist_ctx)
