@@ -374,6 +374,13 @@ typedef struct mlb_peer_table {
     uint32_t* signals[MLB_MAX_PEERS];
 } mlb_peer_table;
 size_t mlb_allreduce_workspace(void);
+/* NVLS variant (NVSwitch in-network reduction): mc_grads / mc_out are the MULTICAST addresses of  */
+/* the arena and of a symmetric `reduced` buffer, out_local this rank's unicast view of the latter */
+/* (what the optimiser then reads).  Rank r reduces slice r with multimem.ld_reduce and broadcasts  */
+/* it with multimem.st.  state = device uint32[4], zero-initialised.                                */
+int mlb_allreduce_nvls_f32(void* stream, const mlb_peer_table* peers_host, const float* mc_grads,
+                           float* mc_out, const float* out_local, long long n, double* sumsq_out,
+                           uint32_t* state, void* ws, size_t ws_bytes);
 int mlb_allreduce_sumsq_f32(void* stream, const mlb_peer_table* peers_host, float* out,
                             long long n, double* sumsq_out, uint32_t* state, void* ws,
                             size_t ws_bytes);

@@ -78,6 +78,7 @@ SIGNATURES = {
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
     'mlb_mb_gather_multi': (c_int, [P, P, c_int, P, c_int, c_int, c_ll, c_ll]),
     'mlb_allreduce_workspace': (c_size_t, []),
+    'mlb_allreduce_nvls_f32': (c_int, [P, P, P, P, P, c_ll, P, P, P, c_size_t]),
     'mlb_allreduce_sumsq_f32': (c_int, [P, P, P, c_ll, P, P, P, c_size_t]),
     'mlb_policy_rollout_tc': (c_int, [P, P, P, P, c_ll, P, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P]),
     'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),
