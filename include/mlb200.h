@@ -358,6 +358,20 @@ int mlb_renorm_segments(void* stream, float* params, const mlb_segment* segments
 int mlb_colsum_f32(void* stream, const float* x, long long rows, int ld, int ncols, float* out);
 
 /* ------------------------------------------------------------------------------------ */
+/* PBT policy-batch reorder: _compute_reorder_chunks                        */
+/* (ml/rollouts.py:1107-1190) as a stable counting sort.  assignments i32 [S] in [0, P);        */
+/* to_policy i32 [B*C] (B chunks of C; B*C >= S), to_sim i32 [S].  Integer-only, bit-exact      */
+/* against the reference's KAT vectors (tests/test_rollouts.py:58-81).                          */
+/* mlb_gather_rows_clip: out[k] = src[clip(idx[k], 0, n_src-1)] -- PolicyBatchReorderState.     */
+/* to_policy / to_sim (ml/rollouts.py:143-168).                                                 */
+/* ------------------------------------------------------------------------------------ */
+size_t mlb_reorder_chunks_workspace(long long S, int P);
+int mlb_reorder_chunks(void* stream, const int32_t* assignments, long long S, int P, int C,
+                       long long B, int32_t* to_policy, int32_t* to_sim, void* ws, size_t ws_bytes);
+int mlb_gather_rows_clip(void* stream, const void* src, const int32_t* idx, void* out,
+                         long long n_idx, long long n_src, long long row_bytes);
+
+/* ------------------------------------------------------------------------------------ */
 /* Data-parallel gradient exchange: SUM all-reduce of the flat gradient arena     */
 /* over NVLink peer memory fused with the clip_by_global_norm reduction (ml/ppo.py:84-90).     */
 /* Every rank's arena and a signal region (uint32[2*MLB_MAX_PEERS], zero-initialised) live in  */

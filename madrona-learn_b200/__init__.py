@@ -11,6 +11,7 @@ from .cfg import (ContinuousActionsConfig, DiscreteActionsConfig, EvalConfig, Pa
                   PBTConfig, TrainConfig)
 from .envs import HostTraceEnv, SyntheticVectorEnv  # noqa: F401
 from .moving_avg import EMANormalizer  # noqa: F401
+from . import pbt_reorder  # noqa: F401
 from .observations import ObservationsCaster, ObservationsEMANormalizer  # noqa: F401
 from .policy import Policy  # noqa: F401
 from .ppo import PPOConfig  # noqa: F401

@@ -77,6 +77,9 @@ SIGNATURES = {
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
     'mlb_mb_gather_multi': (c_int, [P, P, c_int, P, c_int, c_int, c_ll, c_ll]),
+    'mlb_reorder_chunks_workspace': (c_size_t, [c_ll, c_int]),
+    'mlb_reorder_chunks': (c_int, [P, P, c_ll, c_int, c_int, c_ll, P, P, P, c_size_t]),
+    'mlb_gather_rows_clip': (c_int, [P, P, P, P, c_ll, c_ll, c_ll]),
     'mlb_allreduce_workspace': (c_size_t, []),
     'mlb_allreduce_nvls_f32': (c_int, [P, P, P, P, P, c_ll, P, P, P, c_size_t]),
     'mlb_allreduce_sumsq_f32': (c_int, [P, P, P, c_ll, P, P, P, c_size_t]),
