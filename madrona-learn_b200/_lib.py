@@ -94,6 +94,9 @@ SIGNATURES = {
     'mlb_adam_step_f32': (c_int, [P, P, P, P, P, c_ll, P, P, c_float, c_float, c_float, c_float,
                                   c_float, c_float]),
     'mlb_renorm_segments': (c_int, [P, P, P, c_int, P, P]),
+    'mlb_optimizer_fused_workspace': (c_size_t, []),
+    'mlb_optimizer_step_fused': (c_int, [P, P, P, P, P, c_ll, P, c_int, P, P, P, c_int, c_float, c_float, c_float,
+                                         c_float, c_float, c_float, P, P, c_size_t]),
     'mlb_colsum_f32': (c_int, [P, P, c_ll, c_int, c_int, P]),
     'mlb_synth_env_init': (c_int, [P, P, c_ll, c_int, ctypes.c_uint32, P]),
     'mlb_synth_env_step': (c_int, [P, P, P, P, c_int, P, P, P, c_ll, c_int, ctypes.c_uint32,

@@ -129,6 +129,137 @@ renorm_kernel(float* __restrict__ p, const mlb_segment* __restrict__ segs,
     cluster.sync();      // keep every CTA's shared memory alive until all remote reads are done
 }
 
+// ------------------------------------------------------------------------------------------
+// The whole optimiser step in ONE launch (the parameter arena is ~150 K floats: every phase of
+// the three-launch path above is a latency-bound kernel).  The grid (<= #SMs blocks, all
+// co-resident) owns contiguous slices of the arena and meets at two device-wide barriers:
+//   A  sum(g^2) partials                                  -> barrier -> clip scale
+//   B  Adam moments + update, per-(block, segment) sum(p^2) -> barrier
+//   C  re-projection / LayerNorm renorm factor per segment (partials re-reduced in block order:
+//      deterministic, so data-parallel ranks stay bit-identical), rescale, bf16 W / W^T refresh
+// Segments must tile the arena exactly, in offset order.
+// ------------------------------------------------------------------------------------------
+constexpr int FO_BLOCK = 256;
+constexpr int FO_MAX_SEGS = 32;
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// state[0] = arrival count, state[1] = generation.  Bounded spin: trap, never hang.
+__device__ __forceinline__ void grid_barrier(uint32_t* state) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t gen = ld_acquire_gpu(&state[1]);
+        if (atomicAdd(&state[0], 1u) == gridDim.x - 1) {
+            state[0] = 0;
+            __threadfence();
+            st_release_gpu(&state[1], gen + 1);
+        } else {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(&state[1]) == gen)
+                if (clock64() - t0 > 4000000000ll) __trap();
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(FO_BLOCK)
+optimizer_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, long long n, const mlb_segment* __restrict__ segs, int nseg,
+                       const mlb_bf16_copy* __restrict__ copies, int* __restrict__ step,
+                       double* __restrict__ grad_sumsq, int have_sumsq, float lr, float b1, float b2,
+                       float eps, float max_grad_norm, float grad_scale, uint32_t* __restrict__ sync_state,
+                       double* __restrict__ gpart, double* __restrict__ segpart) {
+    __shared__ double smd[32];
+    __shared__ double bcast;
+    const long long slice = (n + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * slice, hi = min(n, lo + slice);
+    // ---- A: global gradient norm --------------------------------------------------------
+    double ssq;
+    if (have_sumsq) ssq = *grad_sumsq;
+    else {
+        double s = 0.0;
+        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) { const float x = g[i]; s += (double)x * x; }
+        s = block_sum_d(s, smd);
+        if (threadIdx.x == 0) gpart[blockIdx.x] = s;
+        grid_barrier(sync_state);
+        double t = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += __ldcg(gpart + b);
+        t = block_sum_d(t, smd);                 // same fixed order in every block
+        if (threadIdx.x == 0) { bcast = t; if (blockIdx.x == 0) *grad_sumsq = t; }
+        __syncthreads();
+        ssq = bcast;
+    }
+    const int t = *step + 1;
+    float scale = grad_scale;
+    if (max_grad_norm > 0.f) {
+        const float gn = (float)(sqrt(ssq) * (double)fabsf(grad_scale));
+        if (!(gn < max_grad_norm)) scale *= max_grad_norm / gn;   // optax: (x / g_norm) * c
+    }
+    const float bc1 = 1.f - powf(b1, (float)t);
+    const float bc2 = 1.f - powf(b2, (float)t);
+    // ---- B: Adam + per-(block, segment) sum of squares of the updated parameters ---------
+    int s0 = 0;
+    while (s0 < nseg - 1 && segs[s0].offset + segs[s0].length <= lo) ++s0;
+    for (int si = s0; si < nseg && segs[si].offset < hi; ++si) {
+        const long long a = max(lo, (long long)segs[si].offset), e = min(hi, (long long)(segs[si].offset + segs[si].length));
+        double s = 0.0;
+        for (long long i = a + threadIdx.x; i < e; i += blockDim.x) {
+            const float gi = g[i] * scale;
+            const float mi = b1 * m[i] + (1.f - b1) * gi;
+            const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+            m[i] = mi; v[i] = vi;
+            const float pn = p[i] + (-lr * (mi / bc1) / (sqrtf(vi / bc2) + eps));
+            p[i] = pn;
+            s += (double)pn * pn;
+        }
+        s = block_sum_d(s, smd);
+        if (threadIdx.x == 0) segpart[(long long)blockIdx.x * FO_MAX_SEGS + si] = s;
+    }
+    grid_barrier(sync_state);
+    // ---- C: renorm factor per segment, rescale, bf16 operand copies -----------------------
+    for (int si = s0; si < nseg && segs[si].offset < hi; ++si) {
+        const mlb_segment sg = segs[si];
+        const long long a = max(lo, (long long)sg.offset), e = min(hi, (long long)(sg.offset + sg.length));
+        float f = 1.f;
+        if (sg.kind != 0) {
+            const int bfirst = (int)(sg.offset / slice), blast = (int)((sg.offset + sg.length - 1) / slice);
+            double tot = 0.0;
+            for (int b = bfirst + threadIdx.x; b <= blast; b += blockDim.x)
+                tot += __ldcg(segpart + (long long)b * FO_MAX_SEGS + si);
+            tot = block_sum_d(tot, smd);
+            if (threadIdx.x == 0)
+                bcast = sg.kind == 1 ? (double)sg.target / sqrt(tot) : sqrt((double)sg.target / tot);
+            __syncthreads();
+            f = (float)bcast;
+            __syncthreads();
+        }
+        mlb_bf16_copy cp;
+        cp.dst = nullptr; cp.dst_t = nullptr; cp.rows = cp.cols = cp.ld_t = cp.ld_d = 0;
+        if (copies) cp = copies[si];
+        if (sg.kind == 0 && !cp.dst_t) continue;
+        for (long long i = a + threadIdx.x; i < e; i += blockDim.x) {
+            float x = p[i];
+            if (sg.kind != 0) { x *= f; p[i] = x; }
+            if (cp.dst_t) {
+                const long long k = i - sg.offset;
+                const int r = (int)(k / cp.cols), c = (int)(k - (long long)r * cp.cols);
+                const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                reinterpret_cast<__nv_bfloat16*>(cp.dst_t)[(long long)c * cp.ld_t + r] = h;
+                if (cp.dst) reinterpret_cast<__nv_bfloat16*>(cp.dst)[(long long)r * cp.ld_d + c] = h;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *step = t;
+}
+
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, long long rows, int ld, int ncols, float* __restrict__ out) {
     // blockDim = (32 cols, 8 row-lanes); each block strides over rows
@@ -194,6 +325,31 @@ MLB_API int mlb_renorm_segments(void* stream, float* params, const mlb_segment* 
     MLB_REQUIRE(params && segments_dev && num_segments > 0);
     renorm_kernel<<<num_segments * RENORM_CLUSTER, 512, 0, mlb_stream(stream)>>>(params, segments_dev,
                                                                                 copies_dev, step);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+MLB_API size_t mlb_optimizer_fused_workspace(void) {
+    return (size_t)MLB_NUM_SMS * (1 + FO_MAX_SEGS) * sizeof(double) + 16;
+}
+
+MLB_API int mlb_optimizer_step_fused(void* stream, float* params, const float* grads, float* m, float* v,
+                                     long long n, const mlb_segment* segments_dev, int num_segments,
+                                     const mlb_bf16_copy* copies_dev, int32_t* step, double* grad_sumsq,
+                                     int have_sumsq, float lr, float b1, float b2, float eps,
+                                     float max_grad_norm, float grad_scale, uint32_t* sync_state, void* ws,
+                                     size_t ws_bytes) {
+    MLB_REQUIRE(params && grads && m && v && step && grad_sumsq && segments_dev && sync_state && n > 0);
+    MLB_REQUIRE(num_segments > 0 && num_segments <= FO_MAX_SEGS);
+    if (!ws || ws_bytes < mlb_optimizer_fused_workspace()) return MLB_EWS;
+    long long gsz = (n + 1023) / 1024;
+    if (gsz > MLB_NUM_SMS) gsz = MLB_NUM_SMS;
+    if (gsz < 1) gsz = 1;
+    double* gpart = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 15) & ~uintptr_t(15));
+    double* segpart = gpart + MLB_NUM_SMS;
+    optimizer_fused_kernel<<<(unsigned)gsz, FO_BLOCK, 0, mlb_stream(stream)>>>(
+        params, grads, m, v, n, segments_dev, num_segments, copies_dev, step, grad_sumsq, have_sumsq, lr, b1, b2,
+        eps, max_grad_norm, grad_scale, sync_state, gpart, segpart);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }

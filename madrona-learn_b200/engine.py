@@ -295,6 +295,23 @@ class PolicyProgram:
         segs.append(_lib.Segment(self.head_w_off, self.feat * self.NH, 0, 0.0))
         copies.append(_lib.Bf16Copy(self.wh_t.data_ptr(), self.wh_c.data_ptr(), self.feat, self.NH, self.feat,
                                     self.NH) if self.tc else none)
+        # tile the arena exactly, in offset order (plain tensors -- head bias, LSTM bias -- become
+        # kind-0 segments): what the single-launch optimiser (mlb_optimizer_step_fused) walks
+        order = sorted(range(len(segs)), key=lambda i: segs[i].offset)
+        tiled, tcopies, pos = [], [], 0
+        for i in order:
+            if segs[i].offset > pos:
+                tiled.append(_lib.Segment(pos, segs[i].offset - pos, 0, 0.0)); tcopies.append(none)
+            tiled.append(segs[i]); tcopies.append(copies[i])
+            pos = segs[i].offset + segs[i].length
+        if pos < self.num_params:
+            tiled.append(_lib.Segment(pos, self.num_params - pos, 0, 0.0)); tcopies.append(none)
+        segs, copies = tiled, tcopies
+        self._fused_opt = (len(segs) <= 32 and os.environ.get('MLB_FUSED_OPT', '1') != '0')
+        if getattr(self, '_opt_sync', None) is None:
+            self._opt_sync = torch.zeros(2, dtype=torch.int32, device=self.device)
+            self._opt_ws = torch.zeros(_lib.lib().mlb_optimizer_fused_workspace(), dtype=torch.uint8,
+                                       device=self.device)
         carr = (_lib.Bf16Copy * len(copies))(*copies)
         self.copies = torch.from_numpy(np.frombuffer(bytes(carr), dtype=np.uint8).copy()).to(self.device) \
             if self.tc else None
@@ -543,6 +560,13 @@ class PolicyProgram:
         reduced: the already all-reduced gradient whose sum of squares is in self.grad_sumsq
         (mlb_allreduce_sumsq_f32); otherwise the local arena is used and its norm computed here."""
         grads = self.grads if reduced is None else reduced
+        if self._fused_opt:
+            call('mlb_optimizer_step_fused', ptr(self.params), ptr(grads), ptr(self.adam_m), ptr(self.adam_v),
+                 c_ll(self.num_params), ptr(self.segments), c_int(self.num_segments), ptr(self.copies),
+                 ptr(self.adam_step), ptr(self.grad_sumsq), c_int(0 if reduced is None else 1), c_float(lr),
+                 c_float(b1), c_float(b2), c_float(eps), c_float(max_grad_norm), c_float(grad_scale),
+                 ptr(self._opt_sync), ptr(self._opt_ws), c_size_t(self._opt_ws.numel()))
+            return
         if reduced is None:
             call('mlb_sumsq_f32', ptr(grads), c_ll(self.num_params), ptr(self.grad_sumsq),
                  ptr(self._sumsq_ws), c_size_t(self._sumsq_ws.numel()))
