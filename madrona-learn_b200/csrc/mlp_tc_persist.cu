@@ -402,8 +402,12 @@ dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         m2 = fmaf(dxh, xh, m2);
                         gx[j] = du * xh;
                         g[j] = du;
+                        r[j] = __float_as_uint(dxh);     // pass 2 reads dxhat back instead of redoing the mask
                     }
+                    tmem_st8_nowait(taddr + c + 8 * q, r[8 * q], r[8 * q + 1], r[8 * q + 2], r[8 * q + 3],
+                                    r[8 * q + 4], r[8 * q + 5], r[8 * q + 6], r[8 * q + 7]);
                 }
+                tmem_st_wait();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p.bars.xh_empty[xs]);       // this warp is done with the panel
                 const float csum = warp_reduce_scatter32p(gx, lane);
@@ -414,7 +418,8 @@ dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             exchange2(part, buf, grp, rt, quad, m1, m2);
             const float c1 = rstd * m1 * invH;               // dz = rstd*dxhat - rstd*m1 - xhat*(rstd*m2)
             const float c2 = rstd * m2 * invH;
-            // pass 2: dz written over xhat in the (re-loaded) panel, then written out by the same warp
+            // pass 2: dz = rstd*dxhat - c1 - xhat*c2 (dxhat from TMEM, where pass 1 left it), written over
+            // xhat in the (re-loaded) panel, then written out by the same warp
             bool released = false;
             for (int ch = grp; ch < nchunks; ch += 4) {
                 const int xit = xbase + num_panels + (ch >> 1);
@@ -435,19 +440,12 @@ dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     uint4* slot = reinterpret_cast<uint4*>(pan + sw128(rt, hf * 4 + q));
                     const uint4 u = *slot;
                     const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-                    const float4 sa = *reinterpret_cast<const float4*>(s + c + 8 * q);
-                    const float4 sb = *reinterpret_cast<const float4*>(s + c + 8 * q + 4);
-                    const float4 ba = *reinterpret_cast<const float4*>(b + c + 8 * q);
-                    const float4 bb = *reinterpret_cast<const float4*>(b + c + 8 * q + 4);
-                    const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-                    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
                     float dz8[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const float xh = (e & 1) ? bf16hi(w4[e >> 1]) : bf16lo(w4[e >> 1]);
-                        const float dy = __uint_as_float(r[8 * q + e]);
-                        const float rs = (fmaf(xh, sv[e], bv[e]) > 0.f) ? rstd * sv[e] : 0.f;
-                        dz8[e] = fmaf(-c2, xh, fmaf(rs, dy, -c1));
+                        const float dxh = __uint_as_float(r[8 * q + e]);
+                        dz8[e] = fmaf(-c2, xh, fmaf(rstd, dxh, -c1));
                     }
                     *slot = make_uint4(pack_bf16(dz8[0], dz8[1]), pack_bf16(dz8[2], dz8[3]),
                                        pack_bf16(dz8[4], dz8[5]), pack_bf16(dz8[6], dz8[7]));

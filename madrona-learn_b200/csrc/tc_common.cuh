@@ -133,6 +133,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 8-column store (no wait: pair with tmem_st_wait) -- lets an epilogue write values back piecewise
+__device__ __forceinline__ void tmem_st8_nowait(uint32_t taddr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, sm100): start>>4 [0,14),
 // LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

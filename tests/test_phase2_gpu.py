@@ -257,3 +257,40 @@ def test_synthetic_env_bit_exact(mlb, p_done):
         np.testing.assert_array_equal(out['rewards'].cpu().numpy()[:, 0], r)
         np.testing.assert_array_equal(out['dones'].cpu().numpy()[:, 0].astype(bool), d)
     assert d.any() or p_done < 0
+
+
+def test_fused_optimizer_step_matches_three_launch_path(mlb):
+    """mlb_optimizer_step_fused (one launch, device-wide barriers) == mlb_sumsq_f32 + mlb_adam_step_f32 +
+    mlb_renorm_segments: same arithmetic, only the fp64 partial-sum grouping of the norms differs
+    (rel 1e-6 on parameters / moments after 3 steps), on both the fp32 and the bf16-copy paths."""
+    from madrona_learn_b200.engine import PolicyProgram
+    m = mlb
+    buckets = [4, 8, 5, 5, 2, 2]
+    for dtype in (torch.float32, torch.bfloat16):
+        progs = []
+        for fused in (True, False):
+            ac = m.ActorCritic(
+                backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(net=m.models.MLP(128, 2))),
+                actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(buckets)),
+                critic=m.models.DenseLayerCritic())
+            p = PolicyProgram(ac, 32, {'act': m.DiscreteActionsConfig(buckets)}, DEV, dtype)
+            p.init_params(3)
+            p.finalize_params()
+            assert p._fused_opt
+            p._fused_opt = fused
+            progs.append(p)
+        g = torch.Generator(device=DEV).manual_seed(0)
+        for step in range(3):
+            grads = torch.randn(progs[0].num_params, device=DEV, generator=g) * (0.3 if step else 30.0)  # clip on/off
+            for p in progs:
+                p.grads.copy_(grads)
+                p.optimizer_step(3e-3, 0.5)
+        torch.cuda.synchronize()
+        a, b = progs
+        assert int(a.adam_step.item()) == int(b.adam_step.item()) == 3
+        for x, y in ((a.params, b.params), (a.adam_m, b.adam_m), (a.adam_v, b.adam_v)):
+            assert torch.allclose(x, y, rtol=1e-6, atol=1e-9), (x - y).abs().max().item()
+        assert abs(a.grad_sumsq.item() - b.grad_sumsq.item()) <= 1e-12 * b.grad_sumsq.item()
+        if dtype == torch.bfloat16:
+            for i in range(a.L):
+                assert torch.equal(a.w_t[i], b.w_t[i]) or (a.w_t[i].float() - b.w_t[i].float()).abs().max() < 1e-2
