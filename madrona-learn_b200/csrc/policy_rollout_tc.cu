@@ -69,10 +69,21 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
     uint64_t* a_bar = acc_bar + 1;               // A operand of the next layer ready (256 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
     uint32_t* keys_sm = tmem_slot + 2;           // policy key (2 words)
+    uint32_t* ckeys_sm = keys_sm + 2;            // per-component sample keys (2 * A words)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long m0 = (long long)blockIdx.x * BM;
     const int kb_of_layer0 = (D + 63) / 64, kb_h = H / 64;
+    // Row pairing: jax's (non-partitionable) random_bits feeds element e and element e + size/2 from
+    // ONE threefry block, i.e. rows r and r + rows/2 of the same component share their random
+    // blocks.  A CTA therefore owns 64 rows of the first half of the batch and the matching 64
+    // rows of the second half, and every threefry evaluation yields two samples.
+    const bool paired = (rows % BM == 0) && !part;
+    const long long half_rows = rows >> 1;
+    auto grow = [&](int r) -> long long {
+        return paired ? (r < 64 ? (long long)blockIdx.x * 64 + r : half_rows + (long long)blockIdx.x * 64 + (r - 64))
+                      : m0 + r;
+    };
 
     if (warp == 0 && lane == 0) {
         for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w[l])) : "memory");
@@ -152,12 +163,17 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
         const int et = threadIdx.x - 64;                 // 0..511
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         float* partials = fsm + 4 * H;
+        if (!deterministic && et < a.A) {                // sample_keys = split(policy_key, A)  (ml/dists.py:31)
+            uint32_t c0, c1;
+            threefry_split_at(keys_sm[0], keys_sm[1], (uint32_t)et, (uint32_t)a.A, part, c0, c1);
+            ckeys_sm[2 * et] = c0; ckeys_sm[2 * et + 1] = c1;
+        }
         // ---- observations: fp32 rows -> store slab (fp32) + bf16 A panels (SWIZZLE_128B, K-major) ----
         {
             const int chunks = kb_of_layer0 * 8;         // 16-byte bf16 chunks per row (zero padded)
             for (int item = et; item < 128 * chunks; item += PR_EPI) {
                 const int r = item / chunks, j = item - r * chunks;
-                const long long row = m0 + r;
+                const long long row = grow(r);
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                 if (row < rows && j * 8 < D) {
                     const float* src = obs + row * D + j * 8;
@@ -239,36 +255,18 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
         if (head_out) {
             for (int e = et; e < 128 * NH; e += PR_EPI) {
                 const int r = e / NH, c = e - r * NH;
-                if (m0 + r < rows) head_out[(m0 + r) * NH + c] = head_sm[r * (NH + 1) + c];
+                if (grow(r) < rows) head_out[grow(r) * NH + c] = head_sm[r * (NH + 1) + c];
             }
         }
         // ---- sampling: (row, component) work items over the 512 epilogue threads ----
-        const uint32_t pk0 = keys_sm[0], pk1 = keys_sm[1];
-        for (int item = et; item < 128 * a.A; item += PR_EPI) {
-            const int r = item / a.A, i = item - r * a.A;
-            const long long row = m0 + r;
-            if (row >= rows) continue;
-            const float* l = head_sm + r * (NH + 1);
-            const int off = a.off[i], nb = a.nb[i];
+        auto lse_of = [&](const float* l, int off, int nb) {
             float mx = -INFINITY;
             for (int j = 0; j < nb; ++j) mx = fmaxf(mx, l[off + j]);
             float se = 0.f;
             for (int j = 0; j < nb; ++j) se += expf(l[off + j] - mx);
-            const float lse = logf(se) + mx;
-            int best = 0;
-            float bv = -INFINITY;
-            if (deterministic) {
-                for (int j = 0; j < nb; ++j) if (l[off + j] > bv) { bv = l[off + j]; best = j; }
-            } else {
-                uint32_t c0, c1;
-                threefry_split_at(pk0, pk1, (uint32_t)i, (uint32_t)a.A, part, c0, c1);
-                const uint64_t size = (uint64_t)rows * (uint64_t)nb;
-                for (int j = 0; j < nb; ++j) {
-                    const uint32_t bits = threefry_bits_at(c0, c1, (uint64_t)row * nb + j, size, part);
-                    const float v = -logf(-logf(uniform_from_bits(bits))) + l[off + j];
-                    if (v > bv) { bv = v; best = j; }
-                }
-            }
+            return logf(se) + mx;
+        };
+        auto emit = [&](long long row, const float* l, int i, int off, int best, float lse) {
             actions[row * a.A + i] = best;
             if (log_probs) log_probs[row * a.A + i] = l[off + best] - lse;
             if (values && i == 0) {
@@ -286,6 +284,54 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
                         acc += expf(lc[mid - 1 - k] - m2) * inv * a.bins[mid - 1 - k] + expf(lc[mid + 1 + k] - m2) * inv * a.bins[mid + 1 + k];
                     values[row] = expf(lc[mid] - m2) * inv * a.bins[mid] + acc;
                 }
+            }
+        };
+        if (paired && !deterministic) {
+            for (int item = et; item < 64 * a.A; item += PR_EPI) {
+                const int r = item / a.A, i = item - r * a.A;
+                const long long rowA = grow(r), rowB = rowA + half_rows;
+                const float* lA = head_sm + r * (NH + 1);
+                const float* lB = head_sm + (r + 64) * (NH + 1);
+                const int off = a.off[i], nb = a.nb[i];
+                const float lseA = lse_of(lA, off, nb), lseB = lse_of(lB, off, nb);
+                const uint32_t c0 = ckeys_sm[2 * i], c1 = ckeys_sm[2 * i + 1];
+                const uint64_t half = (uint64_t)half_rows * (uint64_t)nb;      // = size / 2 (size is even)
+                int bestA = 0, bestB = 0;
+                float bvA = -INFINITY, bvB = -INFINITY;
+                for (int j = 0; j < nb; ++j) {
+                    const uint64_t idx = (uint64_t)rowA * nb + j;
+                    uint32_t x0 = (uint32_t)idx, x1 = (uint32_t)(idx + half);
+                    threefry2x32(c0, c1, x0, x1);               // one block: x0 -> row A, x1 -> row A + rows/2
+                    const float vA = -logf(-logf(uniform_from_bits(x0))) + lA[off + j];
+                    const float vB = -logf(-logf(uniform_from_bits(x1))) + lB[off + j];
+                    if (vA > bvA) { bvA = vA; bestA = j; }
+                    if (vB > bvB) { bvB = vB; bestB = j; }
+                }
+                emit(rowA, lA, i, off, bestA, lseA);
+                emit(rowB, lB, i, off, bestB, lseB);
+            }
+        } else {
+            for (int item = et; item < 128 * a.A; item += PR_EPI) {
+                const int r = item / a.A, i = item - r * a.A;
+                const long long row = grow(r);
+                if (row >= rows) continue;
+                const float* l = head_sm + r * (NH + 1);
+                const int off = a.off[i], nb = a.nb[i];
+                const float lse = lse_of(l, off, nb);
+                int best = 0;
+                float bv = -INFINITY;
+                if (deterministic) {
+                    for (int j = 0; j < nb; ++j) if (l[off + j] > bv) { bv = l[off + j]; best = j; }
+                } else {
+                    const uint32_t c0 = ckeys_sm[2 * i], c1 = ckeys_sm[2 * i + 1];
+                    const uint64_t size = (uint64_t)rows * (uint64_t)nb;
+                    for (int j = 0; j < nb; ++j) {
+                        const uint32_t bits = threefry_bits_at(c0, c1, (uint64_t)row * nb + j, size, part);
+                        const float v = -logf(-logf(uniform_from_bits(bits))) + l[off + j];
+                        if (v > bv) { bv = v; best = j; }
+                    }
+                }
+                emit(row, l, i, off, best, lse);
             }
         }
     }
@@ -331,7 +377,7 @@ MLB_API int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* d, const 
     a.head_bias = d->head_bias;
     const int act_panels = (a.H > a.D ? a.H : a.D + 63) / 64;
     const size_t smem = (size_t)act_panels * 16384 + (size_t)PR_STAGES * a.H * 128 +
-                        (size_t)128 * (a.NH + 1) * 4 + (size_t)(4 * a.H + 1024) * 4 + 16 * 8 + 64 + 1024;
+                        (size_t)128 * (a.NH + 1) * 4 + (size_t)(4 * a.H + 1024) * 4 + 16 * 8 + 64 + 128 + 1024;
     if (smem > 227 * 1024) return MLB_EINVAL;
     cudaError_t e = cudaFuncSetAttribute(policy_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -408,7 +408,7 @@ class PolicyProgram:
         if self.H > 256 or self.H % 64 or self.L > 4 or self.NH > 256 or self.obs_dim > 256:
             return False
         panels = (max(self.H, self.obs_dim + 63)) // 64
-        smem = panels * 16384 + 2 * self.H * 128 + 128 * (self.NH + 1) * 4 + (4 * self.H + 1024) * 4 + 1216
+        smem = panels * 16384 + 2 * self.H * 128 + 128 * (self.NH + 1) * 4 + (4 * self.H + 1024) * 4 + 1344
         return smem <= 227 * 1024
 
     def rollout_step_fused(self, obs, obs_store, rows, key_in, key_out, actions, log_probs, values,
