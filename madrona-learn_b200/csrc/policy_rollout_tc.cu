@@ -14,6 +14,8 @@
 //     of TMEM and write the next layer's A operand straight back into the same panels;
 //   * the head GEMM lands in TMEM columns [256, 256+NH), is staged as fp32 in shared memory and
 //     sampled by all 512 epilogue threads ((row, component) work items, threefry Gumbel-max).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -22,7 +24,7 @@ using namespace tc;
 
 constexpr int PR_THREADS = 576;          // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue (4 lane quadrants x 4 column groups)
 constexpr int PR_EPI = 512;
-constexpr int PR_STAGES = 2;
+constexpr int PR_MAX_STAGES = 4;       // weight ring depth is chosen at launch: as deep as shared memory allows
 constexpr int MAXL = MLB_MLP_TC_MAX_LAYERS;
 constexpr int MAXC = MLB_MAX_ACTION_COMPONENTS;
 constexpr float LN_EPS = 1e-6f;
@@ -52,7 +54,7 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
                       const float* __restrict__ obs, float* __restrict__ obs_store, long long rows,
                       const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_out, int part,
                       int deterministic, int32_t* __restrict__ actions, float* __restrict__ log_probs,
-                      float* __restrict__ values, float* __restrict__ head_out) {
+                      float* __restrict__ values, float* __restrict__ head_out, int PR_STAGES) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align_smem_1024(smem_raw);
     const int H = a.H, NH = a.NH, L = a.L, D = a.D;
@@ -64,8 +66,8 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
     float* fsm = head_sm + 128 * (NH + 1);                            // [2][2H] scale|bias, [4][128][2] partials
     uint64_t* bars = reinterpret_cast<uint64_t*>(fsm + 4 * H + 1024);
     uint64_t* full_bar = bars;                   // [PR_STAGES]
-    uint64_t* empty_bar = bars + PR_STAGES;      // [PR_STAGES]
-    uint64_t* acc_bar = bars + 2 * PR_STAGES;    // accumulator of the current layer complete
+    uint64_t* empty_bar = bars + PR_MAX_STAGES;  // [PR_STAGES]
+    uint64_t* acc_bar = bars + 2 * PR_MAX_STAGES;   // accumulator of the current layer complete
     uint64_t* a_bar = acc_bar + 1;               // A operand of the next layer ready (256 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
     uint32_t* keys_sm = tmem_slot + 2;           // policy key (2 words)
@@ -376,14 +378,20 @@ MLB_API int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* d, const 
     if ((rc = make_map(&maps.wh, d->wh_t, a.H, a.NH, a.H, 64, a.NH))) return rc;
     a.head_bias = d->head_bias;
     const int act_panels = (a.H > a.D ? a.H : a.D + 63) / 64;
-    const size_t smem = (size_t)act_panels * 16384 + (size_t)PR_STAGES * a.H * 128 +
-                        (size_t)128 * (a.NH + 1) * 4 + (size_t)(4 * a.H + 1024) * 4 + 16 * 8 + 64 + 128 + 1024;
+    const size_t fixed = (size_t)act_panels * 16384 + (size_t)128 * (a.NH + 1) * 4 + (size_t)(4 * a.H + 1024) * 4 +
+                         16 * 8 + 64 + 128 + 1024;
+    // measured: a deeper ring (3-4 stages) does not help -- the per-layer chain is MMA -> two-pass
+    // epilogue, not weight-load latency (21.6 us/step with 2 stages, 22.6 with 4)
+    static const int want = [] { const char* v = getenv("MLB_ROLLOUT_STAGES"); return v ? atoi(v) : 2; }();
+    int stages = 2;
+    while (stages < want && stages < PR_MAX_STAGES && fixed + (size_t)(stages + 1) * a.H * 128 <= 227 * 1024) ++stages;
+    const size_t smem = fixed + (size_t)stages * a.H * 128;
     if (smem > 227 * 1024) return MLB_EINVAL;
     cudaError_t e = cudaFuncSetAttribute(policy_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     policy_rollout_kernel<<<mlb_cdiv(rows, BM), PR_THREADS, smem, mlb_stream(stream)>>>(
         maps, a, obs, obs_store, rows, key_in, key_out, partitionable, deterministic, actions, log_probs,
-        values, head_out);
+        values, head_out, stages);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }
