@@ -304,7 +304,8 @@ int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* desc_host, const 
 /* d_head [rows, ld] out: f32, or bf16 when flags has MLB_PPO_DHEAD_BF16 (tensor-core path); */
 /* padding columns are written as zeros.  d_bias (may be NULL): f32 [sumA+1], the heads' bias  */
 /* gradients (column sums of d_head) are ACCUMULATED here.  stats out; ws of                    */
-/* mlb_ppo_loss_workspace(rows) bytes.  ld % 4 == 0; head and d_head 16-byte aligned.             */
+/* mlb_ppo_loss_workspace(rows) bytes, ZERO-INITIALISED once by the caller (it ends with the       */
+/* ticket counter of the last-block final reduction).  ld % 4 == 0; head, d_head 16-byte aligned.  */
 /* ------------------------------------------------------------------------------------ */
 #define MLB_PPO_CLIP_VALUE_LOSS  1
 #define MLB_PPO_HUBER_VALUE_LOSS 2

@@ -229,6 +229,72 @@ __device__ __forceinline__ CompOut loss_component(float* __restrict__ l, int act
     return CompOut{obj, H};
 }
 
+// Final combine over the per-block partials, run by the LAST block of the loss kernel to finish
+// (ticket counter in the workspace): one warp per reduced quantity -- 0-10 the fp64 sums (obj, vl,
+// ent, s[4], ss[4]), 11-14 the minima, 15-18 the maxima -- then thread 0 assembles mlb_ppo_stats.
+__device__ void loss_finalize(const LossPartial* __restrict__ part, int nparts, double rows, int A,
+                              float vcoef, mlb_ppo_stats* __restrict__ out) {
+    __shared__ double sd[11];
+    __shared__ float sf[8];
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int q = threadIdx.x >> 5; q < 19; q += nw) {
+        // independent loads first (the partials sit in L2: one round trip per 8 blocks, not per block)
+        if (q < 11) {
+            double a = 0.0;
+            for (int b0 = lane; b0 < nparts; b0 += 32 * 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int b = b0 + 32 * u;
+                    if (b < nparts) {
+                        const LossPartial& P = part[b];
+                        v[u] = q == 0 ? P.obj : q == 1 ? P.vl : q == 2 ? P.ent : q < 7 ? P.s[q - 3] : P.ss[q - 7];
+                    } else v[u] = 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a += v[u];
+            }
+            a = warp_sum(a);
+            if (lane == 0) sd[q] = a;
+        } else {
+            const bool is_min = q < 15;
+            const int k = is_min ? q - 11 : q - 15;
+            float m = is_min ? INFINITY : -INFINITY;
+            for (int b0 = lane; b0 < nparts; b0 += 32 * 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int b = b0 + 32 * u;
+                    v[u] = b < nparts ? (is_min ? part[b].mn[k] : part[b].mx[k]) : (is_min ? INFINITY : -INFINITY);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) m = is_min ? fminf(m, v[u]) : fmaxf(m, v[u]);
+            }
+            m = is_min ? warp_min_f(m) : warp_max_f(m);
+            if (lane == 0) sf[is_min ? k : 4 + k] = m;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double obj = sd[0], vl = sd[1], ent = sd[2];
+        const float loss = (float)(-obj + (double)vcoef * vl - ent);
+        out->loss = loss; out->action_obj = (float)obj; out->value_loss = (float)((double)vcoef * vl);
+        out->entropy = (float)ent;
+        mlb_metric* m = &out->metrics[0];          // 'Loss': a scalar record (ml/ppo.py:352)
+        m->mean = loss; m->m2 = 0.f; m->min = loss; m->max = loss; m->count = 1;
+    }
+    if (threadIdx.x < 4) {
+        const int k = threadIdx.x;
+        const double s = sd[3 + k], ss = sd[7 + k];
+        const double cnt = (k == 0 || k == 3) ? rows * A : rows;
+        const double mean = s / cnt;
+        double m2 = ss - s * mean;
+        if (m2 < 0) m2 = 0;
+        mlb_metric* m = &out->metrics[k + 1];
+        m->mean = (float)mean; m->m2 = (float)m2; m->min = sf[k]; m->max = sf[4 + k]; m->count = (int32_t)cnt;
+    }
+}
+
 template <int RB>
 __global__ void __launch_bounds__(1024)
 ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restrict__ actions,
@@ -237,7 +303,8 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
                 const float* __restrict__ mb_w, const float* __restrict__ adv_mr,
                 const float* __restrict__ vn, Layout L, long long rows, long long M,
                 float clip, float vcoef, int flags, int vcol, void* __restrict__ dhead,
-                float* __restrict__ dbias, LossPartial* __restrict__ part, CriticBins cb, float inv_rows) {
+                float* __restrict__ dbias, LossPartial* __restrict__ part, CriticBins cb, float inv_rows,
+                unsigned int* __restrict__ ticket, mlb_ppo_stats* __restrict__ stats) {
     extern __shared__ float tile[];
     __shared__ WarpPartial wpart[32];
     const long long row0 = (long long)blockIdx.x * RB;
@@ -405,69 +472,18 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
         __syncthreads();
         for (int c = threadIdx.x; c < ncols; c += blockDim.x) atomicAdd(dbias + c, colsum[c]);
     }
-}
-
-// One warp per reduced quantity: warps 0-10 the fp64 sums (obj, vl, ent, s[4], ss[4]), 11-14 the
-// minima, 15-18 the maxima; thread 0 assembles mlb_ppo_stats.
-__global__ void __launch_bounds__(640)
-ppo_loss_final_kernel(const LossPartial* __restrict__ part, int nparts, double rows, int A,
-                      float vcoef, mlb_ppo_stats* __restrict__ out) {
-    __shared__ double sd[11];
-    __shared__ float sf[8];
-    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // independent loads first (the partials sit in L2: one round trip per 8 blocks, not per block)
-    if (q < 11) {
-        double a = 0.0;
-        for (int b0 = lane; b0 < nparts; b0 += 32 * 8) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int b = b0 + 32 * u;
-                if (b < nparts) {
-                    const LossPartial& P = part[b];
-                    v[u] = q == 0 ? P.obj : q == 1 ? P.vl : q == 2 ? P.ent : q < 7 ? P.s[q - 3] : P.ss[q - 7];
-                } else v[u] = 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a += v[u];
-        }
-        a = warp_sum(a);
-        if (lane == 0) sd[q] = a;
-    } else if (q < 19) {
-        const bool is_min = q < 15;
-        const int k = is_min ? q - 11 : q - 15;
-        float m = is_min ? INFINITY : -INFINITY;
-        for (int b0 = lane; b0 < nparts; b0 += 32 * 8) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int b = b0 + 32 * u;
-                v[u] = b < nparts ? (is_min ? part[b].mn[k] : part[b].mx[k]) : (is_min ? INFINITY : -INFINITY);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) m = is_min ? fminf(m, v[u]) : fmaxf(m, v[u]);
-        }
-        m = is_min ? warp_min_f(m) : warp_max_f(m);
-        if (lane == 0) sf[is_min ? k : 4 + k] = m;
-    }
+    // the last block to finish folds all per-block partials into mlb_ppo_stats (no second launch)
+    __shared__ bool last_block;
     __syncthreads();
     if (threadIdx.x == 0) {
-        const double obj = sd[0], vl = sd[1], ent = sd[2];
-        const float loss = (float)(-obj + (double)vcoef * vl - ent);
-        out->loss = loss; out->action_obj = (float)obj; out->value_loss = (float)((double)vcoef * vl);
-        out->entropy = (float)ent;
-        mlb_metric* m = &out->metrics[0];          // 'Loss': a scalar record (ml/ppo.py:352)
-        m->mean = loss; m->m2 = 0.f; m->min = loss; m->max = loss; m->count = 1;
+        __threadfence();
+        last_block = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (last_block) *ticket = 0;              // re-armed for the next launch
     }
-    if (threadIdx.x < 4) {
-        const int k = threadIdx.x;
-        const double s = sd[3 + k], ss = sd[7 + k];
-        const double cnt = (k == 0 || k == 3) ? rows * A : rows;
-        const double mean = s / cnt;
-        double m2 = ss - s * mean;
-        if (m2 < 0) m2 = 0;
-        mlb_metric* m = &out->metrics[k + 1];
-        m->mean = (float)mean; m->m2 = (float)m2; m->min = sf[k]; m->max = sf[4 + k]; m->count = (int32_t)cnt;
+    __syncthreads();
+    if (last_block) {
+        __threadfence();
+        loss_finalize(part, (int)gridDim.x, (double)rows, L.A, vcoef, stats);
     }
 }
 
@@ -525,7 +541,7 @@ MLB_API int mlb_sample_discrete_f32(void* stream, const float* head, int ld,
 }
 
 MLB_API size_t mlb_ppo_loss_workspace(long long rows) {
-    return (size_t)mlb_cdiv(rows, LOSS_RB_MIN) * sizeof(LossPartial);
+    return (size_t)mlb_cdiv(rows, LOSS_RB_MIN) * sizeof(LossPartial) + 16;      // + the ticket counter
 }
 
 MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int32_t* actions,
@@ -550,7 +566,7 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     if (vcol < 0) return vcol;
     const int RB = (num_components + 1) * 64 <= 1024 ? 64 : LOSS_RB_MIN;
     const unsigned g = mlb_cdiv(rows, RB);
-    if (!ws || ws_bytes < (size_t)g * sizeof(LossPartial)) return MLB_EWS;
+    if (!ws || ws_bytes < mlb_ppo_loss_workspace(rows)) return MLB_EWS;
     const int ncols = vcol + cb.V;
     const size_t smem = ((size_t)RB * (ncols | 1) + ncols) * sizeof(float);
     auto kern = RB == 64 ? ppo_loss_kernel<64> : ppo_loss_kernel<LOSS_RB_MIN>;
@@ -560,10 +576,8 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     LossPartial* part = reinterpret_cast<LossPartial*>(ws);
     kern<<<g, (num_components + 1) * RB, smem, s>>>(head, ld, actions, old_log_probs, advantages,
         returns, old_values, mb_weights, adv_mean_rstd, vn_params, L, rows, M, clip_coef,
-        value_loss_coef, flags, vcol, d_head, d_bias, part, cb, 1.f / (float)rows);
-    MLB_CHECK_LAUNCH();
-    ppo_loss_final_kernel<<<1, 640, 0, s>>>(part, (int)g, (double)rows, num_components,
-                                            value_loss_coef, stats);
+        value_loss_coef, flags, vcol, d_head, d_bias, part, cb, 1.f / (float)rows,
+        reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + mlb_ppo_loss_workspace(rows) - 16), stats);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }

@@ -347,7 +347,7 @@ class PolicyProgram:
                      stats=None if self.tc else [e(rows, 2) for _ in range(self.L)],
                      head=e(rows, self.NH), dhead=e(rows, self.NH, dtype=AT),
                      dy=e(rows, self.H, dtype=AT), dz=e(rows, self.H, dtype=AT),
-                     loss_ws=torch.empty(_lib.lib().mlb_ppo_loss_workspace(rows) + 16, dtype=torch.uint8, device=dev),
+                     loss_ws=torch.zeros(_lib.lib().mlb_ppo_loss_workspace(rows) + 16, dtype=torch.uint8, device=dev),
                      stats_out=torch.zeros(ctypes.sizeof(_lib.PPOStats), dtype=torch.uint8, device=dev))
             if self.tc:
                 w['x'] = e(rows, self.obs_dim, dtype=AT)
