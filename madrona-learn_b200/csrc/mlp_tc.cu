@@ -22,6 +22,7 @@
 //             then fp32 store / bf16 store / fp32 atomic add (split-K)
 // All mbarrier waits are bounded (trap instead of hanging the GPU).
 #include "tc_common.cuh"
+#include "mlp_tc_persist.cuh"
 
 namespace {
 
@@ -239,6 +240,10 @@ MLB_API int mlb_gemm_bf16_tc(void* stream, const void* A, const void* B, void* C
     MLB_REQUIRE(!(splitk > 1 && epi != EPI_ATOMIC));
     MLB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && mlb_aligned16(A) && mlb_aligned16(B) && mlb_aligned16(C));
     MLB_REQUIRE((epi == EPI_BF16 ? ldc % 8 == 0 : ldc % 4 == 0) && N % 8 == 0);
+    if (!a_mn && !b_mn && epi == EPI_F32 && bias && splitk == 1 && mlb_aligned16(bias) &&
+        tcp::gemm_persist_ok(M, N, K, ldc))           // minibatch-size head GEMM: persistent variant
+        return tcp::launch_gemm_bias_persist(mlb_stream(stream), A, B, bias, static_cast<float*>(C), M, N, K, lda,
+                                             ldb, ldc);
     int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     if (epi == EPI_ATOMIC && bn > 128) bn = 128;   // split-K: more output tiles, fewer K-splits
     CUtensorMap tA, tB;

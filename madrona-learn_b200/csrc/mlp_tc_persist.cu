@@ -334,6 +334,73 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
+// plain GEMM + bias -> fp32 (actor / critic heads of a minibatch): same persistent skeleton, no
+// LayerNorm.  Each warp transposes its [32 x 32] fp32 block through a 4 KB swizzled tile so that
+// global stores are 128-byte row segments.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_bias_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int K, int N,
+                         int a_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (M + BM - 1) / BM;
+    PState p = p_prologue(smem_raw, &tmA, &tmB, M, K, N, a_stages, 65536, bias, bias);
+    if (warp < 2) {
+        p_mainloop<0>(&tmA, &tmB, nullptr, p.smem, p.L, p.bars, p.tmem_base, warp, lane, num_tiles, K, N, a_stages);
+    } else {
+        const int quad = warp & 3, grp = (warp - 2) >> 2;
+        const float* b = p.fsm + N;
+        uint8_t* wt = p.smem + p.L.stage_off + (warp - 2) * 4096;
+        const int nchunks = N / 32;
+        int i = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int m0 = tile * BM;
+            const int rows_valid = M - (m0 + quad * 32);
+            const uint32_t taddr = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
+            mbar_wait(&p.bars.acc_full[buf], (i >> 1) & 1);
+            tcgen05_fence_after();
+            bool released = false;
+            for (int ch = grp; ch < nchunks; ch += 4) {
+                const int c = ch * 32;
+                uint32_t r[32];
+                tmem_ld32(taddr + c, r);
+                if (ch + 4 >= nchunks) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+                    released = true;
+                }
+                __syncwarp();                            // earlier read-back of the tile is complete
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 bv = *reinterpret_cast<const float4*>(b + c + 4 * q);
+                    *reinterpret_cast<float4*>(wt + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                        make_float4(__uint_as_float(r[4 * q]) + bv.x, __uint_as_float(r[4 * q + 1]) + bv.y,
+                                    __uint_as_float(r[4 * q + 2]) + bv.z, __uint_as_float(r[4 * q + 3]) + bv.w);
+                }
+                __syncwarp();
+                float* gbase = C + (size_t)(m0 + quad * 32) * ldc + c;
+                const int sl = lane & 7;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int rr = k * 4 + (lane >> 3);
+                    const float4 v = *reinterpret_cast<const float4*>(wt + rr * 128 + ((sl ^ (rr & 7)) << 4));
+                    if (rr < rows_valid) *reinterpret_cast<float4*>(gbase + (size_t)rr * ldc + sl * 4) = v;
+                }
+            }
+            if (!released) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+            }
+        }
+    }
+    p_teardown(p.tmem_base, warp);
+}
+
+// ------------------------------------------------------------------------------------------
 // backward: dZ_prev = LN'/ReLU'(dZ W^T), per-feature dscale / dbias
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(P_THREADS, 1)
@@ -527,6 +594,27 @@ int launch_fwd_persist(cudaStream_t st, const void* X, const void* Wt, const flo
     static const int dbg = [] { const char* v = getenv("MLB_TC_DEBUG"); return v ? atoi(v) : 0; }();
     fwd_persist_kernel<<<grid, P_THREADS, smem, st>>>(tA, tB, scale, bias, static_cast<__nv_bfloat16*>(Y),
                                                      static_cast<__nv_bfloat16*>(XH), rstd, M, K, HN, a_stages, dbg);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+bool gemm_persist_ok(int M, int N, int K, int ldc) {
+    return persist_ok(M, K, N) && N % 32 == 0 && ldc % 4 == 0 && p_layout(K, N, 2, 65536).total <= 227 * 1024;
+}
+
+int launch_gemm_bias_persist(cudaStream_t st, const void* A, const void* Bt, const float* bias, float* C,
+                             int M, int N, int K, int lda, int ldb, int ldc) {
+    CUtensorMap tA, tB;
+    int rc;
+    if ((rc = make_map(&tA, A, K, M, lda, 64, 128))) return rc;
+    if ((rc = make_map(&tB, Bt, K, N, ldb, 64, N))) return rc;
+    const int a_stages = pick_stages(K, N, 65536, 2);
+    const int smem = p_layout(K, N, a_stages, 65536).total;
+    cudaError_t e = cudaFuncSetAttribute(gemm_bias_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles = (M + BM - 1) / BM;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    gemm_bias_persist_kernel<<<grid, P_THREADS, smem, st>>>(tA, tB, bias, C, ldc, M, K, N, a_stages);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }

@@ -38,7 +38,9 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize('M,N,K', [(128, 64, 64), (128, 256, 64), (256, 256, 256), (300, 128, 192),
-                                   (1000, 64, 256), (8192, 256, 64), (4096, 512, 512), (128, 64, 40)])
+                                   (1000, 64, 256), (8192, 256, 64), (4096, 512, 512), (128, 64, 40),
+                                   # > 148 row tiles + bias + fp32 out: the persistent head-GEMM kernel (ragged)
+                                   (20004, 64, 256), (40000, 128, 64), (19500, 256, 256), (65536, 64, 256)])
 def test_tc_gemm_kmajor_fwd(mlb, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g)
