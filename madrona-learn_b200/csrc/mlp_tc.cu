@@ -54,6 +54,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* acc_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int k_begin = blockIdx.z * k_per_split;
@@ -75,6 +76,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    pdl_wait();                    // operands / the accumulated output come from preceding kernels
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -207,8 +209,7 @@ int launch_tc(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, void
     kps = (kps + BK - 1) / BK * BK;
     const int zs = (K + kps - 1) / kps;
     dim3 grid(mlb_cdiv(M, BM), mlb_cdiv(N, BN), zs);
-    kern<<<grid, TC_THREADS, L::TOTAL, s>>>(tA, tB, C, bias, ldc, M, N, K, kps);
-    e = cudaGetLastError();
+    e = launch_pdl(kern, grid, dim3(TC_THREADS), L::TOTAL, s, tA, tB, C, bias, ldc, M, N, K, kps);
     return e == cudaSuccess ? MLB_OK : (int)e;
 }
 

@@ -141,6 +141,7 @@ __device__ __forceinline__ PState p_prologue(uint8_t* smem_raw, const CUtensorMa
                                              int M, int K, int HN, int a_stages, int staging_bytes,
                                              const float* scale, const float* bias) {
     PState p;
+    pdl_launch_dependents();
     p.smem = align_smem_1024(smem_raw);
     p.L = p_layout(K, HN, a_stages, staging_bytes);
     p.fsm = reinterpret_cast<float*>(p.smem + p.L.misc_off);
@@ -162,6 +163,7 @@ __device__ __forceinline__ PState p_prologue(uint8_t* smem_raw, const CUtensorMa
             tma_load_2d(tmB, p.bars.w_bar, p.smem + kb * HN * 128, kb * BK, 0);
         const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         const int prime = my_tiles * num_kb < a_stages ? my_tiles * num_kb : a_stages;
+        pdl_wait();                                  // the activations come from the preceding kernel
         for (int it = 0; it < prime; ++it) {
             mbar_expect_tx(&p.bars.full[it], 16384u);
             tma_load_2d(tmA, &p.bars.full[it], p.smem + p.L.a_off + it * 16384, (it % num_kb) * BK,
@@ -182,6 +184,7 @@ __device__ __forceinline__ PState p_prologue(uint8_t* smem_raw, const CUtensorMa
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    pdl_wait();                                      // everything below touches predecessor data
     p.tmem_base = *p.bars.tmem_slot;
     return p;
 }
@@ -592,9 +595,9 @@ int launch_fwd_persist(cudaStream_t st, const void* X, const void* Wt, const flo
     const int tiles = (M + BM - 1) / BM;
     const int grid = tiles < sm_count() ? tiles : sm_count();
     static const int dbg = [] { const char* v = getenv("MLB_TC_DEBUG"); return v ? atoi(v) : 0; }();
-    fwd_persist_kernel<<<grid, P_THREADS, smem, st>>>(tA, tB, scale, bias, static_cast<__nv_bfloat16*>(Y),
-                                                     static_cast<__nv_bfloat16*>(XH), rstd, M, K, HN, a_stages, dbg);
-    MLB_CHECK_LAUNCH();
+    e = launch_pdl(fwd_persist_kernel, dim3(grid), dim3(P_THREADS), smem, st, tA, tB, scale, bias,
+                   static_cast<__nv_bfloat16*>(Y), static_cast<__nv_bfloat16*>(XH), rstd, M, K, HN, a_stages, dbg);
+    if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }
 
@@ -614,8 +617,8 @@ int launch_gemm_bias_persist(cudaStream_t st, const void* A, const void* Bt, con
     if (e != cudaSuccess) return (int)e;
     const int tiles = (M + BM - 1) / BM;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_bias_persist_kernel<<<grid, P_THREADS, smem, st>>>(tA, tB, bias, C, ldc, M, K, N, a_stages);
-    MLB_CHECK_LAUNCH();
+    e = launch_pdl(gemm_bias_persist_kernel, dim3(grid), dim3(P_THREADS), smem, st, tA, tB, bias, C, ldc, M, K, N, a_stages);
+    if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }
 
@@ -633,9 +636,9 @@ int launch_dx_persist(cudaStream_t st, const void* DZ_in, const void* W, const f
     if (e != cudaSuccess) return (int)e;
     const int tiles = (M + BM - 1) / BM;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    dx_persist_kernel<<<grid, P_THREADS, smem, st>>>(tA, tB, tXH, scale, bias, rstd, static_cast<__nv_bfloat16*>(DZ_out),
-                                                    dscale, dbias, M, K, HN, a_stages);
-    MLB_CHECK_LAUNCH();
+    e = launch_pdl(dx_persist_kernel, dim3(grid), dim3(P_THREADS), smem, st, tA, tB, tXH, scale, bias, rstd,
+                   static_cast<__nv_bfloat16*>(DZ_out), dscale, dbias, M, K, HN, a_stages);
+    if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }
 
