@@ -1,5 +1,6 @@
 // Shared device/host helpers for libmlb200 (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -16,6 +17,38 @@
 #define MLB_REQUIRE(cond) do { if (!(cond)) return MLB_EINVAL; } while (0)
 
 static inline cudaStream_t mlb_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start (prologue: barrier
+// init, TMEM allocation, tensor-map prefetch, resident-weight load) while its predecessor in the
+// stream is still draining its last tiles; pdl_wait() blocks until the predecessor has completed
+// and flushed, and must precede every access to data the predecessor (or anything before it)
+// produced.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as every
+// CTA of this grid has started.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("MLB_PDL"); return !(v && v[0] == '0'); }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+
 
 static inline unsigned mlb_cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 

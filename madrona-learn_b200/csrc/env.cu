@@ -40,6 +40,8 @@ synth_env_step_kernel(const float* obs_in, float* obs_out,   // may alias (in-pl
                       const int32_t* __restrict__ actions, int A, float* __restrict__ rewards,
                       uint8_t* __restrict__ dones, int32_t* tcount, long long N,
                       int D, uint32_t seed, float p_done) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int t = *tcount;     // L1 is invalidated at launch boundaries; only the last block writes it
     if (e < N * D) {
@@ -93,8 +95,8 @@ MLB_API int mlb_synth_env_step(void* stream, const float* obs_in, float* obs_out
                                int32_t* tcount, long long N, int D, uint32_t seed, float p_done) {
     MLB_REQUIRE(obs_in && obs_out && actions && rewards && dones && tcount && N > 0 && D > 0 && A > 0);
     cudaStream_t s = mlb_stream(stream);
-    synth_env_step_kernel<<<mlb_cdiv(N * D, 256), 256, 0, s>>>(obs_in, obs_out, actions, A, rewards,
-                                                               dones, tcount, N, D, seed, p_done);
-    MLB_CHECK_LAUNCH();
+    cudaError_t e = launch_pdl(synth_env_step_kernel, dim3(mlb_cdiv(N * D, 256)), dim3(256), 0, s, obs_in, obs_out, actions, A,
+                               rewards, dones, tcount, N, D, seed, p_done);
+    if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }

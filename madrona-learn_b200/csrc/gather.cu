@@ -69,6 +69,8 @@ struct LeafPack { LeafDev l[MAX_LEAVES]; int n; };
 
 __global__ void __launch_bounds__(256)
 gather_multi_kernel(const __grid_constant__ LeafPack P, const int32_t* __restrict__ idx, int Tp, int B, int M) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int s = blockIdx.y;
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,8 +132,9 @@ MLB_API int mlb_mb_gather_multi(void* stream, const mlb_gather_leaf* leaves_host
     long long gx = (max_total + 255) / 256;
     const long long cap = (long long)MLB_NUM_SMS * 8 / (Tp < 8 ? Tp : 8) + 1;
     if (gx > cap) gx = cap;
-    gather_multi_kernel<<<dim3((unsigned)gx, (unsigned)Tp), 256, 0, mlb_stream(stream)>>>(P, idx, Tp, (int)B, (int)M);
-    MLB_CHECK_LAUNCH();
+    cudaError_t e = launch_pdl(gather_multi_kernel, dim3((unsigned)gx, (unsigned)Tp), dim3(256), 0, mlb_stream(stream), P, idx,
+                               Tp, (int)B, (int)M);
+    if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }
 

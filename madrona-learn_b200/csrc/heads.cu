@@ -307,6 +307,8 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
                 unsigned int* __restrict__ ticket, mlb_ppo_stats* __restrict__ stats) {
     extern __shared__ float tile[];
     __shared__ WarpPartial wpart[32];
+    pdl_launch_dependents();
+    pdl_wait();
     const long long row0 = (long long)blockIdx.x * RB;
     const int ncols = vcol + cb.V;
     const int ts = ncols | 1;                 // odd tile stride
@@ -574,10 +576,11 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t s = mlb_stream(stream);
     LossPartial* part = reinterpret_cast<LossPartial*>(ws);
-    kern<<<g, (num_components + 1) * RB, smem, s>>>(head, ld, actions, old_log_probs, advantages,
+    cudaError_t le = launch_pdl(kern, dim3(g), dim3((num_components + 1) * RB), smem, s,
+        head, ld, actions, old_log_probs, advantages,
         returns, old_values, mb_weights, adv_mean_rstd, vn_params, L, rows, M, clip_coef,
         value_loss_coef, flags, vcol, d_head, d_bias, part, cb, 1.f / (float)rows,
         reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + mlb_ppo_loss_workspace(rows) - 16), stats);
-    MLB_CHECK_LAUNCH();
+    if (le != cudaSuccess) return (int)le;
     return MLB_OK;
 }

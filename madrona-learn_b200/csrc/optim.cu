@@ -179,6 +179,8 @@ optimizer_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float
                        double* __restrict__ gpart, double* __restrict__ segpart) {
     __shared__ double smd[32];
     __shared__ double bcast;
+    pdl_launch_dependents();
+    pdl_wait();
     const long long slice = (n + gridDim.x - 1) / gridDim.x;
     const long long lo = (long long)blockIdx.x * slice, hi = min(n, lo + slice);
     // ---- A: global gradient norm --------------------------------------------------------
@@ -347,10 +349,10 @@ MLB_API int mlb_optimizer_step_fused(void* stream, float* params, const float* g
     if (gsz < 1) gsz = 1;
     double* gpart = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 15) & ~uintptr_t(15));
     double* segpart = gpart + MLB_NUM_SMS;
-    optimizer_fused_kernel<<<(unsigned)gsz, FO_BLOCK, 0, mlb_stream(stream)>>>(
+    cudaError_t e = launch_pdl(optimizer_fused_kernel, dim3((unsigned)gsz), dim3(FO_BLOCK), 0, mlb_stream(stream),
         params, grads, m, v, n, segments_dev, num_segments, copies_dev, step, grad_sumsq, have_sumsq, lr, b1, b2,
         eps, max_grad_norm, grad_scale, sync_state, gpart, segpart);
-    MLB_CHECK_LAUNCH();
+    if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }
 

@@ -56,6 +56,7 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
                       int deterministic, int32_t* __restrict__ actions, float* __restrict__ log_probs,
                       float* __restrict__ values, float* __restrict__ head_out, int PR_STAGES) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_launch_dependents();
     uint8_t* smem = align_smem_1024(smem_raw);
     const int H = a.H, NH = a.NH, L = a.L, D = a.D;
     const int act_panels = (H > D ? H : D + 63) / 64;                 // panels of [128 x 64] bf16
@@ -96,6 +97,7 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // PRNG key chain (ml/rollouts.py:878-880): (prng_key, step_key) = split(prng_key);
         // policy_key = split(step_key, 1)[0].  Every CTA derives it; CTA 0 publishes the new key.
+        pdl_wait();                              // the key was advanced by the previous step's kernel
         if (!deterministic) {
             const uint32_t k0 = key_in[0], k1 = key_in[1];
             uint32_t n0, n1, s0, s1, p0, p1;
@@ -114,6 +116,7 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    pdl_wait();                                  // observations / stores below belong to this step
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -389,9 +392,9 @@ MLB_API int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* d, const 
     if (smem > 227 * 1024) return MLB_EINVAL;
     cudaError_t e = cudaFuncSetAttribute(policy_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    policy_rollout_kernel<<<mlb_cdiv(rows, BM), PR_THREADS, smem, mlb_stream(stream)>>>(
+    e = launch_pdl(policy_rollout_kernel, dim3(mlb_cdiv(rows, BM)), dim3(PR_THREADS), smem, mlb_stream(stream),
         maps, a, obs, obs_store, rows, key_in, key_out, partitionable, deterministic, actions, log_probs,
         values, head_out, stages);
-    MLB_CHECK_LAUNCH();
+    if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }

@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(256)
 post_step_kernel(const float* __restrict__ r, const uint8_t* __restrict__ d, float* __restrict__ rs,
                  uint8_t* __restrict__ ds, float* __restrict__ er, float* __restrict__ trace,
                  long long N, float gamma) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const float ri = r[i];
@@ -388,9 +390,9 @@ MLB_API int mlb_post_step_store_f32(void* stream, const float* rewards, const ui
                                     float* trace, long long N, float gamma) {
     MLB_REQUIRE(rewards && dones && reward_slab && done_slab && env_returns && N >= 0);
     if (N == 0) return MLB_OK;
-    post_step_kernel<<<mlb_cdiv(N, 256), 256, 0, mlb_stream(stream)>>>(rewards, dones, reward_slab, done_slab,
-                                                                       env_returns, trace, N, gamma);
-    MLB_CHECK_LAUNCH();
+    cudaError_t e = launch_pdl(post_step_kernel, dim3(mlb_cdiv(N, 256)), dim3(256), 0, mlb_stream(stream), rewards, dones,
+                               reward_slab, done_slab, env_returns, trace, N, gamma);
+    if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }
 

@@ -164,15 +164,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// Programmatic dependent launch: a kernel launched with launch_pdl() may start (prologue: barrier
-// init, TMEM allocation, tensor-map prefetch, resident-weight load) while its predecessor in the
-// stream is still draining its last tiles; pdl_wait() blocks until the predecessor has completed
-// and flushed, and must precede every access to data the predecessor (or anything before it)
-// produced.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as every
-// CTA of this grid has started.  Both are no-ops for a normally launched kernel.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // ------------------------------------------------------------------------------------------
 // host side: tensor maps through the driver entry point (no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------
@@ -206,27 +197,6 @@ inline int make_map(CUtensorMap* map, const void* base, long long inner, long lo
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? MLB_OK : MLB_EINVAL;
-}
-
-inline bool pdl_enabled() {
-    static const bool on = [] { const char* v = getenv("MLB_PDL"); return !(v && v[0] == '0'); }();
-    return on;
-}
-
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                              Args&&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 }  // namespace tc
