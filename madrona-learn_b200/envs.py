@@ -50,26 +50,35 @@ class HostTraceEnv:
         self.device = torch.device(device)
         self.action_key, self.obs_key = action_key, obs_key
         g = torch.Generator().manual_seed(int(seed))
-        pin = lambda t: t.pin_memory()
-        self.h_obs = pin(torch.randn(self.T + 1, self.N, self.D, generator=g))
-        self.h_rew = pin(torch.randn(self.T, self.N, 1, generator=g) * 0.1)
-        self.h_done = pin((torch.rand(self.T, self.N, 1, generator=g) < p_done).to(torch.uint8))
-        self.obs = torch.empty(self.N, self.D, dtype=torch.float32, device=self.device)
-        self.rewards = torch.empty(self.N, 1, dtype=torch.float32, device=self.device)
-        self.dones = torch.empty(self.N, 1, dtype=torch.uint8, device=self.device)
+        N, T, D = self.N, self.T, self.D
+        h_obs = torch.randn(T + 1, N, D, generator=g)
+        h_rew = torch.randn(T, N, 1, generator=g) * 0.1
+        h_done = (torch.rand(T, N, 1, generator=g) < p_done).to(torch.uint8)
+        # One pinned record per step, laid out as the simulator would export it:
+        #   [ next obs  N*D f32 | rewards  N f32 | dones  N u8 ]   -> ONE host->device copy per step
+        self._o_rew = N * D * 4
+        self._o_done = self._o_rew + N * 4
+        self.rec_bytes = self._o_done + N
+        self.h_rec = torch.empty(T, self.rec_bytes, dtype=torch.uint8).pin_memory()
+        self.h_rec[:, :self._o_rew] = h_obs[1:].reshape(T, -1).view(torch.uint8)
+        self.h_rec[:, self._o_rew:self._o_done] = h_rew.reshape(T, -1).view(torch.uint8)
+        self.h_rec[:, self._o_done:] = h_done.reshape(T, -1)
+        self.h_obs0 = h_obs[0].contiguous().pin_memory()
+        self.d_rec = torch.empty(self.rec_bytes, dtype=torch.uint8, device=self.device)
+        self.obs = self.d_rec[:self._o_rew].view(torch.float32).view(N, D)
+        self.rewards = self.d_rec[self._o_rew:self._o_done].view(torch.float32).view(N, 1)
+        self.dones = self.d_rec[self._o_done:].view(N, 1)
         self.t = 0
-        self.h2d_bytes_per_update = self.T * self.N * (4 * self.D + 4 + 1)
+        self.h2d_bytes_per_update = T * self.rec_bytes
 
     def init(self):
-        self.obs.copy_(self.h_obs[0], non_blocking=True)
+        self.obs.copy_(self.h_obs0, non_blocking=True)
         self.t = 0
         return {'state': None, 'obs': {self.obs_key: self.obs}}
 
     def step(self, step_input):
         t = self.t % self.T
-        self.rewards.copy_(self.h_rew[t], non_blocking=True)
-        self.dones.copy_(self.h_done[t], non_blocking=True)
-        self.obs.copy_(self.h_obs[t + 1], non_blocking=True)
+        self.d_rec.copy_(self.h_rec[t], non_blocking=True)
         self.t += 1
         return {'state': None, 'obs': {self.obs_key: self.obs}, 'rewards': self.rewards,
                 'dones': self.dones}

@@ -199,3 +199,21 @@ def test_checkpoint_roundtrip(mlb, tmp_path, monkeypatch):
     assert torch.equal(p, mgr.state.policy_states.program.params)
     assert torch.equal(k, mgr.state.train_states.update_prng_key)
     assert mgr.update_idx == 1
+
+
+def test_host_trace_env_delivers_the_trace(mlb):
+    """HostTraceEnv (the e2e arm's simulator stand-in): one pinned record per step, one H2D copy;
+    the device views must show exactly the host trace, step after step and across wrap-around."""
+    env = mlb.HostTraceEnv(96, 5, obs_dim=16, seed=3, device=DEV)
+    out = env.init()
+    torch.cuda.synchronize()
+    assert torch.equal(out['obs']['obs'].cpu(), env.h_obs0)
+    for t in range(7):
+        out = env.step({'actions': None})
+        torch.cuda.synchronize()
+        rec = env.h_rec[t % 5]
+        N, D = 96, 16
+        assert torch.equal(out['obs']['obs'].cpu().view(torch.uint8).flatten(), rec[:N * D * 4])
+        assert torch.equal(out['rewards'].cpu().view(torch.uint8).flatten(), rec[N * D * 4:N * D * 4 + N * 4])
+        assert torch.equal(out['dones'].cpu().flatten(), rec[N * D * 4 + N * 4:])
+    assert env.h2d_bytes_per_update == 5 * (N * D * 4 + N * 5)
