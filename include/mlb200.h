@@ -360,13 +360,15 @@ int mlb_renorm_segments(void* stream, float* params, const mlb_segment* segments
 /* the arena exactly in offset order (kind 0 for plain tensors; <= 32).  grad_sumsq: device      */
 /* double, computed here unless have_sumsq (the data-parallel all-reduce kernel already wrote     */
 /* it).  sync_state: device uint32[2], zero-initialised; ws of mlb_optimizer_fused_workspace().   */
+/* zero_after (may be NULL): an n-float arena (the local gradient arena) cleared at the end of    */
+/* the step, ready for the next minibatch's accumulation.                                         */
 size_t mlb_optimizer_fused_workspace(void);
 int mlb_optimizer_step_fused(void* stream, float* params, const float* grads, float* m, float* v,
                              long long n, const mlb_segment* segments_dev, int num_segments,
                              const mlb_bf16_copy* copies_dev, int32_t* step, double* grad_sumsq,
                              int have_sumsq, float lr, float b1, float b2, float eps,
                              float max_grad_norm, float grad_scale, uint32_t* sync_state, void* ws,
-                             size_t ws_bytes);
+                             size_t ws_bytes, float* zero_after);
 /* out[c] += sum_r x[r, c] for c < ncols (bias gradients of the heads) */
 int mlb_colsum_f32(void* stream, const float* x, long long rows, int ld, int ncols, float* out);
 

@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmlb200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                             ctypes.c_float, ctypes.c_size_t)
@@ -96,7 +96,7 @@ SIGNATURES = {
     'mlb_renorm_segments': (c_int, [P, P, P, c_int, P, P]),
     'mlb_optimizer_fused_workspace': (c_size_t, []),
     'mlb_optimizer_step_fused': (c_int, [P, P, P, P, P, c_ll, P, c_int, P, P, P, c_int, c_float, c_float, c_float,
-                                         c_float, c_float, c_float, P, P, c_size_t]),
+                                         c_float, c_float, c_float, P, P, c_size_t, P]),
     'mlb_colsum_f32': (c_int, [P, P, c_ll, c_int, c_int, P]),
     'mlb_synth_env_init': (c_int, [P, P, c_ll, c_int, ctypes.c_uint32, P]),
     'mlb_synth_env_step': (c_int, [P, P, P, P, c_int, P, P, P, c_ll, c_int, ctypes.c_uint32,

@@ -176,7 +176,7 @@ optimizer_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float
                        const mlb_bf16_copy* __restrict__ copies, int* __restrict__ step,
                        double* __restrict__ grad_sumsq, int have_sumsq, float lr, float b1, float b2,
                        float eps, float max_grad_norm, float grad_scale, uint32_t* __restrict__ sync_state,
-                       double* __restrict__ gpart, double* __restrict__ segpart) {
+                       double* __restrict__ gpart, double* __restrict__ segpart, float* __restrict__ zero_after) {
     __shared__ double smd[32];
     __shared__ double bcast;
     pdl_launch_dependents();
@@ -259,6 +259,9 @@ optimizer_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float
             }
         }
     }
+    // the gradient arena is consumed: clear this block's slice for the next minibatch's accumulation
+    if (zero_after)
+        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) zero_after[i] = 0.f;
     if (blockIdx.x == 0 && threadIdx.x == 0) *step = t;
 }
 
@@ -340,7 +343,7 @@ MLB_API int mlb_optimizer_step_fused(void* stream, float* params, const float* g
                                      const mlb_bf16_copy* copies_dev, int32_t* step, double* grad_sumsq,
                                      int have_sumsq, float lr, float b1, float b2, float eps,
                                      float max_grad_norm, float grad_scale, uint32_t* sync_state, void* ws,
-                                     size_t ws_bytes) {
+                                     size_t ws_bytes, float* zero_after) {
     MLB_REQUIRE(params && grads && m && v && step && grad_sumsq && segments_dev && sync_state && n > 0);
     MLB_REQUIRE(num_segments > 0 && num_segments <= FO_MAX_SEGS);
     if (!ws || ws_bytes < mlb_optimizer_fused_workspace()) return MLB_EWS;
@@ -351,7 +354,7 @@ MLB_API int mlb_optimizer_step_fused(void* stream, float* params, const float* g
     double* segpart = gpart + MLB_NUM_SMS;
     cudaError_t e = launch_pdl(optimizer_fused_kernel, dim3((unsigned)gsz), dim3(FO_BLOCK), 0, mlb_stream(stream),
         params, grads, m, v, n, segments_dev, num_segments, copies_dev, step, grad_sumsq, have_sumsq, lr, b1, b2,
-        eps, max_grad_norm, grad_scale, sync_state, gpart, segpart);
+        eps, max_grad_norm, grad_scale, sync_state, gpart, segpart, zero_after);
     if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }

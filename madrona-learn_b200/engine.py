@@ -308,6 +308,7 @@ class PolicyProgram:
             tiled.append(_lib.Segment(pos, self.num_params - pos, 0, 0.0)); tcopies.append(none)
         segs, copies = tiled, tcopies
         self._fused_opt = (len(segs) <= 32 and os.environ.get('MLB_FUSED_OPT', '1') != '0')
+        self._opt_zero = os.environ.get('MLB_OPT_ZERO', '1') != '0'
         if getattr(self, '_opt_sync', None) is None:
             self._opt_sync = torch.zeros(2, dtype=torch.int32, device=self.device)
             self._opt_ws = torch.zeros(_lib.lib().mlb_optimizer_fused_workspace(), dtype=torch.uint8,
@@ -546,6 +547,9 @@ class PolicyProgram:
         return self.head_views(self.grads)[1]
 
     def zero_grads(self):
+        if getattr(self, '_grads_clean', False):      # cleared by the fused optimiser kernel of the last step
+            self._grads_clean = False
+            return
         call('mlb_fill_zero', ptr(self.grads), c_size_t(self.num_params * 4))
 
     def adopt_grad_arena(self, arena):
@@ -565,7 +569,9 @@ class PolicyProgram:
                  c_ll(self.num_params), ptr(self.segments), c_int(self.num_segments), ptr(self.copies),
                  ptr(self.adam_step), ptr(self.grad_sumsq), c_int(0 if reduced is None else 1), c_float(lr),
                  c_float(b1), c_float(b2), c_float(eps), c_float(max_grad_norm), c_float(grad_scale),
-                 ptr(self._opt_sync), ptr(self._opt_ws), c_size_t(self._opt_ws.numel()))
+                 ptr(self._opt_sync), ptr(self._opt_ws), c_size_t(self._opt_ws.numel()),
+                 ptr(self.grads if self._opt_zero else None))
+            self._grads_clean = self._opt_zero    # the kernel cleared the arena behind itself
             return
         if reduced is None:
             call('mlb_sumsq_f32', ptr(grads), c_ll(self.num_params), ptr(self.grad_sumsq),
