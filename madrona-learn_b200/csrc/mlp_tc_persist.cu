@@ -212,6 +212,27 @@ __device__ __forceinline__ float warp_reduce_scatter32p(float (&v)[32], int lane
     return v[0];
 }
 
+// The same on packed bf16x2 pairs (one shuffle + one HADD2.BF16 per step carries TWO sums): used for
+// the per-feature dscale/dbias partials of a 32-row block, which are then accumulated in fp32 over
+// the 2048 blocks of a minibatch -- the bf16 rounding of a 32-term partial is far below the
+// bf16 quantisation of the operands that produced it.
+__device__ __forceinline__ uint32_t warp_reduce_scatter32_bf2(uint32_t (&v)[32], int lane) {
+#pragma unroll
+    for (int b = 16; b >= 1; b >>= 1) {
+        const bool up = (lane & b) != 0;
+#pragma unroll
+        for (int j = 0; j < b; ++j) {
+            const uint32_t send = up ? v[j] : v[j + b];
+            const uint32_t keep = up ? v[j + b] : v[j];
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, send, b);
+            const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&keep),
+                                             *reinterpret_cast<const __nv_bfloat162*>(&got));
+            v[j] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+    }
+    return v[0];
+}
+
 // the four warps of one TMEM lane quadrant (one per column group) meet here
 __device__ __forceinline__ void quad_bar(int quad) { named_bar_sync(1 + quad, 128); }
 
@@ -450,7 +471,7 @@ dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 uint32_t r[32];
                 tmem_ld32(taddr + c, r);
                 const uint8_t* pan = ring + xs * 16384;
-                float gx[32], g[32];
+                uint32_t pk[32];                          // (du * xhat, du) as bf16x2
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint4 u = *reinterpret_cast<const uint4*>(pan + sw128(rt, hf * 4 + q));
@@ -470,8 +491,7 @@ dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const float dxh = du * sv[e];
                         m1 += dxh;
                         m2 = fmaf(dxh, xh, m2);
-                        gx[j] = du * xh;
-                        g[j] = du;
+                        pk[j] = pack_bf16(du * xh, du);
                         r[j] = __float_as_uint(dxh);     // pass 2 reads dxhat back instead of redoing the mask
                     }
                     tmem_st8_nowait(taddr + c + 8 * q, r[8 * q], r[8 * q + 1], r[8 * q + 2], r[8 * q + 3],
@@ -480,10 +500,9 @@ dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tmem_st_wait();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p.bars.xh_empty[xs]);       // this warp is done with the panel
-                const float csum = warp_reduce_scatter32p(gx, lane);
-                const float bsum = warp_reduce_scatter32p(g, lane);
-                atomicAdd(&cs[c + lane], csum);
-                atomicAdd(&cb[c + lane], bsum);
+                const uint32_t cb2 = warp_reduce_scatter32_bf2(pk, lane);
+                atomicAdd(&cs[c + lane], bf16lo(cb2));
+                atomicAdd(&cb[c + lane], bf16hi(cb2));
             }
             exchange2(part, buf, grp, rt, quad, m1, m2);
             const float c1 = rstd * m1 * invH;               // dz = rstd*dxhat - rstd*m1 - xhat*(rstd*m2)
