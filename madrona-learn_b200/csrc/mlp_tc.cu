@@ -85,7 +85,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_wait_spin(&empty_bar[s], ph ^ 1);
                 uint8_t* sa = smem + s * L::STAGE_BYTES;
                 uint8_t* sb = sa + L::A_BYTES;
                 mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
@@ -116,7 +116,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait_spin(&full_bar[s], ph);
                 tcgen05_fence_after();
                 const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
                 const uint32_t sb = sa + L::A_BYTES;
@@ -223,7 +223,10 @@ int dispatch_tc(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, vo
         return launch_tc<BN_, ST_, A_MN, B_MN, EPI_ATOMIC>(s, tA, tB, C, bias, ldc, M, N, K, splitk);                    \
     } while (0)
     if (bn == 64) GO(64, 4);
-    if (bn == 128) GO(128, 4);
+    if (bn == 128) {
+        if (epi == EPI_ATOMIC) return launch_tc<128, 6, A_MN, B_MN, EPI_ATOMIC>(s, tA, tB, C, bias, ldc, M, N, K, splitk);
+        GO(128, 4);
+    }
     GO(256, 3);
 #undef GO
 }
