@@ -48,6 +48,9 @@ def _worker(rank, world, port, out_dir):
     with pytest.raises(ValueError):
         ctx.shard_worlds(63)
     assert ctx.rank_seed(7) != DistContext.rank_seed(type('X', (), {'rank': rank + 1})(), 7)
+    # the fused NVLink all-reduce is an NCCL-only fast path: under gloo it must decline cleanly
+    # (nothing allocated, the program's gradient arena untouched) and leave the collective path
+    assert ctx.enable_fused_allreduce(object()) is False and ctx.fused is False
 
     rng = np.random.default_rng(0)                       # same stream on both ranks
     T, M, D = 4, 16, 6
