@@ -61,6 +61,12 @@ class PolicyTrainState:                                # ml/train_state.py:85-13
         return ks[0], self
 
 
+def _tree_to_host(t):
+    if isinstance(t, dict):
+        return {k: _tree_to_host(v) for k, v in t.items()}
+    return t.detach().cpu().contiguous().numpy()
+
+
 @dataclass
 class TrainStateManager:                               # ml/train_state.py:139-304
     policy_states: PolicyState
@@ -79,7 +85,10 @@ class TrainStateManager:                               # ml/train_state.py:139-3
         prog = ps.program
         ckpt = {
             'next_update': int(next_update),
-            'policy_states': {'params': prog.params.cpu(),
+            # 'params': the flax parameter tree of the reference (ml/train_state.py:34-40) as host
+            # arrays -- what a reference-side loader expects; 'params_flat': our arena (what load() uses)
+            'policy_states': {'params': _tree_to_host(prog.param_tree()),
+                              'params_flat': prog.params.cpu(),
                               'obs_preprocess_state': ps.obs_preprocess_state},
             'train_states': {'opt_state': {'m': prog.adam_m.cpu(), 'v': prog.adam_v.cpu(),
                                            'count': prog.adam_step.cpu()},
@@ -97,7 +106,7 @@ class TrainStateManager:                               # ml/train_state.py:139-3
         ckpt = torch.load(path, map_location='cpu', weights_only=False)
         ps, ts = self.policy_states, self.train_states
         prog = ps.program
-        prog.params.copy_(ckpt['policy_states']['params'])
+        prog.params.copy_(ckpt['policy_states']['params_flat'])
         prog.adam_m.copy_(ckpt['train_states']['opt_state']['m'])
         prog.adam_v.copy_(ckpt['train_states']['opt_state']['v'])
         prog.adam_step.copy_(ckpt['train_states']['opt_state']['count'])

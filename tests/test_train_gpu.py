@@ -217,3 +217,35 @@ def test_host_trace_env_delivers_the_trace(mlb):
         assert torch.equal(out['rewards'].cpu().view(torch.uint8).flatten(), rec[N * D * 4:N * D * 4 + N * 4])
         assert torch.equal(out['dones'].cpu().flatten(), rec[N * D * 4 + N * 4:])
     assert env.h2d_bytes_per_update == 5 * (N * D * 4 + N * 5)
+
+
+def test_checkpoint_roundtrip_and_reference_key_tree(mlb, tmp_path):
+    """TrainStateManager.save / load (ml/train_state.py:145-196): top-level keys of the reference's
+    checkpoint dict, the flax parameter key tree, and a bit-exact restore into a fresh manager via
+    init_training(restore_ckpt=...)."""
+    mgr, cfg, env = _make(mlb, N=64, T=8, M=32, E=1)
+    for _ in range(2):
+        mgr.update_iter()
+    mgr.save_ckpt(str(tmp_path / 'ckpt'))                     # -> <dir>/<next_update>, like the reference
+    path = str(tmp_path / 'ckpt' / str(int(mgr.update_idx)))
+    ck = torch.load(path, map_location='cpu', weights_only=False)
+    assert set(ck) == {'next_update', 'policy_states', 'train_states', 'pbt_rng', 'user_state'}
+    tree = ck['policy_states']['params']
+    assert set(tree) == {'backbone', 'actor', 'critic'}
+    net = tree['backbone']['encoder']['net']
+    assert {'Dense_0', 'LayerNorm_0'} <= set(net) and set(net['LayerNorm_0']['impl']) == {'scale', 'bias'}
+    assert tree['actor']['impl']['kernel'].shape[1] == sum(BUCKETS) and isinstance(net['Dense_0']['kernel'], np.ndarray)
+    m = mlb
+    env2 = m.SyntheticVectorEnv(64, 16, len(BUCKETS), seed=11, p_done=-1.0, device=DEV)
+    policy = m.Policy(actor_critic=m.ActorCritic(
+        backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(net=m.models.MLP(64, 3))),
+        actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(BUCKETS)),
+        critic=m.models.DenseLayerCritic()))
+    new = m.init_training(DEV, cfg, env2.sim_fns(), policy, None, restore_ckpt=path, verbose=False)
+    a, b = mgr.state.policy_states.program, new.state.policy_states.program
+    for x, y in ((a.params, b.params), (a.adam_m, b.adam_m), (a.adam_v, b.adam_v), (a.adam_step, b.adam_step),
+                 (mgr.state.train_states.update_prng_key, new.state.train_states.update_prng_key)):
+        assert torch.equal(x, y)
+    assert new.update_idx == mgr.update_idx
+    new.update_iter()          # the restored manager trains (segment table / bf16 copies rebuilt)
+    torch.cuda.synchronize()
