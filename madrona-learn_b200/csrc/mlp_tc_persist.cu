@@ -254,6 +254,9 @@ __device__ __forceinline__ void wtile_put(uint8_t* wt, int lane, const uint32_t 
             make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 // coalesced write-out: instruction k covers rows 8k..8k+7, four lanes per row (64 contiguous bytes)
+// STREAM: the data is not read again soon (xhat is only needed by the backward pass): evict-first in
+// L2, so the activations the next layer reads right away stay resident.
+template <bool STREAM>
 __device__ __forceinline__ void wtile_store(const uint8_t* wt, int lane, __nv_bfloat16* gbase, int ld,
                                             int rows_valid) {
     const int c = lane & 3;
@@ -261,7 +264,10 @@ __device__ __forceinline__ void wtile_store(const uint8_t* wt, int lane, __nv_bf
     for (int k = 0; k < 4; ++k) {
         const int r = k * 8 + (lane >> 2);
         const uint4 v = *reinterpret_cast<const uint4*>(wt + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
-        if (r < rows_valid) *reinterpret_cast<uint4*>(gbase + (size_t)r * ld + c * 8) = v;
+        if (r < rows_valid) {
+            uint4* dst = reinterpret_cast<uint4*>(gbase + (size_t)r * ld + c * 8);
+            if (STREAM) __stcs(dst, v); else *dst = v;
+        }
     }
 }
 
@@ -339,12 +345,12 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __syncwarp();                                // earlier read-back of the tile is complete
                 wtile_put(wt, lane, yp);
                 __syncwarp();
-                wtile_store(wt, lane, Y + (size_t)(m0 + quad * 32) * HN + c, HN, (dbg & 1) ? 0 : rows_valid);
+                wtile_store<false>(wt, lane, Y + (size_t)(m0 + quad * 32) * HN + c, HN, (dbg & 1) ? 0 : rows_valid);
                 if (XH) {
                     __syncwarp();
                     wtile_put(wt, lane, xp);
                     __syncwarp();
-                    wtile_store(wt, lane, XH + (size_t)(m0 + quad * 32) * HN + c, HN, (dbg & 1) ? 0 : rows_valid);
+                    wtile_store<true>(wt, lane, XH + (size_t)(m0 + quad * 32) * HN + c, HN, (dbg & 1) ? 0 : rows_valid);
                 }
             }
             if (!released) {                                 // column group without chunks (HN < 128)
