@@ -40,8 +40,8 @@ __host__ __device__ inline PLayout p_layout(int K, int HN, int a_stages, int sta
     l.a_off = l.w_bytes;
     l.stage_off = l.a_off + a_stages * 16384;
     l.misc_off = l.stage_off + staging_bytes;
-    // misc: scale|bias (2*HN f32) + colsums (2*HN f32) + row partials [2][4][128][2] f32 + barriers (256 B)
-    l.total = l.misc_off + (4 * HN + 2048) * 4 + 256 + 1024;
+    // misc: scale|bias (2*HN f32) + colsums (2*HN f32) + row partials [2][4][128][2] f32 + barriers (512 B)
+    l.total = l.misc_off + (4 * HN + 2048) * 4 + 512 + 1024;
     return l;
 }
 
@@ -55,7 +55,7 @@ __device__ __forceinline__ PBars p_bars(uint8_t* misc_end) {
     b.full = reinterpret_cast<uint64_t*>(misc_end);
     b.empty = b.full + MAX_A_STAGES;
     b.w_bar = b.empty + MAX_A_STAGES;
-    b.acc_full = b.w_bar + 1;        // [2]
+    b.acc_full = b.w_bar + 4;        // w_bar[4]: one per resident-weight k-block; acc_full[2]
     b.acc_empty = b.acc_full + 2;    // [2]
     b.xh_full = b.acc_empty + 2;     // [4]
     b.xh_empty = b.xh_full + 4;      // [4]
@@ -104,7 +104,6 @@ __device__ __forceinline__ void p_mainloop(const CUtensorMap* tmA, const CUtenso
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(false, false, HN);
-            mbar_wait_spin(bars.w_bar, 0);
             int it = 0, i = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
                 const int buf = i & 1;
@@ -113,6 +112,7 @@ __device__ __forceinline__ void p_mainloop(const CUtensorMap* tmA, const CUtenso
                 const uint32_t d_tmem = tmem_base + buf * 256;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % A_STAGES;
+                    if (i == 0) mbar_wait_spin(&bars.w_bar[kb], 0);          // resident weights: first tile only
                     mbar_wait_spin(&bars.full[s], (it / A_STAGES) & 1);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + L.a_off + s * 16384);
@@ -151,16 +151,17 @@ __device__ __forceinline__ PState p_prologue(uint8_t* smem_raw, const CUtensorMa
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmB)) : "memory");
         for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(&p.bars.full[s], 1); mbar_init(&p.bars.empty[s], 1); }
-        mbar_init(p.bars.w_bar, 1);
+        for (int kb = 0; kb < 4; ++kb) mbar_init(&p.bars.w_bar[kb], 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&p.bars.acc_full[s], 1); mbar_init(&p.bars.acc_empty[s], 16); }
         for (int s = 0; s < 4; ++s) { mbar_init(&p.bars.xh_full[s], 1); mbar_init(&p.bars.xh_empty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // prime the pipeline before anything else in the prologue: resident W + the first ring fill
         const int num_kb = (K + BK - 1) / BK;
         const int num_tiles = (M + BM - 1) / BM;
-        mbar_expect_tx(p.bars.w_bar, (uint32_t)p.L.w_bytes);
-        for (int kb = 0; kb < num_kb; ++kb)
-            tma_load_2d(tmB, p.bars.w_bar, p.smem + kb * HN * 128, kb * BK, 0);
+        for (int kb = 0; kb < num_kb; ++kb) {       // one barrier per k-block: the first MMA needs only W[kb = 0]
+            mbar_expect_tx(&p.bars.w_bar[kb], (uint32_t)(HN * 128));
+            tma_load_2d(tmB, &p.bars.w_bar[kb], p.smem + kb * HN * 128, kb * BK, 0);
+        }
         const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         const int prime = my_tiles * num_kb < a_stages ? my_tiles * num_kb : a_stages;
         pdl_wait();                                  // the activations come from the preceding kernel
