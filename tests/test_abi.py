@@ -37,3 +37,17 @@ def test_no_cpu_fallback(mlb):
     from madrona_learn_b200 import _lib
     with pytest.raises(_lib.MLBError):
         _lib.ptr(torch.zeros(4))
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary must be consumable from C (cgo / JNI / ctypes style bindings): the
+    header compiles as C99 with nothing but <stddef.h>/<stdint.h>."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'mlb200.h')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c', hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
