@@ -14,7 +14,9 @@
  *     Scratch is caller-provided (`ws`, sized by the matching mlb_*_workspace()).
  *   - Returns 0 on success, a positive cudaError_t if the launch failed, or a negative
  *     MLB_E* code for invalid arguments.  Never throws, never prints.
- *   - Re-entrant; no mutable global state; callable from any host thread.
+ *   - Re-entrant; no mutable global state (the MLB_* environment switches documented in
+ *     README.md are read once, on first use, and are immutable afterwards); callable from
+ *     any host thread.
  *   - Built for sm_100a only (nvcc -gencode arch=compute_100a,code=sm_100a).
  */
 #ifndef MLB200_H_

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const float* __restrict__ scale, const float* __restrict__ bias,
                    __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ XH,
-                   float* __restrict__ rstd_out, int M, int K, int HN, int a_stages, int dbg) {
+                   float* __restrict__ rstd_out, int M, int K, int HN, int a_stages) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (M + BM - 1) / BM;
@@ -305,7 +305,6 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tcgen05_fence_after();
             // pass 1: row statistics over this column group's chunks
             float sum = 0.f, sq = 0.f;
-            if (!(dbg & 4))
             for (int ch = grp; ch < nchunks; ch += 4) {
                 uint32_t r[32];
                 tmem_ld32(taddr + ch * 32, r);
@@ -318,7 +317,6 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (grp == 0 && m0 + rt < M && rstd_out) rstd_out[m0 + rt] = rstd;
             // pass 2: normalise, scale/bias, ReLU -> bf16, transposed through the warp tile
             bool released = false;
-            if (!(dbg & 2))
             for (int ch = grp; ch < nchunks; ch += 4) {
                 const int c = ch * 32;
                 uint32_t r[32];
@@ -346,12 +344,12 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __syncwarp();                                // earlier read-back of the tile is complete
                 wtile_put(wt, lane, yp);
                 __syncwarp();
-                wtile_store<false>(wt, lane, Y + (size_t)(m0 + quad * 32) * HN + c, HN, (dbg & 1) ? 0 : rows_valid);
+                wtile_store<false>(wt, lane, Y + (size_t)(m0 + quad * 32) * HN + c, HN, rows_valid);
                 if (XH) {
                     __syncwarp();
                     wtile_put(wt, lane, xp);
                     __syncwarp();
-                    wtile_store<true>(wt, lane, XH + (size_t)(m0 + quad * 32) * HN + c, HN, (dbg & 1) ? 0 : rows_valid);
+                    wtile_store<true>(wt, lane, XH + (size_t)(m0 + quad * 32) * HN + c, HN, rows_valid);
                 }
             }
             if (!released) {                                 // column group without chunks (HN < 128)
@@ -620,9 +618,8 @@ int launch_fwd_persist(cudaStream_t st, const void* X, const void* Wt, const flo
     if (e != cudaSuccess) return (int)e;
     const int tiles = (M + BM - 1) / BM;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    static const int dbg = [] { const char* v = getenv("MLB_TC_DEBUG"); return v ? atoi(v) : 0; }();
     e = launch_pdl(fwd_persist_kernel, dim3(grid), dim3(P_THREADS), smem, st, tA, tB, scale, bias,
-                   static_cast<__nv_bfloat16*>(Y), static_cast<__nv_bfloat16*>(XH), rstd, M, K, HN, a_stages, dbg);
+                   static_cast<__nv_bfloat16*>(Y), static_cast<__nv_bfloat16*>(XH), rstd, M, K, HN, a_stages);
     if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }

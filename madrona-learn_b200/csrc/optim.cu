@@ -179,7 +179,11 @@ optimizer_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float
                        double* __restrict__ gpart, double* __restrict__ segpart, float* __restrict__ zero_after) {
     __shared__ double smd[32];
     __shared__ double bcast;
-    pdl_launch_dependents();
+    // No early launch_dependents here: this kernel rewrites the parameters and their bf16 operand
+    // copies, which the tensor-core kernels further down the chain load in their PRE-wait prologues
+    // (resident-weight TMA, LayerNorm scale/bias).  The trigger is issued at the very end, after the
+    // last parameter write has been fenced, so no successor -- direct or transitive -- can start
+    // before the new weights are in place.
     pdl_wait();
     const long long slice = (n + gridDim.x - 1) / gridDim.x;
     const long long lo = (long long)blockIdx.x * slice, hi = min(n, lo + slice);
@@ -263,6 +267,8 @@ optimizer_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float
     if (zero_after)
         for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) zero_after[i] = 0.f;
     if (blockIdx.x == 0 && threadIdx.x == 0) *step = t;
+    __threadfence();
+    pdl_launch_dependents();
 }
 
 __global__ void __launch_bounds__(256)

@@ -302,7 +302,18 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         """ml/rollouts.py:716-826."""
         st, cfg = self.store, self._train_cfg
         vn_state = train_states.value_normalizer_state if train_states.value_normalizer is not None else None
-        hooked, user_state = finish_hook(st, self.bootstrap, st['values'], self.bootstrap, user_state)
+        # ml/rollouts.py:726-745: with a value normaliser the hook (and the 'Bootstrap Values'
+        # metric, :810) see value_normalizer.invert(...) of the stored values / bootstrap
+        unnorm_values, unnorm_boot = st['values'], self.bootstrap
+        if vn_state is not None:
+            if getattr(self, '_unnorm_boot', None) is None:
+                self._unnorm_boot = torch.empty_like(self.bootstrap)
+                self._unnorm_values = torch.empty_like(st['values'])
+            unnorm_boot = K.ema_invert(vn_state, 1, self.bootstrap, self._unnorm_boot)
+            hook_fn = getattr(finish_hook, '__func__', finish_hook)
+            if getattr(hook_fn, '__qualname__', '') != 'TrainHooks.finish_rollouts':
+                unnorm_values = K.ema_invert(vn_state, 1, st['values'], self._unnorm_values)
+        hooked, user_state = finish_hook(st, self.bootstrap, unnorm_values, unnorm_boot, user_state)
         if hooked is not st:
             raise NotImplementedError('finish_rollouts must modify the rollout store in place')
         if self._use_advantages:
@@ -314,7 +325,7 @@ class RolloutManager:                   # ml/rollouts.py:373-826
             if vn_state is not None:
                 raise NotImplementedError('normalize_values with compute_advantages=False')
             compute_returns(cfg, st['rewards'], st['dones'], self.bootstrap, returns=st['returns'])
-        K.metric(self.bootstrap, metrics.slot('Bootstrap Values'), self._met_ws)
+        K.metric(unnorm_boot, metrics.slot('Bootstrap Values'), self._met_ws)
         K.metric(self.env_returns_trace, metrics.slot('Env Returns'), self._met_ws)
         data = RolloutData(st, self._num_bptt_chunks, self._num_bptt_steps, self._cfg.sim_batch_size)
         metrics = metrics_hook(metrics, data, user_state)

@@ -63,10 +63,22 @@ def _vn_to_oracle(t):
     dict(),                                                        # config 1: 32 worlds x 32 steps
     dict(N=48, T=24, C=3, M=36, E=2, normalize_values=True),       # BPTT chunks + value-norm EMA
     dict(N=64, T=8, M=16, E=3, clipv=True, huber=True, p_done=0.1),
+    # non-trivial value-normaliser state: the GAE input, the finish_rollouts hook arguments and
+    # the 'Bootstrap Values' metric are in UN-normalised units (ml/rollouts.py:726-745, 810)
+    dict(N=48, T=24, C=3, M=36, E=2, normalize_values=True, vn_init=(0.7, 2.5)),
 ])
 def test_update_iter_matches_oracle(mlb, kw, monkeypatch):
     monkeypatch.setenv('MLB_CUDA_GRAPH', '0')
+    kw = dict(kw)
+    vn_init = kw.pop('vn_init', None)
     mgr, cfg, env = _make(mlb, **kw)
+    if vn_init is not None:
+        mu, sigma = vn_init
+        corr = 1.0 - cfg.value_normalizer_decay ** 10
+        with torch.no_grad():
+            vs = mgr.state.train_states.value_normalizer_state
+            vs[:5] = torch.tensor([mu, 1.0 / sigma, sigma, mu * corr, sigma * sigma * corr], device=DEV)
+            vs[5:].view(torch.int32).fill_(10)
     prog = mgr.state.policy_states.program
     N, T, C = cfg.num_worlds, cfg.steps_per_update, cfg.num_bptt_chunks
     Tp, D, A = T // C, prog.obs_dim, len(BUCKETS)
@@ -249,3 +261,46 @@ def test_checkpoint_roundtrip_and_reference_key_tree(mlb, tmp_path):
     assert new.update_idx == mgr.update_idx
     new.update_iter()          # the restored manager trains (segment table / bf16 copies rebuilt)
     torch.cuda.synchronize()
+
+
+def test_finish_rollouts_hook_sees_unnormalized_values(mlb, monkeypatch):
+    """with normalize_values the hook receives value_normalizer.invert(values / bootstrap)
+    (ml/rollouts.py:726-745), not the stored normalised critic outputs."""
+    import dataclasses
+    monkeypatch.setenv('MLB_CUDA_GRAPH', '0')
+    m = mlb
+    seen = {}
+
+    @dataclasses.dataclass(frozen=True)
+    class Hooks(m.TrainHooks):
+        def finish_rollouts(self, rollouts, bootstrap_values, unnormalized_values,
+                            unnormalized_bootstrap_values, user_state):
+            seen['v'] = unnormalized_values.clone()
+            seen['b'] = unnormalized_bootstrap_values.clone()
+            seen['raw_v'] = rollouts['values'].clone()
+            seen['raw_b'] = bootstrap_values.clone()
+            return rollouts, user_state
+
+    env = m.SyntheticVectorEnv(32, 16, len(BUCKETS), seed=11, device=DEV)
+    policy = m.Policy(actor_critic=m.ActorCritic(
+        backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(net=m.models.MLP(64, 2))),
+        actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(BUCKETS)),
+        critic=m.models.DenseLayerCritic()))
+    cfg = m.TrainConfig(
+        num_worlds=32, num_agents_per_world=1, num_updates=10,
+        actions={'act': m.DiscreteActionsConfig(BUCKETS)}, steps_per_update=8, lr=3e-4,
+        algo=m.PPOConfig(num_epochs=1, minibatch_size=16, clip_coef=0.2, value_loss_coef=0.5,
+                         entropy_coef={'act': 0.01}, max_grad_norm=0.5),
+        num_bptt_chunks=1, gamma=0.99, seed=5, metrics_buffer_size=4, gae_lambda=0.95,
+        dreamer_v3_critic=False, normalize_values=True)
+    mgr = m.init_training(DEV, cfg, env.sim_fns(), policy, None, user_hooks=Hooks(), verbose=False)
+    with torch.no_grad():
+        vs = mgr.state.train_states.value_normalizer_state
+        vs[0], vs[1], vs[2] = -1.25, 1.0 / 3.0, 3.0
+    mgr.update_iter()
+    torch.cuda.synchronize()
+    f = np.float32
+    np.testing.assert_allclose(seen['v'].cpu().numpy(), seen['raw_v'].cpu().numpy() * f(3.0) + f(-1.25), rtol=1e-6)
+    np.testing.assert_allclose(seen['b'].cpu().numpy(), seen['raw_b'].cpu().numpy() * f(3.0) + f(-1.25), rtol=1e-6)
+    lat = mgr.metrics.latest()
+    np.testing.assert_allclose(lat['Bootstrap Values'].mean, seen['b'].mean().item(), rtol=1e-5)
