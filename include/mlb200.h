@@ -172,6 +172,15 @@ typedef struct mlb_gather_leaf {
 } mlb_gather_leaf;
 int mlb_mb_gather_multi(void* stream, const mlb_gather_leaf* leaves_host, int num_leaves,
                         const int32_t* idx, int C, int Tp, long long B, long long M);
+/* Index-exact data-parallel variant (the world-sharded analogue of ml/ppo.py:437-466):  */
+/* idx holds GLOBAL trajectory ids j = c*(world*B) + r*B + b; rank r's stores are reachable through */
+/* peer_stores_host[r*num_leaves + leaf] (HOST array of device pointers mapped over NVLink, e.g.     */
+/* symmetric memory; rank order; includes this rank's own stores).  leaves_host[i].store is ignored. */
+/* Up to 8 ranks.  out[s, m, :] = store_owner[c, s, b, :]: bit-identical to mlb_mb_gather_multi on    */
+/* the concatenated [C, T', world*B, row] store.                                                     */
+int mlb_mb_gather_multi_peer(void* stream, const mlb_gather_leaf* leaves_host, int num_leaves,
+                             const void* const* peer_stores_host, int world, const int32_t* idx,
+                             int C, int Tp, long long B, long long M);
 
 /* ------------------------------------------------------------------------------------ */
 /* K6/K9 (fp32 path): Dense layers and their transposes.                                  */

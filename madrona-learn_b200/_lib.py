@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmlb200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                             ctypes.c_float, ctypes.c_size_t)
@@ -77,6 +77,7 @@ SIGNATURES = {
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
     'mlb_mb_gather_multi': (c_int, [P, P, c_int, P, c_int, c_int, c_ll, c_ll]),
+    'mlb_mb_gather_multi_peer': (c_int, [P, P, c_int, P, c_int, P, c_int, c_int, c_ll, c_ll]),
     'mlb_reorder_chunks_workspace': (c_size_t, [c_ll, c_int]),
     'mlb_reorder_chunks': (c_int, [P, P, c_ll, c_int, c_int, c_ll, P, P, P, c_size_t]),
     'mlb_gather_rows_clip': (c_int, [P, P, P, P, c_ll, c_ll, c_ll]),

@@ -103,6 +103,54 @@ gather_multi_kernel(const __grid_constant__ LeafPack P, const int32_t* __restric
     }
 }
 
+// Index-exact data-parallel minibatch gather (SURVEY 8e "index-exact"): idx holds GLOBAL trajectory
+// ids j = c*Bg + bg of the world-sharded run (Bg = world * B); worlds [r*B, (r+1)*B) live in rank r's
+// store, which is mapped into this process over NVLink (symmetric memory).  Rows owned by a peer
+// are fetched by plain peer loads: >= 256-byte observation rows, so the NVLink requests are
+// full-width.  Same addressing as gather_multi_kernel once (owner, c, b) are known.
+constexpr int MAX_PEERS = 8;
+struct PeerStores { const uint8_t* base[MAX_PEERS][MAX_LEAVES]; int world; };
+
+__global__ void __launch_bounds__(256)
+gather_multi_peer_kernel(const __grid_constant__ LeafPack P, const __grid_constant__ PeerStores S,
+                         const int32_t* __restrict__ idx, int Tp, int B, int M) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int s = blockIdx.y;
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Bg = B * S.world;
+    for (int li = 0; li < P.n; ++li) {
+        const LeafDev& L = P.l[li];
+        const int rv = L.row_vecs, total = M * rv;
+        for (int e = t0; e < total; e += stride) {
+            const int m = e / rv, k = e - m * rv;
+            const int j = idx[m];
+            const int c = j / Bg, bg = j - c * Bg;
+            const int owner = bg / B, b = bg - owner * B;
+            const uint8_t* store = S.base[owner][li];
+            const long long src = (((long long)c * Tp + s) * B + b) * rv + k;
+            const long long dst = ((long long)s * M + m) * rv + k;
+            switch (L.vec_bytes) {
+                case 16: {
+                    const uint4 v = *(reinterpret_cast<const uint4*>(store) + src);
+                    if (L.out) reinterpret_cast<uint4*>(L.out)[dst] = v;
+                    if (L.out_bf16) {
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(v.x), __uint_as_float(v.y));
+                        const __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(v.z), __uint_as_float(v.w));
+                        reinterpret_cast<uint2*>(L.out_bf16)[dst] =
+                            make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                    }
+                    break;
+                }
+                case 8: reinterpret_cast<uint2*>(L.out)[dst] = *(reinterpret_cast<const uint2*>(store) + src); break;
+                case 4: reinterpret_cast<uint32_t*>(L.out)[dst] = *(reinterpret_cast<const uint32_t*>(store) + src); break;
+                default: L.out[dst] = store[src]; break;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 MLB_API int mlb_mb_gather_multi(void* stream, const mlb_gather_leaf* leaves_host, int num_leaves,
@@ -134,6 +182,48 @@ MLB_API int mlb_mb_gather_multi(void* stream, const mlb_gather_leaf* leaves_host
     if (gx > cap) gx = cap;
     cudaError_t e = launch_pdl(gather_multi_kernel, dim3((unsigned)gx, (unsigned)Tp), dim3(256), 0, mlb_stream(stream), P, idx,
                                Tp, (int)B, (int)M);
+    if (e != cudaSuccess) return (int)e;
+    return MLB_OK;
+}
+
+MLB_API int mlb_mb_gather_multi_peer(void* stream, const mlb_gather_leaf* leaves_host, int num_leaves,
+                                     const void* const* peer_stores_host, int world, const int32_t* idx,
+                                     int C, int Tp, long long B, long long M) {
+    if (M == 0 || num_leaves == 0) return MLB_OK;
+    MLB_REQUIRE(leaves_host && idx && peer_stores_host && num_leaves > 0 && num_leaves <= MAX_LEAVES && C > 0 &&
+                Tp > 0 && Tp <= 65535 && B > 0 && M > 0 && world >= 1 && world <= MAX_PEERS &&
+                (long long)C * B * world < (1ll << 31));
+    LeafPack P;
+    PeerStores S;
+    P.n = num_leaves;
+    S.world = world;
+    long long max_total = 0;
+    for (int i = 0; i < num_leaves; ++i) {
+        const mlb_gather_leaf& h = leaves_host[i];
+        MLB_REQUIRE((h.out || h.out_bf16) && h.row_bytes > 0);
+        uintptr_t a = reinterpret_cast<uintptr_t>(h.out);
+        for (int r = 0; r < world; ++r) {
+            const void* st = peer_stores_host[(size_t)r * num_leaves + i];
+            MLB_REQUIRE(st);
+            a |= reinterpret_cast<uintptr_t>(st);
+            S.base[r][i] = static_cast<const uint8_t*>(st);
+        }
+        int vb = 1;
+        if (h.row_bytes % 16 == 0 && (a & 15) == 0) vb = 16;
+        else if (h.row_bytes % 8 == 0 && (a & 7) == 0) vb = 8;
+        else if (h.row_bytes % 4 == 0 && (a & 3) == 0) vb = 4;
+        MLB_REQUIRE(!h.out_bf16 || (vb == 16 && (reinterpret_cast<uintptr_t>(h.out_bf16) & 7) == 0));
+        MLB_REQUIRE(h.out || vb == 16);
+        const long long rv = h.row_bytes / vb;
+        MLB_REQUIRE(M * rv < (1ll << 31));
+        P.l[i] = LeafDev{nullptr, static_cast<uint8_t*>(h.out), static_cast<__nv_bfloat16*>(h.out_bf16), (int)rv, vb};
+        if (M * rv > max_total) max_total = M * rv;
+    }
+    long long gx = (max_total + 255) / 256;
+    const long long cap = (long long)MLB_NUM_SMS * 8 / (Tp < 8 ? Tp : 8) + 1;
+    if (gx > cap) gx = cap;
+    cudaError_t e = launch_pdl(gather_multi_peer_kernel, dim3((unsigned)gx, (unsigned)Tp), dim3(256), 0,
+                               mlb_stream(stream), P, S, idx, Tp, (int)B, (int)M);
     if (e != cudaSuccess) return (int)e;
     return MLB_OK;
 }

@@ -234,6 +234,20 @@ def mb_gather_multi(leaves, idx, C, Tp, B):
          c_ll(idx.numel()))
 
 
+def mb_gather_multi_peer(leaves, peer_table, world, idx, C, Tp, B):
+    """mlb_mb_gather_multi_peer.  leaves: list of (local store [C, T', 1, B, *leaf] (shape/dtype only),
+    out, out_bf16); peer_table: HOST void*[world][len(leaves)] (DistContext.peer_store_table)."""
+    arr = (_lib.GatherLeaf * len(leaves))()
+    for i, (store, out, out_bf16) in enumerate(leaves):
+        row_elems = store.numel() // (C * Tp * B)       # P = 1: [C, T', 1, B, *leaf] (or [C, 1, B, *] with Tp = 1)
+        arr[i].store = None
+        arr[i].out = out.data_ptr() if out is not None else None
+        arr[i].out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+        arr[i].row_bytes = row_elems * store.element_size()
+    call('mlb_mb_gather_multi_peer', arr, c_int(len(leaves)), peer_table, c_int(world), ptr(idx), c_int(C),
+         c_int(Tp), c_ll(B), c_ll(idx.numel()))
+
+
 def mb_gather_rnn(store, idx, C, B, out=None):
     M = idx.numel()
     leaf = store.shape[2:]

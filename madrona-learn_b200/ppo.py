@@ -101,11 +101,20 @@ class _PPOWorkspace:
         assert J % M == 0, 'num trajectories must be divisible by minibatch_size (ml/ppo.py:439)'
         self.E, self.M, self.J, self.nmb, self.rows = E, M, J, J // M, Tp * M
         e = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
-        self.perm = e(E, J, dtype=torch.int32)
-        self.perm_ws = torch.empty(K.lib().mlb_ppo_permutations_workspace(E, J) + 16,
+        # index-exact data-parallel mode (parallel.py): ONE permutation of the global trajectory ids,
+        # identical on every rank; this rank trains on its M-wide slice of every (world*M)-wide minibatch
+        self.index_exact = dist_ctx is not None and getattr(dist_ctx, 'perm_mode', 'fast') == 'index_exact'
+        R = dist_ctx.world_size if self.index_exact else 1
+        self.Jp = J * R                                  # length of one permutation
+        self.Mp = M * R                                  # minibatch width in the permutation
+        self.perm = e(E, self.Jp, dtype=torch.int32)
+        self.perm_ws = torch.empty(K.lib().mlb_ppo_permutations_workspace(E, self.Jp) + 16,
                                    dtype=torch.uint8, device=dev)
         self.tm_adv = e(J, 2, dtype=torch.float64)
         self.tm_ret = e(J, 2, dtype=torch.float64)
+        if self.index_exact:
+            self.tm_adv_g = e(self.Jp, 2, dtype=torch.float64)
+            self.tm_ret_g = e(self.Jp, 2, dtype=torch.float64)
         self.mb_adv = e(E * self.nmb, 4)
         self.mb_ret = e(E * self.nmb, 4)
         self.vn_params = e(E * self.nmb, 4)
@@ -150,7 +159,7 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
     hp = train_state.hyper_params
 
     with profile('Compute Minibatch Indices'):
-        K.ppo_permutations(train_state.update_prng_key, E, J, partitionable, ws.perm, ws.perm_ws)
+        K.ppo_permutations(train_state.update_prng_key, E, ws.Jp, partitionable, ws.perm, ws.perm_ws)
 
     # per-minibatch statistics for ALL minibatches of the update (App. C.1)
     score_key = 'advantages' if cfg.compute_advantages else 'returns'
@@ -163,6 +172,23 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
         if vn is not None:
             K.traj_moments(st['returns'].view(T, N), C, ws.tm_ret)
             K.mb_moments(ws.tm_ret, ws.perm, M, Tp, 0.0, ws.mb_ret)
+    elif ws.index_exact:
+        # per-trajectory moments are all-gathered into global trajectory order; every rank then
+        # evaluates the statistics of every GLOBAL minibatch itself (identical bits on all ranks).
+        # The collective doubles as the "all ranks finished GAE" point for the peer gathers below.
+        synced = False
+        if normalize_scores:
+            K.traj_moments(st[score_key].view(T, N), C, ws.tm_adv)
+            dist_ctx.allgather_traj_moments(ws.tm_adv, ws.tm_adv_g, C)
+            K.mb_moments(ws.tm_adv_g, ws.perm, ws.Mp, Tp, 1e-5, ws.mb_adv)
+            synced = True
+        if vn is not None:
+            K.traj_moments(st['returns'].view(T, N), C, ws.tm_ret)
+            dist_ctx.allgather_traj_moments(ws.tm_ret, ws.tm_ret_g, C)
+            K.mb_moments(ws.tm_ret_g, ws.perm, ws.Mp, Tp, 0.0, ws.mb_ret)
+            synced = True
+        if not synced:
+            dist_ctx.stream_barrier(prog.device)
     else:
         # raw (sum, sumsq) of every minibatch -> ONE all-reduce for the whole update
         Kmb = E * nmb
@@ -191,10 +217,27 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
     if prog.lstm is not None:
         keys.append('dones')
         seq = dict(Tp=Tp, M=M, ends=mb['dones'].view(Tp, M), c0=mb['rnn_start_c'], h0=mb['rnn_start_h'])
+    leaf_names = list(dict.fromkeys(keys))
+    if ws.index_exact and getattr(ws, 'peer_tab', None) is None:
+        ws.peer_tab = dist_ctx.peer_store_table(leaf_names)
+        ws.peer_tab_rnn = dist_ctx.peer_store_table(['rnn_start_c', 'rnn_start_h']) if seq is not None else None
+
     def gather(e, k):
+        if ws.index_exact:
+            # this rank's slice of the global minibatch; rows are fetched from their owners' stores
+            lo = k * ws.Mp + dist_ctx.rank * M
+            idx = ws.perm[e, lo:lo + M]
+            leaves = [(st[name], mb[name], tw['x'] if (name == 'obs' and prog.tc) else None)
+                      for name in leaf_names]
+            K.mb_gather_multi_peer(leaves, ws.peer_tab, dist_ctx.world_size, idx, C, Tp, B)
+            if seq is not None:
+                K.mb_gather_multi_peer([(st['rnn_start_c'], mb['rnn_start_c'], None),
+                                        (st['rnn_start_h'], mb['rnn_start_h'], None)],
+                                       ws.peer_tab_rnn, dist_ctx.world_size, idx, C, 1, B)
+            return
         idx = ws.perm[e, k * M:(k + 1) * M]
         leaves = []
-        for name in dict.fromkeys(keys):
+        for name in leaf_names:
             src = st[name][:, :, 0]
             leaves.append((src.view(torch.uint8) if src.dtype == torch.bool else src, mb[name],
                            tw['x'] if (name == 'obs' and prog.tc) else None))

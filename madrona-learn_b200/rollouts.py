@@ -145,7 +145,7 @@ class RolloutData:                      # ml/rollouts.py:311-334
 
 
 class RolloutManager:                   # ml/rollouts.py:373-826
-    def __init__(self, train_cfg, init_rollout_state, example_policy_states):
+    def __init__(self, train_cfg, init_rollout_state, example_policy_states, dist_ctx=None):
         self._cfg = init_rollout_state.cfg
         if train_cfg.hlgauss_critic:
             raise NotImplementedError('hlgauss_critic is a "next" row (SURVEY 8f rank 3)')
@@ -169,24 +169,31 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         self._act_name = prog.groups[0][0]
         e = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
         # store schema: ml/rollouts.py:409-480
-        self.store = {
-            'obs': e(C, Tp, 1, B, prog.obs_dim),
-            'actions': e(C, Tp, 1, B, prog.A, dtype=torch.int32),
-            'log_probs': e(C, Tp, 1, B, prog.A),
-            'rewards': e(C, Tp, 1, B, 1),
-            'dones': e(C, Tp, 1, B, 1, dtype=torch.bool),
-            'values': e(C, Tp, 1, B, 1),
-            'advantages': e(C, Tp, 1, B, 1),
-            'returns': e(C, Tp, 1, B, 1),
+        f32 = torch.float32
+        specs = {
+            'obs': ((C, Tp, 1, B, prog.obs_dim), f32),
+            'actions': ((C, Tp, 1, B, prog.A), torch.int32),
+            'log_probs': ((C, Tp, 1, B, prog.A), f32),
+            'rewards': ((C, Tp, 1, B, 1), f32),
+            'dones': ((C, Tp, 1, B, 1), torch.bool),
+            'values': ((C, Tp, 1, B, 1), f32),
+            'advantages': ((C, Tp, 1, B, 1), f32),
+            'returns': ((C, Tp, 1, B, 1), f32),
         }
-        self.bootstrap = e(1, B, 1)
         self._lstm = prog.lstm
         if self._lstm is not None:
             # rnn_start_states [C, P, B, *] (ml/rollouts.py:471-478): the carry entering each BPTT chunk
             RH = self._lstm.RH
-            self.store['rnn_start_c'] = e(C, 1, B, RH)
-            self.store['rnn_start_h'] = e(C, 1, B, RH)
+            specs['rnn_start_c'] = ((C, 1, B, RH), f32)
+            specs['rnn_start_h'] = ((C, 1, B, RH), f32)
             self._boot_states = self._lstm.init_states(B, dev)
+        # data-parallel index-exact mode: the stores live in NVLink symmetric memory so that peers can
+        # gather the trajectories of a GLOBAL minibatch permutation straight out of them (parallel.py)
+        self.store = dist_ctx.alloc_symmetric_stores(specs, dev) if dist_ctx is not None and \
+            hasattr(dist_ctx, 'alloc_symmetric_stores') else None
+        if self.store is None:
+            self.store = {k: e(*shape, dtype=dt) for k, (shape, dt) in specs.items()}
+        self.bootstrap = e(1, B, 1)
         self._scratch_actions = e(B, prog.A, dtype=torch.int32)
         self.env_returns_trace = e(C * Tp, B)
         self.policy_key = torch.zeros(2, dtype=torch.int32, device=dev)

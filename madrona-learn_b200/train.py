@@ -154,7 +154,7 @@ def _init_training(dev, cfg, sim_fns, policy, sim_ctrl, user_hooks, restore_ckpt
     start_update_idx = 0
     if restore_ckpt is not None:
         train_state_mgr, start_update_idx = train_state_mgr.load(restore_ckpt)
-    rollout_mgr = RolloutManager(cfg, rollout_state, train_state_mgr.policy_states)
+    rollout_mgr = RolloutManager(cfg, rollout_state, train_state_mgr.policy_states, dist_ctx)
     # metric table order: rollout metrics first (Rewards, Values, Est Returns, Advantages are
     # consecutive so the GAE kernel can emit them in one go), then the algorithm's, then user's
     names = ['Rewards', 'Values', 'Est Returns']

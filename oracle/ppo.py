@@ -18,7 +18,8 @@ class PPOCfg:
                  value_loss_coef=0.5, entropy_coef=0.01, max_grad_norm=0.5, lr=3e-4,
                  clip_value_loss=False, huber_value_loss=False, normalize_advantages=True,
                  normalize_values=False, value_normalizer_decay=0.99999, gamma=0.99,
-                 gae_lambda=0.95, partitionable=False, dreamer_v3_critic=False):
+                 gae_lambda=0.95, partitionable=False, dreamer_v3_critic=False, compute_advantages=True,
+                 normalize_returns=True):
         self.__dict__.update(locals())
         del self.__dict__['self']
 
@@ -34,23 +35,43 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, 
     f = dtype
     Tp, M = mb['obs'].shape[:2]
     rows = Tp * M
-    A = len(cfg.buckets)
     p = nn.cast_tree(params, f)
     obs = mb['obs'].reshape(rows, -1).astype(f)
-    acts = mb['actions'].reshape(rows, A)
-    old_lp = mb['log_probs'].reshape(rows, A).astype(f)
-    w = np.broadcast_to(mb['mb_weights'].reshape(1, M, 1), (Tp, M, 1)).reshape(rows, 1).astype(f)
-
     seq = None
     if 'lstm' in p:
         rs = mb['rnn_start_states']
         seq = dict(Tp=Tp, M=M, ends=np.asarray(mb['dones']).reshape(Tp, M).astype(bool), c0=rs[0], h0=rs[1])
     logits, critic, cache = nn.actor_critic_fwd(p, obs, quant, seq)
+    out = ppo_loss_heads(logits, critic, mb, cfg, vn_state, f, want_grads, adv_stats, new_vn_state)
+    if want_grads:
+        out['grads'] = nn.actor_critic_bwd(p, cache, out['dlogits'], out['dcritic'], quant)
+    return out
+
+
+def ppo_loss_heads(logits, critic, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True,
+                   adv_stats=None, new_vn_state=None):
+    """The part of loss_fn downstream of the policy forward (ml/ppo.py:131-262): everything the
+    fused loss kernel computes from the head outputs `logits` [rows, sumA] / `critic` [rows, V],
+    plus d loss / d(logits, critic).  Pinned against the reference's own `_ppo_update` run under
+    oracle/jax_shim (tests/golden/ppo_loss.npz)."""
+    f = dtype
+    Tp, M = mb['actions'].shape[:2]
+    rows = Tp * M
+    A = len(cfg.buckets)
+    logits, critic = np.asarray(logits, f), np.asarray(critic, f)
+    acts = mb['actions'].reshape(rows, A)
+    old_lp = mb['log_probs'].reshape(rows, A).astype(f)
+    w = np.broadcast_to(mb['mb_weights'].reshape(1, M, 1), (Tp, M, 1)).reshape(rows, 1).astype(f)
     new_lp, ent = nn.action_stats(logits, acts, cfg.buckets)
 
     # advantages: per-MINIBATCH z-score (ml/ppo.py:134-137 -> ml/algo_common.py:133-140)
-    adv = mb['advantages'].reshape(rows, 1).astype(np.float32)
-    if cfg.normalize_advantages:
+    if getattr(cfg, 'compute_advantages', True):
+        adv = mb['advantages'].reshape(rows, 1).astype(np.float32)
+        do_norm = cfg.normalize_advantages
+    else:       # :138-143: the returns play the role of the scores
+        adv = mb['returns'].reshape(rows, 1).astype(np.float32)
+        do_norm = getattr(cfg, 'normalize_returns', True)
+    if do_norm:
         if adv_stats is None:
             adv = algo_common.zscore_data(adv)
         else:       # data-parallel: (mean, rstd) of the GLOBAL minibatch, computed elsewhere
@@ -98,7 +119,6 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, 
         dent = -(cfg.entropy_coef * w) / (rows * A) * np.ones_like(ent)
         dlogits = nn.action_stats_bwd(logits, acts, cfg.buckets, dlogp, dent)
         dcritic = cfg.value_loss_coef * w * (np.exp(logp) - two_hot) / rows
-        out['grads'] = nn.actor_critic_bwd(p, cache, dlogits, dcritic, quant)
         out['dlogits'], out['dcritic'] = dlogits, dcritic
         return out
     # value loss, plain critic branch (:186-218)
@@ -150,7 +170,6 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, 
     dent = -(cfg.entropy_coef * w) / (rows * A) * np.ones_like(ent)
     dlogits = nn.action_stats_bwd(logits, acts, cfg.buckets, dlogp, dent)
     dcritic = cfg.value_loss_coef * w * dvloss * vclip_mask / rows
-    out['grads'] = nn.actor_critic_bwd(p, cache, dlogits, dcritic, quant)
     out['dlogits'] = dlogits
     out['dcritic'] = dcritic
     return out
@@ -235,7 +254,7 @@ def initial_weight_norms(params):
 # the update loop (ml/ppo.py:366-488, default branch)
 # ---------------------------------------------------------------------------------------
 def ppo_update(params, opt, init_norms, rollout, cfg, update_key, vn_state=None,
-               dtype=np.float32, perms=None):
+               dtype=np.float32, perms=None, quant=None):
     """rollout: dict name -> [J, T', ...] training layout (ml/rollouts.py:788-804), P=1.
     Returns (params, opt, new_key, vn_state, last_minibatch_outputs, perms)."""
     J = rollout['dones'].shape[0]
@@ -257,7 +276,7 @@ def ppo_update(params, opt, init_norms, rollout, cfg, update_key, vn_state=None,
             mb_inds = inds[i * M:(i + 1) * M]                             # :464-466
             mb = layouts.minibatch(rollout, mb_inds)
             mb['mb_weights'] = traj_w[mb_inds]
-            out = ppo_loss(params, mb, cfg, vn_state, dtype=dtype)
+            out = ppo_loss(params, mb, cfg, vn_state, dtype=dtype, quant=quant)
             if out['new_vn_state'] is not None:
                 vn_state = out['new_vn_state']
             grads = nn.cast_tree(out['grads'], dtype)

@@ -21,6 +21,134 @@ from oracle.jax_shim import _arr, extract_function, install, load_reference  # n
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+def ppo_update_golden(rng, jax, jnp, lax, ac, ma, di):
+    """Runs the reference's OWN `_ppo_update` (ml/ppo.py:109-362, AST-extracted, unmodified) forward
+    under the shim: loss_fn (:129-262), the kernel re-projection and the LayerNorm renorm
+    (:300-338).  The policy forward is replaced by given head outputs (logits | value), optax's
+    transformation by a zero update, so only reference code is exercised:
+        inputs : head outputs, actions, old log-probs, advantages, returns, old values
+        outputs: the five recorded metrics (:351-362), the new value-normaliser state, the
+                 re-projected parameters."""
+    import functools
+    import types as _t
+    from flax.core import FrozenDict
+    f32 = np.float32
+    buckets = [4, 8, 5, 5, 2, 2]
+    A, sumA = len(buckets), sum(buckets)
+    optax = _t.SimpleNamespace(
+        l2_loss=lambda p, t: 0.5 * jnp.square(p - t),                       # optax 0.1.9 l2_loss
+        huber_loss=lambda p, t, delta=1.0: (lambda e: 0.5 * jnp.square(jnp.minimum(jnp.abs(e), delta)) +
+                                            delta * (jnp.abs(e) - jnp.minimum(jnp.abs(e), delta)))(p - t),
+        apply_updates=lambda p, u: jax.tree.map(lambda a, b: a + b, p, u))
+
+    def value_and_grad(fn, has_aux=True):
+        return lambda params: (fn(params), jax.tree.map(lambda x: jnp.zeros_like(x), params))
+    jax_ns = _t.SimpleNamespace(**{k: getattr(jax, k) for k in dir(jax) if not k.startswith('__')})
+    jax_ns.value_and_grad = value_and_grad
+
+    class Ctx:
+        def __init__(self, *a): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+    ns = dict(jax=jax_ns, jnp=jnp, lax=lax, optax=optax, partial=functools.partial, profile=Ctx,
+              zscore_data=ac.zscore_data, FrozenDict=FrozenDict, Any=object, TrainConfig=object,
+              PolicyState=object, PolicyTrainState=object, TrainingMetrics=object)
+    ppo_update = extract_function('ppo.py', '_ppo_update', ns)
+
+    class Obj:
+        def __init__(self, **kw): self.__dict__.update(kw)
+        def update(self, **kw):
+            d = dict(self.__dict__); d.update(kw); return Obj(**d)
+
+    class Rec:
+        def __init__(self): self.out = None
+        def record(self, d): self.out = d; return self
+
+    out = {}
+    Tp, M = 5, 12
+    H = 16
+    for name, kw in {'plain': {}, 'clipv_huber': dict(clipv=True, huber=True),
+                     'valuenorm': dict(vn=True), 'valuenorm_clipv': dict(vn=True, clipv=True),
+                     'twohot': dict(twohot=True), 'returns_only': dict(use_adv=False)}.items():
+        V = 63 if kw.get('twohot') else 1
+        logits = (rng.standard_normal((Tp, M, sumA)) * 1.5).astype(f32)
+        critic = (rng.standard_normal((Tp, M, V)) * (1.0 if V > 1 else 2.0)).astype(f32)
+        acts = np.stack([rng.integers(0, b, (Tp, M)) for b in buckets], -1).astype(np.int32)
+        dist = di.DiscreteActionDistributions(actions_num_buckets=buckets, all_logits=_arr(logits))
+        lp_new, ent = dist.action_stats(_arr(acts))
+        old_lp = (np.asarray(lp_new) + 0.25 * rng.standard_normal((Tp, M, A))).astype(f32)
+        adv = (rng.standard_normal((Tp, M, 1)) * 2 + 0.3).astype(f32)
+        ret = (rng.standard_normal((Tp, M, 1)) * (30 if V > 1 else 3) + 1).astype(f32)
+        oldv = (critic[..., :1] + 0.3 * rng.standard_normal((Tp, M, 1))).astype(f32)
+        mbw = np.ones((M, 1), f32)
+        cfg = _t.SimpleNamespace(
+            compute_advantages=kw.get('use_adv', True), normalize_advantages=True, normalize_returns=True,
+            dreamer_v3_critic=bool(kw.get('twohot')), hlgauss_critic=False,
+            algo=_t.SimpleNamespace(clip_value_loss=bool(kw.get('clipv')), huber_value_loss=bool(kw.get('huber')),
+                                    entropy_coef={'act': 0.02}))
+        vn = vn_state = None
+        if kw.get('vn'):
+            vn = ma.EMANormalizer(decay=0.99999, norm_dtype=jnp.float32, inv_dtype=jnp.float32)
+            vn_state = vn.init_estimates(_arr(np.zeros((1, 1), f32)))
+            for _ in range(3):          # a non-trivial state
+                vn_state, _n = vn.normalize_and_update_estimates(
+                    vn_state, _arr((rng.standard_normal((40, 1)) * 4 + 2).astype(f32)))
+        params = {'backbone': {'encoder': {'net': {
+            'Dense_0': {'kernel': _arr(rng.standard_normal((8, H)).astype(f32))},
+            'LayerNorm_0': {'impl': {'scale': _arr((1 + 0.2 * rng.standard_normal(H)).astype(f32)),
+                                     'bias': _arr((0.2 * rng.standard_normal(H)).astype(f32))}},
+            'Dense_1': {'kernel': _arr(rng.standard_normal((H, H)).astype(f32))},
+            'LayerNorm_1': {'impl': {'scale': _arr((1 + 0.2 * rng.standard_normal(H)).astype(f32)),
+                                     'bias': _arr((0.2 * rng.standard_normal(H)).astype(f32))}}}}},
+            'actor': {'impl': {'kernel': _arr(rng.standard_normal((H, sumA)).astype(f32)),
+                               'bias': _arr(rng.standard_normal(sumA).astype(f32))}},
+            'critic': {'Dense_0': {'kernel': _arr(rng.standard_normal((H, V)).astype(f32)),
+                                   'bias': _arr(rng.standard_normal(V).astype(f32))}}}
+        norms = {'backbone': {'encoder': {'net': {
+            'Dense_0': {'kernel': f32(3.0)}, 'LayerNorm_0': {'impl': {'scale': None, 'bias': None}},
+            'Dense_1': {'kernel': f32(5.5)}, 'LayerNorm_1': {'impl': {'scale': None, 'bias': None}}}}},
+            'actor': {'impl': {'kernel': None, 'bias': None}}, 'critic': {'Dense_0': {'kernel': None, 'bias': None}}}
+        crit_out = di.SymExpTwoHotDistribution.create(_arr(critic)) if V > 1 else _arr(critic)
+
+        def apply_fn(variables, rnn, dones, actions, obs, train, method, mutable):
+            return ({'log_probs': {'act': lp_new}, 'entropies': {'act': ent}, 'critic': crit_out},
+                    {'batch_stats': {}})
+        tx = _t.SimpleNamespace(update=lambda g, o, p: (jax.tree.map(lambda x: jnp.zeros_like(x), p), o))
+        hp = _t.SimpleNamespace(clip_coef=f32(0.2), value_loss_coef=f32(0.5))
+        ps = Obj(apply_fn=apply_fn, params=params, batch_stats={})
+        ts = Obj(value_normalizer=vn, value_normalizer_state=vn_state, hyper_params=hp, tx=tx, opt_state=None,
+                 scaler=None, initial_weight_norms=norms)
+        mb = FrozenDict(rnn_start_states=None, dones=None, actions={'act': _arr(acts)}, obs=None,
+                        log_probs={'act': _arr(old_lp)}, advantages=_arr(adv), returns=_arr(ret), values=_arr(oldv))
+        rec = Rec()
+        ps2, ts2, rec = ppo_update(cfg, mb, _arr(mbw), ps, ts, rec)
+        o = rec.out
+        pre = name + '/'
+        out.update({pre + 'logits': logits, pre + 'critic': critic, pre + 'actions': acts, pre + 'old_log_probs': old_lp,
+                    pre + 'advantages': adv, pre + 'returns': ret, pre + 'old_values': oldv,
+                    pre + 'flags': np.array([int(cfg.algo.clip_value_loss), int(cfg.algo.huber_value_loss),
+                                             int(bool(kw.get('vn'))), int(V > 1), int(cfg.compute_advantages)]),
+                    pre + 'loss': np.asarray(o['Loss'], f32), pre + 'action_obj': np.asarray(o['Action Obj']),
+                    pre + 'value_loss': np.asarray(o['Value Loss']), pre + 'value_errs': np.asarray(o['Value Errors']),
+                    pre + 'entropy': np.asarray(o['Entropy'])})
+        if vn is not None:
+            keys = ('mu', 'inv_sigma', 'sigma', 'mu_biased', 'sigma_sq_biased')
+            out[pre + 'vn_before'] = np.array([float(vn_state[k][0]) for k in keys] + [float(vn_state['N'])], np.float64)
+            s2 = ts2.value_normalizer_state
+            out[pre + 'vn_after'] = np.array([float(s2[k][0]) for k in keys] + [float(s2['N'])], np.float64)
+        if name == 'plain':     # re-projection / LayerNorm renorm of the (un-updated) parameters
+            net, net2 = params['backbone']['encoder']['net'], ps2.params['backbone']['encoder']['net']
+            for k in ('Dense_0', 'Dense_1'):
+                out[f'reproj/{k}_in'], out[f'reproj/{k}_out'] = np.asarray(net[k]['kernel']), np.asarray(net2[k]['kernel'])
+            for k in ('LayerNorm_0', 'LayerNorm_1'):
+                for leaf in ('scale', 'bias'):
+                    out[f'reproj/{k}_{leaf}_in'] = np.asarray(net[k]['impl'][leaf])
+                    out[f'reproj/{k}_{leaf}_out'] = np.asarray(net2[k]['impl'][leaf])
+            out['reproj/norms'] = np.array([3.0, 5.5], f32)
+            assert np.array_equal(np.asarray(ps2.params['actor']['impl']['kernel']), np.asarray(params['actor']['impl']['kernel']))
+    np.savez_compressed(os.path.join(OUT, 'ppo_loss.npz'), **out)
+
+
 def main():
     install()
     import jax
@@ -147,6 +275,9 @@ def main():
         tp, ts = crc(_arr(a), Pn, Cn, Bn)
         out[f'v{i}_in'], out[f'v{i}_to_policy'], out[f'v{i}_to_sim'] = a, np.asarray(tp), np.asarray(ts)
     np.savez_compressed(os.path.join(OUT, 'reorder_chunks.npz'), **out)
+    # ---- the composite PPO loss + re-projection: ml/ppo.py:109-362 (own generator so the
+    # fixtures above keep their random stream and stay bit-identical) ------------------------
+    ppo_update_golden(np.random.default_rng(20261019), jax, jnp, lax, ac, ma, di)
     print('golden fixtures written to', OUT)
 
 

@@ -132,3 +132,65 @@ def test_permutation_properties():
         assert not np.array_equal(a, b)
     assert prng.shuffle_rounds(1625) == 1 and prng.shuffle_rounds(1626) == 2
     assert prng.shuffle_rounds(8192) == 2 and prng.shuffle_rounds(1 << 20) == 2
+
+
+PPO_CASES = ['plain', 'clipv_huber', 'valuenorm', 'valuenorm_clipv', 'twohot', 'returns_only']
+
+
+def _ppo_case(name):
+    """(mb, cfg, vn_state, z) of one tests/golden/ppo_loss.npz case (the reference's own
+    `_ppo_update`, ml/ppo.py:109-362, executed under oracle/jax_shim)."""
+    from oracle import ppo as oppo
+    z = np.load(os.path.join(G, 'ppo_loss.npz'))
+    g = lambda k: z[f'{name}/{k}']
+    clipv, huber, vn, twohot, use_adv = [int(x) for x in g('flags')]
+    cfg = oppo.PPOCfg([4, 8, 5, 5, 2, 2], clip_coef=0.2, value_loss_coef=0.5, entropy_coef=0.02,
+                      clip_value_loss=bool(clipv), huber_value_loss=bool(huber), normalize_values=bool(vn),
+                      dreamer_v3_critic=bool(twohot), compute_advantages=bool(use_adv))
+    M = g('actions').shape[1]
+    mb = dict(actions=g('actions'), log_probs=g('old_log_probs'), advantages=g('advantages'),
+              returns=g('returns'), values=g('old_values'), mb_weights=np.ones((M, 1), np.float32))
+    vn_state = None
+    if vn:
+        b = g('vn_before')
+        vn_state = dict(mu=np.float32(b[0:1]), inv_sigma=np.float32(b[1:2]), sigma=np.float32(b[2:3]),
+                        mu_biased=np.float32(b[3:4]), sigma_sq_biased=np.float32(b[4:5]), N=np.int32(b[5]))
+    return mb, cfg, vn_state, g
+
+
+@pytest.mark.parametrize('name', PPO_CASES)
+def test_ppo_loss_matches_reference(name):
+    """oracle/ppo.ppo_loss_heads vs the reference's loss_fn (ml/ppo.py:129-262) on the same head
+    outputs: the five recorded metrics and the value-normaliser state after the minibatch."""
+    from oracle import ppo as oppo
+    mb, cfg, vn_state, g = _ppo_case(name)
+    Tp, M, A = mb['actions'].shape
+    rows = Tp * M
+    out = oppo.ppo_loss_heads(g('logits').reshape(rows, -1), g('critic').reshape(rows, -1), mb, cfg, vn_state,
+                              dtype=np.float32, want_grads=False)
+    np.testing.assert_allclose(out['loss'], g('loss'), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(out['action_obj'], g('action_obj'), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(out['value_losses'], g('value_loss').reshape(rows, 1), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(np.abs(out['value_errs']), g('value_errs').reshape(rows, 1), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(out['entropies'], g('entropy'), rtol=2e-5, atol=1e-6)
+    if vn_state is not None:
+        a = g('vn_after')
+        nv = out['new_vn_state']
+        got = [nv['mu'][0], nv['inv_sigma'][0], nv['sigma'][0], nv['mu_biased'][0], nv['sigma_sq_biased'][0], nv['N']]
+        np.testing.assert_allclose(got, a, rtol=2e-5, atol=1e-7)
+
+
+def test_reprojection_matches_reference():
+    """oracle/ppo.optimizer_step's kernel re-projection + LayerNorm renorm vs ml/ppo.py:300-338."""
+    from oracle import ppo as oppo
+    z = np.load(os.path.join(G, 'ppo_loss.npz'))
+    p = {'mlp': [{'kernel': z[f'reproj/Dense_{i}_in'], 'scale': z[f'reproj/LayerNorm_{i}_scale_in'],
+                  'bias': z[f'reproj/LayerNorm_{i}_bias_in']} for i in range(2)]}
+    zero = onn.tree_map(np.zeros_like, p)
+    cfg = oppo.PPOCfg([2], lr=0.0, max_grad_norm=0.5)
+    norms = {'mlp': [float(x) for x in z['reproj/norms']]}
+    new_p, _, _ = oppo.optimizer_step(p, zero, oppo.adam_init(p), cfg, norms, np.float32)
+    for i in range(2):
+        np.testing.assert_allclose(new_p['mlp'][i]['kernel'], z[f'reproj/Dense_{i}_out'], rtol=2e-6)
+        np.testing.assert_allclose(new_p['mlp'][i]['scale'], z[f'reproj/LayerNorm_{i}_scale_out'], rtol=2e-6)
+        np.testing.assert_allclose(new_p['mlp'][i]['bias'], z[f'reproj/LayerNorm_{i}_bias_out'], rtol=2e-6)

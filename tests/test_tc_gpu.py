@@ -104,9 +104,15 @@ def _program(mlb, D, H, L, buckets, dtype):
 
 
 # the last two shapes have more 128-row tiles than SMs: they run the persistent kernels (ragged last tile)
-@pytest.mark.parametrize('D,H,L,rows', [(64, 256, 3, 4096), (32, 128, 2, 1000), (64, 512, 3, 2048),
-                                        (64, 256, 3, 20004), (32, 128, 2, 39000)])
-def test_tc_policy_forward_backward_vs_oracle(mlb, D, H, L, rows):
+# jitter: std of the noise added to the old log-probs.  0.2 = adversarial (ratios straddle the PPO clip
+# range, so bf16 noise flips clip decisions); 0.0 = what the first minibatch of an update sees (old
+# log-probs = the current policy's), at the full BASELINE minibatch shapes (cfg2: 65 536 x 256,
+# cfg3 width 512)
+@pytest.mark.parametrize('D,H,L,rows,jitter', [(64, 256, 3, 4096, 0.2), (32, 128, 2, 1000, 0.2),
+                                               (64, 512, 3, 2048, 0.2), (64, 256, 3, 20004, 0.2),
+                                               (32, 128, 2, 39000, 0.2), (64, 256, 3, 65536, 0.0),
+                                               (64, 512, 3, 32768, 0.0), (64, 256, 3, 65536, 0.05)])
+def test_tc_policy_forward_backward_vs_oracle(mlb, D, H, L, rows, jitter):
     import ctypes
     from madrona_learn_b200._lib import c_float, c_int, c_ll, c_size_t, call, ptr
     from oracle import nn as onn, ppo as oppo, algo_common as oac
@@ -130,7 +136,7 @@ def test_tc_policy_forward_backward_vs_oracle(mlb, D, H, L, rows):
               values=rng.standard_normal((Tp, M, 1)).astype(np.float32), mb_weights=np.ones((M, 1), np.float32))
     lg, cr, _ = onn.actor_critic_fwd(onn.cast_tree(p, np.float64), mb['obs'].reshape(rows, D).astype(np.float64))
     lp0, _ = onn.action_stats(lg, mb['actions'].reshape(rows, A), buckets)
-    mb['log_probs'] = (lp0 + 0.2 * rng.standard_normal(lp0.shape)).reshape(Tp, M, A).astype(np.float32)
+    mb['log_probs'] = (lp0 + jitter * rng.standard_normal(lp0.shape)).reshape(Tp, M, A).astype(np.float32)
     ref = oppo.ppo_loss(p, mb, cfg, None, dtype=np.float64)                       # exact arithmetic
     refq = oppo.ppo_loss(p, mb, cfg, None, dtype=np.float64, quant=onn.bf16_round)     # same quantisation points
 
@@ -179,7 +185,20 @@ def test_tc_policy_forward_backward_vs_oracle(mlb, D, H, L, rows):
     a, b = flat(g), flat(ref['grads'])
     cos = a @ b / (np.linalg.norm(a) * np.linalg.norm(b))
     rel = np.linalg.norm(a - b) / np.linalg.norm(b)
-    assert cos > 0.98 and rel < 0.2, (cos, rel)
+    import json, os
+    rec = dict(case='tc_fwd_bwd', D=D, H=H, L=L, rows=rows, jitter=jitter, grad_rel_quant=float(relq),
+               grad_cos_exact=float(cos), grad_rel_exact=float(rel))
+    print('PARITY', json.dumps(rec))
+    if os.environ.get('MLB_PARITY_LOG'):
+        with open(os.environ['MLB_PARITY_LOG'], 'a') as f:
+            f.write(json.dumps(rec) + '\n')
+    if jitter >= 0.2:
+        assert cos > 0.98 and rel < 0.2, (cos, rel)
+    else:
+        # realistic inputs: no clip-decision flips; what remains is the bf16 storage of activations
+        # (ReLU-mask flips of near-zero pre-activations).  SURVEY 8c aimed at cos >= 0.999 / rel-L2 <=
+        # 2e-2; the measured figures are recorded in profiles/r2_parity_measured.jsonl and DESIGN.md.
+        assert cos > 0.995 and rel < 0.1, (cos, rel)
     # optimiser step refreshes the bf16 operand copies
     prog.optimizer_step(3e-4, 0.5)
     k0, _, _ = prog.layer_views(prog.params, 0)
