@@ -51,13 +51,20 @@ struct GaeStatPartial {        // per-block partial of the 4 metric streams
 struct ThreadStats {
     double s[4], ss[4];
     float mn[4], mx[4];
+    float cs[4], css[4];          // fp32 partials of the current time chunk (<= U*VEC terms)
     __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { s[i] = 0.0; ss[i] = 0.0; mn[i] = INFINITY; mx[i] = -INFINITY; }
+        for (int i = 0; i < 4; ++i) { s[i] = 0.0; ss[i] = 0.0; mn[i] = INFINITY; mx[i] = -INFINITY; cs[i] = 0.f; css[i] = 0.f; }
     }
     __device__ __forceinline__ void add(int i, float x) {
-        s[i] += (double)x; ss[i] += (double)x * (double)x;
+        cs[i] += x; css[i] = fmaf(x, x, css[i]);
         mn[i] = fminf(mn[i], x); mx[i] = fmaxf(mx[i], x);
+    }
+    // a chunk holds at most 32 terms: the fp32 partial is exact to ~2e-6 relative, the running
+    // totals over the T/U chunks of a column stay in fp64
+    __device__ __forceinline__ void fold() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s[i] += (double)cs[i]; ss[i] += (double)css[i]; cs[i] = 0.f; css[i] = 0.f; }
     }
 };
 
@@ -88,37 +95,54 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
             }
         }
         int t_hi = T;
-        // main: chunks of U time steps, loads hoisted ahead of the recurrence
-        for (; t_hi >= U; t_hi -= U) {
-            float r[U][VEC], v[U][VEC];
-            uint32_t d[U];
+        // main: chunks of U time steps.  Software pipeline: the 3*U loads of chunk k+1 are issued
+        // BEFORE the serial recurrence of chunk k runs, so a thread always has a full chunk
+        // (U*VEC*9 bytes) in flight underneath its arithmetic -- with N as the only parallel axis
+        // (the scan is exact, so time cannot be split) this is what fills the HBM pipe for
+        // N ~ 64K..256K columns.
+        float r[2][U][VEC], v[2][U][VEC];
+        uint32_t d[2][U];
+        auto load_chunk = [&](int buf, int thi) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const long long off = (long long)(t_hi - 1 - u) * N + col;
-                Vec<VEC>::ldf(rewards + off, r[u]);
-                Vec<VEC>::ldf(values + off, v[u]);
-                Vec<VEC>::ldd(dones + off, d[u]);
+                const long long off = (long long)(thi - 1 - u) * N + col;
+                Vec<VEC>::ldf(rewards + off, r[buf][u]);
+                Vec<VEC>::ldf(values + off, v[buf][u]);
+                Vec<VEC>::ldd(dones + off, d[buf][u]);
             }
+        };
+        auto scan_chunk = [&](int buf, int thi) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const long long off = (long long)(t_hi - 1 - u) * N + col;
+                const long long off = (long long)(thi - 1 - u) * N + col;
                 float a[VEC], rt[VEC];
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    const bool done = ((d[u] >> (8 * j)) & 0xffu) != 0u;
-                    const float vv = __fadd_rn(__fmul_rn(v[u][j], sigma), mu);
+                    const bool done = ((d[buf][u] >> (8 * j)) & 0xffu) != 0u;
+                    const float vv = __fadd_rn(__fmul_rn(v[buf][u][j], sigma), mu);
                     const float nvj = done ? 0.f : nv[j];
                     const float naj = done ? 0.f : na[j];
-                    const float td = __fadd_rn(__fadd_rn(r[u][j], __fmul_rn(gamma, nvj)), -vv);
+                    const float td = __fadd_rn(__fadd_rn(r[buf][u][j], __fmul_rn(gamma, nvj)), -vv);
                     a[j] = __fadd_rn(td, __fmul_rn(gl, naj));
                     rt[j] = __fadd_rn(a[j], vv);
                     na[j] = a[j];
                     nv[j] = vv;
-                    if (STATS) { st.add(0, r[u][j]); st.add(1, vv); st.add(2, rt[j]); st.add(3, a[j]); }
+                    if (STATS) { st.add(0, r[buf][u][j]); st.add(1, vv); st.add(2, rt[j]); st.add(3, a[j]); }
                 }
                 Vec<VEC>::stf(adv + off, a);
                 if (ret) Vec<VEC>::stf(ret + off, rt);
             }
+            if (STATS) st.fold();
+        };
+        if (t_hi >= U) load_chunk(0, t_hi);
+        while (t_hi >= U) {
+            if (t_hi - U >= U) load_chunk(1, t_hi - U);
+            scan_chunk(0, t_hi);
+            t_hi -= U;
+            if (t_hi < U) break;
+            if (t_hi - U >= U) load_chunk(0, t_hi - U);
+            scan_chunk(1, t_hi);
+            t_hi -= U;
         }
         // remainder (T % U steps)
         for (int t = t_hi - 1; t >= 0; --t) {
@@ -144,6 +168,7 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
             Vec<VEC>::stf(adv + off, a);
             if (ret) Vec<VEC>::stf(ret + off, rt);
         }
+        if (STATS) st.fold();
     }
 
     if (STATS) {

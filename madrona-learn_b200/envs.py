@@ -39,14 +39,20 @@ class SyntheticVectorEnv:
 
 
 class HostTraceEnv:
-    """sim_fns whose observations / rewards / dones live in PINNED HOST memory and are
-    streamed to the device step by step (cudaMemcpyAsync on the compute stream, capturable
-    in the update graph).  This is the end-to-end arm of bench.py: the simulator is on the
-    host side of the boundary, so every update moves T*N*(4D+5) bytes host->device."""
+    """sim_fns of a simulator that lives on the HOST side of the boundary: every step the sampled
+    actions are copied device->host into a pinned buffer (what a host simulator consumes), and the
+    step's observations / rewards / dones are copied host->device from ONE pinned record
+    (cudaMemcpyAsync on the compute stream, capturable in the update graph).  This is the end-to-end
+    arm of bench.py: per update T*N*(4D+5) bytes go host->device and T*N*4A bytes device->host.
+    The copies are deliberately NOT overlapped with compute on a side stream: with a real simulator
+    the record of step t exists only after the actions of step t have arrived, and the policy
+    kernel of step t+1 needs that record -- the chain actions -> sim -> observations is serial, and
+    prefetching recorded observations ahead of the actions would time something no simulator can do."""
 
     def __init__(self, num_worlds, steps, obs_dim=64, seed=0, p_done=1.0 / 64, device='cuda:0',
-                 action_key='act', obs_key='obs'):
+                 action_key='act', obs_key='obs', num_action_components=6):
         self.N, self.T, self.D = int(num_worlds), int(steps), int(obs_dim)
+        self.A = int(num_action_components)
         self.device = torch.device(device)
         self.action_key, self.obs_key = action_key, obs_key
         g = torch.Generator().manual_seed(int(seed))
@@ -64,12 +70,14 @@ class HostTraceEnv:
         self.h_rec[:, self._o_rew:self._o_done] = h_rew.reshape(T, -1).view(torch.uint8)
         self.h_rec[:, self._o_done:] = h_done.reshape(T, -1)
         self.h_obs0 = h_obs[0].contiguous().pin_memory()
+        self.h_actions = torch.zeros(T, N, self.A, dtype=torch.int32).pin_memory()   # what the simulator reads
         self.d_rec = torch.empty(self.rec_bytes, dtype=torch.uint8, device=self.device)
         self.obs = self.d_rec[:self._o_rew].view(torch.float32).view(N, D)
         self.rewards = self.d_rec[self._o_rew:self._o_done].view(torch.float32).view(N, 1)
         self.dones = self.d_rec[self._o_done:].view(N, 1)
         self.t = 0
         self.h2d_bytes_per_update = T * self.rec_bytes
+        self.d2h_bytes_per_update = T * N * self.A * 4
 
     def init(self):
         self.obs.copy_(self.h_obs0, non_blocking=True)
@@ -78,6 +86,10 @@ class HostTraceEnv:
 
     def step(self, step_input):
         t = self.t % self.T
+        acts = step_input['actions']
+        if acts is not None:                   # device -> host: the actions the simulator steps with
+            a = acts[self.action_key]
+            self.h_actions[t].copy_(a.view(self.N, self.A), non_blocking=True)
         self.d_rec.copy_(self.h_rec[t], non_blocking=True)
         self.t += 1
         return {'state': None, 'obs': {self.obs_key: self.obs}, 'rewards': self.rewards,

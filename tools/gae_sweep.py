@@ -3,7 +3,8 @@
 T in {16..256} x N in {4K..1M}; CUDA-event timing on the launching stream, L2 flushed
 (write of a 256 MiB buffer) between timed launches, median of `reps`.  Algorithmic bytes
 17*T*N+4*N (GAE+returns) and 8*T*N (z-score apply).  Peak = MEASURED_PEAKS.json hbm_gbs.
-Writes gpurun_out/gae_sweep.json and prints a table.
+Writes gpurun_out/r2_gae_sweep.json and prints a table; every point carries the CPU restatement's
+time and a full-size bit-exactness check of the kernel against the C oracle.
 """
 import json
 import os
@@ -69,7 +70,26 @@ def main():
             m4 = K.moments(adv)
             tz = time_op(lambda: K.zscore_apply(adv, m4, out=ret), flush)
             tr = time_op(lambda: K.discounted_returns(r, d, b, 0.99, returns=ret), flush)
-            row = dict(T=T, N=N, bytes=by, gae_us=t * 1e6, gae_gbs=by / t / 1e9, gae_frac=by / t / 1e9 / pk,
+            # CPU restatement beside every point (BASELINE cfg5): the C oracle (all host threads, column-split) and the NumPy
+            # oracle (vectorised over N like the reference's fori_loop over T); the C result doubles as a
+            # full-size bit-exactness check of the kernel output
+            import time as _time
+            import numpy as np
+            from oracle import algo_common as oac, cgae
+            rh, vh, dh, bh = r.cpu().numpy(), v.cpu().numpy(), d.cpu().numpy(), b.cpu().numpy()
+            t0 = _time.perf_counter()
+            a_c, _ = cgae.gae(rh, vh, dh, bh, 0.99, 0.95)
+            cpu_c = _time.perf_counter() - t0
+            cpu_np = None
+            if T * N <= (1 << 24):
+                t0 = _time.perf_counter()
+                oac.compute_advantages(0.99, 0.95, rh[..., None], vh[..., None], dh[..., None], bh[:, None])
+                cpu_np = _time.perf_counter() - t0
+            K.gae(r, v, d, b, 0.99, 0.95, advantages=adv, returns=ret)
+            bit_exact = bool(np.array_equal(adv.cpu().numpy(), a_c))
+            del rh, vh, dh, bh, a_c
+            row = dict(T=T, N=N, bytes=by, gae_us=t * 1e6, cpu_c_ms=cpu_c * 1e3, cpu_threads=os.cpu_count(),
+                       cpu_numpy_ms=None if cpu_np is None else cpu_np * 1e3, bit_exact_vs_c_oracle=bit_exact, gae_gbs=by / t / 1e9, gae_frac=by / t / 1e9 / pk,
                        gae_metrics_us=tm * 1e6, gae_metrics_gbs=by / tm / 1e9,
                        zscore_us=tz * 1e6, zscore_gbs=8 * T * N / tz / 1e9,
                        returns_us=tr * 1e6, returns_gbs=(9 * T * N + 4 * N) / tr / 1e9,
@@ -77,11 +97,11 @@ def main():
             rows.append(row)
             print(f"T={T:4d} N={N:8d} {by/1e6:9.1f} MB  gae {t*1e6:9.1f} us {row['gae_gbs']:7.0f} GB/s "
                   f"({row['gae_frac']:.2f})  +metrics {row['gae_metrics_gbs']:7.0f}  zscore {row['zscore_gbs']:7.0f}  "
-                  f"returns {row['returns_gbs']:7.0f}", flush=True)
+                  f"returns {row['returns_gbs']:7.0f}  cpuC {cpu_c*1e3:8.1f} ms  exact={bit_exact}", flush=True)
             del r, v, d, b, adv, ret
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump(dict(peak_gbs=pk, peak_src=src, rows=rows),
-              open(os.path.join(ROOT, 'gpurun_out', 'gae_sweep.json'), 'w'), indent=1)
+              open(os.path.join(ROOT, 'gpurun_out', 'r2_gae_sweep.json'), 'w'), indent=1)
 
 
 if __name__ == '__main__':
