@@ -69,7 +69,7 @@ template <int XH_BUFS>
 __device__ __forceinline__ void p_mainloop(const CUtensorMap* tmA, const CUtensorMap* tmB,
                                            const CUtensorMap* tmXH, uint8_t* smem, const PLayout& L,
                                            const PBars& bars, uint32_t tmem_base, int warp, int lane,
-                                           int num_tiles, int K, int HN, int A_STAGES) {
+                                           int num_tiles, int K, int HN, int A_STAGES, int xh_reps = 2) {
     const int num_kb = (K + BK - 1) / BK;
     if (warp == 0) {
         if (lane == 0) {
@@ -91,7 +91,7 @@ __device__ __forceinline__ void p_mainloop(const CUtensorMap* tmA, const CUtenso
                 }
                 if (XH_BUFS > 0) {
                     const int tile = blockIdx.x + ti * gridDim.x;
-                    for (int rep = 0; rep < 2; ++rep)
+                    for (int rep = 0; rep < xh_reps; ++rep)
                         for (int pnl = 0; pnl < num_panels; ++pnl, ++xit) {
                             const int s = xit % (XH_BUFS > 0 ? XH_BUFS : 1);
                             mbar_wait_spin(&bars.xh_empty[s], ((xit / (XH_BUFS > 0 ? XH_BUFS : 1)) & 1) ^ 1);
@@ -576,6 +576,365 @@ dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     p_teardown(p.tmem_base, warp);
 }
 
+// ==========================================================================================
+// Second-generation epilogues: accumulator read in the .16x256b fragment layout (tc_common.cuh).
+//
+// Lane l of an epilogue warp sees rows  rq + 8i  (rq = l/4, i = 0..3) of its 32-row TMEM quadrant and,
+// inside every 32-column chunk, the eight columns  8k + 2c + e  (c = l%4).  Consequences:
+//   * per-FEATURE sums (dscale, dbias) accumulate in registers over every row of every tile the CTA
+//     processes; the cross-lane reduction happens ONCE per kernel (the first-generation kernel paid a
+//     31-shuffle reduce-scatter per 32x32 block: 4 of its 27 instructions per element);
+//   * per-ROW sums need a 2-step butterfly over the 4 lanes that share a row, per tile;
+//   * adjacent columns sit in adjacent registers, so bf16x2 packing is free and the LayerNorm-backward
+//     second pass runs on packed pairs (HFMA2.BF16): pass 1 leaves (rstd*dxhat) and xhat as bf16x2
+//     words in the accumulator's own TMEM cells, pass 2 is two packed FMAs per pair and never
+//     touches shared memory -- every xhat panel is fetched once instead of twice;
+//   * outputs go from registers to global memory directly.  FULLSEC: neighbouring lanes first swap one
+//     packed word so that each lane stores 8 contiguous bytes and the four lanes of a row fill a whole
+//     32-byte sector; otherwise each lane stores its own 4 bytes (half-sector writes merged by L2).
+// ==========================================================================================
+__device__ __forceinline__ float sel4(int c, float a0, float a1, float a2, float a3) {
+    return c == 0 ? a0 : (c == 1 ? a1 : (c == 2 ? a2 : a3));
+}
+
+// packed bf16x2 pair store of the eight (k, h) words a lane holds for one chunk-half.
+// o[k][h]: word of row i = 2*h2 + h, columns cbase + 8k + 2c (+1).
+template <bool FULLSEC, bool STREAM>
+__device__ __forceinline__ void store_pairs(__nv_bfloat16* __restrict__ G, int ld, const uint32_t (&o)[4][2],
+                                            long long row0, long long row1, bool ok0, bool ok1, int cbase, int c) {
+    if (FULLSEC) {
+        const bool odd = (c & 1) != 0;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            const int k0 = 2 * kp, k1 = 2 * kp + 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t send = odd ? o[k0][h] : o[k1][h];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                const uint2 v = odd ? make_uint2(recv, o[k1][h]) : make_uint2(o[k0][h], recv);
+                const int col = cbase + 8 * (odd ? k1 : k0) + 4 * (c >> 1);
+                const bool ok = h ? ok1 : ok0;
+                uint2* dst = reinterpret_cast<uint2*>(G + (h ? row1 : row0) * ld + col);
+                if (ok) { if (STREAM) __stcs(dst, v); else *dst = v; }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool ok = h ? ok1 : ok0;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(G + (h ? row1 : row0) * ld + cbase + 8 * k + 2 * c);
+                if (ok) { if (STREAM) __stcs(dst, o[k][h]); else *dst = o[k][h]; }
+            }
+    }
+}
+
+// row partials (a[i], b[i], i = 0..3) -> totals over the whole row: butterfly over the 4 lanes of a
+// row, then exchange between the 4 column groups of the quadrant through shared memory
+__device__ __forceinline__ void row_totals(float* part, int buf, int grp, int quad, int rq, int c,
+                                           float (&a)[4], float (&b)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[i] += __shfl_xor_sync(0xffffffffu, a[i], 1);
+        b[i] += __shfl_xor_sync(0xffffffffu, b[i], 1);
+        a[i] += __shfl_xor_sync(0xffffffffu, a[i], 2);
+        b[i] += __shfl_xor_sync(0xffffffffu, b[i], 2);
+    }
+    float2* pp = reinterpret_cast<float2*>(part) + buf * 512;
+    // lane c publishes row i = c
+    pp[grp * 128 + quad * 32 + rq + 8 * c] = make_float2(sel4(c, a[0], a[1], a[2], a[3]), sel4(c, b[0], b[1], b[2], b[3]));
+    quad_bar(quad);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rt = quad * 32 + rq + 8 * i;
+        const float2 p0 = pp[rt], p1 = pp[128 + rt], p2 = pp[256 + rt], p3 = pp[384 + rt];
+        a[i] = (p0.x + p1.x) + (p2.x + p3.x);
+        b[i] = (p0.y + p1.y) + (p2.y + p3.y);
+    }
+}
+
+template <bool FULLSEC>
+__global__ void __launch_bounds__(P_THREADS, 1)
+fwd_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const float* __restrict__ scale, const float* __restrict__ bias,
+                    __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ XH,
+                    float* __restrict__ rstd_out, int M, int K, int HN, int a_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (M + BM - 1) / BM;
+    PState p = p_prologue(smem_raw, &tmA, &tmB, M, K, HN, a_stages, 32768, scale, bias);
+    if (warp < 2) {
+        p_mainloop<0>(&tmA, &tmB, nullptr, p.smem, p.L, p.bars, p.tmem_base, warp, lane, num_tiles, K, HN, a_stages);
+    } else {
+        const int quad = warp & 3, grp = (warp - 2) >> 2;
+        const int c = lane & 3, rq = lane >> 2;
+        float* part = p.fsm + 4 * HN;
+        const float* s = p.fsm;
+        const float* b = p.fsm + HN;
+        const int nchunks = HN / 32;
+        const float invH = 1.f / (float)HN;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int m0 = tile * BM;
+            const uint32_t tq = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
+            mbar_wait(&p.bars.acc_full[buf], (it >> 1) & 1);
+            tcgen05_fence_after();
+            // pass 1: row statistics
+            float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int ch = grp + 4 * cc;
+                if (ch < nchunks) {
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        uint32_t r[16];
+                        tmem_ld_16x256b_x4(tq + ((uint32_t)(16 * h2) << 16) + ch * 32, r);
+                        tmem_ld_wait16(r);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const float z = __uint_as_float(r[4 * k + 2 * h + e]);
+                                    sum[2 * h2 + h] += z;
+                                    sq[2 * h2 + h] = fmaf(z, z, sq[2 * h2 + h]);
+                                }
+                    }
+                }
+            }
+            row_totals(part, buf, grp, quad, rq, c, sum, sq);
+            float rs[4], nmr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float mean = sum[i] * invH;
+                rs[i] = rsqrtf(fmaxf(0.f, sq[i] * invH - mean * mean) + LN_EPS);
+                nmr[i] = -mean * rs[i];
+            }
+            if (grp == 0 && rstd_out) {
+                const int row = m0 + quad * 32 + rq + 8 * c;
+                if (row < M) rstd_out[row] = sel4(c, rs[0], rs[1], rs[2], rs[3]);
+            }
+            // pass 2: normalise, scale/bias, ReLU -> bf16 pairs, straight to global memory
+            bool released = false;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int ch = grp + 4 * cc;
+                if (ch < nchunks) {
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        uint32_t r[16];
+                        tmem_ld_16x256b_x4(tq + ((uint32_t)(16 * h2) << 16) + ch * 32, r);
+                        tmem_ld_wait16(r);
+                        if (h2 == 1 && ch + 4 >= nchunks) {          // last TMEM read of this warp for this tile
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+                            released = true;
+                        }
+                        uint32_t yw[4][2], xw[4][2];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 s2 = *reinterpret_cast<const float2*>(s + ch * 32 + 8 * k + 2 * c);
+                            const float2 b2 = *reinterpret_cast<const float2*>(b + ch * 32 + 8 * k + 2 * c);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int i = 2 * h2 + h;
+                                const float x0 = fmaf(__uint_as_float(r[4 * k + 2 * h]), rs[i], nmr[i]);
+                                const float x1 = fmaf(__uint_as_float(r[4 * k + 2 * h + 1]), rs[i], nmr[i]);
+                                yw[k][h] = pack_bf16(fmaxf(0.f, fmaf(x0, s2.x, b2.x)), fmaxf(0.f, fmaf(x1, s2.y, b2.y)));
+                                xw[k][h] = pack_bf16(x0, x1);
+                            }
+                        }
+                        const long long row0 = m0 + quad * 32 + rq + 16 * h2, row1 = row0 + 8;
+                        store_pairs<FULLSEC, false>(Y, HN, yw, row0, row1, row0 < M, row1 < M, ch * 32, c);
+                        if (XH) store_pairs<FULLSEC, true>(XH, HN, xw, row0, row1, row0 < M, row1 < M, ch * 32, c);
+                    }
+                }
+            }
+            if (!released) {                                 // column group without chunks (HN < 128)
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+            }
+        }
+    }
+    p_teardown(p.tmem_base, warp);
+}
+
+template <bool FULLSEC>
+__global__ void __launch_bounds__(P_THREADS, 1)
+dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmXH, const float* __restrict__ scale,
+                   const float* __restrict__ bias, const float* __restrict__ rstd_in,
+                   __nv_bfloat16* __restrict__ DZ, float* __restrict__ dscale, float* __restrict__ dbias,
+                   int M, int K, int HN, int a_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (M + BM - 1) / BM;
+    PState p = p_prologue(smem_raw, &tmA, &tmB, M, K, HN, a_stages, BWD_XH_BUFS * 16384, scale, bias);
+    if (warp < 2) {
+        p_mainloop<BWD_XH_BUFS>(&tmA, &tmB, &tmXH, p.smem, p.L, p.bars, p.tmem_base, warp, lane, num_tiles, K, HN,
+                                a_stages, 1);
+    } else {
+        const int quad = warp & 3, grp = (warp - 2) >> 2;
+        const int c = lane & 3, rq = lane >> 2;
+        const float* s = p.fsm;
+        const float* b = p.fsm + HN;
+        float* cs_sm = p.fsm + 2 * HN;
+        float* cb_sm = p.fsm + 3 * HN;
+        float* part = p.fsm + 4 * HN;
+        const uint8_t* ring = p.smem + p.L.stage_off;
+        const int nchunks = HN / 32, num_panels = HN / 64;
+        const float invH = 1.f / (float)HN;
+        float cs[2][8], cb[2][8];                            // per-feature sums of du*xhat / du, whole kernel
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cs[cc][j] = 0.f; cb[cc][j] = 0.f; }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int m0 = tile * BM;
+            float rstd[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = m0 + quad * 32 + rq + 8 * i;
+                rstd[i] = row < M ? rstd_in[row] : 0.f;
+            }
+            const uint32_t tq = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
+            const int xbase = it * num_panels;               // producer's panel sequence number of this tile
+            mbar_wait(&p.bars.acc_full[buf], (it >> 1) & 1);
+            tcgen05_fence_after();
+            // pass 1: ReLU mask, dxhat, row sums m1 = sum(dxhat), m2 = sum(dxhat * xhat), feature sums;
+            // (rstd * dxhat, xhat) left as bf16x2 words in the accumulator cells
+            float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int ch = grp + 4 * cc;
+                if (ch < nchunks) {
+                    const int xit = xbase + (ch >> 1);
+                    const int xs = xit % BWD_XH_BUFS;
+                    mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
+                    const uint8_t* pan = ring + xs * 16384;
+                    const int hf = ch & 1;
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        uint32_t r[16];
+                        const uint32_t ta = tq + ((uint32_t)(16 * h2) << 16) + ch * 32;
+                        tmem_ld_16x256b_x4(ta, r);
+                        tmem_ld_wait16(r);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 s2 = *reinterpret_cast<const float2*>(s + ch * 32 + 8 * k + 2 * c);
+                            const float2 b2 = *reinterpret_cast<const float2*>(b + ch * 32 + 8 * k + 2 * c);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int i = 2 * h2 + h;
+                                const int rt = quad * 32 + rq + 8 * i;            // rt & 7 == rq
+                                const uint32_t xw = *reinterpret_cast<const uint32_t*>(
+                                    pan + rt * 128 + (((hf * 4 + k) ^ rq) << 4) + 4 * c);
+                                const float xh0 = bf16lo(xw), xh1 = bf16hi(xw);
+                                const float dy0 = __uint_as_float(r[4 * k + 2 * h]);
+                                const float dy1 = __uint_as_float(r[4 * k + 2 * h + 1]);
+                                const float du0 = (fmaf(xh0, s2.x, b2.x) > 0.f) ? dy0 : 0.f;   // ReLU mask
+                                const float du1 = (fmaf(xh1, s2.y, b2.y) > 0.f) ? dy1 : 0.f;
+                                const float dx0 = du0 * s2.x, dx1 = du1 * s2.y;
+                                m1[i] += dx0;
+                                m2[i] = fmaf(dx0, xh0, m2[i]);
+                                m1[i] += dx1;
+                                m2[i] = fmaf(dx1, xh1, m2[i]);
+                                cs[cc][2 * k] = fmaf(du0, xh0, cs[cc][2 * k]);
+                                cs[cc][2 * k + 1] = fmaf(du1, xh1, cs[cc][2 * k + 1]);
+                                cb[cc][2 * k] += du0;
+                                cb[cc][2 * k + 1] += du1;
+                                r[4 * k + 2 * h] = pack_bf16(dx0 * rstd[i], dx1 * rstd[i]);
+                                r[4 * k + 2 * h + 1] = xw;
+                            }
+                        }
+                        tmem_st_16x256b_x4(ta, r);
+                    }
+                    tmem_st_wait();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p.bars.xh_empty[xs]);       // this warp is done with the panel
+                }
+            }
+            row_totals(part, buf, grp, quad, rq, c, m1, m2);
+            // dz = rstd*dxhat - rstd*mean(dxhat) - xhat * rstd*mean(dxhat*xhat), on packed bf16 pairs
+            __nv_bfloat162 nc1[4], nc2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                nc1[i] = __float2bfloat162_rn(-rstd[i] * m1[i] * invH);
+                nc2[i] = __float2bfloat162_rn(-rstd[i] * m2[i] * invH);
+            }
+            bool released = false;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int ch = grp + 4 * cc;
+                if (ch < nchunks) {
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        uint32_t r[16];
+                        tmem_ld_16x256b_x4(tq + ((uint32_t)(16 * h2) << 16) + ch * 32, r);
+                        tmem_ld_wait16(r);
+                        if (h2 == 1 && ch + 4 >= nchunks) {
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+                            released = true;
+                        }
+                        uint32_t o[4][2];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int i = 2 * h2 + h;
+                                const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r[4 * k + 2 * h]);
+                                const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&r[4 * k + 2 * h + 1]);
+                                const __nv_bfloat162 dz = __hfma2(nc2[i], x, __hadd2(a, nc1[i]));
+                                o[k][h] = *reinterpret_cast<const uint32_t*>(&dz);
+                            }
+                        const long long row0 = m0 + quad * 32 + rq + 16 * h2, row1 = row0 + 8;
+                        store_pairs<FULLSEC, false>(DZ, HN, o, row0, row1, row0 < M, row1 < M, ch * 32, c);
+                    }
+                }
+            }
+            if (!released) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+            }
+        }
+        // per-feature sums: reduce over the 8 row lanes once, then across quadrants through shared memory
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int ch = grp + 4 * cc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = cs[cc][j], d = cb[cc][j];
+#pragma unroll
+                for (int o = 4; o <= 16; o <<= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    d += __shfl_xor_sync(0xffffffffu, d, o);
+                }
+                if (rq == 0 && ch < nchunks) {
+                    const int col = ch * 32 + 8 * (j >> 1) + 2 * c + (j & 1);
+                    atomicAdd(&cs_sm[col], a);
+                    atomicAdd(&cb_sm[col], d);
+                }
+            }
+        }
+        named_bar_sync(5, 512);                              // all shared-memory column sums are final
+        for (int k = threadIdx.x - 64; k < HN; k += 512) {
+            atomicAdd(dscale + k, cs_sm[k]);
+            atomicAdd(dbias + k, cb_sm[k]);
+        }
+    }
+    p_teardown(p.tmem_base, warp);
+}
+
 }  // namespace
 
 namespace tcp {
@@ -595,6 +954,14 @@ static int pick_stages(int K, int HN, int staging_bytes, int floor_stages) {
     int st = floor_stages;
     while (st < cap && st < MAX_A_STAGES && p_layout(K, HN, st + 1, staging_bytes).total <= 227 * 1024) ++st;
     return st;
+}
+
+// MLB_TC_EPI: 0 = first-generation epilogues (32x32b rows, shared-memory transposes), 1 = second
+// generation (16x256b fragments, register-resident feature sums, packed pass 2) with full-sector
+// stores, 2 = second generation with direct 4-byte stores.
+static int epi_mode() {
+    static const int mode = [] { const char* v = getenv("MLB_TC_EPI"); return v ? atoi(v) : 0; }();
+    return mode;
 }
 
 bool persist_ok(int M, int K, int HN) {
@@ -618,7 +985,12 @@ int launch_fwd_persist(cudaStream_t st, const void* X, const void* Wt, const flo
     if (e != cudaSuccess) return (int)e;
     const int tiles = (M + BM - 1) / BM;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    e = launch_pdl(fwd_persist_kernel, dim3(grid), dim3(P_THREADS), smem, st, tA, tB, scale, bias,
+    auto kern = epi_mode() == 1 ? fwd_persist2_kernel<true> : (epi_mode() == 2 ? fwd_persist2_kernel<false> : fwd_persist_kernel);
+    if (epi_mode() != 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    e = launch_pdl(kern, dim3(grid), dim3(P_THREADS), smem, st, tA, tB, scale, bias,
                    static_cast<__nv_bfloat16*>(Y), static_cast<__nv_bfloat16*>(XH), rstd, M, K, HN, a_stages);
     if (e != cudaSuccess) return (int)e;
     return MLB_OK;
@@ -659,7 +1031,12 @@ int launch_dx_persist(cudaStream_t st, const void* DZ_in, const void* W, const f
     if (e != cudaSuccess) return (int)e;
     const int tiles = (M + BM - 1) / BM;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    e = launch_pdl(dx_persist_kernel, dim3(grid), dim3(P_THREADS), smem, st, tA, tB, tXH, scale, bias, rstd,
+    auto kern = epi_mode() == 1 ? dx_persist2_kernel<true> : (epi_mode() == 2 ? dx_persist2_kernel<false> : dx_persist_kernel);
+    if (epi_mode() != 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    e = launch_pdl(kern, dim3(grid), dim3(P_THREADS), smem, st, tA, tB, tXH, scale, bias, rstd,
                    static_cast<__nv_bfloat16*>(DZ_out), dscale, dbias, M, K, HN, a_stages);
     if (e != cudaSuccess) return (int)e;
     return MLB_OK;
