@@ -124,6 +124,19 @@ int mlb_ema_normalize_f32(void* stream, const float* state, int dim, const float
 int mlb_ema_invert_f32(void* stream, const float* state, int dim, const float* x,
                        float* out, long long rows);
 
+/* ObservationsEMANormalizer statistics (ml/observations.py:71-132, ml/rollouts.py:670-678):      */
+/* mlb_obs_moments_f32: raw f64 [D][2] = per-feature {sum, sum of squares} over the N rows of one  */
+/* step's raw observations (what a data-parallel run SUM-all-reduces);                            */
+/* mlb_obs_stats_merge_f32: raw [T][D][2] of the T steps of an update -> (mean, var) f32 [D] by     */
+/* the reference's running equal-weight Chan merge (EMANormalizer.update_input_stats,             */
+/* ml/moving_avg.py:103-129; count = rows per step); feed the result to mlb_ema_update_f32.        */
+int mlb_obs_moments_f32(void* stream, const float* obs, long long N, int D, double* raw);
+int mlb_obs_stats_merge_f32(void* stream, const double* raw, int T, double count, int D,
+                            float* mean_out, float* var_out);
+/* EMAEstimate.update_estimates (ml/moving_avg.py:22-44).  state: f32 {mu, mu_biased} followed by   */
+/* the int32 counter N; x: device f32 scalar (the value whose EMA is tracked).                    */
+int mlb_ema_estimate_update_f32(void* stream, float* state, const float* x, float decay);
+
 /* Per-step episodic-return bookkeeping of the rollout loop (ml/rollouts.py:938-939,971-973): */
 /* er = r + gamma*er; trace[n] = er (may be NULL; feeds the 'Env Returns' metric);           */
 /* er = done ? 0 : er.                                                                       */
@@ -150,6 +163,16 @@ int mlb_threefry_bits(void* stream, const uint32_t* key, uint32_t* out, long lon
 size_t mlb_ppo_permutations_workspace(int E, long long J);
 int mlb_ppo_permutations(void* stream, uint32_t* key, int32_t* perm, int E, long long J,
                          int partitionable, void* ws, size_t ws_bytes);
+/* The same shuffle applied to an arbitrary int32 array `values` [J] (device; shared by all E     */
+/* epochs): perm[e] = random.permutation(rnd_e, values) -- the filter_advantages /               */
+/* importance-sampling branches of _ppo permute `valid_inds` (ml/ppo.py:445-451).                */
+int mlb_ppo_permutations_of(void* stream, uint32_t* key, const int32_t* values, int32_t* perm,
+                            int E, long long J, int partitionable, void* ws, size_t ws_bytes);
+/* Ascending in-place sort of n_pad (a power of two, mlb_sort_pad(n)) u64 keys: the bitonic       */
+/* network behind the permutations, exposed for the argsort / top-k selections below (a key is    */
+/* (order-preserving 32-bit value << 32) | index, pads are ~0).                                   */
+long long mlb_sort_pad(long long n);
+int mlb_sort_u64(void* stream, unsigned long long* keys, long long n_pad);
 
 /* ------------------------------------------------------------------------------------ */
 /* K5: minibatch gather straight from the [C, T', P=1, B, *leaf] store                      */
@@ -161,6 +184,42 @@ int mlb_mb_gather(void* stream, const void* store, const int32_t* idx, void* out
 /* rnn_start_states [C, B, row] -> [M, row] (ml/rollouts.py:800-804 + :321-323) */
 int mlb_mb_gather_rnn(void* stream, const void* store, const int32_t* idx, void* out,
                       int C, long long B, long long M, long long row_bytes);
+/* ------------------------------------------------------------------------------------ */
+/* Alternate minibatch selections of _ppo (ml/ppo.py:374-435).  advantages / values / returns are  */
+/* the [C, T', B] rollout-store leaves (P = 1); flattened-time element f = j*T' + s of trajectory  */
+/* j = c*B + b (RolloutData.flatten_time, ml/rollouts.py:331-334).                                 */
+/* filter_advantages: mlb_filter_adv_keys builds the sort keys of abs(advantage) (descending,      */
+/*   stable) for all n = C*T'*B elements (+ pads up to n_pad) and max_abs = max abs(advantage);    */
+/*   after mlb_sort_u64 and the EMAEstimate update, mlb_filter_adv_select counts the elements with */
+/*   abs(adv) >= 0.01 * est_mu, sets counts = {num_minibatches, num_above_threshold} (:392-402)    */
+/*   and valid_inds[i] = sorted index i < num_minibatches*M else -1 (:403-405).                    */
+/* mlb_partition_valid: per row of x [E][J], entries >= 0 first in order, then -1 (:453-458).       */
+/* mlb_flat_time_index: flattened-time ids -> row ids of the [C*T'*B] store (-1 stays -1), so that  */
+/*   mlb_mb_gather_multi(C=1, Tp=1, B=C*T'*B) gathers single-step "trajectories".                  */
+/* importance_sample_trajectories: scores[j] = mean_s abs(adv) + mean_s abs(values - returns)      */
+/*   (:419-425); probs = softmax(scores), weights = (1/J)/probs (:426-427); mlb_gumbel_topk_keys =  */
+/*   the keys of jax.random.choice(key, J, replace=False, p=probs) (Gumbel top-k: g = gumbel(key,   */
+/*   (J,)) + log p, descending); after mlb_sort_u64, mlb_take_sorted_indices reads the first k ids. */
+/* mlb_gather_f32: out[i] = src[idx[i]] (0 where idx < 0): traj_weights[mb_inds] (:468).            */
+/* ------------------------------------------------------------------------------------ */
+int mlb_filter_adv_keys(void* stream, const float* advantages, int C, int Tp, long long B,
+                        long long n_pad, unsigned long long* keys, float* max_abs);
+int mlb_filter_adv_select(void* stream, const unsigned long long* keys_sorted, long long n,
+                          long long M, const float* max_adv_est_mu, int32_t* valid_inds,
+                          int32_t* counts);
+int mlb_partition_valid(void* stream, const int32_t* x, int32_t* out, int E, long long J);
+int mlb_flat_time_index(void* stream, const int32_t* idx, long long n, int Tp, long long B,
+                        int32_t* out);
+int mlb_traj_scores_f32(void* stream, const float* advantages, const float* values,
+                        const float* returns, int C, int Tp, long long B, float* scores);
+int mlb_softmax_weights_f32(void* stream, const float* scores, long long J, float* probs,
+                            float* weights);
+int mlb_gumbel_topk_keys(void* stream, const uint32_t* key, const float* probs, long long J,
+                         long long J_pad, int partitionable, unsigned long long* keys);
+int mlb_take_sorted_indices(void* stream, const unsigned long long* keys_sorted, long long k,
+                            int32_t* out);
+int mlb_gather_f32(void* stream, const float* src, const int32_t* idx, long long n, float* out);
+
 /* All leaves of one minibatch in a single launch.  Per leaf: store [C, T', B, row], out            */
 /* [T', M, row] (may be NULL when out_bf16 is set), out_bf16 (may be NULL): the same rows converted */
 /* f32 -> bf16 (row_bytes % 16 == 0) -- the tensor-core forward's A operand.  Up to 8 leaves.       */

@@ -57,6 +57,21 @@ SIGNATURES = {
     'mlb_threefry_bits': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_ppo_permutations_workspace': (c_size_t, [c_int, c_ll]),
     'mlb_ppo_permutations': (c_int, [P, P, P, c_int, c_ll, c_int, P, c_size_t]),
+    'mlb_ppo_permutations_of': (c_int, [P, P, P, P, c_int, c_ll, c_int, P, c_size_t]),
+    'mlb_sort_pad': (c_ll, [c_ll]),
+    'mlb_sort_u64': (c_int, [P, P, c_ll]),
+    'mlb_obs_moments_f32': (c_int, [P, P, c_ll, c_int, P]),
+    'mlb_obs_stats_merge_f32': (c_int, [P, P, c_int, ctypes.c_double, c_int, P, P]),
+    'mlb_ema_estimate_update_f32': (c_int, [P, P, P, c_float]),
+    'mlb_filter_adv_keys': (c_int, [P, P, c_int, c_int, c_ll, c_ll, P, P]),
+    'mlb_filter_adv_select': (c_int, [P, P, c_ll, c_ll, P, P, P]),
+    'mlb_partition_valid': (c_int, [P, P, P, c_int, c_ll]),
+    'mlb_flat_time_index': (c_int, [P, P, c_ll, c_int, c_ll, P]),
+    'mlb_traj_scores_f32': (c_int, [P, P, P, P, c_int, c_int, c_ll, P]),
+    'mlb_softmax_weights_f32': (c_int, [P, P, c_ll, P, P]),
+    'mlb_gumbel_topk_keys': (c_int, [P, P, P, c_ll, c_ll, c_int, P]),
+    'mlb_take_sorted_indices': (c_int, [P, P, c_ll, P]),
+    'mlb_gather_f32': (c_int, [P, P, P, c_ll, P]),
     'mlb_mb_gather': (c_int, [P, P, P, P, c_int, c_int, c_ll, c_ll, c_ll]),
     'mlb_mb_gather_rnn': (c_int, [P, P, P, P, c_int, c_ll, c_ll, c_ll]),
     'mlb_gemm_f32': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -260,7 +260,7 @@ returns_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ do
     }
 }
 
-struct ScanPlan { int vec; int block; unsigned grid; };
+struct ScanPlan { int vec; int block; unsigned grid; int deep; };
 
 // Pick the widest vector that still leaves >= ~2 resident 256-thread CTAs per SM; narrower
 // vectors (more threads) for mid-size N so all 148 SMs have loads in flight.
@@ -273,6 +273,9 @@ ScanPlan plan_scan(long long N, bool align16) {
     const long long threads = N / p.vec;
     p.block = threads >= (long long)MLB_NUM_SMS * 512 ? 256 : (threads >= MLB_NUM_SMS * 128 ? 128 : 64);
     p.grid = mlb_cdiv(threads, p.block);
+    // fewer than ~1024 threads per SM: a thread must keep more bytes in flight to cover the HBM
+    // latency-bandwidth product (measured r2: N = 64K columns, U = 8 -> 0.69 of peak) -> 16-step chunks
+    p.deep = (p.vec == 1 && threads < (long long)MLB_NUM_SMS * 1024) ? 1 : 0;
     return p;
 }
 
@@ -314,6 +317,7 @@ MLB_API int mlb_gae_f32(void* stream, const float* rewards, const float* values,
     } while (0)
     if (p.vec == 4) LAUNCH(4, 4);
     else if (p.vec == 2) LAUNCH(2, 8);
+    else if (p.deep) LAUNCH(1, 16);
     else LAUNCH(1, 8);
 #undef LAUNCH
     MLB_CHECK_LAUNCH();
@@ -336,6 +340,7 @@ MLB_API int mlb_returns_f32(void* stream, const float* rewards, const uint8_t* d
     cudaStream_t s = mlb_stream(stream);
     if (p.vec == 4) returns_kernel<4, 4><<<p.grid, p.block, 0, s>>>(rewards, dones, bootstrap, returns, T, N, gamma);
     else if (p.vec == 2) returns_kernel<2, 8><<<p.grid, p.block, 0, s>>>(rewards, dones, bootstrap, returns, T, N, gamma);
+    else if (p.deep) returns_kernel<1, 16><<<p.grid, p.block, 0, s>>>(rewards, dones, bootstrap, returns, T, N, gamma);
     else returns_kernel<1, 8><<<p.grid, p.block, 0, s>>>(rewards, dones, bootstrap, returns, T, N, gamma);
     MLB_CHECK_LAUNCH();
     return MLB_OK;

@@ -116,13 +116,13 @@ bitonic_global_kernel(unsigned long long* __restrict__ data, long long Jpad, lon
 }
 
 __global__ void perm_apply_kernel(const unsigned long long* __restrict__ comp,
-                                  const int32_t* __restrict__ in, int32_t* __restrict__ out,
-                                  long long J, long long Jpad) {
+                                  const int32_t* __restrict__ in, long long in_stride,
+                                  int32_t* __restrict__ out, long long J, long long Jpad) {
     const int e = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= J) return;
     const uint32_t pos = comp ? (uint32_t)comp[(long long)e * Jpad + i] : (uint32_t)i;
-    out[(long long)e * J + i] = in ? in[(long long)e * J + pos] : (int32_t)pos;
+    out[(long long)e * J + i] = in ? in[(long long)e * in_stride + pos] : (int32_t)pos;
 }
 
 long long next_pow2(long long n) { long long p = 1; while (p < n) p <<= 1; return p; }
@@ -130,6 +130,27 @@ long long next_pow2(long long n) { long long p = 1; while (p < n) p <<= 1; retur
 int shuffle_rounds(long long n) {
     if (n <= 1) return 0;
     return (int)ceil(3.0 * log((double)n) / log(4294967295.0));
+}
+
+// ascending sort of E independent rows of Jpad (a power of two) u64 keys: shared-memory tiles for
+// strides < tile, one global compare-exchange pass per larger stride
+int sort_rows_u64(cudaStream_t s, unsigned long long* comp, int E, long long Jpad) {
+    const int tile = (int)(Jpad < SORT_TILE ? Jpad : SORT_TILE);
+    if (tile < 2) return MLB_OK;
+    const size_t smem = (size_t)tile * sizeof(unsigned long long);
+    const dim3 tgrid((unsigned)(Jpad / tile), (unsigned)E);
+    const int tthreads = tile / 2 < SORT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : SORT_THREADS;
+    bitonic_tile_kernel<<<tgrid, tthreads, smem, s>>>(comp, Jpad, tile, 2, tile);
+    MLB_CHECK_LAUNCH();
+    for (long long k = 2ll * tile; k <= Jpad; k <<= 1) {
+        for (long long j = k >> 1; j >= tile; j >>= 1) {
+            bitonic_global_kernel<<<dim3(mlb_cdiv(Jpad / 2, 256), E), 256, 0, s>>>(comp, Jpad, k, j);
+            MLB_CHECK_LAUNCH();
+        }
+        bitonic_tile_kernel<<<tgrid, tthreads, smem, s>>>(comp, Jpad, tile, k, k);
+        MLB_CHECK_LAUNCH();
+    }
+    return MLB_OK;
 }
 
 }  // namespace
@@ -156,8 +177,8 @@ MLB_API size_t mlb_ppo_permutations_workspace(int E, long long J) {
            (size_t)E * Jpad * sizeof(unsigned long long) + (size_t)E * J * sizeof(int32_t);
 }
 
-MLB_API int mlb_ppo_permutations(void* stream, uint32_t* key, int32_t* perm, int E, long long J,
-                                 int partitionable, void* ws, size_t ws_bytes) {
+static int permutations_impl(void* stream, uint32_t* key, const int32_t* values, int32_t* perm, int E,
+                             long long J, int partitionable, void* ws, size_t ws_bytes) {
     MLB_REQUIRE(key && perm && E > 0 && J > 0 && J < (1ll << 31));
     if (!ws || ws_bytes < mlb_ppo_permutations_workspace(E, J)) return MLB_EWS;
     const int rounds = shuffle_rounds(J);
@@ -174,37 +195,45 @@ MLB_API int mlb_ppo_permutations(void* stream, uint32_t* key, int32_t* perm, int
     perm_keys_kernel<<<1, 32, 0, s>>>(key, subkeys, E, rounds, partitionable);
     MLB_CHECK_LAUNCH();
     if (rounds == 0) {
-        perm_apply_kernel<<<dim3(mlb_cdiv(J, 256), E), 256, 0, s>>>(nullptr, nullptr, perm, J, Jpad);
+        perm_apply_kernel<<<dim3(mlb_cdiv(J, 256), E), 256, 0, s>>>(nullptr, values, 0, perm, J, Jpad);
         MLB_CHECK_LAUNCH();
         return MLB_OK;
     }
     const int tile = (int)(Jpad < SORT_TILE ? Jpad : SORT_TILE);
-    const size_t smem = (size_t)tile * sizeof(unsigned long long);
-    const dim3 tgrid((unsigned)(Jpad / tile), (unsigned)E);
-    const int tthreads = tile / 2 < SORT_THREADS ? (tile / 2 < 32 ? 32 : tile / 2) : SORT_THREADS;
     // ping-pong so the last round lands in `perm`
     int32_t* bufs[2] = {perm, tmp};
     int cur = (rounds % 2 == 1) ? 0 : 1;   // buffer written by round 0
-    const int32_t* prev = nullptr;
+    const int32_t* prev = values;        // round 0 permutes `values` (NULL: arange(J)), shared by all epochs
+    const long long in_stride = 0;
     for (int r = 0; r < rounds; ++r) {
         perm_fill_kernel<<<dim3(mlb_cdiv(Jpad, 256), E), 256, 0, s>>>(subkeys, r, comp, J, Jpad, partitionable);
         MLB_CHECK_LAUNCH();
         if (tile >= 2) {
-            bitonic_tile_kernel<<<tgrid, tthreads, smem, s>>>(comp, Jpad, tile, 2, tile);
-            MLB_CHECK_LAUNCH();
+            const int rc = sort_rows_u64(s, comp, E, Jpad);
+            if (rc != MLB_OK) return rc;
         }
-        for (long long k = 2ll * tile; k <= Jpad; k <<= 1) {
-            for (long long j = k >> 1; j >= tile; j >>= 1) {
-                bitonic_global_kernel<<<dim3(mlb_cdiv(Jpad / 2, 256), E), 256, 0, s>>>(comp, Jpad, k, j);
-                MLB_CHECK_LAUNCH();
-            }
-            bitonic_tile_kernel<<<tgrid, tthreads, smem, s>>>(comp, Jpad, tile, k, k);
-            MLB_CHECK_LAUNCH();
-        }
-        perm_apply_kernel<<<dim3(mlb_cdiv(J, 256), E), 256, 0, s>>>(comp, prev, bufs[cur], J, Jpad);
+        perm_apply_kernel<<<dim3(mlb_cdiv(J, 256), E), 256, 0, s>>>(comp, prev, r == 0 ? in_stride : J, bufs[cur], J, Jpad);
         MLB_CHECK_LAUNCH();
         prev = bufs[cur];
         cur ^= 1;
     }
     return MLB_OK;
+}
+
+MLB_API int mlb_ppo_permutations(void* stream, uint32_t* key, int32_t* perm, int E, long long J,
+                                 int partitionable, void* ws, size_t ws_bytes) {
+    return permutations_impl(stream, key, nullptr, perm, E, J, partitionable, ws, ws_bytes);
+}
+
+MLB_API int mlb_ppo_permutations_of(void* stream, uint32_t* key, const int32_t* values, int32_t* perm, int E,
+                                    long long J, int partitionable, void* ws, size_t ws_bytes) {
+    MLB_REQUIRE(values);
+    return permutations_impl(stream, key, values, perm, E, J, partitionable, ws, ws_bytes);
+}
+
+MLB_API long long mlb_sort_pad(long long n) { return next_pow2(n); }
+
+MLB_API int mlb_sort_u64(void* stream, unsigned long long* keys, long long n_pad) {
+    MLB_REQUIRE(keys && n_pad > 0 && (n_pad & (n_pad - 1)) == 0);
+    return sort_rows_u64(mlb_stream(stream), keys, 1, n_pad);
 }

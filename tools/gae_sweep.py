@@ -63,6 +63,29 @@ def main():
             ret = torch.empty_like(r)
             t = time_op(lambda: K.gae(r, v, d, b, 0.99, 0.95, advantages=adv, returns=ret), flush)
             by = 17 * T * N + 4 * N
+            # points larger than L2: also time 24 launches back to back over rotating buffer sets whose
+            # total exceeds 2 x L2 (every launch cold, no per-launch event / host gap in the bracket)
+            t_b2b = None
+            if by > 126e6 and by * 3 < 40e9:
+                nsets = max(2, int(260e6 // by) + 2)
+                sets = [(torch.randn(T, N, device=dev), torch.randn(T, N, device=dev),
+                         torch.rand(T, N, device=dev) < 0.02, torch.randn(N, device=dev),
+                         torch.empty(T, N, device=dev), torch.empty(T, N, device=dev)) for _ in range(nsets - 1)]
+                sets.append((r, v, d, b, adv, ret))
+                fns = [(lambda q=q: K.gae(q[0], q[1], q[2], q[3], 0.99, 0.95, advantages=q[4], returns=q[5])) for q in sets]
+                for f in fns:
+                    f()
+                torch.cuda.synchronize()
+                torch.cuda._sleep(400000)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                reps = 24
+                for i in range(reps):
+                    fns[i % nsets]()
+                e1.record()
+                torch.cuda.synchronize()
+                t_b2b = e0.elapsed_time(e1) * 1e-3 / reps
+                del sets, fns
             mbuf = torch.zeros(80, dtype=torch.uint8, device=dev)
             ws = torch.empty(mlb._lib.lib().mlb_gae_workspace(T, N) + 16, dtype=torch.uint8, device=dev)
             tm = time_op(lambda: K.gae(r, v, d, b, 0.99, 0.95, advantages=adv, returns=ret,
@@ -89,7 +112,8 @@ def main():
             bit_exact = bool(np.array_equal(adv.cpu().numpy(), a_c))
             del rh, vh, dh, bh, a_c
             row = dict(T=T, N=N, bytes=by, gae_us=t * 1e6, cpu_c_ms=cpu_c * 1e3, cpu_threads=os.cpu_count(),
-                       cpu_numpy_ms=None if cpu_np is None else cpu_np * 1e3, bit_exact_vs_c_oracle=bit_exact, gae_gbs=by / t / 1e9, gae_frac=by / t / 1e9 / pk,
+                       cpu_numpy_ms=None if cpu_np is None else cpu_np * 1e3, bit_exact_vs_c_oracle=bit_exact, gae_b2b_us=None if t_b2b is None else t_b2b * 1e6,
+                       gae_b2b_frac=None if t_b2b is None else by / t_b2b / 1e9 / pk, gae_gbs=by / t / 1e9, gae_frac=by / t / 1e9 / pk,
                        gae_metrics_us=tm * 1e6, gae_metrics_gbs=by / tm / 1e9,
                        zscore_us=tz * 1e6, zscore_gbs=8 * T * N / tz / 1e9,
                        returns_us=tr * 1e6, returns_gbs=(9 * T * N + 4 * N) / tr / 1e9,
@@ -97,7 +121,8 @@ def main():
             rows.append(row)
             print(f"T={T:4d} N={N:8d} {by/1e6:9.1f} MB  gae {t*1e6:9.1f} us {row['gae_gbs']:7.0f} GB/s "
                   f"({row['gae_frac']:.2f})  +metrics {row['gae_metrics_gbs']:7.0f}  zscore {row['zscore_gbs']:7.0f}  "
-                  f"returns {row['returns_gbs']:7.0f}  cpuC {cpu_c*1e3:8.1f} ms  exact={bit_exact}", flush=True)
+                  f"returns {row['returns_gbs']:7.0f}  cpuC {cpu_c*1e3:8.1f} ms  exact={bit_exact}  "
+                  f"b2b {'' if t_b2b is None else round(by / t_b2b / 1e9 / pk, 3)}", flush=True)
             del r, v, d, b, adv, ret
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump(dict(peak_gbs=pk, peak_src=src, rows=rows),
