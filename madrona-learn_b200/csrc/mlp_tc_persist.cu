@@ -73,32 +73,43 @@ __device__ __forceinline__ void p_mainloop(const CUtensorMap* tmA, const CUtenso
     const int num_kb = (K + BK - 1) / BK;
     if (warp == 0) {
         if (lane == 0) {
-            // W and the first A_STAGES activation k-blocks were issued by p_prologue (p_prime)
+            // W and the first A_STAGES activation k-blocks were issued by p_prologue (p_prime).
+            // ONE thread feeds two independent rings -- the GEMM operand k-blocks (paced by the MMA
+            // warp) and, for the backward, the xhat panels (paced by the epilogue warps) -- by
+            // polling both without blocking: a full operand ring (the MMA of the next tile waits for an
+            // accumulator buffer) must not hold back the panels the CURRENT epilogue is waiting for.
             const int num_panels = HN / 64;
             const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
             const int a_total = my_tiles * num_kb;
+            const int per_tile = num_panels * xh_reps;
+            const int x_total = XH_BUFS > 0 ? my_tiles * per_tile : 0;
             int it = a_total < A_STAGES ? a_total : A_STAGES, xit = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                // the NEXT tile's operand first: its MMA overlaps this tile's epilogue, while the xhat
-                // panels below are paced by that epilogue
-                const int a_target = (ti + 2) * num_kb < a_total ? (ti + 2) * num_kb : a_total;
-                for (; it < a_target; ++it) {
+            uint32_t idle = 0;
+            while (it < a_total || xit < x_total) {
+                bool progress = false;
+                if (XH_BUFS > 0 && xit < x_total) {
+                    const int s = xit % (XH_BUFS > 0 ? XH_BUFS : 1);
+                    if (mbar_test(&bars.xh_empty[s], ((xit / (XH_BUFS > 0 ? XH_BUFS : 1)) & 1) ^ 1)) {
+                        const int tile = blockIdx.x + (xit / per_tile) * gridDim.x;
+                        const int pnl = (xit % per_tile) % num_panels;
+                        mbar_expect_tx(&bars.xh_full[s], 16384u);
+                        tma_load_2d(tmXH, &bars.xh_full[s], smem + L.stage_off + s * 16384, pnl * 64, tile * BM);
+                        ++xit;
+                        progress = true;
+                    }
+                }
+                if (it < a_total) {
                     const int s = it % A_STAGES;
-                    const int tile = blockIdx.x + (it / num_kb) * gridDim.x;
-                    mbar_wait_spin(&bars.empty[s], ((it / A_STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&bars.full[s], 16384u);
-                    tma_load_2d(tmA, &bars.full[s], smem + L.a_off + s * 16384, (it % num_kb) * BK, tile * BM);
+                    if (mbar_test(&bars.empty[s], ((it / A_STAGES) & 1) ^ 1)) {
+                        const int tile = blockIdx.x + (it / num_kb) * gridDim.x;
+                        mbar_expect_tx(&bars.full[s], 16384u);
+                        tma_load_2d(tmA, &bars.full[s], smem + L.a_off + s * 16384, (it % num_kb) * BK, tile * BM);
+                        ++it;
+                        progress = true;
+                    }
                 }
-                if (XH_BUFS > 0) {
-                    const int tile = blockIdx.x + ti * gridDim.x;
-                    for (int rep = 0; rep < xh_reps; ++rep)
-                        for (int pnl = 0; pnl < num_panels; ++pnl, ++xit) {
-                            const int s = xit % (XH_BUFS > 0 ? XH_BUFS : 1);
-                            mbar_wait_spin(&bars.xh_empty[s], ((xit / (XH_BUFS > 0 ? XH_BUFS : 1)) & 1) ^ 1);
-                            mbar_expect_tx(&bars.xh_full[s], 16384u);
-                            tma_load_2d(tmXH, &bars.xh_full[s], smem + L.stage_off + s * 16384, pnl * 64, tile * BM);
-                        }
-                }
+                if (progress) idle = 0;
+                else if (++idle > (1u << 28)) __trap();      // never hang the GPU on a protocol bug
             }
         }
     } else if (warp == 1) {
@@ -593,6 +604,16 @@ dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //     packed word so that each lane stores 8 contiguous bytes and the four lanes of a row fill a whole
 //     32-byte sector; otherwise each lane stores its own 4 bytes (half-sector writes merged by L2).
 // ==========================================================================================
+// phase timestamps for tools/probe/phase_profile.cu (never compiled into libmlb200.so)
+#ifdef MLB_PHASE_PROFILE
+__device__ unsigned long long* g_prof = nullptr;
+#define PROF(slot) do { if (g_prof && lane == 0 && (warp == 2 || warp == 17) && it < 8) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    g_prof[(((size_t)blockIdx.x * 8 + it) * 2 + (warp == 17)) * 8 + (slot)] = t_; } } while (0)
+#else
+#define PROF(slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ float sel4(int c, float a0, float a1, float a2, float a3) {
     return c == 0 ? a0 : (c == 1 ? a1 : (c == 2 ? a2 : a3));
 }
@@ -679,8 +700,10 @@ fwd_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int buf = it & 1;
             const int m0 = tile * BM;
             const uint32_t tq = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
+            PROF(0);
             mbar_wait(&p.bars.acc_full[buf], (it >> 1) & 1);
             tcgen05_fence_after();
+            PROF(1);
             // pass 1: row statistics
             float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -705,7 +728,9 @@ fwd_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
             }
+            PROF(3);
             row_totals(part, buf, grp, quad, rq, c, sum, sq);
+            PROF(4);
             float rs[4], nmr[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -759,6 +784,7 @@ fwd_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
             }
+            PROF(5);
         }
     }
     p_teardown(p.tmem_base, warp);
@@ -806,8 +832,10 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             const uint32_t tq = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
             const int xbase = it * num_panels;               // producer's panel sequence number of this tile
+            PROF(0);
             mbar_wait(&p.bars.acc_full[buf], (it >> 1) & 1);
             tcgen05_fence_after();
+            PROF(1);
             // pass 1: ReLU mask, dxhat, row sums m1 = sum(dxhat), m2 = sum(dxhat * xhat), feature sums;
             // (rstd * dxhat, xhat) left as bf16x2 words in the accumulator cells
             float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -818,6 +846,7 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const int xit = xbase + (ch >> 1);
                     const int xs = xit % BWD_XH_BUFS;
                     mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
+                    if (cc == 0) PROF(2); else PROF(6);
                     const uint8_t* pan = ring + xs * 16384;
                     const int hf = ch & 1;
 #pragma unroll
@@ -861,7 +890,9 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (lane == 0) mbar_arrive(&p.bars.xh_empty[xs]);       // this warp is done with the panel
                 }
             }
+            PROF(3);
             row_totals(part, buf, grp, quad, rq, c, m1, m2);
+            PROF(4);
             // dz = rstd*dxhat - rstd*mean(dxhat) - xhat * rstd*mean(dxhat*xhat), on packed bf16 pairs
             __nv_bfloat162 nc1[4], nc2[4];
 #pragma unroll
@@ -906,6 +937,7 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
             }
+            PROF(5);
         }
         // per-feature sums: reduce over the 8 row lanes once, then across quadrants through shared memory
 #pragma unroll

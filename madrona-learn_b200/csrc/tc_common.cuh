@@ -52,6 +52,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 22)) __trap();      // never hang the GPU on a protocol bug
     }
 }
+// non-blocking probe of a phase (mbarrier.test_wait): lets ONE producer thread serve several
+// independent rings without head-of-line blocking
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // latency-critical single-thread roles (TMA producer, MMA issuer): poll without the suspend hint
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0, spins = 0;

@@ -174,6 +174,43 @@ def ema_invert(state, dim, x, out=None):
     return out
 
 
+def obs_moments(obs, raw_out):
+    """mlb_obs_moments_f32: obs f32 [..., D] -> raw f64 [D, 2] (sum, sumsq over all leading rows)."""
+    D = obs.shape[-1]
+    call('mlb_obs_moments_f32', ptr(obs), c_ll(obs.numel() // D), c_int(D), ptr(raw_out))
+    return raw_out
+
+
+def obs_stats_merge(raw, count, mean=None, var=None):
+    """mlb_obs_stats_merge_f32: raw f64 [T, D, 2] -> (mean, var) f32 [D]."""
+    T, D = raw.shape[0], raw.shape[1]
+    if mean is None:
+        mean = torch.empty(D, dtype=torch.float32, device=raw.device)
+        var = torch.empty(D, dtype=torch.float32, device=raw.device)
+    call('mlb_obs_stats_merge_f32', ptr(raw), c_int(T), ctypes.c_double(count), c_int(D), ptr(mean), ptr(var))
+    return mean, var
+
+
+def ema_estimate_init(device):
+    """EMAEstimate state: [mu, mu_biased | int32 N]."""
+    return torch.zeros(3, dtype=torch.float32, device=device)
+
+
+def ema_estimate_update(state, x, decay):
+    call('mlb_ema_estimate_update_f32', ptr(state), ptr(x), c_float(decay))
+    return state
+
+
+def sort_u64(keys):
+    """In-place ascending sort of a power-of-two-length int64 tensor holding u64 keys."""
+    call('mlb_sort_u64', ptr(keys), c_ll(keys.numel()))
+    return keys
+
+
+def sort_pad(n):
+    return int(lib().mlb_sort_pad(c_ll(n)))
+
+
 # ---------------------------------------------------------------------------------------
 # PRNG
 # ---------------------------------------------------------------------------------------

@@ -51,6 +51,18 @@ class EMANormalizer:
 
 
 @dataclass(frozen=True)
-class EMAEstimate:                                     # :7-44, only used by filter_advantages ("next")
+class EMAEstimate:                                     # :7-44 (max-abs-advantage tracker of filter_advantages)
     decay: float
     eps: float = 1e-5
+
+    def init_estimates(self, x):                      # :12-20 -- state: [mu, mu_biased | int32 N]
+        return K.ema_estimate_init(x.device)
+
+    def update_estimates(self, est, x):               # :22-44 (in place); x: device tensor, its mean is tracked
+        if x.numel() != 1:
+            x = K.moments(x.reshape(-1).float(), 0.0)[0:1]
+        return K.ema_estimate_update(est, x.reshape(1), self.decay)
+
+    @staticmethod
+    def state_dict(est):
+        return {'mu': est[0:1], 'mu_biased': est[1:2], 'N': est[2:3].view(torch.int32)}

@@ -97,8 +97,22 @@ class _PPOWorkspace:
     def __init__(self, cfg, prog, C, Tp, B, dist_ctx):
         dev = prog.device
         E, M = cfg.algo.num_epochs, cfg.algo.minibatch_size
+        self.mode = ('filter' if cfg.filter_advantages else
+                     'importance' if cfg.importance_sample_trajectories else 'default')
+        self.store_dims = (C, Tp, B)
+        if self.mode != 'default' and dist_ctx is not None:
+            raise NotImplementedError('filter_advantages / importance_sample_trajectories are single-GPU')
+        if self.mode == 'filter':
+            # rollout_data.flatten_time() (ml/ppo.py:375, ml/rollouts.py:331-334): every step becomes
+            # its own length-1 trajectory; minibatch_size then counts steps
+            if prog.lstm is not None:
+                raise NotImplementedError('filter_advantages flattens time: feed-forward policies only')
+            C, Tp, B = 1, 1, C * Tp * B
         J = C * B
-        assert J % M == 0, 'num trajectories must be divisible by minibatch_size (ml/ppo.py:439)'
+        if self.mode == 'default':
+            assert J % M == 0, 'num trajectories must be divisible by minibatch_size (ml/ppo.py:439)'
+        else:
+            assert J >= M
         self.E, self.M, self.J, self.nmb, self.rows = E, M, J, J // M, Tp * M
         e = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
         # index-exact data-parallel mode (parallel.py): ONE permutation of the global trajectory ids,
@@ -128,6 +142,24 @@ class _PPOWorkspace:
             self.mb['rnn_start_c'] = e(M, prog.lstm.RH)
             self.mb['rnn_start_h'] = e(M, prog.lstm.RH)
         self.Tp = Tp
+        if self.mode != 'default':
+            npad = K.sort_pad(J)
+            self.sort_keys = e(npad, dtype=torch.int64)               # u64 keys of the argsort / top-k
+            self.valid = e(J, dtype=torch.int32)                      # valid_inds (ml/ppo.py:403-405, :435)
+            self.perm_raw = e(E, J, dtype=torch.int32)
+            self.counts = torch.zeros(2, dtype=torch.int32, device=dev)
+            self.max_abs = e(1)
+            self.idx_tmp = e(M, dtype=torch.int32)
+            self.mb_stats = e(4)
+            self.mb_ret_stats = e(1, 4)
+            self.vn_one = e(1, 4)
+            self.mom_ws = torch.empty(K.lib().mlb_moments_workspace(Tp * M) + 16, dtype=torch.uint8, device=dev)
+            if self.mode == 'importance':
+                self.nsel = cfg.importance_sample_num_minibatches * M
+                assert 0 < self.nsel < J, 'ml/ppo.py:416-417'
+                self.scores, self.probs, self.traj_w = e(J), e(J), e(J)
+                self.mb_w = e(M)
+                self.sample_key = torch.zeros(2, dtype=torch.int32, device=dev)
         self.side = torch.cuda.Stream(device=dev)      # minibatch-gather prefetch stream
         A = prog.A
         g_name, _, g_size = prog.groups[0]
@@ -142,9 +174,6 @@ class _PPOWorkspace:
 def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics, dist_ctx=None,
          ws=None, partitionable=False):
     """ml/ppo.py:366-488, default branch (valid_inds = arange(J), weights = 1)."""
-    if cfg.filter_advantages or cfg.importance_sample_trajectories:
-        raise NotImplementedError('filter_advantages / importance_sample_trajectories are "next" '
-                                  'rows (SURVEY 8f rank 2)')
     prog = policy_state.program
     if bool(cfg.dreamer_v3_critic) != bool(prog.twohot) or cfg.hlgauss_critic:
         raise ValueError('cfg.dreamer_v3_critic must match the critic module (DreamerV3Critic <-> True, '
@@ -153,6 +182,9 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
     C, Tp, B = rollout_data.C, rollout_data.Tp, rollout_data.B
     if ws is None:
         ws = _PPOWorkspace(cfg, prog, C, Tp, B, dist_ctx)
+    if ws.mode != 'default':
+        return _ppo_selected(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics, ws,
+                             partitionable)
     E, M, J, nmb, rows = ws.E, ws.M, ws.J, ws.nmb, ws.rows
     T, N = C * Tp, B
     tx = train_state.tx
@@ -297,4 +329,126 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
         # per-minibatch records overwrite the same slot: the last minibatch wins (App. C.4)
         dst = metrics.slot('Loss', 5)
         call('mlb_copy_bytes', ptr(tw['stats_out'][16:]), ptr(dst), c_size_t(dst.numel()))
+    return policy_state, train_state, metrics
+
+
+def _ppo_selected(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics, ws, partitionable):
+    """The two alternate minibatch selections of ml/ppo.py:374-435 in front of the same epoch x
+    minibatch loop (:445-486).
+
+    filter_advantages (:374-405): time is flattened; valid_inds = the indices of the largest
+    abs(advantage) elements, as many whole minibatches as there are elements >= 1 % of the running
+    (EMAEstimate) maximum; the rest is -1 and is partitioned to the tail of every epoch's
+    permutation.  The minibatch count is data dependent: it is read back once per update (one
+    4-byte device->host copy) and the update runs eagerly (no CUDA graph).
+    importance_sample_trajectories (:407-435): trajectories are drawn without replacement with
+    probability softmax(mean abs(adv) + mean abs(value error)) (Gumbel top-k, jax.random.choice) and
+    weighted by (1/J)/p in the loss."""
+    prog = policy_state.program
+    st = rollout_data.store
+    C0, Tp0, B0 = ws.store_dims
+    E, M, J = ws.E, ws.M, ws.J
+    Tp = ws.Tp                                    # 1 in filter mode
+    rows = Tp * M
+    hp, tx = train_state.hyper_params, train_state.tx
+    score_key = 'advantages' if cfg.compute_advantages else 'returns'
+    normalize_scores = cfg.normalize_advantages if cfg.compute_advantages else cfg.normalize_returns
+    vn = train_state.value_normalizer
+    flat = lambda name: st[name].view(-1) if st[name].dtype != torch.bool else st[name].view(torch.uint8).view(-1)
+    mb_w = None
+    if ws.mode == 'filter':
+        with profile('Filter Advantages'):
+            call('mlb_filter_adv_keys', ptr(flat('advantages')), c_int(C0), c_int(Tp0), c_ll(B0),
+                 c_ll(ws.sort_keys.numel()), ptr(ws.sort_keys), ptr(ws.max_abs))
+            K.sort_u64(ws.sort_keys)
+            est = train_state.max_advantage_est_state
+            train_state.max_advantage_est.update_estimates(est, ws.max_abs)           # :381-388
+            call('mlb_filter_adv_select', ptr(ws.sort_keys), c_ll(J), c_ll(M), ptr(est), ptr(ws.valid),
+                 ptr(ws.counts))
+            nmb = int(ws.counts[0].item())            # data-dependent loop bound (:399-402)
+            nsel = J
+    else:
+        with profile('Importance Sample Trajectories'):
+            call('mlb_traj_scores_f32', ptr(flat('advantages')), ptr(flat('values')), ptr(flat('returns')),
+                 c_int(C0), c_int(Tp0), c_ll(B0), ptr(ws.scores))
+            call('mlb_softmax_weights_f32', ptr(ws.scores), c_ll(J), ptr(ws.probs), ptr(ws.traj_w))
+            ks = K.threefry_split(train_state.update_prng_key, 2, partitionable)      # gen_update_rnd (:429)
+            ws.sample_key.copy_(ks[0])
+            train_state.update_prng_key.copy_(ks[1])
+            call('mlb_gumbel_topk_keys', ptr(ws.sample_key), ptr(ws.probs), c_ll(J), c_ll(ws.sort_keys.numel()),
+                 c_int(int(partitionable)), ptr(ws.sort_keys))
+            K.sort_u64(ws.sort_keys)
+            nsel = ws.nsel
+            call('mlb_take_sorted_indices', ptr(ws.sort_keys), c_ll(nsel), ptr(ws.valid))
+            nmb = nsel // M
+            mb_w = ws.mb_w
+    with profile('Compute Minibatch Indices'):
+        # per epoch: permutation(rnd, valid_inds), then the stable partition of the -1s (:445-458)
+        perm_raw = ws.perm_raw[:, :nsel] if nsel == J else ws.perm_raw.view(-1)[:E * nsel].view(E, nsel)
+        perm = ws.perm[:, :nsel] if nsel == J else ws.perm.view(-1)[:E * nsel].view(E, nsel)
+        call('mlb_ppo_permutations_of', ptr(train_state.update_prng_key), ptr(ws.valid), ptr(perm_raw), c_int(E),
+             c_ll(nsel), c_int(int(partitionable)), ptr(ws.perm_ws), c_size_t(ws.perm_ws.numel()))
+        call('mlb_partition_valid', ptr(perm_raw), ptr(perm), c_int(E), c_ll(nsel))
+    flags = (1 if cfg.algo.clip_value_loss else 0) | (2 if cfg.algo.huber_value_loss else 0)
+    keys = ['obs', 'actions', 'log_probs', score_key, 'returns']
+    if cfg.algo.clip_value_loss:
+        keys.append('values')
+    keys = list(dict.fromkeys(keys))
+    tw = prog.train_ws(rows)
+    mb = ws.mb
+    seq = None
+    if prog.lstm is not None:
+        keys.append('dones')
+        seq = dict(Tp=Tp, M=M, ends=mb['dones'].view(Tp, M), c0=mb['rnn_start_c'], h0=mb['rnn_start_h'])
+    for e in range(E):
+        for k in range(nmb):
+            idx = perm[e, k * M:(k + 1) * M]
+            with profile('Gather Minibatch'):
+                if ws.mode == 'filter':
+                    call('mlb_flat_time_index', ptr(idx), c_ll(M), c_int(Tp0), c_ll(B0), ptr(ws.idx_tmp))
+                    leaves = []
+                    for name in keys:
+                        src = st[name]
+                        src = src.view(torch.uint8) if src.dtype == torch.bool else src
+                        leaves.append((src.view(1, 1, C0 * Tp0 * B0, *src.shape[4:]), mb[name],
+                                       tw['x'] if (name == 'obs' and prog.tc) else None))
+                    K.mb_gather_multi(leaves, ws.idx_tmp, 1, 1, C0 * Tp0 * B0)
+                else:
+                    leaves = []
+                    for name in keys:
+                        src = st[name][:, :, 0]
+                        leaves.append((src.view(torch.uint8) if src.dtype == torch.bool else src, mb[name],
+                                       tw['x'] if (name == 'obs' and prog.tc) else None))
+                    K.mb_gather_multi(leaves, idx, C0, Tp0, B0)
+                    if seq is not None:
+                        K.mb_gather_rnn(st['rnn_start_c'][:, 0], idx, C0, B0, mb['rnn_start_c'])
+                        K.mb_gather_rnn(st['rnn_start_h'][:, 0], idx, C0, B0, mb['rnn_start_h'])
+                    call('mlb_gather_f32', ptr(ws.traj_w), ptr(idx), c_ll(M), ptr(mb_w))      # :468
+            if normalize_scores:                      # zscore_data over THIS minibatch (:134-143)
+                K.moments(mb[score_key].view(-1), 1e-5, ws.mb_stats, ws.mom_ws)
+            if vn is not None:                        # normalize_and_update_estimates (:205-211)
+                K.moments(mb['returns'].view(-1), 0.0, ws.mb_ret_stats.view(-1), ws.mom_ws)
+                K.ema_scan(train_state.value_normalizer_state, ws.mb_ret_stats, vn.decay, vn.eps, ws.vn_one)
+            with profile('AC Forward'):
+                head = prog.forward_train(mb['obs'].view(rows, prog.obs_dim), rows, seq, x_ready=prog.tc)
+            with profile('Optimize'):
+                prog.zero_grads()
+                call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(mb['actions']),
+                     ptr(mb['log_probs']), ptr(mb[score_key]), ptr(mb['returns']),
+                     ptr(mb['values']) if cfg.algo.clip_value_loss else ptr(None), ptr(mb_w),
+                     ptr(ws.mb_stats) if normalize_scores else ptr(None),
+                     ptr(ws.vn_one) if vn is not None else ptr(None),
+                     prog._buckets_c, ws.obj_scale, ws.ent_scale, c_int(prog.A), c_ll(rows), c_ll(M),
+                     c_float(hp.clip_coef), c_float(hp.value_loss_coef), c_int(flags | prog.loss_flags),
+                     ptr(tw['dhead']), ptr(prog.head_bias_grad()), ptr(tw['stats_out']), ptr(tw['loss_ws']),
+                     c_size_t(tw['loss_ws'].numel()), prog._bins_c, c_int(prog.V))
+                prog.backward(mb['obs'].view(rows, prog.obs_dim), rows, seq)
+                prog.optimizer_step(tx['lr'], tx['max_grad_norm'], 1.0, tx['b1'], tx['b2'], tx['eps'])
+            with profile('Metrics Callback'):
+                metrics = user_metrics_cb(metrics, e, mb, policy_state, train_state)
+    ws.last_num_minibatches = nmb
+    if nmb > 0:
+        with profile('Record Metrics'):
+            dst = metrics.slot('Loss', 5)
+            call('mlb_copy_bytes', ptr(tw['stats_out'][16:]), ptr(dst), c_size_t(dst.numel()))
     return policy_state, train_state, metrics

@@ -203,6 +203,11 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         self._gae_ws = torch.empty(K.lib().mlb_gae_workspace(T, B) + 16, dtype=torch.uint8, device=dev)
         self._met_ws = torch.empty(K.lib().mlb_moments_workspace(T * B) + 16, dtype=torch.uint8, device=dev)
         self.partitionable = False
+        # per-update observation statistics (ml/rollouts.py:670-678); None entries for preprocessors
+        # without state (Noop / Caster)
+        self._obs_stats = example_policy_states.obs_preprocess.init_obs_stats(
+            example_policy_states.obs_preprocess_state, True, num_steps=C * Tp,
+            example_obs=init_rollout_state.cur_obs)
 
     def add_metrics(self, train_cfg, metrics):          # :482-499
         names = ['Rewards', 'Est Returns', 'Env Returns', 'Values']
@@ -233,7 +238,7 @@ class RolloutManager:                   # ml/rollouts.py:373-826
             rollout_data, metrics, user_state = self._finalize_rollouts(
                 train_states, metrics, user_state, user_finish_rollouts_hook, user_metrics_hook)
         train_state_mgr.user_state = user_state
-        return train_state_mgr, rollout_state, rollout_data, None, metrics
+        return train_state_mgr, rollout_state, rollout_data, self._obs_stats, metrics
 
     def rollout_loop(self, rs, policy_states, c):
         """rollout_iter x T' (ml/rollouts.py:829-978) for BPTT chunk c."""
@@ -246,6 +251,8 @@ class RolloutManager:                   # ml/rollouts.py:373-826
                 pre = policy_states.obs_preprocess.preprocess(
                     policy_states.obs_preprocess_state, rs.cur_obs, True)
                 ob = pre[self._ob_name]
+                policy_states.obs_preprocess.update_obs_stats(
+                    policy_states.obs_preprocess_state, self._obs_stats, c * Tp + s, rs.cur_obs, True)
                 slab = st['obs'][c, s, 0]
                 actions = st['actions'][c, s, 0]
                 if prog.fused_rollout:

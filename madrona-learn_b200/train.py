@@ -180,6 +180,10 @@ def _init_training(dev, cfg, sim_fns, policy, sim_ctrl, user_hooks, restore_ckpt
                           profile_port=profile_port)
     mgr.rollout_mgr = rollout_mgr
     mgr.ppo_ws = ppo_ws
+    if cfg.filter_advantages:
+        # the number of minibatches is data dependent and read back every update (ml/ppo.py:399-402):
+        # the update is not one static launch sequence, so it is not captured into a CUDA graph
+        mgr.use_cuda_graph = False
     return mgr
 
 
@@ -192,7 +196,10 @@ def _update_impl(algo, cfg, user_hooks, rollout_state, rollout_mgr, train_state_
                 train_state_mgr, rollout_state, metrics, user_hooks.start_rollouts,
                 user_hooks.finish_rollouts, user_hooks.rollout_metrics)
         with profile('Update Observations Stats'):
-            pass                                      # Noop / Caster preprocessors hold no state
+            # ml/train.py:193-204: safe right away, the learner only sees preprocessed observations
+            ps0 = train_state_mgr.policy_states
+            ps0.obs_preprocess_state = ps0.obs_preprocess.update_state(
+                ps0.obs_preprocess_state, obs_stats, True, dist_ctx=dist_ctx)
         with profile('Learn'):
             ps, ts, metrics = algo.update(cfg, train_state_mgr.policy_states,
                                           train_state_mgr.train_states, rollout_data,

@@ -162,10 +162,12 @@ class TrainStateManager:                               # ml/train_state.py:139-3
             obs_preprocess_state=obs_state, reward_hyper_params=None,
             get_episode_scores_fn=policy.get_episode_scores or (lambda x: 0.0),
             episode_score=None, mmr=None, program=prog)
+        max_adv_est = EMAEstimate(hyper.max_advantage_est_decay)        # ml/train_state.py:407-411
         ts = PolicyTrainState(
-            value_normalizer=vn, max_advantage_est=EMAEstimate(hyper.max_advantage_est_decay),
+            value_normalizer=vn, max_advantage_est=max_adv_est,
             initial_weight_norms=dict(prog.initial_weight_norms), tx=tx,
-            value_normalizer_state=vn_state, max_advantage_est_state=None, hyper_params=hyper,
+            value_normalizer_state=vn_state,
+            max_advantage_est_state=max_adv_est.init_estimates(prog.params), hyper_params=hyper,
             opt_state={'m': prog.adam_m, 'v': prog.adam_v, 'count': prog.adam_step},
             scheduler=None, scaler=None, update_prng_key=train_init)
         return TrainStateManager(policy_states=ps, train_states=ts, pbt_rng=pbt_rng,
