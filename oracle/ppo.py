@@ -253,14 +253,55 @@ def initial_weight_norms(params):
 # ---------------------------------------------------------------------------------------
 # the update loop (ml/ppo.py:366-488, default branch)
 # ---------------------------------------------------------------------------------------
+def flatten_time(rollout):
+    """RolloutData.flatten_time (ml/rollouts.py:331-334): [J, T', ...] -> [J*T', 1, ...]."""
+    return {k: v.reshape(-1, 1, *v.shape[2:]) for k, v in rollout.items() if k != 'rnn_start_states'}
+
+
+def select_filter_advantages(advantages, est_state, decay, M):
+    """filter_advantages branch of _ppo (ml/ppo.py:374-405).  advantages [J, T', 1] (training layout).
+    -> (valid_inds int32 [J*T'], num_minibatches, new max_advantage_est_state)."""
+    from .moving_avg import EMAEstimate
+    flat = np.abs(np.asarray(advantages, np.float32)).reshape(-1)          # flatten_time order f = j*T' + s
+    est = EMAEstimate(decay).update_estimates(est_state, flat.max())
+    order = np.argsort(-flat, kind='stable').astype(np.int32)              # argsort(descending=True)
+    num_above = int(np.sum(flat >= np.float32(0.01) * est['mu'][0]))
+    nmb = min((num_above + (M - 1)) // M, flat.size // M)
+    valid = np.where(np.arange(flat.size) < nmb * M, order, -1).astype(np.int32)
+    return valid, nmb, est
+
+
+def select_importance(advantages, values, returns, key, num_minibatches, M, partitionable=False):
+    """importance_sample_trajectories branch (ml/ppo.py:407-435): [J, T', 1] inputs ->
+    (sampled trajectory ids int32 [num_minibatches*M], traj_weights f32 [J, 1], probs).
+    jax.random.choice(replace=False, p) is the Gumbel top-k trick (PARITY UNPINNED: jax)."""
+    f = np.float32
+    a = np.abs(np.asarray(advantages, f)).mean(axis=1)
+    ve = np.abs(np.asarray(values, f) - np.asarray(returns, f)).mean(axis=1)
+    scores = (a + ve).astype(f)                                             # [J, 1]
+    e = np.exp(scores - scores.max(axis=0, keepdims=True))
+    probs = (e / e.sum(axis=0, keepdims=True)).astype(f)
+    J = scores.shape[0]
+    weights = ((f(1.0) / f(J)) / probs).astype(f)
+    g = prng.gumbel_from_bits(prng.random_bits(key, (J,), partitionable)) + np.log(probs.reshape(-1))
+    ind = np.argsort(-g, kind='stable')[:num_minibatches * M].astype(np.int32)
+    return ind, weights, probs
+
+
 def ppo_update(params, opt, init_norms, rollout, cfg, update_key, vn_state=None,
-               dtype=np.float32, perms=None, quant=None):
+               dtype=np.float32, perms=None, quant=None, valid_inds=None, traj_weights=None,
+               num_minibatches=None):
     """rollout: dict name -> [J, T', ...] training layout (ml/rollouts.py:788-804), P=1.
+    valid_inds / traj_weights / num_minibatches: the alternate selections of ml/ppo.py:374-435
+    (None: the default branch :437-443).
     Returns (params, opt, new_key, vn_state, last_minibatch_outputs, perms)."""
     J = rollout['dones'].shape[0]
     M = cfg.minibatch_size
-    assert J % M == 0                                                     # :439
-    traj_w = np.ones((J, 1), np.float32)                                  # :443
+    if valid_inds is None:
+        assert J % M == 0                                                 # :439
+        valid_inds = np.arange(J, dtype=np.int32)                         # :441
+        num_minibatches = J // M
+    traj_w = np.ones((J, 1), np.float32) if traj_weights is None else traj_weights   # :443
     key = np.asarray(update_key, np.uint32)
     used = []
     last = None
@@ -268,11 +309,12 @@ def ppo_update(params, opt, init_norms, rollout, cfg, update_key, vn_state=None,
         if perms is None:
             ks = prng.split(key, 2, cfg.partitionable)                    # gen_update_rnd
             rnd, key = ks[0], ks[1]
-            inds = prng.permutation(rnd, J, cfg.partitionable)            # :451
+            inds = prng.permutation(rnd, valid_inds, cfg.partitionable)   # :451
+            inds = inds[np.argsort(np.where(inds == -1, 1, 0), kind='stable')]    # :453-458
         else:
             inds = perms[e]
         used.append(inds)
-        for i in range(J // M):
+        for i in range(num_minibatches):
             mb_inds = inds[i * M:(i + 1) * M]                             # :464-466
             mb = layouts.minibatch(rollout, mb_inds)
             mb['mb_weights'] = traj_w[mb_inds]

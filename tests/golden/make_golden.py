@@ -149,6 +149,91 @@ def ppo_update_golden(rng, jax, jnp, lax, ac, ma, di):
     np.savez_compressed(os.path.join(OUT, 'ppo_loss.npz'), **out)
 
 
+def select_golden(rng, jax, jnp, lax, ma):
+    """Runs the reference's OWN `_ppo` (ml/ppo.py:366-488, AST-extracted, unmodified) under the shim
+    for the three selection branches: default, filter_advantages, importance_sample_trajectories.
+    `_ppo_update` is replaced by a recorder of (mb_inds-derived minibatch, mb_weights); jax.random
+    (third party) by oracle/prng.py's restatement of split / permutation / choice."""
+    import types as _t
+    import flax
+    from flax.core import FrozenDict
+    from oracle import prng
+    f32 = np.float32
+    ns_rd = dict(jax=jax, jnp=jnp, lax=lax, flax=flax, FrozenDict=FrozenDict, Any=object)
+    RolloutData = extract_function('rollouts.py', 'RolloutData', ns_rd)
+
+    class Ctx:
+        def __init__(self, *a): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+
+    rec = []
+
+    def fake_ppo_update(cfg, mb, mb_weights, policy_state, train_state, metrics):
+        rec.append((np.asarray(mb['tag']).copy(), np.asarray(mb_weights).copy()))
+        return policy_state, train_state, metrics
+
+    def permutation(key, x):
+        return _arr(prng.permutation(np.asarray(key), np.asarray(x)))
+
+    def choice(key, n, shape, replace, p):
+        assert not replace
+        g = prng.gumbel_from_bits(prng.random_bits(np.asarray(key), (n,))) + np.log(np.asarray(p, f32))
+        return _arr(np.argsort(-g, kind='stable')[:shape[0]].astype(np.int32))
+    random = _t.SimpleNamespace(permutation=permutation, choice=choice)
+    ns = dict(jax=jax, jnp=jnp, lax=lax, random=random, profile=Ctx, _ppo_update=fake_ppo_update,
+              TrainConfig=object, PolicyState=object, PolicyTrainState=object, RolloutData=object,
+              TrainingMetrics=object, Callable=object)
+    ppo_fn = extract_function('ppo.py', '_ppo', ns)
+
+    class TS:
+        def __init__(self, key, est, est_state):
+            self.key, self.max_advantage_est, self.max_advantage_est_state = key, est, est_state
+        def gen_update_rnd(self):
+            ks = prng.split(self.key, 2)
+            return ks[0], TS(ks[1], self.max_advantage_est, self.max_advantage_est_state)
+        def update(self, max_advantage_est_state=None):
+            return TS(self.key, self.max_advantage_est, max_advantage_est_state)
+
+    out = {}
+    J, Tp, M, E = 24, 3, 8, 2
+    for name in ('default', 'filter', 'importance'):
+        adv = (rng.standard_normal((J, Tp, 1)) * np.exp(rng.standard_normal((J, 1, 1)) * 2)).astype(f32)
+        if name == 'filter':
+            adv[rng.random((J, Tp, 1)) < 0.6] *= f32(1e-4)            # most elements fall below 1 % of the max
+        if name == 'importance':
+            adv = (adv * f32(0.05)).astype(f32)                       # keep softmax / the (1/J)/p weights in a sane range
+        val = rng.standard_normal((J, Tp, 1)).astype(f32)
+        ret = (val + rng.standard_normal((J, Tp, 1))).astype(f32)
+        tag = np.arange(J * Tp, dtype=np.int32).reshape(J, Tp, 1)   # identifies (trajectory, step)
+        data = FrozenDict(advantages=_arr(adv), values=_arr(val), returns=_arr(ret), dones=_arr(np.zeros((J, Tp, 1), bool)),
+                          tag=_arr(tag), rnn_start_states=_arr(np.zeros((J, Tp), f32)))   # flattens to J*T' rows like the rest
+        rd = RolloutData(data=data, num_train_seqs_per_policy=J, num_train_policies=1)
+        est = ma.EMAEstimate(decay=0.9)
+        est_state = est.init_estimates(_arr(np.zeros((1,), f32)))
+        for x in (3.0, 5.0):                                          # a non-trivial estimator state
+            est_state = est.update_estimates(est_state, _arr(np.array(x, f32)))
+        key0 = prng.key(1234 + len(name))
+        ts = TS(key0, est, est_state)
+        cfg = _t.SimpleNamespace(filter_advantages=name == 'filter', importance_sample_trajectories=name == 'importance',
+                                 importance_sample_num_minibatches=2,
+                                 algo=_t.SimpleNamespace(minibatch_size=M, num_epochs=E))
+        rec.clear()
+        _, ts2, _ = ppo_fn(cfg, None, ts, rd, lambda m, *a: m, None)
+        pre = name + '/'
+        out[pre + 'advantages'], out[pre + 'values'], out[pre + 'returns'] = adv, val, ret
+        out[pre + 'key0'] = np.asarray(key0, np.uint32)
+        out[pre + 'key1'] = np.asarray(ts2.key, np.uint32)
+        out[pre + 'dims'] = np.array([J, Tp, M, E], np.int32)
+        out[pre + 'num_minibatches'] = np.int32(len(rec) // E)
+        out[pre + 'mb_tags'] = np.stack([r[0].reshape(-1) for r in rec]) if rec else np.zeros((0, M), np.int32)
+        out[pre + 'mb_weights'] = np.stack([r[1].reshape(-1) for r in rec]) if rec else np.zeros((0, M), f32)
+        out[pre + 'est_before'] = np.array([float(est_state['mu'][0]), float(est_state['mu_biased'][0]), float(est_state['N'])])
+        s2 = ts2.max_advantage_est_state
+        out[pre + 'est_after'] = np.array([float(s2['mu'][0]), float(s2['mu_biased'][0]), float(s2['N'])])
+    np.savez_compressed(os.path.join(OUT, 'ppo_select.npz'), **out)
+
+
 def main():
     install()
     import jax
@@ -278,6 +363,7 @@ def main():
     # ---- the composite PPO loss + re-projection: ml/ppo.py:109-362 (own generator so the
     # fixtures above keep their random stream and stay bit-identical) ------------------------
     ppo_update_golden(np.random.default_rng(20261019), jax, jnp, lax, ac, ma, di)
+    select_golden(np.random.default_rng(20261020), jax, jnp, lax, ma)
     print('golden fixtures written to', OUT)
 
 

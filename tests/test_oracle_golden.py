@@ -194,3 +194,49 @@ def test_reprojection_matches_reference():
         np.testing.assert_allclose(new_p['mlp'][i]['kernel'], z[f'reproj/Dense_{i}_out'], rtol=2e-6)
         np.testing.assert_allclose(new_p['mlp'][i]['scale'], z[f'reproj/LayerNorm_{i}_scale_out'], rtol=2e-6)
         np.testing.assert_allclose(new_p['mlp'][i]['bias'], z[f'reproj/LayerNorm_{i}_bias_out'], rtol=2e-6)
+
+
+@pytest.mark.parametrize('name', ['default', 'filter', 'importance'])
+def test_minibatch_selection_matches_reference(name):
+    """oracle/ppo's restatement of the three selection branches of _ppo (ml/ppo.py:374-488) vs the
+    reference's own _ppo run under the shim: number of minibatches, the (trajectory, step) composition
+    of every minibatch of every epoch, the minibatch weights, the EMAEstimate state, the key advance."""
+    from oracle import ppo as oppo
+    from oracle.moving_avg import EMAEstimate
+    z = np.load(os.path.join(G, 'ppo_select.npz'))
+    g = lambda k: z[f'{name}/{k}']
+    J, Tp, M, E = [int(x) for x in g('dims')]
+    adv, val, ret = g('advantages'), g('values'), g('returns')
+    tag = np.arange(J * Tp, dtype=np.int32).reshape(J, Tp, 1)
+    roll = dict(advantages=adv, values=val, returns=ret, tag=tag, dones=np.zeros((J, Tp, 1), bool))
+    key = g('key0')
+    b = g('est_before')
+    est0 = dict(mu=np.float32([b[0]]), mu_biased=np.float32([b[1]]), N=np.int32(b[2]))
+    valid = weights = nmb = None
+    est1 = est0
+    if name == 'filter':
+        valid, nmb, est1 = oppo.select_filter_advantages(adv, est0, 0.9, M)
+        roll = oppo.flatten_time(roll)
+    elif name == 'importance':
+        ks = prng.split(key, 2)                                  # gen_update_rnd (:429)
+        key = ks[1]
+        valid, weights, _ = oppo.select_importance(adv, val, ret, ks[0], 2, M)
+        nmb = 2
+    else:
+        valid, nmb = np.arange(J, dtype=np.int32), J // M
+    assert nmb == int(g('num_minibatches'))
+    np.testing.assert_allclose([est1['mu'][0], est1['mu_biased'][0], est1['N']], g('est_after'), rtol=1e-6)
+    w = np.ones((roll['dones'].shape[0], 1), np.float32) if weights is None else weights
+    tags, ws = [], []
+    for e in range(E):
+        ks = prng.split(key, 2)
+        rnd, key = ks[0], ks[1]
+        inds = prng.permutation(rnd, valid)
+        inds = inds[np.argsort(np.where(inds == -1, 1, 0), kind='stable')]
+        for i in range(nmb):
+            mi = inds[i * M:(i + 1) * M]
+            tags.append(layouts.minibatch(roll, mi)['tag'].reshape(-1))
+            ws.append(w[mi].reshape(-1))
+    np.testing.assert_array_equal(np.stack(tags), g('mb_tags'))          # bit-exact composition
+    np.testing.assert_allclose(np.stack(ws), g('mb_weights'), rtol=1e-5)
+    np.testing.assert_array_equal(key, g('key1'))
