@@ -150,7 +150,7 @@ struct PState {
 
 __device__ __forceinline__ PState p_prologue(uint8_t* smem_raw, const CUtensorMap* tmA, const CUtensorMap* tmB,
                                              int M, int K, int HN, int a_stages, int staging_bytes,
-                                             const float* scale, const float* bias) {
+                                             const float* scale, const float* bias, int xh_consumers = 8) {
     PState p;
     pdl_launch_dependents();
     p.smem = align_smem_1024(smem_raw);
@@ -164,7 +164,7 @@ __device__ __forceinline__ PState p_prologue(uint8_t* smem_raw, const CUtensorMa
         for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(&p.bars.full[s], 1); mbar_init(&p.bars.empty[s], 1); }
         for (int kb = 0; kb < 4; ++kb) mbar_init(&p.bars.w_bar[kb], 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&p.bars.acc_full[s], 1); mbar_init(&p.bars.acc_empty[s], 16); }
-        for (int s = 0; s < 4; ++s) { mbar_init(&p.bars.xh_full[s], 1); mbar_init(&p.bars.xh_empty[s], 8); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&p.bars.xh_full[s], 1); mbar_init(&p.bars.xh_empty[s], xh_consumers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // prime the pipeline before anything else in the prologue: resident W + the first ring fill
         const int num_kb = (K + BK - 1) / BK;
@@ -790,6 +790,12 @@ fwd_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     p_teardown(p.tmem_base, warp);
 }
 
+// Backward, second generation.  Work order is PANEL-sequential: for every 64-column xhat panel all 16
+// epilogue warps process it together (warp (quad, grp): its 32 rows x the 16 columns 64p + 16grp ..),
+// so the panel ring behaves like an ordinary pipeline (the first generation needed all panels of a tile
+// at once and stalled on its 3-slot ring), and the accumulator reads are software-pipelined: the
+// tcgen05.ld of the next 16x16 block is in flight while the current one is processed (TMEM delivers
+// 64 B/clk per SM -- 1 us per pass over a 128 x 256 fp32 tile -- which otherwise adds to the math).
 template <bool FULLSEC>
 __global__ void __launch_bounds__(P_THREADS, 1)
 dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -800,7 +806,7 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (M + BM - 1) / BM;
-    PState p = p_prologue(smem_raw, &tmA, &tmB, M, K, HN, a_stages, BWD_XH_BUFS * 16384, scale, bias);
+    PState p = p_prologue(smem_raw, &tmA, &tmB, M, K, HN, a_stages, BWD_XH_BUFS * 16384, scale, bias, 16);
     if (warp < 2) {
         p_mainloop<BWD_XH_BUFS>(&tmA, &tmB, &tmXH, p.smem, p.L, p.bars, p.tmem_base, warp, lane, num_tiles, K, HN,
                                 a_stages, 1);
@@ -813,13 +819,15 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         float* cb_sm = p.fsm + 3 * HN;
         float* part = p.fsm + 4 * HN;
         const uint8_t* ring = p.smem + p.L.stage_off;
-        const int nchunks = HN / 32, num_panels = HN / 64;
+        const int num_panels = HN / 64;                      // <= 4
+        const int nblk = 2 * num_panels;                     // (panel, half) blocks per pass
         const float invH = 1.f / (float)HN;
-        float cs[2][8], cb[2][8];                            // per-feature sums of du*xhat / du, whole kernel
+        const int cw = 16 * grp;                             // this warp's column offset inside a panel
+        float cs[4][4], cb[4][4];                            // per-feature sums of du*xhat / du, whole kernel
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc)
+        for (int pp = 0; pp < 4; ++pp)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { cs[cc][j] = 0.f; cb[cc][j] = 0.f; }
+            for (int j = 0; j < 4; ++j) { cs[pp][j] = 0.f; cb[pp][j] = 0.f; }
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -830,129 +838,139 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int row = m0 + quad * 32 + rq + 8 * i;
                 rstd[i] = row < M ? rstd_in[row] : 0.f;
             }
-            const uint32_t tq = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
+            const uint32_t tq = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16) + cw;
             const int xbase = it * num_panels;               // producer's panel sequence number of this tile
             PROF(0);
             mbar_wait(&p.bars.acc_full[buf], (it >> 1) & 1);
             tcgen05_fence_after();
             PROF(1);
-            // pass 1: ReLU mask, dxhat, row sums m1 = sum(dxhat), m2 = sum(dxhat * xhat), feature sums;
-            // (rstd * dxhat, xhat) left as bf16x2 words in the accumulator cells
+            // ---- pass 1 ------------------------------------------------------------------------
             float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t r[2][8];
+            tmem_ld_16x256b_x2(tq, r[0]);                    // block 0 = (panel 0, half 0)
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int ch = grp + 4 * cc;
-                if (ch < nchunks) {
-                    const int xit = xbase + (ch >> 1);
+            for (int blk = 0; blk < 8; ++blk) {
+                if (blk < nblk) {
+                    const int pn = blk >> 1, h2 = blk & 1, cur = blk & 1;
+                    const int xit = xbase + pn;
                     const int xs = xit % BWD_XH_BUFS;
-                    mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
-                    if (cc == 0) PROF(2); else PROF(6);
-                    const uint8_t* pan = ring + xs * 16384;
-                    const int hf = ch & 1;
-#pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        uint32_t r[16];
-                        const uint32_t ta = tq + ((uint32_t)(16 * h2) << 16) + ch * 32;
-                        tmem_ld_16x256b_x4(ta, r);
-                        tmem_ld_wait16(r);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float2 s2 = *reinterpret_cast<const float2*>(s + ch * 32 + 8 * k + 2 * c);
-                            const float2 b2 = *reinterpret_cast<const float2*>(b + ch * 32 + 8 * k + 2 * c);
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const int i = 2 * h2 + h;
-                                const int rt = quad * 32 + rq + 8 * i;            // rt & 7 == rq
-                                const uint32_t xw = *reinterpret_cast<const uint32_t*>(
-                                    pan + rt * 128 + (((hf * 4 + k) ^ rq) << 4) + 4 * c);
-                                const float xh0 = bf16lo(xw), xh1 = bf16hi(xw);
-                                const float dy0 = __uint_as_float(r[4 * k + 2 * h]);
-                                const float dy1 = __uint_as_float(r[4 * k + 2 * h + 1]);
-                                const float du0 = (fmaf(xh0, s2.x, b2.x) > 0.f) ? dy0 : 0.f;   // ReLU mask
-                                const float du1 = (fmaf(xh1, s2.y, b2.y) > 0.f) ? dy1 : 0.f;
-                                const float dx0 = du0 * s2.x, dx1 = du1 * s2.y;
-                                m1[i] += dx0;
-                                m2[i] = fmaf(dx0, xh0, m2[i]);
-                                m1[i] += dx1;
-                                m2[i] = fmaf(dx1, xh1, m2[i]);
-                                cs[cc][2 * k] = fmaf(du0, xh0, cs[cc][2 * k]);
-                                cs[cc][2 * k + 1] = fmaf(du1, xh1, cs[cc][2 * k + 1]);
-                                cb[cc][2 * k] += du0;
-                                cb[cc][2 * k + 1] += du1;
-                                r[4 * k + 2 * h] = pack_bf16(dx0 * rstd[i], dx1 * rstd[i]);
-                                r[4 * k + 2 * h + 1] = xw;
-                            }
-                        }
-                        tmem_st_16x256b_x4(ta, r);
+                    if (h2 == 0) {
+                        mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
+                        if (pn == 0) PROF(2);
                     }
-                    tmem_st_wait();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&p.bars.xh_empty[xs]);       // this warp is done with the panel
+                    tmem_ld_wait8(r[cur]);
+                    if (blk + 1 < nblk)                      // next block's accumulator read overlaps this block's math
+                        tmem_ld_16x256b_x2(tq + ((uint32_t)(16 * ((blk + 1) & 1)) << 16) + ((blk + 1) >> 1) * 64, r[cur ^ 1]);
+                    const uint8_t* pan = ring + xs * 16384;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const float2 s2 = *reinterpret_cast<const float2*>(s + pn * 64 + cw + 8 * k + 2 * c);
+                        const float2 b2 = *reinterpret_cast<const float2*>(b + pn * 64 + cw + 8 * k + 2 * c);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = 2 * h2 + h;
+                            const int rt = quad * 32 + rq + 8 * i;            // rt & 7 == rq
+                            const uint32_t xw = *reinterpret_cast<const uint32_t*>(
+                                pan + rt * 128 + (((2 * grp + k) ^ rq) << 4) + 4 * c);
+                            const float xh0 = bf16lo(xw), xh1 = bf16hi(xw);
+                            const float dy0 = __uint_as_float(r[cur][4 * k + 2 * h]);
+                            const float dy1 = __uint_as_float(r[cur][4 * k + 2 * h + 1]);
+                            const float du0 = (fmaf(xh0, s2.x, b2.x) > 0.f) ? dy0 : 0.f;   // ReLU mask
+                            const float du1 = (fmaf(xh1, s2.y, b2.y) > 0.f) ? dy1 : 0.f;
+                            const float dx0 = du0 * s2.x, dx1 = du1 * s2.y;
+                            m1[i] += dx0;
+                            m2[i] = fmaf(dx0, xh0, m2[i]);
+                            m1[i] += dx1;
+                            m2[i] = fmaf(dx1, xh1, m2[i]);
+                            cs[pn][2 * k] = fmaf(du0, xh0, cs[pn][2 * k]);
+                            cs[pn][2 * k + 1] = fmaf(du1, xh1, cs[pn][2 * k + 1]);
+                            cb[pn][2 * k] += du0;
+                            cb[pn][2 * k + 1] += du1;
+                            r[cur][4 * k + 2 * h] = pack_bf16(dx0 * rstd[i], dx1 * rstd[i]);
+                            r[cur][4 * k + 2 * h + 1] = xw;
+                        }
+                    }
+                    tmem_st_16x256b_x2(tq + ((uint32_t)(16 * h2) << 16) + pn * 64, r[cur]);
+                    if (h2 == 1) {                           // both halves of the panel read: release it
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&p.bars.xh_empty[xs]);
+                    }
                 }
             }
+            tmem_st_wait();
             PROF(3);
             row_totals(part, buf, grp, quad, rq, c, m1, m2);
             PROF(4);
-            // dz = rstd*dxhat - rstd*mean(dxhat) - xhat * rstd*mean(dxhat*xhat), on packed bf16 pairs
+            // ---- pass 2: dz = rstd*dxhat - rstd*mean(dxhat) - xhat * rstd*mean(dxhat*xhat), packed pairs -----
             __nv_bfloat162 nc1[4], nc2[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 nc1[i] = __float2bfloat162_rn(-rstd[i] * m1[i] * invH);
                 nc2[i] = __float2bfloat162_rn(-rstd[i] * m2[i] * invH);
             }
-            bool released = false;
+            tmem_ld_16x256b_x2(tq, r[0]);
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int ch = grp + 4 * cc;
-                if (ch < nchunks) {
+            for (int blk = 0; blk < 8; ++blk) {
+                if (blk < nblk) {
+                    const int pn = blk >> 1, h2 = blk & 1, cur = blk & 1;
+                    tmem_ld_wait8(r[cur]);
+                    if (blk + 1 < nblk) {
+                        tmem_ld_16x256b_x2(tq + ((uint32_t)(16 * ((blk + 1) & 1)) << 16) + ((blk + 1) >> 1) * 64, r[cur ^ 1]);
+                    } else {                                 // last accumulator read of this warp for this tile
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+                    }
+                    uint32_t o[2][2];
 #pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        uint32_t r[16];
-                        tmem_ld_16x256b_x4(tq + ((uint32_t)(16 * h2) << 16) + ch * 32, r);
-                        tmem_ld_wait16(r);
-                        if (h2 == 1 && ch + 4 >= nchunks) {
-                            tcgen05_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
-                            released = true;
+                    for (int k = 0; k < 2; ++k)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = 2 * h2 + h;
+                            const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r[cur][4 * k + 2 * h]);
+                            const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&r[cur][4 * k + 2 * h + 1]);
+                            const __nv_bfloat162 dz = __hfma2(nc2[i], x, __hadd2(a, nc1[i]));
+                            o[k][h] = *reinterpret_cast<const uint32_t*>(&dz);
                         }
-                        uint32_t o[4][2];
+                    const long long row0 = m0 + quad * 32 + rq + 16 * h2, row1 = row0 + 8;
+                    const int cbase = pn * 64 + cw;
+                    if (FULLSEC) {
+                        const bool odd = (c & 1) != 0;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t send = odd ? o[0][h] : o[1][h];
+                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                            const uint2 v = odd ? make_uint2(recv, o[1][h]) : make_uint2(o[0][h], recv);
+                            const long long row = h ? row1 : row0;
+                            if (row < M)
+                                *reinterpret_cast<uint2*>(DZ + row * HN + cbase + 8 * (odd ? 1 : 0) + 4 * (c >> 1)) = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
-                                const int i = 2 * h2 + h;
-                                const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r[4 * k + 2 * h]);
-                                const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&r[4 * k + 2 * h + 1]);
-                                const __nv_bfloat162 dz = __hfma2(nc2[i], x, __hadd2(a, nc1[i]));
-                                o[k][h] = *reinterpret_cast<const uint32_t*>(&dz);
+                                const long long row = h ? row1 : row0;
+                                if (row < M) *reinterpret_cast<uint32_t*>(DZ + row * HN + cbase + 8 * k + 2 * c) = o[k][h];
                             }
-                        const long long row0 = m0 + quad * 32 + rq + 16 * h2, row1 = row0 + 8;
-                        store_pairs<FULLSEC, false>(DZ, HN, o, row0, row1, row0 < M, row1 < M, ch * 32, c);
                     }
                 }
-            }
-            if (!released) {
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
             }
             PROF(5);
         }
         // per-feature sums: reduce over the 8 row lanes once, then across quadrants through shared memory
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int ch = grp + 4 * cc;
+        for (int pn = 0; pn < 4; ++pn) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float a = cs[cc][j], d = cb[cc][j];
+            for (int j = 0; j < 4; ++j) {
+                float a = cs[pn][j], d = cb[pn][j];
 #pragma unroll
                 for (int o = 4; o <= 16; o <<= 1) {
                     a += __shfl_xor_sync(0xffffffffu, a, o);
                     d += __shfl_xor_sync(0xffffffffu, d, o);
                 }
-                if (rq == 0 && ch < nchunks) {
-                    const int col = ch * 32 + 8 * (j >> 1) + 2 * c + (j & 1);
+                if (rq == 0 && pn < num_panels) {
+                    const int col = pn * 64 + cw + 8 * (j >> 1) + 2 * c + (j & 1);
                     atomicAdd(&cs_sm[col], a);
                     atomicAdd(&cb_sm[col], d);
                 }
