@@ -195,10 +195,11 @@ def test_tc_policy_forward_backward_vs_oracle(mlb, D, H, L, rows, jitter):
     if jitter >= 0.2:
         assert cos > 0.98 and rel < 0.2, (cos, rel)
     else:
-        # realistic inputs: no clip-decision flips; what remains is the bf16 storage of activations
-        # (ReLU-mask flips of near-zero pre-activations).  SURVEY 8c aimed at cos >= 0.999 / rel-L2 <=
-        # 2e-2; the measured figures are recorded in profiles/r2_parity_measured.jsonl and DESIGN.md.
-        assert cos > 0.995 and rel < 0.1, (cos, rel)
+        # realistic inputs (no clip-decision flips): the tolerance SURVEY 8c states for the bf16 path,
+        # gradients cosine >= 0.999 and rel-L2 <= 2e-2 vs the EXACT fp64 oracle.  Measured on B200
+        # (profiles/r2_parity_measured.jsonl): cosine 0.999998 / rel-L2 2.7e-3 at the cfg2 minibatch
+        # shape (65 536 x 256), 0.99999 / 5.0e-3 at width 512.
+        assert cos >= 0.999 and rel <= 2e-2, (cos, rel)
     # optimiser step refreshes the bf16 operand copies
     prog.optimizer_step(3e-4, 0.5)
     k0, _, _ = prog.layer_views(prog.params, 0)

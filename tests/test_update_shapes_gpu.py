@@ -16,9 +16,9 @@ exact fp32 oracle.  What is checked (VERDICT r1 "next" 1a-1c):
 Tolerances.  Adam's first steps are sign-like (u = -lr * m / (sqrt(v) + eps) ~ -lr * sign(g)), so
 the parameter DELTA amplifies the sign of every gradient element whose magnitude is below the bf16
 noise floor; the Adam moment `m` is linear in the gradients and is the well-conditioned quantity.
-Stated bounds: m vs the same-quantisation oracle rel-L2 <= 3e-2 / cosine >= 0.999; parameter delta
-cosine >= 0.97; vs the exact fp32 oracle (the precision cost of bf16 storage) m cosine
->= 0.995.  The measured figures are appended to $MLB_PARITY_LOG when set (profiles/r2_parity_*.jsonl).
+Stated bounds: m vs the same-quantisation oracle rel-L2 <= 5e-3 / cosine >= 0.9999, parameter delta
+cosine >= 0.999; vs the exact fp32 oracle (the precision cost of bf16 storage) m cosine >= 0.999 and
+rel-L2 <= 2e-2 -- the tolerance SURVEY 8c states -- and parameter delta cosine >= 0.99.  The measured figures are appended to $MLB_PARITY_LOG when set (profiles/r2_parity_*.jsonl).
 """
 import json
 import os
@@ -132,8 +132,11 @@ def test_bf16_update_iter_vs_oracle_at_baseline_shape(mlb, monkeypatch, name, N,
     rec['loss_gpu'], rec['loss_quant'], rec['loss_exact'] = (float(lat['Loss'].mean), float(res['quant'][3]['loss']),
                                                              float(res['exact'][3]['loss']))
     _log(rec)
-    assert rec['adam_m_cos_quant'] >= 0.999 and rec['adam_m_rel_quant'] <= 3e-2, rec
-    assert rec['delta_cos_quant'] >= 0.97, rec
-    assert rec['adam_m_cos_exact'] >= 0.995, rec
+    # measured on B200 (profiles/r2_parity_measured.jsonl): cfg2 m rel 1.1e-3 (quant) / 1.07e-2 (exact),
+    # delta cosine 0.99996 / 0.9975; width 512: 2.6e-4 / 2.4e-3, 0.99995 / 0.9981
+    assert rec['adam_m_cos_quant'] >= 0.9999 and rec['adam_m_rel_quant'] <= 5e-3, rec
+    assert rec['delta_cos_quant'] >= 0.999, rec
+    assert rec['adam_m_cos_exact'] >= 0.999 and rec['adam_m_rel_exact'] <= 2e-2, rec      # SURVEY 8c bound
+    assert rec['delta_cos_exact'] >= 0.99, rec
     np.testing.assert_allclose(rec['loss_gpu'], rec['loss_quant'], rtol=2e-2, atol=2e-4)
     np.testing.assert_allclose(lat['Entropy'].mean, np.mean(res['quant'][3]['entropies']), rtol=2e-3)
