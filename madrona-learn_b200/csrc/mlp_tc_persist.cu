@@ -15,6 +15,8 @@
 //     segments -- no TMA-store staging panels, proxy fences or CTA barriers on the critical path.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 #include "mlp_tc_persist.cuh"
 
@@ -109,7 +111,10 @@ __device__ __forceinline__ void p_mainloop(const CUtensorMap* tmA, const CUtenso
                     }
                 }
                 if (progress) idle = 0;
-                else if (++idle > (1u << 28)) __trap();      // never hang the GPU on a protocol bug
+                else {
+                    if (++idle > (1u << 26)) __trap();       // never hang the GPU on a protocol bug
+                    __nanosleep(40);                          // leave the issue slots to the epilogue warps
+                }
             }
         }
     } else if (warp == 1) {
@@ -676,7 +681,7 @@ __device__ __forceinline__ void row_totals(float* part, int buf, int grp, int qu
 }
 
 template <bool FULLSEC>
-__global__ void __launch_bounds__(P_THREADS, 1)
+__global__ void __maxnreg__(112)
 fwd_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ scale, const float* __restrict__ bias,
                     __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ XH,
@@ -797,7 +802,7 @@ fwd_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // tcgen05.ld of the next 16x16 block is in flight while the current one is processed (TMEM delivers
 // 64 B/clk per SM -- 1 us per pass over a 128 x 256 fp32 tile -- which otherwise adds to the math).
 template <bool FULLSEC>
-__global__ void __launch_bounds__(P_THREADS, 1)
+__global__ void __maxnreg__(112)          // 576 threads x 112 registers = 63 K of the 64 K register file
 dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmXH, const float* __restrict__ scale,
                    const float* __restrict__ bias, const float* __restrict__ rstd_in,
@@ -828,15 +833,26 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int pp = 0; pp < 4; ++pp)
 #pragma unroll
             for (int j = 0; j < 4; ++j) { cs[pp][j] = 0.f; cb[pp][j] = 0.f; }
+        // per-thread constants of the xhat panel reads: row rq of the quadrant, 16-byte chunk (2*grp + k)
+        // swizzled by the row, word c; rows of the same lane are 8 apart = +1024 bytes (immediates)
+        const uint32_t xoff0 = (uint32_t)((quad * 32 + rq) * 128 + (((2 * grp + 0) ^ rq) << 4) + 4 * c);
+        const uint32_t xoff1 = (uint32_t)((quad * 32 + rq) * 128 + (((2 * grp + 1) ^ rq) << 4) + 4 * c);
+        const bool odd = (c & 1) != 0;
+        // column of this lane's 8-byte (FULLSEC) / 4-byte store inside a 16-column block
+        const int scol = FULLSEC ? (cw + (odd ? 8 : 0) + 4 * (c >> 1)) : (cw + 2 * c);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const int m0 = tile * BM;
+            auto tile_body = [&](auto full_c) {
+            constexpr bool FULLROWS = decltype(full_c)::value;     // all 128 rows of the tile are inside M
             float rstd[4];
+            __nv_bfloat16* rp[4];                                  // output row pointers (+ this lane's column)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int row = m0 + quad * 32 + rq + 8 * i;
-                rstd[i] = row < M ? rstd_in[row] : 0.f;
+                rstd[i] = (FULLROWS || row < M) ? rstd_in[row] : 0.f;
+                rp[i] = DZ + (size_t)row * HN + scol;
             }
             const uint32_t tq = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16) + cw;
             const int xbase = it * num_panels;               // producer's panel sequence number of this tile
@@ -847,40 +863,43 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // ---- pass 1 ------------------------------------------------------------------------
             float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t r[2][8];
+            float2 s2[2], b2[2];
+            const uint8_t* pan = ring;
+            int xs = 0;
             tmem_ld_16x256b_x2(tq, r[0]);                    // block 0 = (panel 0, half 0)
 #pragma unroll
             for (int blk = 0; blk < 8; ++blk) {
                 if (blk < nblk) {
                     const int pn = blk >> 1, h2 = blk & 1, cur = blk & 1;
-                    const int xit = xbase + pn;
-                    const int xs = xit % BWD_XH_BUFS;
                     if (h2 == 0) {
+                        const int xit = xbase + pn;
+                        xs = xit % BWD_XH_BUFS;
                         mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
                         if (pn == 0) PROF(2);
+                        pan = ring + xs * 16384;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {        // this lane's four feature columns of the panel
+                            s2[k] = *reinterpret_cast<const float2*>(s + pn * 64 + cw + 8 * k + 2 * c);
+                            b2[k] = *reinterpret_cast<const float2*>(b + pn * 64 + cw + 8 * k + 2 * c);
+                        }
                     }
                     tmem_ld_wait8(r[cur]);
                     if (blk + 1 < nblk)                      // next block's accumulator read overlaps this block's math
                         tmem_ld_16x256b_x2(tq + ((uint32_t)(16 * ((blk + 1) & 1)) << 16) + ((blk + 1) >> 1) * 64, r[cur ^ 1]);
-                    const uint8_t* pan = ring + xs * 16384;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        const float2 s2 = *reinterpret_cast<const float2*>(s + pn * 64 + cw + 8 * k + 2 * c);
-                        const float2 b2 = *reinterpret_cast<const float2*>(b + pn * 64 + cw + 8 * k + 2 * c);
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int i = 2 * h2 + h;
-                            const int rt = quad * 32 + rq + 8 * i;            // rt & 7 == rq
-                            const uint32_t xw = *reinterpret_cast<const uint32_t*>(
-                                pan + rt * 128 + (((2 * grp + k) ^ rq) << 4) + 4 * c);
+                            const uint32_t xw = *reinterpret_cast<const uint32_t*>(pan + (k ? xoff1 : xoff0) + i * 1024);
                             const float xh0 = bf16lo(xw), xh1 = bf16hi(xw);
                             const float dy0 = __uint_as_float(r[cur][4 * k + 2 * h]);
                             const float dy1 = __uint_as_float(r[cur][4 * k + 2 * h + 1]);
-                            const float du0 = (fmaf(xh0, s2.x, b2.x) > 0.f) ? dy0 : 0.f;   // ReLU mask
-                            const float du1 = (fmaf(xh1, s2.y, b2.y) > 0.f) ? dy1 : 0.f;
-                            const float dx0 = du0 * s2.x, dx1 = du1 * s2.y;
-                            m1[i] += dx0;
+                            const float du0 = (fmaf(xh0, s2[k].x, b2[k].x) > 0.f) ? dy0 : 0.f;   // ReLU mask
+                            const float du1 = (fmaf(xh1, s2[k].y, b2[k].y) > 0.f) ? dy1 : 0.f;
+                            const float dx0 = du0 * s2[k].x, dx1 = du1 * s2[k].y;
+                            m1[i] += dx0 + dx1;
                             m2[i] = fmaf(dx0, xh0, m2[i]);
-                            m1[i] += dx1;
                             m2[i] = fmaf(dx1, xh1, m2[i]);
                             cs[pn][2 * k] = fmaf(du0, xh0, cs[pn][2 * k]);
                             cs[pn][2 * k + 1] = fmaf(du1, xh1, cs[pn][2 * k + 1]);
@@ -932,31 +951,30 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             const __nv_bfloat162 dz = __hfma2(nc2[i], x, __hadd2(a, nc1[i]));
                             o[k][h] = *reinterpret_cast<const uint32_t*>(&dz);
                         }
-                    const long long row0 = m0 + quad * 32 + rq + 16 * h2, row1 = row0 + 8;
-                    const int cbase = pn * 64 + cw;
                     if (FULLSEC) {
-                        const bool odd = (c & 1) != 0;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
+                            const int i = 2 * h2 + h;
                             const uint32_t send = odd ? o[0][h] : o[1][h];
                             const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
                             const uint2 v = odd ? make_uint2(recv, o[1][h]) : make_uint2(o[0][h], recv);
-                            const long long row = h ? row1 : row0;
-                            if (row < M)
-                                *reinterpret_cast<uint2*>(DZ + row * HN + cbase + 8 * (odd ? 1 : 0) + 4 * (c >> 1)) = v;
+                            if (FULLROWS || m0 + quad * 32 + rq + 8 * i < M) *reinterpret_cast<uint2*>(rp[i] + pn * 64) = v;
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
-                                const long long row = h ? row1 : row0;
-                                if (row < M) *reinterpret_cast<uint32_t*>(DZ + row * HN + cbase + 8 * k + 2 * c) = o[k][h];
+                                const int i = 2 * h2 + h;
+                                if (FULLROWS || m0 + quad * 32 + rq + 8 * i < M)
+                                    *reinterpret_cast<uint32_t*>(rp[i] + pn * 64 + 8 * k) = o[k][h];
                             }
                     }
                 }
             }
             PROF(5);
+            };
+            if (m0 + BM <= M) tile_body(std::true_type{}); else tile_body(std::false_type{});
         }
         // per-feature sums: reduce over the 8 row lanes once, then across quadrants through shared memory
 #pragma unroll
