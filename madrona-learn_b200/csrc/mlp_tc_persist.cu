@@ -681,7 +681,7 @@ __device__ __forceinline__ void row_totals(float* part, int buf, int grp, int qu
 }
 
 template <bool FULLSEC>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(P_THREADS, 1)
 fwd_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ scale, const float* __restrict__ bias,
                     __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ XH,
@@ -802,7 +802,7 @@ fwd_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // tcgen05.ld of the next 16x16 block is in flight while the current one is processed (TMEM delivers
 // 64 B/clk per SM -- 1 us per pass over a 128 x 256 fp32 tile -- which otherwise adds to the math).
 template <bool FULLSEC>
-__global__ void __maxnreg__(112)          // 576 threads x 112 registers = 63 K of the 64 K register file
+__global__ void __launch_bounds__(P_THREADS, 1)       // 18 warps = 5 on one scheduler: 16 K / (5 x 32) -> 96 registers
 dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmXH, const float* __restrict__ scale,
                    const float* __restrict__ bias, const float* __restrict__ rstd_in,
@@ -847,12 +847,12 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             auto tile_body = [&](auto full_c) {
             constexpr bool FULLROWS = decltype(full_c)::value;     // all 128 rows of the tile are inside M
             float rstd[4];
-            __nv_bfloat16* rp[4];                                  // output row pointers (+ this lane's column)
+            uint32_t ro[4];                                        // output element offsets (row start + this lane's column)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int row = m0 + quad * 32 + rq + 8 * i;
                 rstd[i] = (FULLROWS || row < M) ? rstd_in[row] : 0.f;
-                rp[i] = DZ + (size_t)row * HN + scol;
+                ro[i] = (uint32_t)row * (uint32_t)HN + (uint32_t)scol;
             }
             const uint32_t tq = p.tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16) + cw;
             const int xbase = it * num_panels;               // producer's panel sequence number of this tile
@@ -877,11 +877,11 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
                         if (pn == 0) PROF(2);
                         pan = ring + xs * 16384;
+                    }
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {        // this lane's four feature columns of the panel
-                            s2[k] = *reinterpret_cast<const float2*>(s + pn * 64 + cw + 8 * k + 2 * c);
-                            b2[k] = *reinterpret_cast<const float2*>(b + pn * 64 + cw + 8 * k + 2 * c);
-                        }
+                    for (int k = 0; k < 2; ++k) {            // this lane's four feature columns of the panel
+                        s2[k] = *reinterpret_cast<const float2*>(s + pn * 64 + cw + 8 * k + 2 * c);
+                        b2[k] = *reinterpret_cast<const float2*>(b + pn * 64 + cw + 8 * k + 2 * c);
                     }
                     tmem_ld_wait8(r[cur]);
                     if (blk + 1 < nblk)                      // next block's accumulator read overlaps this block's math
@@ -958,7 +958,7 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             const uint32_t send = odd ? o[0][h] : o[1][h];
                             const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
                             const uint2 v = odd ? make_uint2(recv, o[1][h]) : make_uint2(o[0][h], recv);
-                            if (FULLROWS || m0 + quad * 32 + rq + 8 * i < M) *reinterpret_cast<uint2*>(rp[i] + pn * 64) = v;
+                            if (FULLROWS || m0 + quad * 32 + rq + 8 * i < M) *reinterpret_cast<uint2*>(DZ + ro[i] + pn * 64) = v;
                         }
                     } else {
 #pragma unroll
@@ -967,7 +967,7 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             for (int h = 0; h < 2; ++h) {
                                 const int i = 2 * h2 + h;
                                 if (FULLROWS || m0 + quad * 32 + rq + 8 * i < M)
-                                    *reinterpret_cast<uint32_t*>(rp[i] + pn * 64 + 8 * k) = o[k][h];
+                                    *reinterpret_cast<uint32_t*>(DZ + ro[i] + pn * 64 + 8 * k) = o[k][h];
                             }
                     }
                 }

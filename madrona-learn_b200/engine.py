@@ -253,6 +253,24 @@ class PolicyProgram:
                 'actor': {'kernel': c(t['actor']['impl']['kernel']), 'bias': c(t['actor']['impl']['bias'])},
                 'critic': {'kernel': c(t['critic']['Dense_0']['kernel']), 'bias': c(t['critic']['Dense_0']['bias'])}}
 
+    def initial_weight_norms_tree(self):
+        """initial_weight_norms in the parameter tree's shape (ml/train_state.py:413-423): the initial L2
+        norm at every backbone `kernel` leaf, None at every other leaf and under actor / critic."""
+        n = self.initial_weight_norms
+        net = {}
+        for i in range(self.L):
+            net[f'Dense_{i}'] = {'kernel': float(n[f'Dense_{i}'])}
+            net[f'LayerNorm_{i}'] = {'impl': {'scale': None, 'bias': None}}
+        enc = {'net': net}
+        if self.lstm is not None:
+            cell = {}
+            for g in ('i', 'f', 'g', 'o'):
+                cell['i' + g] = {'kernel': n.get(f'lstm0/i{g}')}
+                cell['h' + g] = {'kernel': n.get(f'lstm0/h{g}'), 'bias': None}
+            enc['rnn'] = {'cell': {'OptimizedLSTMCell_0': cell}}
+        return {'backbone': {'encoder': enc}, 'actor': {'impl': {'kernel': None, 'bias': None}},
+                'critic': {'Dense_0': {'kernel': None, 'bias': None}}}
+
     def finalize_params(self):
         """Record initial kernel norms (ml/train_state.py:413-423) -> device segment table."""
         self.initial_weight_norms = {}

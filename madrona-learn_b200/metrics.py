@@ -85,6 +85,23 @@ class TrainingMetrics:
         s = (self.cur_buffer_offset - 1) % self.update_buffer_size
         return {k: v[s] for k, v in h.items()}
 
+    def tensorboard_log(self, base_update_idx, writer):
+        """ml/metrics.py:218-244: every ring slot `buf_idx` is written at step base_update_idx +
+        buf_idx with the reference's tag set; all metrics on this path are per-policy records
+        (Metric.init(True), ml/ppo.py:98-104, ml/rollouts.py:482-499) and P = 1, so the tags are
+        `p0/<name> Mean`, `p0/<name> σ`, `p0/<name> Min`, `p0/<name> Max`."""
+        h = self.to_host()
+        for buf_idx in range(self.update_buffer_size):
+            out_idx = base_update_idx + buf_idx
+            for name, recs in h.items():
+                m = recs[buf_idx]
+                stddev = float(np.sqrt(m.m2 / m.count)) if m.count else float('nan')
+                pre = 'p0/' if m.per_policy else ''
+                writer.scalar(f'{pre}{name} Mean', m.mean, out_idx)
+                writer.scalar(f'{pre}{name} σ', stddev, out_idx)
+                writer.scalar(f'{pre}{name} Min', m.min, out_idx)
+                writer.scalar(f'{pre}{name} Max', m.max, out_idx)
+
     def pretty_print(self, tab=2):
         for k, m in self.latest().items():
             std = (m.m2 / max(m.count, 1)) ** 0.5

@@ -89,9 +89,8 @@ class TrainingManager:                                 # ml/train.py:35-64
             self.update_fn(self.state, self.rollout, self.metrics, self.update_idx)
         self._graph = g
 
-    def log_metrics_tensorboard(self, tb_writer):
-        for k, m in self.metrics.latest().items():
-            tb_writer.scalar(k, m.mean, self.update_idx - 1)
+    def log_metrics_tensorboard(self, tb_writer):        # ml/train.py:62-64
+        self.metrics.tensorboard_log(self.update_idx - 1, tb_writer)
 
 
 def init_training(dev, cfg: TrainConfig, sim_fns: Dict[str, Callable], policy: Policy,

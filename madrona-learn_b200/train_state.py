@@ -79,46 +79,69 @@ class TrainStateManager:                               # ml/train_state.py:139-3
             setattr(self, k, v)
         return self
 
-    # checkpoint: same dict keys as ml/train_state.py:145-164; torch.save stands in for orbax
+    # checkpoint: the reference's key tree (ml/train_state.py:145-164 saves the PolicyState /
+    # PolicyTrainState pytrees: :34-47, :85-99) with every leaf a host array; torch.save stands in
+    # for orbax.  Only arrays / scalars / None are written, so load() runs with weights_only=True;
+    # `user_state` (arbitrary user pytree) goes to a separate opt-in pickle next to it.
     def save(self, next_update, path):
         ps, ts = self.policy_states, self.train_states
         prog = ps.program
+        np_ = lambda t: None if t is None else t.detach().cpu().contiguous().numpy()
+        obs_state = {k: np_(v) for k, v in (ps.obs_preprocess_state or {}).items()}
+        est = ts.max_advantage_est_state
         ckpt = {
             'next_update': int(next_update),
-            # 'params': the flax parameter tree of the reference (ml/train_state.py:34-40) as host
-            # arrays -- what a reference-side loader expects; 'params_flat': our arena (what load() uses)
-            'policy_states': {'params': _tree_to_host(prog.param_tree()),
-                              'params_flat': prog.params.cpu(),
-                              'obs_preprocess_state': ps.obs_preprocess_state},
-            'train_states': {'opt_state': {'m': prog.adam_m.cpu(), 'v': prog.adam_v.cpu(),
-                                           'count': prog.adam_step.cpu()},
-                             'value_normalizer_state': None if ts.value_normalizer_state is None
-                             else ts.value_normalizer_state.cpu(),
-                             'update_prng_key': ts.update_prng_key.cpu(),
-                             'initial_weight_norms': ts.initial_weight_norms},
-            'pbt_rng': self.pbt_rng.cpu(),
-            'user_state': self.user_state,
+            'policy_states': {
+                'params': _tree_to_host(prog.param_tree()),          # flax parameter tree (:34-40)
+                'params_flat': prog.params.cpu().numpy(),            # our arena (what load() restores)
+                'batch_stats': {}, 'obs_preprocess_state': obs_state, 'reward_hyper_params': None,
+                'episode_score': None, 'mmr': None,
+            },
+            'train_states': {
+                'opt_state': {'m': prog.adam_m.cpu().numpy(), 'v': prog.adam_v.cpu().numpy(),
+                              'count': prog.adam_step.cpu().numpy()},
+                'value_normalizer_state': np_(ts.value_normalizer_state),
+                'max_advantage_est_state': np_(est),
+                'hyper_params': {k: float(v) for k, v in vars(ts.hyper_params).items()
+                                 if isinstance(v, (int, float, bool))},
+                'scaler': None,
+                'update_prng_key': ts.update_prng_key.cpu().numpy(),
+                # per kernel leaf of the parameter tree, None elsewhere (:413-423)
+                'initial_weight_norms': prog.initial_weight_norms_tree(),
+                'initial_weight_norms_flat': {k: float(v) for k, v in ts.initial_weight_norms.items()},
+            },
+            'pbt_rng': self.pbt_rng.cpu().numpy(),
+            'user_state': None,            # the user pytree itself is in <path>.user_state (opt-in pickle)
         }
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         torch.save(ckpt, path)
+        if self.user_state is not None:
+            torch.save({'user_state': self.user_state}, path + '.user_state')
 
-    def load(self, path):
-        ckpt = torch.load(path, map_location='cpu', weights_only=False)
+    def load(self, path, load_user_state=False):
+        ckpt = torch.load(path, map_location='cpu', weights_only=True)
         ps, ts = self.policy_states, self.train_states
         prog = ps.program
-        prog.params.copy_(ckpt['policy_states']['params_flat'])
-        prog.adam_m.copy_(ckpt['train_states']['opt_state']['m'])
-        prog.adam_v.copy_(ckpt['train_states']['opt_state']['v'])
-        prog.adam_step.copy_(ckpt['train_states']['opt_state']['count'])
+        t = lambda a: torch.from_numpy(a)
+        prog.params.copy_(t(ckpt['policy_states']['params_flat']))
+        prog.adam_m.copy_(t(ckpt['train_states']['opt_state']['m']))
+        prog.adam_v.copy_(t(ckpt['train_states']['opt_state']['v']))
+        prog.adam_step.copy_(t(ckpt['train_states']['opt_state']['count']))
         if ts.value_normalizer_state is not None:
-            ts.value_normalizer_state.copy_(ckpt['train_states']['value_normalizer_state'])
-        ts.update_prng_key.copy_(ckpt['train_states']['update_prng_key'])
-        ts.initial_weight_norms = ckpt['train_states']['initial_weight_norms']
+            ts.value_normalizer_state.copy_(t(ckpt['train_states']['value_normalizer_state']))
+        if ts.max_advantage_est_state is not None and ckpt['train_states'].get('max_advantage_est_state') is not None:
+            ts.max_advantage_est_state.copy_(t(ckpt['train_states']['max_advantage_est_state']))
+        for k, v in (ckpt['policy_states'].get('obs_preprocess_state') or {}).items():
+            if v is not None and ps.obs_preprocess_state.get(k) is not None:
+                ps.obs_preprocess_state[k].copy_(t(v))
+        ts.update_prng_key.copy_(t(ckpt['train_states']['update_prng_key']))
+        ts.initial_weight_norms = dict(ckpt['train_states']['initial_weight_norms_flat'])
         # re-derive the device segment table from the restored initial norms
         prog.initial_weight_norms = ts.initial_weight_norms
         prog.rebuild_segments()
-        self.pbt_rng.copy_(ckpt['pbt_rng'])
-        self.user_state = ckpt['user_state']
+        self.pbt_rng.copy_(t(ckpt['pbt_rng']))
+        if load_user_state and os.path.exists(path + '.user_state'):       # opt-in: unpickles arbitrary objects
+            self.user_state = torch.load(path + '.user_state', map_location='cpu', weights_only=False)['user_state']
         return self, ckpt['next_update']
 
     @staticmethod

@@ -51,3 +51,31 @@ def test_header_is_plain_c():
     r = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c', hdr],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_tensorboard_tag_set(mlb):
+    """TrainingMetrics.tensorboard_log writes the reference's tag set (ml/metrics.py:218-244): for every
+    ring slot and metric `p0/<name> Mean|σ|Min|Max` at step base_update_idx + slot (host-side logic)."""
+    import ctypes
+    import numpy as np
+    import torch
+    from madrona_learn_b200 import _lib
+    from madrona_learn_b200.metrics import REC, TrainingMetrics
+    tm = TrainingMetrics(['Loss', 'Rewards'], buffer_size=2, start_update_idx=0, device='cpu')
+    recs = [_lib.Metric(1.5, 8.0, -1.0, 4.0, 2), _lib.Metric(0.25, 0.0, 0.25, 0.25, 1),
+            _lib.Metric(2.5, 18.0, 0.0, 5.0, 2), _lib.Metric(0.5, 0.0, 0.5, 0.5, 1)]
+    raw = np.frombuffer(b''.join(bytes(r) for r in recs), dtype=np.uint8).copy()
+    assert raw.size == 4 * REC == 4 * ctypes.sizeof(_lib.Metric)
+    tm.ring.copy_(torch.from_numpy(raw))
+    out = []
+
+    class W:
+        def scalar(self, tag, value, step):
+            out.append((tag, float(value), step))
+    tm.tensorboard_log(7, W())
+    tags = [t for t, _, _ in out]
+    assert tags[:4] == ['p0/Loss Mean', 'p0/Loss σ', 'p0/Loss Min', 'p0/Loss Max']
+    assert len(out) == 2 * 2 * 4 and {s for _, _, s in out} == {7, 8}
+    d = {(t, s): v for t, v, s in out}
+    assert d[('p0/Loss Mean', 7)] == 1.5 and d[('p0/Loss σ', 7)] == 2.0 and d[('p0/Loss Max', 8)] == 5.0
+    assert d[('p0/Rewards Min', 8)] == 0.5

@@ -240,8 +240,15 @@ def test_checkpoint_roundtrip_and_reference_key_tree(mlb, tmp_path):
         mgr.update_iter()
     mgr.save_ckpt(str(tmp_path / 'ckpt'))                     # -> <dir>/<next_update>, like the reference
     path = str(tmp_path / 'ckpt' / str(int(mgr.update_idx)))
-    ck = torch.load(path, map_location='cpu', weights_only=False)
+    ck = torch.load(path, map_location='cpu', weights_only=True)      # arrays / scalars only: no pickled code
     assert set(ck) == {'next_update', 'policy_states', 'train_states', 'pbt_rng', 'user_state'}
+    # the reference's PolicyState / PolicyTrainState leaves (ml/train_state.py:34-47, 85-99)
+    assert {'params', 'batch_stats', 'obs_preprocess_state', 'reward_hyper_params', 'episode_score', 'mmr'} <= set(ck['policy_states'])
+    assert {'opt_state', 'value_normalizer_state', 'max_advantage_est_state', 'hyper_params', 'scaler',
+            'update_prng_key', 'initial_weight_norms'} <= set(ck['train_states'])
+    iwn = ck['train_states']['initial_weight_norms']
+    assert iwn['backbone']['encoder']['net']['Dense_0']['kernel'] > 0 and iwn['actor']['impl']['kernel'] is None
+    assert iwn['backbone']['encoder']['net']['LayerNorm_0']['impl']['scale'] is None
     tree = ck['policy_states']['params']
     assert set(tree) == {'backbone', 'actor', 'critic'}
     net = tree['backbone']['encoder']['net']
