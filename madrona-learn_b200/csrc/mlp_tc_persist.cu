@@ -31,6 +31,19 @@ constexpr int BWD_XH_BUFS = 3;
 constexpr int MAX_A_STAGES = 8;
 constexpr float LN_EPS = 1e-6f;
 
+// phase timestamps for tools/probe/phase_profile.cu (never compiled into libmlb200.so)
+#ifdef MLB_PHASE_PROFILE
+__device__ int g_dbg = 0;      // probe-only knobs: 1 skip pass-1 math, 2 skip stores, 4 no xhat panels, 8 null epilogue
+#define DBG(bit) (g_dbg & (bit))
+__device__ unsigned long long* g_prof = nullptr;
+#define PROF(slot) do { if (g_prof && lane == 0 && (warp == 2 || warp == 17) && it < 8) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    g_prof[(((size_t)blockIdx.x * 8 + it) * 2 + (warp == 17)) * 8 + (slot)] = t_; } } while (0)
+#else
+#define PROF(slot) do { } while (0)
+#define DBG(bit) 0
+#endif
+
 struct PLayout {
     int w_bytes, a_off, stage_off, misc_off, total;
 };
@@ -84,7 +97,7 @@ __device__ __forceinline__ void p_mainloop(const CUtensorMap* tmA, const CUtenso
             const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
             const int a_total = my_tiles * num_kb;
             const int per_tile = num_panels * xh_reps;
-            const int x_total = XH_BUFS > 0 ? my_tiles * per_tile : 0;
+            const int x_total = (XH_BUFS > 0 && !DBG(12)) ? my_tiles * per_tile : 0;
             int it = a_total < A_STAGES ? a_total : A_STAGES, xit = 0;
             uint32_t idle = 0;
             while (it < a_total || xit < x_total) {
@@ -609,15 +622,6 @@ dx_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //     packed word so that each lane stores 8 contiguous bytes and the four lanes of a row fill a whole
 //     32-byte sector; otherwise each lane stores its own 4 bytes (half-sector writes merged by L2).
 // ==========================================================================================
-// phase timestamps for tools/probe/phase_profile.cu (never compiled into libmlb200.so)
-#ifdef MLB_PHASE_PROFILE
-__device__ unsigned long long* g_prof = nullptr;
-#define PROF(slot) do { if (g_prof && lane == 0 && (warp == 2 || warp == 17) && it < 8) { unsigned long long t_; \
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
-    g_prof[(((size_t)blockIdx.x * 8 + it) * 2 + (warp == 17)) * 8 + (slot)] = t_; } } while (0)
-#else
-#define PROF(slot) do { } while (0)
-#endif
 
 __device__ __forceinline__ float sel4(int c, float a0, float a1, float a2, float a3) {
     return c == 0 ? a0 : (c == 1 ? a1 : (c == 2 ? a2 : a3));
@@ -860,6 +864,12 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_wait(&p.bars.acc_full[buf], (it >> 1) & 1);
             tcgen05_fence_after();
             PROF(1);
+            if (DBG(8)) {                                    // probe: null epilogue (mainloop floor)
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p.bars.acc_empty[buf]);
+                return;
+            }
             // ---- pass 1 ------------------------------------------------------------------------
             float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t r[2][8];
@@ -874,7 +884,7 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (h2 == 0) {
                         const int xit = xbase + pn;
                         xs = xit % BWD_XH_BUFS;
-                        mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
+                        if (!DBG(4)) mbar_wait(&p.bars.xh_full[xs], (xit / BWD_XH_BUFS) & 1);
                         if (pn == 0) PROF(2);
                         pan = ring + xs * 16384;
                     }
@@ -888,6 +898,7 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         tmem_ld_16x256b_x2(tq + ((uint32_t)(16 * ((blk + 1) & 1)) << 16) + ((blk + 1) >> 1) * 64, r[cur ^ 1]);
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
+                        if (DBG(1)) break;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int i = 2 * h2 + h;
@@ -910,7 +921,7 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         }
                     }
                     tmem_st_16x256b_x2(tq + ((uint32_t)(16 * h2) << 16) + pn * 64, r[cur]);
-                    if (h2 == 1) {                           // both halves of the panel read: release it
+                    if (h2 == 1 && !DBG(4)) {                // both halves of the panel read: release it
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&p.bars.xh_empty[xs]);
                     }
@@ -958,7 +969,7 @@ dx_persist2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             const uint32_t send = odd ? o[0][h] : o[1][h];
                             const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
                             const uint2 v = odd ? make_uint2(recv, o[1][h]) : make_uint2(o[0][h], recv);
-                            if (FULLROWS || m0 + quad * 32 + rq + 8 * i < M) *reinterpret_cast<uint2*>(DZ + ro[i] + pn * 64) = v;
+                            if ((FULLROWS || m0 + quad * 32 + rq + 8 * i < M) && !DBG(2)) *reinterpret_cast<uint2*>(DZ + ro[i] + pn * 64) = v;
                         }
                     } else {
 #pragma unroll

@@ -67,5 +67,22 @@ int main() {
     }
     cudaMemcpy(h.data(), dprof, n * 8, cudaMemcpyDeviceToHost);
     report("dx_persist2", h, ctas, 4, true);
+    // decomposition of the backward kernel: device time with parts of the epilogue switched off
+    unsigned long long* nullp = nullptr;
+    cudaMemcpyToSymbol(g_prof, &nullp, sizeof(nullp));
+    const int modes[] = {0, 8, 4 | 1 | 2, 4 | 1, 4, 1, 2, 1 | 2};
+    const char* names[] = {"full", "null epilogue (TMA + MMA only)", "TMEM passes only (no xhat, no math, no stores)",
+                           "no xhat, no pass-1 math", "no xhat panels", "no pass-1 math", "no stores", "no pass-1 math, no stores"};
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int mi = 0; mi < 8; ++mi) {
+        cudaMemcpyToSymbol(g_dbg, &modes[mi], sizeof(int));
+        for (int w = 0; w < 3; ++w) tcp::launch_dx_persist(0, X, W, scale, bias, XH, rstd, DZ, ds, db, M, K, HN, K, HN);
+        cudaEventRecord(e0);
+        for (int w = 0; w < 10; ++w) tcp::launch_dx_persist(0, X, W, scale, bias, XH, rstd, DZ, ds, db, M, K, HN, K, HN);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        printf("dx2 dbg=%2d %-48s %7.2f us/launch (warm L2, 10 back-to-back)  err=%d\n", modes[mi], names[mi], ms * 100.f, (int)e);
+    }
     return 0;
 }
