@@ -429,6 +429,8 @@ MLB_API int mlb_dense_ln_relu_fwd_tc(void* stream, const void* X, const void* Wt
                 (XH == nullptr || mlb_aligned16(XH)));
     if (tcp::persist_ok(M, K, HN))
         return tcp::launch_fwd_persist(mlb_stream(stream), X, Wt, scale, bias, Y, XH, rstd, M, K, HN, ldx, ldw);
+    if (tcp::stream_ok(M, K, HN))
+        return tcp::launch_fwd_stream(mlb_stream(stream), X, Wt, scale, bias, Y, XH, rstd, M, K, HN, ldx, ldw);
     CUtensorMap tA, tB;
     int rc = make_map(&tA, X, K, M, ldx, 64, 128);
     if (rc) return rc;
@@ -463,6 +465,9 @@ MLB_API int mlb_dense_dx_lnbwd_tc(void* stream, const void* DZ_in, const void* W
     if (tcp::persist_ok(M, K, HN))
         return tcp::launch_dx_persist(mlb_stream(stream), DZ_in, W, scale, bias, XH, rstd, DZ_out, dscale, dbias,
                                       M, K, HN, lda, ldw);
+    if (tcp::stream_ok(M, K, HN))
+        return tcp::launch_dx_stream(mlb_stream(stream), DZ_in, W, scale, bias, XH, rstd, DZ_out, dscale, dbias,
+                                     M, K, HN, lda, ldw);
     CUtensorMap tA, tB;
     int rc = make_map(&tA, DZ_in, K, M, lda, 64, 128);
     if (rc) return rc;

@@ -18,4 +18,12 @@ int launch_dx_persist(cudaStream_t st, const void* DZ_in, const void* W, const f
                       const void* XH, const float* rstd, void* DZ_out, float* dscale, float* dbias, int M,
                       int K, int HN, int lda, int ldw);
 
+// weight-streaming persistent kernels for HN = 512 (two 256-column accumulator halves per row tile)
+bool stream_ok(int M, int K, int HN);
+int launch_fwd_stream(cudaStream_t st, const void* X, const void* Wt, const float* scale, const float* bias,
+                      void* Y, void* XH, float* rstd, int M, int K, int HN, int ldx, int ldw);
+int launch_dx_stream(cudaStream_t st, const void* DZ_in, const void* W, const float* scale, const float* bias,
+                     const void* XH, const float* rstd, void* DZ_out, float* dscale, float* dbias, int M,
+                     int K, int HN, int lda, int ldw);
+
 }  // namespace tcp

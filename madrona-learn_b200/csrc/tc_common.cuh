@@ -46,10 +46,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded waits trap instead of hanging the GPU.  Before trapping, the waiter leaves a word in a mapped
+// host buffer (when the translation unit registered one) saying WHICH wait gave up: the context is
+// unusable after a trap, the host word is still readable (mlb_debug_trap_word).
+static __device__ unsigned int* g_trap_host = nullptr;
+// g_trap_prog: per-CTA progress words (shared memory, optional) the trapping thread copies out
+static __device__ __noinline__ void trap_with(uint32_t code, const volatile uint32_t* prog = nullptr, int nprog = 0) {
+    if (g_trap_host) {
+        volatile unsigned int* h = reinterpret_cast<volatile unsigned int*>(g_trap_host);
+        if (atomicCAS(g_trap_host, 0u, 0x80000000u | (code << 16) | (blockIdx.x << 5) | (threadIdx.x >> 5)) == 0u) {
+            for (int i = 0; i < nprog && i < 24; ++i) h[1 + i] = prog[i];
+        }
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t code = 0,
+                                          const volatile uint32_t* prog = nullptr) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();      // never hang the GPU on a protocol bug
+        if (++spins > (1u << 22)) trap_with(code, prog, 20);      // never hang the GPU on a protocol bug
     }
 }
 // non-blocking probe of a phase (mbarrier.test_wait): lets ONE producer thread serve several
@@ -66,7 +82,8 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // latency-critical single-thread roles (TMA producer, MMA issuer): poll without the suspend hint
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, uint32_t code = 0,
+                                               const volatile uint32_t* prog = nullptr) {
     uint32_t ok = 0, spins = 0;
     while (true) {
         asm volatile(
@@ -77,7 +94,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (ok) break;
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 26)) trap_with(code, prog, 20);
     }
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst,

@@ -111,7 +111,8 @@ def _program(mlb, D, H, L, buckets, dtype):
 @pytest.mark.parametrize('D,H,L,rows,jitter', [(64, 256, 3, 4096, 0.2), (32, 128, 2, 1000, 0.2),
                                                (64, 512, 3, 2048, 0.2), (64, 256, 3, 20004, 0.2),
                                                (32, 128, 2, 39000, 0.2), (64, 256, 3, 65536, 0.0),
-                                               (64, 512, 3, 32768, 0.0), (64, 256, 3, 65536, 0.05)])
+                                               (64, 512, 3, 32768, 0.0), (64, 256, 3, 65536, 0.05),
+                                               (64, 512, 2, 20004, 0.2)])
 def test_tc_policy_forward_backward_vs_oracle(mlb, D, H, L, rows, jitter):
     import ctypes
     from madrona_learn_b200._lib import c_float, c_int, c_ll, c_size_t, call, ptr
