@@ -312,6 +312,16 @@ int mlb_lstm_cell_fwd_f32(void* stream, const float* z, const float* bias, const
 int mlb_lstm_cell_bwd_f32(void* stream, const float* dh_seq, int ld_dh, const float* dh_carry,
                           const float* dc_carry, const uint8_t* ends, const float* stash,
                           const float* c_prev, float* dz, float* dc_prev, long long M, int H);
+/* Tensor-core path (compute_dtype = bfloat16; ml/rnn.py:10-111 with the recurrent products on tcgen05   */
+/* through mlb_gemm_bf16_tc): same cell math, fp32 cell state, bf16 GEMM operands.  h_seq_bf16 [M, H]     */
+/* unmasked output; h_carry (f32, may be NULL) / h_carry_bf16 (may be NULL): masked carry; bias may be    */
+/* NULL when the GEMM epilogue already added it.  dz_bf16 [M, 4H].                                        */
+int mlb_lstm_cell_fwd_tc(void* stream, const float* z, const float* bias, const float* c_prev,
+                         const uint8_t* ends, void* h_seq_bf16, float* c_carry, float* h_carry,
+                         void* h_carry_bf16, float* stash, long long M, int H);
+int mlb_lstm_cell_bwd_tc(void* stream, const float* dh_seq, int ld_dh, const float* dh_carry,
+                         const float* dc_carry, const uint8_t* ends, const float* stash,
+                         const float* c_prev, void* dz_bf16, float* dc_prev, long long M, int H);
 /* clear_recurrent_state (ml/rnn.py:66-81): state[m, :] = 0 where dones[m] */
 int mlb_rnn_reset_f32(void* stream, float* state, const uint8_t* dones, long long M, int H);
 
@@ -441,6 +451,7 @@ int mlb_optimizer_step_fused(void* stream, float* params, const float* grads, fl
                              size_t ws_bytes, float* zero_after);
 /* out[c] += sum_r x[r, c] for c < ncols (bias gradients of the heads) */
 int mlb_colsum_f32(void* stream, const float* x, long long rows, int ld, int ncols, float* out);
+int mlb_colsum_bf16(void* stream, const void* x, long long rows, int ld, int ncols, float* out);
 
 /* ------------------------------------------------------------------------------------ */
 /* PBT policy-batch reorder: _compute_reorder_chunks                        */

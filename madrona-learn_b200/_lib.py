@@ -88,6 +88,8 @@ SIGNATURES = {
     'mlb_cast_weight_bf16': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int]),
     'mlb_lstm_cell_fwd_f32': (c_int, [P, P, P, P, P, P, P, P, P, c_ll, c_int]),
     'mlb_lstm_cell_bwd_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_lstm_cell_fwd_tc': (c_int, [P, P, P, P, P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_lstm_cell_bwd_tc': (c_int, [P, P, c_int, P, P, P, P, P, P, P, c_ll, c_int]),
     'mlb_rnn_reset_f32': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
@@ -114,6 +116,7 @@ SIGNATURES = {
     'mlb_optimizer_step_fused': (c_int, [P, P, P, P, P, c_ll, P, c_int, P, P, P, c_int, c_float, c_float, c_float,
                                          c_float, c_float, c_float, P, P, c_size_t, P]),
     'mlb_colsum_f32': (c_int, [P, P, c_ll, c_int, c_int, P]),
+    'mlb_colsum_bf16': (c_int, [P, P, c_ll, c_int, c_int, P]),
     'mlb_synth_env_init': (c_int, [P, P, c_ll, c_int, ctypes.c_uint32, P]),
     'mlb_synth_env_step': (c_int, [P, P, P, P, c_int, P, P, P, c_ll, c_int, ctypes.c_uint32,
                                    c_float]),

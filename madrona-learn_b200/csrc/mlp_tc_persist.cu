@@ -1072,17 +1072,33 @@ __host__ __device__ inline SLayout s_layout(int HN, int nh, int stages, int stag
     return l;
 }
 
+struct SBars {
+    uint64_t *full, *empty, *acc_full, *acc_empty, *xh_full, *xh_empty;
+    uint32_t* tmem_slot;
+};
+__device__ __forceinline__ SBars s_bars(uint8_t* base) {
+    SBars b;
+    b.full = reinterpret_cast<uint64_t*>(base);
+    b.empty = b.full + MAX_A_STAGES;
+    b.acc_full = b.empty + MAX_A_STAGES;     // [4]: one per TMEM accumulator buffer
+    b.acc_empty = b.acc_full + 4;            // [4]
+    b.xh_full = b.acc_empty + 4;             // [4]
+    b.xh_empty = b.xh_full + 4;              // [4]
+    b.tmem_slot = reinterpret_cast<uint32_t*>(b.xh_empty + 4);
+    return b;
+}
+
 struct SState {
     uint8_t* smem;
     SLayout L;
-    PBars bars;
+    SBars bars;
     float* fsm;
     uint32_t tmem_base;
 };
 
 template <int NH>
 __device__ __forceinline__ void s_issue_stage(const CUtensorMap* tmA, const CUtensorMap* tmB, uint8_t* smem,
-                                              const SLayout& L, const PBars& bars, int it, int num_kb, int stages,
+                                              const SLayout& L, const SBars& bars, int it, int num_kb, int stages,
                                               int w_rows) {
     const int s = it % stages;
     const int u = it / num_kb, kb = it % num_kb;
@@ -1102,13 +1118,13 @@ __device__ __forceinline__ SState s_prologue(uint8_t* smem_raw, const CUtensorMa
     p.smem = align_smem_1024(smem_raw);
     p.L = s_layout(HN, NH, stages, staging_bytes);
     p.fsm = reinterpret_cast<float*>(p.smem + p.L.misc_off);
-    p.bars = p_bars(reinterpret_cast<uint8_t*>(p.fsm + 4 * HN + 2048));
+    p.bars = s_bars(reinterpret_cast<uint8_t*>(p.fsm + 4 * HN + 2048));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmB)) : "memory");
         for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(&p.bars.full[s], 1); mbar_init(&p.bars.empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&p.bars.acc_full[s], 1); mbar_init(&p.bars.acc_empty[s], 16); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&p.bars.acc_full[s], 1); mbar_init(&p.bars.acc_empty[s], 16); }
         for (int s = 0; s < 4; ++s) { mbar_init(&p.bars.xh_full[s], 1); mbar_init(&p.bars.xh_empty[s], 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const int num_kb = (K + BK - 1) / BK;
@@ -1146,6 +1162,7 @@ __device__ __forceinline__ void s_mainloop(const CUtensorMap* tmA, const CUtenso
                                            int stages) {
     const int num_kb = (K + BK - 1) / BK;
     const int w_rows = HN / NH;
+    constexpr int NB = NH;                                   // TMEM accumulator buffers: 512 / (HN / NH) columns each
     if (warp == 0) {
         if (lane == 0) {
             const int num_panels = HN / 64;
@@ -1189,10 +1206,10 @@ __device__ __forceinline__ void s_mainloop(const CUtensorMap* tmA, const CUtenso
             int it = 0, u = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int h = 0; h < NH; ++h, ++u) {
-                    const int buf = u & 1;
-                    mbar_wait_spin(&p.bars.acc_empty[buf], ((u >> 1) & 1) ^ 1, 5);   // epilogue drained this half
+                    const int buf = u % NB;
+                    mbar_wait_spin(&p.bars.acc_empty[buf], ((u / NB) & 1) ^ 1, 5);   // epilogue drained this buffer
                     tcgen05_fence_after();
-                    const uint32_t d_tmem = p.tmem_base + buf * 256;
+                    const uint32_t d_tmem = p.tmem_base + buf * w_rows;
                     for (int kb = 0; kb < num_kb; ++kb, ++it) {
                         const int s = it % stages;
                         mbar_wait_spin(&p.bars.full[s], (it / stages) & 1, 6);
@@ -1235,7 +1252,8 @@ fwd_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float* s = p.fsm;
         const float* b = p.fsm + HN;
         uint8_t* wt = p.smem + p.L.stage_off + (warp - 2) * 2048;
-        const int nchunks = HN / 32, cpu = nchunks / NH;          // chunks per accumulator unit (>= 4)
+        constexpr int cpu = 16 / NH;                              // 32-column chunks per accumulator unit (HN = 512)
+        const int nchunks = HN / 32;
         const float invH = 1.f / (float)HN;
         const uint32_t tq = p.tmem_base + ((uint32_t)(quad * 32) << 16);
         int i = 0;
@@ -1248,12 +1266,12 @@ fwd_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int ch = grp; ch < nchunks; ch += 4) {
                 const int u = s_unit<NH>(i, ch, cpu);
                 if (u != seen) {
-                    mbar_wait(&p.bars.acc_full[u & 1], (u >> 1) & 1, 1);
+                    mbar_wait(&p.bars.acc_full[u % NH], (u / NH) & 1, 1);
                     tcgen05_fence_after();
                     seen = u;
                 }
                 uint32_t r[32];
-                tmem_ld32(tq + (u & 1) * 256 + (ch % cpu) * 32, r);
+                tmem_ld32(tq + (u % NH) * (32 * cpu) + (ch % cpu) * 32, r);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { const float z = __uint_as_float(r[j]); sum += z; sq = fmaf(z, z, sq); }
             }
@@ -1266,11 +1284,11 @@ fwd_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int c = ch * 32;
                 const int u = s_unit<NH>(i, ch, cpu);
                 uint32_t r[32];
-                tmem_ld32(tq + (u & 1) * 256 + (ch % cpu) * 32, r);
+                tmem_ld32(tq + (u % NH) * (32 * cpu) + (ch % cpu) * 32, r);
                 if ((ch % cpu) + 4 >= cpu) {                 // last read of this warp from this accumulator unit
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&p.bars.acc_empty[u & 1]);
+                    if (lane == 0) mbar_arrive(&p.bars.acc_empty[u % NH]);
                 }
                 uint32_t yp[16], xp[16];
                 ln_relu_chunk(r, rstd, -mean * rstd, s + c, b + c, yp, xp);
@@ -1312,7 +1330,8 @@ dx_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float* cb = p.fsm + 3 * HN;
         float* part = p.fsm + 4 * HN;
         uint8_t* ring = p.smem + p.L.stage_off;
-        const int nchunks = HN / 32, num_panels = HN / 64, cpu = nchunks / NH;
+        constexpr int cpu = 16 / NH;
+        const int nchunks = HN / 32, num_panels = HN / 64;
         const float invH = 1.f / (float)HN;
         const uint32_t tq = p.tmem_base + ((uint32_t)(quad * 32) << 16);
         int i = 0;
@@ -1337,11 +1356,11 @@ dx_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int ch = 2 * pn + (grp & 1);
                 const int u = s_unit<NH>(i, ch, cpu);
                 if (u != seen) {
-                    mbar_wait(&p.bars.acc_full[u & 1], (u >> 1) & 1, 2);
+                    mbar_wait(&p.bars.acc_full[u % NH], (u / NH) & 1, 2);
                     tcgen05_fence_after();
                     seen = u;
                 }
-                const uint32_t taddr = tq + (u & 1) * 256 + (ch % cpu) * 32;
+                const uint32_t taddr = tq + (u % NH) * (32 * cpu) + (ch % cpu) * 32;
                 const int c = ch * 32, hf = ch & 1;
                 uint32_t r[32];
                 tmem_ld32(taddr, r);
@@ -1403,11 +1422,11 @@ dx_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int u = s_unit<NH>(i, ch, cpu);
                 const int c = ch * 32, hf = ch & 1;
                 uint32_t r[32];
-                tmem_ld32(tq + (u & 1) * 256 + (ch % cpu) * 32, r);
+                tmem_ld32(tq + (u % NH) * (32 * cpu) + (ch % cpu) * 32, r);
                 if ((ch % cpu) + 4 >= cpu) {
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&p.bars.acc_empty[u & 1]);
+                    if (lane == 0) mbar_arrive(&p.bars.acc_empty[u % NH]);
                 }
                 uint8_t* pan = ring + xs * 16384;
 #pragma unroll
@@ -1586,6 +1605,13 @@ bool stream_ok(int M, int K, int HN) {
     return mode == 2 || (M + tc::BM - 1) / tc::BM > sm_count() / 2;
 }
 
+// accumulator units per row tile: 2 x 256 columns (default) or 4 x 128 (MLB_TC_STREAM_NH=4: finer release
+// granularity, but N = 128 MMAs and twice the activation re-reads -- measured 10-15 % slower on B200)
+static int stream_nh() {
+    static const int nh = [] { const char* v = getenv("MLB_TC_STREAM_NH"); return (v && atoi(v) == 4) ? 4 : 2; }();
+    return nh;
+}
+
 static int stream_stages(int HN, int nh, int staging_bytes) {
     int st = 2;
     while (st < MAX_A_STAGES && s_layout(HN, nh, st + 1, staging_bytes).total <= 227 * 1024) ++st;
@@ -1597,11 +1623,12 @@ int launch_fwd_stream(cudaStream_t st, const void* X, const void* Wt, const floa
     CUtensorMap tA, tB;
     int rc;
     if ((rc = make_map(&tA, X, K, M, ldx, 64, 128))) return rc;
-    if ((rc = make_map(&tB, Wt, K, HN, ldw, 64, HN / 2))) return rc;
+    const int nh = stream_nh();
+    if ((rc = make_map(&tB, Wt, K, HN, ldw, 64, HN / nh))) return rc;
     ensure_trap_slot();
-    const int stages = stream_stages(HN, 2, 32768);
-    const int smem = s_layout(HN, 2, stages, 32768).total;
-    auto kern = fwd_stream_kernel<2>;
+    const int stages = stream_stages(HN, nh, 32768);
+    const int smem = s_layout(HN, nh, stages, 32768).total;
+    auto kern = nh == 2 ? fwd_stream_kernel<2> : fwd_stream_kernel<4>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const int tiles = (M + BM - 1) / BM;
@@ -1618,11 +1645,13 @@ int launch_dx_stream(cudaStream_t st, const void* DZ_in, const void* W, const fl
     CUtensorMap tA, tB, tXH;
     int rc;
     if ((rc = make_map(&tA, DZ_in, K, M, lda, 64, 128))) return rc;
-    if ((rc = make_map(&tB, W, K, HN, ldw, 64, HN / 2))) return rc;
+    const int nh = stream_nh();
+    if ((rc = make_map(&tB, W, K, HN, ldw, 64, HN / nh))) return rc;
     if ((rc = make_map(&tXH, XH, HN, M, HN, 64, 128))) return rc;
-    const int stages = stream_stages(HN, 2, BWD_XH_BUFS * 16384);
-    const int smem = s_layout(HN, 2, stages, BWD_XH_BUFS * 16384).total;
-    auto kern = dx_stream_kernel<2>;
+    ensure_trap_slot();
+    const int stages = stream_stages(HN, nh, BWD_XH_BUFS * 16384);
+    const int smem = s_layout(HN, nh, stages, BWD_XH_BUFS * 16384).total;
+    auto kern = nh == 2 ? dx_stream_kernel<2> : dx_stream_kernel<4>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const int tiles = (M + BM - 1) / BM;

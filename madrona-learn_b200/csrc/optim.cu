@@ -271,14 +271,18 @@ optimizer_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float
     pdl_launch_dependents();
 }
 
+__device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ x, long long rows, int ld, int ncols, float* __restrict__ out) {
+colsum_kernel(const T* __restrict__ x, long long rows, int ld, int ncols, float* __restrict__ out) {
     // blockDim = (32 cols, 8 row-lanes); each block strides over rows
     const int c = blockIdx.y * 32 + threadIdx.x;
     float s = 0.f;
     if (c < ncols)
         for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y)
-            s += x[r * ld + c];
+            s += ld_as_float(x + r * ld + c);
     __shared__ float sm[8][33];
     sm[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
@@ -371,7 +375,18 @@ MLB_API int mlb_colsum_f32(void* stream, const float* x, long long rows, int ld,
     if (rows == 0) return MLB_OK;
     long long g = (rows + 63) / 64;
     if (g > MLB_NUM_SMS * 4) g = MLB_NUM_SMS * 4;
-    colsum_kernel<<<dim3((unsigned)g, (unsigned)((ncols + 31) / 32)), dim3(32, 8), 0, mlb_stream(stream)>>>(x, rows, ld, ncols, out);
+    colsum_kernel<float><<<dim3((unsigned)g, (unsigned)((ncols + 31) / 32)), dim3(32, 8), 0, mlb_stream(stream)>>>(x, rows, ld, ncols, out);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
+MLB_API int mlb_colsum_bf16(void* stream, const void* x, long long rows, int ld, int ncols, float* out) {
+    MLB_REQUIRE(x && out && rows >= 0 && ncols > 0 && ld >= ncols);
+    if (rows == 0) return MLB_OK;
+    long long g = (rows + 63) / 64;
+    if (g > MLB_NUM_SMS * 4) g = MLB_NUM_SMS * 4;
+    colsum_kernel<__nv_bfloat16><<<dim3((unsigned)g, (unsigned)((ncols + 31) / 32)), dim3(32, 8), 0, mlb_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), rows, ld, ncols, out);
     MLB_CHECK_LAUNCH();
     return MLB_OK;
 }

@@ -71,8 +71,6 @@ class PolicyProgram:
         if not isinstance(enc, (BackboneEncoder, RecurrentBackboneEncoder)) or not isinstance(enc.net, MLP):
             raise NotImplementedError('encoder must be [Recurrent]BackboneEncoder(net=MLP[, rnn=LSTM])')
         self._rnn_desc = enc.rnn if isinstance(enc, RecurrentBackboneEncoder) else None
-        if self._rnn_desc is not None and self.tc:
-            raise NotImplementedError('LSTM on the bf16 tensor-core path: next (use compute_dtype=float32)')
         if not isinstance(actor_critic.actor, DenseLayerDiscreteActor):
             raise NotImplementedError('actor must be DenseLayerDiscreteActor')
         if not isinstance(actor_critic.critic, (DenseLayerCritic, DreamerV3Critic)):
@@ -293,6 +291,8 @@ class PolicyProgram:
         W, _ = self.head_views(self.params)
         call('mlb_cast_weight_bf16', ptr(W), ptr(self.wh_t), ptr(self.wh_c), c_int(self.feat), c_int(self.NH),
              c_int(self.NH), c_int(self.feat), c_int(self.NH))
+        if self.lstm is not None:
+            self.lstm.refresh_bf16()
 
     def rebuild_segments(self):
         self.refresh_bf16()
@@ -308,7 +308,7 @@ class PolicyProgram:
         if self.lstm is not None:
             lsegs = self.lstm.segments(self.params.detach().cpu(), self.initial_weight_norms)
             segs += lsegs
-            copies += [none] * len(lsegs)
+            copies += self.lstm.bf16_copies() if self.tc else [none] * len(lsegs)
         # the fused actor+critic head matrix is not re-projected (kind 0) but its bf16 copies are refreshed
         segs.append(_lib.Segment(self.head_w_off, self.feat * self.NH, 0, 0.0))
         copies.append(_lib.Bf16Copy(self.wh_t.data_ptr(), self.wh_c.data_ptr(), self.feat, self.NH, self.feat,
@@ -385,7 +385,8 @@ class PolicyProgram:
         `rnn_states` ([c], [h]) in place."""
         w = self.infer_ws(rows)
         if self.tc:
-            return self._forward_tc(obs, rows, w, [w['y'][i & 1] for i in range(self.L)], None, None)
+            return self._forward_tc(obs, rows, w, [w['y'][i & 1] for i in range(self.L)], None, None,
+                                    rnn_states=rnn_states)
         x, d = obs, self.obs_dim
         for i in range(self.L):
             k, s, b = self.layer_views(self.params, i)
@@ -402,7 +403,7 @@ class PolicyProgram:
         gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
         return w['head']
 
-    def _forward_tc(self, obs, rows, w, ys, xhs, rstds, x_ready=False):
+    def _forward_tc(self, obs, rows, w, ys, xhs, rstds, x_ready=False, seq=None, rnn_states=None):
         """bf16 tensor-core forward: cast obs -> L x fused [tcgen05 GEMM + LayerNorm + ReLU epilogue
         out of TMEM] -> head GEMM (fp32 out + bias).  Training also stashes xhat (bf16) and rstd."""
         if not x_ready:                    # x_ready: the minibatch gather already wrote the bf16 copy into w['x']
@@ -414,6 +415,14 @@ class PolicyProgram:
                  ptr(None if xhs is None else xhs[i]), ptr(None if rstds is None else rstds[i]),
                  c_int(rows), c_int(d), c_int(self.H), c_int(d), c_int(d))
             x, d = ys[i], self.H
+        if self.lstm is not None:
+            if seq is not None:                       # training: the whole T' sequence
+                x = self.lstm.sequence_fwd(x, seq)
+            else:                                     # rollout: one step, states updated in place
+                if 'rz' not in w:
+                    w['rz'] = torch.empty(rows, 4 * self.lstm.RH, dtype=F32, device=self.device)
+                    w['rout'] = torch.empty(rows, self.lstm.RH, dtype=torch.bfloat16, device=self.device)
+                x = self.lstm.step_infer(x, rows, rnn_states, w['rz'], w['rout'])
         _, B = self.head_views(self.params)
         gemm_tc(x, self.wh_t, w['head'], B, rows, self.NH, self.feat, self.feat, self.feat, self.NH, 0, 0, 0)
         return w['head']
@@ -460,7 +469,7 @@ class PolicyProgram:
         """seq (recurrent encoders): dict(Tp, M, ends u8 [T', M], c0, h0 [M, RH])."""
         w = self.train_ws(rows)
         if self.tc:
-            return self._forward_tc(obs, rows, w, w['y'], w['xh'], w['rstd'], x_ready)
+            return self._forward_tc(obs, rows, w, w['y'], w['xh'], w['rstd'], x_ready, seq=seq)
         x, d = obs, self.obs_dim
         for i in range(self.L):
             k, s, b = self.layer_views(self.params, i)
@@ -478,7 +487,7 @@ class PolicyProgram:
         """Consumes train_ws['dhead']; accumulates into self.grads (pre-zeroed)."""
         w = self.train_ws(rows)
         if self.tc:
-            return self._backward_tc(rows, w)
+            return self._backward_tc(rows, w, seq)
         W, B = self.head_views(self.params)
         gW, gB = self.head_views(self.grads)
         if self.lstm is not None:
@@ -505,7 +514,7 @@ class PolicyProgram:
             if i > 0:
                 gemm(w['dz'], k, w['dy'], None, rows, d, self.H, self.H, self.H, d, ta=0, tb=1)
 
-    def _backward_tc(self, rows, w):
+    def _backward_tc(self, rows, w, seq=None):
         """bf16 tensor-core backward.  dW products are MN-major x MN-major split-K GEMMs with
         fp32 atomic accumulation straight into the gradient arena.  The dW GEMMs only depend on
         the dZ their layer's dx kernel produced, so they run on a side stream underneath the next
@@ -524,18 +533,30 @@ class PolicyProgram:
                 fn()
 
         gW, _ = self.head_views(self.grads)       # (head bias grads were accumulated by the loss kernel)
-        feat = w['y'][self.L - 1]
+        lw = self.lstm.train_ws(seq['Tp'], seq['M']) if self.lstm is not None else None
+        feat = w['y'][self.L - 1] if lw is None else lw['h_seq'].view(rows, self.feat)
         on_side(lambda: gemm_tc(feat, w['dhead'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH,
                                 1, 1, 2, _splitk_tc(self.feat, self.NH, rows)))
-        # dfeat = dhead Wh^T fused with the LayerNorm/ReLU backward of the last layer -> dZ_{L-1}
         bufs = w['dzs']                           # rotating dZ buffers (3: a dW may still read the oldest)
         cur = 0
         i = self.L - 1
         _, s, b = self.layer_views(self.params, i)
         _, gs, gb = self.layer_views(self.grads, i)
-        call('mlb_dense_dx_lnbwd_tc', ptr(w['dhead']), ptr(self.wh_c), ptr(s), ptr(b), ptr(w['xh'][i]),
-             ptr(w['rstd'][i]), ptr(bufs[cur]), ptr(gs), ptr(gb), c_int(rows), c_int(self.NH), c_int(self.H),
-             c_int(self.NH), c_int(self.NH))
+        if lw is None:
+            # dfeat = dhead Wh^T fused with the LayerNorm/ReLU backward of the last layer -> dZ_{L-1}
+            call('mlb_dense_dx_lnbwd_tc', ptr(w['dhead']), ptr(self.wh_c), ptr(s), ptr(b), ptr(w['xh'][i]),
+                 ptr(w['rstd'][i]), ptr(bufs[cur]), ptr(gs), ptr(gb), c_int(rows), c_int(self.NH), c_int(self.H),
+                 c_int(self.NH), c_int(self.NH))
+        else:
+            # d(encoder output) = dhead Wh^T (fp32), BPTT through the LSTM, then the gradient to the MLP output
+            # (dz_all W_i) fused with the last layer's LayerNorm/ReLU backward
+            RH4 = 4 * self.lstm.RH
+            gemm_tc(w['dhead'], self.wh_c, lw['d_hseq'], None, rows, self.feat, self.NH, self.NH, self.NH, self.feat,
+                    0, 0, 0)
+            self.lstm.sequence_bwd(w['y'][i], seq, None)
+            call('mlb_dense_dx_lnbwd_tc', ptr(lw['dz']), ptr(self.lstm.wi_t), ptr(s), ptr(b), ptr(w['xh'][i]),
+                 ptr(w['rstd'][i]), ptr(bufs[cur]), ptr(gs), ptr(gb), c_int(rows), c_int(RH4), c_int(self.H),
+                 c_int(RH4), c_int(RH4))
         for i in range(self.L - 1, -1, -1):
             gk, _, _ = self.layer_views(self.grads, i)
             d = self.layer_off[i][2]

@@ -11,6 +11,12 @@ then adds h_{t-1} W_h (accumulating GEMM) and runs the cell kernel, which writes
 output and the carry zeroed where the step ended an episode.  BPTT walks the steps backwards
 with the cell backward kernel + one GEMM per step; dW_i, dW_h, db_h and the gradient to the
 layer below are single GEMMs over all steps.
+
+compute_dtype = bfloat16 (`prog.tc`): every one of those products runs on the tcgen05 tensor cores
+(mlb_gemm_bf16_tc: bf16 operands, fp32 accumulation).  The cell state c, the gate pre-activations z
+and the stash stay fp32; h, the encoder output and dz are written as bf16 by the cell kernels because
+they are GEMM operands.  bf16 copies of W_i (both orientations) and W_h are refreshed by the fused
+optimiser, like the Dense kernels.
 """
 import math
 
@@ -42,6 +48,15 @@ class LSTMLowering:
         self.end_off = off
         self.prog = prog
         self._ws = None
+        self.tc = bool(getattr(prog, 'tc', False))
+        if self.tc:
+            if self.RH % 64 or self.in_dim % 8:
+                raise NotImplementedError('tensor-core LSTM needs num_hidden_channels % 64 == 0 and in_dim % 8 == 0')
+            BF, dev, RH, d = torch.bfloat16, prog.device, self.RH, self.in_dim
+            self.wi_c = torch.zeros(4 * RH, d, dtype=BF, device=dev)       # z = x W_i^T : B [N = 4RH, K = in]
+            self.wi_t = torch.zeros(d, 4 * RH, dtype=BF, device=dev)       # dx = dz W_i : B [N = in, K = 4RH]
+            self.wh_c = torch.zeros(4 * RH, RH, dtype=BF, device=dev)      # z += h W_h^T ; dh = dz W_h (MN-major B)
+            self.wh_t = torch.zeros(RH, 4 * RH, dtype=BF, device=dev)      # (the optimiser writes both orientations)
 
     # ---- parameter views ---------------------------------------------------------------
     def views(self, arena):
@@ -92,6 +107,26 @@ class LSTMLowering:
                 segs.append(_lib.Segment(off, n, 1, norms[k]))
         return segs
 
+    def refresh_bf16(self):
+        wi, wh, _ = self.views(self.prog.params)
+        RH, d = self.RH, self.in_dim
+        call('mlb_cast_weight_bf16', ptr(wi), ptr(self.wi_t), ptr(self.wi_c), c_int(4 * RH), c_int(d), c_int(d),
+             c_int(4 * RH), c_int(d))
+        call('mlb_cast_weight_bf16', ptr(wh), ptr(self.wh_t), ptr(self.wh_c), c_int(4 * RH), c_int(RH), c_int(RH),
+             c_int(4 * RH), c_int(RH))
+
+    def bf16_copies(self):
+        """One mlb_bf16_copy per segment of segments(), same order: gate block g of W_i is the [RH, in]
+        row block g of wi_c (and the column block g of wi_t); likewise W_h."""
+        RH, d = self.RH, self.in_dim
+        out = []
+        for g in range(4):
+            out.append(_lib.Bf16Copy(self.wi_t.data_ptr() + 2 * g * RH, self.wi_c.data_ptr() + 2 * g * RH * d,
+                                     RH, d, 4 * RH, d))
+            out.append(_lib.Bf16Copy(self.wh_t.data_ptr() + 2 * g * RH, self.wh_c.data_ptr() + 2 * g * RH * RH,
+                                     RH, RH, 4 * RH, RH))
+        return out
+
     # ---- state ------------------------------------------------------------------------
     def init_states(self, N, device):
         z = lambda: torch.zeros(N, self.RH, dtype=F32, device=device)
@@ -100,15 +135,29 @@ class LSTMLowering:
     # ---- rollout step -------------------------------------------------------------------
     def step_infer(self, x, rows, states, z_buf, out):
         """x [rows, in] -> out [rows, RH]; states ([c], [h]) updated in place."""
-        from .engine import gemm
+        from .engine import gemm, gemm_tc
         wi, wh, b = self.views(self.prog.params)
         c, h = states[0][0], states[1][0]
         RH, d = self.RH, self.in_dim
+        if self.tc:                    # x, out: bf16; states stay fp32 (h is cast for the recurrent GEMM)
+            hb = self._h_bf(rows)
+            call('mlb_cast_f32_bf16', ptr(h), ptr(hb), c_ll(rows * RH))
+            gemm_tc(x, self.wi_c, z_buf, b, rows, 4 * RH, d, d, d, 4 * RH, 0, 0, 0)
+            gemm_tc(hb, self.wh_c, z_buf, None, rows, 4 * RH, RH, RH, RH, 4 * RH, 0, 0, 2)
+            call('mlb_lstm_cell_fwd_tc', ptr(z_buf), ptr(None), ptr(c), ptr(None), ptr(out), ptr(c), ptr(h),
+                 ptr(None), ptr(None), c_ll(rows), c_int(RH))
+            return out
         gemm(x, wi, z_buf, None, rows, 4 * RH, d, d, d, 4 * RH, ta=0, tb=1)
         gemm(h, wh, z_buf, None, rows, 4 * RH, RH, RH, RH, 4 * RH, ta=0, tb=1, accumulate=1)
         call('mlb_lstm_cell_fwd_f32', ptr(z_buf), ptr(b), ptr(c), ptr(None), ptr(out), ptr(c), ptr(h),
              ptr(None), c_ll(rows), c_int(RH))
         return out
+
+    def _h_bf(self, rows):
+        hb = getattr(self, '_hb', None)
+        if hb is None or hb.shape[0] < rows:
+            hb = self._hb = torch.empty(rows, self.RH, dtype=torch.bfloat16, device=self.prog.device)
+        return hb
 
     def reset(self, states, dones, rows):
         for s in (states[0][0], states[1][0]):
@@ -120,20 +169,34 @@ class LSTMLowering:
         if w is None or w['Tp'] != Tp or w['M'] < M:
             dev, RH = self.prog.device, self.RH
             e = lambda *s: torch.empty(*s, dtype=F32, device=dev)
-            w = dict(Tp=Tp, M=M, z=e(Tp, M, 4 * RH), h_in=e(Tp + 1, M, RH), c_in=e(Tp + 1, M, RH),
-                     h_seq=e(Tp, M, RH), stash=e(Tp, M, 5 * RH), d_hseq=e(Tp, M, RH),
-                     dh=e(M, RH), dc=[e(M, RH), e(M, RH)])
+            HT = torch.bfloat16 if self.tc else F32      # h / encoder output: GEMM operands on the tc path
+            w = dict(Tp=Tp, M=M, z=e(Tp, M, 4 * RH), c_in=e(Tp + 1, M, RH),
+                     h_in=torch.empty(Tp + 1, M, RH, dtype=HT, device=dev),
+                     h_seq=torch.empty(Tp, M, RH, dtype=HT, device=dev), stash=e(Tp, M, 5 * RH),
+                     d_hseq=e(Tp, M, RH), dh=e(M, RH), dc=[e(M, RH), e(M, RH)])
+            if self.tc:
+                w['dz'] = torch.empty(Tp, M, 4 * RH, dtype=HT, device=dev)
             self._ws = w
         return w
 
     def sequence_fwd(self, feats, seq):
         """feats [T'*M, in]; seq: dict(Tp, M, ends u8 [T', M], c0 [M, RH], h0 [M, RH]).
         Returns h_seq [T'*M, RH] (the encoder output)."""
-        from .engine import gemm
+        from .engine import gemm, gemm_tc
         Tp, M = seq['Tp'], seq['M']
         w = self.train_ws(Tp, M)
         wi, wh, b = self.views(self.prog.params)
         RH, d, rows = self.RH, self.in_dim, Tp * M
+        if self.tc:
+            gemm_tc(feats, self.wi_c, w['z'], b, rows, 4 * RH, d, d, d, 4 * RH, 0, 0, 0)     # + bias in the epilogue
+            call('mlb_copy_bytes', ptr(seq['c0']), ptr(w['c_in'][0]), _lib.c_size_t(M * RH * 4))
+            call('mlb_cast_f32_bf16', ptr(seq['h0']), ptr(w['h_in'][0]), c_ll(M * RH))
+            for t in range(Tp):
+                gemm_tc(w['h_in'][t], self.wh_c, w['z'][t], None, M, 4 * RH, RH, RH, RH, 4 * RH, 0, 0, 2)
+                call('mlb_lstm_cell_fwd_tc', ptr(w['z'][t]), ptr(None), ptr(w['c_in'][t]), ptr(seq['ends'][t]),
+                     ptr(w['h_seq'][t]), ptr(w['c_in'][t + 1]), ptr(None), ptr(w['h_in'][t + 1]), ptr(w['stash'][t]),
+                     c_ll(M), c_int(RH))
+            return w['h_seq'].view(rows, RH)
         gemm(feats, wi, w['z'], None, rows, 4 * RH, d, d, d, 4 * RH, ta=0, tb=1)
         call('mlb_copy_bytes', ptr(seq['c0']), ptr(w['c_in'][0]), _lib.c_size_t(M * RH * 4))
         call('mlb_copy_bytes', ptr(seq['h0']), ptr(w['h_in'][0]), _lib.c_size_t(M * RH * 4))
@@ -153,6 +216,8 @@ class LSTMLowering:
         wi, wh, b = self.views(self.prog.params)
         gwi, gwh, gb = self.views(self.prog.grads)
         RH, d, rows = self.RH, self.in_dim, Tp * M
+        if self.tc:
+            return self._sequence_bwd_tc(feats, seq, dfeats, w, gwi, gwh, gb)
         dz = w['z']                                   # pre-activations are dead: reuse as dz_all
         for t in range(Tp - 1, -1, -1):
             last = t == Tp - 1
@@ -170,3 +235,27 @@ class LSTMLowering:
         call('mlb_colsum_f32', ptr(dz2), c_ll(rows), c_int(4 * RH), c_int(4 * RH), ptr(gb))
         gemm(dz2, wi, dfeats, None, rows, d, 4 * RH, 4 * RH, d, d)
         return dfeats
+
+    def _sequence_bwd_tc(self, feats, seq, dfeats, w, gwi, gwh, gb):
+        """Tensor-core BPTT.  feats bf16 [T'*M, in]; consumes w['d_hseq'] (f32).  dfeats is None: the gradient
+        to the layer below, dz_all W_i, is fused into that layer's LayerNorm-backward kernel by the caller
+        (mlb_dense_dx_lnbwd_tc with DZ_in = w['dz'], W = wi_t)."""
+        from .engine import _splitk_tc, gemm_tc
+        Tp, M = seq['Tp'], seq['M']
+        RH, d, rows = self.RH, self.in_dim, Tp * M
+        dz = w['dz']
+        for t in range(Tp - 1, -1, -1):
+            last = t == Tp - 1
+            dc_in, dc_out = w['dc'][t & 1], w['dc'][(t & 1) ^ 1]
+            call('mlb_lstm_cell_bwd_tc', ptr(w['d_hseq'][t]), c_int(RH), ptr(None if last else w['dh']),
+                 ptr(None if last else dc_in), ptr(seq['ends'][t]), ptr(w['stash'][t]), ptr(w['c_in'][t]),
+                 ptr(dz[t]), ptr(dc_out), c_ll(M), c_int(RH))
+            if t > 0:                                 # dh_prev = dz_t W_h : B = W_h^T stored [K = 4RH, N = RH] (MN-major)
+                gemm_tc(dz[t], self.wh_c, w['dh'], None, M, RH, 4 * RH, 4 * RH, RH, RH, 0, 1, 0)
+        dz2 = dz.view(rows, 4 * RH)
+        # dW_h^T [4RH, RH] += dz^T h_in ; dW_i^T [4RH, in] += dz^T feats  (MN-major x MN-major, split-K atomics)
+        gemm_tc(dz2, w['h_in'].view(-1, RH), gwh, None, 4 * RH, RH, rows, 4 * RH, RH, RH, 1, 1, 2,
+                _splitk_tc(4 * RH, RH, rows))
+        gemm_tc(dz2, feats, gwi, None, 4 * RH, d, rows, 4 * RH, d, d, 1, 1, 2, _splitk_tc(4 * RH, d, rows))
+        call('mlb_colsum_bf16', ptr(dz2), c_ll(rows), c_int(4 * RH), c_int(4 * RH), ptr(gb))
+        return None

@@ -234,6 +234,39 @@ def select_golden(rng, jax, jnp, lax, ma):
     np.savez_compressed(os.path.join(OUT, 'ppo_select.npz'), **out)
 
 
+def hlgauss_golden(rng, jax, jnp):
+    """HLGaussDist / HLGaussCritic.create (ml/models.py:177-306), AST-extracted and executed unmodified:
+    bin centres and bounds, mean() (symmetric summation) and loss() (Gaussian-histogram cross-entropy)."""
+    import types as _t
+    import flax
+    import scipy.special
+    f32 = np.float32
+    jax_ns = _t.SimpleNamespace(**{k: getattr(jax, k) for k in dir(jax) if not k.startswith('__')})
+    jax_ns.scipy = _t.SimpleNamespace(special=_t.SimpleNamespace(
+        erf=lambda x: _arr(scipy.special.erf(np.asarray(x, np.float32)).astype(np.float32))))
+    jax_ns.nn = _t.SimpleNamespace(**{k: getattr(jax.nn, k) for k in dir(jax.nn) if not k.startswith('__')})
+    jax_ns.nn.initializers = _t.SimpleNamespace(constant=lambda v: None)      # only names a default argument
+    nn = _t.SimpleNamespace(Module=object, compact=lambda f: f, Dense=None)
+    ns = dict(jax=jax_ns, jnp=jnp, np=np, flax=flax, nn=nn, Callable=object)
+    Dist = extract_function('models.py', 'HLGaussDist', ns)
+    Critic = extract_function('models.py', 'HLGaussCritic', ns)
+    # the staticmethod only builds the bin tables; capture its arguments instead of constructing the Module
+    caught = {}
+    ns['HLGaussCritic'] = lambda **kw: caught.update(kw)
+    out = {}
+    for name, (nb, lo, hi, sm) in {'default': (127, -100, 100, 0.75), 'small': (31, -10, 10, 0.5)}.items():
+        Critic.create(dtype=jnp.float32, num_bins=nb, min_bound=lo, max_bound=hi, smoothness=sm)
+        centers, bounds = np.asarray(caught['centers'], f32), np.asarray(caught['bounds'], f32)
+        logits = (rng.standard_normal((40, nb)) * 1.5).astype(f32)
+        tgt = (rng.standard_normal((40, 1)) * 0.6 * hi).astype(f32)      # some beyond the outer centres (clipped)
+        tgt[:3, 0] = [centers[0], centers[-1], 0.0]
+        d = Dist(logits=_arr(logits), smoothness=sm, centers=_arr(centers), bounds=_arr(bounds))
+        out[f'{name}_centers'], out[f'{name}_bounds'], out[f'{name}_smoothness'] = centers, bounds, f32(sm)
+        out[f'{name}_logits'], out[f'{name}_targets'] = logits, tgt
+        out[f'{name}_mean'], out[f'{name}_loss'] = np.asarray(d.mean()), np.asarray(d.loss(_arr(tgt)))
+    np.savez_compressed(os.path.join(OUT, 'hlgauss.npz'), **out)
+
+
 def main():
     install()
     import jax
@@ -364,6 +397,7 @@ def main():
     # fixtures above keep their random stream and stay bit-identical) ------------------------
     ppo_update_golden(np.random.default_rng(20261019), jax, jnp, lax, ac, ma, di)
     select_golden(np.random.default_rng(20261020), jax, jnp, lax, ma)
+    hlgauss_golden(np.random.default_rng(20261021), jax, jnp)
     print('golden fixtures written to', OUT)
 
 

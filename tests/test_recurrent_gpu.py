@@ -89,6 +89,115 @@ def test_lstm_forward_backward_vs_oracle(mlb):
     np.testing.assert_allclose(states[1][0].cpu().numpy(), hs[0], rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize('D,H,L,RH,Tp,M', [(32, 128, 2, 64, 6, 300), (64, 256, 2, 256, 8, 2048)])
+def test_lstm_tc_forward_backward_vs_oracle(mlb, D, H, L, RH, Tp, M):
+    """compute_dtype = bfloat16: the LSTM's products run on tcgen05 (bf16 operands, fp32 accumulation and
+    cell state).  Bounds vs the EXACT fp64 oracle: the SURVEY 8c bf16 tolerance (heads rel-L2 <= 2e-2, gradient
+    cosine >= 0.999 / rel-L2 <= 5e-2 -- the recurrence compounds the bf16 rounding of h over T' steps)."""
+    from madrona_learn_b200._lib import c_float, c_int, c_ll, c_size_t, call, ptr
+    from madrona_learn_b200.engine import PolicyProgram
+    m = mlb
+    rows, A = Tp * M, len(BUCKETS)
+    rng = np.random.default_rng(RH)
+    p = onn.init_params(rng, D, H, L, BUCKETS, lstm_hidden=RH, lstm_layers=1)
+    p['actor']['kernel'] = (rng.standard_normal(p['actor']['kernel'].shape) * 0.2).astype(np.float32)
+    p['lstm'][0]['bh'] = (0.1 * rng.standard_normal(4 * RH)).astype(np.float32)
+    prog = PolicyProgram(_policy(m, H, L, RH).actor_critic, D, {'act': m.DiscreteActionsConfig(BUCKETS)}, DEV,
+                         torch.bfloat16)
+    assert prog.tc and prog.lstm.tc
+    prog.load_oracle_params(p)
+    cfg = oppo.PPOCfg(BUCKETS, entropy_coef=0.02)
+    c0 = rng.standard_normal((M, RH)).astype(np.float32)
+    h0 = rng.standard_normal((M, RH)).astype(np.float32) * 0.5
+    mb = dict(obs=rng.standard_normal((Tp, M, D)).astype(np.float32),
+              actions=np.stack([rng.integers(0, b, (Tp, M)) for b in BUCKETS], -1).astype(np.int32),
+              advantages=rng.standard_normal((Tp, M, 1)).astype(np.float32),
+              returns=rng.standard_normal((Tp, M, 1)).astype(np.float32),
+              values=rng.standard_normal((Tp, M, 1)).astype(np.float32),
+              dones=(rng.random((Tp, M, 1)) < 0.2), mb_weights=np.ones((M, 1), np.float32),
+              rnn_start_states=([c0], [h0]))
+    p64 = onn.cast_tree(p, np.float64)
+    mb['log_probs'] = np.zeros((Tp, M, A), np.float32)
+    ref0 = oppo.ppo_loss(p, mb, cfg, None, dtype=np.float64)
+    lp0, _ = onn.action_stats(ref0['logits'], mb['actions'].reshape(rows, A), BUCKETS)
+    mb['log_probs'] = lp0.reshape(Tp, M, A).astype(np.float32)      # old policy = current policy (first minibatch)
+    ref = oppo.ppo_loss(p, mb, cfg, None, dtype=np.float64)
+    dv = {k: torch.from_numpy(np.ascontiguousarray(v)).to(DEV) for k, v in mb.items() if k != 'rnn_start_states'}
+    seq = dict(Tp=Tp, M=M, ends=dv['dones'].view(torch.uint8).view(Tp, M), c0=torch.from_numpy(c0).to(DEV),
+               h0=torch.from_numpy(h0).to(DEV))
+    obs_d = dv['obs'].view(rows, D)
+    head = prog.forward_train(obs_d, rows, seq)
+    h = head.cpu().numpy()
+    assert _rel(h[:, :26], ref['logits']) < 2e-2 and _rel(h[:, 26:27], ref['critic']) < 2e-2
+    tw = prog.train_ws(rows)
+    mean, rstd = oac.zscore_stats(mb['advantages'])
+    adv_mr = torch.tensor([mean, rstd, 0, 0], dtype=torch.float32, device=DEV)
+    obj_scale = (ctypes.c_float * A)(*[1.0 / (rows * A)] * A)
+    ent_scale = (ctypes.c_float * A)(*[cfg.entropy_coef / (rows * A)] * A)
+    prog.zero_grads()
+    call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(dv['actions']), ptr(dv['log_probs']),
+         ptr(dv['advantages']), ptr(dv['returns']), ptr(None), ptr(None), ptr(adv_mr), ptr(None),
+         prog._buckets_c, obj_scale, ent_scale, c_int(A), c_ll(rows), c_ll(M), c_float(cfg.clip_coef),
+         c_float(cfg.value_loss_coef), c_int(prog.loss_flags), ptr(tw['dhead']), ptr(prog.head_bias_grad()),
+         ptr(tw['stats_out']), ptr(tw['loss_ws']), c_size_t(tw['loss_ws'].numel()), None, c_int(0))
+    prog.backward(obs_d, rows, seq)
+    g = prog.to_oracle_params(prog.grads)
+    flat = lambda t: np.concatenate([np.asarray(x, np.float64).reshape(-1) for k in ('mlp', 'lstm', 'actor', 'critic')
+                                     for x in onn.tree_leaves(t[k])])
+    a, b = flat(g), flat(ref['grads'])
+    cos = a @ b / (np.linalg.norm(a) * np.linalg.norm(b))
+    rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+    print('PARITY lstm_tc', dict(RH=RH, rows=rows, grad_cos=float(cos), grad_rel=float(rel),
+                                 logits_rel=float(_rel(h[:, :26], ref['logits']))))
+    assert cos >= 0.999 and rel <= 5e-2, (cos, rel)
+    for name in ('wi', 'wh', 'bh'):
+        assert _rel(g['lstm'][0][name], ref['grads']['lstm'][0][name]) < 6e-2, name
+    # rollout-mode single step == first step of the sequence
+    states = ([torch.from_numpy(c0).to(DEV).clone()], [torch.from_numpy(h0).to(DEV).clone()])
+    h1 = prog.forward_infer(dv['obs'][0].contiguous(), M, states).cpu().numpy()
+    np.testing.assert_allclose(h1[:, :27], h[:M, :27], rtol=2e-2, atol=2e-3)
+    cs, hs, out, _ = onn.lstm_step([c0.astype(np.float64)], [h0.astype(np.float64)],
+                                   onn.mlp_fwd(mb['obs'][0].astype(np.float64), p64['mlp'])[0], p64['lstm'])
+    assert _rel(states[0][0].cpu().numpy(), cs[0]) < 1e-2 and _rel(states[1][0].cpu().numpy(), hs[0]) < 1e-2
+    # the optimiser refreshes the LSTM's bf16 operand copies
+    prog.optimizer_step(3e-4, 0.5)
+    wi, wh, _ = prog.lstm.views(prog.params)
+    assert torch.equal(prog.lstm.wi_c, wi.to(torch.bfloat16)) and torch.equal(prog.lstm.wi_t, wi.t().contiguous().to(torch.bfloat16))
+    assert torch.equal(prog.lstm.wh_c, wh.to(torch.bfloat16))
+
+
+def test_recurrent_tc_update_iter_tracks_fp32(mlb, monkeypatch):
+    """config-4 family through the public API on the tensor-core path: graph capture + replay, parameters
+    track the fp32 run of the same seeds to bf16 precision."""
+    m = mlb
+    N, T, C, M, E, D, H, L, RH = 512, 16, 2, 256, 2, 32, 128, 2, 64
+    out = {}
+    for dt in (torch.float32, torch.bfloat16):
+        env = m.SyntheticVectorEnv(N, D, len(BUCKETS), seed=11, p_done=0.1, device=DEV)
+        cfg = m.TrainConfig(
+            num_worlds=N, num_agents_per_world=1, num_updates=10, actions={'act': m.DiscreteActionsConfig(BUCKETS)},
+            steps_per_update=T, lr=3e-4,
+            algo=m.PPOConfig(num_epochs=E, minibatch_size=M, clip_coef=0.2, value_loss_coef=0.5,
+                             entropy_coef={'act': 0.01}, max_grad_norm=0.5),
+            num_bptt_chunks=C, gamma=0.99, seed=5, metrics_buffer_size=4, gae_lambda=0.95,
+            dreamer_v3_critic=False, normalize_values=True, compute_dtype=dt)
+        mgr = m.init_training(DEV, cfg, env.sim_fns(), _policy(m, H, L, RH), None, verbose=False)
+        prog = mgr.state.policy_states.program
+        flat = lambda: np.concatenate([np.asarray(x, np.float64).reshape(-1) for k in ('mlp', 'lstm', 'actor', 'critic')
+                                       for x in onn.tree_leaves(prog.to_oracle_params()[k])])
+        p0 = flat()                          # (the arenas differ: the tensor-core path pads the head to 64 columns)
+        for _ in range(3):
+            mgr.update_iter()
+        torch.cuda.synchronize()
+        out[dt] = flat() - p0, mgr.metrics.latest()
+        assert np.isfinite(out[dt][1]['Loss'].mean)
+    d32, dbf = out[torch.float32][0], out[torch.bfloat16][0]
+    cos = float(d32 @ dbf / (np.linalg.norm(d32) * np.linalg.norm(dbf)))
+    print('PARITY lstm_tc_update', dict(delta_cos=cos))
+    assert cos > 0.9, cos
+    assert abs(out[torch.bfloat16][1]['Entropy'].mean - out[torch.float32][1]['Entropy'].mean) < 0.05
+
+
 def test_recurrent_update_iter_matches_oracle(mlb, monkeypatch):
     """config-4 family end to end: 3 BPTT chunks, LSTM, normalize_values=True."""
     monkeypatch.setenv('MLB_CUDA_GRAPH', '0')

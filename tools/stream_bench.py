@@ -41,7 +41,10 @@ def timeit(fn, n=10):
 
 def main():
     H = 512
-    for M, K in ((65536, 512), (262144, 512), (65536, 64)):
+    shapes = ((65536, 512), (262144, 512), (65536, 64))
+    if len(sys.argv) > 2:
+        shapes = ((int(sys.argv[1]), int(sys.argv[2])),)
+    for M, K in shapes:
         x = torch.randn(M, K, device=dev).to(BF)
         wt = (torch.randn(H, K, device=dev) / K ** 0.5).to(BF)
         s = torch.ones(H, device=dev)
