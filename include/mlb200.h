@@ -390,6 +390,8 @@ int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* desc_host, const 
 #define MLB_PPO_CLIP_VALUE_LOSS  1
 #define MLB_PPO_HUBER_VALUE_LOSS 2
 #define MLB_PPO_DHEAD_BF16       4
+/* HL-Gauss critic (ml/models.py:177-306): critic_bins_host = centres[V] | bounds[V+1] | smoothness */
+#define MLB_PPO_HLGAUSS_CRITIC   8
 typedef struct mlb_ppo_stats {
     float loss, action_obj, value_loss, entropy;
     mlb_metric metrics[5];   /* Loss, Action Obj, Value Loss, Value Errors (abs), Entropy

@@ -30,9 +30,14 @@ struct Layout {
 
 // Distributional critic (DreamerV3Critic, ml/models.py:157-174 -> SymExpTwoHotDistribution,
 // ml/dists.py:119-208): V logits over fixed symexp-spaced bins.  V == 1 is the plain critic.
+// kind 1: HL-Gauss critic (HLGaussCritic / HLGaussDist, ml/models.py:177-306): V logits over linearly spaced
+// bin centres (`bins`), V + 1 bin bounds and the smoothness of the Gaussian histogram target.
 struct CriticBins {
     int V;
+    int kind;
+    float smooth;
     float bins[MLB_MAX_CRITIC_BINS];
+    float bounds[MLB_MAX_CRITIC_BINS + 1];
 };
 
 // SymExpTwoHotDistribution.mean (ml/dists.py:143-170): softmax-weighted bins, summed symmetrically
@@ -372,6 +377,38 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
             p1 = (w * o.H) * es;
             x0 = o.obj;
             x1 = o.H;
+        } else if (cb.V > 1 && cb.kind == 1) {
+            // HL-Gauss critic (ml/ppo.py:178-185, HLGaussDist.loss ml/models.py:212-250): cross-entropy against
+            // the histogram of a Gaussian centred on the (clipped) return, sigma = smoothness * bin width
+            const int V = cb.V;
+            float* lc = l + vcol;
+            const float rr = ret[row];
+            const float vmean = twohot_mean(lc, cb);
+            const float t = fminf(fmaxf(rr, cb.bins[0]), cb.bins[V - 1]);
+            int nle = 0;
+            for (int k = 0; k <= V; ++k) nle += (cb.bounds[k] <= t);
+            const int lo = min(max(nle - 1, 0), V - 1), hi = min(max(nle, 1), V);
+            const float den = 1.41421356237f * (cb.smooth * (cb.bounds[hi] - cb.bounds[lo]));
+            const float cdf0 = erff((cb.bounds[0] - t) / den);
+            const float zinv = 1.f / (erff((cb.bounds[V] - t) / den) - cdf0);
+            float mxc = -INFINITY;
+            for (int k = 0; k < V; ++k) mxc = fmaxf(mxc, lc[k]);
+            float sec = 0.f;
+            for (int k = 0; k < V; ++k) sec += expf(lc[k] - mxc);
+            const float lsec = logf(sec) + mxc;
+            const float gsc = vcoef * w * inv_rows;
+            float vl = 0.f, prev = cdf0;
+            for (int k = 0; k < V; ++k) {
+                const float cur = erff((cb.bounds[k + 1] - t) / den);
+                const float ck = zinv * (cur - prev);
+                prev = cur;
+                const float lp = lc[k] - lsec;
+                vl -= ck * lp;
+                lc[k] = gsc * (expf(lp) - ck);                          // d CE / d logit = softmax - target
+            }
+            p0 = (w * vl) * inv_rows;
+            x0 = vl;
+            x1 = fabsf(vmean - rr);
         } else if (cb.V > 1) {
             // distributional critic: two-hot cross-entropy (ml/ppo.py:169-177, ml/dists.py:172-208)
             const int V = cb.V;
@@ -489,11 +526,20 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
     }
 }
 
-int make_bins(CriticBins& cb, const float* bins_host, int num_bins) {
-    if (num_bins <= 1 || !bins_host) { cb.V = 1; return MLB_OK; }
+// hlgauss: bins_host holds  centres[V] | bounds[V + 1] | smoothness
+int make_bins(CriticBins& cb, const float* bins_host, int num_bins, bool hlgauss = false) {
+    cb.kind = 0;
+    cb.smooth = 0.f;
+    if (num_bins <= 1 || !bins_host) { cb.V = 1; return hlgauss ? MLB_EINVAL : MLB_OK; }
     if (num_bins > MLB_MAX_CRITIC_BINS || num_bins % 2 == 0) return MLB_EINVAL;
     cb.V = num_bins;
     for (int k = 0; k < num_bins; ++k) cb.bins[k] = bins_host[k];
+    if (hlgauss) {
+        cb.kind = 1;
+        for (int k = 0; k <= num_bins; ++k) cb.bounds[k] = bins_host[num_bins + k];
+        cb.smooth = bins_host[2 * num_bins + 1];
+        if (!(cb.smooth > 0.f)) return MLB_EINVAL;
+    }
     return MLB_OK;
 }
 
@@ -562,7 +608,7 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     MLB_REQUIRE(!(flags & MLB_PPO_CLIP_VALUE_LOSS) || old_values);
     Layout L;
     CriticBins cb;
-    if (make_bins(cb, critic_bins_host, num_critic_bins)) return MLB_EINVAL;
+    if (make_bins(cb, critic_bins_host, num_critic_bins, (flags & MLB_PPO_HLGAUSS_CRITIC) != 0)) return MLB_EINVAL;
     MLB_REQUIRE(cb.V == 1 || !(vn_params || (flags & (MLB_PPO_CLIP_VALUE_LOSS | MLB_PPO_HUBER_VALUE_LOSS))));
     const int vcol = make_layout(L, buckets_host, num_components, obj_scale_host, ent_scale_host, ld, cb.V);
     if (vcol < 0) return vcol;

@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import c_float, c_int, c_ll, c_size_t, call, ptr
 from .actor_critic import ActorCritic, BackboneEncoder, BackboneShared, RecurrentBackboneEncoder
 from .cfg import DiscreteActionsConfig
-from .models import MLP, DenseLayerCritic, DenseLayerDiscreteActor, DreamerV3Critic
+from .models import MLP, DenseLayerCritic, DenseLayerDiscreteActor, DreamerV3Critic, HLGaussCritic
 
 F32 = torch.float32
 
@@ -73,8 +73,8 @@ class PolicyProgram:
         self._rnn_desc = enc.rnn if isinstance(enc, RecurrentBackboneEncoder) else None
         if not isinstance(actor_critic.actor, DenseLayerDiscreteActor):
             raise NotImplementedError('actor must be DenseLayerDiscreteActor')
-        if not isinstance(actor_critic.critic, (DenseLayerCritic, DreamerV3Critic)):
-            raise NotImplementedError('critic must be DenseLayerCritic or DreamerV3Critic (HL-Gauss: next)')
+        if not isinstance(actor_critic.critic, (DenseLayerCritic, DreamerV3Critic, HLGaussCritic)):
+            raise NotImplementedError('critic must be DenseLayerCritic, DreamerV3Critic or HLGaussCritic')
         self.ac = actor_critic
         self.device = torch.device(device)
         self.mlp = enc.net
@@ -100,8 +100,17 @@ class PolicyProgram:
         self.sumA = int(sum(buckets))
         # critic columns: 1 (plain) or num_bins two-hot logits (DreamerV3Critic, ml/models.py:157-174)
         self.twohot = isinstance(actor_critic.critic, DreamerV3Critic)
-        self.V = int(actor_critic.critic.num_bins) if self.twohot else 1
-        if self.twohot:
+        self.hlgauss = isinstance(actor_critic.critic, HLGaussCritic)
+        self.V = int(actor_critic.critic.num_bins) if (self.twohot or self.hlgauss) else 1
+        if self.hlgauss:
+            # HLGaussCritic (ml/models.py:253-306): centres | bounds | smoothness, the table mlb_ppo_loss_f32 reads
+            # under MLB_PPO_HLGAUSS_CRITIC; the value decode (rollout) only uses the V centres in front
+            cr = actor_critic.critic
+            if cr.centers is None or self.V % 2 == 0 or self.V > 127:
+                raise NotImplementedError('HLGaussCritic: build with HLGaussCritic.create, odd num_bins <= 127')
+            tab = np.concatenate([cr.centers, cr.bounds, [cr.smoothness]]).astype(np.float32)
+            self._bins_c = (ctypes.c_float * tab.size)(*tab.tolist())
+        elif self.twohot:
             # SymExpTwoHotDistribution._compute_bins (ml/dists.py:127-141), float32 like the reference
             half = np.linspace(-14, 0, self.V // 2 + 1, dtype=np.float32)
             half = (np.sign(half) * np.expm1(np.abs(half))).astype(np.float32)
@@ -213,7 +222,7 @@ class PolicyProgram:
             self.lstm.init_host(host, orth)
         W = torch.zeros(self.feat, self.NH, dtype=F32)
         W[:, :self.sumA] = orth(self.feat, self.sumA, self.ac.actor.weight_init_scale)
-        if not self.twohot:      # DreamerV3Critic is zero-initialised (ml/models.py:159)
+        if not (self.twohot or self.hlgauss):      # DreamerV3Critic / HLGaussCritic are zero-initialised (ml/models.py:159,261)
             W[:, self.sumA:self.sumA + 1] = orth(self.feat, 1, self.ac.critic.weight_init_scale)
         host[self.head_w_off:self.head_w_off + W.numel()] = W.reshape(-1)
         self.params.copy_(host)
@@ -580,7 +589,7 @@ class PolicyProgram:
     @property
     def loss_flags(self):
         """Extra mlb_ppo_loss_f32 flags for this program (bf16 d_head on the tensor-core path)."""
-        return 4 if self.tc else 0
+        return (4 if self.tc else 0) | (8 if self.hlgauss else 0)
 
     def head_bias_grad(self):
         return self.head_views(self.grads)[1]

@@ -50,3 +50,29 @@ class DenseLayerCritic:                  # ml/models.py:142-154
 class DreamerV3Critic:                   # ml/models.py:157-174 (SURVEY 8f rank 3 -- "next")
     dtype: Any = torch.float32
     num_bins: int = 63
+
+
+@dataclass(frozen=True)
+class HLGaussCritic:                     # ml/models.py:253-306
+    """Dense(num_bins, bias, zero init) -> HLGaussDist: logits over linearly spaced bin centres; value =
+    softmax-weighted centres (symmetric summation), loss = cross-entropy against the histogram of a
+    Gaussian around the return (sigma = smoothness * bin width).  Build with `create`, like the reference."""
+    dtype: Any = torch.float32
+    centers: Any = None
+    bounds: Any = None
+    smoothness: float = 0.75
+
+    @staticmethod
+    def create(dtype=torch.float32, num_bins: int = 127, min_bound=-100, max_bound=100, smoothness: float = 0.75):
+        import numpy as np
+        half = np.linspace(min_bound, 0, num_bins // 2 + 1)           # gen_bins (ml/models.py:271-283)
+        bins = np.concatenate([half, -half[:-1][::-1]], axis=0)
+        width = bins[1] - bins[0]
+        bounds = bins - 0.5 * width
+        bounds = np.concatenate([bounds, np.asarray([bounds[-1] + width])], axis=0)
+        return HLGaussCritic(dtype=dtype, centers=bins.astype(np.float32), bounds=bounds.astype(np.float32),
+                             smoothness=float(smoothness))
+
+    @property
+    def num_bins(self):
+        return int(self.centers.shape[0])

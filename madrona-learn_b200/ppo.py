@@ -175,9 +175,10 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
          ws=None, partitionable=False):
     """ml/ppo.py:366-488, default branch (valid_inds = arange(J), weights = 1)."""
     prog = policy_state.program
-    if bool(cfg.dreamer_v3_critic) != bool(prog.twohot) or cfg.hlgauss_critic:
-        raise ValueError('cfg.dreamer_v3_critic must match the critic module (DreamerV3Critic <-> True, '
-                         'DenseLayerCritic <-> False); hlgauss_critic is a "next" row')
+    if bool(cfg.dreamer_v3_critic) != bool(prog.twohot) or bool(cfg.hlgauss_critic) != bool(prog.hlgauss):
+        raise ValueError('cfg.dreamer_v3_critic / cfg.hlgauss_critic must match the critic module '
+                         '(DreamerV3Critic <-> dreamer_v3_critic, HLGaussCritic <-> hlgauss_critic, '
+                         'DenseLayerCritic <-> neither)')
     st = rollout_data.store
     C, Tp, B = rollout_data.C, rollout_data.Tp, rollout_data.B
     if ws is None:

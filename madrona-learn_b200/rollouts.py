@@ -147,11 +147,9 @@ class RolloutData:                      # ml/rollouts.py:311-334
 class RolloutManager:                   # ml/rollouts.py:373-826
     def __init__(self, train_cfg, init_rollout_state, example_policy_states, dist_ctx=None):
         self._cfg = init_rollout_state.cfg
-        if train_cfg.hlgauss_critic:
-            raise NotImplementedError('hlgauss_critic is a "next" row (SURVEY 8f rank 3)')
-        # distributional critics store their mean as the value estimate (ml/rollouts.py:601-605);
-        # the sampling kernel emits the two-hot mean directly
-        self._critic_outputs_distribution = train_cfg.dreamer_v3_critic
+        # distributional critics store their mean as the value estimate (ml/rollouts.py:384, 601-605);
+        # the sampling kernel emits the two-hot / HL-Gauss mean directly
+        self._critic_outputs_distribution = train_cfg.dreamer_v3_critic or train_cfg.hlgauss_critic
         self._num_bptt_chunks = train_cfg.num_bptt_chunks
         assert train_cfg.steps_per_update % train_cfg.num_bptt_chunks == 0
         self._num_bptt_steps = train_cfg.steps_per_update // train_cfg.num_bptt_chunks

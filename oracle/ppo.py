@@ -19,7 +19,8 @@ class PPOCfg:
                  clip_value_loss=False, huber_value_loss=False, normalize_advantages=True,
                  normalize_values=False, value_normalizer_decay=0.99999, gamma=0.99,
                  gae_lambda=0.95, partitionable=False, dreamer_v3_critic=False, compute_advantages=True,
-                 normalize_returns=True):
+                 normalize_returns=True, hlgauss=None):
+        """hlgauss: (centers, bounds, smoothness) of an HLGaussCritic (cfg.hlgauss_critic), else None."""
         self.__dict__.update(locals())
         del self.__dict__['self']
 
@@ -85,25 +86,33 @@ def ppo_loss_heads(logits, critic, mb, cfg, vn_state=None, dtype=np.float64, wan
     obj = np.minimum(surr1, surr2)                                        # :162
 
     returns = mb['returns'].reshape(rows, 1).astype(np.float32)
-    if cfg.dreamer_v3_critic:
-        # two-hot cross-entropy on the critic's bin logits (:169-177, ml/dists.py:172-208)
+    if cfg.dreamer_v3_critic or getattr(cfg, 'hlgauss', None) is not None:
         from . import dists
         clog = critic.reshape(rows, -1)
         V = clog.shape[1]
-        b = dists.bins(V)
-        lo = np.clip((b <= returns).astype(np.int32).sum(-1) - 1, 0, V - 1)
-        hi = np.clip(V - (b > returns).astype(np.int32).sum(-1), 0, V - 1)
-        same = lo == hi
-        dl = np.where(same, 1, np.abs(b[lo] - returns[:, 0]))
-        du = np.where(same, 1, np.abs(b[hi] - returns[:, 0]))
-        wl, wu = dl / (dl + du), du / (dl + du)
-        two_hot = np.zeros((rows, V), f)
-        np.add.at(two_hot, (np.arange(rows), lo), wl)
-        np.add.at(two_hot, (np.arange(rows), hi), wu)
+        if cfg.dreamer_v3_critic:
+            # two-hot cross-entropy on the critic's bin logits (:169-177, ml/dists.py:172-208)
+            b = dists.bins(V)
+            lo = np.clip((b <= returns).astype(np.int32).sum(-1) - 1, 0, V - 1)
+            hi = np.clip(V - (b > returns).astype(np.int32).sum(-1), 0, V - 1)
+            same = lo == hi
+            dl = np.where(same, 1, np.abs(b[lo] - returns[:, 0]))
+            du = np.where(same, 1, np.abs(b[hi] - returns[:, 0]))
+            wl, wu = dl / (dl + du), du / (dl + du)
+            two_hot = np.zeros((rows, V), f)
+            np.add.at(two_hot, (np.arange(rows), lo), wl)
+            np.add.at(two_hot, (np.arange(rows), hi), wu)
+            vmean = dists.twohot_mean(clog.astype(np.float32))
+        else:
+            # HL-Gauss: cross-entropy against the Gaussian histogram (:178-185, ml/models.py:212-250);
+            # `two_hot` is the target distribution c (it sums to 1, so d loss / d logits = softmax - c)
+            centers, bounds, smooth = cfg.hlgauss
+            two_hot = dists.hlgauss_target(returns, centers, bounds, smooth, dtype=f)
+            vmean = dists.hlgauss_mean(clog.astype(np.float32), centers)
         m_ = clog.max(-1, keepdims=True)
         logp = clog - (np.log(np.exp(clog - m_).sum(-1, keepdims=True)) + m_)
         vloss = -(two_hot * logp).sum(-1, keepdims=True)
-        value_errs = dists.twohot_mean(clog.astype(np.float32)).astype(f) - returns.astype(f)
+        value_errs = vmean.astype(f) - returns.astype(f)
         action_obj_avg = np.mean(w * obj)
         value_loss = cfg.value_loss_coef * np.mean(w * vloss)
         entropy_avg = cfg.entropy_coef * np.mean(w * ent)

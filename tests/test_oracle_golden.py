@@ -240,3 +240,19 @@ def test_minibatch_selection_matches_reference(name):
     np.testing.assert_array_equal(np.stack(tags), g('mb_tags'))          # bit-exact composition
     np.testing.assert_allclose(np.stack(ws), g('mb_weights'), rtol=1e-5)
     np.testing.assert_array_equal(key, g('key1'))
+
+
+def test_hlgauss_oracle_matches_reference_golden():
+    """oracle/dists.py HL-Gauss restatement vs HLGaussDist / HLGaussCritic.create executed from the reference
+    source (tests/golden/hlgauss.npz, ml/models.py:177-306)."""
+    from oracle import dists
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'hlgauss.npz'))
+    for name, nb, lo, hi in (('default', 127, -100, 100), ('small', 31, -10, 10)):
+        c, b = dists.hlgauss_bins(nb, lo, hi)
+        np.testing.assert_array_equal(c, d[name + '_centers'])
+        np.testing.assert_array_equal(b, d[name + '_bounds'])
+        np.testing.assert_allclose(dists.hlgauss_mean(d[name + '_logits'], c), d[name + '_mean'], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(dists.hlgauss_loss(d[name + '_logits'], d[name + '_targets'], c, b,
+                                                      float(d[name + '_smoothness'])), d[name + '_loss'], rtol=2e-6)
+        t = dists.hlgauss_target(d[name + '_targets'], c, b, float(d[name + '_smoothness']))
+        np.testing.assert_allclose(t.sum(-1), 1.0, rtol=1e-5)
