@@ -322,6 +322,17 @@ int mlb_lstm_cell_fwd_tc(void* stream, const float* z, const float* bias, const 
 int mlb_lstm_cell_bwd_tc(void* stream, const float* dh_seq, int ld_dh, const float* dh_carry,
                          const float* dc_carry, const uint8_t* ends, const float* stash,
                          const float* c_prev, void* dz_bf16, float* dc_prev, long long M, int H);
+/* Fused step: z = [x_t | h_{t-1}] [W_i | W_h]^T on tcgen05 with the cell math in the epilogue, */
+/* gate pre-activations never written to memory.  w_packed bf16 [4H, in + H], bias_packed f32 [4H]: rows     */
+/* permuted to  nb*256 + gate*64 + j  <->  (gate, hidden unit nb*64 + j)  by mlb_lstm_pack_weights_bf16 from  */
+/* the arena's W_i^T [4H, in], W_h^T [4H, H], b [4H] (after every optimiser step).  x bf16 [M, in] (ldx),    */
+/* h_prev bf16 [M, H]; outputs as mlb_lstm_cell_fwd_tc.  in, H multiples of 64.                               */
+int mlb_lstm_pack_weights_bf16(void* stream, const float* wi_t, const float* wh_t, const float* bias,
+                               void* w_packed, float* bias_packed, int in_dim, int H);
+int mlb_lstm_step_tc(void* stream, const void* x, int ldx, const void* h_prev, const void* w_packed,
+                     const float* bias_packed, const float* c_prev, const uint8_t* ends, void* h_seq_bf16,
+                     float* c_carry, float* h_carry, void* h_carry_bf16, float* stash, long long M,
+                     int in_dim, int H);
 /* clear_recurrent_state (ml/rnn.py:66-81): state[m, :] = 0 where dones[m] */
 int mlb_rnn_reset_f32(void* stream, float* state, const uint8_t* dones, long long M, int H);
 

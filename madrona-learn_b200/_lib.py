@@ -90,6 +90,8 @@ SIGNATURES = {
     'mlb_lstm_cell_bwd_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, c_ll, c_int]),
     'mlb_lstm_cell_fwd_tc': (c_int, [P, P, P, P, P, P, P, P, P, P, c_ll, c_int]),
     'mlb_lstm_cell_bwd_tc': (c_int, [P, P, c_int, P, P, P, P, P, P, P, c_ll, c_int]),
+    'mlb_lstm_pack_weights_bf16': (c_int, [P, P, P, P, P, P, c_int, c_int]),
+    'mlb_lstm_step_tc': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_ll, c_int, c_int]),
     'mlb_rnn_reset_f32': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),

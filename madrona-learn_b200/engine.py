@@ -620,6 +620,8 @@ class PolicyProgram:
                  ptr(self._opt_sync), ptr(self._opt_ws), c_size_t(self._opt_ws.numel()),
                  ptr(self.grads if self._opt_zero else None))
             self._grads_clean = self._opt_zero    # the kernel cleared the arena behind itself
+            if self.lstm is not None:
+                self.lstm.pack()
             return
         if reduced is None:
             call('mlb_sumsq_f32', ptr(grads), c_ll(self.num_params), ptr(self.grad_sumsq),
@@ -629,6 +631,8 @@ class PolicyProgram:
              c_float(b1), c_float(b2), c_float(eps), c_float(max_grad_norm), c_float(grad_scale))
         call('mlb_renorm_segments', ptr(self.params), ptr(self.segments), c_int(self.num_segments),
              ptr(self.adam_step), ptr(self.copies))
+        if self.lstm is not None:
+            self.lstm.pack()
 
     # ---------------------------------------------------------------------------------
     # flax-style apply(method=...) entry points (ml/actor_critic.py:65-128); these allocate

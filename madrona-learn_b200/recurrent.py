@@ -57,6 +57,13 @@ class LSTMLowering:
             self.wi_t = torch.zeros(d, 4 * RH, dtype=BF, device=dev)       # dx = dz W_i : B [N = in, K = 4RH]
             self.wh_c = torch.zeros(4 * RH, RH, dtype=BF, device=dev)      # z += h W_h^T ; dh = dz W_h (MN-major B)
             self.wh_t = torch.zeros(RH, 4 * RH, dtype=BF, device=dev)      # (the optimiser writes both orientations)
+            # fused step kernel (mlb_lstm_step_tc): [W_i | W_h] with the rows permuted so that one 256-column
+            # accumulator unit holds the four gates of 64 hidden units; re-packed after every optimiser step
+            import os
+            self.fused = d % 64 == 0 and os.environ.get('MLB_LSTM_FUSED', '1') != '0'
+            if self.fused:
+                self.w_packed = torch.zeros(4 * RH, d + RH, dtype=BF, device=dev)
+                self.b_packed = torch.zeros(4 * RH, dtype=F32, device=dev)
 
     # ---- parameter views ---------------------------------------------------------------
     def views(self, arena):
@@ -114,6 +121,14 @@ class LSTMLowering:
              c_int(4 * RH), c_int(d))
         call('mlb_cast_weight_bf16', ptr(wh), ptr(self.wh_t), ptr(self.wh_c), c_int(4 * RH), c_int(RH), c_int(RH),
              c_int(4 * RH), c_int(RH))
+        self.pack()
+
+    def pack(self):
+        """Refresh the fused step kernel's packed operand from the fp32 master weights."""
+        if self.tc and self.fused:
+            wi, wh, b = self.views(self.prog.params)
+            call('mlb_lstm_pack_weights_bf16', ptr(wi), ptr(wh), ptr(b), ptr(self.w_packed), ptr(self.b_packed),
+                 c_int(self.in_dim), c_int(self.RH))
 
     def bf16_copies(self):
         """One mlb_bf16_copy per segment of segments(), same order: gate block g of W_i is the [RH, in]
@@ -142,6 +157,10 @@ class LSTMLowering:
         if self.tc:                    # x, out: bf16; states stay fp32 (h is cast for the recurrent GEMM)
             hb = self._h_bf(rows)
             call('mlb_cast_f32_bf16', ptr(h), ptr(hb), c_ll(rows * RH))
+            if self.fused:             # one launch: [x | h] GEMM with the cell math in the epilogue
+                call('mlb_lstm_step_tc', ptr(x), c_int(d), ptr(hb), ptr(self.w_packed), ptr(self.b_packed), ptr(c),
+                     ptr(None), ptr(out), ptr(c), ptr(h), ptr(None), ptr(None), c_ll(rows), c_int(d), c_int(RH))
+                return out
             gemm_tc(x, self.wi_c, z_buf, b, rows, 4 * RH, d, d, d, 4 * RH, 0, 0, 0)
             gemm_tc(hb, self.wh_c, z_buf, None, rows, 4 * RH, RH, RH, RH, 4 * RH, 0, 0, 2)
             call('mlb_lstm_cell_fwd_tc', ptr(z_buf), ptr(None), ptr(c), ptr(None), ptr(out), ptr(c), ptr(h),
@@ -170,7 +189,7 @@ class LSTMLowering:
             dev, RH = self.prog.device, self.RH
             e = lambda *s: torch.empty(*s, dtype=F32, device=dev)
             HT = torch.bfloat16 if self.tc else F32      # h / encoder output: GEMM operands on the tc path
-            w = dict(Tp=Tp, M=M, z=e(Tp, M, 4 * RH), c_in=e(Tp + 1, M, RH),
+            w = dict(Tp=Tp, M=M, z=None if (self.tc and self.fused) else e(Tp, M, 4 * RH), c_in=e(Tp + 1, M, RH),
                      h_in=torch.empty(Tp + 1, M, RH, dtype=HT, device=dev),
                      h_seq=torch.empty(Tp, M, RH, dtype=HT, device=dev), stash=e(Tp, M, 5 * RH),
                      d_hseq=e(Tp, M, RH), dh=e(M, RH), dc=[e(M, RH), e(M, RH)])
@@ -187,6 +206,15 @@ class LSTMLowering:
         w = self.train_ws(Tp, M)
         wi, wh, b = self.views(self.prog.params)
         RH, d, rows = self.RH, self.in_dim, Tp * M
+        if self.tc and self.fused:
+            call('mlb_copy_bytes', ptr(seq['c0']), ptr(w['c_in'][0]), _lib.c_size_t(M * RH * 4))
+            call('mlb_cast_f32_bf16', ptr(seq['h0']), ptr(w['h_in'][0]), c_ll(M * RH))
+            f3 = feats.view(Tp, M, d)
+            for t in range(Tp):
+                call('mlb_lstm_step_tc', ptr(f3[t]), c_int(d), ptr(w['h_in'][t]), ptr(self.w_packed), ptr(self.b_packed),
+                     ptr(w['c_in'][t]), ptr(seq['ends'][t]), ptr(w['h_seq'][t]), ptr(w['c_in'][t + 1]), ptr(None),
+                     ptr(w['h_in'][t + 1]), ptr(w['stash'][t]), c_ll(M), c_int(d), c_int(RH))
+            return w['h_seq'].view(rows, RH)
         if self.tc:
             gemm_tc(feats, self.wi_c, w['z'], b, rows, 4 * RH, d, d, d, 4 * RH, 0, 0, 0)     # + bias in the epilogue
             call('mlb_copy_bytes', ptr(seq['c0']), ptr(w['c_in'][0]), _lib.c_size_t(M * RH * 4))

@@ -1,5 +1,5 @@
 """Per-kernel device-time breakdown of one update_iter (eager, CUPTI through torch.profiler):
-python tools/profile_update.py cfg2|cfg3 [updates].  Prints the kernels sorted by total device time."""
+python tools/profile_update.py cfg2|cfg3|cfg4 [updates].  Prints the kernels sorted by total device time."""
 import json
 import os
 import sys
@@ -18,10 +18,27 @@ def main():
     n_upd = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     wl = bench.CFG3 if name == 'cfg3' else bench.WORKLOAD
     dev = torch.device('cuda', 0)
-    N = wl['worlds']
-    env = m.SyntheticVectorEnv(N, bench.WORKLOAD['obs_dim'], len(bench.BUCKETS), seed=0, device=dev)
-    mgr = m.init_training(dev, bench.make_cfg(m, N, dtype='bf16', wl=wl), env.sim_fns(), bench.make_policy(m, wl), None,
-                          verbose=False)
+    if name == 'cfg4':          # recurrent actor-critic: LSTM 256, 16384 worlds x 128 steps, 4 BPTT chunks, value-norm EMA
+        N, T, C, H, L, RH = 16384, 128, 4, 256, 2, 256
+        policy = m.Policy(actor_critic=m.ActorCritic(
+            backbone=m.BackboneShared(prefix=None, encoder=m.RecurrentBackboneEncoder(
+                net=m.models.MLP(H, L), rnn=m.rnn.LSTM(RH, 1))),
+            actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(bench.BUCKETS)),
+            critic=m.models.DenseLayerCritic()))
+        env = m.SyntheticVectorEnv(N, 64, len(bench.BUCKETS), seed=0, device=dev)
+        cfg = m.TrainConfig(
+            num_worlds=N, num_agents_per_world=1, num_updates=1 << 30,
+            actions={'act': m.DiscreteActionsConfig(bench.BUCKETS)}, steps_per_update=T, lr=3e-4,
+            algo=m.PPOConfig(num_epochs=2, minibatch_size=N * C // 4, clip_coef=0.2, value_loss_coef=0.5,
+                             entropy_coef={'act': 0.01}, max_grad_norm=0.5),
+            num_bptt_chunks=C, gamma=0.99, seed=0, metrics_buffer_size=4, gae_lambda=0.95,
+            dreamer_v3_critic=False, normalize_values=True, compute_dtype=torch.bfloat16)
+        mgr = m.init_training(dev, cfg, env.sim_fns(), policy, None, verbose=False)
+    else:
+        N = wl['worlds']
+        env = m.SyntheticVectorEnv(N, bench.WORKLOAD['obs_dim'], len(bench.BUCKETS), seed=0, device=dev)
+        mgr = m.init_training(dev, bench.make_cfg(m, N, dtype='bf16', wl=wl), env.sim_fns(), bench.make_policy(m, wl),
+                              None, verbose=False)
     mgr.update_iter()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
