@@ -15,8 +15,9 @@
 // x_t for k < in, from h_{t-1} after) and the matching 32 KB k-block of the unit's weights (streamed from
 // L2: the packed matrix is 4 RH x (in + RH) bf16 = 1 MB at RH = in = 256).  Two 256-column accumulator
 // buffers: the tensor core fills unit u+1 while the sixteen epilogue warps run the cell math on unit u.
-// Epilogue warp (quadrant q, group g): rows 32q.., hidden units 16g..16g+15 of the unit, one row per lane:
-// every global access is a whole 32-byte sector (8 fp32 / 16 bf16 per lane).
+// Epilogue warp (quadrant q, group g): rows 32q.., hidden units 16g..16g+15 of the unit, one row per lane in
+// registers; c, h and the gate stash move through a per-warp shared-memory transpose tile so that global
+// accesses are 64-byte row segments (8 rows per instruction) instead of 32 scattered sectors.
 #include <cuda_bf16.h>
 
 #include "tc_common.cuh"
@@ -28,6 +29,7 @@ using namespace tc;
 constexpr int L_THREADS = 576;           // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
 constexpr int L_STAGE = 16384 + 32768;
 constexpr int L_MAX_STAGES = 4;
+constexpr int L_STAGES = 3;              // 3 x 48 KB ring + 32 KB transpose tiles
 
 struct LBars {
     uint64_t *full, *empty, *acc_full, *acc_empty;
@@ -44,6 +46,80 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16 accumulator columns of this lane's row
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// Per-warp transpose tile [32 rows x 64 B]: 16-byte slot q of row r at r*64 + ((q ^ ((r >> 1) & 3)) << 4)
+// (conflict-free for both the row-per-lane and the 4-lanes-per-row access).
+__device__ __forceinline__ uint4* tslot(uint8_t* wt, int r, int q) {
+    return reinterpret_cast<uint4*>(wt + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+}
+// row-per-lane registers -> global [rows, ld] fp32, 16 columns: instruction k covers rows 8k..8k+7, four lanes
+// per 64-byte row segment
+template <bool STREAM>
+__device__ __forceinline__ void tile_store16(uint8_t* wt, int lane, float* g, int ld, int rows_valid, const float (&v)[16]) {
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *tslot(wt, lane, q) = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                                         __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+    __syncwarp();
+    const int c = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = k * 8 + (lane >> 2);
+        const uint4 x = *tslot(wt, r, c);
+        if (r < rows_valid) {
+            uint4* dst = reinterpret_cast<uint4*>(g + (size_t)r * ld + c * 4);
+            if (STREAM) __stcs(dst, x); else *dst = x;
+        }
+    }
+}
+// the same for a bf16 destination: 32 bytes per row, two lanes per row, instruction k covers rows 16k..16k+15
+__device__ __forceinline__ void tile_store16_bf(uint8_t* wt, int lane, __nv_bfloat16* g, int ld, int rows_valid,
+                                                const float (&v)[16]) {
+    __syncwarp();
+    *tslot(wt, lane, 0) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *tslot(wt, lane, 1) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+    __syncwarp();
+    const int c = lane & 1;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int r = k * 16 + (lane >> 1);
+        const uint4 x = *tslot(wt, r, c);
+        if (r < rows_valid) *reinterpret_cast<uint4*>(g + (size_t)r * ld + c * 8) = x;
+    }
+}
+// global [rows, ld] fp32, 16 columns -> row-per-lane registers
+__device__ __forceinline__ void tile_load16(uint8_t* wt, int lane, const float* g, int ld, int rows_valid, float (&v)[16]) {
+    __syncwarp();
+    const int c = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = k * 8 + (lane >> 2);
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows_valid) x = *reinterpret_cast<const uint4*>(g + (size_t)r * ld + c * 4);
+        *tslot(wt, r, c) = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 x = *tslot(wt, lane, q);
+        v[4 * q] = __uint_as_float(x.x); v[4 * q + 1] = __uint_as_float(x.y);
+        v[4 * q + 2] = __uint_as_float(x.z); v[4 * q + 3] = __uint_as_float(x.w);
+    }
+}
+
 __global__ void __launch_bounds__(L_THREADS, 1)
 lstm_step_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
                     const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias_packed,
@@ -54,7 +130,8 @@ lstm_step_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     pdl_launch_dependents();
     uint8_t* smem = align_smem_1024(smem_raw);
-    float* bsm = reinterpret_cast<float*>(smem + stages * L_STAGE);          // packed bias [4 RH]
+    uint8_t* tiles = smem + stages * L_STAGE;                                // 16 x 2 KB transpose tiles
+    float* bsm = reinterpret_cast<float*>(tiles + 16 * 2048);                // packed bias [4 RH]
     LBars bars;
     bars.full = reinterpret_cast<uint64_t*>(bsm + 4 * RH);
     bars.empty = bars.full + L_MAX_STAGES;
@@ -131,76 +208,65 @@ lstm_step_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
         }
     } else {
+        // Epilogue warp (quad, grp): rows 32 quad.., hidden units 16 grp.. of the unit -- one accumulator row per
+        // lane.  Every global array is row-major [M, RH], so a lane's 64 bytes sit 4 RH bytes from its
+        // neighbour's: all loads and stores go through a per-warp [32 rows x 64 B] transpose tile so that one
+        // instruction covers 8 rows x 64 contiguous bytes (4x fewer LSU wavefronts than row-per-lane access).
         const int quad = warp & 3, grp = (warp - 2) >> 2;
+        uint8_t* wt = tiles + (warp - 2) * 2048;
         for (int i = 0; i < my_units; ++i) {
             const int buf = i & 1;
             const int u = blockIdx.x + i * gridDim.x;
             const int tile = u / nblk, nb = u % nblk;
-            const int row = tile * BM + quad * 32 + lane;
-            const bool ok = row < M;
-            const float keep = (ok && ends && ends[row]) ? 0.f : 1.f;
+            const int row0 = tile * BM + quad * 32;
+            const int rows_valid = M - row0;                  // rows of this warp's block inside M
+            const int j0 = nb * 64 + grp * 16;                // first hidden unit of this warp's group
+            const bool ok = lane < rows_valid;
+            const float keep = (ok && ends && ends[row0 + lane]) ? 0.f : 1.f;
             const uint32_t tq = tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16) + grp * 16;
+            const float* bp = bsm + nb * 256 + grp * 16;      // packed bias: gate blocks of 64
+            const size_t gofs = (size_t)row0 * RH + j0;
+            float cp[16], a[16], ig[16];
+            tile_load16(wt, lane, c_prev + gofs, RH, rows_valid, cp);          // (overlaps the accumulator wait)
             mbar_wait(&bars.acc_full[buf], (i >> 1) & 1, 0x21);
             tcgen05_fence_after();
+            float* sp = stash ? stash + (size_t)row0 * 5 * RH + j0 : nullptr;
+            // gate i, gate g  ->  ig = i * g
+            tmem_ld16(tq, a);
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {                  // 8 hidden units at a time
-                const int j0 = nb * 64 + grp * 16 + hf * 8;   // first hidden unit of this lane's group
-                uint32_t zi[8], zf[8], zg[8], zo[8];
-                tmem_ld8(tq + hf * 8, zi);
-                tmem_ld8(tq + 64 + hf * 8, zf);
-                tmem_ld8(tq + 128 + hf * 8, zg);
-                tmem_ld8(tq + 192 + hf * 8, zo);
-                float cp[8];
-                if (ok) {
-                    const float4 a = *reinterpret_cast<const float4*>(c_prev + (size_t)row * RH + j0);
-                    const float4 b = *reinterpret_cast<const float4*>(c_prev + (size_t)row * RH + j0 + 4);
-                    cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
-                } else {
+            for (int k = 0; k < 16; ++k) { a[k] = sigm(a[k] + bp[k]); ig[k] = a[k]; }
+            if (sp) tile_store16<true>(wt, lane, sp, 5 * RH, rows_valid, a);
+            tmem_ld16(tq + 128, a);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) cp[k] = 0.f;
-                }
-                tmem_wait_ld();
-                if (hf == 1) {                                // last TMEM read of this warp for this unit
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars.acc_empty[buf]);
-                }
-                const float* bp = bsm + nb * 256 + grp * 16 + hf * 8;          // packed bias: gate blocks of 64
-                float gi[8], gf[8], gg[8], go[8], tc8[8], c8[8], h8[8];
+            for (int k = 0; k < 16; ++k) { a[k] = tanh_fast(a[k] + bp[128 + k]); ig[k] *= a[k]; }
+            if (sp) tile_store16<true>(wt, lane, sp + 2 * RH, 5 * RH, rows_valid, a);
+            // gate f  ->  c' = f c + i g
+            tmem_ld16(tq + 64, a);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    gi[k] = sigm(__uint_as_float(zi[k]) + bp[k]);
-                    gf[k] = sigm(__uint_as_float(zf[k]) + bp[64 + k]);
-                    gg[k] = tanh_fast(__uint_as_float(zg[k]) + bp[128 + k]);
-                    go[k] = sigm(__uint_as_float(zo[k]) + bp[192 + k]);
-                    c8[k] = gf[k] * cp[k] + gi[k] * gg[k];
-                    tc8[k] = tanh_fast(c8[k]);
-                    h8[k] = go[k] * tc8[k];
-                }
-                if (ok) {
-                    const size_t o = (size_t)row * RH + j0;
-                    *reinterpret_cast<uint4*>(h_seq + o) = make_uint4(pack_bf16(h8[0], h8[1]), pack_bf16(h8[2], h8[3]),
-                                                                      pack_bf16(h8[4], h8[5]), pack_bf16(h8[6], h8[7]));
-                    *reinterpret_cast<float4*>(c_carry + o) = make_float4(keep * c8[0], keep * c8[1], keep * c8[2], keep * c8[3]);
-                    *reinterpret_cast<float4*>(c_carry + o + 4) = make_float4(keep * c8[4], keep * c8[5], keep * c8[6], keep * c8[7]);
-                    if (h_carry) {
-                        *reinterpret_cast<float4*>(h_carry + o) = make_float4(keep * h8[0], keep * h8[1], keep * h8[2], keep * h8[3]);
-                        *reinterpret_cast<float4*>(h_carry + o + 4) = make_float4(keep * h8[4], keep * h8[5], keep * h8[6], keep * h8[7]);
-                    }
-                    if (h_carry_bf)
-                        *reinterpret_cast<uint4*>(h_carry_bf + o) =
-                            make_uint4(pack_bf16(keep * h8[0], keep * h8[1]), pack_bf16(keep * h8[2], keep * h8[3]),
-                                       pack_bf16(keep * h8[4], keep * h8[5]), pack_bf16(keep * h8[6], keep * h8[7]));
-                    if (stash) {
-                        float* sp = stash + (size_t)row * 5 * RH + j0;
-                        const float* src[5] = {gi, gf, gg, go, tc8};
+            for (int k = 0; k < 16; ++k) { a[k] = sigm(a[k] + bp[64 + k]); cp[k] = a[k] * cp[k] + ig[k]; }
+            if (sp) tile_store16<true>(wt, lane, sp + RH, 5 * RH, rows_valid, a);
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) {
-                            __stcs(reinterpret_cast<float4*>(sp + q * RH), make_float4(src[q][0], src[q][1], src[q][2], src[q][3]));
-                            __stcs(reinterpret_cast<float4*>(sp + q * RH + 4), make_float4(src[q][4], src[q][5], src[q][6], src[q][7]));
-                        }
-                    }
-                }
+            for (int k = 0; k < 16; ++k) a[k] = keep * cp[k];
+            tile_store16<false>(wt, lane, c_carry + gofs, RH, rows_valid, a);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) ig[k] = tanh_fast(cp[k]);              // ig := tanh(c')
+            if (sp) tile_store16<true>(wt, lane, sp + 4 * RH, 5 * RH, rows_valid, ig);
+            // gate o  ->  h' = o tanh(c')
+            tmem_ld16(tq + 192, a);
+            tcgen05_fence_before();                           // last TMEM read of this warp for this unit
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.acc_empty[buf]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = sigm(a[k] + bp[192 + k]);
+            if (sp) tile_store16<true>(wt, lane, sp + 3 * RH, 5 * RH, rows_valid, a);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] *= ig[k];                         // h'
+            tile_store16_bf(wt, lane, h_seq + gofs, RH, rows_valid, a);
+            if (h_carry || h_carry_bf) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) a[k] *= keep;
+                if (h_carry) tile_store16<false>(wt, lane, h_carry + gofs, RH, rows_valid, a);
+                if (h_carry_bf) tile_store16_bf(wt, lane, h_carry_bf + gofs, RH, rows_valid, a);
             }
         }
     }
@@ -254,8 +320,8 @@ MLB_API int mlb_lstm_step_tc(void* stream, const void* x, int ldx, const void* h
     if ((rc = make_map(&tX, x, in_dim, M, ldx, 64, 128))) return rc;
     if ((rc = make_map(&tH, h_prev, RH, M, RH, 64, 128))) return rc;
     if ((rc = make_map(&tW, w_packed, in_dim + RH, 4 * RH, in_dim + RH, 64, 256))) return rc;
-    const int stages = L_MAX_STAGES;
-    const int smem = stages * L_STAGE + 4 * RH * 4 + 256 + 1024;
+    const int stages = L_STAGES;
+    const int smem = stages * L_STAGE + 16 * 2048 + 4 * RH * 4 + 256 + 1024;
     cudaError_t e = cudaFuncSetAttribute(lstm_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     int sms = MLB_NUM_SMS, dev = 0;

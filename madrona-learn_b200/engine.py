@@ -237,7 +237,7 @@ class PolicyProgram:
             host[ln_off:ln_off + self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['scale'], np.float32))
             host[ln_off + self.H:ln_off + 2 * self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['bias'], np.float32))
         if self.lstm is not None:
-            self.lstm.load_oracle(host, p['lstm'][0])
+            self.lstm.load_oracle(host, p['lstm'])
         W = torch.zeros(self.feat, self.NH, dtype=F32)
         W[:, :self.sumA] = torch.from_numpy(np.asarray(p['actor']['kernel'], np.float32))
         W[:, self.sumA:self.sumA + self.V] = torch.from_numpy(np.asarray(p['critic']['kernel'], np.float32))
@@ -270,11 +270,14 @@ class PolicyProgram:
             net[f'LayerNorm_{i}'] = {'impl': {'scale': None, 'bias': None}}
         enc = {'net': net}
         if self.lstm is not None:
-            cell = {}
-            for g in ('i', 'f', 'g', 'o'):
-                cell['i' + g] = {'kernel': n.get(f'lstm0/i{g}')}
-                cell['h' + g] = {'kernel': n.get(f'lstm0/h{g}'), 'bias': None}
-            enc['rnn'] = {'cell': {'OptimizedLSTMCell_0': cell}}
+            cells = {}
+            for li in range(self.lstm.RL):
+                cell = {}
+                for g in ('i', 'f', 'g', 'o'):
+                    cell['i' + g] = {'kernel': n.get(f'lstm{li}/i{g}')}
+                    cell['h' + g] = {'kernel': n.get(f'lstm{li}/h{g}'), 'bias': None}
+                cells[f'OptimizedLSTMCell_{li}'] = cell
+            enc['rnn'] = {'cell': cells}
         return {'backbone': {'encoder': enc}, 'actor': {'impl': {'kernel': None, 'bias': None}},
                 'critic': {'Dense_0': {'kernel': None, 'bias': None}}}
 
@@ -403,14 +406,26 @@ class PolicyProgram:
             y = w['y'][i & 1]
             call('mlb_ln_relu_fwd_f32', ptr(w['z']), ptr(s), ptr(b), ptr(y), ptr(None), c_ll(rows), c_int(self.H))
             x, d = y, self.H
-        if self.lstm is not None:
-            if 'rz' not in w:
-                w['rz'] = torch.empty(rows, 4 * self.lstm.RH, dtype=F32, device=self.device)
-                w['rout'] = torch.empty(rows, self.lstm.RH, dtype=F32, device=self.device)
-            x = self.lstm.step_infer(x, rows, rnn_states, w['rz'], w['rout'])
+        xs = [x] if self.lstm is None else self.lstm.step_infer(x, rows, rnn_states, w)
+        return self._head_fwd_f32(xs, w['head'], rows)
+
+    def _head_fwd_f32(self, xs, head, rows):
+        """head = concat(xs) W + b; xs: the encoder's feature slices (one per LSTM layer, else the MLP output)."""
         W, B = self.head_views(self.params)
-        gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
-        return w['head']
+        fw = self.feat // len(xs)
+        for l, x in enumerate(xs):
+            gemm(x, W[l * fw:(l + 1) * fw], head, B if l == 0 else None, rows, self.NH, fw, fw, self.NH, self.NH,
+                 accumulate=0 if l == 0 else 1)
+        return head
+
+    def _head_fwd_tc(self, xs, head, rows):
+        _, B = self.head_views(self.params)
+        fw = self.feat // len(xs)
+        for l, x in enumerate(xs):               # K-slice l of wh_t [NH, feat]: pointer offset, ldb = feat
+            Bt = self.wh_t if len(xs) == 1 else self.wh_t.view(-1)[l * fw:]
+            gemm_tc(x, Bt, head, B if l == 0 else None, rows, self.NH, fw, fw, self.feat, self.NH, 0, 0,
+                    0 if l == 0 else 2)
+        return head
 
     def _forward_tc(self, obs, rows, w, ys, xhs, rstds, x_ready=False, seq=None, rnn_states=None):
         """bf16 tensor-core forward: cast obs -> L x fused [tcgen05 GEMM + LayerNorm + ReLU epilogue
@@ -424,17 +439,13 @@ class PolicyProgram:
                  ptr(None if xhs is None else xhs[i]), ptr(None if rstds is None else rstds[i]),
                  c_int(rows), c_int(d), c_int(self.H), c_int(d), c_int(d))
             x, d = ys[i], self.H
+        xs = [x]
         if self.lstm is not None:
             if seq is not None:                       # training: the whole T' sequence
-                x = self.lstm.sequence_fwd(x, seq)
+                xs = self.lstm.sequence_fwd(x, seq)
             else:                                     # rollout: one step, states updated in place
-                if 'rz' not in w:
-                    w['rz'] = torch.empty(rows, 4 * self.lstm.RH, dtype=F32, device=self.device)
-                    w['rout'] = torch.empty(rows, self.lstm.RH, dtype=torch.bfloat16, device=self.device)
-                x = self.lstm.step_infer(x, rows, rnn_states, w['rz'], w['rout'])
-        _, B = self.head_views(self.params)
-        gemm_tc(x, self.wh_t, w['head'], B, rows, self.NH, self.feat, self.feat, self.feat, self.NH, 0, 0, 0)
-        return w['head']
+                xs = self.lstm.step_infer(x, rows, rnn_states, w)
+        return self._head_fwd_tc(xs, w['head'], rows)
 
     @property
     def fused_rollout(self):
@@ -486,11 +497,8 @@ class PolicyProgram:
             call('mlb_ln_relu_fwd_f32', ptr(w['z'][i]), ptr(s), ptr(b), ptr(w['y'][i]), ptr(w['stats'][i]),
                  c_ll(rows), c_int(self.H))
             x, d = w['y'][i], self.H
-        if self.lstm is not None:
-            x = self.lstm.sequence_fwd(x, seq)
-        W, B = self.head_views(self.params)
-        gemm(x, W, w['head'], B, rows, self.NH, self.feat, self.feat, self.NH, self.NH)
-        return w['head']
+        xs = [x] if self.lstm is None else self.lstm.sequence_fwd(x, seq)
+        return self._head_fwd_f32(xs, w['head'], rows)
 
     def backward(self, obs, rows, seq=None):
         """Consumes train_ws['dhead']; accumulates into self.grads (pre-zeroed)."""
@@ -500,15 +508,18 @@ class PolicyProgram:
         W, B = self.head_views(self.params)
         gW, gB = self.head_views(self.grads)
         if self.lstm is not None:
-            lw = self.lstm.train_ws(seq['Tp'], seq['M'])
-            feat, dfeat = lw['h_seq'].view(rows, self.feat), lw['d_hseq'].view(rows, self.feat)
+            lws = self.lstm.train_ws(seq['Tp'], seq['M'])
+            fw = self.lstm.RH
+            pairs = [(lw['h_seq'].view(rows, fw), lw['d_hseq'].view(rows, fw)) for lw in lws]
         else:
-            feat, dfeat = w['y'][self.L - 1], w['dy']
-        # dW_h = feat^T dhead ; db_h = colsum(dhead) ; dfeat = dhead W_h^T
-        gemm(feat, w['dhead'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH,
-             ta=1, tb=0, accumulate=1, splitk=_splitk_for(self.feat, self.NH, rows))
-        gemm(w['dhead'], W, dfeat, None, rows, self.feat, self.NH, self.NH, self.NH, self.feat,
-             ta=0, tb=1)
+            fw = self.feat
+            pairs = [(w['y'][self.L - 1], w['dy'])]
+        # dW_h = feat^T dhead ; db_h = colsum(dhead) ; dfeat = dhead W_h^T   (per feature slice)
+        for l, (feat, dfeat) in enumerate(pairs):
+            gemm(feat, w['dhead'], gW[l * fw:(l + 1) * fw], None, fw, self.NH, rows, fw, self.NH, self.NH,
+                 ta=1, tb=0, accumulate=1, splitk=_splitk_for(fw, self.NH, rows))
+            gemm(w['dhead'], W[l * fw:(l + 1) * fw], dfeat, None, rows, fw, self.NH, self.NH, self.NH, fw,
+                 ta=0, tb=1)
         if self.lstm is not None:
             self.lstm.sequence_bwd(w['y'][self.L - 1], seq, w['dy'])
         for i in range(self.L - 1, -1, -1):
@@ -542,10 +553,13 @@ class PolicyProgram:
                 fn()
 
         gW, _ = self.head_views(self.grads)       # (head bias grads were accumulated by the loss kernel)
-        lw = self.lstm.train_ws(seq['Tp'], seq['M']) if self.lstm is not None else None
-        feat = w['y'][self.L - 1] if lw is None else lw['h_seq'].view(rows, self.feat)
-        on_side(lambda: gemm_tc(feat, w['dhead'], gW, None, self.feat, self.NH, rows, self.feat, self.NH, self.NH,
-                                1, 1, 2, _splitk_tc(self.feat, self.NH, rows)))
+        lws = self.lstm.train_ws(seq['Tp'], seq['M']) if self.lstm is not None else None
+        lw = None if lws is None else lws[0]
+        fw = self.feat if lws is None else self.lstm.RH
+        feats = [w['y'][self.L - 1]] if lws is None else [x['h_seq'].view(rows, fw) for x in lws]
+        for l, feat in enumerate(feats):
+            on_side(lambda feat=feat, l=l: gemm_tc(feat, w['dhead'], gW[l * fw:(l + 1) * fw], None, fw, self.NH, rows,
+                                                   fw, self.NH, self.NH, 1, 1, 2, _splitk_tc(fw, self.NH, rows)))
         bufs = w['dzs']                           # rotating dZ buffers (3: a dW may still read the oldest)
         cur = 0
         i = self.L - 1
@@ -560,8 +574,9 @@ class PolicyProgram:
             # d(encoder output) = dhead Wh^T (fp32), BPTT through the LSTM, then the gradient to the MLP output
             # (dz_all W_i) fused with the last layer's LayerNorm/ReLU backward
             RH4 = 4 * self.lstm.RH
-            gemm_tc(w['dhead'], self.wh_c, lw['d_hseq'], None, rows, self.feat, self.NH, self.NH, self.NH, self.feat,
-                    0, 0, 0)
+            for l, x in enumerate(lws):           # rows l*RH.. of wh_c [feat, NH]: the slice's own B[N = RH, K = NH]
+                gemm_tc(w['dhead'], self.wh_c[l * fw:(l + 1) * fw], x['d_hseq'], None, rows, fw, self.NH, self.NH,
+                        self.NH, fw, 0, 0, 0)
             self.lstm.sequence_bwd(w['y'][i], seq, None)
             call('mlb_dense_dx_lnbwd_tc', ptr(lw['dz']), ptr(self.lstm.wi_t), ptr(s), ptr(b), ptr(w['xh'][i]),
                  ptr(w['rstd'][i]), ptr(bufs[cur]), ptr(gs), ptr(gb), c_int(rows), c_int(RH4), c_int(self.H),

@@ -139,8 +139,8 @@ class _PPOWorkspace:
             'values': e(Tp, M, 1), 'dones': e(Tp, M, 1, dtype=torch.uint8),
         }
         if prog.lstm is not None:
-            self.mb['rnn_start_c'] = e(M, prog.lstm.RH)
-            self.mb['rnn_start_h'] = e(M, prog.lstm.RH)
+            self.mb['rnn_start_c'] = e(M, prog.lstm.RH * prog.lstm.RL)      # layers side by side
+            self.mb['rnn_start_h'] = e(M, prog.lstm.RH * prog.lstm.RL)
         self.Tp = Tp
         if self.mode != 'default':
             npad = K.sort_pad(J)
@@ -169,6 +169,13 @@ class _PPOWorkspace:
         self.obj_scale = (ctypes.c_float * A)(*[1.0 / (rows_global * g_size)] * A)
         self.ent_scale = (ctypes.c_float * A)(*[coef / (rows_global * g_size)] * A)
         prog.train_ws(self.rows)
+
+
+def _layer_states(lstm, mb):
+    """Per-layer [M, RH] views of the gathered chunk-start states (ml/rollouts.py:471-478)."""
+    RH = lstm.RH
+    return dict(c0=[mb['rnn_start_c'][:, l * RH:(l + 1) * RH] for l in range(lstm.RL)],
+                h0=[mb['rnn_start_h'][:, l * RH:(l + 1) * RH] for l in range(lstm.RL)])
 
 
 def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics, dist_ctx=None,
@@ -249,7 +256,7 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
     seq = None
     if prog.lstm is not None:
         keys.append('dones')
-        seq = dict(Tp=Tp, M=M, ends=mb['dones'].view(Tp, M), c0=mb['rnn_start_c'], h0=mb['rnn_start_h'])
+        seq = dict(Tp=Tp, M=M, ends=mb['dones'].view(Tp, M), **_layer_states(prog.lstm, mb))
     leaf_names = list(dict.fromkeys(keys))
     if ws.index_exact and getattr(ws, 'peer_tab', None) is None:
         ws.peer_tab = dist_ctx.peer_store_table(leaf_names)
@@ -400,7 +407,7 @@ def _ppo_selected(cfg, policy_state, train_state, rollout_data, user_metrics_cb,
     seq = None
     if prog.lstm is not None:
         keys.append('dones')
-        seq = dict(Tp=Tp, M=M, ends=mb['dones'].view(Tp, M), c0=mb['rnn_start_c'], h0=mb['rnn_start_h'])
+        seq = dict(Tp=Tp, M=M, ends=mb['dones'].view(Tp, M), **_layer_states(prog.lstm, mb))
     for e in range(E):
         for k in range(nmb):
             idx = perm[e, k * M:(k + 1) * M]

@@ -30,12 +30,12 @@ F32 = torch.float32
 GATES = ('i', 'f', 'g', 'o')
 
 
-class LSTMLowering:
-    def __init__(self, prog, rnn, in_dim, off):
-        if rnn.num_layers != 1:
-            raise NotImplementedError('LSTM with num_layers > 1: next (single-layer LSTM is lowered)')
+class _LSTMLayer:
+    """One OptimizedLSTMCell of the stack (layer `li`; input = the MLP output for li = 0, else h of li - 1)."""
+
+    def __init__(self, prog, rnn, in_dim, off, li=0):
+        self.li = int(li)
         self.RH = int(rnn.num_hidden_channels)
-        self.RL = 1
         self.in_dim = int(in_dim)
         if self.RH % 4:
             raise NotImplementedError('LSTM width must be a multiple of 4')
@@ -80,7 +80,7 @@ class LSTMLowering:
         for g, name in enumerate(GATES):
             cell['i' + name] = {'kernel': wi[g * RH:(g + 1) * RH].t()}
             cell['h' + name] = {'kernel': wh[g * RH:(g + 1) * RH].t(), 'bias': b[g * RH:(g + 1) * RH]}
-        return {'cell': {'OptimizedLSTMCell_0': cell}}
+        return cell
 
     def init_host(self, host, orth):
         RH, d = self.RH, self.in_dim
@@ -99,7 +99,7 @@ class LSTMLowering:
     def to_oracle(self, arena):
         wi, wh, b = self.views(arena)
         c = lambda x: x.detach().cpu().numpy().copy()
-        return [{'wi': c(wi.t()), 'wh': c(wh.t()), 'bh': c(b)}]
+        return {'wi': c(wi.t()), 'wh': c(wh.t()), 'bh': c(b)}
 
     def segments(self, host, norms):
         """One re-projection segment per gate kernel (8 per layer)."""
@@ -108,7 +108,7 @@ class LSTMLowering:
         for g, name in enumerate(GATES):
             for key, off, n in (('i' + name, self.wi_off + g * RH * d, RH * d),
                                 ('h' + name, self.wh_off + g * RH * RH, RH * RH)):
-                k = f'lstm0/{key}'
+                k = f'lstm{self.li}/{key}'
                 if k not in norms:
                     norms[k] = float(torch.linalg.vector_norm(host[off:off + n].double()))
                 segs.append(_lib.Segment(off, n, 1, norms[k]))
@@ -145,14 +145,14 @@ class LSTMLowering:
     # ---- state ------------------------------------------------------------------------
     def init_states(self, N, device):
         z = lambda: torch.zeros(N, self.RH, dtype=F32, device=device)
-        return [z()], [z()]
+        return z(), z()
 
     # ---- rollout step -------------------------------------------------------------------
     def step_infer(self, x, rows, states, z_buf, out):
         """x [rows, in] -> out [rows, RH]; states ([c], [h]) updated in place."""
         from .engine import gemm, gemm_tc
         wi, wh, b = self.views(self.prog.params)
-        c, h = states[0][0], states[1][0]
+        c, h = states[0][self.li], states[1][self.li]
         RH, d = self.RH, self.in_dim
         if self.tc:                    # x, out: bf16; states stay fp32 (h is cast for the recurrent GEMM)
             hb = self._h_bf(rows)
@@ -179,7 +179,7 @@ class LSTMLowering:
         return hb
 
     def reset(self, states, dones, rows):
-        for s in (states[0][0], states[1][0]):
+        for s in (states[0][self.li], states[1][self.li]):
             call('mlb_rnn_reset_f32', ptr(s), ptr(dones), c_ll(rows), c_int(self.RH))
 
     # ---- training sequence --------------------------------------------------------------
@@ -198,8 +198,22 @@ class LSTMLowering:
             self._ws = w
         return w
 
+    def _load_start(self, seq, w):
+        """c_in[0], h_in[0] <- this layer's chunk-start state (a strided feature slice when RL > 1)."""
+        c0, h0 = seq['c0'][self.li], seq['h0'][self.li]
+        M, RH = seq['M'], self.RH
+        if c0.is_contiguous() and h0.is_contiguous():
+            call('mlb_copy_bytes', ptr(c0), ptr(w['c_in'][0]), _lib.c_size_t(M * RH * 4))
+            if self.tc:
+                call('mlb_cast_f32_bf16', ptr(h0), ptr(w['h_in'][0]), c_ll(M * RH))
+            else:
+                call('mlb_copy_bytes', ptr(h0), ptr(w['h_in'][0]), _lib.c_size_t(M * RH * 4))
+        else:
+            w['c_in'][0].copy_(c0)
+            w['h_in'][0].copy_(h0)
+
     def sequence_fwd(self, feats, seq):
-        """feats [T'*M, in]; seq: dict(Tp, M, ends u8 [T', M], c0 [M, RH], h0 [M, RH]).
+        """feats [T'*M, in]; seq: dict(Tp, M, ends u8 [T', M], c0 / h0: per-layer lists of [M, RH]).
         Returns h_seq [T'*M, RH] (the encoder output)."""
         from .engine import gemm, gemm_tc
         Tp, M = seq['Tp'], seq['M']
@@ -207,8 +221,7 @@ class LSTMLowering:
         wi, wh, b = self.views(self.prog.params)
         RH, d, rows = self.RH, self.in_dim, Tp * M
         if self.tc and self.fused:
-            call('mlb_copy_bytes', ptr(seq['c0']), ptr(w['c_in'][0]), _lib.c_size_t(M * RH * 4))
-            call('mlb_cast_f32_bf16', ptr(seq['h0']), ptr(w['h_in'][0]), c_ll(M * RH))
+            self._load_start(seq, w)
             f3 = feats.view(Tp, M, d)
             for t in range(Tp):
                 call('mlb_lstm_step_tc', ptr(f3[t]), c_int(d), ptr(w['h_in'][t]), ptr(self.w_packed), ptr(self.b_packed),
@@ -217,8 +230,7 @@ class LSTMLowering:
             return w['h_seq'].view(rows, RH)
         if self.tc:
             gemm_tc(feats, self.wi_c, w['z'], b, rows, 4 * RH, d, d, d, 4 * RH, 0, 0, 0)     # + bias in the epilogue
-            call('mlb_copy_bytes', ptr(seq['c0']), ptr(w['c_in'][0]), _lib.c_size_t(M * RH * 4))
-            call('mlb_cast_f32_bf16', ptr(seq['h0']), ptr(w['h_in'][0]), c_ll(M * RH))
+            self._load_start(seq, w)
             for t in range(Tp):
                 gemm_tc(w['h_in'][t], self.wh_c, w['z'][t], None, M, 4 * RH, RH, RH, RH, 4 * RH, 0, 0, 2)
                 call('mlb_lstm_cell_fwd_tc', ptr(w['z'][t]), ptr(None), ptr(w['c_in'][t]), ptr(seq['ends'][t]),
@@ -226,8 +238,7 @@ class LSTMLowering:
                      c_ll(M), c_int(RH))
             return w['h_seq'].view(rows, RH)
         gemm(feats, wi, w['z'], None, rows, 4 * RH, d, d, d, 4 * RH, ta=0, tb=1)
-        call('mlb_copy_bytes', ptr(seq['c0']), ptr(w['c_in'][0]), _lib.c_size_t(M * RH * 4))
-        call('mlb_copy_bytes', ptr(seq['h0']), ptr(w['h_in'][0]), _lib.c_size_t(M * RH * 4))
+        self._load_start(seq, w)
         for t in range(Tp):
             gemm(w['h_in'][t], wh, w['z'][t], None, M, 4 * RH, RH, RH, RH, 4 * RH, ta=0, tb=1, accumulate=1)
             call('mlb_lstm_cell_fwd_f32', ptr(w['z'][t]), ptr(b), ptr(w['c_in'][t]), ptr(seq['ends'][t]),
@@ -235,9 +246,10 @@ class LSTMLowering:
                  c_ll(M), c_int(RH))
         return w['h_seq'].view(rows, RH)
 
-    def sequence_bwd(self, feats, seq, dfeats):
-        """Consumes ws['d_hseq'] [T', M, RH] (gradient w.r.t. the encoder output); accumulates the
-        LSTM parameter gradients into the program's gradient arena and writes dfeats [T'*M, in]."""
+    def sequence_bwd(self, feats, seq, dfeats, accumulate=False):
+        """Consumes ws['d_hseq'] [T', M, RH] (gradient w.r.t. this layer's output); accumulates the
+        LSTM parameter gradients into the program's gradient arena and writes (accumulate: adds to)
+        dfeats [T'*M, in], the gradient w.r.t. the layer's input."""
         from .engine import _splitk_for, gemm
         Tp, M = seq['Tp'], seq['M']
         w = self.train_ws(Tp, M)
@@ -245,7 +257,7 @@ class LSTMLowering:
         gwi, gwh, gb = self.views(self.prog.grads)
         RH, d, rows = self.RH, self.in_dim, Tp * M
         if self.tc:
-            return self._sequence_bwd_tc(feats, seq, dfeats, w, gwi, gwh, gb)
+            return self._sequence_bwd_tc(feats, seq, dfeats, w, gwi, gwh, gb, accumulate)
         dz = w['z']                                   # pre-activations are dead: reuse as dz_all
         for t in range(Tp - 1, -1, -1):
             last = t == Tp - 1
@@ -261,13 +273,14 @@ class LSTMLowering:
         gemm(dz2, feats, gwi, None, 4 * RH, d, rows, 4 * RH, d, d, ta=1, tb=0, accumulate=1,
              splitk=_splitk_for(4 * RH, d, rows))
         call('mlb_colsum_f32', ptr(dz2), c_ll(rows), c_int(4 * RH), c_int(4 * RH), ptr(gb))
-        gemm(dz2, wi, dfeats, None, rows, d, 4 * RH, 4 * RH, d, d)
+        gemm(dz2, wi, dfeats, None, rows, d, 4 * RH, 4 * RH, d, d, accumulate=1 if accumulate else 0)
         return dfeats
 
-    def _sequence_bwd_tc(self, feats, seq, dfeats, w, gwi, gwh, gb):
-        """Tensor-core BPTT.  feats bf16 [T'*M, in]; consumes w['d_hseq'] (f32).  dfeats is None: the gradient
-        to the layer below, dz_all W_i, is fused into that layer's LayerNorm-backward kernel by the caller
-        (mlb_dense_dx_lnbwd_tc with DZ_in = w['dz'], W = wi_t)."""
+    def _sequence_bwd_tc(self, feats, seq, dfeats, w, gwi, gwh, gb, accumulate=False):
+        """Tensor-core BPTT.  feats bf16 [T'*M, in]; consumes w['d_hseq'] (f32).  dfeats None (layer 0): the
+        gradient to the MLP output, dz_all W_i, is fused into the last Dense layer's LayerNorm-backward kernel by
+        the caller (mlb_dense_dx_lnbwd_tc with DZ_in = w['dz'], W = wi_t); otherwise (upper layers) it is ADDED
+        to dfeats = the f32 d_hseq of the layer below."""
         from .engine import _splitk_tc, gemm_tc
         Tp, M = seq['Tp'], seq['M']
         RH, d, rows = self.RH, self.in_dim, Tp * M
@@ -286,4 +299,124 @@ class LSTMLowering:
                 _splitk_tc(4 * RH, RH, rows))
         gemm_tc(dz2, feats, gwi, None, 4 * RH, d, rows, 4 * RH, d, d, 1, 1, 2, _splitk_tc(4 * RH, d, rows))
         call('mlb_colsum_bf16', ptr(dz2), c_ll(rows), c_int(4 * RH), c_int(4 * RH), ptr(gb))
+        if dfeats is not None:                    # += dz_all W_i : B = W_i^T stored [K = 4RH, N = in] (MN-major)
+            assert accumulate
+            gemm_tc(dz2, self.wi_c, dfeats, None, rows, d, 4 * RH, 4 * RH, d, d, 0, 1, 2)
         return None
+
+
+class LSTMLowering:
+    """The LSTM stack of a RecurrentBackboneEncoder (ml/rnn.py:10-111): `num_layers` cells, layer l fed by the
+    hidden state of layer l - 1, encoder output = the concatenation of every layer's hidden state
+    (MultiLayerLSTMCell.__call__ :27-45).  The concatenation is never materialised: the heads read the layers'
+    outputs as RL separate K-slices of the head GEMM (and scatter their gradient the same way)."""
+
+    def __init__(self, prog, rnn, in_dim, off):
+        self.RH = int(rnn.num_hidden_channels)
+        self.RL = int(rnn.num_layers)
+        if self.RL < 1:
+            raise NotImplementedError('LSTM needs num_layers >= 1')
+        self.prog = prog
+        self.layers = []
+        d = int(in_dim)
+        for li in range(self.RL):
+            lyr = _LSTMLayer(prog, rnn, d, off, li)
+            self.layers.append(lyr)
+            off, d = lyr.end_off, self.RH
+        self.end_off = off
+        self.in_dim = int(in_dim)
+        self.tc = self.layers[0].tc
+
+    # single-layer shorthands (tests, the tensor-core backward's fused dx call)
+    def views(self, arena, li=0):
+        return self.layers[li].views(arena)
+
+    def __getattr__(self, name):
+        if name in ('wi_c', 'wi_t', 'wh_c', 'wh_t', 'w_packed', 'b_packed', 'fused'):
+            return getattr(self.layers[0], name)
+        raise AttributeError(name)
+
+    def param_tree(self, arena):
+        return {'cell': {f'OptimizedLSTMCell_{l.li}': l.param_tree(arena) for l in self.layers}}
+
+    def init_host(self, host, orth):
+        for l in self.layers:
+            l.init_host(host, orth)
+
+    def load_oracle(self, host, lstm):
+        assert len(lstm) == self.RL
+        for l, lyr in zip(self.layers, lstm):
+            l.load_oracle(host, lyr)
+
+    def to_oracle(self, arena):
+        return [l.to_oracle(arena) for l in self.layers]
+
+    def segments(self, host, norms):
+        return [sg for l in self.layers for sg in l.segments(host, norms)]
+
+    def bf16_copies(self):
+        return [c for l in self.layers for c in l.bf16_copies()]
+
+    def refresh_bf16(self):
+        for l in self.layers:
+            l.refresh_bf16()
+
+    def pack(self):
+        for l in self.layers:
+            l.pack()
+
+    def init_states(self, N, device):
+        st = [l.init_states(N, device) for l in self.layers]
+        return [c for c, _ in st], [h for _, h in st]
+
+    def reset(self, states, dones, rows):
+        for l in self.layers:
+            l.reset(states, dones, rows)
+
+    def step_infer(self, x, rows, states, ws):
+        """One rollout step through the stack; returns the per-layer outputs [rows, RH] (ws: the caller's
+        workspace dict, holds the per-layer scratch)."""
+        outs = []
+        OT = torch.bfloat16 if self.tc else F32
+        for l in self.layers:
+            key = f'rout{l.li}'
+            if key not in ws or ws[key].shape[0] < rows:
+                ws[key] = torch.empty(rows, self.RH, dtype=OT, device=self.prog.device)
+                ws['rz'] = torch.empty(rows, 4 * self.RH, dtype=F32, device=self.prog.device)
+            x = l.step_infer(x, rows, states, ws['rz'], ws[key])
+            outs.append(x)
+        return outs
+
+    def train_ws(self, Tp, M):
+        return [l.train_ws(Tp, M) for l in self.layers]
+
+    @staticmethod
+    def _seq(seq):
+        """c0 / h0 as per-layer lists (a bare tensor is accepted for a single layer)."""
+        if isinstance(seq['c0'], (list, tuple)):
+            return seq
+        return {**seq, 'c0': [seq['c0']], 'h0': [seq['h0']]}
+
+    def sequence_fwd(self, feats, seq):
+        seq = self._seq(seq)
+        outs = []
+        for l in self.layers:
+            feats = l.sequence_fwd(feats, seq)
+            outs.append(feats)
+        return outs
+
+    def sequence_bwd(self, feats, seq, dfeats):
+        """Top layer first: each layer adds the gradient w.r.t. its input to the d_hseq of the layer below
+        (already holding the heads' contribution); layer 0 writes dfeats (f32 path) or leaves dz for the fused
+        dx kernel (tensor-core path, dfeats None)."""
+        seq = self._seq(seq)
+        lws = self.train_ws(seq['Tp'], seq['M'])
+        rows = seq['Tp'] * seq['M']
+        for li in range(self.RL - 1, -1, -1):
+            l = self.layers[li]
+            if li == 0:
+                l.sequence_bwd(feats, seq, dfeats)
+            else:
+                below = lws[li - 1]
+                l.sequence_bwd(below['h_seq'].view(rows, self.RH), seq, below['d_hseq'].view(rows, self.RH),
+                               accumulate=True)

@@ -144,6 +144,14 @@ class RolloutData:                      # ml/rollouts.py:311-334
         return res
 
 
+def _copy_state(dst, src):
+    """dst[...] = src for one [N, RH] recurrent-state block (a feature slice of the store when RL > 1)."""
+    if dst.is_contiguous() and src.is_contiguous():
+        call('mlb_copy_bytes', ptr(src), ptr(dst), c_size_t(src.numel() * src.element_size()))
+    else:
+        dst.copy_(src)
+
+
 class RolloutManager:                   # ml/rollouts.py:373-826
     def __init__(self, train_cfg, init_rollout_state, example_policy_states, dist_ctx=None):
         self._cfg = init_rollout_state.cfg
@@ -181,7 +189,8 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         self._lstm = prog.lstm
         if self._lstm is not None:
             # rnn_start_states [C, P, B, *] (ml/rollouts.py:471-478): the carry entering each BPTT chunk
-            RH = self._lstm.RH
+            # (layers concatenated along the feature axis: [.., l*RH:(l+1)*RH] is layer l's state)
+            RH = self._lstm.RH * self._lstm.RL
             specs['rnn_start_c'] = ((C, 1, B, RH), f32)
             specs['rnn_start_h'] = ((C, 1, B, RH), f32)
             self._boot_states = self._lstm.init_states(B, dev)
@@ -224,11 +233,10 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         for c in range(self._num_bptt_chunks):
             if self._lstm is not None:
                 with profile('Cache RNN state'):          # :533-537
-                    nbytes = self._cfg.sim_batch_size * self._lstm.RH * 4
-                    call('mlb_copy_bytes', ptr(rollout_state.rnn_states[0][0]),
-                         ptr(self.store['rnn_start_c'][c, 0]), c_size_t(nbytes))
-                    call('mlb_copy_bytes', ptr(rollout_state.rnn_states[1][0]),
-                         ptr(self.store['rnn_start_h'][c, 0]), c_size_t(nbytes))
+                    RH = self._lstm.RH
+                    for l in range(self._lstm.RL):
+                        _copy_state(self.store['rnn_start_c'][c, 0][:, l * RH:(l + 1) * RH], rollout_state.rnn_states[0][l])
+                        _copy_state(self.store['rnn_start_h'][c, 0][:, l * RH:(l + 1) * RH], rollout_state.rnn_states[1][l])
             rollout_state = self.rollout_loop(rollout_state, policy_states, c)
         with profile('Bootstrap Values'):
             self._bootstrap_values(policy_states, rollout_state)
@@ -299,9 +307,9 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         states = None
         if self._lstm is not None:                        # critic_only must not advance the rollout's carry
             states = self._boot_states
-            nbytes = N * self._lstm.RH * 4
-            call('mlb_copy_bytes', ptr(rs.rnn_states[0][0]), ptr(states[0][0]), c_size_t(nbytes))
-            call('mlb_copy_bytes', ptr(rs.rnn_states[1][0]), ptr(states[1][0]), c_size_t(nbytes))
+            for l in range(self._lstm.RL):
+                _copy_state(states[0][l], rs.rnn_states[0][l])
+                _copy_state(states[1][l], rs.rnn_states[1][l])
         # critic column of the head -> bootstrap [1, B, 1] (the greedy actions are discarded)
         if prog.fused_rollout:
             prog.rollout_step_fused(ob, None, N, None, None, self._scratch_actions, None, self.bootstrap,

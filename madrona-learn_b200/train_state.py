@@ -64,7 +64,7 @@ class PolicyTrainState:                                # ml/train_state.py:85-13
 def _tree_to_host(t):
     if isinstance(t, dict):
         return {k: _tree_to_host(v) for k, v in t.items()}
-    return t.detach().cpu().contiguous().numpy()
+    return t.detach().cpu().contiguous().clone()
 
 
 @dataclass
@@ -80,37 +80,36 @@ class TrainStateManager:                               # ml/train_state.py:139-3
         return self
 
     # checkpoint: the reference's key tree (ml/train_state.py:145-164 saves the PolicyState /
-    # PolicyTrainState pytrees: :34-47, :85-99) with every leaf a host array; torch.save stands in
-    # for orbax.  Only arrays / scalars / None are written, so load() runs with weights_only=True;
+    # PolicyTrainState pytrees: :34-47, :85-99) with every leaf a host (CPU) tensor; torch.save stands
+    # in for orbax.  Only tensors / scalars / None are written, so load() runs with weights_only=True;
     # `user_state` (arbitrary user pytree) goes to a separate opt-in pickle next to it.
     def save(self, next_update, path):
         ps, ts = self.policy_states, self.train_states
         prog = ps.program
-        np_ = lambda t: None if t is None else t.detach().cpu().contiguous().numpy()
+        np_ = lambda t: None if t is None else t.detach().cpu().contiguous().clone()
         obs_state = {k: np_(v) for k, v in (ps.obs_preprocess_state or {}).items()}
         est = ts.max_advantage_est_state
         ckpt = {
             'next_update': int(next_update),
             'policy_states': {
                 'params': _tree_to_host(prog.param_tree()),          # flax parameter tree (:34-40)
-                'params_flat': prog.params.cpu().numpy(),            # our arena (what load() restores)
+                'params_flat': np_(prog.params),                     # our arena (what load() restores)
                 'batch_stats': {}, 'obs_preprocess_state': obs_state, 'reward_hyper_params': None,
                 'episode_score': None, 'mmr': None,
             },
             'train_states': {
-                'opt_state': {'m': prog.adam_m.cpu().numpy(), 'v': prog.adam_v.cpu().numpy(),
-                              'count': prog.adam_step.cpu().numpy()},
+                'opt_state': {'m': np_(prog.adam_m), 'v': np_(prog.adam_v), 'count': np_(prog.adam_step)},
                 'value_normalizer_state': np_(ts.value_normalizer_state),
                 'max_advantage_est_state': np_(est),
                 'hyper_params': {k: float(v) for k, v in vars(ts.hyper_params).items()
                                  if isinstance(v, (int, float, bool))},
                 'scaler': None,
-                'update_prng_key': ts.update_prng_key.cpu().numpy(),
+                'update_prng_key': np_(ts.update_prng_key),
                 # per kernel leaf of the parameter tree, None elsewhere (:413-423)
                 'initial_weight_norms': prog.initial_weight_norms_tree(),
                 'initial_weight_norms_flat': {k: float(v) for k, v in ts.initial_weight_norms.items()},
             },
-            'pbt_rng': self.pbt_rng.cpu().numpy(),
+            'pbt_rng': np_(self.pbt_rng),
             'user_state': None,            # the user pytree itself is in <path>.user_state (opt-in pickle)
         }
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
@@ -122,7 +121,7 @@ class TrainStateManager:                               # ml/train_state.py:139-3
         ckpt = torch.load(path, map_location='cpu', weights_only=True)
         ps, ts = self.policy_states, self.train_states
         prog = ps.program
-        t = lambda a: torch.from_numpy(a)
+        t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(a)
         prog.params.copy_(t(ckpt['policy_states']['params_flat']))
         prog.adam_m.copy_(t(ckpt['train_states']['opt_state']['m']))
         prog.adam_v.copy_(t(ckpt['train_states']['opt_state']['v']))

@@ -253,7 +253,7 @@ def test_checkpoint_roundtrip_and_reference_key_tree(mlb, tmp_path):
     assert set(tree) == {'backbone', 'actor', 'critic'}
     net = tree['backbone']['encoder']['net']
     assert {'Dense_0', 'LayerNorm_0'} <= set(net) and set(net['LayerNorm_0']['impl']) == {'scale', 'bias'}
-    assert tree['actor']['impl']['kernel'].shape[1] == sum(BUCKETS) and isinstance(net['Dense_0']['kernel'], np.ndarray)
+    assert tree['actor']['impl']['kernel'].shape[1] == sum(BUCKETS) and torch.is_tensor(net['Dense_0']['kernel'])
     m = mlb
     env2 = m.SyntheticVectorEnv(64, 16, len(BUCKETS), seed=11, p_done=-1.0, device=DEV)
     policy = m.Policy(actor_critic=m.ActorCritic(
