@@ -14,6 +14,8 @@ JSON line; for N > 1 it is launched under torch.distributed.run (one rank per GP
   kernels   per-kernel table: fused forward layer, backward-dx layer, dW GEMM, head GEMM, PPO loss,
             rollout step kernel, optimiser -- us/launch, algorithmic bytes, fraction of the HBM roofline
   f32       (N = 1) the same update with compute_dtype=float32 (the reference's default dtype)
+  cfg4      (N = 1) BASELINE configs[3]: recurrent (LSTM) actor-critic, 16384 worlds x 128 steps, BPTT
+            minibatches, value-normaliser EMA, bf16 tensor-core path
   cfg3      BASELINE configs[2] (MLP 3x512, 65536 worlds x 64 steps) STRONG scaling: 65536/N worlds
             per rank, index-exact global minibatch permutation, gradient all-reduce per minibatch
   dp_check  (N > 1) the fused all-reduce kernel self-check run before timing
@@ -97,6 +99,12 @@ CFG3 = dict(name='cfg3: PPO MLP 3x512, 65536 worlds x 64 steps, 4 epochs x 4 min
             worlds=65536, steps=64, hidden=512, layers=3, epochs=4, minibatches=4)
 
 
+CFG4 = dict(name='cfg4: recurrent actor-critic (MLP 2x256 + LSTM 256), 16384 worlds x 128 steps, 4 BPTT chunks, '
+                 '2 epochs x 4 minibatches, value-normaliser EMA',
+            worlds=16384, steps=128, hidden=256, layers=2, rnn=256, chunks=4, epochs=2, minibatches=4,
+            normalize_values=True)
+
+
 def make_cfg(m, worlds, lr=3e-4, dtype=None, wl=None):
     import torch
     wl = wl or WORKLOAD
@@ -104,18 +112,19 @@ def make_cfg(m, worlds, lr=3e-4, dtype=None, wl=None):
         num_worlds=worlds, num_agents_per_world=1, num_updates=1 << 30,
         actions={'act': m.DiscreteActionsConfig(BUCKETS)}, steps_per_update=wl['steps'], lr=lr,
         algo=m.PPOConfig(num_epochs=wl['epochs'],
-                         minibatch_size=worlds // wl['minibatches'], clip_coef=0.2,
+                         minibatch_size=worlds * wl.get('chunks', 1) // wl['minibatches'], clip_coef=0.2,
                          value_loss_coef=0.5, entropy_coef={'act': 0.01}, max_grad_norm=0.5),
-        num_bptt_chunks=1, gamma=0.99, seed=0, metrics_buffer_size=4, gae_lambda=0.95,
-        dreamer_v3_critic=False, normalize_values=False,
+        num_bptt_chunks=wl.get('chunks', 1), gamma=0.99, seed=0, metrics_buffer_size=4, gae_lambda=0.95,
+        dreamer_v3_critic=False, normalize_values=bool(wl.get('normalize_values', False)),
         compute_dtype=torch.bfloat16 if dtype == 'bf16' else torch.float32)
 
 
 def make_policy(m, wl=None):
     wl = wl or WORKLOAD
+    net = m.models.MLP(wl['hidden'], wl['layers'])
+    enc = m.RecurrentBackboneEncoder(net=net, rnn=m.rnn.LSTM(wl['rnn'], 1)) if wl.get('rnn') else m.BackboneEncoder(net=net)
     return m.Policy(actor_critic=m.ActorCritic(
-        backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(
-            net=m.models.MLP(wl['hidden'], wl['layers']))),
+        backbone=m.BackboneShared(prefix=None, encoder=enc),
         actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(BUCKETS)),
         critic=m.models.DenseLayerCritic()))
 
@@ -526,6 +535,15 @@ def main():
         f32 = dict(value=N * T * kf / secf, unit=UNIT, ms_per_step=secf / kf * 1e3, steps=kf, warmup=3,
                    dtype='f32', note='compute_dtype=float32 (ml/cfg.py:96 default) on the same workload')
 
+    # ---- cfg4: recurrent (LSTM) actor-critic with BPTT minibatches, N = 1 only --------------
+    cfg4 = None
+    if not args.no_extras and world == 1 and args.dtype == 'bf16':
+        k4 = max(3, min(args.steps, 6))
+        sec4, _ = run_arm(torch, m, dev, CFG4, CFG4['worlds'], 'bf16', None, rank, k4, 3)
+        cfg4 = dict(workload=CFG4['name'], value=CFG4['worlds'] * CFG4['steps'] * k4 / sec4, unit=UNIT,
+                    ms_per_step=sec4 / k4 * 1e3, steps=k4, warmup=3, dtype='bf16',
+                    note='LSTM products on tcgen05: fused [x|h] GEMM + cell epilogue per step (mlb_lstm_step_tc)')
+
     out = None
     if rank == 0:
         table, roof = [], None
@@ -573,7 +591,7 @@ def main():
             'gpu_launches_note': 'C-ABI enqueue calls (each >= 1 kernel) per update x steps; replayed from '
                                  'the captured CUDA graph after the first eager update',
             'clocks': clocks, 'roofline': roof, 'kernels': table, 'gae': gae, 'cpu_baseline': cpu,
-            'f32': f32, 'cfg3': cfg3, 'dp_check': dp_check,
+            'f32': f32, 'cfg3': cfg3, 'cfg4': cfg4, 'dp_check': dp_check,
         }
         print(json.dumps(out))
     if world > 1:
