@@ -248,6 +248,10 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
         K.ema_scan(train_state.value_normalizer_state, ws.mb_ret, vn.decay, vn.eps, ws.vn_params)
 
     flags = (1 if cfg.algo.clip_value_loss else 0) | (2 if cfg.algo.huber_value_loss else 0)
+    # The loss kernel averages the value loss over ITS rows; the action / entropy terms carry explicit
+    # 1 / (global rows) scales.  Data-parallel: the gradient all-reduce SUMS the ranks' arenas, so the value
+    # term must be this rank's share of the GLOBAL mean too (rows_local / rows_global of its local mean).
+    vscale = 1.0 if dist_ctx is None else float(rows) / float(ws.rows_global)
     keys = ['obs', 'actions', 'log_probs', score_key, 'returns']
     if cfg.algo.clip_value_loss:
         keys.append('values')
@@ -311,7 +315,7 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
                      ptr(ws.mb_adv[mbi]) if normalize_scores else ptr(None),
                      ptr(ws.vn_params[mbi]) if vn is not None else ptr(None),
                      prog._buckets_c, ws.obj_scale, ws.ent_scale, c_int(prog.A), c_ll(rows), c_ll(M),
-                     c_float(hp.clip_coef), c_float(hp.value_loss_coef), c_int(flags | prog.loss_flags),
+                     c_float(hp.clip_coef), c_float(hp.value_loss_coef * vscale), c_int(flags | prog.loss_flags),
                      ptr(tw['dhead']), ptr(prog.head_bias_grad()), ptr(tw['stats_out']), ptr(tw['loss_ws']),
                      c_size_t(tw['loss_ws'].numel()), prog._bins_c, c_int(prog.V))
                 prog.backward(mb['obs'].view(rows, prog.obs_dim), rows, seq)
