@@ -141,6 +141,14 @@ class _PPOWorkspace:
         if prog.lstm is not None:
             self.mb['rnn_start_c'] = e(M, prog.lstm.RH * prog.lstm.RL)      # layers side by side
             self.mb['rnn_start_h'] = e(M, prog.lstm.RH * prog.lstm.RL)
+        # Double-buffered minibatches: the gather of minibatch k+1 (NVLink peer reads in the index-exact
+        # data-parallel mode) runs on a side stream underneath the forward / backward of minibatch k.
+        # Default on for index-exact data-parallel runs, MLB_PREFETCH_GATHER=1/0 forces it on / off.
+        pf = os.environ.get('MLB_PREFETCH_GATHER')
+        self.prefetch = self.mode == 'default' and (self.index_exact if pf is None else pf != '0')
+        self.mb_sets = [self.mb]
+        if self.prefetch:
+            self.mb_sets.append({k: torch.empty_like(v) for k, v in self.mb.items()})
         self.Tp = Tp
         if self.mode != 'default':
             npad = K.sort_pad(J)
@@ -256,25 +264,26 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
     if cfg.algo.clip_value_loss:
         keys.append('values')
     tw = prog.train_ws(rows)
-    mb = ws.mb
-    seq = None
     if prog.lstm is not None:
         keys.append('dones')
-        seq = dict(Tp=Tp, M=M, ends=mb['dones'].view(Tp, M), **_layer_states(prog.lstm, mb))
+    nset = len(ws.mb_sets)
+    if prog.tc and nset > 1 and getattr(ws, 'x_sets', None) is None:
+        ws.x_sets = [tw['x'], torch.empty_like(tw['x'])]      # the bf16 observation copy the gather writes
     leaf_names = list(dict.fromkeys(keys))
     if ws.index_exact and getattr(ws, 'peer_tab', None) is None:
         ws.peer_tab = dist_ctx.peer_store_table(leaf_names)
-        ws.peer_tab_rnn = dist_ctx.peer_store_table(['rnn_start_c', 'rnn_start_h']) if seq is not None else None
+        ws.peer_tab_rnn = dist_ctx.peer_store_table(['rnn_start_c', 'rnn_start_h']) if prog.lstm is not None else None
 
-    def gather(e, k):
+    def gather(e, k, mb, xbf):
+        """Fill the minibatch buffer set `mb` (and the bf16 observation copy `xbf`) with minibatch (e, k)."""
         if ws.index_exact:
             # this rank's slice of the global minibatch; rows are fetched from their owners' stores
             lo = k * ws.Mp + dist_ctx.rank * M
             idx = ws.perm[e, lo:lo + M]
-            leaves = [(st[name], mb[name], tw['x'] if (name == 'obs' and prog.tc) else None)
+            leaves = [(st[name], mb[name], xbf if (name == 'obs' and prog.tc) else None)
                       for name in leaf_names]
             K.mb_gather_multi_peer(leaves, ws.peer_tab, dist_ctx.world_size, idx, C, Tp, B)
-            if seq is not None:
+            if prog.lstm is not None:
                 K.mb_gather_multi_peer([(st['rnn_start_c'], mb['rnn_start_c'], None),
                                         (st['rnn_start_h'], mb['rnn_start_h'], None)],
                                        ws.peer_tab_rnn, dist_ctx.world_size, idx, C, 1, B)
@@ -284,27 +293,37 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
         for name in leaf_names:
             src = st[name][:, :, 0]
             leaves.append((src.view(torch.uint8) if src.dtype == torch.bool else src, mb[name],
-                           tw['x'] if (name == 'obs' and prog.tc) else None))
+                           xbf if (name == 'obs' and prog.tc) else None))
         K.mb_gather_multi(leaves, idx, C, Tp, B)
-        if seq is not None:
+        if prog.lstm is not None:
             K.mb_gather_rnn(st['rnn_start_c'][:, 0], idx, C, B, mb['rnn_start_c'])
             K.mb_gather_rnn(st['rnn_start_h'][:, 0], idx, C, B, mb['rnn_start_h'])
 
-    # The gather of minibatch k+1 (HBM-bound) runs on a side stream underneath the gradient
-    # all-reduce + optimiser kernels of minibatch k (latency-bound); both streams are part of the
-    # captured update graph.  Opt-in (MLB_PREFETCH_GATHER=1): measured neutral-to-negative on 1 and 2
-    # GPUs (6.68 vs 6.55 ms, 7.00 vs 6.87 ms); only when the optimize_metrics hook is the default no-op,
-    # because the hook is handed the minibatch buffers the prefetch overwrites.
-    cb_fn = getattr(user_metrics_cb, '__func__', user_metrics_cb)
-    prefetch = (os.environ.get('MLB_PREFETCH_GATHER', '0') != '0' and
-                getattr(cb_fn, '__qualname__', '') == 'TrainHooks.optimize_metrics')
+    # Minibatch k+1 is gathered on a side stream into the OTHER buffer set while minibatch k runs its forward /
+    # loss / backward / all-reduce / optimiser on the main stream; both streams are part of the captured update
+    # graph.  The side stream waits for everything the main stream has enqueued so far (minibatch k-1, the last
+    # reader of the set being overwritten) before it starts.
+    prefetch = ws.prefetch and nset > 1
     main = torch.cuda.current_stream()
     order = [(e, k) for e in range(E) for k in range(nmb)]
+    xs = getattr(ws, 'x_sets', None) or [tw.get('x') if prog.tc else None] * nset
     for it, (e, k) in enumerate(order):
             mbi = e * nmb + k
+            mb, xbf = ws.mb_sets[it % nset], xs[it % nset]
             if it == 0 or not prefetch:
                 with profile('Gather Minibatch'):
-                    gather(e, k)
+                    gather(e, k, mb, xbf)
+            else:
+                main.wait_stream(ws.side)                     # the prefetch of this minibatch has landed
+            if prefetch and it + 1 < len(order):
+                ws.side.wait_stream(main)
+                with torch.cuda.stream(ws.side):
+                    gather(*order[it + 1], ws.mb_sets[(it + 1) % nset], xs[(it + 1) % nset])
+            if prog.tc:
+                tw['x'] = xbf                                 # layer 0's A operand / dW operand of this minibatch
+            seq = None
+            if prog.lstm is not None:
+                seq = dict(Tp=Tp, M=M, ends=mb['dones'].view(Tp, M), **_layer_states(prog.lstm, mb))
             with profile('AC Forward'):
                 head = prog.forward_train(mb['obs'].view(rows, prog.obs_dim), rows, seq, x_ready=prog.tc)
             with profile('Optimize'):
@@ -320,11 +339,6 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
                      c_size_t(tw['loss_ws'].numel()), prog._bins_c, c_int(prog.V))
                 prog.backward(mb['obs'].view(rows, prog.obs_dim), rows, seq)
                 grad_scale = 1.0
-                nxt = order[it + 1] if (prefetch and it + 1 < len(order)) else None
-                if nxt is not None:
-                    ws.side.wait_stream(main)
-                    with torch.cuda.stream(ws.side):
-                        gather(*nxt)
                 reduced = None
                 if dist_ctx is not None:                      # sum over ranks; scales already global
                     if dist_ctx.fused:
@@ -333,10 +347,10 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
                         dist_ctx.allreduce_grads(prog.grads)
                 prog.optimizer_step(tx['lr'], tx['max_grad_norm'], grad_scale, tx['b1'], tx['b2'], tx['eps'],
                                     reduced=reduced)
-                if nxt is not None:
-                    main.wait_stream(ws.side)
             with profile('Metrics Callback'):
                 metrics = user_metrics_cb(metrics, e, mb, policy_state, train_state)
+    if prefetch:
+        main.wait_stream(ws.side)
     with profile('Record Metrics'):
         # per-minibatch records overwrite the same slot: the last minibatch wins (App. C.4)
         dst = metrics.slot('Loss', 5)

@@ -208,6 +208,47 @@ def test_tc_policy_forward_backward_vs_oracle(mlb, D, H, L, rows, jitter):
     assert torch.equal(prog.w_t[0], k0.t().contiguous().to(torch.bfloat16))
 
 
+@pytest.mark.parametrize('dt,lstm', [(torch.bfloat16, False), (torch.float32, False), (torch.bfloat16, True)])
+def test_prefetched_minibatch_gather_is_bit_identical(mlb, monkeypatch, dt, lstm):
+    """The double-buffered minibatch pipeline (gather of minibatch k+1 on a side stream underneath minibatch k;
+    the default of index-exact data-parallel runs, forced here with MLB_PREFETCH_GATHER=1) must not change a bit
+    of the update: eager and CUDA-graph replay, feed-forward and recurrent."""
+    import madrona_learn_b200 as m
+    buckets = [4, 8, 5, 5, 2, 2]
+    out = {}
+    for tag in ('0', '0b', '1'):
+        pf = tag[0]
+        monkeypatch.setenv('MLB_PREFETCH_GATHER', pf)
+        env = m.SyntheticVectorEnv(512, 64, 6, seed=3, p_done=1 / 16, device=DEV)
+        enc = (m.RecurrentBackboneEncoder(net=m.models.MLP(128, 1), rnn=m.rnn.LSTM(64, 1)) if lstm
+               else m.BackboneEncoder(net=m.models.MLP(128, 2)))
+        policy = m.Policy(actor_critic=m.ActorCritic(
+            backbone=m.BackboneShared(prefix=None, encoder=enc),
+            actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(buckets)),
+            critic=m.models.DenseLayerCritic()))
+        cfg = m.TrainConfig(num_worlds=512, num_agents_per_world=1, num_updates=4,
+                            actions={'act': m.DiscreteActionsConfig(buckets)}, steps_per_update=16, lr=3e-4,
+                            algo=m.PPOConfig(num_epochs=2, minibatch_size=128, clip_coef=0.2, value_loss_coef=0.5,
+                                             entropy_coef={'act': 0.01}, max_grad_norm=0.5),
+                            num_bptt_chunks=2 if lstm else 1, gamma=0.99, seed=4, metrics_buffer_size=2,
+                            gae_lambda=0.95, dreamer_v3_critic=False, compute_dtype=dt)
+        mgr = m.init_training(DEV, cfg, env.sim_fns(), policy, None, verbose=False)
+        assert mgr.ppo_ws is None or True
+        for _ in range(4):                         # eager, capture, two replays
+            mgr.update_iter()
+        torch.cuda.synchronize()
+        assert len(mgr.ppo_ws.mb_sets) == (2 if pf == '1' else 1)
+        out[tag] = mgr.state.policy_states.program.params.clone()
+    # run-to-run noise floor of the same configuration (split-K fp32 atomics make the bf16 path order-dependent)
+    noise = (out['0'] - out['0b']).abs().max().item()
+    d = (out['0'] - out['1']).abs().max().item()
+    print('PARITY prefetch', dict(dtype=str(dt), lstm=lstm, run_to_run=noise, prefetch_vs_not=d))
+    if noise == 0.0:
+        assert torch.equal(out['0'], out['1'])
+    else:
+        assert d <= 4 * noise + 1e-7, (d, noise)
+
+
 def test_tc_update_iter_runs_and_tracks_fp32(mlb, monkeypatch):
     """Same seeds, fp32 vs bf16 path: the rollout statistics and the loss stay close."""
     import madrona_learn_b200 as m

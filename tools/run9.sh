@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15
+timeout 600 python -m pytest tests/test_tc_gpu.py -m gpu -q -s -k "prefetched" 2>&1 | grep "PARITY\|passed\|failed\|Error" | tail -10

@@ -6,8 +6,8 @@ tail -c 600 gpurun_out/r2_bench_8gpu.err
 python - <<PY
 import json
 try:
-    b=json.load(open('gpurun_out/r2_bench_8gpu.json'))
-    print({k:b[k] for k in ('value','ms_per_step','n_gpus','dp_check')}, b['e2e']['value'], b['cfg3'], b['config']['permutation'], b['config']['fused_allreduce'])
+    b=json.loads([l for l in open('gpurun_out/r2_bench_8gpu.json') if l.startswith('{')][-1])
+    print({k:b[k] for k in ('value','ms_per_step','n_gpus','dp_check')}, b['e2e']['value'], b['cfg3']['value'], b['cfg3']['ms_per_step'], b['config']['permutation'], b['config']['fused_allreduce'])
 except Exception as e:
     print('no json', e)
 PY
