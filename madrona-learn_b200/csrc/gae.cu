@@ -12,6 +12,8 @@
 // in flight (HBM latency hiding; the recurrence itself is 4 flops per element).
 // Arithmetic is deliberately NOT contracted into FMAs (__fmul_rn/__fadd_rn) so the result is
 // bit-identical to the float32 reference evaluated op by op.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -272,6 +274,8 @@ ScanPlan plan_scan(long long N, bool align16) {
     else p.vec = 1;
     const long long threads = N / p.vec;
     p.block = threads >= (long long)MLB_NUM_SMS * 512 ? 256 : (threads >= MLB_NUM_SMS * 128 ? 128 : 64);
+    static const int forced = [] { const char* v = getenv("MLB_GAE_BLOCK"); return v ? atoi(v) : 0; }();
+    if (forced >= 32 && forced <= 1024 && forced % 32 == 0) p.block = forced;
     p.grid = mlb_cdiv(threads, p.block);
     // fewer than ~1024 threads per SM: a thread must keep more bytes in flight to cover the HBM
     // latency-bandwidth product (measured r2: N = 64K columns, U = 8 -> 0.69 of peak) -> 16-step chunks

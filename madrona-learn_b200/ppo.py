@@ -142,7 +142,7 @@ class _PPOWorkspace:
             self.mb['rnn_start_c'] = e(M, prog.lstm.RH * prog.lstm.RL)      # layers side by side
             self.mb['rnn_start_h'] = e(M, prog.lstm.RH * prog.lstm.RL)
         # Double-buffered minibatches: the gather of minibatch k+1 (NVLink peer reads in the index-exact
-        # data-parallel mode) runs on a side stream underneath the forward / backward of minibatch k.
+        # data-parallel mode) runs on a side stream underneath the all-reduce + optimiser of minibatch k.
         # Default on for index-exact data-parallel runs, MLB_PREFETCH_GATHER=1/0 forces it on / off.
         pf = os.environ.get('MLB_PREFETCH_GATHER')
         self.prefetch = self.mode == 'default' and (self.index_exact if pf is None else pf != '0')
@@ -299,10 +299,8 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
             K.mb_gather_rnn(st['rnn_start_c'][:, 0], idx, C, B, mb['rnn_start_c'])
             K.mb_gather_rnn(st['rnn_start_h'][:, 0], idx, C, B, mb['rnn_start_h'])
 
-    # Minibatch k+1 is gathered on a side stream into the OTHER buffer set while minibatch k runs its forward /
-    # loss / backward / all-reduce / optimiser on the main stream; both streams are part of the captured update
-    # graph.  The side stream waits for everything the main stream has enqueued so far (minibatch k-1, the last
-    # reader of the set being overwritten) before it starts.
+    # Minibatch k+1 is gathered on a side stream into the OTHER buffer set while minibatch k runs its gradient
+    # all-reduce and optimiser on the main stream; both streams are part of the captured update graph.
     prefetch = ws.prefetch and nset > 1
     main = torch.cuda.current_stream()
     order = [(e, k) for e in range(E) for k in range(nmb)]
@@ -315,10 +313,6 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
                     gather(e, k, mb, xbf)
             else:
                 main.wait_stream(ws.side)                     # the prefetch of this minibatch has landed
-            if prefetch and it + 1 < len(order):
-                ws.side.wait_stream(main)
-                with torch.cuda.stream(ws.side):
-                    gather(*order[it + 1], ws.mb_sets[(it + 1) % nset], xs[(it + 1) % nset])
             if prog.tc:
                 tw['x'] = xbf                                 # layer 0's A operand / dW operand of this minibatch
             seq = None
@@ -339,6 +333,13 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
                      c_size_t(tw['loss_ws'].numel()), prog._bins_c, c_int(prog.V))
                 prog.backward(mb['obs'].view(rows, prog.obs_dim), rows, seq)
                 grad_scale = 1.0
+                if prefetch and it + 1 < len(order):
+                    # the persistent layer kernels own every SM's registers, so a gather issued earlier would only
+                    # displace them; the all-reduce and optimiser kernels that follow are latency-bound and leave
+                    # the SMs (and NVLink) idle: the next minibatch's peer gather runs underneath THEM
+                    ws.side.wait_stream(main)
+                    with torch.cuda.stream(ws.side):
+                        gather(*order[it + 1], ws.mb_sets[(it + 1) % nset], xs[(it + 1) % nset])
                 reduced = None
                 if dist_ctx is not None:                      # sum over ranks; scales already global
                     if dist_ctx.fused:
