@@ -174,6 +174,13 @@ int mlb_ppo_permutations_of(void* stream, uint32_t* key, const int32_t* values, 
 long long mlb_sort_pad(long long n);
 int mlb_sort_u64(void* stream, unsigned long long* keys, long long n_pad);
 
+/* Index-exact data-parallel mode: this rank's M trajectory ids of every GLOBAL minibatch                 */
+/* perm[e, k*world*M : (k+1)*world*M] (global ids j = c*(world*B) + r*B + b, perm identical on all ranks): */
+/* every rank keeps the ids it owns (permutation order, at most M); the surplus of over-represented ranks */
+/* fills the deficits of the others, both in rank order -- the union over ranks is exactly the global     */
+/* minibatch, and only the binomial imbalance is fetched from peers.  out [E, nmb, M].                    */
+int mlb_dp_assign_minibatches(void* stream, const int32_t* perm, long long perm_ld, int E, int nmb,
+                              int world, int rank, long long B, long long M, int32_t* out);
 /* ------------------------------------------------------------------------------------ */
 /* K5: minibatch gather straight from the [C, T', P=1, B, *leaf] store                      */
 /* (RolloutData.minibatch ml/rollouts.py:319-329 composed with the relayout :788-804):      */

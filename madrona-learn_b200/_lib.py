@@ -97,6 +97,7 @@ SIGNATURES = {
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
     'mlb_mb_gather_multi': (c_int, [P, P, c_int, P, c_int, c_int, c_ll, c_ll]),
     'mlb_mb_gather_multi_peer': (c_int, [P, P, c_int, P, c_int, P, c_int, c_int, c_ll, c_ll]),
+    'mlb_dp_assign_minibatches': (c_int, [P, P, c_ll, c_int, c_int, c_int, c_int, c_ll, c_ll, P]),
     'mlb_reorder_chunks_workspace': (c_size_t, [c_ll, c_int]),
     'mlb_reorder_chunks': (c_int, [P, P, c_ll, c_int, c_int, c_ll, P, P, P, c_size_t]),
     'mlb_gather_rows_clip': (c_int, [P, P, P, P, c_ll, c_ll, c_ll]),

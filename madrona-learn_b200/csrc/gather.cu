@@ -151,6 +151,93 @@ gather_multi_peer_kernel(const __grid_constant__ LeafPack P, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Owner-affine split of the global minibatches (index-exact data-parallel mode).
+//
+// Global minibatch (e, k) = perm[e, k*Mp : (k+1)*Mp] (Mp = world * M trajectory ids, identical on every
+// rank).  WHICH rank trains on which of its trajectories does not change the update (the loss is a sum
+// over the minibatch, its statistics are global), so instead of handing rank r the r-th contiguous slice
+// -- (world-1)/world of whose rows live on other GPUs -- every rank keeps the trajectories it OWNS (in
+// permutation order, at most M) and only the binomial imbalance moves: the surplus of the over-represented
+// ranks, in rank order, fills the deficits of the under-represented ones, in rank order.  Every rank
+// evaluates the same assignment and extracts its own M ids, so the union over ranks is exactly the
+// reference's minibatch.  Expected remote fraction ~ sqrt((world-1) / (2 pi M)) instead of (world-1)/world.
+// One block per (epoch, minibatch); owner(j) = (j mod (world*B)) / B.
+// ------------------------------------------------------------------------------------------
+constexpr int ASSIGN_THREADS = 1024;
+
+__global__ void __launch_bounds__(ASSIGN_THREADS)
+dp_assign_kernel(const int32_t* __restrict__ perm, long long perm_ld, int nmb, int world, int rank, int B, int M,
+                 int32_t* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ int wsum[32][MLB_MAX_PEERS];          // per-warp totals per owner
+    __shared__ int cnt[MLB_MAX_PEERS], sur_pre[MLB_MAX_PEERS + 1], def_pre[MLB_MAX_PEERS + 1];
+    const int e = blockIdx.x / nmb, k = blockIdx.x - e * nmb;
+    const int Mp = world * M;
+    const int32_t* ids = perm + (long long)e * perm_ld + (long long)k * Mp;
+    int32_t* o = out + ((long long)e * nmb + k) * M;
+    const int ipt = (Mp + ASSIGN_THREADS - 1) / ASSIGN_THREADS;         // ids per thread (contiguous: stable)
+    const int lo = threadIdx.x * ipt, hi = min(Mp, lo + ipt);
+    const int Bg = world * B;
+    int local[MLB_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < MLB_MAX_PEERS; ++r) local[r] = 0;
+    for (int i = lo; i < hi; ++i) {
+        const int ow = (ids[i] % Bg) / B;
+#pragma unroll
+        for (int r = 0; r < MLB_MAX_PEERS; ++r) local[r] += (ow == r);
+    }
+    // exclusive scan over threads, per owner: warp shuffles, then the warp totals through shared memory
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int pre[MLB_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < MLB_MAX_PEERS; ++r) {
+        int v = local[r];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += t;
+        }
+        pre[r] = v - local[r];
+        if (lane == 31) wsum[warp][r] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < MLB_MAX_PEERS) {
+        int run = 0;
+        for (int w = 0; w < ASSIGN_THREADS / 32; ++w) { const int t = wsum[w][threadIdx.x]; wsum[w][threadIdx.x] = run; run += t; }
+        cnt[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, d = 0;
+        for (int r = 0; r < world; ++r) {
+            sur_pre[r] = a; def_pre[r] = d;
+            a += max(cnt[r] - M, 0);
+            d += max(M - cnt[r], 0);
+        }
+        sur_pre[world] = a; def_pre[world] = d;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < MLB_MAX_PEERS; ++r) pre[r] += wsum[warp][r];
+    for (int i = lo; i < hi; ++i) {
+        const int id = ids[i];
+        const int ow = (id % Bg) / B;
+        int p = 0;
+#pragma unroll
+        for (int r = 0; r < MLB_MAX_PEERS; ++r) if (ow == r) { p = pre[r]; pre[r] += 1; }
+        if (p < M) {
+            if (ow == rank) o[p] = id;                              // kept by its owner
+        } else {
+            const int q = sur_pre[ow] + (p - M);                    // q-th element of the global surplus list
+            int dst = 0;
+            while (dst + 1 < world && def_pre[dst + 1] <= q) ++dst; // the deficit rank it goes to
+            if (dst == rank) o[min(cnt[dst], M) + (q - def_pre[dst])] = id;
+        }
+    }
+}
+
 }  // namespace
 
 MLB_API int mlb_mb_gather_multi(void* stream, const mlb_gather_leaf* leaves_host, int num_leaves,
@@ -242,4 +329,15 @@ MLB_API int mlb_mb_gather_rnn(void* stream, const void* store, const int32_t* id
     MLB_REQUIRE(store && idx && out && C > 0 && B > 0 && M > 0 && row_bytes > 0);
     // [C, B, row] is the Tp == 1 case of the step store: out[m] = store[j/B, j%B] = flat[j]
     return gather_dispatch(mlb_stream(stream), store, idx, out, 1, B, M, row_bytes);
+}
+
+// out [E, nmb, M]: this rank's trajectory ids of every global minibatch (see dp_assign_kernel).
+MLB_API int mlb_dp_assign_minibatches(void* stream, const int32_t* perm, long long perm_ld, int E, int nmb,
+                                      int world, int rank, long long B, long long M, int32_t* out) {
+    MLB_REQUIRE(perm && out && E > 0 && nmb > 0 && world >= 1 && world <= MLB_MAX_PEERS && rank >= 0 && rank < world);
+    MLB_REQUIRE(B > 0 && M > 0 && (long long)world * M < (1ll << 30) && (long long)world * B < (1ll << 31) &&
+                perm_ld >= (long long)nmb * world * M);
+    cudaError_t e = launch_pdl(dp_assign_kernel, dim3((unsigned)(E * nmb)), dim3(ASSIGN_THREADS), 0, mlb_stream(stream),
+                               perm, perm_ld, nmb, world, rank, (int)B, (int)M, out);
+    return e == cudaSuccess ? MLB_OK : (int)e;
 }

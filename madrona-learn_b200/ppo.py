@@ -122,6 +122,11 @@ class _PPOWorkspace:
         self.Jp = J * R                                  # length of one permutation
         self.Mp = M * R                                  # minibatch width in the permutation
         self.perm = e(E, self.Jp, dtype=torch.int32)
+        # index-exact mode: this rank's ids of every global minibatch.  'owner' (default): every rank keeps the
+        # trajectories it owns, only the binomial imbalance is fetched from peers (mlb_dp_assign_minibatches);
+        # 'slice' (MLB_DP_ASSIGN=slice): the rank-th contiguous M-slice of the permutation.
+        self.assign = os.environ.get('MLB_DP_ASSIGN', 'owner') if self.index_exact else None
+        self.idx_local = e(E, J // M, M, dtype=torch.int32) if self.assign == 'owner' else None
         self.perm_ws = torch.empty(K.lib().mlb_ppo_permutations_workspace(E, self.Jp) + 16,
                                    dtype=torch.uint8, device=dev)
         self.tm_adv = e(J, 2, dtype=torch.float64)
@@ -208,6 +213,9 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
 
     with profile('Compute Minibatch Indices'):
         K.ppo_permutations(train_state.update_prng_key, E, ws.Jp, partitionable, ws.perm, ws.perm_ws)
+        if ws.idx_local is not None:
+            call('mlb_dp_assign_minibatches', ptr(ws.perm), c_ll(ws.Jp), c_int(E), c_int(nmb),
+                 c_int(dist_ctx.world_size), c_int(dist_ctx.rank), c_ll(B), c_ll(M), ptr(ws.idx_local))
 
     # per-minibatch statistics for ALL minibatches of the update (App. C.1)
     score_key = 'advantages' if cfg.compute_advantages else 'returns'
@@ -279,7 +287,7 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
         if ws.index_exact:
             # this rank's slice of the global minibatch; rows are fetched from their owners' stores
             lo = k * ws.Mp + dist_ctx.rank * M
-            idx = ws.perm[e, lo:lo + M]
+            idx = ws.idx_local[e, k] if ws.idx_local is not None else ws.perm[e, lo:lo + M]
             leaves = [(st[name], mb[name], xbf if (name == 'obs' and prog.tc) else None)
                       for name in leaf_names]
             K.mb_gather_multi_peer(leaves, ws.peer_tab, dist_ctx.world_size, idx, C, Tp, B)

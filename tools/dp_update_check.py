@@ -1,8 +1,9 @@
 """Multi-GPU parity of one whole data-parallel update (launched by torchrun, one rank per GPU):
 
-  1. index-exact minibatches: the R-rank gather of every rank's slice of global minibatch (e, k),
-     concatenated over ranks, equals BIT FOR BIT the 1-GPU gather of perm[e, k*M:(k+1)*M] from the
-     concatenated rollout store (ml/ppo.py:437-466 on the concatenated data);
+  1. index-exact minibatches: the ranks' trajectory-id lists of global minibatch (e, k) partition
+     perm[e, k*Mg:(k+1)*Mg] exactly, and the rows every rank gathers (from its own store or over NVLink from
+     the owner's) equal BIT FOR BIT the 1-GPU gather of the same trajectories from the concatenated rollout
+     store (ml/ppo.py:437-466 on the concatenated data);
   2. the R-rank `update_iter` (worlds sharded, per-minibatch gradient all-reduce through the fused
      NVLink / NVLS kernel, global z-score statistics) equals the 1-GPU update on the concatenated
      rollout: same permutations, parameters rel-L2 <= 1e-5 (fp32 path; only summation order differs).
@@ -90,7 +91,17 @@ def main():
         checked = 0
         for (e, k) in ((0, 0), (E - 1, C * Ng // Mg - 1)):
             lo = k * Mg + rank * M
-            idx = perm[e, lo:lo + M].contiguous()
+            idx = (ws.idx_local[e, k] if ws.idx_local is not None else perm[e, lo:lo + M]).contiguous()
+            # the ranks' id lists partition the global minibatch perm[e, k*Mg:(k+1)*Mg] exactly
+            ids_all = [torch.empty_like(idx) for _ in range(world)]
+            dist.all_gather(ids_all, idx)
+            got_ids = torch.cat(ids_all)
+            ref_ids = perm[e, k * Mg:(k + 1) * Mg]
+            assert torch.equal(got_ids.sort().values, ref_ids.sort().values), (case, e, k, 'id multiset differs')
+            owners = (idx % (world * N)) // N
+            remote_frac = float((owners != rank).float().mean())
+            order = got_ids.sort().indices                         # position of every global id in the R-rank concat
+            ref_order = ref_ids.sort().indices
             leaves = [(mgr.rollout_mgr.store[n], ws.mb[n], None) for n in names]
             K.mb_gather_multi_peer(leaves, ctx.peer_store_table(names), world, idx, C, Tp, N)
             torch.cuda.synchronize()
@@ -98,9 +109,10 @@ def main():
                 mine = ws.mb[n].clone()
                 parts = [torch.empty_like(mine) for _ in range(world)]
                 dist.all_gather(parts, mine)
-                got = torch.cat(parts, dim=1)                                  # [T', Mg, *]
-                ref = K.mb_gather(gstore[n][:, :, 0].contiguous(), perm[e, k * Mg:(k + 1) * Mg].contiguous(), C, Tp, Ng)
-                assert torch.equal(got.view(torch.uint8), ref.view(torch.uint8)), (case, n, e, k)
+                got = torch.cat(parts, dim=1)                                  # [T', Mg, *] in R-rank order
+                ref = K.mb_gather(gstore[n][:, :, 0].contiguous(), ref_ids.contiguous(), C, Tp, Ng)
+                # same trajectory -> same bytes, whichever rank trained on it
+                assert torch.equal(got[:, order].contiguous().view(torch.uint8), ref[:, ref_order].contiguous().view(torch.uint8)), (case, n, e, k)
                 checked += 1
         # ---- (2) the update == the 1-GPU update on the concatenated rollout ---------------------------
         one, cfg1 = make(m, dev, dtype=dtype, seed=100, dist_ctx=None,
@@ -130,6 +142,7 @@ def main():
             vb = one.state.train_states.value_normalizer_state[:5]
             assert torch.allclose(va, vb, rtol=1e-5, atol=1e-7), (va, vb)
         report[case] = dict(world=world, fused_allreduce=bool(ctx.fused), nvls=bool(getattr(ctx, 'nvls', False)),
+                            assign=ws.assign, remote_row_fraction=remote_frac,
                             minibatch_leaves_bit_exact=checked, params_rel_l2=rel, delta_rel_l2=rel_delta)
         del mgr, one
         dist.barrier()

@@ -1,13 +1,14 @@
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
 timeout 600 python -m pytest tests/test_dp_gpu.py -m gpu -q -k "8" 2>&1 | tail -4 | tee gpurun_out/r2_pytest_dp_8gpu.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_8gpu.json 2> gpurun_out/r2_bench_8gpu.err; echo "bench8 rc=$?"
-tail -c 600 gpurun_out/r2_bench_8gpu.err
-python - <<PY
+for n in 8 4; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_${n}gpu.json 2> gpurun_out/r2_bench_${n}gpu.err; echo "bench$n rc=$?"
+  python - <<PY
 import json
 try:
-    b=json.loads([l for l in open('gpurun_out/r2_bench_8gpu.json') if l.startswith('{')][-1])
+    b=json.loads([l for l in open('gpurun_out/r2_bench_${n}gpu.json') if l.startswith('{')][-1])
     print({k:b[k] for k in ('value','ms_per_step','n_gpus','dp_check')}, b['e2e']['value'], b['cfg3']['value'], b['cfg3']['ms_per_step'], b['config']['permutation'], b['config']['fused_allreduce'])
 except Exception as e:
     print('no json', e)
 PY
+done
