@@ -104,3 +104,24 @@ def compute_reorder_chunks(assignments, P, C, B):
     to_sim = np.empty(S, np.int32)
     to_sim[sort_idxs] = pos
     return to_policy, to_sim
+
+
+def dp_assign_minibatch(ids, world, B, M):
+    """Owner-affine split of one GLOBAL minibatch `ids` (world*M global trajectory ids j = c*(world*B) + r*B + b,
+    i.e. a slice of the reference's permutation, ml/ppo.py:445-463 on the concatenated rollout) into `world`
+    lists of M ids (the data-parallel extension; not in the single-device reference): every rank
+    keeps the ids it owns, in order, at most M; the surplus of the over-represented ranks (rank order, then
+    list order) fills the deficits of the others (rank order).  The union is `ids` exactly."""
+    import numpy as np
+    ids = np.asarray(ids)
+    owner = (ids % (world * B)) // B
+    own = [ids[owner == r] for r in range(world)]
+    keep = [o[:M] for o in own]
+    surplus = np.concatenate([o[M:] for o in own]) if world else ids[:0]
+    out, q = [], 0
+    for r in range(world):
+        need = M - len(keep[r])
+        out.append(np.concatenate([keep[r], surplus[q:q + need]]).astype(np.int32))
+        q += need
+    assert q == len(surplus)
+    return out

@@ -3,7 +3,7 @@ single-GPU boxes; world > 2 selects the NVLS `multimem` all-reduce variant):
   * tools/dp_allreduce_check.py -- the fused NVLink gradient all-reduce + global-norm kernel: bit-exact
     against the rank-ordered fp32 sum (peer-load variant) / identical on all ranks and fp32-close
     (NVLS), equal to NCCL to fp32 rounding, CUDA-graph replay;
-  * tools/dp_update_check.py -- index-exact global minibatch permutation (R-rank minibatches ==
+  * tools/dp_update_check.py -- index-exact global minibatch permutation (the ranks' owner-affine id lists partition every global minibatch; R-rank rows ==
     1-GPU minibatches bit for bit) and the R-rank update_iter == the 1-GPU update on the
     concatenated rollout (parameters rel-L2 <= 1e-5, fp32)."""
 import os

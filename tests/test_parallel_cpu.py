@@ -98,3 +98,30 @@ def test_data_parallel_equals_single_process(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), f'ok{r}')) for r in range(world))
+
+
+def test_dp_assign_oracle_partitions_the_global_minibatch():
+    """oracle/layouts.dp_assign_minibatch (the checker of mlb_dp_assign_minibatches): the ranks' lists partition
+    the global minibatch, every rank holds exactly M ids, a rank never fetches remotely while it still owns
+    unassigned ids, and the remote fraction of a random permutation is the binomial imbalance."""
+    import numpy as np
+    from oracle import layouts
+    rng = np.random.default_rng(0)
+    for world, B, M, C in ((2, 64, 16, 1), (4, 96, 24, 2), (8, 2048, 512, 1), (8, 32, 8, 3)):
+        Jp = C * world * B
+        perm = rng.permutation(Jp)
+        remote = total = 0
+        for k in range(Jp // (world * M)):
+            ids = perm[k * world * M:(k + 1) * world * M]
+            lists = layouts.dp_assign_minibatch(ids, world, B, M)
+            assert all(len(x) == M for x in lists)
+            assert np.array_equal(np.sort(np.concatenate(lists)), np.sort(ids))
+            owner = (ids % (world * B)) // B
+            for r, x in enumerate(lists):
+                mine = (x % (world * B)) // B == r
+                n_own = int(np.sum(owner == r))
+                assert int(mine.sum()) == min(n_own, M)            # keeps everything it owns, up to M
+                remote += int((~mine).sum())
+                total += M
+        if M >= 512:
+            assert remote / total < 0.06

@@ -265,3 +265,36 @@ def test_minibatch_gather_bit_exact(mlb, C, Tp, B, M, leaf, dtype):
     rnn = rng.integers(0, 250, size=(C, 1, B, 7)).astype(np.float32)
     out = K.mb_gather_rnn(_dev(rnn[:, 0]), _dev(idx), C, B).cpu().numpy()
     np.testing.assert_array_equal(out, layouts.reorder_rnn_data(rnn)[0][idx])
+
+
+@pytest.mark.parametrize('world,B,M,C', [(2, 64, 16, 1), (4, 96, 24, 2), (8, 2048, 512, 1), (8, 32, 8, 3), (3, 50, 25, 2)])
+def test_dp_assign_minibatches_vs_oracle(mlb, world, B, M, C):
+    """mlb_dp_assign_minibatches (owner-affine split of the global minibatches, index-exact data-parallel mode)
+    for every rank of an emulated world against oracle/layouts.dp_assign_minibatch: exact id lists, the ranks'
+    lists partition every global minibatch, own trajectories stay local."""
+    from madrona_learn_b200._lib import c_int, c_ll, call, ptr
+    from oracle import layouts
+    rng = np.random.default_rng(world * 1000 + M)
+    E, Jp = 3, C * world * B
+    nmb = Jp // (world * M)
+    perms = np.stack([rng.permutation(Jp) for _ in range(E)]).astype(np.int32)
+    perms[1] = np.sort(perms[1])                       # worst case: every minibatch owned by one or two ranks
+    perm_d = torch.from_numpy(perms).to(DEV)
+    outs = []
+    for r in range(world):
+        out = torch.full((E, nmb, M), -1, dtype=torch.int32, device=DEV)
+        call('mlb_dp_assign_minibatches', ptr(perm_d), c_ll(Jp), c_int(E), c_int(nmb), c_int(world), c_int(r),
+             c_ll(B), c_ll(M), ptr(out))
+        outs.append(out.cpu().numpy())
+    remote = 0
+    for e in range(E):
+        for k in range(nmb):
+            ids = perms[e, k * world * M:(k + 1) * world * M]
+            ref = layouts.dp_assign_minibatch(ids, world, B, M)
+            for r in range(world):
+                np.testing.assert_array_equal(outs[r][e, k], ref[r])
+                if e != 1:
+                    remote += int(np.sum((ref[r] % (world * B)) // B != r))
+            assert np.array_equal(np.sort(np.concatenate([outs[r][e, k] for r in range(world)])), np.sort(ids))
+    if M >= 512:                                       # random permutations: only the binomial imbalance moves
+        assert remote / (2 * nmb * world * M) < 0.06
