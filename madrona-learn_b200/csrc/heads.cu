@@ -300,8 +300,12 @@ __device__ void loss_finalize(const LossPartial* __restrict__ part, int nparts, 
     }
 }
 
-template <int RB>
-__global__ void __launch_bounds__(1024)
+// MAXT / MINB: the common layouts (<= 7 roles x 64 rows = 448 threads) are compiled for 3 resident blocks per SM
+// (48 registers): the kernel is a latency chain (tile load -> barrier -> per-row math -> barrier -> store) that
+// only other resident blocks can hide (r2 ncu: barrier 7.9 + long_scoreboard 3.9 stall cycles per issue at 2
+// blocks per SM).
+template <int RB, int MAXT = 1024, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB)
 ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restrict__ actions,
                 const float* __restrict__ old_lp, const float* __restrict__ adv,
                 const float* __restrict__ ret, const float* __restrict__ old_v,
@@ -617,7 +621,8 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     if (!ws || ws_bytes < mlb_ppo_loss_workspace(rows)) return MLB_EWS;
     const int ncols = vcol + cb.V;
     const size_t smem = ((size_t)RB * (ncols | 1) + ncols) * sizeof(float);
-    auto kern = RB == 64 ? ppo_loss_kernel<64> : ppo_loss_kernel<LOSS_RB_MIN>;
+    const int nthreads = (num_components + 1) * RB;
+    auto kern = RB == 64 ? (nthreads <= 448 ? ppo_loss_kernel<64, 448, 3> : ppo_loss_kernel<64>) : ppo_loss_kernel<LOSS_RB_MIN>;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t s = mlb_stream(stream);

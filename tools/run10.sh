@@ -1,4 +1,8 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_phase1_gpu.py -m gpu -q -k "dp_assign" 2>&1 | tail -3
-for b in auto 64 32; do if [ $b = auto ]; then timeout 120 python tools/gae_block.py; else MLB_GAE_BLOCK=$b timeout 120 python tools/gae_block.py; fi; done 2>&1 | grep block | tee gpurun_out/r2_gae_block.jsonl
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ppo_loss_kernel" -s 3 -c 1 -f -o gpurun_out/r2_ppo_loss python tools/profile_update.py cfg2 1 > gpurun_out/r2_ncu_ppo_loss.log 2>&1; echo "ncu rc=$?"
+timeout 600 python -m pytest tests/test_phase2_gpu.py tests/test_twohot_gpu.py tests/test_hlgauss_gpu.py tests/test_golden_gpu.py -m gpu -q 2>&1 | tail -3
+MLB_PDL=0 timeout 300 python tools/profile_update.py cfg2 2 2>&1 | grep -v -i warn | head -9
+timeout 300 python - <<'PY' 2>&1 | grep -v Warn | tail -2 | cut -c1-200
+import sys; sys.path.insert(0,'tools'); sys.path.insert(0,'.')
+import torch, bench_configs as b
+b.run('cfg2 PPO MLP 3x256, 8192x32', 8192, 32, 1, 256, 3, 4, 4, torch.bfloat16, steps=30, warm=10)
+PY
