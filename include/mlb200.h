@@ -258,6 +258,17 @@ int mlb_mb_gather_multi_peer(void* stream, const mlb_gather_leaf* leaves_host, i
 int mlb_gemm_f32(void* stream, const float* A, const float* B, float* C, const float* bias,
                  int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
                  int accumulate, int splitk);
+/* The same product on the tensor cores (tcgen05.mma.kind::tf32, fp32 accumulation): what XLA:GPU  */
+/* evaluates for an f32 dot_general at its default precision, i.e. the reference's compute_dtype   */
+/* default (ml/cfg.py:96).  Same arguments as mlb_gemm_f32; operands are read as fp32 straight from */
+/* the activations / master weights (TMA needs lda, ldb, ldc, N multiples of 4 and 16-byte aligned  */
+/* bases: mlb_gemm_tf32_ok says whether a problem qualifies).  With accumulate != 0 the reduction is */
+/* fp32 red.global.add and the launch widens splitk so that tiles x K-slices fill the SMs.           */
+int mlb_gemm_tf32_tc(void* stream, const float* A, const float* B, float* C, const float* bias,
+                     int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+                     int accumulate, int splitk);
+int mlb_gemm_tf32_ok(int M, int N, int K, int lda, int ldb, int ldc, const void* A, const void* B,
+                     const void* C);
 
 /* LayerNorm(eps 1e-6, fast variance) + ReLU (ml/models.py:46-56,116-117).                  */
 /* fwd: y = relu(((z-mean)*rstd)*scale+bias); stats (may be NULL) f32 [rows][2]={mean,rstd}  */
@@ -361,6 +372,14 @@ int mlb_sample_discrete_f32(void* stream, const float* head, int ld, const uint3
                             int partitionable, int deterministic, int32_t* actions,
                             float* log_probs, float* values, const float* critic_bins_host,
                             int num_critic_bins);
+/* ContinuousActionDistributions.sample / .best (ml/dists.py:216-258): mean = tanh(raw), std = (max - min) *  */
+/* sigmoid(raw + 2) + min, action = mean + std * normal(split(policy_key, 1)[0]) (XLA's erf_inv polynomial on   */
+/* the threefry uniform; deterministic: the mean), log_probs = Normal log-density.  actions int32 [rows,       */
+/* num_dims] receive the fp32 BIT PATTERNS.                                                                    */
+int mlb_sample_continuous_f32(void* stream, const float* head, int ld, const uint32_t* policy_key,
+                              int num_dims, float stddev_min, float stddev_max, long long rows,
+                              int partitionable, int deterministic, int32_t* actions, float* log_probs,
+                              float* values, const float* critic_bins_host, int num_critic_bins);
 /* critic_bins_host / num_critic_bins: NULL / <=1 for the plain critic (one value column); else  */
 /* the HOST array of the DreamerV3 critic's bin centres (odd count, ml/dists.py:127-141): the    */
 /* head then carries num_critic_bins critic logits and `values` receives the two-hot mean.       */
@@ -410,6 +429,10 @@ int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* desc_host, const 
 #define MLB_PPO_DHEAD_BF16       4
 /* HL-Gauss critic (ml/models.py:177-306): critic_bins_host = centres[V] | bounds[V+1] | smoothness */
 #define MLB_PPO_HLGAUSS_CRITIC   8
+/* Continuous action group (ContinuousActionDistributions, ml/dists.py:211-284): num_components action   */
+/* dimensions, head columns = raw means [0, A) | raw stds [A, 2A) | critic; `actions` holds the fp32 bit  */
+/* patterns; buckets_host is ignored; ent_scale_host has A + 2 entries, the last two = stddev_min, _max.  */
+#define MLB_PPO_CONTINUOUS_ACTIONS 16
 typedef struct mlb_ppo_stats {
     float loss, action_obj, value_loss, entropy;
     mlb_metric metrics[5];   /* Loss, Action Obj, Value Loss, Value Errors (abs), Entropy

@@ -9,6 +9,7 @@ from .actor_critic import (ActorCritic, Backbone, BackboneEncoder, BackboneSepar
                            BackboneShared, RecurrentBackboneEncoder)
 from .cfg import (ContinuousActionsConfig, DiscreteActionsConfig, EvalConfig, ParamExplore,  # noqa: F401
                   PBTConfig, TrainConfig)
+from .engine import matmul_precision, set_matmul_precision  # noqa: F401
 from .envs import HostTraceEnv, SyntheticVectorEnv  # noqa: F401
 from .moving_avg import EMANormalizer  # noqa: F401
 from . import pbt_reorder  # noqa: F401

@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmlb200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                             ctypes.c_float, ctypes.c_size_t)
@@ -76,6 +76,9 @@ SIGNATURES = {
     'mlb_mb_gather_rnn': (c_int, [P, P, P, P, c_int, c_ll, c_ll, c_ll]),
     'mlb_gemm_f32': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_int]),
+    'mlb_gemm_tf32_tc': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                         c_int, c_int]),
+    'mlb_gemm_tf32_ok': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     'mlb_ln_relu_fwd_f32': (c_int, [P, P, P, P, P, P, c_ll, c_int]),
     'mlb_ln_relu_bwd_f32': (c_int, [P, P, P, P, P, P, P, P, P, c_ll, c_int]),
     'mlb_ln_relu_fwd_bf16': (c_int, [P, P, P, P, P, P, c_ll, c_int]),
@@ -95,6 +98,7 @@ SIGNATURES = {
     'mlb_rnn_reset_f32': (c_int, [P, P, P, c_ll, c_int]),
     'mlb_rollout_keys': (c_int, [P, P, P, c_int]),
     'mlb_sample_discrete_f32': (c_int, [P, P, c_int, P, P, c_int, c_ll, c_int, c_int, P, P, P, P, c_int]),
+    'mlb_sample_continuous_f32': (c_int, [P, P, c_int, P, c_int, c_float, c_float, c_ll, c_int, c_int, P, P, P, P, c_int]),
     'mlb_mb_gather_multi': (c_int, [P, P, c_int, P, c_int, c_int, c_ll, c_ll]),
     'mlb_mb_gather_multi_peer': (c_int, [P, P, c_int, P, c_int, P, c_int, c_int, c_ll, c_ll]),
     'mlb_dp_assign_minibatches': (c_int, [P, P, c_ll, c_int, c_int, c_int, c_int, c_ll, c_ll, P]),

@@ -1,0 +1,269 @@
+// Tensor-core GEMM for compute_dtype=float32: tcgen05.mma.kind::tf32 on fp32 operands read straight from the
+// fp32 activations / master weights (no operand copies), fp32 accumulation in TMEM.
+//
+// The reference's default compute dtype is float32 (ml/cfg.py:96) and XLA:GPU evaluates an f32 dot_general at
+// its default precision on the tensor cores as TF32; this is that product for nn.Dense and its two autodiff
+// transposes (ml/models.py:110-154, jax.value_and_grad at ml/ppo.py:276-281), with mlb_gemm_f32's interface:
+//
+//     C[M, N] (+)= op(A)[M, K] * op(B)[K, N] (+ bias[N])        op(X) = X or X^T, row-major storage
+//
+//   transA = 0   A stored [M, K]   K-major operand     transA = 1   A stored [K, M]   MN-major operand
+//   transB = 1   B stored [N, K]   K-major operand     transB = 0   B stored [K, N]   MN-major operand
+//
+// so none of the three products of a Dense layer (Z = X W, dX = dZ W^T, dW = X^T dZ) transposes anything in
+// memory.  A k-block is 32 fp32 = one 128-byte SWIZZLE_128B row (K-major: one 32(k) x 128(m) box; MN-major:
+// 32(mn) x 32(k) boxes, 4096 B apart), UMMA K = 8 (32 bytes), so the shared-memory descriptors have the same
+// byte geometry as the bf16 kernel's (mlp_tc.cu).  Kernel anatomy as there: warp 0 TMA producer, warp 1 TMEM
+// allocation + single-thread MMA issue, warps 2-5 epilogue (tcgen05.ld -> fp32 store or red.global.add.v4 for
+// accumulate / split-K).  All mbarrier waits are bounded.
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int T32_THREADS = 192;
+constexpr int BK32 = 32;               // 32 fp32 = 128 bytes
+constexpr int UMMA_K32 = 8;            // 8 tf32 = 32 bytes per instruction
+
+template <int BN, int STAGES>
+struct Smem32 {
+    static constexpr int A_BYTES = BM * BK32 * 4;          // 16 KB
+    static constexpr int B_BYTES = BN * BK32 * 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// ATOMIC: fp32 vector reductions into a pre-initialised C (accumulate and / or split-K)
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC>
+__global__ void __launch_bounds__(T32_THREADS)
+tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 float* __restrict__ C, const float* __restrict__ bias, int ldc, int M, int N, int K,
+                 int k_per_split) {
+    using L = Smem32<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align_smem_1024(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int k_begin = blockIdx.z * k_per_split;
+    const int k_end = min(K, k_begin + k_per_split);
+    const int num_kb = (k_end - k_begin + BK32 - 1) / BK32;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    pdl_wait();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0 && num_kb > 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait_spin(&empty_bar[s], ph ^ 1, 0x71);
+                uint8_t* sa = smem + s * L::STAGE_BYTES;
+                uint8_t* sb = sa + L::A_BYTES;
+                mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                const int k0 = k_begin + kb * BK32;
+                if (A_MN) {         // A stored [K, M]: four 32(m) x 32(k) boxes
+#pragma unroll
+                    for (int j = 0; j < BM / 32; ++j) tma_load_2d(&tmA, &full_bar[s], sa + j * 4096, m0 + 32 * j, k0);
+                } else {            // A stored [M, K]: one 32(k) x 128(m) box
+                    tma_load_2d(&tmA, &full_bar[s], sa, k0, m0);
+                }
+                if (B_MN) {         // B stored [K, N]: BN/32 boxes of 32(n) x 32(k)
+#pragma unroll
+                    for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmB, &full_bar[s], sb + j * 4096, n0 + 32 * j, k0);
+                } else {            // B stored [N, K]: one 32(k) x BN(n) box
+                    tma_load_2d(&tmB, &full_bar[s], sb, k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && num_kb > 0) {
+            // instruction descriptor: c = F32 [4,6) = 1, a = b = TF32 (format 2) [7,10) / [10,13), a_major bit 15,
+            // b_major bit 16, N >> 3 [17,23), M >> 4 [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait_spin(&full_bar[s], ph, 0x72);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK32 / UMMA_K32; ++k) {
+                    // K-major: 8-row groups 1024 B apart (SBO), K slice = +32 B inside the swizzle row
+                    // MN-major: 32-wide MN atoms 4096 B apart (LBO), 8-k-row groups 1024 B apart (SBO),
+                    //           K slice = 8 k-rows = +1024 B
+                    const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 1024) : umma_desc(sa + k * 32, 16, 1024);
+                    const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 1024) : umma_desc(sb + k * 32, 16, 1024);
+                    tcgen05_mma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                }
+                tcgen05_commit(&empty_bar[s]);
+            }
+            tcgen05_commit(acc_bar);
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = m0 + quad * 32 + lane;
+        if (num_kb > 0) {
+            mbar_wait(acc_bar, 0, 0x73);
+            tcgen05_fence_after();
+            const bool add_bias = bias != nullptr && blockIdx.z == 0;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= N) break;                                   // warp-uniform
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+                if (row < M) {
+                    float* dst = C + (long long)row * ldc + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (col0 + j < N) {                             // N % 4 == 0
+                            float4 v;
+                            v.x = __uint_as_float(r[j]);     v.y = __uint_as_float(r[j + 1]);
+                            v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+                            if (add_bias) {
+                                const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            if (ATOMIC)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                             ::"l"(dst + j), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                            else
+                                *reinterpret_cast<float4*>(dst + j) = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN)
+                     : "memory");
+    }
+}
+
+// 2-D fp32 row-major tensor [outer, inner] with row stride ld (elements); box = [box_outer, 32 inner]
+int make_map_f32(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_outer) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return MLB_EINVAL;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? MLB_OK : MLB_EINVAL;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC>
+int launch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float* C, const float* bias, int ldc,
+             int M, int N, int K, int splitk) {
+    using L = Smem32<BN, STAGES>;
+    auto kern = tf32_gemm_kernel<BN, STAGES, A_MN, B_MN, ATOMIC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    int kps = (K + splitk - 1) / splitk;
+    kps = (kps + BK32 - 1) / BK32 * BK32;
+    const int zs = (K + kps - 1) / kps;
+    dim3 grid(mlb_cdiv(M, BM), mlb_cdiv(N, BN), zs);
+    e = launch_pdl(kern, grid, dim3(T32_THREADS), L::TOTAL, s, tA, tB, C, bias, ldc, M, N, K, kps);
+    return e == cudaSuccess ? MLB_OK : (int)e;
+}
+
+template <bool A_MN, bool B_MN>
+int dispatch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float* C, const float* bias, int ldc,
+               int M, int N, int K, bool atomic, int splitk, int bn) {
+#define GO(BN_, ST_)                                                                                       \
+    do {                                                                                                   \
+        if (atomic) return launch32<BN_, ST_, A_MN, B_MN, true>(s, tA, tB, C, bias, ldc, M, N, K, splitk); \
+        return launch32<BN_, ST_, A_MN, B_MN, false>(s, tA, tB, C, bias, ldc, M, N, K, splitk);            \
+    } while (0)
+    if (bn == 32) GO(32, 6);
+    if (bn == 64) GO(64, 6);
+    if (bn == 128) GO(128, 6);
+    GO(256, 4);
+#undef GO
+}
+
+}  // namespace
+
+MLB_API int mlb_gemm_tf32_ok(int M, int N, int K, int lda, int ldb, int ldc, const void* A, const void* B,
+                             const void* C) {
+    return M > 0 && N > 0 && K > 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 &&
+           mlb_aligned16(A) && mlb_aligned16(B) && mlb_aligned16(C);
+}
+
+// Same contract as mlb_gemm_f32 (split-K needs accumulate != 0; with accumulate the launch picks its own
+// split so that the output tiles x K-slices fill the SMs -- `splitk` is a lower bound).
+MLB_API int mlb_gemm_tf32_tc(void* stream, const float* A, const float* B, float* C, const float* bias, int M,
+                             int N, int K, int lda, int ldb, int ldc, int transA, int transB, int accumulate,
+                             int splitk) {
+    MLB_REQUIRE(A && B && C && M >= 0 && N >= 0 && K >= 0 && splitk >= 1);
+    if (M == 0 || N == 0) return MLB_OK;
+    MLB_REQUIRE(!(splitk > 1 && !accumulate));
+    MLB_REQUIRE(mlb_gemm_tf32_ok(M, N, K, lda, ldb, ldc, A, B, C));
+    MLB_REQUIRE(!bias || mlb_aligned16(bias));
+    const bool a_mn = transA != 0, b_mn = transB == 0;
+    int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+    if (accumulate && bn > 128) bn = 128;          // reductions: more output tiles, fewer K-slices
+    if (accumulate) {
+        const long long tiles = (long long)mlb_cdiv(M, BM) * mlb_cdiv(N, bn);
+        long long want = MLB_NUM_SMS / (tiles > 0 ? tiles : 1);
+        const long long cap = K / 256;             // >= 8 k-blocks per slice
+        if (want > cap) want = cap;
+        if (want > splitk) splitk = (int)want;
+    }
+    CUtensorMap tA, tB;
+    int rc;
+    if (a_mn) rc = make_map_f32(&tA, A, M, K, lda, 32);           // [K, M]: inner = M, 32(m) x 32(k) boxes
+    else rc = make_map_f32(&tA, A, K, M, lda, BM);                // [M, K]: inner = K, 32(k) x 128(m) box
+    if (rc) return rc;
+    if (b_mn) rc = make_map_f32(&tB, B, N, K, ldb, 32);           // [K, N]: inner = N
+    else rc = make_map_f32(&tB, B, K, N, ldb, bn);                // [N, K]: inner = K
+    if (rc) return rc;
+    cudaStream_t s = mlb_stream(stream);
+    const bool atomic = accumulate != 0;
+    if (!a_mn && !b_mn) return dispatch32<false, false>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn);
+    if (a_mn && b_mn) return dispatch32<true, true>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn);
+    if (a_mn) return dispatch32<true, false>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn);
+    return dispatch32<false, true>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn);
+}

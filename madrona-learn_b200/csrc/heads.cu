@@ -26,7 +26,18 @@ struct Layout {
     int nb[MAXC];
     float obj_scale[MAXC];
     float ent_scale[MAXC];
+    // continuous action group (ContinuousActionDistributions, ml/dists.py:211-284): component i = action
+    // dimension i, raw mean in column i, raw std in column A + i; std = (hi - lo) * sigmoid(raw + 2) + lo
+    int continuous;
+    float std_lo, std_hi;
 };
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+// jax.scipy.stats.norm.logpdf(x, loc, scale) = -(z^2)/2 - log(scale) - log(sqrt(2 pi)), z = (x - loc) / scale
+__device__ __forceinline__ float normal_logpdf(float x, float mu, float sd) {
+    const float z = (x - mu) / sd;
+    return -0.5f * z * z - logf(sd) - 0.918938533204672742f;
+}
 
 // Distributional critic (DreamerV3Critic, ml/models.py:157-174 -> SymExpTwoHotDistribution,
 // ml/dists.py:119-208): V logits over fixed symexp-spaced bins.  V == 1 is the plain critic.
@@ -164,6 +175,56 @@ sample_kernel(const float* __restrict__ head, int ld, const uint32_t* __restrict
     }
     actions[row * L.A + i] = best;
     if (log_probs) log_probs[row * L.A + i] = __ldg(l + off + best) - lse;
+    if (values && i == 0) values[row] = cb.V == 1 ? __ldg(l + vcol) : twohot_mean(l + vcol, cb);
+}
+
+// XLA's fp32 erf_inv (the polynomial of M. Giles, "Approximating the erfinv function"), which
+// jax.random.normal evaluates on a uniform in (-1, 1): normal = sqrt(2) * erf_inv(u)
+__device__ __forceinline__ float erfinv_xla(float x) {
+    float w = -log1pf(-x * x), p;
+    if (w < 5.f) {
+        w -= 2.5f;
+        p = 2.81022636e-08f;
+        p = fmaf(p, w, 3.43273939e-07f); p = fmaf(p, w, -3.5233877e-06f); p = fmaf(p, w, -4.39150654e-06f);
+        p = fmaf(p, w, 0.00021858087f); p = fmaf(p, w, -0.00125372503f); p = fmaf(p, w, -0.00417768164f);
+        p = fmaf(p, w, 0.246640727f); p = fmaf(p, w, 1.50140941f);
+    } else {
+        w = sqrtf(w) - 3.f;
+        p = -0.000200214257f;
+        p = fmaf(p, w, 0.000100950558f); p = fmaf(p, w, 0.00134934322f); p = fmaf(p, w, -0.00367342844f);
+        p = fmaf(p, w, 0.00573950773f); p = fmaf(p, w, -0.0076224613f); p = fmaf(p, w, 0.00943887047f);
+        p = fmaf(p, w, 1.00167406f); p = fmaf(p, w, 2.83297682f);
+    }
+    return fabsf(x) == 1.f ? copysignf(INFINITY, x) : p * x;
+}
+
+// ContinuousActionDistributions.sample / .best (ml/dists.py:216-258): one thread per (row, dimension).
+// actions are stored as the fp32 bit pattern in the int32 action buffer.
+__global__ void __launch_bounds__(128)
+sample_continuous_kernel(const float* __restrict__ head, int ld, const uint32_t* __restrict__ policy_key,
+                         int A, float lo, float hi, long long rows, int part, int deterministic,
+                         int32_t* __restrict__ actions, float* __restrict__ log_probs,
+                         float* __restrict__ values, int vcol, CriticBins cb) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * A) return;
+    const long long row = t / A;
+    const int i = (int)(t - row * A);
+    const float* l = head + row * ld;
+    const float mu = tanhf(__ldg(l + i));
+    const float sd = (hi - lo) * sigmoid_f(__ldg(l + A + i) + 2.0f) + lo;
+    float a = mu;
+    if (!deterministic) {
+        uint32_t c0, c1;
+        threefry_split_at(policy_key[0], policy_key[1], 0u, 1u, part, c0, c1);      // sample_keys = split(prng_key, 1)
+        const uint32_t bits = threefry_bits_at(c0, c1, (uint64_t)t, (uint64_t)rows * (uint64_t)A, part);
+        // jax.random.normal: uniform(minval = nextafter(-1, 0), maxval = 1), then sqrt(2) * erf_inv
+        const float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+        const float mn = -0.99999994f;
+        const float u = fmaxf(mn, f * (1.0f - mn) + mn);
+        a = fmaf(1.41421356237f * erfinv_xla(u), sd, mu);
+    }
+    actions[row * A + i] = __float_as_int(a);
+    if (log_probs) log_probs[row * A + i] = normal_logpdf(a, mu, sd);
     if (values && i == 0) values[row] = cb.V == 1 ? __ldg(l + vcol) : twohot_mean(l + vcol, cb);
 }
 
@@ -332,7 +393,37 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
     if (valid) {
         float* l = tile + r * ts;
         const float w = mb_w ? mb_w[row % M] : 1.f;
-        if (role < L.A) {
+        if (role < L.A && L.continuous) {
+            // continuous action dimension `role`: Normal(tanh(m), std(s)) (ml/dists.py:260-284), the clipped
+            // surrogate and the entropy bonus of ml/ppo.py:146-165 on its log-density
+            const int i = role;
+            float a = adv[row];
+            if (adv_mr) a = (a - adv_mr[0]) * adv_mr[1];
+            const float x = __int_as_float(actions[row * L.A + i]);
+            const float olp = old_lp[row * L.A + i];
+            const float os = L.obj_scale[i], es = L.ent_scale[i];
+            const float mu = tanhf(l[i]);
+            const float sg = sigmoid_f(l[L.A + i] + 2.0f);
+            const float sd = (L.std_hi - L.std_lo) * sg + L.std_lo;
+            const float lp = normal_logpdf(x, mu, sd);
+            const float H = 0.5f * logf(6.28318530717958648f * sd * sd) + 0.5f;
+            const float ratio = expf(lp - olp);
+            const float surr1 = a * ratio;
+            const float surr2 = a * fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
+            const bool inside = (ratio >= 1.f - clip) && (ratio <= 1.f + clip);
+            const float dobj = (surr1 <= surr2 || inside) ? a : 0.f;
+            const float dlp = -(w * dobj * ratio) * os;
+            const float dH = -(w * es);
+            const float d = x - mu;
+            const float dmu = dlp * d / (sd * sd);                           // d lp / d mu
+            const float dsd = dlp * (d * d / (sd * sd * sd) - 1.f / sd) + dH / sd;
+            l[i] = dmu * (1.f - mu * mu);                                    // tanh'
+            l[L.A + i] = dsd * (L.std_hi - L.std_lo) * sg * (1.f - sg);      // sigmoid'
+            p0 = (w * fminf(surr1, surr2)) * os;
+            p1 = (w * H) * es;
+            x0 = fminf(surr1, surr2);
+            x1 = H;
+        } else if (role < L.A) {
             const int i = role;
             float a = adv[row];
             if (adv_mr) a = (a - adv_mr[0]) * adv_mr[1];                // zscore_data, per minibatch
@@ -548,7 +639,26 @@ int make_bins(CriticBins& cb, const float* bins_host, int num_bins, bool hlgauss
 }
 
 int make_layout(Layout& L, const int32_t* buckets, int A, const float* obj_scale,
-                const float* ent_scale, int ld, int extra_cols) {
+                const float* ent_scale, int ld, int extra_cols, bool continuous = false) {
+    L.continuous = 0;
+    L.std_lo = L.std_hi = 0.f;
+    if (continuous) {
+        // A action dimensions: raw means in columns [0, A), raw stds in [A, 2A); ent_scale_host carries the two
+        // extra floats stddev_min, stddev_max behind its A entries
+        if (A <= 0 || A > MAXC || !ent_scale || !obj_scale) return MLB_EINVAL;
+        L.A = A;
+        L.continuous = 1;
+        L.std_lo = ent_scale[A];
+        L.std_hi = ent_scale[A + 1];
+        if (!(L.std_hi >= L.std_lo) || !(L.std_lo >= 0.f)) return MLB_EINVAL;
+        for (int i = 0; i < A; ++i) {
+            L.off[i] = i; L.nb[i] = 0;
+            L.obj_scale[i] = obj_scale[i];
+            L.ent_scale[i] = ent_scale[i];
+        }
+        if (2 * A + extra_cols > ld) return MLB_EINVAL;
+        return 2 * A;
+    }
     if (A <= 0 || A > MAXC || !buckets) return MLB_EINVAL;
     L.A = A;
     int off = 0;
@@ -592,6 +702,24 @@ MLB_API int mlb_sample_discrete_f32(void* stream, const float* head, int ld,
     return MLB_OK;
 }
 
+MLB_API int mlb_sample_continuous_f32(void* stream, const float* head, int ld, const uint32_t* policy_key,
+                                      int num_dims, float stddev_min, float stddev_max, long long rows,
+                                      int partitionable, int deterministic, int32_t* actions, float* log_probs,
+                                      float* values, const float* critic_bins_host, int num_critic_bins) {
+    MLB_REQUIRE(head && actions && rows >= 0 && ld > 0 && num_dims > 0 && (deterministic || policy_key));
+    MLB_REQUIRE(stddev_max >= stddev_min && stddev_min >= 0.f);
+    if (rows == 0) return MLB_OK;
+    CriticBins cb;
+    if (make_bins(cb, critic_bins_host, num_critic_bins)) return MLB_EINVAL;
+    const int vcol = 2 * num_dims;
+    MLB_REQUIRE(vcol + (values ? cb.V : 0) <= ld);
+    sample_continuous_kernel<<<mlb_cdiv(rows * num_dims, 128), 128, 0, mlb_stream(stream)>>>(
+        head, ld, policy_key, num_dims, stddev_min, stddev_max, rows, partitionable, deterministic, actions,
+        log_probs, values, vcol, cb);
+    MLB_CHECK_LAUNCH();
+    return MLB_OK;
+}
+
 MLB_API size_t mlb_ppo_loss_workspace(long long rows) {
     return (size_t)mlb_cdiv(rows, LOSS_RB_MIN) * sizeof(LossPartial) + 16;      // + the ticket counter
 }
@@ -614,7 +742,8 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     CriticBins cb;
     if (make_bins(cb, critic_bins_host, num_critic_bins, (flags & MLB_PPO_HLGAUSS_CRITIC) != 0)) return MLB_EINVAL;
     MLB_REQUIRE(cb.V == 1 || !(vn_params || (flags & (MLB_PPO_CLIP_VALUE_LOSS | MLB_PPO_HUBER_VALUE_LOSS))));
-    const int vcol = make_layout(L, buckets_host, num_components, obj_scale_host, ent_scale_host, ld, cb.V);
+    const int vcol = make_layout(L, buckets_host, num_components, obj_scale_host, ent_scale_host, ld, cb.V,
+                                 (flags & MLB_PPO_CONTINUOUS_ACTIONS) != 0);
     if (vcol < 0) return vcol;
     const int RB = (num_components + 1) * 64 <= 1024 ? 64 : LOSS_RB_MIN;
     const unsigned g = mlb_cdiv(rows, RB);

@@ -19,8 +19,9 @@ import torch
 from . import _lib
 from ._lib import c_float, c_int, c_ll, c_size_t, call, ptr
 from .actor_critic import ActorCritic, BackboneEncoder, BackboneShared, RecurrentBackboneEncoder
-from .cfg import DiscreteActionsConfig
-from .models import MLP, DenseLayerCritic, DenseLayerDiscreteActor, DreamerV3Critic, HLGaussCritic
+from .cfg import ContinuousActionsConfig, DiscreteActionsConfig
+from .models import (MLP, DenseLayerContinuousActor, DenseLayerCritic, DenseLayerDiscreteActor, DreamerV3Critic,
+                     HLGaussCritic)
 
 F32 = torch.float32
 
@@ -29,7 +30,34 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+# compute_dtype=float32 products: 'tf32' = tcgen05.mma.kind::tf32 (what XLA:GPU runs for an f32 dot at its
+# default precision, i.e. the reference's default: ml/cfg.py:96), 'highest' = exact fp32 FFMA (SIMT).
+# MLB_MATMUL_PRECISION / set_matmul_precision() mirror jax_default_matmul_precision.
+_PRECISION = {'tf32': os.environ.get('MLB_MATMUL_PRECISION', 'highest').lower() in ('tf32', 'default')}
+
+
+def set_matmul_precision(precision):
+    """'tf32' | 'default' (tensor cores) or 'highest' | 'float32' (exact fp32) for compute_dtype=float32."""
+    p = str(precision).lower()
+    if p not in ('tf32', 'default', 'highest', 'float32'):
+        raise ValueError("matmul precision must be 'tf32'/'default' or 'highest'/'float32'")
+    _PRECISION['tf32'] = p in ('tf32', 'default')
+
+
+def matmul_precision():
+    return 'tf32' if _PRECISION['tf32'] else 'highest'
+
+
+def _tma_ok(t, ld):
+    return ld % 4 == 0 and t.data_ptr() % 16 == 0
+
+
 def gemm(A, B, C, bias, M, N, K, lda, ldb, ldc, ta=0, tb=0, accumulate=0, splitk=1):
+    if (_PRECISION['tf32'] and N % 4 == 0 and _tma_ok(A, lda) and _tma_ok(B, ldb) and _tma_ok(C, ldc) and
+            (bias is None or bias.data_ptr() % 16 == 0)):
+        call('mlb_gemm_tf32_tc', ptr(A), ptr(B), ptr(C), ptr(bias), c_int(M), c_int(N), c_int(K),
+             c_int(lda), c_int(ldb), c_int(ldc), c_int(ta), c_int(tb), c_int(accumulate), c_int(splitk))
+        return
     call('mlb_gemm_f32', ptr(A), ptr(B), ptr(C), ptr(bias), c_int(M), c_int(N), c_int(K),
          c_int(lda), c_int(ldb), c_int(ldc), c_int(ta), c_int(tb), c_int(accumulate),
          c_int(splitk))
@@ -71,8 +99,8 @@ class PolicyProgram:
         if not isinstance(enc, (BackboneEncoder, RecurrentBackboneEncoder)) or not isinstance(enc.net, MLP):
             raise NotImplementedError('encoder must be [Recurrent]BackboneEncoder(net=MLP[, rnn=LSTM])')
         self._rnn_desc = enc.rnn if isinstance(enc, RecurrentBackboneEncoder) else None
-        if not isinstance(actor_critic.actor, DenseLayerDiscreteActor):
-            raise NotImplementedError('actor must be DenseLayerDiscreteActor')
+        if not isinstance(actor_critic.actor, (DenseLayerDiscreteActor, DenseLayerContinuousActor)):
+            raise NotImplementedError('actor must be DenseLayerDiscreteActor or DenseLayerContinuousActor')
         if not isinstance(actor_critic.critic, (DenseLayerCritic, DreamerV3Critic, HLGaussCritic)):
             raise NotImplementedError('critic must be DenseLayerCritic, DreamerV3Critic or HLGaussCritic')
         self.ac = actor_critic
@@ -88,16 +116,30 @@ class PolicyProgram:
         # action layout: groups in cfg.actions order, components concatenated
         self.groups = []
         buckets = []
+        self.continuous = None
         for name, ac in actions_cfg.items():
+            if isinstance(ac, ContinuousActionsConfig):
+                # ContinuousActionDistributions (ml/dists.py:211-284): num_dims components, each a Normal with
+                # mean = tanh(raw), std = (max - min) * sigmoid(raw + 2) + min; head columns means | stds
+                self.continuous = (float(ac.stddev_min), float(ac.stddev_max), int(ac.num_dims))
+                self.groups.append((name, 0, int(ac.num_dims)))
+                continue
             if not isinstance(ac, DiscreteActionsConfig):
-                raise NotImplementedError('continuous actions: next (SURVEY 8f rank 3)')
+                raise NotImplementedError('actions must be DiscreteActionsConfig or ContinuousActionsConfig')
             self.groups.append((name, len(buckets), len(ac.actions_num_buckets)))
             buckets += list(ac.actions_num_buckets)
         if len(self.groups) != 1:
-            raise NotImplementedError('DenseLayerDiscreteActor drives exactly one action group')
+            raise NotImplementedError('the actor head drives exactly one action group')
+        if (self.continuous is not None) != isinstance(actor_critic.actor, DenseLayerContinuousActor):
+            raise ValueError('ContinuousActionsConfig <-> DenseLayerContinuousActor, DiscreteActionsConfig <-> '
+                             'DenseLayerDiscreteActor')
         self.buckets = buckets
-        self.A = len(buckets)
-        self.sumA = int(sum(buckets))
+        if self.continuous is not None:
+            self.A = self.continuous[2]
+            self.sumA = 2 * self.A
+        else:
+            self.A = len(buckets)
+            self.sumA = int(sum(buckets))
         # critic columns: 1 (plain) or num_bins two-hot logits (DreamerV3Critic, ml/models.py:157-174)
         self.twohot = isinstance(actor_critic.critic, DreamerV3Critic)
         self.hlgauss = isinstance(actor_critic.critic, HLGaussCritic)
@@ -121,7 +163,7 @@ class PolicyProgram:
         # head width: padded to 4 (fp32 path) or to 64 (tensor-core path: one 64-wide UMMA N tile
         # and one SWIZZLE_128B atom of the MN-major dhead operand)
         self.NH = _round_up(self.sumA + self.V, 64 if self.tc else 4)
-        self._buckets_c = (ctypes.c_int32 * self.A)(*buckets)
+        self._buckets_c = (ctypes.c_int32 * self.A)(*buckets) if self.continuous is None else None
         # ---- arena layout -------------------------------------------------------------
         off = 0
         self.layer_off = []
@@ -451,7 +493,8 @@ class PolicyProgram:
     def fused_rollout(self):
         """True when mlb_policy_rollout_tc covers this network (bf16, feed-forward MLP encoder that
         fits one CTA's shared memory); MLB_FUSED_ROLLOUT=0 keeps the layer-by-layer path."""
-        if not self.tc or self.lstm is not None or os.environ.get('MLB_FUSED_ROLLOUT', '1') == '0':
+        if (not self.tc or self.lstm is not None or self.continuous is not None or
+                os.environ.get('MLB_FUSED_ROLLOUT', '1') == '0'):
             return False
         if self.H > 256 or self.H % 64 or self.L > 4 or self.NH > 256 or self.obs_dim > 256:
             return False
@@ -478,6 +521,12 @@ class PolicyProgram:
 
     def sample(self, head, rows, policy_key, actions, log_probs, values, partitionable=False,
                deterministic=False):
+        if self.continuous is not None:          # actions: fp32 bit patterns in the int32 buffer
+            lo, hi, n = self.continuous
+            call('mlb_sample_continuous_f32', ptr(head), c_int(self.NH), ptr(policy_key), c_int(n), c_float(lo),
+                 c_float(hi), c_ll(rows), c_int(int(partitionable)), c_int(int(deterministic)), ptr(actions),
+                 ptr(log_probs), ptr(values), self._bins_c, c_int(self.V))
+            return
         call('mlb_sample_discrete_f32', ptr(head), c_int(self.NH), ptr(policy_key), self._buckets_c,
              c_int(self.A), c_ll(rows), c_int(int(partitionable)), c_int(int(deterministic)),
              ptr(actions), ptr(log_probs), ptr(values), self._bins_c, c_int(self.V))
@@ -604,7 +653,7 @@ class PolicyProgram:
     @property
     def loss_flags(self):
         """Extra mlb_ppo_loss_f32 flags for this program (bf16 d_head on the tensor-core path)."""
-        return (4 if self.tc else 0) | (8 if self.hlgauss else 0)
+        return (4 if self.tc else 0) | (8 if self.hlgauss else 0) | (16 if self.continuous is not None else 0)
 
     def head_bias_grad(self):
         return self.head_views(self.grads)[1]

@@ -76,3 +76,14 @@ class HLGaussCritic:                     # ml/models.py:253-306
     @property
     def num_bins(self):
         return int(self.centers.shape[0])
+
+
+@dataclass(frozen=True)
+class DenseLayerContinuousActor:         # (ours) the continuous counterpart of DenseLayerDiscreteActor
+    """Dense(2 * num_dims, bias, orthogonal(0.01)) -> ContinuousActionDistributions (ml/dists.py:211-284):
+    columns [0, n) are the raw means (tanh'ed), [n, 2n) the raw stds ((max - min) * sigmoid(raw + 2) + min).
+    The reference ships the distribution class but no actor module for it (users write their own head); this is
+    the Dense head with the discrete actor's initialisation.  Paths: impl/kernel [F, 2n], impl/bias [2n]."""
+    cfg: Any
+    dtype: Any = torch.float32
+    weight_init_scale: float = 0.01

@@ -180,7 +180,10 @@ class _PPOWorkspace:
         rows_global = self.rows * (dist_ctx.world_size if dist_ctx else 1)
         self.rows_global = rows_global
         self.obj_scale = (ctypes.c_float * A)(*[1.0 / (rows_global * g_size)] * A)
-        self.ent_scale = (ctypes.c_float * A)(*[coef / (rows_global * g_size)] * A)
+        ent = [coef / (rows_global * g_size)] * A
+        if prog.continuous is not None:          # MLB_PPO_CONTINUOUS_ACTIONS: + stddev_min, stddev_max
+            ent = ent + [prog.continuous[0], prog.continuous[1]]
+        self.ent_scale = (ctypes.c_float * len(ent))(*ent)
         prog.train_ws(self.rows)
 
 

@@ -277,7 +277,9 @@ class RolloutManager:                   # ml/rollouts.py:373-826
                                 st['values'][c, s, 0], self.partitionable)
             with profile('Rollout Step'):
                 step_input = {
-                    'state': rs.sim_state, 'actions': {self._act_name: actions},
+                    'state': rs.sim_state,
+                    # continuous groups: the int32 buffer holds fp32 bit patterns (ml/rollouts.py:985-998 hands f32)
+                    'actions': {self._act_name: actions.view(torch.float32) if prog.continuous is not None else actions},
                     'resets': self.resets, 'sim_ctrl': rs.sim_ctrl,
                     'pbt': {'policy_assignments': rs.policy_assignments},
                 }

@@ -90,3 +90,69 @@ def hlgauss_loss(logits, targets, centers, bounds, smoothness):       # :233-250
     m = l.max(-1, keepdims=True)
     logp = l - (np.log(np.exp(l - m).sum(-1, keepdims=True)) + m)
     return (-(c * logp).sum(-1, keepdims=True)).astype(F32)
+
+
+# ---------------------------------------------------------------------------------------------
+# ContinuousActionDistributions -- /root/reference/src/madrona_learn/dists.py:211-284.  Pinned by
+# tests/golden/continuous.npz (the reference's own class executed under the shim).
+# logits layout used by the lowering: raw means [rows, n] | raw stds [rows, n].
+# ---------------------------------------------------------------------------------------------
+def continuous_params(raw_means, raw_stds, stddev_min, stddev_max, dtype=F32):
+    f = dtype
+    mean = np.tanh(raw_means.astype(f))                                          # :230, :253, :272
+    sig = 1 / (1 + np.exp(-(raw_stds.astype(f) + f(2.0))))
+    std = (f(stddev_max) - f(stddev_min)) * sig + f(stddev_min)                  # :231, :273
+    return mean, std
+
+
+def continuous_action_stats(raw_means, raw_stds, actions, stddev_min, stddev_max, dtype=F32):   # :260-284
+    f = dtype
+    mean, std = continuous_params(raw_means, raw_stds, stddev_min, stddev_max, f)
+    z = (actions.astype(f) - mean) / std
+    log_probs = -0.5 * z * z - np.log(std) - f(0.5 * np.log(2 * np.pi))           # jax.scipy.stats.norm.logpdf
+    entropies = 0.5 * np.log(2 * f(np.pi) * np.square(std)) + f(0.5)
+    return log_probs.astype(f), entropies.astype(f)
+
+
+def continuous_action_stats_bwd(raw_means, raw_stds, actions, stddev_min, stddev_max, dlogp, dent, dtype=np.float64):
+    """Gradient of sum(dlogp * log_probs + dent * entropies) w.r.t. (raw_means, raw_stds)."""
+    f = dtype
+    mean, std = continuous_params(raw_means, raw_stds, stddev_min, stddev_max, f)
+    sig = (std - f(stddev_min)) / (f(stddev_max) - f(stddev_min)) if stddev_max > stddev_min else np.zeros_like(std)
+    d = actions.astype(f) - mean
+    dmu = dlogp * d / (std * std)
+    dsd = dlogp * (d * d / std ** 3 - 1 / std) + dent / std
+    return dmu * (1 - mean * mean), dsd * (f(stddev_max) - f(stddev_min)) * sig * (1 - sig)
+
+
+def erfinv_xla(x):
+    """XLA's fp32 erf_inv (Giles' polynomial), evaluated by jax.random.normal on a uniform in (-1, 1)."""
+    x = np.asarray(x, F32)
+    w = (-np.log1p((-x * x).astype(F32))).astype(F32)
+    lt = w < 5
+    w1, w2 = (w - F32(2.5)).astype(F32), (np.sqrt(np.maximum(w, 0)).astype(F32) - F32(3)).astype(F32)
+    c1 = [2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503,
+          -0.00417768164, 0.246640727, 1.50140941]
+    c2 = [-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613,
+          0.00943887047, 1.00167406, 2.83297682]
+    p1, p2 = np.full_like(x, c1[0]), np.full_like(x, c2[0])
+    for a, b in zip(c1[1:], c2[1:]):
+        p1 = (p1 * w1 + F32(a)).astype(F32)
+        p2 = (p2 * w2 + F32(b)).astype(F32)
+    return (np.where(lt, p1, p2) * x).astype(F32)
+
+
+def continuous_sample(raw_means, raw_stds, key, stddev_min, stddev_max, partitionable=False):   # :216-246
+    """sample_keys = split(prng_key, 1); actions = normal(sample_key) * std + mean; jax.random.normal =
+    sqrt(2) * erf_inv(uniform(minval=nextafter(-1, 0), maxval=1)) on threefry bits (parity UNPINNED: jax is
+    not installable here; restated from jax/_src/random.py `_normal_real`)."""
+    from . import prng
+    mean, std = continuous_params(raw_means, raw_stds, stddev_min, stddev_max)
+    k = prng.split(key, 1, partitionable)[0]
+    bits = prng.random_bits(k, mean.shape, partitionable)
+    fl = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(F32) - F32(1.0)
+    mn = np.nextafter(F32(-1.0), F32(0.0))
+    u = np.maximum(mn, (fl * (F32(1.0) - mn) + mn).astype(F32))
+    a = (F32(np.sqrt(2)) * erfinv_xla(u) * std + mean).astype(F32)
+    lp, _ = continuous_action_stats(raw_means, raw_stds, a, stddev_min, stddev_max)
+    return a, lp

@@ -19,8 +19,10 @@ class PPOCfg:
                  clip_value_loss=False, huber_value_loss=False, normalize_advantages=True,
                  normalize_values=False, value_normalizer_decay=0.99999, gamma=0.99,
                  gae_lambda=0.95, partitionable=False, dreamer_v3_critic=False, compute_advantages=True,
-                 normalize_returns=True, hlgauss=None):
-        """hlgauss: (centers, bounds, smoothness) of an HLGaussCritic (cfg.hlgauss_critic), else None."""
+                 normalize_returns=True, hlgauss=None, continuous=None):
+        """hlgauss: (centers, bounds, smoothness) of an HLGaussCritic (cfg.hlgauss_critic), else None.
+        continuous: (stddev_min, stddev_max) of a ContinuousActionsConfig (then `buckets` = [None] * num_dims
+        and the actor columns are raw means | raw stds), else None."""
         self.__dict__.update(locals())
         del self.__dict__['self']
 
@@ -49,6 +51,15 @@ def ppo_loss(params, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True, 
     return out
 
 
+def _action_bwd(logits, acts, cfg, dlogp, dent, A, f):
+    cont = getattr(cfg, 'continuous', None)
+    if cont is None:
+        return nn.action_stats_bwd(logits, acts, cfg.buckets, dlogp, dent)
+    from . import dists as _d
+    dm, ds = _d.continuous_action_stats_bwd(logits[:, :A], logits[:, A:2 * A], acts, cont[0], cont[1], dlogp, dent, f)
+    return np.concatenate([dm, ds], axis=1)
+
+
 def ppo_loss_heads(logits, critic, mb, cfg, vn_state=None, dtype=np.float64, want_grads=True,
                    adv_stats=None, new_vn_state=None):
     """The part of loss_fn downstream of the policy forward (ml/ppo.py:131-262): everything the
@@ -63,7 +74,13 @@ def ppo_loss_heads(logits, critic, mb, cfg, vn_state=None, dtype=np.float64, wan
     acts = mb['actions'].reshape(rows, A)
     old_lp = mb['log_probs'].reshape(rows, A).astype(f)
     w = np.broadcast_to(mb['mb_weights'].reshape(1, M, 1), (Tp, M, 1)).reshape(rows, 1).astype(f)
-    new_lp, ent = nn.action_stats(logits, acts, cfg.buckets)
+    cont = getattr(cfg, 'continuous', None)
+    if cont is not None:          # ContinuousActionDistributions.action_stats (ml/dists.py:260-284)
+        from . import dists as _d
+        acts = np.asarray(acts).view(np.float32) if acts.dtype == np.int32 else acts.astype(np.float32)
+        new_lp, ent = _d.continuous_action_stats(logits[:, :A], logits[:, A:2 * A], acts, cont[0], cont[1], dtype=f)
+    else:
+        new_lp, ent = nn.action_stats(logits, acts, cfg.buckets)
 
     # advantages: per-MINIBATCH z-score (ml/ppo.py:134-137 -> ml/algo_common.py:133-140)
     if getattr(cfg, 'compute_advantages', True):
@@ -126,7 +143,7 @@ def ppo_loss_heads(logits, critic, mb, cfg, vn_state=None, dtype=np.float64, wan
         dobj_dratio = np.where(pick1 | inside, adv, 0.0)
         dlogp = -(w * dobj_dratio * ratio) / (rows * A)
         dent = -(cfg.entropy_coef * w) / (rows * A) * np.ones_like(ent)
-        dlogits = nn.action_stats_bwd(logits, acts, cfg.buckets, dlogp, dent)
+        dlogits = _action_bwd(logits, acts, cfg, dlogp, dent, A, f)
         dcritic = cfg.value_loss_coef * w * (np.exp(logp) - two_hot) / rows
         out['dlogits'], out['dcritic'] = dlogits, dcritic
         return out
@@ -177,7 +194,7 @@ def ppo_loss_heads(logits, critic, mb, cfg, vn_state=None, dtype=np.float64, wan
     dobj_dratio = np.where(pick1 | inside, adv, 0.0)
     dlogp = -(w * dobj_dratio * ratio) / (rows * A)
     dent = -(cfg.entropy_coef * w) / (rows * A) * np.ones_like(ent)
-    dlogits = nn.action_stats_bwd(logits, acts, cfg.buckets, dlogp, dent)
+    dlogits = _action_bwd(logits, acts, cfg, dlogp, dent, A, f)
     dcritic = cfg.value_loss_coef * w * dvloss * vclip_mask / rows
     out['dlogits'] = dlogits
     out['dcritic'] = dcritic

@@ -267,6 +267,32 @@ def hlgauss_golden(rng, jax, jnp):
     np.savez_compressed(os.path.join(OUT, 'hlgauss.npz'), **out)
 
 
+def continuous_golden(rng, jax, jnp, di):
+    """ContinuousActionDistributions.action_stats / .best (ml/dists.py:211-284) executed from the reference
+    module: two action groups with different std ranges; means / stds in the reference's [rows, groups, dims]."""
+    import types as _t
+    import scipy.stats
+    f32 = np.float32
+    if not hasattr(jax, 'scipy'):
+        jax.scipy = _t.SimpleNamespace()
+    jax.scipy.stats = _t.SimpleNamespace(norm=_t.SimpleNamespace(
+        logpdf=lambda x, loc, scale: _arr(scipy.stats.norm.logpdf(np.asarray(x, np.float64), np.asarray(loc, np.float64),
+                                                                     np.asarray(scale, np.float64)).astype(np.float32))))
+    from madrona_learn.cfg import ContinuousActionsConfig
+    cfgs = [ContinuousActionsConfig(stddev_min=0.05, stddev_max=1.5, num_dims=3),
+            ContinuousActionsConfig(stddev_min=0.2, stddev_max=0.8, num_dims=3)]
+    rows = 64
+    means = (rng.standard_normal((rows, 2, 3)) * 1.5).astype(f32)
+    stds = (rng.standard_normal((rows, 2, 3)) * 2.0).astype(f32)
+    acts = (rng.standard_normal((rows, 2, 3))).astype(f32)
+    d = di.ContinuousActionDistributions(cfgs=cfgs, means=_arr(means), stds=_arr(stds))
+    lp, ent = d.action_stats(_arr(acts))
+    np.savez_compressed(os.path.join(OUT, 'continuous.npz'), means=means, stds=stds, actions=acts,
+                        log_probs=np.asarray(lp), entropies=np.asarray(ent), best=np.asarray(d.best()),
+                        stddev_min=np.array([c.stddev_min for c in cfgs], f32),
+                        stddev_max=np.array([c.stddev_max for c in cfgs], f32))
+
+
 def main():
     install()
     import jax
@@ -398,6 +424,7 @@ def main():
     ppo_update_golden(np.random.default_rng(20261019), jax, jnp, lax, ac, ma, di)
     select_golden(np.random.default_rng(20261020), jax, jnp, lax, ma)
     hlgauss_golden(np.random.default_rng(20261021), jax, jnp)
+    continuous_golden(np.random.default_rng(20261022), jax, jnp, di)
     print('golden fixtures written to', OUT)
 
 

@@ -256,3 +256,47 @@ def test_hlgauss_oracle_matches_reference_golden():
                                                       float(d[name + '_smoothness'])), d[name + '_loss'], rtol=2e-6)
         t = dists.hlgauss_target(d[name + '_targets'], c, b, float(d[name + '_smoothness']))
         np.testing.assert_allclose(t.sum(-1), 1.0, rtol=1e-5)
+
+
+def test_continuous_oracle_matches_reference_golden():
+    """oracle/dists.py ContinuousActionDistributions restatement vs the reference class executed under the shim
+    (tests/golden/continuous.npz, ml/dists.py:211-284): two groups with different std ranges."""
+    from oracle import dists
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'continuous.npz'))
+    for gi in range(2):
+        lo, hi = float(g['stddev_min'][gi]), float(g['stddev_max'][gi])
+        lp, ent = dists.continuous_action_stats(g['means'][:, gi], g['stds'][:, gi], g['actions'][:, gi], lo, hi)
+        np.testing.assert_allclose(lp, g['log_probs'][:, gi], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(ent, g['entropies'][:, gi], rtol=1e-6, atol=1e-6)
+        mean, std = dists.continuous_params(g['means'][:, gi], g['stds'][:, gi], lo, hi)
+        np.testing.assert_allclose(mean, g['best'][:, gi], rtol=1e-6, atol=1e-7)
+        assert (std >= lo).all() and (std <= hi).all()
+        # analytic gradient of the restatement vs central differences (fp64)
+        rng = np.random.default_rng(gi)
+        dlp, dent = rng.standard_normal(lp.shape), rng.standard_normal(lp.shape)
+        m64, s64, a64 = (g[k][:, gi].astype(np.float64) for k in ('means', 'stds', 'actions'))
+        dm, ds = dists.continuous_action_stats_bwd(m64, s64, a64, lo, hi, dlp, dent)
+        f = lambda m_, s_: sum((w * x).sum() for w, x in zip(
+            (dlp, dent), dists.continuous_action_stats(m_, s_, a64, lo, hi, dtype=np.float64)))
+        e = 1e-6
+        for (i, j) in ((0, 0), (5, 2), (63, 1)):
+            dmn, dsn = np.zeros_like(m64), np.zeros_like(s64)
+            dmn[i, j] = dsn[i, j] = e
+            np.testing.assert_allclose((f(m64 + dmn, s64) - f(m64 - dmn, s64)) / (2 * e), dm[i, j], rtol=1e-5, atol=1e-8)
+            np.testing.assert_allclose((f(m64, s64 + dsn) - f(m64, s64 - dsn)) / (2 * e), ds[i, j], rtol=1e-5, atol=1e-8)
+
+
+def test_continuous_sample_is_standard_normal():
+    """oracle continuous_sample (jax.random.normal restated: threefry bits -> uniform(-1, 1) -> sqrt2 * erf_inv):
+    the draws are N(mean, std) -- moments and a KS distance -- and erfinv_xla inverts scipy's erf."""
+    from oracle import dists
+    import scipy.special, scipy.stats
+    x = np.linspace(-0.999999, 0.999999, 20001).astype(np.float32)
+    np.testing.assert_allclose(scipy.special.erf(dists.erfinv_xla(x).astype(np.float64)), x, atol=3e-7)
+    rows, n = 8192, 3
+    z = np.zeros((rows, n), np.float32)
+    key = np.array([7, 9], np.uint32)
+    a, lp = dists.continuous_sample(z, z - 2.0, key, 0.0, 2.0)            # mean 0, std 2 * sigmoid(0) = 1
+    assert abs(a.mean()) < 0.02 and abs(a.std() - 1) < 0.02
+    assert scipy.stats.kstest(a.ravel(), 'norm').statistic < 0.01
+    np.testing.assert_allclose(lp, scipy.stats.norm.logpdf(a.astype(np.float64)), atol=1e-5)

@@ -1,0 +1,192 @@
+"""GPU parity of the tensor-core path for compute_dtype=float32 (mlb_gemm_tf32_tc: tcgen05.mma.kind::tf32 on the
+fp32 activations / master weights, ml/cfg.py:96 + XLA:GPU's default f32 dot precision).
+
+Tolerances: rel-L2 <= 1e-3 against the exact (fp64) product / oracle for the
+TF32 path; <= 2e-6 against the product of the operands with their low 13 mantissa bits dropped (what the tensor
+core reads), which pins the operand layouts, the transposes, the K tails and the split-K reduction exactly."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn as onn, ppo as oppo
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a, np.float64) - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def _trunc_tf32(x):
+    return (np.ascontiguousarray(x, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _rna_tf32(x):
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+SHAPES = [
+    # M, N, K, ta, tb, accumulate, bias
+    (1000, 256, 256, 0, 0, 0, False),      # forward  Z = X W          (B stored [K, N]: MN-major)
+    (1000, 256, 64, 0, 0, 0, False),       # first layer, K = obs_dim
+    (777, 28, 256, 0, 0, 0, True),         # head forward: narrow N with a tail, bias, ragged M
+    (1000, 256, 256, 0, 1, 0, False),      # dX = dZ W^T               (B stored [N, K]: K-major)
+    (515, 256, 28, 0, 1, 0, False),        # dfeat = dhead W_h^T: K tail of 28 (< one k-block)
+    (256, 256, 5000, 1, 0, 1, False),      # dW = X^T dZ: both MN-major, split-K reduction over rows
+    (64, 256, 4099, 1, 0, 1, False),       # dW of the first layer: M = 64 < tile, ragged K
+    (256, 28, 3000, 1, 0, 1, False),       # head dW
+    (130, 100, 72, 1, 1, 0, True),         # transA with K-major B, all dims ragged
+    (128, 1024, 256, 0, 1, 1, False),      # LSTM gate pre-activations (+= h W_h^T), N = 4 RH
+]
+
+
+@pytest.mark.parametrize('M,N,K,ta,tb,acc,with_bias', SHAPES)
+def test_gemm_tf32_vs_exact_product(mlb, M, N, K, ta, tb, acc, with_bias):
+    from madrona_learn_b200._lib import c_int, call, ptr
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32) if with_bias else None
+    opA = lambda a: (a.T if ta else a).astype(np.float64)
+    opB = lambda b: (b.T if tb else b).astype(np.float64)
+    extra = (C0.astype(np.float64) if acc else 0.0) + (bias.astype(np.float64) if with_bias else 0.0)
+    exact = opA(A) @ opB(B) + extra
+    dropped = opA(_trunc_tf32(A)) @ opB(_trunc_tf32(B)) + extra
+    rounded = opA(_rna_tf32(A)) @ opB(_rna_tf32(B)) + extra
+    d = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    Ad, Bd, Cd, bd = d(A), d(B), d(C0 if acc else np.full((M, N), np.nan, np.float32)), d(bias)
+    call('mlb_gemm_tf32_tc', ptr(Ad), ptr(Bd), ptr(Cd), ptr(bd), c_int(M), c_int(N), c_int(K),
+         c_int(A.shape[1]), c_int(B.shape[1]), c_int(N), c_int(ta), c_int(tb), c_int(acc), c_int(1))
+    torch.cuda.synchronize()
+    out = Cd.cpu().numpy()
+    assert np.isfinite(out).all()
+    assert _rel(out, exact) < 1e-3, _rel(out, exact)
+    # the tensor core's operand conversion is one of: drop the low 13 bits / round to nearest
+    assert min(_rel(out, dropped), _rel(out, rounded)) < 2e-6, (_rel(out, dropped), _rel(out, rounded))
+
+
+def test_gemm_tf32_contract(mlb):
+    """Same refusals as mlb_gemm_f32 plus the TMA constraints (no fallback inside the entry point)."""
+    from madrona_learn_b200 import _lib
+    from madrona_learn_b200._lib import c_int, ptr
+    L = _lib.lib()
+    a = torch.zeros(64, 64, device=DEV)
+    args = lambda lda=64, n=64, acc=0, sk=1: (None, ptr(a), ptr(a), ptr(a), ptr(None), c_int(64), c_int(n), c_int(64),
+                                              c_int(lda), c_int(64), c_int(64), c_int(0), c_int(0), c_int(acc), c_int(sk))
+    assert L.mlb_gemm_tf32_tc(*args()) == 0
+    assert L.mlb_gemm_tf32_tc(*args(lda=66)) != 0             # row stride not a multiple of 16 bytes
+    assert L.mlb_gemm_tf32_tc(*args(n=30)) != 0               # N % 4
+    assert L.mlb_gemm_tf32_tc(*args(sk=4)) != 0               # split-K without accumulate
+    assert L.mlb_gemm_tf32_ok(c_int(64), c_int(64), c_int(64), c_int(64), c_int(64), c_int(64), ptr(a), ptr(a), ptr(a)) == 1
+    assert L.mlb_gemm_tf32_ok(c_int(64), c_int(64), c_int(64), c_int(66), c_int(64), c_int(64), ptr(a), ptr(a), ptr(a)) == 0
+    torch.cuda.synchronize()
+
+
+@pytest.fixture
+def tf32(mlb):
+    prev = mlb.matmul_precision()
+    mlb.set_matmul_precision('tf32')
+    yield mlb
+    mlb.set_matmul_precision(prev)
+
+
+BUCKETS = [4, 8, 5, 5, 2, 2]
+
+
+@pytest.mark.parametrize('H,L,Tp,M', [(64, 2, 4, 256), (256, 3, 8, 512)])
+def test_tf32_loss_and_grads_vs_oracle(tf32, H, L, Tp, M):
+    """compute_dtype=float32 with matmul precision 'tf32': forward / PPO loss / backward of the whole network
+    against the fp64 oracle (no operand rounding in the oracle): rel-L2 <= 1e-3 on the head, 2e-3 on gradients."""
+    import ctypes
+    from madrona_learn_b200 import _lib
+    from madrona_learn_b200._lib import c_float, c_int, c_ll, c_size_t, call, ptr
+    from madrona_learn_b200.engine import PolicyProgram
+    from oracle import algo_common as oac
+    m = tf32
+    D = 64
+    rows, A = Tp * M, len(BUCKETS)
+    rng = np.random.default_rng(21)
+    p = onn.init_params(rng, D, H, L, BUCKETS)
+    p['actor']['kernel'] = (rng.standard_normal(p['actor']['kernel'].shape) * 0.2).astype(np.float32)
+    pol = m.Policy(actor_critic=m.ActorCritic(
+        backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(net=m.models.MLP(H, L))),
+        actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(BUCKETS)), critic=m.models.DenseLayerCritic()))
+    prog = PolicyProgram(pol.actor_critic, D, {'act': m.DiscreteActionsConfig(BUCKETS)}, DEV, torch.float32)
+    prog.load_oracle_params(p)
+    cfg = oppo.PPOCfg(BUCKETS, entropy_coef=0.02)
+    mb = dict(obs=rng.standard_normal((Tp, M, D)).astype(np.float32),
+              actions=np.stack([rng.integers(0, b, (Tp, M)) for b in BUCKETS], -1).astype(np.int32),
+              advantages=rng.standard_normal((Tp, M, 1)).astype(np.float32),
+              returns=rng.standard_normal((Tp, M, 1)).astype(np.float32),
+              values=rng.standard_normal((Tp, M, 1)).astype(np.float32), mb_weights=np.ones((M, 1), np.float32))
+    mb['log_probs'] = (-np.abs(rng.standard_normal((Tp, M, A))) - 0.5).astype(np.float32)
+    ref = oppo.ppo_loss(p, mb, cfg, None, dtype=np.float64)
+    dv = {k: torch.from_numpy(v).to(DEV) for k, v in mb.items()}
+    obs_d = dv['obs'].view(rows, D)
+    head = prog.forward_train(obs_d, rows)
+    h = head.cpu().numpy()
+    nA = sum(BUCKETS)
+    assert _rel(h[:, :nA], ref['logits']) < 1e-3
+    assert _rel(h[:, nA:nA + 1], ref['critic']) < 1e-3
+    tw = prog.train_ws(rows)
+    mean, rstd = oac.zscore_stats(mb['advantages'])
+    adv_mr = torch.tensor([mean, rstd, 0, 0], dtype=torch.float32, device=DEV)
+    obj_scale = (ctypes.c_float * A)(*[1.0 / (rows * A)] * A)
+    ent_scale = (ctypes.c_float * A)(*[cfg.entropy_coef / (rows * A)] * A)
+    prog.zero_grads()
+    call('mlb_ppo_loss_f32', ptr(head), c_int(prog.NH), ptr(dv['actions']), ptr(dv['log_probs']),
+         ptr(dv['advantages']), ptr(dv['returns']), ptr(None), ptr(None), ptr(adv_mr), ptr(None),
+         prog._buckets_c, obj_scale, ent_scale, c_int(A), c_ll(rows), c_ll(M), c_float(cfg.clip_coef),
+         c_float(cfg.value_loss_coef), c_int(prog.loss_flags), ptr(tw['dhead']), ptr(prog.head_bias_grad()),
+         ptr(tw['stats_out']), ptr(tw['loss_ws']), c_size_t(tw['loss_ws'].numel()), prog._bins_c, c_int(1))
+    stt = _lib.PPOStats.from_buffer_copy(tw['stats_out'].cpu().numpy().tobytes())
+    np.testing.assert_allclose(stt.loss, ref['loss'], rtol=2e-3, atol=1e-5)
+    prog.backward(obs_d, rows)
+    g = prog.to_oracle_params(prog.grads)
+    worst = []
+    onn.tree_map(lambda a, b: worst.append(_rel(a, b)), g, ref['grads'])
+    print('tf32 grads rel-L2 per leaf: max %.3g' % max(worst))
+    assert max(worst) < 2e-3, worst
+
+
+def test_tf32_update_iter_tracks_exact_fp32(mlb):
+    """update_iter (rollout, GAE, 2 epochs x 2 minibatches, CUDA graph replay) with 'tf32' against 'highest':
+    same seeds, the parameters after three updates agree to TF32 precision and the loss is finite."""
+    m = mlb
+    N, T, D = 512, 8, 64
+    out = {}
+    prev = m.matmul_precision()
+    try:
+        for prec in ('highest', 'tf32'):
+            m.set_matmul_precision(prec)
+            env = m.SyntheticVectorEnv(N, D, len(BUCKETS), seed=2, device=DEV)
+            pol = m.Policy(actor_critic=m.ActorCritic(
+                backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(net=m.models.MLP(128, 2))),
+                actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(BUCKETS)),
+                critic=m.models.DenseLayerCritic()))
+            cfg = m.TrainConfig(
+                num_worlds=N, num_agents_per_world=1, num_updates=4, actions={'act': m.DiscreteActionsConfig(BUCKETS)},
+                steps_per_update=T, lr=3e-4,
+                algo=m.PPOConfig(num_epochs=2, minibatch_size=N // 2, clip_coef=0.2, value_loss_coef=0.5,
+                                 entropy_coef={'act': 0.01}, max_grad_norm=0.5),
+                num_bptt_chunks=1, gamma=0.99, seed=3, metrics_buffer_size=4, gae_lambda=0.95,
+                dreamer_v3_critic=False)
+            mgr = m.init_training(DEV, cfg, env.sim_fns(), pol, None, verbose=False)
+            p0 = mgr.state.policy_states.program.params.clone()
+            for _ in range(3):
+                mgr.update_iter()
+            torch.cuda.synchronize()
+            out[prec] = (mgr.state.policy_states.program.params.double().cpu().numpy() - p0.double().cpu().numpy(),
+                         mgr.metrics.latest()['Loss'].mean)
+    finally:
+        m.set_matmul_precision(prev)
+    assert np.isfinite(out['tf32'][1])
+    # sampled actions may differ where two logits are within TF32 error of each other, so compare the update
+    # direction, not bits: cosine of the parameter deltas
+    a, b = out['highest'][0], out['tf32'][0]
+    cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+    assert cos > 0.98, cos
+    np.testing.assert_allclose(out['tf32'][1], out['highest'][1], rtol=0.05, atol=5e-3)

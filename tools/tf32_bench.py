@@ -1,0 +1,54 @@
+"""Times mlb_gemm_tf32_tc against mlb_gemm_f32 on the cfg2 minibatch shapes (65536 rows) and the whole cfg2 update
+with compute_dtype=float32 under both matmul precisions."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import madrona_learn_b200 as m  # noqa: E402
+from madrona_learn_b200._lib import c_int, call, ptr  # noqa: E402
+
+DEV = 'cuda:0'
+
+
+def time_gemm(name, fn, M, N, K, ta, tb, acc, iters=20):
+    A = torch.randn((K, M) if ta else (M, K), device=DEV)
+    B = torch.randn((N, K) if tb else (K, N), device=DEV)
+    C = torch.zeros(M, N, device=DEV)
+    flush = torch.zeros(64 << 20, device=DEV)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2 * iters)]
+    for i in range(iters + 3):
+        flush.zero_()
+        if i >= 3:
+            e[2 * (i - 3)].record()
+        call(fn, ptr(A), ptr(B), ptr(C), ptr(None), c_int(M), c_int(N), c_int(K), c_int(A.shape[1]), c_int(B.shape[1]),
+             c_int(N), c_int(ta), c_int(tb), c_int(acc), c_int(1 if fn == 'mlb_gemm_tf32_tc' or not acc else 16))
+        if i >= 3:
+            e[2 * (i - 3) + 1].record()
+    torch.cuda.synchronize()
+    us = sorted(e[2 * i].elapsed_time(e[2 * i + 1]) * 1e3 for i in range(iters))[iters // 2]
+    byt = 4 * (M * K + N * K + M * N)
+    print(json.dumps(dict(gemm=name, fn=fn, M=M, N=N, K=K, us=round(us, 2), tflops=round(2 * M * N * K / us / 1e6, 1),
+                          gbs=round(byt / us / 1e3, 1))), flush=True)
+
+
+if __name__ == '__main__':
+    R = 65536
+    for fn in ('mlb_gemm_tf32_tc', 'mlb_gemm_f32'):
+        time_gemm('fwd Z=XW', fn, R, 256, 256, 0, 0, 0)
+        time_gemm('fwd0 Z=XW (K=64)', fn, R, 256, 64, 0, 0, 0)
+        time_gemm('dX=dZ W^T', fn, R, 256, 256, 0, 1, 0)
+        time_gemm('dW=X^T dZ', fn, 256, 256, R, 1, 0, 1)
+        time_gemm('head fwd', fn, R, 28, 256, 0, 0, 0)
+        time_gemm('head dX', fn, R, 256, 28, 0, 1, 0)
+        time_gemm('head dW', fn, 256, 28, R, 1, 0, 1)
+    import bench_configs as b
+    for prec in ('tf32', 'highest'):
+        m.set_matmul_precision(prec)
+        b.run('cfg2 f32 matmul=' + prec, 8192, 32, 1, 256, 3, 4, 4, torch.float32, steps=10 if prec == 'tf32' else 4, warm=3)
+    m.set_matmul_precision('tf32')
+    if len(sys.argv) > 1 and sys.argv[1] == 'profile':
+        import profile_update  # noqa: F401
