@@ -11,9 +11,9 @@
 //   transB = 1   B stored [N, K]   K-major operand     transB = 0   B stored [K, N]   MN-major operand
 //
 // so none of the three products of a Dense layer (Z = X W, dX = dZ W^T, dW = X^T dZ) transposes anything in
-// memory.  A k-block is 32 fp32 = one 128-byte SWIZZLE_128B row (K-major: one 32(k) x 128(m) box; MN-major:
-// 32(mn) x 32(k) boxes, 4096 B apart), UMMA K = 8 (32 bytes), so the shared-memory descriptors have the same
-// byte geometry as the bf16 kernel's (mlp_tc.cu).  Kernel anatomy as there: warp 0 TMA producer, warp 1 TMEM
+// memory.  A k-block is 32 fp32 = one 128-byte swizzle row (K-major: one 32(k) x 128(m) SWIZZLE_128B box;
+// MN-major: 32(mn) x 32(k) boxes, 4096 B apart, in the 32-byte-atom 128 B swizzle that is the only MN-major
+// layout tcgen05 accepts for 32-bit operands), UMMA K = 8 (32 bytes).  Kernel anatomy as there: warp 0 TMA producer, warp 1 TMEM
 // allocation + single-thread MMA issue, warps 2-5 epilogue (tcgen05.ld -> fp32 store or red.global.add.v4 for
 // accumulate / split-K).  All mbarrier waits are bounded.
 #include "tc_common.cuh"
@@ -32,7 +32,7 @@ struct Smem32 {
     static constexpr int B_BYTES = BN * BK32 * 4;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static constexpr int TOTAL = BAR_OFF + (3 * STAGES + 1) * 8 + 16 + 1024;
 };
 
 __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -45,8 +45,20 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc
         : "memory");
 }
 
+// shared-memory descriptor with layout type SWIZZLE_128B_BASE32B (= 1, bits [61,64)): 32-byte chunks swizzled
+// inside a 128-byte row by (row & 3) -- what TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes
+__device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61);
+}
+
 // ATOMIC: fp32 vector reductions into a pre-initialised C (accumulate and / or split-K)
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC>
+// ROUND:  the tensor core drops the low 13 mantissa bits of an fp32 operand (a biased conversion: every product
+//         shrinks by ~1e-3).  With ROUND the four epilogue warps, idle during the main loop, convert each landed
+//         stage in place with cvt.rna.tf32.f32 (round to nearest) before the MMA thread reads it: the operand
+//         error becomes zero-mean and the products of a 256-deep dot average it out (rel-L2 ~1e-4 instead of
+//         ~1e-3 against the exact product).  The pipeline is then TMA -> round -> MMA per stage.
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC, bool ROUND>
 __global__ void __launch_bounds__(T32_THREADS)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  float* __restrict__ C, const float* __restrict__ bias, int ldc, int M, int N, int K,
@@ -56,7 +68,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = align_smem_1024(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* acc_bar = empty_bar + STAGES;
+    uint64_t* ready_bar = empty_bar + STAGES;              // ROUND: stage converted, 128 arrivals
+    uint64_t* acc_bar = ready_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
     pdl_launch_dependents();
@@ -69,7 +82,9 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128);
+        }
         mbar_init(acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -118,17 +133,18 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait_spin(&full_bar[s], ph, 0x72);
+                mbar_wait_spin(ROUND ? &ready_bar[s] : &full_bar[s], ph, 0x72);
                 tcgen05_fence_after();
                 const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
                 const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
                 for (int k = 0; k < BK32 / UMMA_K32; ++k) {
-                    // K-major: 8-row groups 1024 B apart (SBO), K slice = +32 B inside the swizzle row
-                    // MN-major: 32-wide MN atoms 4096 B apart (LBO), 8-k-row groups 1024 B apart (SBO),
-                    //           K slice = 8 k-rows = +1024 B
-                    const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 1024) : umma_desc(sa + k * 32, 16, 1024);
-                    const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 1024) : umma_desc(sb + k * 32, 16, 1024);
+                    // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), K slice = +32 B inside the swizzle row
+                    // MN-major (SWIZZLE_128B_BASE32B, the only MN-major layout of 32-bit operands): 32-wide MN
+                    //           atoms 4096 B apart (LBO), 4-k-row groups 512 B apart (SBO), K slice = 8 k-rows
+                    //           = +1024 B
+                    const uint64_t ad = A_MN ? umma_desc_mn32(sa + k * 1024, 4096, 512) : umma_desc(sa + k * 32, 16, 1024);
+                    const uint64_t bd = B_MN ? umma_desc_mn32(sb + k * 1024, 4096, 512) : umma_desc(sb + k * 32, 16, 1024);
                     tcgen05_mma_tf32(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
                 }
                 tcgen05_commit(&empty_bar[s]);
@@ -138,6 +154,30 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
         const int quad = warp & 3;
         const int row = m0 + quad * 32 + lane;
+        if (ROUND) {
+            // in-place round-to-nearest of every landed stage (element-wise: the swizzle does not matter);
+            // the generic-proxy writes are fenced towards the async proxy the MMA reads through
+            const int et = threadIdx.x - 64;                           // 0..127
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full_bar[s], (kb / STAGES) & 1, 0x74);
+                const uint32_t base = smem_u32(smem + s * L::STAGE_BYTES) + et * 16;
+#pragma unroll 8
+                for (int v = 0; v < L::STAGE_BYTES / (128 * 16); ++v) {
+                    uint32_t a, b, c, d;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(base + v * 2048));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(__uint_as_float(a)));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(__uint_as_float(b)));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(__uint_as_float(c)));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(__uint_as_float(d)));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                 ::"r"(base + v * 2048), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+                }
+                fence_async_smem();
+                mbar_arrive(&ready_bar[s]);
+            }
+        }
         if (num_kb > 0) {
             mbar_wait(acc_bar, 0, 0x73);
             tcgen05_fence_after();
@@ -181,7 +221,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // 2-D fp32 row-major tensor [outer, inner] with row stride ld (elements); box = [box_outer, 32 inner]
-int make_map_f32(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_outer) {
+int make_map_f32(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_outer,
+                 bool mn_major) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return MLB_EINVAL;
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -189,16 +230,17 @@ int make_map_f32(CUtensorMap* map, const void* base, long long inner, long long 
     cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? MLB_OK : MLB_EINVAL;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC, bool ROUND>
 int launch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float* C, const float* bias, int ldc,
              int M, int N, int K, int splitk) {
     using L = Smem32<BN, STAGES>;
-    auto kern = tf32_gemm_kernel<BN, STAGES, A_MN, B_MN, ATOMIC>;
+    auto kern = tf32_gemm_kernel<BN, STAGES, A_MN, B_MN, ATOMIC, ROUND>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return (int)e;
     int kps = (K + splitk - 1) / splitk;
@@ -209,19 +251,29 @@ int launch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float
     return e == cudaSuccess ? MLB_OK : (int)e;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool ROUND>
 int dispatch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float* C, const float* bias, int ldc,
-               int M, int N, int K, bool atomic, int splitk, int bn) {
-#define GO(BN_, ST_)                                                                                       \
-    do {                                                                                                   \
-        if (atomic) return launch32<BN_, ST_, A_MN, B_MN, true>(s, tA, tB, C, bias, ldc, M, N, K, splitk); \
-        return launch32<BN_, ST_, A_MN, B_MN, false>(s, tA, tB, C, bias, ldc, M, N, K, splitk);            \
+               int M, int N, int K, bool atomic, int splitk, int bn, int stages256) {
+#define GO(BN_, ST_)                                                                                              \
+    do {                                                                                                          \
+        if (atomic) return launch32<BN_, ST_, A_MN, B_MN, true, ROUND>(s, tA, tB, C, bias, ldc, M, N, K, splitk); \
+        return launch32<BN_, ST_, A_MN, B_MN, false, ROUND>(s, tA, tB, C, bias, ldc, M, N, K, splitk);            \
     } while (0)
     if (bn == 32) GO(32, 6);
     if (bn == 64) GO(64, 6);
     if (bn == 128) GO(128, 6);
+    // 256-wide tiles (the Dense forward / dX): 2 stages = 96 KB, two CTAs per SM (256 TMEM columns each), so one
+    // CTA's epilogue runs under the other's main loop; 4 stages = 192 KB, one CTA per SM
+    if (stages256 == 2) GO(256, 2);
     GO(256, 4);
 #undef GO
+}
+
+// immutable after first use (read once): MLB_TF32_ROUND=0 keeps the hardware's truncating conversion,
+// MLB_TF32_STAGES=4 the one-CTA-per-SM pipeline of the 256-wide tiles
+int tf32_knob(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 }  // namespace
@@ -254,16 +306,23 @@ MLB_API int mlb_gemm_tf32_tc(void* stream, const float* A, const float* B, float
     }
     CUtensorMap tA, tB;
     int rc;
-    if (a_mn) rc = make_map_f32(&tA, A, M, K, lda, 32);           // [K, M]: inner = M, 32(m) x 32(k) boxes
-    else rc = make_map_f32(&tA, A, K, M, lda, BM);                // [M, K]: inner = K, 32(k) x 128(m) box
+    if (a_mn) rc = make_map_f32(&tA, A, M, K, lda, 32, true);           // [K, M]: inner = M, 32(m) x 32(k) boxes
+    else rc = make_map_f32(&tA, A, K, M, lda, BM, false);                // [M, K]: inner = K, 32(k) x 128(m) box
     if (rc) return rc;
-    if (b_mn) rc = make_map_f32(&tB, B, N, K, ldb, 32);           // [K, N]: inner = N
-    else rc = make_map_f32(&tB, B, K, N, ldb, bn);                // [N, K]: inner = K
+    if (b_mn) rc = make_map_f32(&tB, B, N, K, ldb, 32, true);           // [K, N]: inner = N
+    else rc = make_map_f32(&tB, B, K, N, ldb, bn, false);                // [N, K]: inner = K
     if (rc) return rc;
     cudaStream_t s = mlb_stream(stream);
     const bool atomic = accumulate != 0;
-    if (!a_mn && !b_mn) return dispatch32<false, false>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn);
-    if (a_mn && b_mn) return dispatch32<true, true>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn);
-    if (a_mn) return dispatch32<true, false>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn);
-    return dispatch32<false, true>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn);
+    static const int round = tf32_knob("MLB_TF32_ROUND", 1), st256 = tf32_knob("MLB_TF32_STAGES", 2);
+#define DISPATCH(R_)                                                                                                    \
+    do {                                                                                                                \
+        if (!a_mn && !b_mn) return dispatch32<false, false, R_>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn, st256); \
+        if (a_mn && b_mn) return dispatch32<true, true, R_>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn, st256);     \
+        if (a_mn) return dispatch32<true, false, R_>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn, st256);            \
+        return dispatch32<false, true, R_>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn, st256);                      \
+    } while (0)
+    if (round) DISPATCH(true);
+    DISPATCH(false);
+#undef DISPATCH
 }

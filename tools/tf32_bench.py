@@ -37,7 +37,8 @@ def time_gemm(name, fn, M, N, K, ta, tb, acc, iters=20):
 
 if __name__ == '__main__':
     R = 65536
-    for fn in ('mlb_gemm_tf32_tc', 'mlb_gemm_f32'):
+    print('MLB_TF32_ROUND=%s MLB_TF32_STAGES=%s' % (os.environ.get('MLB_TF32_ROUND', '1'), os.environ.get('MLB_TF32_STAGES', '2')))
+    for fn in ('mlb_gemm_tf32_tc',) + (('mlb_gemm_f32',) if 'sgemm' in sys.argv else ()):
         time_gemm('fwd Z=XW', fn, R, 256, 256, 0, 0, 0)
         time_gemm('fwd0 Z=XW (K=64)', fn, R, 256, 64, 0, 0, 0)
         time_gemm('dX=dZ W^T', fn, R, 256, 256, 0, 1, 0)
@@ -46,9 +47,7 @@ if __name__ == '__main__':
         time_gemm('head dX', fn, R, 256, 28, 0, 1, 0)
         time_gemm('head dW', fn, 256, 28, R, 1, 0, 1)
     import bench_configs as b
-    for prec in ('tf32', 'highest'):
-        m.set_matmul_precision(prec)
-        b.run('cfg2 f32 matmul=' + prec, 8192, 32, 1, 256, 3, 4, 4, torch.float32, steps=10 if prec == 'tf32' else 4, warm=3)
     m.set_matmul_precision('tf32')
-    if len(sys.argv) > 1 and sys.argv[1] == 'profile':
-        import profile_update  # noqa: F401
+    b.run('cfg2 f32 matmul=tf32', 8192, 32, 1, 256, 3, 4, 4, torch.float32, steps=10, warm=3)
+    if 'cfg4' in sys.argv:
+        b.run('cfg4 f32 matmul=tf32', 16384, 128, 4, 256, 2, 4, 2, torch.float32, rnn=256, normalize_values=True, steps=2, warm=2)
