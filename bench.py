@@ -451,7 +451,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the f32 / cfg3 / kernel-table arms')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'],
-                    help='bf16: tcgen05 tensor-core MLP (fp32 accumulate/statistics); f32: SIMT fp32 MLP')
+                    help='bf16: tcgen05 tensor-core MLP (fp32 accumulate/statistics); f32: fp32 activations, Dense '
+                         'products on tcgen05 kind::tf32 (MLB_MATMUL_PRECISION=highest: SIMT FFMA)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get('RANK', '0'))
@@ -533,7 +534,10 @@ def main():
         kf = max(3, min(args.steps, 10))
         secf, _ = run_arm(torch, m, dev, WORKLOAD, N, 'f32', None, rank, kf, 3)
         f32 = dict(value=N * T * kf / secf, unit=UNIT, ms_per_step=secf / kf * 1e3, steps=kf, warmup=3,
-                   dtype='f32', note='compute_dtype=float32 (ml/cfg.py:96 default) on the same workload')
+                   dtype='f32', matmul_precision=m.matmul_precision(),
+                   note='compute_dtype=float32 (ml/cfg.py:96 default) on the same workload; Dense products on '
+                        'tcgen05.mma.kind::tf32 (mlb_gemm_tf32_tc), XLA:GPU\'s default f32 dot precision; '
+                        'MLB_MATMUL_PRECISION=highest selects exact fp32 FFMA')
 
     # ---- cfg4: recurrent (LSTM) actor-critic with BPTT minibatches, N = 1 only --------------
     cfg4 = None

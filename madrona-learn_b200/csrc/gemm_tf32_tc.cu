@@ -14,8 +14,8 @@
 // memory.  A k-block is 32 fp32 = one 128-byte swizzle row (K-major: one 32(k) x 128(m) SWIZZLE_128B box;
 // MN-major: 32(mn) x 32(k) boxes, 4096 B apart, in the 32-byte-atom 128 B swizzle that is the only MN-major
 // layout tcgen05 accepts for 32-bit operands), UMMA K = 8 (32 bytes).  Kernel anatomy as there: warp 0 TMA producer, warp 1 TMEM
-// allocation + single-thread MMA issue, warps 2-5 epilogue (tcgen05.ld -> fp32 store or red.global.add.v4 for
-// accumulate / split-K).  All mbarrier waits are bounded.
+// allocation + single-thread MMA issue, warps 2-5 epilogue (tcgen05.ld -> swizzled smem panels -> TMA store, or
+// red.global.add.v4 for accumulate / split-K).  All mbarrier waits are bounded.
 #include "tc_common.cuh"
 
 namespace {
@@ -54,14 +54,18 @@ __device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t saddr, uint32_t lbo_
 
 // ATOMIC: fp32 vector reductions into a pre-initialised C (accumulate and / or split-K)
 // ROUND:  the tensor core drops the low 13 mantissa bits of an fp32 operand (a biased conversion: every product
-//         shrinks by ~1e-3).  With ROUND the four epilogue warps, idle during the main loop, convert each landed
+//         shrinks by ~1e-3).  With ROUND the four epilogue warps, idle during the main loop, convert a landed
 //         stage in place with cvt.rna.tf32.f32 (round to nearest) before the MMA thread reads it: the operand
-//         error becomes zero-mean and the products of a 256-deep dot average it out (rel-L2 ~1e-4 instead of
-//         ~1e-3 against the exact product).  The pipeline is then TMA -> round -> MMA per stage.
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC, bool ROUND>
+//         error becomes zero-mean and a 256-deep dot averages it out (rel-L2 2.9e-4 instead of 8.7e-4 against
+//         the exact product, measured).  The pipeline is then TMA -> round -> MMA per stage; the conversion is
+//         bound by shared-memory bandwidth (read + write of the stage), so ROUND = 1 converts only the
+//         ACTIVATION operands -- A, and B too in the dW-type product (A MN-major: both operands are
+//         activations) -- and leaves the weight operand, two thirds of a forward stage, to the hardware;
+//         ROUND = 2 converts both operands always.
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC, int ROUND>
 __global__ void __launch_bounds__(T32_THREADS)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 float* __restrict__ C, const float* __restrict__ bias, int ldc, int M, int N, int K,
+                 const __grid_constant__ CUtensorMap tmC, float* __restrict__ C, const float* __restrict__ bias, int ldc, int M, int N, int K,
                  int k_per_split) {
     using L = Smem32<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -163,7 +167,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&full_bar[s], (kb / STAGES) & 1, 0x74);
                 const uint32_t base = smem_u32(smem + s * L::STAGE_BYTES) + et * 16;
 #pragma unroll 8
-                for (int v = 0; v < L::STAGE_BYTES / (128 * 16); ++v) {
+                for (int v = 0; v < ((ROUND == 2 || A_MN) ? L::STAGE_BYTES : L::A_BYTES) / (128 * 16); ++v) {
                     uint32_t a, b, c, d;
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                                  : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(base + v * 2048));
@@ -182,32 +186,72 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(acc_bar, 0, 0x73);
             tcgen05_fence_after();
             const bool add_bias = bias != nullptr && blockIdx.z == 0;
+            if (ATOMIC) {
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = n0 + c * 32;
-                if (col0 >= N) break;                                   // warp-uniform
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
-                if (row < M) {
-                    float* dst = C + (long long)row * ldc + col0;
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= N) break;                                   // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+                    if (row < M) {
+                        float* dst = C + (long long)row * ldc + col0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (col0 + j < N) {                             // N % 4 == 0
-                            float4 v;
-                            v.x = __uint_as_float(r[j]);     v.y = __uint_as_float(r[j + 1]);
-                            v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
-                            if (add_bias) {
-                                const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
-                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                            }
-                            if (ATOMIC)
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j < N) {                             // N % 4 == 0
+                                float4 v;
+                                v.x = __uint_as_float(r[j]);     v.y = __uint_as_float(r[j + 1]);
+                                v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+                                if (add_bias) {
+                                    const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+                                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                                }
                                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                                              ::"l"(dst + j), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-                            else
-                                *reinterpret_cast<float4*>(dst + j) = v;
+                            }
                         }
                     }
                 }
+            } else {
+                // Coalesced output through TMA: the accumulator is complete, so every operand stage is free; each
+                // warp stages its 32 rows x 32 columns (thread = row) as a SWIZZLE_128B panel in the stage memory
+                // (conflict-free 16-byte shared stores) and one lane hands the panel to cp.async.bulk.tensor --
+                // full 128-byte rows instead of 32 scattered 16-byte pieces per store instruction; rows >= M and
+                // columns >= N are clipped by the tensor map.  Two panels per warp: the store of chunk c drains
+                // while chunk c + 1 is read out of TMEM.
+                uint8_t* panels = smem + quad * 8192;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= N) break;                                   // warp-uniform
+                    uint8_t* panel = panels + (c & 1) * 4096;
+                    if (c >= 2) {
+                        if (lane == 0) tma_store_wait_read<1>();            // the store that last read this panel
+                        __syncwarp();
+                    }
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+                    const uint32_t pa = smem_u32(panel);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v;
+                        v.x = __uint_as_float(r[4 * j]);     v.y = __uint_as_float(r[4 * j + 1]);
+                        v.z = __uint_as_float(r[4 * j + 2]); v.w = __uint_as_float(r[4 * j + 3]);
+                        if (add_bias && col0 + 4 * j < N) {
+                            const float4 b = *reinterpret_cast<const float4*>(bias + col0 + 4 * j);
+                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                                     ::"r"(pa + sw128(lane, j)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, panel, col0, m0 + quad * 32);
+                        tma_store_commit();
+                    }
+                }
+                if (lane == 0) tma_store_wait<0>();
+                __syncwarp();
             }
         }
     }
@@ -236,9 +280,14 @@ int make_map_f32(CUtensorMap* map, const void* base, long long inner, long long 
     return r == CUDA_SUCCESS ? MLB_OK : MLB_EINVAL;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC, bool ROUND>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC, int ROUND>
 int launch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float* C, const float* bias, int ldc,
              int M, int N, int K, int splitk) {
+    CUtensorMap tC{};
+    if (!ATOMIC) {                 // output panels: 32 columns x 32 rows, SWIZZLE_128B
+        const int rc = make_map_f32(&tC, C, N, M, ldc, 32, false);
+        if (rc) return rc;
+    }
     using L = Smem32<BN, STAGES>;
     auto kern = tf32_gemm_kernel<BN, STAGES, A_MN, B_MN, ATOMIC, ROUND>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
@@ -247,11 +296,11 @@ int launch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float
     kps = (kps + BK32 - 1) / BK32 * BK32;
     const int zs = (K + kps - 1) / kps;
     dim3 grid(mlb_cdiv(M, BM), mlb_cdiv(N, BN), zs);
-    e = launch_pdl(kern, grid, dim3(T32_THREADS), L::TOTAL, s, tA, tB, C, bias, ldc, M, N, K, kps);
+    e = launch_pdl(kern, grid, dim3(T32_THREADS), L::TOTAL, s, tA, tB, tC, C, bias, ldc, M, N, K, kps);
     return e == cudaSuccess ? MLB_OK : (int)e;
 }
 
-template <bool A_MN, bool B_MN, bool ROUND>
+template <bool A_MN, bool B_MN, int ROUND>
 int dispatch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float* C, const float* bias, int ldc,
                int M, int N, int K, bool atomic, int splitk, int bn, int stages256) {
 #define GO(BN_, ST_)                                                                                              \
@@ -269,8 +318,9 @@ int dispatch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, flo
 #undef GO
 }
 
-// immutable after first use (read once): MLB_TF32_ROUND=0 keeps the hardware's truncating conversion,
-// MLB_TF32_STAGES=4 the one-CTA-per-SM pipeline of the 256-wide tiles
+// immutable after first use (read once): MLB_TF32_ROUND = 0 hardware conversion only, 1 (default) activations
+// rounded to nearest, 2 both operands; MLB_TF32_STAGES = 2 selects the two-CTAs-per-SM pipeline of the 256-wide
+// tiles (measured slower than 4 stages / one CTA: 55 vs 51 us on 65536 x 256 x 256)
 int tf32_knob(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -314,7 +364,7 @@ MLB_API int mlb_gemm_tf32_tc(void* stream, const float* A, const float* B, float
     if (rc) return rc;
     cudaStream_t s = mlb_stream(stream);
     const bool atomic = accumulate != 0;
-    static const int round = tf32_knob("MLB_TF32_ROUND", 1), st256 = tf32_knob("MLB_TF32_STAGES", 2);
+    static const int round = tf32_knob("MLB_TF32_ROUND", 1), st256 = tf32_knob("MLB_TF32_STAGES", 4);
 #define DISPATCH(R_)                                                                                                    \
     do {                                                                                                                \
         if (!a_mn && !b_mn) return dispatch32<false, false, R_>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn, st256); \
@@ -322,7 +372,8 @@ MLB_API int mlb_gemm_tf32_tc(void* stream, const float* A, const float* B, float
         if (a_mn) return dispatch32<true, false, R_>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn, st256);            \
         return dispatch32<false, true, R_>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn, st256);                      \
     } while (0)
-    if (round) DISPATCH(true);
-    DISPATCH(false);
+    if (round == 1) DISPATCH(1);
+    if (round >= 2) DISPATCH(2);
+    DISPATCH(0);
 #undef DISPATCH
 }

@@ -30,10 +30,11 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
-# compute_dtype=float32 products: 'tf32' = tcgen05.mma.kind::tf32 (what XLA:GPU runs for an f32 dot at its
-# default precision, i.e. the reference's default: ml/cfg.py:96), 'highest' = exact fp32 FFMA (SIMT).
-# MLB_MATMUL_PRECISION / set_matmul_precision() mirror jax_default_matmul_precision.
-_PRECISION = {'tf32': os.environ.get('MLB_MATMUL_PRECISION', 'highest').lower() in ('tf32', 'default')}
+# compute_dtype=float32 products: 'tf32' (the default) = tcgen05.mma.kind::tf32, what XLA:GPU runs for an f32 dot
+# at its default precision, i.e. the reference's default configuration (ml/cfg.py:96); 'highest' = exact fp32 FFMA
+# (SIMT).  MLB_MATMUL_PRECISION / set_matmul_precision() mirror jax_default_matmul_precision; the exact-parity
+# test suites pin 'highest' (tests/conftest.py).
+_PRECISION = {'tf32': os.environ.get('MLB_MATMUL_PRECISION', 'tf32').lower() in ('tf32', 'default')}
 
 
 def set_matmul_precision(precision):

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# compute_dtype=float32 parity tests compare against the oracle at fp32 tolerances: exact FFMA products.  The
+# library default ('tf32', like XLA:GPU) is covered by tests/test_tf32_gpu.py, which sets the precision itself.
+os.environ.setdefault('MLB_MATMUL_PRECISION', 'highest')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
