@@ -458,6 +458,9 @@ typedef struct mlb_segment {
     float target;               /* kind 1: initial L2 norm; kind 2: num_features */
 } mlb_segment;
 int mlb_fill_zero(void* stream, void* p, size_t bytes);
+/* rows x cols block of a row-major fp32 matrix with row stride ld elements (BackboneSeparate: the  */
+/* off-diagonal blocks of the fused head gradient, ml/actor_critic.py:247-303)                     */
+int mlb_fill_zero_2d(void* stream, float* p, int rows, int cols, int ld);
 int mlb_copy_bytes(void* stream, const void* src, void* dst, size_t bytes);
 size_t mlb_sumsq_workspace(long long n);
 int mlb_sumsq_f32(void* stream, const float* x, long long n, double* out, void* ws, size_t ws_bytes);

@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmlb200.so')
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                             ctypes.c_float, ctypes.c_size_t)
@@ -113,6 +113,7 @@ SIGNATURES = {
     'mlb_ppo_loss_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, c_ll, c_ll,
                                  c_float, c_float, c_int, P, P, P, P, c_size_t, P, c_int]),
     'mlb_fill_zero': (c_int, [P, P, c_size_t]),
+    'mlb_fill_zero_2d': (c_int, [P, P, c_int, c_int, c_int]),
     'mlb_copy_bytes': (c_int, [P, P, P, c_size_t]),
     'mlb_sumsq_workspace': (c_size_t, [c_ll]),
     'mlb_sumsq_f32': (c_int, [P, P, c_ll, P, P, c_size_t]),

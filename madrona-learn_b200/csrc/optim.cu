@@ -302,6 +302,15 @@ MLB_API int mlb_fill_zero(void* stream, void* p, size_t bytes) {
     return e == cudaSuccess ? MLB_OK : (int)e;
 }
 
+// rows x cols block of a row-major fp32 matrix with row stride ld (elements): cudaMemset2DAsync, a memset node
+// in a captured graph like mlb_fill_zero
+MLB_API int mlb_fill_zero_2d(void* stream, float* p, int rows, int cols, int ld) {
+    MLB_REQUIRE(rows >= 0 && cols >= 0 && ld >= cols && (p || rows == 0 || cols == 0));
+    if (rows == 0 || cols == 0) return MLB_OK;
+    cudaError_t e = cudaMemset2DAsync(p, (size_t)ld * 4, 0, (size_t)cols * 4, (size_t)rows, mlb_stream(stream));
+    return e == cudaSuccess ? MLB_OK : (int)e;
+}
+
 MLB_API int mlb_copy_bytes(void* stream, const void* src, void* dst, size_t bytes) {
     MLB_REQUIRE((src && dst) || bytes == 0);
     if (bytes == 0) return MLB_OK;

@@ -18,7 +18,8 @@ import torch
 
 from . import _lib
 from ._lib import c_float, c_int, c_ll, c_size_t, call, ptr
-from .actor_critic import ActorCritic, BackboneEncoder, BackboneShared, RecurrentBackboneEncoder
+from .actor_critic import (ActorCritic, BackboneEncoder, BackboneSeparate, BackboneShared,
+                           RecurrentBackboneEncoder)
 from .cfg import ContinuousActionsConfig, DiscreteActionsConfig
 from .models import (MLP, DenseLayerContinuousActor, DenseLayerCritic, DenseLayerDiscreteActor, DreamerV3Critic,
                      HLGaussCritic)
@@ -92,11 +93,27 @@ class PolicyProgram:
             raise NotImplementedError('compute_dtype must be float32 (SIMT) or bfloat16 (tcgen05)')
         self.tc = compute_dtype == torch.bfloat16
         bb = actor_critic.backbone
-        if not isinstance(bb, BackboneShared):
-            raise NotImplementedError('only BackboneShared is lowered (BackboneSeparate: next)')
+        if not isinstance(bb, (BackboneShared, BackboneSeparate)):
+            raise NotImplementedError('backbone must be BackboneShared or BackboneSeparate')
         if bb.prefix is not None and not getattr(bb.prefix, 'is_identity', False):
-            raise NotImplementedError('BackboneShared.prefix must be None (obs are one [N, D] tensor)')
-        enc = bb.encoder
+            raise NotImplementedError('Backbone.prefix must be None (obs are one [N, D] tensor)')
+        # BackboneSeparate (ml/actor_critic.py:247-303): two encoder towers on the same processed observations,
+        # the actor head on the actor tower's features, the critic head on the critic tower's.  Lowered as NT = 2
+        # MLP stacks in the one arena (flat layer index t * L + i) feeding ONE head GEMM over the concatenated
+        # features [feat_actor | feat_critic] whose weight is block-diagonal: the off-diagonal blocks are zero
+        # at init and their gradient is cleared before the optimiser sees it (mlb_fill_zero_2d), so they stay
+        # exactly zero and the product equals the two separate Dense heads.
+        self.NT = 2 if isinstance(bb, BackboneSeparate) else 1
+        if self.NT == 2:
+            enc, enc_c = bb.actor_encoder, bb.critic_encoder
+            if not (isinstance(enc, BackboneEncoder) and isinstance(enc_c, BackboneEncoder) and
+                    isinstance(enc.net, MLP) and isinstance(enc_c.net, MLP)):
+                raise NotImplementedError('BackboneSeparate encoders must be BackboneEncoder(net=MLP) '
+                                          '(recurrent separate towers are not lowered)')
+            if (enc.net.num_channels, enc.net.num_layers) != (enc_c.net.num_channels, enc_c.net.num_layers):
+                raise NotImplementedError('BackboneSeparate: actor and critic MLPs must have the same shape')
+        else:
+            enc = bb.encoder
         if not isinstance(enc, (BackboneEncoder, RecurrentBackboneEncoder)) or not isinstance(enc.net, MLP):
             raise NotImplementedError('encoder must be [Recurrent]BackboneEncoder(net=MLP[, rnn=LSTM])')
         self._rnn_desc = enc.rnn if isinstance(enc, RecurrentBackboneEncoder) else None
@@ -167,17 +184,19 @@ class PolicyProgram:
         self._buckets_c = (ctypes.c_int32 * self.A)(*buckets) if self.continuous is None else None
         # ---- arena layout -------------------------------------------------------------
         off = 0
-        self.layer_off = []
-        d = self.obs_dim
-        for _ in range(self.L):
-            k_off = off
-            off += d * self.H
-            ln_off = off                      # scale[H] | bias[H] contiguous (one LN segment)
-            off += 2 * self.H
-            self.layer_off.append((k_off, ln_off, d))
-            d = self.H
+        self.layer_off = []                   # flat layer index f = tower * L + i
+        self.LT = self.NT * self.L
+        for _t in range(self.NT):
+            d = self.obs_dim
+            for _ in range(self.L):
+                k_off = off
+                off += d * self.H
+                ln_off = off                  # scale[H] | bias[H] contiguous (one LN segment)
+                off += 2 * self.H
+                self.layer_off.append((k_off, ln_off, d))
+                d = self.H
         self.lstm = None
-        self.feat = self.H
+        self.feat = self.H * self.NT          # BackboneSeparate: [actor features | critic features]
         if self._rnn_desc is not None:
             from .recurrent import LSTMLowering
             self.lstm = LSTMLowering(self, self._rnn_desc, self.H, off)
@@ -224,16 +243,32 @@ class PolicyProgram:
         return (self._view(arena, self.head_w_off, self.feat, self.NH),
                 self._view(arena, self.head_b_off, self.NH))
 
+    def _lname(self, f):
+        """Key of flat layer f in initial_weight_norms (tower 1 = the critic encoder of BackboneSeparate)."""
+        return f'Dense_{f}' if f < self.L else f'critic/Dense_{f - self.L}'
+
+    def _net_tree(self, a, t):
+        net = {}
+        for i in range(self.L):
+            k, s, b = self.layer_views(a, t * self.L + i)
+            net[f'Dense_{i}'] = {'kernel': k}
+            net[f'LayerNorm_{i}'] = {'impl': {'scale': s, 'bias': b}}
+        return net
+
     def param_tree(self, arena=None):
         """flax-style nested dict of VIEWS into the arena (ml/train_state.py:34-40 `params`)."""
         a = self.params if arena is None else arena
-        net = {}
-        for i in range(self.L):
-            k, s, b = self.layer_views(a, i)
-            net[f'Dense_{i}'] = {'kernel': k}
-            net[f'LayerNorm_{i}'] = {'impl': {'scale': s, 'bias': b}}
         W, B = self.head_views(a)
-        enc = {'net': net}
+        if self.NT == 2:                      # ml/actor_critic.py:247-250: actor_encoder / critic_encoder
+            H = self.H
+            return {
+                'backbone': {'actor_encoder': {'net': self._net_tree(a, 0)},
+                             'critic_encoder': {'net': self._net_tree(a, 1)}},
+                'actor': {'impl': {'kernel': W[:H, :self.sumA], 'bias': B[:self.sumA]}},
+                'critic': {'Dense_0': {'kernel': W[H:, self.sumA:self.sumA + self.V],
+                                       'bias': B[self.sumA:self.sumA + self.V]}},
+            }
+        enc = {'net': self._net_tree(a, 0)}
         if self.lstm is not None:
             enc['rnn'] = self.lstm.param_tree(a)
         return {
@@ -257,16 +292,17 @@ class PolicyProgram:
                 q = q.t()
             return (scale * q[:rows, :cols]).to(F32)
         host = torch.zeros(self.num_params, dtype=F32)
-        for i in range(self.L):
+        for i in range(self.LT):
             k_off, ln_off, d = self.layer_off[i]
             host[k_off:k_off + d * self.H] = orth(d, self.H, self.mlp.weight_init_scale).reshape(-1)
             host[ln_off:ln_off + self.H] = 1.0
         if self.lstm is not None:
             self.lstm.init_host(host, orth)
         W = torch.zeros(self.feat, self.NH, dtype=F32)
-        W[:, :self.sumA] = orth(self.feat, self.sumA, self.ac.actor.weight_init_scale)
+        fa = self.H if self.NT == 2 else self.feat          # BackboneSeparate: block-diagonal head
+        W[:fa, :self.sumA] = orth(fa, self.sumA, self.ac.actor.weight_init_scale)
         if not (self.twohot or self.hlgauss):      # DreamerV3Critic / HLGaussCritic are zero-initialised (ml/models.py:159,261)
-            W[:, self.sumA:self.sumA + 1] = orth(self.feat, 1, self.ac.critic.weight_init_scale)
+            W[self.feat - fa:, self.sumA:self.sumA + 1] = orth(fa, 1, self.ac.critic.weight_init_scale)
         host[self.head_w_off:self.head_w_off + W.numel()] = W.reshape(-1)
         self.params.copy_(host)
         self.finalize_params()
@@ -274,16 +310,18 @@ class PolicyProgram:
     def load_oracle_params(self, p):
         """Load a parameter tree in oracle/nn.py format (tests)."""
         host = torch.zeros(self.num_params, dtype=F32)
-        for i in range(self.L):
-            k_off, ln_off, d = self.layer_off[i]
-            host[k_off:k_off + d * self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['kernel'], np.float32)).reshape(-1)
-            host[ln_off:ln_off + self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['scale'], np.float32))
-            host[ln_off + self.H:ln_off + 2 * self.H] = torch.from_numpy(np.asarray(p['mlp'][i]['bias'], np.float32))
+        for f in range(self.LT):
+            k_off, ln_off, d = self.layer_off[f]
+            lyr = p['mlp'][f] if f < self.L else p['mlp_critic'][f - self.L]
+            host[k_off:k_off + d * self.H] = torch.from_numpy(np.asarray(lyr['kernel'], np.float32)).reshape(-1)
+            host[ln_off:ln_off + self.H] = torch.from_numpy(np.asarray(lyr['scale'], np.float32))
+            host[ln_off + self.H:ln_off + 2 * self.H] = torch.from_numpy(np.asarray(lyr['bias'], np.float32))
         if self.lstm is not None:
             self.lstm.load_oracle(host, p['lstm'])
         W = torch.zeros(self.feat, self.NH, dtype=F32)
-        W[:, :self.sumA] = torch.from_numpy(np.asarray(p['actor']['kernel'], np.float32))
-        W[:, self.sumA:self.sumA + self.V] = torch.from_numpy(np.asarray(p['critic']['kernel'], np.float32))
+        fa = self.H if self.NT == 2 else self.feat
+        W[:fa, :self.sumA] = torch.from_numpy(np.asarray(p['actor']['kernel'], np.float32))
+        W[self.feat - fa:, self.sumA:self.sumA + self.V] = torch.from_numpy(np.asarray(p['critic']['kernel'], np.float32))
         B = torch.zeros(self.NH, dtype=F32)
         B[:self.sumA] = torch.from_numpy(np.asarray(p['actor']['bias'], np.float32))
         B[self.sumA:self.sumA + self.V] = torch.from_numpy(np.asarray(p['critic']['bias'], np.float32))
@@ -294,12 +332,17 @@ class PolicyProgram:
 
     def to_oracle_params(self, arena=None):
         t = self.param_tree(arena)
-        net = t['backbone']['encoder']['net']
         c = lambda x: x.detach().cpu().numpy().copy()
+        layers = lambda net: [{'kernel': c(net[f'Dense_{i}']['kernel']),
+                               'scale': c(net[f'LayerNorm_{i}']['impl']['scale']),
+                               'bias': c(net[f'LayerNorm_{i}']['impl']['bias'])} for i in range(self.L)]
         extra = {'lstm': self.lstm.to_oracle(self.params if arena is None else arena)} if self.lstm is not None else {}
-        return {**extra, 'mlp': [{'kernel': c(net[f'Dense_{i}']['kernel']),
-                         'scale': c(net[f'LayerNorm_{i}']['impl']['scale']),
-                         'bias': c(net[f'LayerNorm_{i}']['impl']['bias'])} for i in range(self.L)],
+        if self.NT == 2:
+            extra['mlp_critic'] = layers(t['backbone']['critic_encoder']['net'])
+            net = t['backbone']['actor_encoder']['net']
+        else:
+            net = t['backbone']['encoder']['net']
+        return {**extra, 'mlp': layers(net),
                 'actor': {'kernel': c(t['actor']['impl']['kernel']), 'bias': c(t['actor']['impl']['bias'])},
                 'critic': {'kernel': c(t['critic']['Dense_0']['kernel']), 'bias': c(t['critic']['Dense_0']['bias'])}}
 
@@ -307,11 +350,18 @@ class PolicyProgram:
         """initial_weight_norms in the parameter tree's shape (ml/train_state.py:413-423): the initial L2
         norm at every backbone `kernel` leaf, None at every other leaf and under actor / critic."""
         n = self.initial_weight_norms
-        net = {}
-        for i in range(self.L):
-            net[f'Dense_{i}'] = {'kernel': float(n[f'Dense_{i}'])}
-            net[f'LayerNorm_{i}'] = {'impl': {'scale': None, 'bias': None}}
-        enc = {'net': net}
+
+        def net_of(t):
+            net = {}
+            for i in range(self.L):
+                net[f'Dense_{i}'] = {'kernel': float(n[self._lname(t * self.L + i)])}
+                net[f'LayerNorm_{i}'] = {'impl': {'scale': None, 'bias': None}}
+            return net
+        if self.NT == 2:
+            return {'backbone': {'actor_encoder': {'net': net_of(0)}, 'critic_encoder': {'net': net_of(1)}},
+                    'actor': {'impl': {'kernel': None, 'bias': None}},
+                    'critic': {'Dense_0': {'kernel': None, 'bias': None}}}
+        enc = {'net': net_of(0)}
         if self.lstm is not None:
             cells = {}
             for li in range(self.lstm.RL):
@@ -328,17 +378,17 @@ class PolicyProgram:
         """Record initial kernel norms (ml/train_state.py:413-423) -> device segment table."""
         self.initial_weight_norms = {}
         host = self.params.detach().cpu()
-        for i in range(self.L):
+        for i in range(self.LT):
             k_off, ln_off, d = self.layer_off[i]
             n0 = float(torch.linalg.vector_norm(host[k_off:k_off + d * self.H].double()))
-            self.initial_weight_norms[f'Dense_{i}'] = n0
+            self.initial_weight_norms[self._lname(i)] = n0
         self.rebuild_segments()
 
     def refresh_bf16(self):
         """Re-derive the bf16 operand copies from the fp32 master weights (tensor-core path)."""
         if not self.tc:
             return
-        for i in range(self.L):
+        for i in range(self.LT):
             k, _, _ = self.layer_views(self.params, i)
             d = self.layer_off[i][2]
             call('mlb_cast_weight_bf16', ptr(k), ptr(self.w_t[i]), ptr(self.w_c[i]), c_int(d), c_int(self.H),
@@ -353,9 +403,9 @@ class PolicyProgram:
         self.refresh_bf16()
         segs, copies = [], []
         none = _lib.Bf16Copy(None, None, 0, 0, 0, 0)
-        for i in range(self.L):
+        for i in range(self.LT):
             k_off, ln_off, d = self.layer_off[i]
-            segs.append(_lib.Segment(k_off, d * self.H, 1, float(self.initial_weight_norms[f'Dense_{i}'])))
+            segs.append(_lib.Segment(k_off, d * self.H, 1, float(self.initial_weight_norms[self._lname(i)])))
             copies.append(_lib.Bf16Copy(self.w_t[i].data_ptr(), self.w_c[i].data_ptr(), d, self.H, d, self.H)
                           if self.tc else none)
             segs.append(_lib.Segment(ln_off, 2 * self.H, 2, float(self.H)))
@@ -403,7 +453,7 @@ class PolicyProgram:
             dev = self.device
             AT = torch.bfloat16 if self.tc else F32
             w = dict(rows=rows, z=None if self.tc else torch.empty(rows, self.H, dtype=F32, device=dev),
-                     y=[torch.empty(rows, self.H, dtype=AT, device=dev) for _ in range(2)],
+                     y=[torch.empty(rows, self.H, dtype=AT, device=dev) for _ in range(2 * self.NT)],
                      head=torch.empty(rows, self.NH, dtype=F32, device=dev))
             if self.tc:
                 w['x'] = torch.empty(rows, self.obs_dim, dtype=AT, device=dev)
@@ -416,17 +466,17 @@ class PolicyProgram:
             dev = self.device
             AT = torch.bfloat16 if self.tc else F32
             e = lambda *s, dtype=F32: torch.empty(*s, dtype=dtype, device=dev)
-            w = dict(rows=rows, z=None if self.tc else [e(rows, self.H) for _ in range(self.L)],
-                     y=[e(rows, self.H, dtype=AT) for _ in range(self.L)],
-                     stats=None if self.tc else [e(rows, 2) for _ in range(self.L)],
+            w = dict(rows=rows, z=None if self.tc else [e(rows, self.H) for _ in range(self.LT)],
+                     y=[e(rows, self.H, dtype=AT) for _ in range(self.LT)],
+                     stats=None if self.tc else [e(rows, 2) for _ in range(self.LT)],
                      head=e(rows, self.NH), dhead=e(rows, self.NH, dtype=AT),
                      dy=e(rows, self.H, dtype=AT), dz=e(rows, self.H, dtype=AT),
                      loss_ws=torch.zeros(_lib.lib().mlb_ppo_loss_workspace(rows) + 16, dtype=torch.uint8, device=dev),
                      stats_out=torch.zeros(ctypes.sizeof(_lib.PPOStats), dtype=torch.uint8, device=dev))
             if self.tc:
                 w['x'] = e(rows, self.obs_dim, dtype=AT)
-                w['xh'] = [e(rows, self.H, dtype=AT) for _ in range(self.L)]     # normalised pre-activations
-                w['rstd'] = [e(rows) for _ in range(self.L)]
+                w['xh'] = [e(rows, self.H, dtype=AT) for _ in range(self.LT)]    # normalised pre-activations
+                w['rstd'] = [e(rows) for _ in range(self.LT)]
                 w['dzs'] = [w['dz'], e(rows, self.H, dtype=AT), w['dy']]       # rotating dZ buffers of the backward
                 w['z'] = None                                                    # never materialised
             self._train_ws = w
@@ -439,17 +489,20 @@ class PolicyProgram:
         """obs f32 [rows, D] -> head f32 [rows, NH] (logits | value).  Recurrent encoders update
         `rnn_states` ([c], [h]) in place."""
         w = self.infer_ws(rows)
-        if self.tc:
-            return self._forward_tc(obs, rows, w, [w['y'][i & 1] for i in range(self.L)], None, None,
-                                    rnn_states=rnn_states)
-        x, d = obs, self.obs_dim
-        for i in range(self.L):
-            k, s, b = self.layer_views(self.params, i)
-            gemm(x, k, w['z'], None, rows, self.H, d, d, self.H, self.H)
-            y = w['y'][i & 1]
-            call('mlb_ln_relu_fwd_f32', ptr(w['z']), ptr(s), ptr(b), ptr(y), ptr(None), c_ll(rows), c_int(self.H))
-            x, d = y, self.H
-        xs = [x] if self.lstm is None else self.lstm.step_infer(x, rows, rnn_states, w)
+        if self.tc:                          # two ping-pong activation buffers per tower
+            return self._forward_tc(obs, rows, w, [w['y'][2 * (f // self.L) + (f & 1)] for f in range(self.LT)],
+                                    None, None, rnn_states=rnn_states)
+        feats = []
+        for t in range(self.NT):
+            x, d = obs, self.obs_dim
+            for i in range(self.L):
+                k, s, b = self.layer_views(self.params, t * self.L + i)
+                gemm(x, k, w['z'], None, rows, self.H, d, d, self.H, self.H)
+                y = w['y'][2 * t + (i & 1)]
+                call('mlb_ln_relu_fwd_f32', ptr(w['z']), ptr(s), ptr(b), ptr(y), ptr(None), c_ll(rows), c_int(self.H))
+                x, d = y, self.H
+            feats.append(x)
+        xs = feats if self.lstm is None else self.lstm.step_infer(feats[0], rows, rnn_states, w)
         return self._head_fwd_f32(xs, w['head'], rows)
 
     def _head_fwd_f32(self, xs, head, rows):
@@ -475,14 +528,16 @@ class PolicyProgram:
         out of TMEM] -> head GEMM (fp32 out + bias).  Training also stashes xhat (bf16) and rstd."""
         if not x_ready:                    # x_ready: the minibatch gather already wrote the bf16 copy into w['x']
             call('mlb_cast_f32_bf16', ptr(obs), ptr(w['x']), c_ll(rows * self.obs_dim))
-        x, d = w['x'], self.obs_dim
-        for i in range(self.L):
-            _, s, b = self.layer_views(self.params, i)
-            call('mlb_dense_ln_relu_fwd_tc', ptr(x), ptr(self.w_t[i]), ptr(s), ptr(b), ptr(ys[i]),
-                 ptr(None if xhs is None else xhs[i]), ptr(None if rstds is None else rstds[i]),
-                 c_int(rows), c_int(d), c_int(self.H), c_int(d), c_int(d))
-            x, d = ys[i], self.H
-        xs = [x]
+        xs = []
+        for t in range(self.NT):
+            x, d = w['x'], self.obs_dim
+            for i in range(t * self.L, (t + 1) * self.L):
+                _, s, b = self.layer_views(self.params, i)
+                call('mlb_dense_ln_relu_fwd_tc', ptr(x), ptr(self.w_t[i]), ptr(s), ptr(b), ptr(ys[i]),
+                     ptr(None if xhs is None else xhs[i]), ptr(None if rstds is None else rstds[i]),
+                     c_int(rows), c_int(d), c_int(self.H), c_int(d), c_int(d))
+                x, d = ys[i], self.H
+            xs.append(x)
         if self.lstm is not None:
             if seq is not None:                       # training: the whole T' sequence
                 xs = self.lstm.sequence_fwd(x, seq)
@@ -494,7 +549,7 @@ class PolicyProgram:
     def fused_rollout(self):
         """True when mlb_policy_rollout_tc covers this network (bf16, feed-forward MLP encoder that
         fits one CTA's shared memory); MLB_FUSED_ROLLOUT=0 keeps the layer-by-layer path."""
-        if (not self.tc or self.lstm is not None or self.continuous is not None or
+        if (not self.tc or self.lstm is not None or self.continuous is not None or self.NT != 1 or
                 os.environ.get('MLB_FUSED_ROLLOUT', '1') == '0'):
             return False
         if self.H > 256 or self.H % 64 or self.L > 4 or self.NH > 256 or self.obs_dim > 256:
@@ -540,14 +595,17 @@ class PolicyProgram:
         w = self.train_ws(rows)
         if self.tc:
             return self._forward_tc(obs, rows, w, w['y'], w['xh'], w['rstd'], x_ready, seq=seq)
-        x, d = obs, self.obs_dim
-        for i in range(self.L):
-            k, s, b = self.layer_views(self.params, i)
-            gemm(x, k, w['z'][i], None, rows, self.H, d, d, self.H, self.H)
-            call('mlb_ln_relu_fwd_f32', ptr(w['z'][i]), ptr(s), ptr(b), ptr(w['y'][i]), ptr(w['stats'][i]),
-                 c_ll(rows), c_int(self.H))
-            x, d = w['y'][i], self.H
-        xs = [x] if self.lstm is None else self.lstm.sequence_fwd(x, seq)
+        feats = []
+        for t in range(self.NT):
+            x, d = obs, self.obs_dim
+            for i in range(t * self.L, (t + 1) * self.L):
+                k, s, b = self.layer_views(self.params, i)
+                gemm(x, k, w['z'][i], None, rows, self.H, d, d, self.H, self.H)
+                call('mlb_ln_relu_fwd_f32', ptr(w['z'][i]), ptr(s), ptr(b), ptr(w['y'][i]), ptr(w['stats'][i]),
+                     c_ll(rows), c_int(self.H))
+                x, d = w['y'][i], self.H
+            feats.append(x)
+        xs = feats if self.lstm is None else self.lstm.sequence_fwd(feats[0], seq)
         return self._head_fwd_f32(xs, w['head'], rows)
 
     def backward(self, obs, rows, seq=None):
@@ -562,27 +620,36 @@ class PolicyProgram:
             fw = self.lstm.RH
             pairs = [(lw['h_seq'].view(rows, fw), lw['d_hseq'].view(rows, fw)) for lw in lws]
         else:
-            fw = self.feat
-            pairs = [(w['y'][self.L - 1], w['dy'])]
-        # dW_h = feat^T dhead ; db_h = colsum(dhead) ; dfeat = dhead W_h^T   (per feature slice)
-        for l, (feat, dfeat) in enumerate(pairs):
-            gemm(feat, w['dhead'], gW[l * fw:(l + 1) * fw], None, fw, self.NH, rows, fw, self.NH, self.NH,
-                 ta=1, tb=0, accumulate=1, splitk=_splitk_for(fw, self.NH, rows))
-            gemm(w['dhead'], W[l * fw:(l + 1) * fw], dfeat, None, rows, fw, self.NH, self.NH, self.NH, fw,
-                 ta=0, tb=1)
-        if self.lstm is not None:
+            fw = self.H
+            pairs = None
+        if pairs is not None:
+            # dW_h = feat^T dhead ; db_h = colsum(dhead) ; dfeat = dhead W_h^T   (per feature slice)
+            for l, (feat, dfeat) in enumerate(pairs):
+                gemm(feat, w['dhead'], gW[l * fw:(l + 1) * fw], None, fw, self.NH, rows, fw, self.NH, self.NH,
+                     ta=1, tb=0, accumulate=1, splitk=_splitk_for(fw, self.NH, rows))
+                gemm(w['dhead'], W[l * fw:(l + 1) * fw], dfeat, None, rows, fw, self.NH, self.NH, self.NH, fw,
+                     ta=0, tb=1)
             self.lstm.sequence_bwd(w['y'][self.L - 1], seq, w['dy'])
-        for i in range(self.L - 1, -1, -1):
-            k, s, b = self.layer_views(self.params, i)
-            gk, gs, gb = self.layer_views(self.grads, i)
-            d = self.layer_off[i][2]
-            call('mlb_ln_relu_bwd_f32', ptr(w['dy']), ptr(w['z'][i]), ptr(w['stats'][i]), ptr(s), ptr(b),
-                 ptr(w['dz']), ptr(gs), ptr(gb), c_ll(rows), c_int(self.H))
-            x = obs if i == 0 else w['y'][i - 1]
-            gemm(x, w['dz'], gk, None, d, self.H, rows, d, self.H, self.H, ta=1, tb=0,
-                 accumulate=1, splitk=_splitk_for(d, self.H, rows))
-            if i > 0:
-                gemm(w['dz'], k, w['dy'], None, rows, d, self.H, self.H, self.H, d, ta=0, tb=1)
+        for t in range(self.NT):
+            base = t * self.L
+            if pairs is None:                 # this tower's slice of the head: dW_h, then dfeat -> w['dy']
+                feat = w['y'][base + self.L - 1]
+                gemm(feat, w['dhead'], gW[t * fw:(t + 1) * fw], None, fw, self.NH, rows, fw, self.NH, self.NH,
+                     ta=1, tb=0, accumulate=1, splitk=_splitk_for(fw, self.NH, rows))
+                gemm(w['dhead'], W[t * fw:(t + 1) * fw], w['dy'], None, rows, fw, self.NH, self.NH, self.NH, fw,
+                     ta=0, tb=1)
+            for i in range(base + self.L - 1, base - 1, -1):
+                k, s, b = self.layer_views(self.params, i)
+                gk, gs, gb = self.layer_views(self.grads, i)
+                d = self.layer_off[i][2]
+                call('mlb_ln_relu_bwd_f32', ptr(w['dy']), ptr(w['z'][i]), ptr(w['stats'][i]), ptr(s), ptr(b),
+                     ptr(w['dz']), ptr(gs), ptr(gb), c_ll(rows), c_int(self.H))
+                x = obs if i == base else w['y'][i - 1]
+                gemm(x, w['dz'], gk, None, d, self.H, rows, d, self.H, self.H, ta=1, tb=0,
+                     accumulate=1, splitk=_splitk_for(d, self.H, rows))
+                if i > base:
+                    gemm(w['dz'], k, w['dy'], None, rows, d, self.H, self.H, self.H, d, ta=0, tb=1)
+        self._mask_head_grads()
 
     def _backward_tc(self, rows, w, seq=None):
         """bf16 tensor-core backward.  dW products are MN-major x MN-major split-K GEMMs with
@@ -605,51 +672,70 @@ class PolicyProgram:
         gW, _ = self.head_views(self.grads)       # (head bias grads were accumulated by the loss kernel)
         lws = self.lstm.train_ws(seq['Tp'], seq['M']) if self.lstm is not None else None
         lw = None if lws is None else lws[0]
-        fw = self.feat if lws is None else self.lstm.RH
-        feats = [w['y'][self.L - 1]] if lws is None else [x['h_seq'].view(rows, fw) for x in lws]
+        fw = self.H if lws is None else self.lstm.RH
+        feats = ([w['y'][t * self.L + self.L - 1] for t in range(self.NT)] if lws is None
+                 else [x['h_seq'].view(rows, fw) for x in lws])
         for l, feat in enumerate(feats):
             on_side(lambda feat=feat, l=l: gemm_tc(feat, w['dhead'], gW[l * fw:(l + 1) * fw], None, fw, self.NH, rows,
                                                    fw, self.NH, self.NH, 1, 1, 2, _splitk_tc(fw, self.NH, rows)))
         bufs = w['dzs']                           # rotating dZ buffers (3: a dW may still read the oldest)
         cur = 0
-        i = self.L - 1
-        _, s, b = self.layer_views(self.params, i)
-        _, gs, gb = self.layer_views(self.grads, i)
-        if lw is None:
-            # dfeat = dhead Wh^T fused with the LayerNorm/ReLU backward of the last layer -> dZ_{L-1}
-            call('mlb_dense_dx_lnbwd_tc', ptr(w['dhead']), ptr(self.wh_c), ptr(s), ptr(b), ptr(w['xh'][i]),
-                 ptr(w['rstd'][i]), ptr(bufs[cur]), ptr(gs), ptr(gb), c_int(rows), c_int(self.NH), c_int(self.H),
-                 c_int(self.NH), c_int(self.NH))
-        else:
-            # d(encoder output) = dhead Wh^T (fp32), BPTT through the LSTM, then the gradient to the MLP output
-            # (dz_all W_i) fused with the last layer's LayerNorm/ReLU backward
-            RH4 = 4 * self.lstm.RH
-            for l, x in enumerate(lws):           # rows l*RH.. of wh_c [feat, NH]: the slice's own B[N = RH, K = NH]
-                gemm_tc(w['dhead'], self.wh_c[l * fw:(l + 1) * fw], x['d_hseq'], None, rows, fw, self.NH, self.NH,
-                        self.NH, fw, 0, 0, 0)
-            self.lstm.sequence_bwd(w['y'][i], seq, None)
-            call('mlb_dense_dx_lnbwd_tc', ptr(lw['dz']), ptr(self.lstm.wi_t), ptr(s), ptr(b), ptr(w['xh'][i]),
-                 ptr(w['rstd'][i]), ptr(bufs[cur]), ptr(gs), ptr(gb), c_int(rows), c_int(RH4), c_int(self.H),
-                 c_int(RH4), c_int(RH4))
-        for i in range(self.L - 1, -1, -1):
-            gk, _, _ = self.layer_views(self.grads, i)
-            d = self.layer_off[i][2]
-            x = w['x'] if i == 0 else w['y'][i - 1]
-            dz_cur = bufs[cur]
-            on_side(lambda x=x, dz_cur=dz_cur, gk=gk, d=d: gemm_tc(
-                x, dz_cur, gk, None, d, self.H, rows, d, self.H, self.H, 1, 1, 2, _splitk_tc(d, self.H, rows)))
-            if i > 0:
-                nxt = (cur + 1) % len(bufs)
-                if two and len(bufs) < 3:
-                    main.wait_stream(side)        # the buffer about to be overwritten may still be read
-                _, s, b = self.layer_views(self.params, i - 1)
-                _, gs, gb = self.layer_views(self.grads, i - 1)
-                call('mlb_dense_dx_lnbwd_tc', ptr(dz_cur), ptr(self.w_c[i]), ptr(s), ptr(b), ptr(w['xh'][i - 1]),
-                     ptr(w['rstd'][i - 1]), ptr(bufs[nxt]), ptr(gs), ptr(gb), c_int(rows), c_int(self.H), c_int(d),
-                     c_int(self.H), c_int(self.H))
-                cur = nxt
+        for t in range(self.NT):                  # BackboneSeparate: the critic tower after the actor tower
+            base = t * self.L
+            i = base + self.L - 1
+            _, s, b = self.layer_views(self.params, i)
+            _, gs, gb = self.layer_views(self.grads, i)
+            if lw is None:
+                # dfeat = dhead Wh^T (this tower's rows of Wh) fused with the LayerNorm/ReLU backward of the
+                # tower's last layer -> dZ_{L-1}
+                call('mlb_dense_dx_lnbwd_tc', ptr(w['dhead']), ptr(self.wh_c[t * self.H:(t + 1) * self.H]), ptr(s),
+                     ptr(b), ptr(w['xh'][i]), ptr(w['rstd'][i]), ptr(bufs[cur]), ptr(gs), ptr(gb), c_int(rows),
+                     c_int(self.NH), c_int(self.H), c_int(self.NH), c_int(self.NH))
+            else:
+                # d(encoder output) = dhead Wh^T (fp32), BPTT through the LSTM, then the gradient to the MLP output
+                # (dz_all W_i) fused with the last layer's LayerNorm/ReLU backward
+                RH4 = 4 * self.lstm.RH
+                for l, x in enumerate(lws):       # rows l*RH.. of wh_c [feat, NH]: the slice's own B[N = RH, K = NH]
+                    gemm_tc(w['dhead'], self.wh_c[l * fw:(l + 1) * fw], x['d_hseq'], None, rows, fw, self.NH, self.NH,
+                            self.NH, fw, 0, 0, 0)
+                self.lstm.sequence_bwd(w['y'][i], seq, None)
+                call('mlb_dense_dx_lnbwd_tc', ptr(lw['dz']), ptr(self.lstm.wi_t), ptr(s), ptr(b), ptr(w['xh'][i]),
+                     ptr(w['rstd'][i]), ptr(bufs[cur]), ptr(gs), ptr(gb), c_int(rows), c_int(RH4), c_int(self.H),
+                     c_int(RH4), c_int(RH4))
+            for i in range(base + self.L - 1, base - 1, -1):
+                gk, _, _ = self.layer_views(self.grads, i)
+                d = self.layer_off[i][2]
+                x = w['x'] if i == base else w['y'][i - 1]
+                dz_cur = bufs[cur]
+                on_side(lambda x=x, dz_cur=dz_cur, gk=gk, d=d: gemm_tc(
+                    x, dz_cur, gk, None, d, self.H, rows, d, self.H, self.H, 1, 1, 2, _splitk_tc(d, self.H, rows)))
+                if i > base or t + 1 < self.NT:
+                    nxt = (cur + 1) % len(bufs)
+                    if two and len(bufs) < 3:
+                        main.wait_stream(side)    # the buffer about to be overwritten may still be read
+                    if i > base:
+                        _, s, b = self.layer_views(self.params, i - 1)
+                        _, gs, gb = self.layer_views(self.grads, i - 1)
+                        call('mlb_dense_dx_lnbwd_tc', ptr(dz_cur), ptr(self.w_c[i]), ptr(s), ptr(b), ptr(w['xh'][i - 1]),
+                             ptr(w['rstd'][i - 1]), ptr(bufs[nxt]), ptr(gs), ptr(gb), c_int(rows), c_int(self.H),
+                             c_int(d), c_int(self.H), c_int(self.H))
+                    cur = nxt
         if two:
             main.wait_stream(side)
+        self._mask_head_grads()
+
+    def _mask_head_grads(self):
+        """BackboneSeparate: the head product runs over [actor features | critic features], so the dW GEMMs also
+        fill the two off-diagonal blocks (actor features x critic columns and vice versa); clearing them keeps
+        those weights at their initial zero and out of the gradient norm (ml/actor_critic.py:247-303: the two
+        heads never see the other tower)."""
+        if self.NT != 2:
+            return
+        gW, _ = self.head_views(self.grads)
+        H, nA = self.H, self.sumA
+        base = gW.data_ptr()                   # strided blocks: explicit addresses (ptr() takes contiguous buffers)
+        call('mlb_fill_zero_2d', ctypes.c_void_p(base + 4 * nA), c_int(H), c_int(self.NH - nA), c_int(self.NH))
+        call('mlb_fill_zero_2d', ctypes.c_void_p(base + 4 * H * self.NH), c_int(H), c_int(nA), c_int(self.NH))
 
     @property
     def loss_flags(self):

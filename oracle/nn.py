@@ -250,6 +250,14 @@ def actor_critic_fwd(params, obs, q=None, seq=None):
     seq (recurrent, ActorCritic.update -> RecurrentBackboneEncoder.sequence :179-199):
     dict(Tp, M, ends [T', M], c0 [list of M x RH], h0) -- obs rows are in [T', M] order."""
     feat, caches = mlp_fwd(obs, params['mlp'], q)
+    if 'mlp_critic' in params:
+        # BackboneSeparate (ml/actor_critic.py:247-303): a second encoder on the same observations feeds the
+        # critic head; the actor head sees only the actor encoder's features
+        qq = q or _id
+        cfeat, ccaches = mlp_fwd(obs, params['mlp_critic'], q)
+        logits = feat @ qq(params['actor']['kernel']) + params['actor']['bias']
+        critic = cfeat @ qq(params['critic']['kernel']) + params['critic']['bias']
+        return logits, critic, (feat, caches, cfeat, ccaches, 'separate')
     if 'lstm' in params:
         Tp, M = seq['Tp'], seq['M']
         xs = feat.reshape(Tp, M, -1)
@@ -264,6 +272,15 @@ def actor_critic_fwd(params, obs, q=None, seq=None):
 
 
 def actor_critic_bwd(params, cache, dlogits, dcritic, q=None):
+    if len(cache) == 5:                       # BackboneSeparate: two independent towers
+        feat, caches, cfeat, ccaches, _ = cache
+        qq = q or _id
+        dl, dc = qq(dlogits), qq(dcritic)
+        g = {'actor': {'kernel': feat.T @ dl, 'bias': dlogits.sum(axis=0)},
+             'critic': {'kernel': cfeat.T @ dc, 'bias': dcritic.sum(axis=0)}}
+        _, g['mlp'] = mlp_bwd(qq(dl @ qq(params['actor']['kernel']).T), caches, params['mlp'], q=q)
+        _, g['mlp_critic'] = mlp_bwd(qq(dc @ qq(params['critic']['kernel']).T), ccaches, params['mlp_critic'], q=q)
+        return g
     if len(cache) == 4:                       # recurrent
         rfeat, caches, lcaches, (Tp, M) = cache
         g = {'actor': {'kernel': rfeat.T @ dlogits, 'bias': dlogits.sum(axis=0)},
@@ -284,7 +301,7 @@ def actor_critic_bwd(params, cache, dlogits, dcritic, q=None):
 
 
 def init_params(rng, obs_dim, hidden, num_layers, buckets, critic_dim=1, dtype=np.float32,
-                lstm_hidden=0, lstm_layers=0):
+                lstm_hidden=0, lstm_layers=0, separate=False):
     """Orthogonal-ish init (QR of a Gaussian, sign-fixed) with the reference's scales
     (ml/models.py:103,125,144).  Init parity is NOT required (tests load identical weights)."""
     def orth(shape, scale):
@@ -301,6 +318,13 @@ def init_params(rng, obs_dim, hidden, num_layers, buckets, critic_dim=1, dtype=n
                        'bias': np.zeros(hidden, dtype)})
         d = hidden
     p = {'mlp': layers}
+    if separate:                              # BackboneSeparate: the critic encoder's own stack
+        p['mlp_critic'] = []
+        d = obs_dim
+        for _ in range(num_layers):
+            p['mlp_critic'].append({'kernel': orth((d, hidden), np.sqrt(2)), 'scale': np.ones(hidden, dtype),
+                                    'bias': np.zeros(hidden, dtype)})
+            d = hidden
     feat = hidden
     if lstm_layers:
         lst = []

@@ -243,14 +243,15 @@ def optimizer_step(params, grads, opt, cfg, init_norms, dtype=np.float32):
 
     # kernel re-projection to the initial L2 norm for every backbone 'kernel' (:303-310);
     # top-level actor / critic are excluded (ml/train_state.py:422-423)
-    for i, lyr in enumerate(new_p['mlp']):
-        k = lyr['kernel']
-        lyr['kernel'] = (f(init_norms['mlp'][i]) * k / np.sqrt(np.sum(np.square(k), dtype=np.float64))).astype(f)
-        # LayerNorm renorm (:312-338): factor = sqrt(F / (b.b + s.s))
-        s, b = lyr['scale'], lyr['bias']
-        fac = np.sqrt(s.shape[-1] / (np.dot(b.astype(np.float64), b) + np.dot(s.astype(np.float64), s)))
-        lyr['scale'] = (fac * s).astype(f)
-        lyr['bias'] = (fac * b).astype(f)
+    for name in ('mlp', 'mlp_critic'):        # 'mlp_critic': the critic encoder of a BackboneSeparate
+        for i, lyr in enumerate(new_p.get(name, [])):
+            k = lyr['kernel']
+            lyr['kernel'] = (f(init_norms[name][i]) * k / np.sqrt(np.sum(np.square(k), dtype=np.float64))).astype(f)
+            # LayerNorm renorm (:312-338): factor = sqrt(F / (b.b + s.s))
+            s, b = lyr['scale'], lyr['bias']
+            fac = np.sqrt(s.shape[-1] / (np.dot(b.astype(np.float64), b) + np.dot(s.astype(np.float64), s)))
+            lyr['scale'] = (fac * s).astype(f)
+            lyr['bias'] = (fac * b).astype(f)
     # flax keeps one kernel leaf PER GATE (ii, if, ig, io, hi, hf, hg, ho): each column block of the
     # stacked [in, 4H] matrices is re-projected to its own initial norm
     for i, lyr in enumerate(new_p.get('lstm', [])):
@@ -268,6 +269,8 @@ def optimizer_step(params, grads, opt, cfg, init_norms, dtype=np.float32):
 def initial_weight_norms(params):
     """ml/train_state.py:413-423."""
     n = {'mlp': [float(np.sqrt(np.sum(np.square(l['kernel'].astype(np.float64))))) for l in params['mlp']]}
+    if 'mlp_critic' in params:
+        n['mlp_critic'] = [float(np.sqrt(np.sum(np.square(l['kernel'].astype(np.float64))))) for l in params['mlp_critic']]
     if 'lstm' in params:
         def gate_norms(k):
             Hh = k.shape[1] // 4

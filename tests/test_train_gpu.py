@@ -24,11 +24,13 @@ BUCKETS = [4, 8, 5, 5, 2, 2]
 
 
 def _make(mlb, N=32, T=32, C=1, M=8, E=2, H=64, L=3, D=16, normalize_values=False, clipv=False,
-          huber=False, seed=5, p_done=-1.0, lr=3e-4):
+          huber=False, seed=5, p_done=-1.0, lr=3e-4, separate=False):
     m = mlb
     env = m.SyntheticVectorEnv(N, D, len(BUCKETS), seed=11, p_done=p_done, device=DEV)
+    enc = lambda: m.BackboneEncoder(net=m.models.MLP(H, L))
     policy = m.Policy(actor_critic=m.ActorCritic(
-        backbone=m.BackboneShared(prefix=None, encoder=m.BackboneEncoder(net=m.models.MLP(H, L))),
+        backbone=(m.BackboneSeparate(prefix=None, actor_encoder=enc(), critic_encoder=enc()) if separate
+                  else m.BackboneShared(prefix=None, encoder=enc())),
         actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(BUCKETS)),
         critic=m.models.DenseLayerCritic()))
     cfg = m.TrainConfig(
@@ -66,6 +68,8 @@ def _vn_to_oracle(t):
     # non-trivial value-normaliser state: the GAE input, the finish_rollouts hook arguments and
     # the 'Bootstrap Values' metric are in UN-normalised units (ml/rollouts.py:726-745, 810)
     dict(N=48, T=24, C=3, M=36, E=2, normalize_values=True, vn_init=(0.7, 2.5)),
+    # BackboneSeparate (ml/actor_critic.py:247-303): actor and critic towers, block-diagonal fused head
+    dict(N=48, T=16, M=24, E=2, L=2, separate=True, p_done=0.05),
 ])
 def test_update_iter_matches_oracle(mlb, kw, monkeypatch):
     monkeypatch.setenv('MLB_CUDA_GRAPH', '0')
