@@ -228,53 +228,94 @@ class RolloutManager:                   # ml/rollouts.py:373-826
                 user_finish_rollouts_hook, user_metrics_hook):
         """ml/rollouts.py:501-577."""
         rollout_state, user_state = user_start_rollouts_hook(rollout_state, train_state_mgr.user_state)
+        train_state_mgr.user_state = user_state
         policy_states = train_state_mgr.policy_states
-        train_states = train_state_mgr.train_states
         for c in range(self._num_bptt_chunks):
-            if self._lstm is not None:
-                with profile('Cache RNN state'):          # :533-537
-                    RH = self._lstm.RH
-                    for l in range(self._lstm.RL):
-                        _copy_state(self.store['rnn_start_c'][c, 0][:, l * RH:(l + 1) * RH], rollout_state.rnn_states[0][l])
-                        _copy_state(self.store['rnn_start_h'][c, 0][:, l * RH:(l + 1) * RH], rollout_state.rnn_states[1][l])
+            self.begin_chunk(rollout_state, c)
             rollout_state = self.rollout_loop(rollout_state, policy_states, c)
+        return self.finish(train_state_mgr, rollout_state, metrics, user_finish_rollouts_hook, user_metrics_hook)
+
+    # The pieces of collect() -- also driven in lockstep over several policies that share one simulator
+    # (multi_policy.py: every policy runs policy_step for step s, THEN the simulator steps once).
+    def begin_chunk(self, rs, c):
+        if self._lstm is not None:
+            with profile('Cache RNN state'):              # :533-537
+                RH = self._lstm.RH
+                for l in range(self._lstm.RL):
+                    _copy_state(self.store['rnn_start_c'][c, 0][:, l * RH:(l + 1) * RH], rs.rnn_states[0][l])
+                    _copy_state(self.store['rnn_start_h'][c, 0][:, l * RH:(l + 1) * RH], rs.rnn_states[1][l])
+        self._key_home = rs.prng_key
+
+    def finish(self, train_state_mgr, rollout_state, metrics, user_finish_rollouts_hook, user_metrics_hook):
         with profile('Bootstrap Values'):
-            self._bootstrap_values(policy_states, rollout_state)
+            self._bootstrap_values(train_state_mgr.policy_states, rollout_state)
         with profile('Finalize Rollouts'):
             rollout_data, metrics, user_state = self._finalize_rollouts(
-                train_states, metrics, user_state, user_finish_rollouts_hook, user_metrics_hook)
+                train_state_mgr.train_states, metrics, train_state_mgr.user_state, user_finish_rollouts_hook,
+                user_metrics_hook)
         train_state_mgr.user_state = user_state
         return train_state_mgr, rollout_state, rollout_data, self._obs_stats, metrics
 
+    def policy_step(self, rs, policy_states, c, s):
+        """Policy inference of step s of BPTT chunk c on rs.cur_obs; returns the sampled actions (the store slab:
+        int32 [B, A], fp32 bit patterns for a continuous group)."""
+        prog, N, st = self._prog, self._cfg.sim_batch_size, self.store
+        Tp = self._num_bptt_steps
+        with profile('Policy Inference'):
+            pre = policy_states.obs_preprocess.preprocess(
+                policy_states.obs_preprocess_state, rs.cur_obs, True)
+            ob = pre[self._ob_name]
+            policy_states.obs_preprocess.update_obs_stats(
+                policy_states.obs_preprocess_state, self._obs_stats, c * Tp + s, rs.cur_obs, True)
+            slab = st['obs'][c, s, 0]
+            actions = st['actions'][c, s, 0]
+            if prog.fused_rollout:
+                # key chain + obs store + MLP + heads + sampling in one launch; the advanced
+                # PRNG key lands in the alternate buffer, so the two buffers trade places
+                prog.rollout_step_fused(ob, slab, N, rs.prng_key, self._key_alt, actions,
+                                        st['log_probs'][c, s, 0], st['values'][c, s, 0],
+                                        self.partitionable)
+                rs.prng_key, self._key_alt = self._key_alt, rs.prng_key
+            else:
+                call('mlb_rollout_keys', ptr(rs.prng_key), ptr(self.policy_key),
+                     c_int(int(self.partitionable)))
+                call('mlb_copy_bytes', ptr(ob), ptr(slab), c_size_t(slab.numel() * 4))
+                head = prog.forward_infer(slab, N, rs.rnn_states)
+                prog.sample(head, N, self.policy_key, actions, st['log_probs'][c, s, 0],
+                            st['values'][c, s, 0], self.partitionable)
+        return actions
+
+    def post_step(self, rs, c, s, out):
+        """Consumes one simulator step's outputs (this policy's rows): next observations, reward / done store,
+        env-return trace, RNN reset."""
+        N, st = self._cfg.sim_batch_size, self.store
+        Tp = self._num_bptt_steps
+        rs.sim_state = out['state']
+        rs.cur_obs = dict(out['obs'])
+        dones, rewards = out['dones'], out['rewards']
+        if dones.dtype not in (torch.bool, torch.uint8):
+            dones = dones != 0
+        if rewards.dtype != torch.float32:
+            rewards = rewards.float()
+        with profile('Post Step Rollout Store'):
+            d_slab, r_slab = st['dones'][c, s, 0], st['rewards'][c, s, 0]
+            call('mlb_post_step_store_f32', ptr(rewards), ptr(dones), ptr(r_slab), ptr(d_slab),
+                 ptr(rs.env_returns), ptr(self.env_returns_trace[c * Tp + s]), c_ll(N),
+                 c_float(self._cfg.reward_gamma))
+            if self._lstm is not None:                    # rnn_reset_fn(rnn_states, dones)  (:942)
+                self._lstm.reset(rs.rnn_states, d_slab.view(torch.uint8), N)
+
+    def end_chunk(self, rs):
+        key_home = self._key_home
+        if rs.prng_key is not key_home:                   # odd number of fused steps: move the key home
+            call('mlb_copy_bytes', ptr(rs.prng_key), ptr(key_home), c_size_t(8))
+            rs.prng_key, self._key_alt = key_home, rs.prng_key
+
     def rollout_loop(self, rs, policy_states, c):
         """rollout_iter x T' (ml/rollouts.py:829-978) for BPTT chunk c."""
-        prog, N, st = self._prog, self._cfg.sim_batch_size, self.store
-        gamma = self._cfg.reward_gamma
-        Tp = self._num_bptt_steps
-        key_home = rs.prng_key
-        for s in range(Tp):
-            with profile('Policy Inference'):
-                pre = policy_states.obs_preprocess.preprocess(
-                    policy_states.obs_preprocess_state, rs.cur_obs, True)
-                ob = pre[self._ob_name]
-                policy_states.obs_preprocess.update_obs_stats(
-                    policy_states.obs_preprocess_state, self._obs_stats, c * Tp + s, rs.cur_obs, True)
-                slab = st['obs'][c, s, 0]
-                actions = st['actions'][c, s, 0]
-                if prog.fused_rollout:
-                    # key chain + obs store + MLP + heads + sampling in one launch; the advanced
-                    # PRNG key lands in the alternate buffer, so the two buffers trade places
-                    prog.rollout_step_fused(ob, slab, N, rs.prng_key, self._key_alt, actions,
-                                            st['log_probs'][c, s, 0], st['values'][c, s, 0],
-                                            self.partitionable)
-                    rs.prng_key, self._key_alt = self._key_alt, rs.prng_key
-                else:
-                    call('mlb_rollout_keys', ptr(rs.prng_key), ptr(self.policy_key),
-                         c_int(int(self.partitionable)))
-                    call('mlb_copy_bytes', ptr(ob), ptr(slab), c_size_t(slab.numel() * 4))
-                    head = prog.forward_infer(slab, N, rs.rnn_states)
-                    prog.sample(head, N, self.policy_key, actions, st['log_probs'][c, s, 0],
-                                st['values'][c, s, 0], self.partitionable)
+        prog = self._prog
+        for s in range(self._num_bptt_steps):
+            actions = self.policy_step(rs, policy_states, c, s)
             with profile('Rollout Step'):
                 step_input = {
                     'state': rs.sim_state,
@@ -284,22 +325,8 @@ class RolloutManager:                   # ml/rollouts.py:373-826
                     'pbt': {'policy_assignments': rs.policy_assignments},
                 }
                 out = rs.step_fn(step_input)
-                rs.sim_state = out['state']
-                rs.cur_obs = dict(out['obs'])
-                dones, rewards = out['dones'], out['rewards']
-                if dones.dtype not in (torch.bool, torch.uint8):
-                    dones = dones != 0
-                if rewards.dtype != torch.float32:
-                    rewards = rewards.float()
-            with profile('Post Step Rollout Store'):
-                d_slab, r_slab = st['dones'][c, s, 0], st['rewards'][c, s, 0]
-                call('mlb_post_step_store_f32', ptr(rewards), ptr(dones), ptr(r_slab), ptr(d_slab),
-                     ptr(rs.env_returns), ptr(self.env_returns_trace[c * Tp + s]), c_ll(N), c_float(gamma))
-                if self._lstm is not None:                # rnn_reset_fn(rnn_states, dones)  (:942)
-                    self._lstm.reset(rs.rnn_states, d_slab.view(torch.uint8), N)
-        if rs.prng_key is not key_home:                   # odd number of fused steps: move the key home
-            call('mlb_copy_bytes', ptr(rs.prng_key), ptr(key_home), c_size_t(8))
-            rs.prng_key, self._key_alt = key_home, rs.prng_key
+            self.post_step(rs, c, s, out)
+        self.end_chunk(rs)
         return rs
 
     def _bootstrap_values(self, policy_states, rs):     # :607-635

@@ -103,6 +103,11 @@ def init_training(dev, cfg: TrainConfig, sim_fns: Dict[str, Callable], policy: P
     dev = torch.device(dev)
     if dev.type != 'cuda':
         raise RuntimeError('madrona_learn_b200 runs on CUDA devices only (no CPU fallback)')
+    if cfg.pbt is not None:
+        from .multi_policy import init_multi_policy_training
+        with torch.cuda.device(dev):
+            return init_multi_policy_training(dev, cfg, sim_fns, policy, init_sim_ctrl, user_hooks, restore_ckpt,
+                                              profile_port, dist_ctx)
     with torch.cuda.device(dev):
         return _init_training(dev, cfg, sim_fns, policy, init_sim_ctrl, user_hooks, restore_ckpt,
                               profile_port, dist_ctx)
@@ -191,18 +196,25 @@ def _update_impl(algo, cfg, user_hooks, rollout_state, rollout_mgr, train_state_
     """ml/train.py:155-225 (P = 1: the vmap over policies is the identity)."""
     with profile('Update Iter'):
         with profile('Collect Rollouts'):
-            train_state_mgr, rollout_state, rollout_data, obs_stats, metrics = rollout_mgr.collect(
+            collected = rollout_mgr.collect(
                 train_state_mgr, rollout_state, metrics, user_hooks.start_rollouts,
                 user_hooks.finish_rollouts, user_hooks.rollout_metrics)
-        with profile('Update Observations Stats'):
-            # ml/train.py:193-204: safe right away, the learner only sees preprocessed observations
-            ps0 = train_state_mgr.policy_states
-            ps0.obs_preprocess_state = ps0.obs_preprocess.update_state(
-                ps0.obs_preprocess_state, obs_stats, True, dist_ctx=dist_ctx)
-        with profile('Learn'):
-            ps, ts, metrics = algo.update(cfg, train_state_mgr.policy_states,
-                                          train_state_mgr.train_states, rollout_data,
-                                          user_hooks.optimize_metrics, metrics,
-                                          dist_ctx=dist_ctx, ws=ppo_ws)
-        train_state_mgr.policy_states, train_state_mgr.train_states = ps, ts
+        return _learn_impl(algo, cfg, user_hooks, collected, dist_ctx, ppo_ws)
+
+
+def _learn_impl(algo, cfg, user_hooks, collected, dist_ctx, ppo_ws):
+    """The part of _update_impl after rollout collection (ml/train.py:193-225): one policy's observation
+    statistics + algo.update.  The multi-policy learner (multi_policy.py) calls it once per policy."""
+    train_state_mgr, rollout_state, rollout_data, obs_stats, metrics = collected
+    with profile('Update Observations Stats'):
+        # ml/train.py:193-204: safe right away, the learner only sees preprocessed observations
+        ps0 = train_state_mgr.policy_states
+        ps0.obs_preprocess_state = ps0.obs_preprocess.update_state(
+            ps0.obs_preprocess_state, obs_stats, True, dist_ctx=dist_ctx)
+    with profile('Learn'):
+        ps, ts, metrics = algo.update(cfg, train_state_mgr.policy_states,
+                                      train_state_mgr.train_states, rollout_data,
+                                      user_hooks.optimize_metrics, metrics,
+                                      dist_ctx=dist_ctx, ws=ppo_ws)
+    train_state_mgr.policy_states, train_state_mgr.train_states = ps, ts
     return train_state_mgr, rollout_state, metrics
