@@ -84,7 +84,7 @@ ln_relu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ scale,
 }
 
 template <int NV, typename TD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 2 ? 2 : 1)
 ln_relu_bwd_kernel(const TD* __restrict__ dy, const float* __restrict__ z,
                    const float* __restrict__ stats, const float* __restrict__ scale,
                    const float* __restrict__ bias, TD* __restrict__ dz,
@@ -106,17 +106,37 @@ ln_relu_bwd_kernel(const TD* __restrict__ dy, const float* __restrict__ z,
                         b[i] = __ldg(reinterpret_cast<const float4*>(bias) + c); }
     }
     const float invH = 1.f / (float)H;
-    for (long long r = warp; r < rows; r += nwarps) {
-        const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    // Software-pipelined over the rows a warp visits: the loads of row r + nwarps are issued before the
+    // reductions of row r (88 registers allow two 256-thread blocks per SM; one row per warp in flight left the
+    // kernel latency-bound at 3.5 TB/s, two rows double the bytes in flight).
+    float4 zc[NV], dc[NV];
+    float2 stc = make_float2(0.f, 1.f);
+    auto load_row = [&](long long r, float4 (&zz)[NV], float4 (&dd)[NV], float2& st) {
         const float4* zr = reinterpret_cast<const float4*>(z + r * H);
         const TD* dr = dy + r * H;
+        st = __ldg(reinterpret_cast<const float2*>(stats) + r);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nvec) { zz[i] = __ldg(zr + c); dd[i] = ld4(dr, c); }
+        }
+    };
+    long long r = warp;
+    if (r < rows) load_row(r, zc, dc, stc);
+    while (r < rows) {
+        const long long rn = r + nwarps;
+        float4 zn[NV], dn[NV];
+        float2 stn = make_float2(0.f, 1.f);
+        constexpr bool PIPE = NV <= 2;             // wider rows: the second row in flight would spill
+        if (PIPE && rn < rows) load_row(rn, zn, dn, stn);
+        const float mean = stc.x, rstd = stc.y;
         float4 xh[NV], dx[NV];
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
             if (c < nvec) {
-                const float4 zv = __ldg(zr + c), dv = ld4(dr, c);
+                const float4 zv = zc[i], dv = dc[i];
                 float4 x, g;
                 x.x = (zv.x - mean) * rstd; x.y = (zv.y - mean) * rstd;
                 x.z = (zv.z - mean) * rstd; x.w = (zv.w - mean) * rstd;
@@ -147,6 +167,14 @@ ln_relu_bwd_kernel(const TD* __restrict__ dy, const float* __restrict__ z,
                 st4(or_, c, o);
             }
         }
+        if (PIPE) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { zc[i] = zn[i]; dc[i] = dn[i]; }
+            stc = stn;
+        } else if (rn < rows) {
+            load_row(rn, zc, dc, stc);
+        }
+        r = rn;
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {

@@ -37,7 +37,7 @@ def main():
     else:
         N = wl['worlds']
         env = m.SyntheticVectorEnv(N, bench.WORKLOAD['obs_dim'], len(bench.BUCKETS), seed=0, device=dev)
-        mgr = m.init_training(dev, bench.make_cfg(m, N, dtype='bf16', wl=wl), env.sim_fns(), bench.make_policy(m, wl),
+        mgr = m.init_training(dev, bench.make_cfg(m, N, dtype=os.environ.get('PROFILE_DTYPE', 'bf16'), wl=wl), env.sim_fns(), bench.make_policy(m, wl),
                               None, verbose=False)
     mgr.update_iter()
     torch.cuda.synchronize()
