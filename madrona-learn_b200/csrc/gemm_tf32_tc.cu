@@ -59,20 +59,25 @@ __device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t saddr, uint32_t lbo_
 //         error becomes zero-mean and a 256-deep dot averages it out (rel-L2 2.9e-4 instead of 8.7e-4 against
 //         the exact product, measured).  The pipeline is then TMA -> round -> MMA per stage; the conversion is
 //         bound by shared-memory bandwidth (read + write of the stage), so ROUND = 1 converts only the
-//         ACTIVATION operands -- A, and B too in the dW-type product (A MN-major: both operands are
-//         activations) -- and leaves the weight operand, two thirds of a forward stage, to the hardware;
-//         ROUND = 2 converts both operands always.
+//         ACTIVATION operand of the store-epilogue products (A of Z = X W and dX = dZ W^T; both operands if A
+//         is MN-major) and leaves the weight operand, two thirds of a forward stage, and the reduction
+//         (dW-type) products to the hardware; ROUND = 2 converts both operands always.
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool ATOMIC, int ROUND>
 __global__ void __launch_bounds__(T32_THREADS)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, float* __restrict__ C, const float* __restrict__ bias, int ldc, int M, int N, int K,
                  int k_per_split) {
     using L = Smem32<BN, STAGES>;
+    // ROUND = 1 leaves the reduction (accumulate / split-K: the dW-type products) to the hardware conversion:
+    // there both operands are activations, the conversion pass doubles the shared-memory traffic of a kernel
+    // that is bound by it (TMA write + convert read + convert write + MMA read per stage: 37 -> 43 us), and a
+    // uniform -1e-3 scale on a gradient is invisible to Adam and to the global-norm clip
+    constexpr bool DO_ROUND = ROUND == 2 || (ROUND == 1 && !ATOMIC);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem_1024(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* ready_bar = empty_bar + STAGES;              // ROUND: stage converted, 128 arrivals
+    uint64_t* ready_bar = empty_bar + STAGES;              // DO_ROUND: stage converted, 128 arrivals
     uint64_t* acc_bar = ready_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
@@ -137,7 +142,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait_spin(ROUND ? &ready_bar[s] : &full_bar[s], ph, 0x72);
+                mbar_wait_spin(DO_ROUND ? &ready_bar[s] : &full_bar[s], ph, 0x72);
                 tcgen05_fence_after();
                 const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
                 const uint32_t sb = sa + L::A_BYTES;
@@ -158,7 +163,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
         const int quad = warp & 3;
         const int row = m0 + quad * 32 + lane;
-        if (ROUND) {
+        if (DO_ROUND) {
             // in-place round-to-nearest of every landed stage (element-wise: the swizzle does not matter);
             // the generic-proxy writes are fenced towards the async proxy the MMA reads through
             const int et = threadIdx.x - 64;                           // 0..127
@@ -264,6 +269,210 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant of the store-epilogue kernel (no accumulate): one CTA per SM walks output tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ...  (tile t -> m-tile t / n_tiles, n-tile t % n_tiles: the n-tiles of one
+// row block run back to back and share its A rows through L2).  The ncu capture of the one-tile-per-CTA kernel
+// (profiles/r2_tf32_gemm_ncu_raw.csv) shows every unit below 25 % busy -- L2 19 %, DRAM 24 %, tensor pipe 22 %,
+// 9 % of the warp slots -- i.e. the launch is a chain of per-CTA latencies (prologue -> operand stream -> MMA
+// -> TMEM read-out -> store drain, 12 us per tile, nothing overlapped).  Here the accumulator is double-buffered
+// in TMEM (2 x BN columns), so while the four epilogue warps read tile i out (tcgen05.ld -> swizzled smem
+// panels -> TMA store) the producer / MMA warps already stream and multiply tile i + 1, and the prologue is paid
+// once per SM instead of once per tile.  Operand rounding (ROUND) has its own four warps (the epilogue warps are
+// busy with the previous tile).  Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue,
+// warps 6-9 rounding.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct Smem32P {
+    static constexpr int A_BYTES = BM * BK32 * 4;
+    static constexpr int B_BYTES = BN * BK32 * 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int PANEL_OFF = STAGES * STAGE_BYTES;          // 4 warps x 2 panels x 4 KB
+    static constexpr int BAR_OFF = PANEL_OFF + 32768;
+    static constexpr int TOTAL = BAR_OFF + (3 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int ROUND>
+__global__ void __launch_bounds__(ROUND ? 320 : 192)
+tf32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N,
+                         int K, int n_tiles, int num_tiles) {
+    using L = Smem32P<BN, STAGES>;
+    constexpr uint32_t TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align_smem_1024(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* ready_bar = empty_bar + STAGES;
+    uint64_t* tfull_bar = ready_bar + STAGES;              // [2] accumulator complete (MMA -> epilogue)
+    uint64_t* tempty_bar = tfull_bar + 2;                  // [2] accumulator drained (4 epilogue warps -> MMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (K + BK32 - 1) / BK32;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128);
+        }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    pdl_wait();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer: one continuous stream of k-blocks over all of this CTA's tiles
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait_spin(&empty_bar[s], ((it / STAGES) & 1) ^ 1, 0x75);
+                    uint8_t* sa = smem + s * L::STAGE_BYTES;
+                    uint8_t* sb = sa + L::A_BYTES;
+                    mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                    const int k0 = kb * BK32;
+                    if (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < BM / 32; ++j) tma_load_2d(&tmA, &full_bar[s], sa + j * 4096, m0 + 32 * j, k0);
+                    } else {
+                        tma_load_2d(&tmA, &full_bar[s], sa, k0, m0);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmB, &full_bar[s], sb + j * 4096, n0 + 32 * j, k0);
+                    } else {
+                        tma_load_2d(&tmB, &full_bar[s], sb, k0, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            uint32_t it = 0, li = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++li) {
+                const uint32_t acc = li & 1;
+                mbar_wait_spin(&tempty_bar[acc], ((li >> 1) & 1) ^ 1, 0x76);       // epilogue drained this buffer
+                tcgen05_fence_after();
+                const uint32_t tacc = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait_spin(ROUND ? &ready_bar[s] : &full_bar[s], (it / STAGES) & 1, 0x77);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+                    const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK32 / UMMA_K32; ++k) {
+                        const uint64_t ad = A_MN ? umma_desc_mn32(sa + k * 1024, 4096, 512) : umma_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? umma_desc_mn32(sb + k * 1024, 4096, 512) : umma_desc(sb + k * 32, 16, 1024);
+                        tcgen05_mma_tf32(tacc, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    tcgen05_commit(&empty_bar[s]);
+                }
+                tcgen05_commit(&tfull_bar[acc]);
+            }
+        }
+    } else if (warp < 6) {
+        // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2, 3, 0, 1)
+        const int quad = warp & 3;
+        uint8_t* panels = smem + L::PANEL_OFF + quad * 8192;
+        uint32_t li = 0, cnt = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++li) {
+            const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+            const uint32_t acc = li & 1;
+            mbar_wait(&tfull_bar[acc], (li >> 1) & 1, 0x78);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= N) break;                                       // warp-uniform
+                uint8_t* panel = panels + (cnt & 1) * 4096;
+                if (cnt >= 2) {
+                    if (lane == 0) tma_store_wait_read<1>();                // the store that last read this panel
+                    __syncwarp();
+                }
+                ++cnt;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+                const uint32_t pa = smem_u32(panel);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 v;
+                    v.x = __uint_as_float(r[4 * j]);     v.y = __uint_as_float(r[4 * j + 1]);
+                    v.z = __uint_as_float(r[4 * j + 2]); v.w = __uint_as_float(r[4 * j + 3]);
+                    if (bias != nullptr && col0 + 4 * j < N) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias + col0 + 4 * j);
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                    }
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                                 ::"r"(pa + sw128(lane, j)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmC, panel, col0, m0 + quad * 32);
+                    tma_store_commit();
+                }
+            }
+            // every lane's tcgen05.ld of this accumulator has completed (tmem_ld32 waits): hand it back
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (lane == 0) tma_store_wait<0>();
+        __syncwarp();
+    } else if (ROUND) {
+        // ================= operand rounding (warps 6..9): cvt.rna.tf32.f32 in place on every landed stage
+        const int et = threadIdx.x - 192;                                   // 0..127
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full_bar[s], (it / STAGES) & 1, 0x79);
+                const uint32_t base = smem_u32(smem + s * L::STAGE_BYTES) + et * 16;
+#pragma unroll 8
+                for (int v = 0; v < ((ROUND == 2 || A_MN) ? L::STAGE_BYTES : L::A_BYTES) / (128 * 16); ++v) {
+                    uint32_t a, b, c, d;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(base + v * 2048));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(__uint_as_float(a)));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(__uint_as_float(b)));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(__uint_as_float(c)));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(__uint_as_float(d)));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                 ::"r"(base + v * 2048), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+                }
+                fence_async_smem();
+                mbar_arrive(&ready_bar[s]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
+    }
+}
+
 // 2-D fp32 row-major tensor [outer, inner] with row stride ld (elements); box = [box_outer, 32 inner]
 int make_map_f32(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_outer,
                  bool mn_major) {
@@ -298,6 +507,33 @@ int launch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float
     dim3 grid(mlb_cdiv(M, BM), mlb_cdiv(N, BN), zs);
     e = launch_pdl(kern, grid, dim3(T32_THREADS), L::TOTAL, s, tA, tB, tC, C, bias, ldc, M, N, K, kps);
     return e == cudaSuccess ? MLB_OK : (int)e;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int ROUND>
+int launch32p(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float* C, const float* bias, int ldc,
+              int M, int N, int K) {
+    using L = Smem32P<BN, STAGES>;
+    CUtensorMap tC{};
+    const int rc = make_map_f32(&tC, C, N, M, ldc, 32, false);
+    if (rc) return rc;
+    auto kern = tf32_gemm_persist_kernel<BN, STAGES, A_MN, B_MN, ROUND>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    const int n_tiles = (int)mlb_cdiv(N, BN);
+    const long long tiles = (long long)mlb_cdiv(M, BM) * n_tiles;
+    const unsigned grid = (unsigned)(tiles < MLB_NUM_SMS ? tiles : MLB_NUM_SMS);
+    e = launch_pdl(kern, dim3(grid), dim3(ROUND ? 320 : 192), L::TOTAL, s, tA, tB, tC, bias, M, N, K, n_tiles,
+                   (int)tiles);
+    return e == cudaSuccess ? MLB_OK : (int)e;
+}
+
+template <bool A_MN, bool B_MN, int ROUND>
+int dispatch32p(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float* C, const float* bias, int ldc,
+                int M, int N, int K, int bn) {
+    if (bn == 32) return launch32p<32, 6, A_MN, B_MN, ROUND>(s, tA, tB, C, bias, ldc, M, N, K);
+    if (bn == 64) return launch32p<64, 6, A_MN, B_MN, ROUND>(s, tA, tB, C, bias, ldc, M, N, K);
+    if (bn == 128) return launch32p<128, 5, A_MN, B_MN, ROUND>(s, tA, tB, C, bias, ldc, M, N, K);
+    return launch32p<256, 4, A_MN, B_MN, ROUND>(s, tA, tB, C, bias, ldc, M, N, K);
 }
 
 template <bool A_MN, bool B_MN, int ROUND>
@@ -365,6 +601,21 @@ MLB_API int mlb_gemm_tf32_tc(void* stream, const float* A, const float* B, float
     cudaStream_t s = mlb_stream(stream);
     const bool atomic = accumulate != 0;
     static const int round = tf32_knob("MLB_TF32_ROUND", 1), st256 = tf32_knob("MLB_TF32_STAGES", 4);
+    static const int persist = tf32_knob("MLB_TF32_PERSIST", 1);
+    // more output tiles than SMs and a plain store: the persistent kernel (accumulator double-buffered in TMEM)
+    if (persist && !atomic && (long long)mlb_cdiv(M, BM) * mlb_cdiv(N, bn) > MLB_NUM_SMS) {
+#define DISPATCHP(R_)                                                                                          \
+    do {                                                                                                       \
+        if (!a_mn && !b_mn) return dispatch32p<false, false, R_>(s, tA, tB, C, bias, ldc, M, N, K, bn);        \
+        if (a_mn && b_mn) return dispatch32p<true, true, R_>(s, tA, tB, C, bias, ldc, M, N, K, bn);            \
+        if (a_mn) return dispatch32p<true, false, R_>(s, tA, tB, C, bias, ldc, M, N, K, bn);                   \
+        return dispatch32p<false, true, R_>(s, tA, tB, C, bias, ldc, M, N, K, bn);                             \
+    } while (0)
+        if (round == 1) DISPATCHP(1);
+        if (round >= 2) DISPATCHP(2);
+        DISPATCHP(0);
+#undef DISPATCHP
+    }
 #define DISPATCH(R_)                                                                                                    \
     do {                                                                                                                \
         if (!a_mn && !b_mn) return dispatch32<false, false, R_>(s, tA, tB, C, bias, ldc, M, N, K, atomic, splitk, bn, st256); \

@@ -39,6 +39,12 @@ SHAPES = [
     (256, 28, 3000, 1, 0, 1, False),       # head dW
     (132, 100, 72, 1, 1, 0, True),         # transA with K-major B, ragged tiles
     (128, 1024, 256, 0, 1, 1, False),      # LSTM gate pre-activations (+= h W_h^T), N = 4 RH
+    # more output tiles than SMs -> the persistent kernel (double-buffered TMEM accumulator, several tiles per CTA)
+    (19277, 256, 256, 0, 0, 0, False),     # 151 row tiles, ragged last tile
+    (19277, 256, 64, 0, 1, 0, False),
+    (40000, 28, 256, 0, 0, 0, True),       # head forward at minibatch size: 313 tiles of BN = 32, bias
+    (5000, 1024, 200, 0, 1, 0, True),      # 40 x 4 tiles: n-tiles of a row block back to back, K tail
+    (19280, 100, 72, 1, 1, 0, True),       # MN-major A in the persistent kernel
 ]
 
 
@@ -64,11 +70,12 @@ def test_gemm_tf32_vs_exact_product(mlb, M, N, K, ta, tb, acc, with_bias):
     out = Cd.cpu().numpy()
     assert np.isfinite(out).all()
     import os
-    # MLB_TF32_ROUND: 0 = the tensor core's own conversion (low 13 bits dropped), 1 (default) = activation operands
-    # rounded to nearest in the kernel (A always; B too when A is MN-major, the dW-type product), 2 = both operands
+    # MLB_TF32_ROUND: 0 = the tensor core's own conversion (low 13 bits dropped), 1 (default) = the activation
+    # operand of the store products rounded to nearest in the kernel (A; B too when A is MN-major), reductions
+    # (accumulate: the dW-type products) left to the hardware, 2 = both operands always
     mode = int(os.environ.get('MLB_TF32_ROUND', '1'))
-    cvA = _rna_tf32 if mode >= 1 else _trunc_tf32
-    cvB = _rna_tf32 if (mode >= 2 or (mode == 1 and ta)) else _trunc_tf32
+    cvA = _rna_tf32 if (mode >= 2 or (mode == 1 and not acc)) else _trunc_tf32
+    cvB = _rna_tf32 if (mode >= 2 or (mode == 1 and ta and not acc)) else _trunc_tf32
     model = opA(cvA(A)) @ opB(cvB(B)) + extra
     print('tf32 gemm rel-L2: exact %.3g dropped-bits %.3g rounded %.3g kernel-model %.3g' % (
         _rel(out, exact), _rel(out, dropped), _rel(out, rounded), _rel(out, model)))

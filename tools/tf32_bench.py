@@ -46,6 +46,8 @@ if __name__ == '__main__':
         time_gemm('head fwd', fn, R, 28, 256, 0, 0, 0)
         time_gemm('head dX', fn, R, 256, 28, 0, 1, 0)
         time_gemm('head dW', fn, 256, 28, R, 1, 0, 1)
+    if 'gemm-only' in sys.argv:
+        sys.exit(0)
     import bench_configs as b
     m.set_matmul_precision('tf32')
     b.run('cfg2 f32 matmul=tf32', 8192, 32, 1, 256, 3, 4, 4, torch.float32, steps=10, warm=3)
