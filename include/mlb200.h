@@ -269,6 +269,14 @@ int mlb_gemm_tf32_tc(void* stream, const float* A, const float* B, float* C, con
                      int accumulate, int splitk);
 int mlb_gemm_tf32_ok(int M, int N, int K, int lda, int ldb, int ldc, const void* A, const void* B,
                      const void* C);
+/* One Dense -> LayerNorm -> ReLU layer of compute_dtype=float32 (ml/models.py:107-117) in ONE launch: */
+/* z = x W on tcgen05 kind::tf32 with the LayerNorm statistics, affine and ReLU computed out of TMEM in */
+/* the epilogue (same arithmetic as mlb_ln_relu_fwd_f32).  x [rows, K] (row stride ldx), w [K, H] (the   */
+/* flax Dense kernel), z [rows, H] or NULL, y [rows, H], stats [rows][2] = {mean, rstd} or NULL;         */
+/* H in {64, 128, 256} (the accumulator tile spans the whole feature row).                               */
+int mlb_dense_ln_relu_fwd_tf32(void* stream, const float* x, const float* w, const float* scale,
+                               const float* bias, float* z, float* y, float* stats, long long rows, int K,
+                               int H, int ldx);
 
 /* LayerNorm(eps 1e-6, fast variance) + ReLU (ml/models.py:46-56,116-117).                  */
 /* fwd: y = relu(((z-mean)*rstd)*scale+bias); stats (may be NULL) f32 [rows][2]={mean,rstd}  */

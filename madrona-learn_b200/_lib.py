@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmlb200.so')
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                             ctypes.c_float, ctypes.c_size_t)
@@ -79,6 +79,7 @@ SIGNATURES = {
     'mlb_gemm_tf32_tc': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_int, c_int]),
     'mlb_gemm_tf32_ok': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    'mlb_dense_ln_relu_fwd_tf32': (c_int, [P, P, P, P, P, P, P, P, c_ll, c_int, c_int, c_int]),
     'mlb_ln_relu_fwd_f32': (c_int, [P, P, P, P, P, P, c_ll, c_int]),
     'mlb_ln_relu_bwd_f32': (c_int, [P, P, P, P, P, P, P, P, P, c_ll, c_int]),
     'mlb_ln_relu_fwd_bf16': (c_int, [P, P, P, P, P, P, c_ll, c_int]),

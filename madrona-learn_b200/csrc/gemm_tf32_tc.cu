@@ -282,22 +282,36 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // busy with the previous tile).  Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue,
 // warps 6-9 rounding.
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool LN = false>
 struct Smem32P {
     static constexpr int A_BYTES = BM * BK32 * 4;
     static constexpr int B_BYTES = BN * BK32 * 4;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int PANEL_OFF = STAGES * STAGE_BYTES;          // 4 warps x 2 panels x 4 KB
-    static constexpr int BAR_OFF = PANEL_OFF + 32768;
+    static constexpr int EPW = LN ? 8 : 4;                          // epilogue warps
+    static constexpr int PANEL_OFF = STAGES * STAGE_BYTES;          // per epilogue warp: 2 panels x 4 KB
+    static constexpr int XCH_OFF = PANEL_OFF + EPW * 8192;          // LN: row-statistics exchange [2][2][128] float2
+    static constexpr int BAR_OFF = XCH_OFF + (LN ? 4096 : 0);
     static constexpr int TOTAL = BAR_OFF + (3 * STAGES + 4) * 8 + 16 + 1024;
+    static constexpr int THREADS_NOROUND = 64 + 32 * EPW;
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int ROUND>
-__global__ void __launch_bounds__(ROUND ? 320 : 192)
+// LN: the Dense -> LayerNorm -> ReLU layer of compute_dtype=float32 in one launch (ml/models.py:107-117): BN
+// covers the whole feature row (N == BN), so the epilogue thread that owns an accumulator row computes the row's
+// mean / rstd out of TMEM (pass 1), then re-reads it and emits z (the pre-activation the fp32 backward
+// differentiates through; skipped when tmC is unused) and y = relu((z - mean) * rstd * scale + bias) as two
+// panel streams (pass 2), plus stats[row] = {mean, rstd}.  Same arithmetic as mlb_ln_relu_fwd_f32 (eps 1e-6,
+// fast variance); saves that kernel's 8 * rows * H bytes and its launch.  The LayerNorm epilogue is ~10
+// instructions per element, so it runs on EIGHT warps (two per TMEM lane quadrant, each half of the columns;
+// the two partial row sums meet through shared memory) -- with four the epilogue, not the operand stream,
+// set the tile period (13 us instead of 7.5).
+template <int BN, int STAGES, bool A_MN, bool B_MN, int ROUND, bool LN>
+__global__ void __launch_bounds__((LN ? 320 : 192) + (ROUND ? 128 : 0))
 tf32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N,
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmY,
+                         const float* __restrict__ bias, const float* __restrict__ ln_scale,
+                         const float* __restrict__ ln_bias, float* __restrict__ stats, int store_z, int M, int N,
                          int K, int n_tiles, int num_tiles) {
-    using L = Smem32P<BN, STAGES>;
+    using L = Smem32P<BN, STAGES, LN>;
     constexpr uint32_t TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem_1024(smem_raw);
@@ -316,10 +330,11 @@ tf32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+        if (LN) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128);
         }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], L::EPW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -390,16 +405,81 @@ tf32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 tcgen05_commit(&tfull_bar[acc]);
             }
         }
-    } else if (warp < 6) {
-        // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2, 3, 0, 1)
+    } else if (warp < 2 + L::EPW) {
+        // ================= epilogue (warps 2..5 [6..9] -> TMEM lane quadrants 2, 3, 0, 1 [again])
         const int quad = warp & 3;
-        uint8_t* panels = smem + L::PANEL_OFF + quad * 8192;
+        const int ew = warp - 2;
+        uint8_t* panels = smem + L::PANEL_OFF + ew * 8192;
         uint32_t li = 0, cnt = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++li) {
             const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
             const uint32_t acc = li & 1;
             mbar_wait(&tfull_bar[acc], (li >> 1) & 1, 0x78);
             tcgen05_fence_after();
+            if (LN) {
+                constexpr int CH = BN / 64;                                 // 32-column chunks per warp (half a row)
+                const int half = ew >> 2;
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + (uint32_t)(half * CH * 32);
+                float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < CH; ++c) {                              // pass 1: row statistics of this half
+                    uint32_t r[32];
+                    tmem_ld32(trow + (uint32_t)(c * 32), r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const float v = __uint_as_float(r[j]); sum += v; sq = fmaf(v, v, sq); }
+                }
+                // the partner warp of this quadrant holds the other half: exchange through shared memory
+                // (double-buffered by tile parity; the pair meets at a 64-thread named barrier)
+                float2* xch = reinterpret_cast<float2*>(smem + L::XCH_OFF) + (li & 1) * 256;
+                xch[half * 128 + quad * 32 + lane] = make_float2(sum, sq);
+                named_bar_sync(1 + quad, 64);
+                const float2 o = xch[(half ^ 1) * 128 + quad * 32 + lane];
+                sum += o.x; sq += o.y;
+                const float invH = 1.f / (float)BN;
+                const float mean = sum * invH;
+                const float rstd = rsqrtf(fmaxf(0.f, sq * invH - mean * mean) + 1e-6f);
+                const int row = m0 + quad * 32 + lane;
+                if (half == 0 && stats != nullptr && row < M)
+                    *reinterpret_cast<float2*>(stats + 2 * (long long)row) = make_float2(mean, rstd);
+                uint8_t* pz = panels;
+                uint8_t* py = panels + 4096;
+                const uint32_t paz = smem_u32(pz), pay = smem_u32(py);
+#pragma unroll 1
+                for (int c = 0; c < CH; ++c) {                              // pass 2: z and y panels
+                    const int col0 = (half * CH + c) * 32;
+                    if (cnt >= 1) {
+                        if (lane == 0) tma_store_wait_read<0>();            // the panels' previous stores were read
+                        __syncwarp();
+                    }
+                    ++cnt;
+                    uint32_t r[32];
+                    tmem_ld32(trow + (uint32_t)(c * 32), r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(ln_scale + col0) + j);
+                        const float4 bi = __ldg(reinterpret_cast<const float4*>(ln_bias + col0) + j);
+                        float4 v, y;
+                        v.x = __uint_as_float(r[4 * j]);     v.y = __uint_as_float(r[4 * j + 1]);
+                        v.z = __uint_as_float(r[4 * j + 2]); v.w = __uint_as_float(r[4 * j + 3]);
+                        y.x = fmaxf(0.f, (v.x - mean) * rstd * sc.x + bi.x);
+                        y.y = fmaxf(0.f, (v.y - mean) * rstd * sc.y + bi.y);
+                        y.z = fmaxf(0.f, (v.z - mean) * rstd * sc.z + bi.z);
+                        y.w = fmaxf(0.f, (v.w - mean) * rstd * sc.w + bi.w);
+                        if (store_z)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                                         ::"r"(paz + sw128(lane, j)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                                     ::"r"(pay + sw128(lane, j)), "f"(y.x), "f"(y.y), "f"(y.z), "f"(y.w) : "memory");
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {                                        // one bulk group per chunk (z + y)
+                        if (store_z) tma_store_2d(&tmC, pz, col0, m0 + quad * 32);
+                        tma_store_2d(&tmY, py, col0, m0 + quad * 32);
+                        tma_store_commit();
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 const int col0 = n0 + c * 32;
@@ -432,6 +512,7 @@ tf32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     tma_store_commit();
                 }
             }
+            }
             // every lane's tcgen05.ld of this accumulator has completed (tmem_ld32 waits): hand it back
             tcgen05_fence_before();
             __syncwarp();
@@ -441,7 +522,7 @@ tf32_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         __syncwarp();
     } else if (ROUND) {
         // ================= operand rounding (warps 6..9): cvt.rna.tf32.f32 in place on every landed stage
-        const int et = threadIdx.x - 192;                                   // 0..127
+        const int et = threadIdx.x - L::THREADS_NOROUND;                    // 0..127
         uint32_t it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -512,18 +593,39 @@ int launch32(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float
 template <int BN, int STAGES, bool A_MN, bool B_MN, int ROUND>
 int launch32p(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tB, float* C, const float* bias, int ldc,
               int M, int N, int K) {
-    using L = Smem32P<BN, STAGES>;
+    using L = Smem32P<BN, STAGES, false>;
     CUtensorMap tC{};
     const int rc = make_map_f32(&tC, C, N, M, ldc, 32, false);
     if (rc) return rc;
-    auto kern = tf32_gemm_persist_kernel<BN, STAGES, A_MN, B_MN, ROUND>;
+    auto kern = tf32_gemm_persist_kernel<BN, STAGES, A_MN, B_MN, ROUND, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return (int)e;
     const int n_tiles = (int)mlb_cdiv(N, BN);
     const long long tiles = (long long)mlb_cdiv(M, BM) * n_tiles;
     const unsigned grid = (unsigned)(tiles < MLB_NUM_SMS ? tiles : MLB_NUM_SMS);
-    e = launch_pdl(kern, dim3(grid), dim3(ROUND ? 320 : 192), L::TOTAL, s, tA, tB, tC, bias, M, N, K, n_tiles,
-                   (int)tiles);
+    e = launch_pdl(kern, dim3(grid), dim3(L::THREADS_NOROUND + (ROUND ? 128 : 0)), L::TOTAL, s, tA, tB, tC, tC, bias,
+                   (const float*)nullptr, (const float*)nullptr, (float*)nullptr, 0, M, N, K, n_tiles, (int)tiles);
+    return e == cudaSuccess ? MLB_OK : (int)e;
+}
+
+// Dense (B = W stored [K, H], MN-major) + LayerNorm + ReLU, H == BN
+template <int BN, int STAGES, int ROUND>
+int launch32ln(cudaStream_t s, const float* x, const float* w, const float* scale, const float* bias, float* z,
+               float* y, float* stats, long long rows, int K, int ldx) {
+    using L = Smem32P<BN, STAGES, true>;
+    CUtensorMap tA, tB, tZ{}, tY;
+    int rc = make_map_f32(&tA, x, K, rows, ldx, BM, false);
+    if (!rc) rc = make_map_f32(&tB, w, BN, K, BN, 32, true);
+    if (!rc) rc = make_map_f32(&tY, y, BN, rows, BN, 32, false);
+    if (!rc && z) rc = make_map_f32(&tZ, z, BN, rows, BN, 32, false);
+    if (rc) return rc;
+    auto kern = tf32_gemm_persist_kernel<BN, STAGES, false, true, ROUND, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    const long long tiles = mlb_cdiv(rows, BM);
+    const unsigned grid = (unsigned)(tiles < MLB_NUM_SMS ? tiles : MLB_NUM_SMS);
+    e = launch_pdl(kern, dim3(grid), dim3(L::THREADS_NOROUND + (ROUND ? 128 : 0)), L::TOTAL, s, tA, tB, z ? tZ : tY, tY,
+                   (const float*)nullptr, scale, bias, stats, z ? 1 : 0, (int)rows, BN, K, 1, (int)tiles);
     return e == cudaSuccess ? MLB_OK : (int)e;
 }
 
@@ -627,4 +729,31 @@ MLB_API int mlb_gemm_tf32_tc(void* stream, const float* A, const float* B, float
     if (round >= 2) DISPATCH(2);
     DISPATCH(0);
 #undef DISPATCH
+}
+
+// One MLP layer of compute_dtype=float32 in one launch: z = x W (tcgen05 kind::tf32), y = relu(LayerNorm(z)).
+//   x [rows, K] (row stride ldx), w [K, H] row-major (the flax Dense kernel), scale / bias [H],
+//   z [rows, H] or NULL (rollout inference does not need the pre-activation), y [rows, H],
+//   stats [rows][2] = {mean, rstd} or NULL.  H in {64, 128, 256} (one accumulator tile = the whole feature row).
+MLB_API int mlb_dense_ln_relu_fwd_tf32(void* stream, const float* x, const float* w, const float* scale,
+                                       const float* bias, float* z, float* y, float* stats, long long rows, int K,
+                                       int H, int ldx) {
+    MLB_REQUIRE(x && w && scale && bias && y && rows >= 0 && K > 0 && ldx >= K && ldx % 4 == 0);
+    MLB_REQUIRE(H == 64 || H == 128 || H == 256);
+    MLB_REQUIRE(rows <= 0x7FFFFFFF);
+    if (rows == 0) return MLB_OK;
+    MLB_REQUIRE(mlb_aligned16(x) && mlb_aligned16(w) && mlb_aligned16(y) && mlb_aligned16(scale) &&
+                mlb_aligned16(bias) && (!z || mlb_aligned16(z)) && (!stats || (reinterpret_cast<uintptr_t>(stats) & 7) == 0));
+    static const int round = tf32_knob("MLB_TF32_ROUND", 1);
+    cudaStream_t s = mlb_stream(stream);
+#define LNGO(R_)                                                                                          \
+    do {                                                                                                  \
+        if (H == 64) return launch32ln<64, 6, R_>(s, x, w, scale, bias, z, y, stats, rows, K, ldx);        \
+        if (H == 128) return launch32ln<128, 4, R_>(s, x, w, scale, bias, z, y, stats, rows, K, ldx);      \
+        return launch32ln<256, 3, R_>(s, x, w, scale, bias, z, y, stats, rows, K, ldx);                    \
+    } while (0)
+    if (round == 1) LNGO(1);
+    if (round >= 2) LNGO(2);
+    LNGO(0);
+#undef LNGO
 }

@@ -65,6 +65,20 @@ def gemm(A, B, C, bias, M, N, K, lda, ldb, ldc, ta=0, tb=0, accumulate=0, splitk
          c_int(splitk))
 
 
+def dense_ln_relu_f32(x, d, k, s, b, z, y, stats, rows, H, need_z=True):
+    """One fp32 MLP layer (ml/models.py:107-117): z = x k, y = relu(LayerNorm(z)), stats = {mean, rstd}.  With
+    matmul precision 'tf32' and H in {64, 128, 256}: ONE launch (mlb_dense_ln_relu_fwd_tf32, LayerNorm in the
+    tensor-core GEMM's epilogue; z is written only if need_z); otherwise GEMM + LayerNorm kernels (z is scratch)."""
+    if (_PRECISION['tf32'] and H in (64, 128, 256) and _tma_ok(x, d) and _tma_ok(k, H) and _tma_ok(y, H) and
+            (z is None or _tma_ok(z, H)) and s.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+        call('mlb_dense_ln_relu_fwd_tf32', ptr(x), ptr(k), ptr(s), ptr(b), ptr(z if need_z else None), ptr(y),
+             ptr(stats), c_ll(rows),
+             c_int(d), c_int(H), c_int(d))
+        return
+    gemm(x, k, z, None, rows, H, d, d, H, H)
+    call('mlb_ln_relu_fwd_f32', ptr(z), ptr(s), ptr(b), ptr(y), ptr(stats), c_ll(rows), c_int(H))
+
+
 def gemm_tc(A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn=0, b_mn=0, epi=0, splitk=1):
     """mlb_gemm_bf16_tc: C[M,N] (+)= A * B^T on tcgen05 (bf16 operands, fp32 accumulate)."""
     call('mlb_gemm_bf16_tc', ptr(A), ptr(B), ptr(C), ptr(bias), c_int(M), c_int(N), c_int(K), c_int(lda),
@@ -497,9 +511,8 @@ class PolicyProgram:
             x, d = obs, self.obs_dim
             for i in range(self.L):
                 k, s, b = self.layer_views(self.params, t * self.L + i)
-                gemm(x, k, w['z'], None, rows, self.H, d, d, self.H, self.H)
                 y = w['y'][2 * t + (i & 1)]
-                call('mlb_ln_relu_fwd_f32', ptr(w['z']), ptr(s), ptr(b), ptr(y), ptr(None), c_ll(rows), c_int(self.H))
+                dense_ln_relu_f32(x, d, k, s, b, w['z'], y, None, rows, self.H, need_z=False)
                 x, d = y, self.H
             feats.append(x)
         xs = feats if self.lstm is None else self.lstm.step_infer(feats[0], rows, rnn_states, w)
@@ -600,9 +613,7 @@ class PolicyProgram:
             x, d = obs, self.obs_dim
             for i in range(t * self.L, (t + 1) * self.L):
                 k, s, b = self.layer_views(self.params, i)
-                gemm(x, k, w['z'][i], None, rows, self.H, d, d, self.H, self.H)
-                call('mlb_ln_relu_fwd_f32', ptr(w['z'][i]), ptr(s), ptr(b), ptr(w['y'][i]), ptr(w['stats'][i]),
-                     c_ll(rows), c_int(self.H))
+                dense_ln_relu_f32(x, d, k, s, b, w['z'][i], w['y'][i], w['stats'][i], rows, self.H)
                 x, d = w['y'][i], self.H
             feats.append(x)
         xs = feats if self.lstm is None else self.lstm.sequence_fwd(feats[0], seq)

@@ -215,3 +215,41 @@ def test_tf32_update_iter_tracks_exact_fp32(mlb):
     cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
     assert cos > 0.98, cos
     np.testing.assert_allclose(out['tf32'][1], out['highest'][1], rtol=0.05, atol=5e-3)
+
+
+@pytest.mark.parametrize('rows,K,H,with_z', [(1000, 64, 256, True), (40000, 256, 256, True), (8192, 256, 256, False),
+                                              (19277, 128, 128, True), (777, 64, 64, True)])
+def test_dense_ln_relu_fwd_tf32_vs_unfused(mlb, rows, K, H, with_z):
+    """mlb_dense_ln_relu_fwd_tf32 (LayerNorm + ReLU in the TF32 GEMM's epilogue) against the exact fp64 layer and
+    against its own pieces: z equals mlb_gemm_tf32_tc bit for bit (same MMA schedule), y / stats equal
+    mlb_ln_relu_fwd_f32 applied to that z up to the summation order of the row statistics."""
+    from madrona_learn_b200._lib import c_int, c_ll, call, ptr
+    rng = np.random.default_rng(rows + H)
+    x = rng.standard_normal((rows, K)).astype(np.float32)
+    w = (rng.standard_normal((K, H)) / np.sqrt(K)).astype(np.float32)
+    sc = (1 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+    bi = (0.1 * rng.standard_normal(H)).astype(np.float32)
+    d = lambda a: torch.from_numpy(a).to(DEV)
+    xd, wd, scd, bid = d(x), d(w), d(sc), d(bi)
+    z = torch.full((rows, H), float('nan'), device=DEV) if with_z else None
+    y = torch.full((rows, H), float('nan'), device=DEV)
+    st = torch.full((rows, 2), float('nan'), device=DEV)
+    call('mlb_dense_ln_relu_fwd_tf32', ptr(xd), ptr(wd), ptr(scd), ptr(bid), ptr(z), ptr(y), ptr(st), c_ll(rows),
+         c_int(K), c_int(H), c_int(K))
+    z2 = torch.empty(rows, H, device=DEV)
+    y2 = torch.empty(rows, H, device=DEV)
+    st2 = torch.empty(rows, 2, device=DEV)
+    call('mlb_gemm_tf32_tc', ptr(xd), ptr(wd), ptr(z2), ptr(None), c_int(rows), c_int(H), c_int(K), c_int(K), c_int(H),
+         c_int(H), c_int(0), c_int(0), c_int(0), c_int(1))
+    call('mlb_ln_relu_fwd_f32', ptr(z2), ptr(scd), ptr(bid), ptr(y2), ptr(st2), c_ll(rows), c_int(H))
+    torch.cuda.synchronize()
+    if with_z:
+        assert torch.equal(z, z2)
+    assert bool(torch.isfinite(y).all()) and bool(torch.isfinite(st).all())
+    np.testing.assert_allclose(y.cpu().numpy(), y2.cpu().numpy(), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(st.cpu().numpy(), st2.cpu().numpy(), rtol=2e-5, atol=2e-6)
+    z64 = x.astype(np.float64) @ w.astype(np.float64)
+    mean = z64.mean(-1, keepdims=True)
+    var = np.maximum(0, (z64 * z64).mean(-1, keepdims=True) - mean * mean)
+    yref = np.maximum(0, (z64 - mean) / np.sqrt(var + 1e-6) * sc + bi)
+    assert _rel(y.cpu().numpy(), yref) < 1e-3

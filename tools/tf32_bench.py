@@ -46,6 +46,23 @@ if __name__ == '__main__':
         time_gemm('head fwd', fn, R, 28, 256, 0, 0, 0)
         time_gemm('head dX', fn, R, 256, 28, 0, 1, 0)
         time_gemm('head dW', fn, 256, 28, R, 1, 0, 1)
+    # fused Dense + LayerNorm + ReLU layer vs GEMM + LayerNorm kernel
+    x = torch.randn(R, 256, device=DEV); w = torch.randn(256, 256, device=DEV) / 16
+    sc = torch.ones(256, device=DEV); bi = torch.zeros(256, device=DEV)
+    z = torch.empty(R, 256, device=DEV); y = torch.empty(R, 256, device=DEV); st = torch.empty(R, 2, device=DEV)
+    flush = torch.zeros(64 << 20, device=DEV)
+    from madrona_learn_b200._lib import c_ll
+    for name, fn in (('fused layer', lambda: call('mlb_dense_ln_relu_fwd_tf32', ptr(x), ptr(w), ptr(sc), ptr(bi), ptr(z), ptr(y), ptr(st), c_ll(R), c_int(256), c_int(256), c_int(256))),
+                     ('gemm + ln', lambda: (call('mlb_gemm_tf32_tc', ptr(x), ptr(w), ptr(z), ptr(None), c_int(R), c_int(256), c_int(256), c_int(256), c_int(256), c_int(256), c_int(0), c_int(0), c_int(0), c_int(1)),
+                                            call('mlb_ln_relu_fwd_f32', ptr(z), ptr(sc), ptr(bi), ptr(y), ptr(st), c_ll(R), c_int(256))))):
+        ev = []
+        for i in range(13):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); ev.append((e0, e1))
+        torch.cuda.synchronize()
+        us = sorted(a.elapsed_time(b) * 1e3 for a, b in ev[3:])[5]
+        print(json.dumps(dict(layer=name, rows=R, H=256, K=256, us=round(us, 2))), flush=True)
     if 'gemm-only' in sys.argv:
         sys.exit(0)
     import bench_configs as b
