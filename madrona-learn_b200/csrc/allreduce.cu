@@ -233,6 +233,8 @@ MLB_API int mlb_allreduce_nvls_f32(void* stream, const mlb_peer_table* peers_hos
     }
     long long g = mlb_cdiv(n >> 2, AR_BLOCK);
     if (g > AR_MAX_GRID) g = AR_MAX_GRID;
+    static const int cap_nvls = mlb_coresident_cap(allreduce_nvls_kernel, AR_BLOCK, 0);  // grid-wide tickets inside
+    if (g > cap_nvls) g = cap_nvls;
     if (g < 1) g = 1;
     allreduce_nvls_kernel<<<(unsigned)g, AR_BLOCK, 0, mlb_stream(stream)>>>(
         T, mc_grads, mc_out, out_local, n, sumsq_out, state, static_cast<double*>(ws));
@@ -258,6 +260,8 @@ MLB_API int mlb_allreduce_sumsq_f32(void* stream, const mlb_peer_table* peers_ho
     }
     long long g = mlb_cdiv(n >> 2, AR_BLOCK);
     if (g > AR_MAX_GRID) g = AR_MAX_GRID;
+    static const int cap_p2p = mlb_coresident_cap(allreduce_sumsq_kernel, AR_BLOCK, 0);
+    if (g > cap_p2p) g = cap_p2p;
     if (g < 1) g = 1;
     allreduce_sumsq_kernel<<<(unsigned)g, AR_BLOCK, 0, mlb_stream(stream)>>>(
         T, out, n, sumsq_out, state, static_cast<double*>(ws));

@@ -50,6 +50,20 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 
 
 
+// Kernels that meet at device-wide spin barriers need every CTA of the grid resident at once.  They are launched
+// non-cooperatively (inside PDL chains / CUDA graphs), so the grid is capped by what the CURRENT device can hold:
+// its queried SM count (not the compile-time MLB_NUM_SMS) x the occupancy of that kernel.  Cached per process
+// (one process per GPU).  A concurrent kernel on another stream can still delay a CTA; the barriers' bounded
+// spins then trap instead of hanging.
+template <typename Kern>
+inline int mlb_coresident_cap(Kern kern, int block, size_t smem) {
+    int dev = 0, sms = 0, per = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, block, smem) != cudaSuccess || per < 1) return 1;
+    return sms * per;
+}
+
 static inline unsigned mlb_cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 constexpr int MLB_NUM_SMS = 148;   // B200: 2 dies x 74 SMs

@@ -368,6 +368,8 @@ MLB_API int mlb_optimizer_step_fused(void* stream, float* params, const float* g
     if (!ws || ws_bytes < mlb_optimizer_fused_workspace()) return MLB_EWS;
     long long gsz = (n + 1023) / 1024;
     if (gsz > MLB_NUM_SMS) gsz = MLB_NUM_SMS;
+    static const int cap = mlb_coresident_cap(optimizer_fused_kernel, FO_BLOCK, 0);      // two grid barriers inside
+    if (gsz > cap) gsz = cap;
     if (gsz < 1) gsz = 1;
     double* gpart = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 15) & ~uintptr_t(15));
     double* segpart = gpart + MLB_NUM_SMS;

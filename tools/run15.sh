@@ -1,13 +1,6 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --tb=short 2>&1 > gpurun_out/r2_pytest_full.log
 grep -E "^E  |^FAILED|^ERROR|passed|failed" gpurun_out/r2_pytest_full.log | cut -c1-300 | head -30
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -2
-timeout 900 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err
-tail -2 gpurun_out/r2_bench_final.err | cut -c1-300
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2_bench_final.json').read().strip().splitlines()[-1])
-for k in ('value','ms_per_step','e2e','gpu_launches','clocks','f32','cfg3','cfg4'):
-    print(k, json.dumps(d.get(k))[:300])
-print('roofline', json.dumps(d['roofline'])[:500])
-PY
+timeout 600 python bench.py --no-extras --no-cpu-baseline --steps 30 --warmup 10 2>/dev/null | python -c "
+import sys, json
+b=json.loads(sys.stdin.readline()); print(b['ms_per_step'], b['value'], b['e2e']['value'])"
