@@ -253,3 +253,41 @@ def test_dense_ln_relu_fwd_tf32_vs_unfused(mlb, rows, K, H, with_z):
     var = np.maximum(0, (z64 * z64).mean(-1, keepdims=True) - mean * mean)
     yref = np.maximum(0, (z64 - mean) / np.sqrt(var + 1e-6) * sc + bi)
     assert _rel(y.cpu().numpy(), yref) < 1e-3
+
+
+def test_tf32_recurrent_update_tracks_exact_fp32(mlb):
+    """compute_dtype=float32 with an LSTM encoder under the default 'tf32' precision: the recurrent / input / BPTT
+    products (accumulating GEMMs with N = 4 RH, MN-major reductions over T' x M rows) run on mlb_gemm_tf32_tc too.
+    Same seeds as an exact-fp32 run: the parameter update points the same way and the loss agrees."""
+    m = mlb
+    N, T, D, C = 256, 16, 32, 2
+    out = {}
+    prev = m.matmul_precision()
+    try:
+        for prec in ('highest', 'tf32'):
+            m.set_matmul_precision(prec)
+            env = m.SyntheticVectorEnv(N, D, len(BUCKETS), seed=2, p_done=1 / 16, device=DEV)
+            pol = m.Policy(actor_critic=m.ActorCritic(
+                backbone=m.BackboneShared(prefix=None, encoder=m.RecurrentBackboneEncoder(
+                    net=m.models.MLP(64, 1), rnn=m.rnn.LSTM(64, 2))),
+                actor=m.models.DenseLayerDiscreteActor(m.DiscreteActionsConfig(BUCKETS)),
+                critic=m.models.DenseLayerCritic()))
+            cfg = m.TrainConfig(
+                num_worlds=N, num_agents_per_world=1, num_updates=4, actions={'act': m.DiscreteActionsConfig(BUCKETS)},
+                steps_per_update=T, lr=3e-4,
+                algo=m.PPOConfig(num_epochs=2, minibatch_size=N * C // 2, clip_coef=0.2, value_loss_coef=0.5,
+                                 entropy_coef={'act': 0.01}, max_grad_norm=0.5),
+                num_bptt_chunks=C, gamma=0.99, seed=3, metrics_buffer_size=4, gae_lambda=0.95,
+                dreamer_v3_critic=False, normalize_values=True)
+            mgr = m.init_training(DEV, cfg, env.sim_fns(), pol, None, verbose=False)
+            p0 = mgr.state.policy_states.program.params.clone()
+            mgr.update_iter()
+            torch.cuda.synchronize()
+            out[prec] = (mgr.state.policy_states.program.params.double().cpu().numpy() - p0.double().cpu().numpy(),
+                         mgr.metrics.latest()['Loss'].mean)
+    finally:
+        m.set_matmul_precision(prev)
+    a, b = out['highest'][0], out['tf32'][0]
+    cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+    assert np.isfinite(out['tf32'][1]) and cos > 0.98, (cos, out)
+    np.testing.assert_allclose(out['tf32'][1], out['highest'][1], rtol=0.05, atol=5e-3)
