@@ -684,7 +684,8 @@ MLB_API int mlb_gemm_tf32_tc(void* stream, const float* A, const float* B, float
     MLB_REQUIRE(!bias || mlb_aligned16(bias));
     const bool a_mn = transA != 0, b_mn = transB == 0;
     int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
-    if (accumulate && bn > 128) bn = 128;          // reductions: more output tiles, fewer K-slices
+    static const int dw_bn = tf32_knob("MLB_TF32_DW_BN", 128);
+    if (accumulate && bn > dw_bn) bn = dw_bn;      // reductions: more output tiles, fewer K-slices
     if (accumulate) {
         const long long tiles = (long long)mlb_cdiv(M, BM) * mlb_cdiv(N, bn);
         long long want = MLB_NUM_SMS / (tiles > 0 ? tiles : 1);

@@ -79,3 +79,40 @@ def test_tensorboard_tag_set(mlb):
     d = {(t, s): v for t, v, s in out}
     assert d[('p0/Loss Mean', 7)] == 1.5 and d[('p0/Loss σ', 7)] == 2.0 and d[('p0/Loss Max', 8)] == 5.0
     assert d[('p0/Rewards Min', 8)] == 0.5
+
+
+def test_ffi_shim_type_checks(tmp_path):
+    """csrc/ffi_xla.cc (the jax.ffi handlers a reference maintainer builds against jaxlib) cannot be built here:
+    jaxlib's xla/ffi/api/ffi.h is not in this image.  g++ type-checks it against tests/ffi_mock (a stand-in for
+    the slice of that API the shim uses): every call into include/mlb200.h is checked against the C prototypes and
+    every binding's .Ctx/.Arg/.Ret/.Attr list against its implementation's parameters.  A deliberately wrong
+    binding must FAIL the same check (the mock has teeth), and every handler wraps a declared entry point."""
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which('g++') is None:
+        pytest.skip('g++ not available')
+    cuda_inc = '/usr/local/cuda/include'
+    if not os.path.exists(os.path.join(cuda_inc, 'cuda_runtime.h')):
+        pytest.skip('CUDA headers not available')
+    shim = os.path.join(root, 'madrona-learn_b200', 'csrc', 'ffi_xla.cc')
+    base = ['g++', '-std=c++17', '-fsyntax-only', '-Wall', '-Werror', '-I', os.path.join(root, 'tests', 'ffi_mock'),
+            '-I', cuda_inc]
+    r = subprocess.run(base + [shim], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    src = open(shim).read()
+    handlers = re.findall(r'XLA_FFI_DEFINE_HANDLER_SYMBOL\(\s*(\w+)_ffi,', src)
+    assert len(handlers) >= 14
+    header = open(os.path.join(root, 'include', 'mlb200.h')).read()
+    for h in handlers:
+        assert re.search(r'\b%s\(' % h, header), f'{h}_ffi wraps an entry point that include/mlb200.h does not declare'
+    # negative control: drop one .Arg from a binding -> the static_assert in the mock's To() must fire
+    bad = src.replace('.Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>(),',
+                      '.Arg<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>(),', 1)
+    assert bad != src
+    bad = bad.replace('#include "../../include/mlb200.h"', '#include "%s"' % os.path.join(root, 'include', 'mlb200.h'))
+    f = tmp_path / 'bad_ffi.cc'
+    f.write_text(bad)
+    r = subprocess.run(base + [str(f)], capture_output=True, text=True)
+    assert r.returncode != 0 and 'disagree on the parameter list' in r.stderr
