@@ -5,9 +5,12 @@ arena (with gradient / Adam-moment arenas of the same layout) so the optimiser, 
 all-reduce and the norm re-projection are single launches; activations live in preallocated
 workspaces so the whole update can be captured in a CUDA graph.
 
-Supported family: BackboneShared(prefix=None|identity,
-encoder=BackboneEncoder(net=MLP)) + DenseLayerDiscreteActor + DenseLayerCritic, fp32.
-Everything else raises NotImplementedError loudly (no fallback).
+Supported family (SURVEY 8a rows a15-a19 and the 8f rows lowered in round 2): BackboneShared or BackboneSeparate
+(prefix=None|identity; encoders BackboneEncoder(net=MLP) or, shared only, RecurrentBackboneEncoder(net=MLP,
+rnn=LSTM)) + DenseLayerDiscreteActor | DenseLayerContinuousActor + DenseLayerCritic | DreamerV3Critic |
+HLGaussCritic; compute_dtype float32 (Dense products on tcgen05 kind::tf32 by default, exact FFMA with
+set_matmul_precision('highest')) or bfloat16 (fused tcgen05 layer kernels).  Everything else raises
+NotImplementedError loudly (no fallback).
 """
 import ctypes
 import math
