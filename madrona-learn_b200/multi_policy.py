@@ -104,7 +104,9 @@ class MultiPolicyTrainingManager:
 
     def _update(self):
         subs, B = self.subs, self.B
+        from .ppo import hoist_permutations
         for m in subs:
+            hoist_permutations(m.state.train_states, m.ppo_ws)       # every policy's own key / side stream
             m.rollout, m.state.user_state = m.hooks.start_rollouts(m.rollout, m.state.user_state)
         C = subs[0].rollout_mgr._num_bptt_chunks
         Tp = subs[0].rollout_mgr._num_bptt_steps

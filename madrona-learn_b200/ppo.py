@@ -114,6 +114,7 @@ class _PPOWorkspace:
         else:
             assert J >= M
         self.E, self.M, self.J, self.nmb, self.rows = E, M, J, J // M, Tp * M
+        self.B = B                                       # trajectories per BPTT chunk on this rank
         e = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
         # index-exact data-parallel mode (parallel.py): ONE permutation of the global trajectory ids,
         # identical on every rank; this rank trains on its M-wide slice of every (world*M)-wide minibatch
@@ -194,6 +195,31 @@ def _layer_states(lstm, mb):
                 h0=[mb['rnn_start_h'][:, l * RH:(l + 1) * RH] for l in range(lstm.RL)])
 
 
+def _compute_minibatch_indices(train_state, ws, dist_ctx, partitionable=False):
+    """ml/ppo.py:445-458: E x (split the update key, permutation(arange(J))); data-parallel index-exact mode adds
+    the owner-affine split of every global minibatch.  Depends on the update key only."""
+    K.ppo_permutations(train_state.update_prng_key, ws.E, ws.Jp, partitionable, ws.perm, ws.perm_ws)
+    if ws.idx_local is not None:
+        call('mlb_dp_assign_minibatches', ptr(ws.perm), c_ll(ws.Jp), c_int(ws.E), c_int(ws.nmb),
+             c_int(dist_ctx.world_size), c_int(dist_ctx.rank), c_ll(ws.B), c_ll(ws.M), ptr(ws.idx_local))
+
+
+def hoist_permutations(train_state, ws, dist_ctx=None, partitionable=False):
+    """The minibatch permutations of an update depend only on the update PRNG key, not on the rollout: enqueue
+    them on the workspace's side stream BEFORE rollout collection, where the sort kernels (4 x 27 us at cfg2) run
+    underneath the rollout phase -- the one-CTA-per-128-agents rollout kernel leaves more than half of the SMs
+    idle.  _ppo joins the side stream where the reference computes the indices.  Default branch only (the
+    filter_advantages / importance-sampling permutations shuffle data-dependent index sets).
+    MLB_HOIST_PERM=0 disables."""
+    if ws is None or ws.mode != 'default' or os.environ.get('MLB_HOIST_PERM', '1') == '0':
+        return
+    main = torch.cuda.current_stream()
+    ws.side.wait_stream(main)
+    with torch.cuda.stream(ws.side):
+        _compute_minibatch_indices(train_state, ws, dist_ctx, partitionable)
+    ws.perm_pending = True
+
+
 def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics, dist_ctx=None,
          ws=None, partitionable=False):
     """ml/ppo.py:366-488, default branch (valid_inds = arange(J), weights = 1)."""
@@ -215,10 +241,11 @@ def _ppo(cfg, policy_state, train_state, rollout_data, user_metrics_cb, metrics,
     hp = train_state.hyper_params
 
     with profile('Compute Minibatch Indices'):
-        K.ppo_permutations(train_state.update_prng_key, E, ws.Jp, partitionable, ws.perm, ws.perm_ws)
-        if ws.idx_local is not None:
-            call('mlb_dp_assign_minibatches', ptr(ws.perm), c_ll(ws.Jp), c_int(E), c_int(nmb),
-                 c_int(dist_ctx.world_size), c_int(dist_ctx.rank), c_ll(B), c_ll(M), ptr(ws.idx_local))
+        if getattr(ws, 'perm_pending', False):       # hoisted underneath the rollout phase (hoist_permutations)
+            torch.cuda.current_stream().wait_stream(ws.side)
+            ws.perm_pending = False
+        else:
+            _compute_minibatch_indices(train_state, ws, dist_ctx, partitionable)
 
     # per-minibatch statistics for ALL minibatches of the update (App. C.1)
     score_key = 'advantages' if cfg.compute_advantages else 'returns'

@@ -23,7 +23,7 @@ from . import kernels as K
 from .cfg import TrainConfig
 from .metrics import TrainingMetrics
 from .policy import Policy
-from .ppo import _PPOWorkspace
+from .ppo import _PPOWorkspace, hoist_permutations
 from .profile import profile
 from .rollouts import RolloutConfig, RolloutManager, RolloutState
 from .train_state import TrainStateManager
@@ -195,6 +195,8 @@ def _update_impl(algo, cfg, user_hooks, rollout_state, rollout_mgr, train_state_
                  update_idx, dist_ctx, ppo_ws):
     """ml/train.py:155-225 (P = 1: the vmap over policies is the identity)."""
     with profile('Update Iter'):
+        # the minibatch permutations depend on the update key only: side stream, underneath the rollout phase
+        hoist_permutations(train_state_mgr.train_states, ppo_ws, dist_ctx)
         with profile('Collect Rollouts'):
             collected = rollout_mgr.collect(
                 train_state_mgr, rollout_state, metrics, user_hooks.start_rollouts,
