@@ -418,6 +418,25 @@ int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* desc_host, const 
                           int partitionable, int deterministic, int32_t* actions,
                           float* log_probs, float* values, const float* critic_bins_host,
                           int num_critic_bins, float* head_out);
+/* The same launch also doing the PREVIOUS step's "Post Step Rollout Store" (ml/rollouts.py:946-978, */
+/* what mlb_post_step_store_f32 does) on the rows each CTA owns: the simulator's rewards / dones of    */
+/* step t-1 reach the store inside the policy launch of step t (the bootstrap launch takes the last    */
+/* step's), one launch fewer per rollout step.  post_step_host may be NULL (= mlb_policy_rollout_tc).   */
+typedef struct mlb_post_step {
+    const float* rewards;
+    const uint8_t* dones;
+    float* reward_slab;
+    uint8_t* done_slab;
+    float* env_returns;
+    float* trace;              /* may be NULL */
+    float gamma;
+} mlb_post_step;
+int mlb_policy_rollout_ps_tc(void* stream, const mlb_mlp_tc_desc* desc_host, const float* obs,
+                             float* obs_store, long long rows, const uint32_t* key_in,
+                             uint32_t* key_out, const int32_t* buckets_host, int num_components,
+                             int partitionable, int deterministic, int32_t* actions,
+                             float* log_probs, float* values, const float* critic_bins_host,
+                             int num_critic_bins, float* head_out, const mlb_post_step* post_step_host);
 
 /* ------------------------------------------------------------------------------------ */
 /* K8: fused PPO loss + gradient w.r.t. the head outputs (ml/ppo.py:129-262 + autodiff).    */

@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmlb200.so')
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
                                             ctypes.c_float, ctypes.c_size_t)
@@ -110,6 +110,7 @@ SIGNATURES = {
     'mlb_allreduce_nvls_f32': (c_int, [P, P, P, P, P, c_ll, P, P, P, c_size_t]),
     'mlb_allreduce_sumsq_f32': (c_int, [P, P, P, c_ll, P, P, P, c_size_t]),
     'mlb_policy_rollout_tc': (c_int, [P, P, P, P, c_ll, P, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P]),
+    'mlb_policy_rollout_ps_tc': (c_int, [P, P, P, P, c_ll, P, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P, P]),
     'mlb_ppo_loss_workspace': (c_size_t, [c_ll]),
     'mlb_ppo_loss_f32': (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, c_int, c_ll, c_ll,
                                  c_float, c_float, c_int, P, P, P, P, c_size_t, P, c_int]),
@@ -159,6 +160,12 @@ class MlpTcDesc(ctypes.Structure):
     _fields_ = [('num_layers', ctypes.c_int32), ('obs_dim', ctypes.c_int32), ('hidden', ctypes.c_int32),
                 ('head_width', ctypes.c_int32), ('w_t', c_void_p * 4), ('scale', c_void_p * 4),
                 ('bias', c_void_p * 4), ('wh_t', c_void_p), ('head_bias', c_void_p)]
+
+
+class PostStep(ctypes.Structure):
+    """mlb_post_step."""
+    _fields_ = [('rewards', c_void_p), ('dones', c_void_p), ('reward_slab', c_void_p), ('done_slab', c_void_p),
+                ('env_returns', c_void_p), ('trace', c_void_p), ('gamma', c_float)]
 
 
 class PPOStats(ctypes.Structure):

@@ -41,6 +41,14 @@ struct PRArgs {
     const float* bias[MAXL];
     const float* head_bias;
     float bins[MLB_MAX_CRITIC_BINS];
+    // optional: the PREVIOUS step's "Post Step Rollout Store" (ml/rollouts.py:946-978) done by this launch
+    const float* ps_r;
+    const uint8_t* ps_d;
+    float* ps_rs;
+    uint8_t* ps_ds;
+    float* ps_er;
+    float* ps_trace;
+    float ps_gamma;
 };
 
 __device__ __forceinline__ float uniform_from_bits(uint32_t bits) {
@@ -118,6 +126,20 @@ policy_rollout_kernel(const __grid_constant__ PRMaps maps, const __grid_constant
     tcgen05_fence_after();
     pdl_wait();                                  // observations / stores below belong to this step
     const uint32_t tmem_base = *tmem_slot;
+    if (a.ps_r != nullptr && threadIdx.x >= PR_THREADS - BM) {
+        // the simulator's rewards / dones of the previous step -> rollout store, discounted env-return trace
+        // (same arithmetic as post_step_kernel); the last four epilogue warps, idle until the first accumulator
+        const long long i = m0 + (threadIdx.x - (PR_THREADS - BM));
+        if (i < rows) {
+            const float ri = a.ps_r[i];
+            const uint8_t di = a.ps_d[i];
+            a.ps_rs[i] = ri;
+            a.ps_ds[i] = di;
+            const float v = __fadd_rn(ri, __fmul_rn(a.ps_gamma, a.ps_er[i]));
+            if (a.ps_trace) a.ps_trace[i] = v;
+            a.ps_er[i] = di ? 0.f : v;
+        }
+    }
 
     if (warp == 0) {
         // ================= weight producer: all layers + heads through the ring =================
@@ -356,7 +378,19 @@ MLB_API int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* d, const 
                                   int partitionable, int deterministic, int32_t* actions,
                                   float* log_probs, float* values, const float* critic_bins_host,
                                   int num_critic_bins, float* head_out) {
+    return mlb_policy_rollout_ps_tc(stream, d, obs, obs_store, rows, key_in, key_out, buckets_host, num_components,
+                                    partitionable, deterministic, actions, log_probs, values, critic_bins_host,
+                                    num_critic_bins, head_out, nullptr);
+}
+
+MLB_API int mlb_policy_rollout_ps_tc(void* stream, const mlb_mlp_tc_desc* d, const float* obs,
+                                     float* obs_store, long long rows, const uint32_t* key_in,
+                                     uint32_t* key_out, const int32_t* buckets_host, int num_components,
+                                     int partitionable, int deterministic, int32_t* actions,
+                                     float* log_probs, float* values, const float* critic_bins_host,
+                                     int num_critic_bins, float* head_out, const mlb_post_step* ps) {
     MLB_REQUIRE(d && obs && actions && rows > 0 && buckets_host);
+    MLB_REQUIRE(!ps || (ps->rewards && ps->dones && ps->reward_slab && ps->done_slab && ps->env_returns));
     MLB_REQUIRE(deterministic || (key_in && key_out));
     MLB_REQUIRE(d->num_layers >= 1 && d->num_layers <= MAXL && d->hidden >= 64 && d->hidden <= 256 &&
                 d->hidden % 64 == 0 && d->obs_dim % 8 == 0 && d->obs_dim >= 8 && d->obs_dim <= 256 &&
@@ -372,6 +406,13 @@ MLB_API int mlb_policy_rollout_tc(void* stream, const mlb_mlp_tc_desc* d, const 
     if (a.V > MLB_MAX_CRITIC_BINS || off + a.V > a.NH) return MLB_EINVAL;
     for (int k = 0; k < a.V && a.V > 1; ++k) a.bins[k] = critic_bins_host[k];
     a.vcol = off;
+    a.ps_r = ps ? ps->rewards : nullptr;
+    a.ps_d = ps ? ps->dones : nullptr;
+    a.ps_rs = ps ? ps->reward_slab : nullptr;
+    a.ps_ds = ps ? ps->done_slab : nullptr;
+    a.ps_er = ps ? ps->env_returns : nullptr;
+    a.ps_trace = ps ? ps->trace : nullptr;
+    a.ps_gamma = ps ? ps->gamma : 0.f;
     int rc;
     for (int l = 0; l < a.L; ++l) {
         const int dl = l == 0 ? a.D : a.H;

@@ -575,8 +575,10 @@ class PolicyProgram:
         return smem <= 227 * 1024
 
     def rollout_step_fused(self, obs, obs_store, rows, key_in, key_out, actions, log_probs, values,
-                           partitionable=False, deterministic=False, head_out=None):
-        """One launch: key chain + obs store copy + MLP + heads + sampling (mlb_policy_rollout_tc)."""
+                           partitionable=False, deterministic=False, head_out=None, post_step=None):
+        """One launch: key chain + obs store copy + MLP + heads + sampling (mlb_policy_rollout_tc).
+        post_step: (rewards, dones, reward_slab, done_slab, env_returns, trace, gamma) of the PREVIOUS simulator
+        step -- its rollout-store write rides in this launch (mlb_policy_rollout_ps_tc)."""
         if getattr(self, '_tc_desc', None) is None or self._tc_desc_base != self.params.data_ptr():
             d = _lib.MlpTcDesc()
             d.num_layers, d.obs_dim, d.hidden, d.head_width = self.L, self.obs_dim, self.H, self.NH
@@ -586,10 +588,15 @@ class PolicyProgram:
             _, B = self.head_views(self.params)
             d.wh_t, d.head_bias = self.wh_t.data_ptr(), B.data_ptr()
             self._tc_desc, self._tc_desc_base = d, self.params.data_ptr()
-        call('mlb_policy_rollout_tc', ctypes.byref(self._tc_desc), ptr(obs), ptr(obs_store), c_ll(rows),
+        ps = None
+        if post_step is not None:
+            r, d, rs, ds, er, tr, gamma = post_step
+            ps = ctypes.byref(_lib.PostStep(r.data_ptr(), d.data_ptr(), rs.data_ptr(), ds.data_ptr(), er.data_ptr(),
+                                            tr.data_ptr() if tr is not None else None, float(gamma)))
+        call('mlb_policy_rollout_ps_tc', ctypes.byref(self._tc_desc), ptr(obs), ptr(obs_store), c_ll(rows),
              ptr(key_in), ptr(key_out), self._buckets_c, c_int(self.A), c_int(int(partitionable)),
              c_int(int(deterministic)), ptr(actions), ptr(log_probs), ptr(values), self._bins_c,
-             c_int(self.V), ptr(head_out))
+             c_int(self.V), ptr(head_out), ps)
 
     def sample(self, head, rows, policy_key, actions, log_probs, values, partitionable=False,
                deterministic=False):

@@ -9,6 +9,7 @@ Differences from the reference that are deliberate B200 design, not omissions:
     (`RolloutData.minibatch`), bit-identical to take+swapaxes on the relayout.
 """
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional
 
@@ -210,6 +211,11 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         self._gae_ws = torch.empty(K.lib().mlb_gae_workspace(T, B) + 16, dtype=torch.uint8, device=dev)
         self._met_ws = torch.empty(K.lib().mlb_moments_workspace(T * B) + 16, dtype=torch.uint8, device=dev)
         self.partitionable = False
+        # fused one-launch rollout step: the post-step store of step t rides in the policy launch of step t + 1
+        # (mlb_policy_rollout_ps_tc); MLB_FUSE_POST_STEP=0 keeps the separate mlb_post_step_store_f32 launch
+        self._fuse_post_step = (prog.fused_rollout and self._lstm is None and
+                                os.environ.get('MLB_FUSE_POST_STEP', '1') != '0')
+        self._pending_post_step = None
         # per-update observation statistics (ml/rollouts.py:670-678); None entries for preprocessors
         # without state (Noop / Caster)
         self._obs_stats = example_policy_states.obs_preprocess.init_obs_stats(
@@ -274,7 +280,7 @@ class RolloutManager:                   # ml/rollouts.py:373-826
                 # PRNG key lands in the alternate buffer, so the two buffers trade places
                 prog.rollout_step_fused(ob, slab, N, rs.prng_key, self._key_alt, actions,
                                         st['log_probs'][c, s, 0], st['values'][c, s, 0],
-                                        self.partitionable)
+                                        self.partitionable, post_step=self._take_pending_post_step())
                 rs.prng_key, self._key_alt = self._key_alt, rs.prng_key
             else:
                 call('mlb_rollout_keys', ptr(rs.prng_key), ptr(self.policy_key),
@@ -299,11 +305,23 @@ class RolloutManager:                   # ml/rollouts.py:373-826
             rewards = rewards.float()
         with profile('Post Step Rollout Store'):
             d_slab, r_slab = st['dones'][c, s, 0], st['rewards'][c, s, 0]
+            if self._fuse_post_step:
+                # rides in the NEXT policy launch of this rollout (the next step's, or the bootstrap's): one
+                # launch fewer per step.  The simulator's reward / done buffers are still intact then -- the
+                # policy launch precedes the next simulator step.
+                assert self._pending_post_step is None
+                self._pending_post_step = (rewards.contiguous(), dones.contiguous(), r_slab, d_slab, rs.env_returns,
+                                           self.env_returns_trace[c * Tp + s], self._cfg.reward_gamma)
+                return
             call('mlb_post_step_store_f32', ptr(rewards), ptr(dones), ptr(r_slab), ptr(d_slab),
                  ptr(rs.env_returns), ptr(self.env_returns_trace[c * Tp + s]), c_ll(N),
                  c_float(self._cfg.reward_gamma))
             if self._lstm is not None:                    # rnn_reset_fn(rnn_states, dones)  (:942)
                 self._lstm.reset(rs.rnn_states, d_slab.view(torch.uint8), N)
+
+    def _take_pending_post_step(self):
+        p, self._pending_post_step = self._pending_post_step, None
+        return p
 
     def end_chunk(self, rs):
         key_home = self._key_home
@@ -342,7 +360,7 @@ class RolloutManager:                   # ml/rollouts.py:373-826
         # critic column of the head -> bootstrap [1, B, 1] (the greedy actions are discarded)
         if prog.fused_rollout:
             prog.rollout_step_fused(ob, None, N, None, None, self._scratch_actions, None, self.bootstrap,
-                                    deterministic=True)
+                                    deterministic=True, post_step=self._take_pending_post_step())
             return
         head = prog.forward_infer(ob, N, states)
         prog.sample(head, N, None, self._scratch_actions, None, self.bootstrap, deterministic=True)
