@@ -13,9 +13,17 @@
 // so none of the three products of a Dense layer (Z = X W, dX = dZ W^T, dW = X^T dZ) transposes anything in
 // memory.  A k-block is 32 fp32 = one 128-byte swizzle row (K-major: one 32(k) x 128(m) SWIZZLE_128B box;
 // MN-major: 32(mn) x 32(k) boxes, 4096 B apart, in the 32-byte-atom 128 B swizzle that is the only MN-major
-// layout tcgen05 accepts for 32-bit operands), UMMA K = 8 (32 bytes).  Kernel anatomy as there: warp 0 TMA producer, warp 1 TMEM
-// allocation + single-thread MMA issue, warps 2-5 epilogue (tcgen05.ld -> swizzled smem panels -> TMA store, or
-// red.global.add.v4 for accumulate / split-K).  All mbarrier waits are bounded.
+// layout tcgen05 accepts for 32-bit operands), UMMA K = 8 (32 bytes).
+//
+// Three kernels share that operand path (all mbarrier waits are bounded):
+//   tf32_gemm_kernel            one output tile per CTA (anatomy of mlp_tc.cu: warp 0 TMA producer, warp 1 TMEM
+//                               allocation + single-thread MMA issue, warps 2-5 epilogue): the split-K / accumulate
+//                               reductions (red.global.add.v4) and problems with fewer tiles than SMs
+//   tf32_gemm_persist_kernel    one CTA per SM walking its tiles with the accumulator double-buffered in TMEM and
+//                               the output through swizzled smem panels + TMA store: Z = X W, dX = dZ W^T at
+//                               minibatch size (mlb_gemm_tf32_tc picks it when tiles > SMs)
+//   the same with LN = true     mlb_dense_ln_relu_fwd_tf32: LayerNorm + ReLU of the layer in the epilogue (eight
+//                               epilogue warps, row statistics out of TMEM)
 #include "tc_common.cuh"
 
 namespace {
