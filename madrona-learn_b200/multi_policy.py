@@ -35,6 +35,19 @@ from ._lib import c_size_t, call, ptr
 from .pbt_reorder import reorder_state_for
 
 
+def sim_to_train_indices(num_train_policies, sim_batch_size, assignments=None):
+    """Rows of the simulator batch that policy p trains on, [P, B] (host ints): the reference's
+    `_compute_sim_to_train_indices` for self-play-only matchmaking (ml/rollouts.py:1071-1104 -- there
+    `arange(S).reshape(P, -1)`, pinned by tests/golden/multi_policy.npz), or, for an explicit assignment vector,
+    the rows assigned to p in simulator order (what pbt_reorder's chunk p holds)."""
+    import numpy as np
+    P, S = int(num_train_policies), int(sim_batch_size)
+    if assignments is None:
+        return np.arange(S, dtype=np.int64).reshape(P, S // P)
+    a = np.asarray(assignments).reshape(-1)
+    return np.stack([np.flatnonzero(a == p) for p in range(P)]).astype(np.int64)
+
+
 def _check_pbt(cfg):
     pbt = cfg.pbt
     if pbt.num_past_policies != 0 or pbt.self_play_portion != 1.0 or pbt.cross_play_portion != 0.0 or \

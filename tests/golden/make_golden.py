@@ -293,6 +293,32 @@ def continuous_golden(rng, jax, jnp, di):
                         stddev_max=np.array([c.stddev_max for c in cfgs], f32))
 
 
+def multi_policy_golden(jax, jnp):
+    """`_compute_sim_to_train_indices` / `_compute_num_train_agents_per_policy` (ml/rollouts.py:1053-1104,
+    AST-extracted, unmodified) under the shim: the simulator-order -> training-order index table the reference's
+    multi-policy rollouts use.  Pins (a) the self-play layout the multi-policy learner lowers (policy p owns the
+    contiguous block p of the simulator batch == `x.reshape(P, -1)`, ml/rollouts.py:579-588) and (b) the general
+    table with cross-play / past-play batches (team 0 of every non-self-play match only), for the record."""
+    import types as _t
+    ns = dict(jax=jax, jnp=jnp)
+    nper = extract_function('rollouts.py', '_compute_num_train_agents_per_policy', ns)
+    idxf = extract_function('rollouts.py', '_compute_sim_to_train_indices', ns)
+    out = {}
+    cases = {  # name: (P, num_teams, team_size, self, cross, past)   batch sizes in agents
+        'selfplay_p2': (2, 1, 1, 48, 0, 0),
+        'selfplay_p3_teams': (3, 2, 2, 72, 0, 0),
+        'mixed_p2': (2, 2, 1, 32, 16, 16),
+    }
+    for name, (P, nt, ts, sp, cp, pp) in cases.items():
+        pbt = _t.SimpleNamespace(num_current_policies=P, num_teams=nt, team_size=ts, self_play_batch_size=sp,
+                                 cross_play_batch_size=cp, past_play_batch_size=pp)
+        cfg = _t.SimpleNamespace(pbt=pbt, sim_batch_size=sp + cp + pp)
+        out[name + '_cfg'] = np.array([P, nt, ts, sp, cp, pp], np.int64)
+        out[name + '_idx'] = np.asarray(idxf(cfg)).astype(np.int64)
+        out[name + '_nper'] = np.int64(nper(cfg))
+    np.savez_compressed(os.path.join(OUT, 'multi_policy.npz'), **out)
+
+
 def main():
     install()
     import jax
@@ -425,6 +451,7 @@ def main():
     select_golden(np.random.default_rng(20261020), jax, jnp, lax, ma)
     hlgauss_golden(np.random.default_rng(20261021), jax, jnp)
     continuous_golden(np.random.default_rng(20261022), jax, jnp, di)
+    multi_policy_golden(jax, jnp)
     print('golden fixtures written to', OUT)
 
 

@@ -300,3 +300,43 @@ def test_continuous_sample_is_standard_normal():
     assert abs(a.mean()) < 0.02 and abs(a.std() - 1) < 0.02
     assert scipy.stats.kstest(a.ravel(), 'norm').statistic < 0.01
     np.testing.assert_allclose(lp, scipy.stats.norm.logpdf(a.astype(np.float64)), atol=1e-5)
+
+
+def test_multi_policy_train_order_matches_reference():
+    """The multi-policy learner's block layout (policy p owns rows [p * B, (p + 1) * B) of the simulator batch) is
+    the reference's `_compute_sim_to_train_indices` for self-play-only matchmaking, executed from the reference
+    source (tests/golden/multi_policy.npz, ml/rollouts.py:1053-1104); the refusals of everything else."""
+    import dataclasses
+    import madrona_learn_b200 as m
+    from madrona_learn_b200.multi_policy import _check_pbt, sim_to_train_indices
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'multi_policy.npz'))
+    for name in ('selfplay_p2', 'selfplay_p3_teams'):
+        P, nt, ts, sp, cp, pp = (int(x) for x in g[name + '_cfg'])
+        idx = g[name + '_idx']
+        np.testing.assert_array_equal(idx, sim_to_train_indices(P, sp))
+        assert int(g[name + '_nper']) == sp // P == idx.shape[1]
+    # with cross-play / past-play batches the table is no longer a reshape (team 0 of those matches only):
+    # that mode is refused, not approximated
+    P, nt, ts, sp, cp, pp = (int(x) for x in g['mixed_p2_cfg'])
+    assert g['mixed_p2_idx'].shape == (P, (sp + cp // nt + pp // nt) // P)
+    assert not np.array_equal(g['mixed_p2_idx'].reshape(-1), np.arange(g['mixed_p2_idx'].size))
+    # an explicit assignment vector: rows of policy p in simulator order
+    a = np.array([1, 0, 1, 1, 0, 0], np.int32)
+    np.testing.assert_array_equal(sim_to_train_indices(2, 6, a), [[1, 4, 5], [0, 2, 3]])
+    B = [4, 3]
+    mk = lambda **kw: m.TrainConfig(
+        num_worlds=8, num_agents_per_world=2, num_updates=1, actions={'act': m.DiscreteActionsConfig(B)},
+        steps_per_update=4, lr=1e-3, algo=m.PPOConfig(num_epochs=1, minibatch_size=4, clip_coef=0.2,
+                                                      value_loss_coef=0.5, entropy_coef=0.01, max_grad_norm=0.5),
+        num_bptt_chunks=1, gamma=0.99, seed=0, metrics_buffer_size=2,
+        pbt=m.PBTConfig(**{**dict(num_teams=2, team_size=1, num_train_policies=2, num_past_policies=0,
+                                  self_play_portion=1.0, cross_play_portion=0.0, past_play_portion=0.0), **kw}))
+    assert _check_pbt(mk()) == 2
+    for bad in (dict(num_past_policies=1), dict(self_play_portion=0.5, cross_play_portion=0.5),
+                dict(self_play_portion=0.5, past_play_portion=0.5)):
+        with pytest.raises(NotImplementedError):
+            _check_pbt(mk(**bad))
+    with pytest.raises(ValueError):
+        _check_pbt(mk(num_train_policies=3))          # 8 worlds do not split into 3 blocks
+    with pytest.raises(ValueError):
+        _check_pbt(mk(team_size=2))                   # teams x team_size != agents per world
