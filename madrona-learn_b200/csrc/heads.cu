@@ -379,14 +379,26 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
     __shared__ WarpPartial wpart[32];
     pdl_launch_dependents();
     pdl_wait();
-    const long long row0 = (long long)blockIdx.x * RB;
     const int ncols = vcol + cb.V;
     const int ts = ncols | 1;                 // odd tile stride
     float* colsum = tile + RB * ts;           // [ncols]
-    stage_in(tile, ts, head, row0, rows, ld, ncols, RB);
     for (int c = threadIdx.x; c < ncols; c += blockDim.x) colsum[c] = 0.f;
-    __syncthreads();
     const int role = threadIdx.x / RB, r = threadIdx.x - role * RB;
+    // A block walks row tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...: the launch is one resident wave
+    // (host: grid = min(tiles, resident blocks)), so the block-level tail -- the fp64 fold of the warp partials,
+    // the bias-gradient flush, the ticket -- is paid once per block instead of once per 64 rows (a third of a
+    // one-tile block's life was spent at those barriers).  Per-thread accumulators carry the loss / metric
+    // partials across the tiles; the bias-gradient column sums accumulate in shared memory.
+    float ap0 = 0.f, ap1 = 0.f, as0 = 0.f, ass0 = 0.f, as1 = 0.f, ass1 = 0.f;
+    float amn0 = INFINITY, amx0 = -INFINITY, amn1 = INFINITY, amx1 = -INFINITY;
+    const long long ntiles = (rows + RB - 1) / RB;
+    bool first = true;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long long row0 = t * RB;
+    if (!first) __syncthreads();              // the previous tile's stage_out / column sums have read `tile`
+    first = false;
+    stage_in(tile, ts, head, row0, rows, ld, ncols, RB);
+    __syncthreads();
     const long long row = row0 + r;
     const bool valid = row < rows;
     float p0 = 0.f, p1 = 0.f, x0 = 0.f, x1 = 0.f;
@@ -559,17 +571,11 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
             l[vcol] = vcoef * w * dvl * vmask * inv_rows;
         }
     }
-    // warp-level partials (fp32 over 32 rows), combined across warps / blocks in fp64 below
-    {
-        WarpPartial P;
-        P.p0 = warp_sum(p0); P.p1 = warp_sum(p1);
-        P.s0 = warp_sum(x0); P.ss0 = warp_sum(x0 * x0);
-        P.s1 = warp_sum(x1); P.ss1 = warp_sum(x1 * x1);
-        P.mn0 = warp_min_f(valid ? x0 : INFINITY); P.mx0 = warp_max_f(valid ? x0 : -INFINITY);
-        P.mn1 = warp_min_f(valid ? x1 : INFINITY); P.mx1 = warp_max_f(valid ? x1 : -INFINITY);
-        if ((threadIdx.x & 31) == 0) wpart[threadIdx.x >> 5] = P;
-    }
-    __syncthreads();
+    ap0 += p0; ap1 += p1;
+    as0 += x0; ass0 = fmaf(x0, x0, ass0);
+    as1 += x1; ass1 = fmaf(x1, x1, ass1);
+    if (valid) { amn0 = fminf(amn0, x0); amx0 = fmaxf(amx0, x0); amn1 = fminf(amn1, x1); amx1 = fmaxf(amx1, x1); }
+    __syncthreads();                          // every role has written its gradients into the tile
     if (flags & MLB_PPO_DHEAD_BF16) stage_out(tile, ts, reinterpret_cast<__nv_bfloat16*>(dhead), row0, rows, ld, ncols, RB);
     else stage_out(tile, ts, reinterpret_cast<float*>(dhead), row0, rows, ld, ncols, RB);
     if (dbias) {                              // bias gradients of the heads: column sums of this tile
@@ -581,6 +587,18 @@ ppo_loss_kernel(const float* __restrict__ head, int ld, const int32_t* __restric
             atomicAdd(&colsum[cc], acc);
         }
     }
+    }   // tile loop
+    // warp-level partials (fp32 over the rows a warp visited), combined across warps / blocks in fp64 below
+    {
+        WarpPartial P;
+        P.p0 = warp_sum(ap0); P.p1 = warp_sum(ap1);
+        P.s0 = warp_sum(as0); P.ss0 = warp_sum(ass0);
+        P.s1 = warp_sum(as1); P.ss1 = warp_sum(ass1);
+        P.mn0 = warp_min_f(amn0); P.mx0 = warp_max_f(amx0);
+        P.mn1 = warp_min_f(amn1); P.mx1 = warp_max_f(amx1);
+        if ((threadIdx.x & 31) == 0) wpart[threadIdx.x >> 5] = P;
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
         // one warp folds the per-warp partials of the block: lane = warp index
         const int nw = blockDim.x >> 5, wpr = RB >> 5;       // warps per role
@@ -746,7 +764,7 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
                                  (flags & MLB_PPO_CONTINUOUS_ACTIONS) != 0);
     if (vcol < 0) return vcol;
     const int RB = (num_components + 1) * 64 <= 1024 ? 64 : LOSS_RB_MIN;
-    const unsigned g = mlb_cdiv(rows, RB);
+    unsigned g = mlb_cdiv(rows, RB);
     if (!ws || ws_bytes < mlb_ppo_loss_workspace(rows)) return MLB_EWS;
     const int ncols = vcol + cb.V;
     const size_t smem = ((size_t)RB * (ncols | 1) + ncols) * sizeof(float);
@@ -754,6 +772,13 @@ MLB_API int mlb_ppo_loss_f32(void* stream, const float* head, int ld, const int3
     auto kern = RB == 64 ? (nthreads <= 448 ? ppo_loss_kernel<64, 448, 3> : ppo_loss_kernel<64>) : ppo_loss_kernel<LOSS_RB_MIN>;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {   // one resident wave: a block walks several row tiles (MLB_LOSS_PERSIST=0: one tile per block)
+        static const bool persist = [] { const char* v = getenv("MLB_LOSS_PERSIST"); return !(v && v[0] == '0'); }();
+        int per = 0;
+        if (persist && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, nthreads, smem) == cudaSuccess &&
+            per > 0 && g > (unsigned)(per * MLB_NUM_SMS))
+            g = (unsigned)(per * MLB_NUM_SMS);
+    }
     cudaStream_t s = mlb_stream(stream);
     LossPartial* part = reinterpret_cast<LossPartial*>(ws);
     cudaError_t le = launch_pdl(kern, dim3(g), dim3((num_components + 1) * RB), smem, s,
