@@ -1,6 +1,7 @@
 """Configuration dataclasses -- field names and defaults follow the reference verbatim
 (ml/cfg.py:9-142) because they ARE the user-facing API of the path.  `compute_dtype` takes a
-torch dtype (torch.float32 -> SIMT fp32 kernels, torch.bfloat16 -> tcgen05 tensor-core path).
+torch dtype (torch.float32 -> fp32 activations with the Dense products on tcgen05 kind::tf32 (exact FFMA under
+set_matmul_precision("highest")), torch.bfloat16 -> fused tcgen05 tensor-core path).
 """
 import dataclasses
 from dataclasses import dataclass, field

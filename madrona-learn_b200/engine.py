@@ -107,7 +107,7 @@ class PolicyProgram:
         if not isinstance(actor_critic, ActorCritic):
             raise TypeError('policy.actor_critic must be an ActorCritic descriptor')
         if compute_dtype not in (F32, torch.bfloat16):
-            raise NotImplementedError('compute_dtype must be float32 (SIMT) or bfloat16 (tcgen05)')
+            raise NotImplementedError('compute_dtype must be float32 (tf32 tensor cores | exact FFMA) or bfloat16 (tcgen05)')
         self.tc = compute_dtype == torch.bfloat16
         bb = actor_critic.backbone
         if not isinstance(bb, (BackboneShared, BackboneSeparate)):
